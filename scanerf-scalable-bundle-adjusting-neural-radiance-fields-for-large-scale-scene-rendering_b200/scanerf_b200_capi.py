@@ -1,0 +1,83 @@
+"""ctypes loader for libscanerf_b200.so -- the C-ABI boundary (include/scanerf_b200.h).
+
+There is NO CPU fallback and no alternative backend: if the shared library is
+missing, or a tensor is not on a CUDA device, the call raises.  PyTorch is used
+only for device memory and streams; every op takes raw device pointers, sizes
+and the current CUDA stream.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libscanerf_b200.so")
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_float = ctypes.c_float
+
+
+def lib():
+    """Load (once) and return the CDLL.  Raises loudly when the build is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"scanerf_b200: native library not found at {LIB_PATH}. "
+                "Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C <package>/csrc`). There is no CPU / PyTorch fallback.")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.snrf_last_error.restype = ctypes.c_char_p
+    return _lib
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(rc, name):
+    if rc != 0:
+        msg = lib().snrf_last_error()
+        raise RuntimeError(f"scanerf_b200::{name} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def _require_cuda(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (scanerf_b200 has no CPU fallback)")
+
+
+def inp(t, dtype, name):
+    """Input tensor -> contiguous tensor of `dtype` on the GPU (the reference calls
+    .contiguous() on every input too).  Returns the tensor; keep it alive during the call."""
+    _require_cuda(t, name)
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must have dtype {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+class Out:
+    """Output tensor written in place.  A non-contiguous output is staged through a
+    contiguous copy and copied back (the reference silently wrote to a temporary)."""
+
+    def __init__(self, t, dtype, name):
+        _require_cuda(t, name)
+        if t.dtype != dtype:
+            raise RuntimeError(f"{name} must have dtype {dtype}, got {t.dtype}")
+        self.orig = t
+        self.t = t if t.is_contiguous() else t.contiguous()
+
+    @property
+    def ptr(self):
+        return c_void_p(self.t.data_ptr())
+
+    def done(self):
+        if self.t is not self.orig:
+            self.orig.copy_(self.t)
+
+
+def ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)

@@ -1,0 +1,42 @@
+import importlib
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_NAME = "scanerf-scalable-bundle-adjusting-neural-radiance-fields-for-large-scale-scene-rendering_b200"
+PKG_DIR = os.path.join(ROOT, PKG_NAME)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def load_pkg():
+    """Import the (hyphen-named) product package and install its drop-in packages
+    (hashgrid / cuda / fastMesh / vdbAdam) at the front of sys.path."""
+    pkg = importlib.import_module(PKG_NAME)
+    pkg.install()
+    return pkg
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    return load_pkg()
+
+
+def ref_module(name):
+    """Import one of the reference extension modules rebuilt by oracle/build_ref.py
+    (oracle/_ref/<name>.so) or return None when it was not built."""
+    d = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(d, name + ".so")):
+        return None
+    import torch  # noqa: F401  (libtorch must be loaded first)
+    if d not in sys.path:
+        sys.path.append(d)
+    return importlib.import_module(name)
