@@ -1,0 +1,78 @@
+/*
+ * scanerf_b200.h -- C ABI of libscanerf_b200.so, the drop-in boundary of the
+ * B200-native (sm_100a) ScaNeRF hot path.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - row-major, dense (contiguous) arrays; shapes are given in the comments;
+ *   - outputs are written in place into caller-allocated memory, elements the
+ *     reference leaves untouched (sentinel fills) are left untouched here too;
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream, which is what the
+ *     reference launches on);
+ *   - return value 0 = launched; otherwise a cudaError_t, and snrf_last_error()
+ *     returns a thread-local description.  Asynchronous faults surface at the next
+ *     synchronisation, as with the reference's AT_CUDA_CHECK(cudaGetLastError()).
+ * Each entry point cites the reference interface (file:line under the reference
+ * checkout) it replaces.
+ */
+#ifndef SCANERF_B200_H
+#define SCANERF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ---------------------------------------------------------------- */
+const char* snrf_last_error(void);
+int snrf_version(void);
+int snrf_device_sm_count(void);
+
+/* ---- hash-grid encode ------------------------------------------------------- */
+/* hashgrid/include/hashgrid.h:19-25 (embedding_forward_cuda, corner/size != NULL) and
+ * :38-42 (embedding_bg_forward_cuda, corner = size = NULL).
+ * points[B,3] f32, table[L,T,2] f32 (T power of two), res[L,3] i32, corner[3], size[3]
+ * -> out[B,L,2] f32 (out_bf16=0) or out[B,2L] bf16 (out_bf16=1, tensor-core MLP input).
+ * idx_out (optional) [B,L,8] u32: the hashed table indices of the 8 cell corners. */
+int snrf_hash_fwd(const float* points, const float* table, const int* res, const float* corner,
+                  const float* size, void* out, unsigned* idx_out, int B, int L, int T, int out_bf16,
+                  void* stream);
+/* hashgrid/include/hashgrid.h:27-35 / :45-51 (embedding_backward_cuda, embedding_bg_backward_cuda).
+ * grad_in[B,L,2]; ACCUMULATES into grad_points[B,3] (may be NULL: skip d/dx) and
+ * grad_table[L,T,2].  aggregate_levels: levels [0,n) use the warp-aggregated scatter
+ * (-1 = default L/2). */
+int snrf_hash_bwd(const float* points, const float* grad_in, const float* table, const int* res,
+                  const float* corner, const float* size, float* grad_points, float* grad_table,
+                  int B, int L, int T, int aggregate_levels, void* stream);
+/* tuning hook: force the number of levels walked per CTA row (0 = automatic) */
+void snrf_hash_set_levels_per_block(int lpb);
+
+/* ---- rays, boxes, samplers -------------------------------------------------- */
+/* cuda/include/compute_ray.h (compute_ray_forward): Ks[N,9], C2Ws[N,12], locs[B,3] i32
+ * = (view, px, py) -> rays_o, rays_d [B,3]. */
+int snrf_compute_ray_fwd(float* rays_o, float* rays_d, const float* Ks, const float* C2Ws,
+                         const int* locs, int B, void* stream);
+/* cuda/include/compute_ray.h (compute_ray_backward): accumulates grad_C2Ws[N,12].
+ * ref_index_bug=1 reproduces cuda/compute_ray_kernel.cu:71-72 (gradients read at view_idx). */
+int snrf_compute_ray_bwd(const float* grad_o, const float* grad_d, const float* Ks, float* grad_C2Ws,
+                         const int* locs, int B, int ref_index_bug, void* stream);
+/* cuda/include/helper.h (ray_aabb_intersection K=1, ray_aabb_intersection_v2):
+ * centers[K,3], sizes[K,3] (full extents) -> bounds[B,K,2] = (near,far) or (-1,-1). */
+int snrf_ray_aabb(const float* rays_o, const float* rays_d, const float* centers, const float* sizes,
+                  float* bounds, int B, int K, void* stream);
+/* cuda/include/helper.h (sample_points_grid): occupied[2^lx,2^ly,2^lz] bytes, log2dim[3] i32
+ * (device) -> z_vals, dists [B,S]; counts[B] i32 optional (occupied segments per ray). */
+int snrf_sample_grid(const float* rays_o, const float* rays_d, float* z_vals, float* dists,
+                     const float* corner, const float* size, const unsigned char* occupied,
+                     const int* log2dim, int* counts, int B, int S, void* stream);
+/* cuda/include/sample.h (background_sampling_cuda) */
+int snrf_bg_sampling(const float* starts, const float* bg_depth, float* z_vals, int B, int S,
+                     float sample_range, void* stream);
+/* cuda/include/sample.h (sample_insideout_block); *miss_flag set to 1 if any ray misses the box */
+int snrf_sample_insideout(const float* rays_o, const float* rays_d, int S, int Sbg, const float* center,
+                          const float* size, float far, float* z_vals, float* z_vals_bg, int* miss_flag,
+                          int B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCANERF_B200_H */

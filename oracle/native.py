@@ -63,3 +63,63 @@ def hash_encode_bwd(points, grad_in, table, res, corner=None, size=None):
     lib().oracle_hash_encode_bwd(_p(points), _p(grad_in), _p(table), _p(res), _p(c), _p(s), _p(gp), _p(gt),
                                  ctypes.c_int(B), ctypes.c_int(L), ctypes.c_int(T))
     return gp, gt
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def compute_ray_fwd(Ks, C2Ws, locs):
+    Ks, C2Ws, locs = _f32(Ks), _f32(C2Ws), _i32(locs)
+    B = locs.shape[0]
+    o, d = np.zeros((B, 3), np.float32), np.zeros((B, 3), np.float32)
+    lib().oracle_compute_ray_fwd(_p(o), _p(d), _p(Ks), _p(C2Ws), _p(locs), ctypes.c_int(B))
+    return o, d
+
+
+def compute_ray_bwd(g_o, g_d, Ks, locs, n_cam, ref_index_bug=False):
+    g_o, g_d, Ks, locs = _f32(g_o), _f32(g_d), _f32(Ks), _i32(locs)
+    g = np.zeros((n_cam, 12), np.float32)
+    lib().oracle_compute_ray_bwd(_p(g_o), _p(g_d), _p(Ks), _p(g), _p(locs), ctypes.c_int(locs.shape[0]),
+                                 ctypes.c_int(int(ref_index_bug)))
+    return g
+
+
+def ray_aabb(rays_o, rays_d, centers, sizes):
+    rays_o, rays_d = _f32(rays_o), _f32(rays_d)
+    centers, sizes = _f32(centers).reshape(-1, 3), _f32(sizes).reshape(-1, 3)
+    B, K = rays_o.shape[0], centers.shape[0]
+    out = np.zeros((B, K, 2), np.float32)
+    lib().oracle_ray_aabb(_p(rays_o), _p(rays_d), _p(centers), _p(sizes), _p(out), ctypes.c_int(B), ctypes.c_int(K))
+    return out
+
+
+def sample_points_grid(rays_o, rays_d, corner, size, occupied, log2dim, S, fill=-1.0):
+    rays_o, rays_d, corner, size = _f32(rays_o), _f32(rays_d), _f32(corner), _f32(size)
+    occ, log2dim = _u8(occupied), _i32(log2dim)
+    B = rays_o.shape[0]
+    z = np.full((B, S), fill, np.float32)
+    d = np.full((B, S), fill, np.float32)
+    counts = np.zeros(B, np.int32)
+    lib().oracle_sample_points_grid(_p(rays_o), _p(rays_d), _p(z), _p(d), _p(corner), _p(size), _p(occ),
+                                    _p(log2dim), _p(counts), ctypes.c_int(B), ctypes.c_int(S))
+    return z, d, counts
+
+
+def background_sampling(starts, bg_depth, S, sample_range):
+    starts, bg_depth = _f32(starts), _f32(bg_depth)
+    B = starts.shape[0]
+    z = np.zeros((B, S), np.float32)
+    lib().oracle_background_sampling(_p(starts), _p(bg_depth), _p(z), ctypes.c_int(B), ctypes.c_int(S),
+                                     ctypes.c_float(sample_range))
+    return z
+
+
+def sample_insideout(rays_o, rays_d, S, Sbg, center, size, far):
+    rays_o, rays_d, center, size = _f32(rays_o), _f32(rays_d), _f32(center), _f32(size)
+    B = rays_o.shape[0]
+    z, zb = np.zeros((B, S), np.float32), np.zeros((B, Sbg), np.float32)
+    lib().oracle_sample_insideout.restype = ctypes.c_int
+    miss = lib().oracle_sample_insideout(_p(rays_o), _p(rays_d), ctypes.c_int(S), ctypes.c_int(Sbg), _p(center),
+                                         _p(size), ctypes.c_float(far), _p(z), _p(zb), ctypes.c_int(B))
+    return z, zb, miss

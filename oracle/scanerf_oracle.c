@@ -265,3 +265,205 @@ ORACLE_API void oracle_hash_encode_bwd(const float *points, const float *grad_in
     parallel_for(B, enc_gp_range, &x);
     free(x.gp_lvl);
 }
+
+/* ------------------------------------------------------------------------- */
+/* 2. ray generation, ray/box test, occupancy-grid sampler                    */
+/* ------------------------------------------------------------------------- */
+
+/* cuda/include/cuda_utils.h:143-155 (get_rays, +0.5 pixel centre) via
+ * cuda/compute_ray_kernel.cu:17-43.  locs[B,3] = (view, px, py). */
+ORACLE_API void oracle_compute_ray_fwd(float *rays_o, float *rays_d, const float *Ks, const float *C2Ws,
+                                       const int *locs, int B)
+{
+    for (int i = 0; i < B; ++i) {
+        const int v = locs[3 * i], px = locs[3 * i + 1], py = locs[3 * i + 2];
+        const float *K = Ks + 9 * v, *M = C2Ws + 12 * v;
+        const float x = (1.0f * px + 0.5f - K[2]) / K[0];
+        const float y = (1.0f * py + 0.5f - K[5]) / K[4];
+        rays_d[3 * i + 0] = fmaf(M[1], y, M[0] * x) + M[2];
+        rays_d[3 * i + 1] = fmaf(M[5], y, M[4] * x) + M[6];
+        rays_d[3 * i + 2] = fmaf(M[9], y, M[8] * x) + M[10];
+        rays_o[3 * i + 0] = M[3]; rays_o[3 * i + 1] = M[7]; rays_o[3 * i + 2] = M[11];
+    }
+}
+
+/* cuda/compute_ray_kernel.cu:45-92.  ref_index_bug != 0 reproduces the reference's
+ * read of grad_rays_*[view_idx] (:71-72); 0 reads grad_rays_*[ray] (the correct
+ * gradient of the forward above).  Accumulates into grad_C2Ws[N,12]. */
+ORACLE_API void oracle_compute_ray_bwd(const float *g_o, const float *g_d, const float *Ks, float *grad_C2Ws,
+                                       const int *locs, int B, int ref_index_bug)
+{
+    for (int i = 0; i < B; ++i) {
+        const int v = locs[3 * i], px = locs[3 * i + 1], py = locs[3 * i + 2];
+        const float *K = Ks + 9 * v;
+        const float x = (1.0f * px + 0.5f - K[2]) / K[0];
+        const float y = (1.0f * py + 0.5f - K[5]) / K[4];
+        const int gi = ref_index_bug ? v : i;
+        const float *go = g_o + 3 * gi, *gd = g_d + 3 * gi;
+        float *g = grad_C2Ws + 12 * v;
+        g[3] += go[0]; g[7] += go[1]; g[11] += go[2];
+        g[0] += gd[0] * x; g[1] += gd[0] * y; g[2] += gd[0];
+        g[4] += gd[1] * x; g[5] += gd[1] * y; g[6] += gd[1];
+        g[8] += gd[2] * x; g[9] += gd[2] * y; g[10] += gd[2];
+    }
+}
+
+/* cuda/include/cuda_utils.h:564-613 (float3 half-size overload) */
+static void ray_aabb1(const float *o, const float *d, const float *c, const float *h, float *lo_out, float *hi_out)
+{
+    float f_low = 0.0f, f_high = 100000.0f;
+    for (int a = 0; a < 3; ++a) {
+        float inv = safe_divide(1.0f, d[a]);
+        float lo = (c[a] - h[a] - o[a]) * inv;
+        float hi = (c[a] + h[a] - o[a]) * inv;
+        if (hi < lo) { float t = lo; lo = hi; hi = t; }
+        if (hi < f_low || lo > f_high) { *lo_out = -1.0f; *hi_out = -1.0f; return; }
+        f_low = lo > f_low ? lo : f_low;
+        f_high = hi < f_high ? hi : f_high;
+        if (f_low > f_high) { *lo_out = -1.0f; *hi_out = -1.0f; return; }
+    }
+    *lo_out = f_low; *hi_out = f_high;
+}
+
+/* cuda/helper_kernel.cu:107-197: boxes given as center[K,3], size[K,3]; bounds[B,K,2] */
+ORACLE_API void oracle_ray_aabb(const float *rays_o, const float *rays_d, const float *centers, const float *sizes,
+                                float *bounds, int B, int K)
+{
+    for (int i = 0; i < B; ++i)
+        for (int k = 0; k < K; ++k) {
+            float h[3] = {sizes[3 * k] * 0.5f, sizes[3 * k + 1] * 0.5f, sizes[3 * k + 2] * 0.5f};
+            ray_aabb1(rays_o + 3 * i, rays_d + 3 * i, centers + 3 * k, h,
+                      bounds + ((size_t)i * K + k) * 2, bounds + ((size_t)i * K + k) * 2 + 1);
+        }
+}
+
+/* cuda/include/dda.h:206-268 (DDASatateScene_v2) */
+typedef struct {
+    int c[3], s[3], m[3], n[3];
+    float tmax[3], tdelta[3], t0, t1;
+} walk_t;
+
+static void walk_init(walk_t *w, const float *o_in, const float *d, float t_near, float t_far, const int *n, const float *cell)
+{
+    float o[3];
+    for (int a = 0; a < 3; ++a) {
+        w->n[a] = n[a];
+        o[a] = fmaf(t_near, d[a], o_in[a]);                 /* origin + t*dir contracts */
+        w->c[a] = iclamp((int)(o[a] / cell[a]), 0, n[a] - 1);
+        w->s[a] = signf_i(d[a]);
+        float nb = (float)(w->c[a] + w->s[a]) * cell[a];
+        if (w->s[a] < 0) nb += cell[a];
+        w->tmax[a] = fmaxf(safe_divide(nb - o[a], d[a]), 0.0f) + t_near;
+        w->tdelta[a] = fabsf(safe_divide(cell[a], d[a]));
+    }
+    w->t0 = t_near; w->t1 = t_far;
+}
+static void walk_next(walk_t *w)
+{
+    w->m[0] = (w->tmax[0] < w->tmax[1]) & (w->tmax[0] <= w->tmax[2]);
+    w->m[1] = (w->tmax[1] < w->tmax[2]) & (w->tmax[1] <= w->tmax[0]);
+    w->m[2] = !(w->m[0] | w->m[1]);
+    w->t1 = w->m[0] ? w->tmax[0] : (w->m[1] ? w->tmax[1] : w->tmax[2]);
+}
+static void walk_step(walk_t *w)
+{
+    w->t0 = w->t1;
+    for (int a = 0; a < 3; ++a) {
+        w->tmax[a] = fmaf((float)w->m[a], w->tdelta[a], w->tmax[a]);
+        w->c[a] += w->m[a] * w->s[a];
+    }
+}
+static int walk_done(const walk_t *w)
+{
+    for (int a = 0; a < 3; ++a) if (w->c[a] < 0 || w->c[a] >= w->n[a]) return 1;
+    return w->tmax[0] <= 0 && w->tmax[1] <= 0 && w->tmax[2] <= 0;
+}
+
+/* cuda/helper_kernel.cu:539-671 (sample_points_sparse_single_ray + launcher).
+ * z_vals/dists[B,S] keep the caller's fill for rays that miss or see nothing.
+ * counts[B] (optional) = number of occupied segments with positive length. */
+ORACLE_API void oracle_sample_points_grid(const float *rays_o, const float *rays_d, float *z_vals, float *dists,
+                                          const float *corner, const float *size, const unsigned char *occ,
+                                          const int *log2dim, int *counts, int B, int S)
+{
+    const int n[3] = {1 << log2dim[0], 1 << log2dim[1], 1 << log2dim[2]};
+    const int ly = log2dim[1], lz = log2dim[2];
+    float cell[3], half[3], center[3];
+    for (int a = 0; a < 3; ++a) {
+        cell[a] = size[a] / (float)n[a];
+        half[a] = size[a] * 0.5f;
+        center[a] = corner[a] + half[a];
+    }
+    for (int i = 0; i < B; ++i) {
+        const float *o = rays_o + 3 * i, *d = rays_d + 3 * i;
+        float tn, tf;
+        if (counts) counts[i] = 0;
+        ray_aabb1(o, d, center, half, &tn, &tf);
+        if (tn == -1.0f) continue;
+        float ol[3] = {o[0] - corner[0], o[1] - corner[1], o[2] - corner[2]};
+        walk_t w;
+        walk_init(&w, ol, d, tn, tf, n, cell);
+        float total = 0.0f; int count = 0;
+        while (!walk_done(&w)) {
+            walk_next(&w);
+            uint32_t idx = ((uint32_t)w.c[0] << (ly + lz)) | ((uint32_t)w.c[1] << lz) | (uint32_t)w.c[2];
+            if (occ[idx]) { float len = w.t1 - w.t0; if (len > 0) { total += len; ++count; } }
+            walk_step(&w);
+        }
+        if (counts) counts[i] = count;
+        if (count == 0) continue;
+        walk_init(&w, ol, d, tn, tf, n, cell);
+        int left = S, seen = 0;
+        while (!walk_done(&w)) {
+            walk_next(&w);
+            uint32_t idx = ((uint32_t)w.c[0] << (ly + lz)) | ((uint32_t)w.c[1] << lz) | (uint32_t)w.c[2];
+            if (occ[idx]) {
+                float len = w.t1 - w.t0;
+                if (len > 0) {
+                    int num = imin(imax((int)((float)S * len / total), 1), left);
+                    if (seen == count - 1) num = left;
+                    /* uniform_sample_bound_v3, cuda_utils.h:101-113 */
+                    float interval = (w.t1 - w.t0) / (float)num;
+                    for (int k = 0; k < num; ++k) {
+                        z_vals[(size_t)i * S + (S - left) + k] = fmaf((float)k, interval, w.t0);
+                        dists[(size_t)i * S + (S - left) + k] = interval;
+                    }
+                    left -= num; ++seen;
+                }
+            }
+            walk_step(&w);
+        }
+    }
+}
+
+/* cuda/sample_kernel.cu:17-44 + uniform_sample_bound (cuda_utils.h:77-87) */
+ORACLE_API void oracle_background_sampling(const float *starts, const float *bg_depth, float *z_vals,
+                                           int B, int S, float range)
+{
+    for (int i = 0; i < B; ++i) {
+        float near = fmaxf(starts[i] + 0.00001f, fmaf(-range, 0.5f, bg_depth[i]));
+        float far = near + range;
+        float interval = (far - near) / (float)(S - 1);
+        for (int k = 0; k < S; ++k) z_vals[(size_t)i * S + k] = fmaf((float)k, interval, near);
+    }
+}
+
+/* cuda/sample_kernel.cu:70-100 + inverse_z_sample_bound (cuda_utils.h:61-75).
+ * Returns the number of rays that miss the box (the reference device-asserts). */
+ORACLE_API int oracle_sample_insideout(const float *rays_o, const float *rays_d, int S, int Sbg, const float *center,
+                                       const float *size, float far, float *z_vals, float *z_bg, int B)
+{
+    int misses = 0;
+    float half[3] = {size[0] * 0.5f, size[1] * 0.5f, size[2] * 0.5f};
+    for (int i = 0; i < B; ++i) {
+        float tn, tf;
+        ray_aabb1(rays_o + 3 * i, rays_d + 3 * i, center, half, &tn, &tf);
+        if (tn == -1.0f || tf == -1.0f) { ++misses; continue; }
+        float interval = (tf - tn) / (float)(S - 1);
+        for (int k = 0; k < S; ++k) z_vals[(size_t)i * S + k] = fmaf((float)k, interval, tn);
+        float inv_near = 1.0f / tf, inv_far = 1.0f / far, inv_bound = inv_far - inv_near;
+        float step = 1.0f / (float)(Sbg - 1);
+        for (int k = 0; k < Sbg; ++k) z_bg[(size_t)i * Sbg + k] = 1.0f / fmaf(step * (float)k, inv_bound, inv_near);
+    }
+    return misses;
+}

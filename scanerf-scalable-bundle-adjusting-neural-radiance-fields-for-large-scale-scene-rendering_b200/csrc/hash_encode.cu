@@ -107,17 +107,22 @@ __global__ void __launch_bounds__(kThreads)
 hash_fwd_kernel(const float* __restrict__ points, const float2* __restrict__ table,
                 const int* __restrict__ res, const float* __restrict__ corner_p,
                 const float* __restrict__ size_p, void* __restrict__ out_v,
-                uint32_t* __restrict__ idx_out, int B, int L, uint32_t T)
+                uint32_t* __restrict__ idx_out, int B, int L, uint32_t T, int lpb)
 {
     const uint32_t mask = T - 1u;
     f3 corner = mk3(0, 0, 0), size = mk3(1, 1, 1);
     if (BBOX) { corner = ld3(corner_p); size = ld3(size_p); }
+    // blockIdx.y selects a group of `lpb` consecutive levels: CTAs are dispatched
+    // x-fastest, so the whole GPU works on one level group at a time and the live
+    // table footprint (128 MiB per level at T=2^24) stays within TLB / L2 reach.
+    const int l_begin = blockIdx.y * lpb;
+    const int l_end = min(L, l_begin + lpb);
 
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         const f3 p = ld3(points + 3 * (size_t)b);
-        int l = 0;
+        int l = l_begin;
         // two levels per trip: 16 independent 8-byte gathers in flight
-        for (; l + 1 < L; l += 2) {
+        for (; l + 1 < l_end; l += 2) {
             const Cell c0 = locate<BBOX>(p, res + 3 * l, corner, size);
             const Cell c1 = locate<BBOX>(p, res + 3 * (l + 1), corner, size);
             uint32_t i0[8], i1[8];
@@ -139,7 +144,7 @@ hash_fwd_kernel(const float* __restrict__ points, const float2* __restrict__ tab
             }
             if (OUT_MODE == 0) {
                 float* o = (float*)out_v + ((size_t)b * L + l) * 2;
-                if ((L & 1) == 0) {
+                if (((L | l) & 1) == 0) {
                     *reinterpret_cast<float4*>(o) = make_float4(a0.x, a0.y, a1.x, a1.y);
                 } else {
                     o[0] = a0.x; o[1] = a0.y; o[2] = a1.x; o[3] = a1.y;
@@ -157,7 +162,7 @@ hash_fwd_kernel(const float* __restrict__ points, const float2* __restrict__ tab
                 }
             }
         }
-        if (l < L) {  // odd level count tail
+        if (l < l_end) {  // odd level count tail
             const Cell c0 = locate<BBOX>(p, res + 3 * l, corner, size);
             uint32_t i0[8]; float w0[8];
             corner_idx(i0, c0, mask);
@@ -201,10 +206,13 @@ hash_bwd_kernel(const float* __restrict__ points, const float2* __restrict__ gra
                 const float2* __restrict__ table, const int* __restrict__ res,
                 const float* __restrict__ corner_p, const float* __restrict__ size_p,
                 float* __restrict__ grad_points, float2* __restrict__ grad_table,
-                int B, int L, uint32_t T, int aggregate_levels)
+                int B, int L, uint32_t T, int aggregate_levels, int lpb)
 {
     const uint32_t mask = T - 1u;
     const int lane = threadIdx.x & 31;
+    const int l_begin = blockIdx.y * lpb;
+    const int l_end = min(L, l_begin + lpb);
+    const bool sole_writer = (lpb >= L);   // one CTA row owns every level of a point
     f3 corner = mk3(0, 0, 0), size = mk3(1, 1, 1);
     if (BBOX) { corner = ld3(corner_p); size = ld3(size_p); }
 
@@ -216,7 +224,7 @@ hash_bwd_kernel(const float* __restrict__ points, const float2* __restrict__ gra
         const f3 p = live ? ld3(points + 3 * (size_t)b) : mk3(0, 0, 0);
         float gpx = 0.f, gpy = 0.f, gpz = 0.f;
 
-        for (int l = 0; l < L; ++l) {
+        for (int l = l_begin; l < l_end; ++l) {
             const Cell c = locate<BBOX>(p, res + 3 * l, corner, size);
             uint32_t idx[8]; float w[8];
             corner_idx(idx, c, mask);
@@ -276,8 +284,12 @@ hash_bwd_kernel(const float* __restrict__ points, const float2* __restrict__ gra
             }
         }
         if (NEED_DX && live) {
-            float* gp = grad_points + 3 * (size_t)b;   // single writer per point: accumulate semantics, no atomics
-            gp[0] += gpx; gp[1] += gpy; gp[2] += gpz;
+            float* gp = grad_points + 3 * (size_t)b;
+            if (sole_writer) {   // single writer per point: accumulate semantics, no atomics
+                gp[0] += gpx; gp[1] += gpy; gp[2] += gpz;
+            } else {             // one reduction per level group (the reference: one per level)
+                atomicAdd(gp + 0, gpx); atomicAdd(gp + 1, gpy); atomicAdd(gp + 2, gpz);
+            }
         }
     }
 }
@@ -292,9 +304,26 @@ inline int grid_for(int B)
     return wave * ((want + wave - 1) / wave > 4 ? 4 : (want + wave - 1) / wave);
 }
 
+// Levels per CTA row (blockIdx.y = level group).  Measured on B200 (tools/microbench.py
+// encode --sweep): walking ONE level at a time is fastest once a level's table slice
+// is large (T=2^24: fwd 3.2 ms vs 5.1 ms all-levels-per-thread; the 2 MiB-page TLB
+// reaches 256 MiB and a 128 MiB level fits L2), while small tables prefer a few
+// levels per thread (T=2^19: 4).  Rule: as many levels as fit 16 MiB, power of two.
+int g_lpb_override = 0;
+inline int pick_lpb(int L, int T)
+{
+    if (g_lpb_override > 0) return g_lpb_override > L ? L : g_lpb_override;
+    const long long level_bytes = (long long)T * 8;
+    int lpb = 1;
+    while (lpb * 2 <= L && (long long)lpb * 2 * level_bytes <= (16ll << 20)) lpb *= 2;
+    return lpb;
+}
+
 }  // namespace
 
 // ------------------------------- C ABI --------------------------------------
+SNRF_API void snrf_hash_set_levels_per_block(int lpb) { g_lpb_override = lpb; }
+
 SNRF_API int snrf_hash_fwd(const float* points, const float* table, const int* res,
                            const float* corner, const float* size, void* out, unsigned* idx_out,
                            int B, int L, int T, int out_bf16, void* stream)
@@ -303,14 +332,15 @@ SNRF_API int snrf_hash_fwd(const float* points, const float* table, const int* r
     SNRF_CHECK_ARG((corner == nullptr) == (size == nullptr), "snrf_hash_fwd: corner and size must be given together");
     if (B == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    const int grid = grid_for(B);
+    const int lpb = pick_lpb(L, T);
+    const dim3 grid(grid_for(B), snrf_div_up(L, lpb));
     const float2* tb = (const float2*)table;
     if (corner) {
-        if (out_bf16) hash_fwd_kernel<true, 1><<<grid, kThreads, 0, s>>>(points, tb, res, corner, size, out, idx_out, B, L, (uint32_t)T);
-        else          hash_fwd_kernel<true, 0><<<grid, kThreads, 0, s>>>(points, tb, res, corner, size, out, idx_out, B, L, (uint32_t)T);
+        if (out_bf16) hash_fwd_kernel<true, 1><<<grid, kThreads, 0, s>>>(points, tb, res, corner, size, out, idx_out, B, L, (uint32_t)T, lpb);
+        else          hash_fwd_kernel<true, 0><<<grid, kThreads, 0, s>>>(points, tb, res, corner, size, out, idx_out, B, L, (uint32_t)T, lpb);
     } else {
-        if (out_bf16) hash_fwd_kernel<false, 1><<<grid, kThreads, 0, s>>>(points, tb, res, corner, size, out, idx_out, B, L, (uint32_t)T);
-        else          hash_fwd_kernel<false, 0><<<grid, kThreads, 0, s>>>(points, tb, res, corner, size, out, idx_out, B, L, (uint32_t)T);
+        if (out_bf16) hash_fwd_kernel<false, 1><<<grid, kThreads, 0, s>>>(points, tb, res, corner, size, out, idx_out, B, L, (uint32_t)T, lpb);
+        else          hash_fwd_kernel<false, 0><<<grid, kThreads, 0, s>>>(points, tb, res, corner, size, out, idx_out, B, L, (uint32_t)T, lpb);
     }
     SNRF_RETURN_LAUNCH("snrf_hash_fwd");
 }
@@ -324,17 +354,18 @@ SNRF_API int snrf_hash_bwd(const float* points, const float* grad_in, const floa
     SNRF_CHECK_ARG(grad_table != nullptr, "snrf_hash_bwd: grad_table is required");
     if (B == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    const int grid = grid_for(B);
+    const int lpb = pick_lpb(L, T);
+    const dim3 grid(grid_for(B), snrf_div_up(L, lpb));
     const float2* tb = (const float2*)table;
     const float2* gi = (const float2*)grad_in;
     float2* gt = (float2*)grad_table;
     if (aggregate_levels < 0) aggregate_levels = L / 2;
     if (corner) {
-        if (grad_points) hash_bwd_kernel<true, true><<<grid, kThreads, 0, s>>>(points, gi, tb, res, corner, size, grad_points, gt, B, L, (uint32_t)T, aggregate_levels);
-        else             hash_bwd_kernel<true, false><<<grid, kThreads, 0, s>>>(points, gi, tb, res, corner, size, grad_points, gt, B, L, (uint32_t)T, aggregate_levels);
+        if (grad_points) hash_bwd_kernel<true, true><<<grid, kThreads, 0, s>>>(points, gi, tb, res, corner, size, grad_points, gt, B, L, (uint32_t)T, aggregate_levels, lpb);
+        else             hash_bwd_kernel<true, false><<<grid, kThreads, 0, s>>>(points, gi, tb, res, corner, size, grad_points, gt, B, L, (uint32_t)T, aggregate_levels, lpb);
     } else {
-        if (grad_points) hash_bwd_kernel<false, true><<<grid, kThreads, 0, s>>>(points, gi, tb, res, corner, size, grad_points, gt, B, L, (uint32_t)T, aggregate_levels);
-        else             hash_bwd_kernel<false, false><<<grid, kThreads, 0, s>>>(points, gi, tb, res, corner, size, grad_points, gt, B, L, (uint32_t)T, aggregate_levels);
+        if (grad_points) hash_bwd_kernel<false, true><<<grid, kThreads, 0, s>>>(points, gi, tb, res, corner, size, grad_points, gt, B, L, (uint32_t)T, aggregate_levels, lpb);
+        else             hash_bwd_kernel<false, false><<<grid, kThreads, 0, s>>>(points, gi, tb, res, corner, size, grad_points, gt, B, L, (uint32_t)T, aggregate_levels, lpb);
     }
     SNRF_RETURN_LAUNCH("snrf_hash_bwd");
 }

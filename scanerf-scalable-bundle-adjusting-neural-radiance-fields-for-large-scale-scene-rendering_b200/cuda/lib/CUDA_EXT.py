@@ -1,0 +1,114 @@
+"""Python face of the CUDA_EXT extension module (reference: cuda/binding.cpp:10-53).
+
+Same names, argument order, dtypes and in-place-output convention as the
+reference pybind module; every op forwards raw device pointers + the current
+stream to the C ABI in libscanerf_b200.so (include/scanerf_b200.h).
+"""
+import ctypes
+
+import torch
+
+import scanerf_b200_capi as capi
+from scanerf_b200_capi import c_float, c_int, c_void_p, inp, Out, ptr
+
+f32, i32, u8, b8 = torch.float32, torch.int32, torch.uint8, torch.bool
+
+
+def compute_ray_forward(rays_o, rays_d, Ks, C2Ws, locs):
+    """cuda/include/compute_ray.h -- rays_o, rays_d [B,3] written in place from
+    Ks [N,9], C2Ws [N,12] and locs [B,3] int32 = (view, px, py)."""
+    B = int(rays_o.shape[0])
+    o, d = Out(rays_o, f32, "rays_o"), Out(rays_d, f32, "rays_d")
+    k, c, l = inp(Ks, f32, "Ks"), inp(C2Ws, f32, "C2Ws"), inp(locs, i32, "locs")
+    capi.check(capi.lib().snrf_compute_ray_fwd(o.ptr, d.ptr, ptr(k), ptr(c), ptr(l), c_int(B), capi.stream()),
+               "snrf_compute_ray_fwd")
+    o.done(); d.done()
+
+
+def compute_ray_backward(grad_rays_o, grad_rays_d, Ks, grad_C2Ws, locs, ref_index_bug=False):
+    """cuda/include/compute_ray.h -- accumulates dL/dC2W [N,12].  The reference
+    kernel reads the incoming gradients at index view_idx (compute_ray_kernel.cu:71-72),
+    which is only right when ray i belongs to view i; this op indexes by ray.  Pass
+    ref_index_bug=True to reproduce the reference arithmetic exactly."""
+    B = int(grad_rays_o.shape[0])
+    go, gd = inp(grad_rays_o, f32, "grad_rays_o"), inp(grad_rays_d, f32, "grad_rays_d")
+    k, l = inp(Ks, f32, "Ks"), inp(locs, i32, "locs")
+    g = Out(grad_C2Ws, f32, "grad_C2Ws")
+    capi.check(capi.lib().snrf_compute_ray_bwd(ptr(go), ptr(gd), ptr(k), g.ptr, ptr(l), c_int(B),
+                                               c_int(int(ref_index_bug)), capi.stream()), "snrf_compute_ray_bwd")
+    g.done()
+
+
+def ray_aabb_intersection(rays_o, rays_d, aabb_center, aabb_size, bounds):
+    """cuda/include/helper.h -- bounds [B,2] = (near, far) or (-1,-1)."""
+    B = int(rays_o.shape[0])
+    o, d = inp(rays_o, f32, "rays_o"), inp(rays_d, f32, "rays_d")
+    c, s = inp(aabb_center, f32, "aabb_center"), inp(aabb_size, f32, "aabb_size")
+    b = Out(bounds, f32, "bounds")
+    capi.check(capi.lib().snrf_ray_aabb(ptr(o), ptr(d), ptr(c), ptr(s), b.ptr, c_int(B), c_int(1), capi.stream()),
+               "snrf_ray_aabb")
+    b.done()
+
+
+def ray_aabb_intersection_v2(rays_o, rays_d, aabb_center, aabb_size, bounds):
+    """cuda/include/helper.h -- K boxes: bounds [B,K,2]."""
+    B, K = int(rays_o.shape[0]), int(aabb_center.shape[0])
+    o, d = inp(rays_o, f32, "rays_o"), inp(rays_d, f32, "rays_d")
+    c, s = inp(aabb_center, f32, "aabb_center"), inp(aabb_size, f32, "aabb_size")
+    b = Out(bounds, f32, "bounds")
+    capi.check(capi.lib().snrf_ray_aabb(ptr(o), ptr(d), ptr(c), ptr(s), b.ptr, c_int(B), c_int(K), capi.stream()),
+               "snrf_ray_aabb")
+    b.done()
+
+
+def sample_points_grid(rays_o, rays_d, z_vals, dists, block_corner, block_size, occupied_gird, log2dim,
+                       counts=None):
+    """cuda/include/helper.h -- occupancy-proportional sample placement; z_vals,
+    dists [B,S] keep the caller's fill (-1) on rays that miss / see nothing.
+    `counts` (extension, int32 [B]) receives the number of occupied segments."""
+    B, S = int(rays_o.shape[0]), int(z_vals.shape[1])
+    o, d = inp(rays_o, f32, "rays_o"), inp(rays_d, f32, "rays_d")
+    c, s = inp(block_corner, f32, "block_corner"), inp(block_size, f32, "block_size")
+    occ = inp(occupied_gird, b8, "occupied_grid")
+    lg = inp(log2dim, i32, "log2dim")
+    z, di = Out(z_vals, f32, "z_vals"), Out(dists, f32, "dists")
+    cn = Out(counts, i32, "counts") if counts is not None else None
+    capi.check(capi.lib().snrf_sample_grid(ptr(o), ptr(d), z.ptr, di.ptr, ptr(c), ptr(s), ptr(occ), ptr(lg),
+                                           cn.ptr if cn else c_void_p(0), c_int(B), c_int(S), capi.stream()),
+               "snrf_sample_grid")
+    z.done(); di.done()
+    if cn:
+        cn.done()
+
+
+def sample_points_contract(*args, **kwargs):
+    """The reference declares this op at::Tensor but never returns a value
+    (cuda/helper_kernel.cu:511-536: undefined behaviour if called; no caller exists)."""
+    raise NotImplementedError("sample_points_contract has no defined behaviour in the reference (UB); unsupported")
+
+
+def background_sampling_cuda(rays_o, rays_d, starts, bg_depth, z_vals, num_sample, sample_range):
+    """cuda/include/sample.h -- uniform samples in a window of `sample_range` around the mesh depth."""
+    B = int(rays_o.shape[0])
+    st, bd = inp(starts, f32, "starts"), inp(bg_depth, f32, "bg_depth")
+    z = Out(z_vals, f32, "z_vals")
+    capi.check(capi.lib().snrf_bg_sampling(ptr(st), ptr(bd), z.ptr, c_int(B), c_int(int(num_sample)),
+                                           c_float(float(sample_range)), capi.stream()), "snrf_bg_sampling")
+    z.done()
+
+
+def sample_insideout_block(rays_o, rays_d, num_sample, num_sample_bg, block_center, block_size, far,
+                           z_vals, z_vals_bg):
+    """cuda/include/sample.h -- uniform inside the box + inverse-z beyond it.  A ray
+    missing the box trips a device assert in the reference; here it raises."""
+    B = int(rays_o.shape[0])
+    o, d = inp(rays_o, f32, "rays_o"), inp(rays_d, f32, "rays_d")
+    c, s = inp(block_center, f32, "block_center"), inp(block_size, f32, "block_size")
+    z, zb = Out(z_vals, f32, "z_vals"), Out(z_vals_bg, f32, "z_vals_bg")
+    flag = torch.zeros(1, dtype=i32, device=rays_o.device)
+    capi.check(capi.lib().snrf_sample_insideout(ptr(o), ptr(d), c_int(int(num_sample)), c_int(int(num_sample_bg)),
+                                                ptr(c), ptr(s), c_float(float(far)), z.ptr, zb.ptr, ptr(flag),
+                                                c_int(B), capi.stream()), "snrf_sample_insideout")
+    z.done(); zb.done()
+    if int(flag.item()) != 0:
+        raise RuntimeError("sample_insideout_block: a ray does not intersect the block (reference: device assert)")

@@ -70,6 +70,22 @@ def bench_encode(a):
     gt = torch.zeros_like(table)
     flush = torch.zeros(64 * 1024 * 1024, device=dev)  # 256 MB > L2
     r = {"B": B, "log2T": a.log2T, "uniform": a.uniform}
+    import scanerf_b200_capi as capi
+    import ctypes
+    if a.sweep:
+        for lpb in (1, 2, 4, 16):
+            capi.lib().snrf_hash_set_levels_per_block(ctypes.c_int(lpb))
+            t = timeit(lambda: ops.embedding_bg_forward_cuda(pts, out, table, res), a.iters, flush)
+            r[f"lpb{lpb}_fwd_ms"] = round(t, 3)
+            t = timeit(lambda: ops._encode_fwd(pts, obf0, table, None, None, res), a.iters, flush) if False else 0
+            for agg in (0, 8):
+                t = timeit(lambda: ops._encode_bwd(pts, gin, gp, gt, table, None, None, res, aggregate_levels=agg), a.iters, flush)
+                r[f"lpb{lpb}_bwd_agg{agg}_ms"] = round(t, 3)
+            t = timeit(lambda: ops._encode_bwd(pts, gin, None, gt, table, None, None, res, aggregate_levels=8), a.iters, flush)
+            r[f"lpb{lpb}_bwd_nodx_ms"] = round(t, 3)
+        capi.lib().snrf_hash_set_levels_per_block(ctypes.c_int(0))
+        print(json.dumps(r))
+        return r
     t = timeit(lambda: ops.embedding_bg_forward_cuda(pts, out, table, res), a.iters, flush)
     r["fwd_ms"] = t; r["fwd_GBs_alg"] = B * 1164 / t / 1e6
     obf = torch.zeros(B, 2 * L, device=dev, dtype=torch.bfloat16)
@@ -102,5 +118,6 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--uniform", action="store_true")
     ap.add_argument("--ref", action="store_true")
+    ap.add_argument("--sweep", action="store_true")
     a = ap.parse_args()
     {"encode": bench_encode}[a.what](a)
