@@ -72,6 +72,36 @@ int snrf_sample_insideout(const float* rays_o, const float* rays_d, int S, int S
                           const float* size, float far, float* z_vals, float* z_vals_bg, int* miss_flag,
                           int B, void* stream);
 
+/* ---- front-to-back compositing ------------------------------------------------ */
+/* hashgrid/__init__.py:344-366,564-596 (HashGrid.cal_integrate_weight / accumulate / tail of
+ * render_batch_rays), which the reference runs as a chain of torch ops.
+ * Per-sample heads are addressed base + n*stride (strides in floats): sigma[R*S], tint,
+ * diffuse, specular [R*S,3]; z_vals, dists [R,S]; rays_d [R,3] (|d| scales the step).
+ * -> weights[R,S], trans[R,S] (transmittance before each sample; may be NULL in fwd),
+ *    out[R,16] = depth, tint3, diffuse3, specular3 (= sum w tint*spec), l2_3 (= sum w spec^2),
+ *    T_left, 2 pad.  infinity != 0: last step is 1e10. */
+int snrf_composite_fwd(const float* sigma, const float* tint, const float* diffuse, const float* specular,
+                       int s_sigma, int s_tint, int s_diffuse, int s_specular,
+                       const float* z_vals, const float* dists, const float* rays_d, int R, int S,
+                       int infinity, float* weights, float* trans, float* out, void* stream);
+/* backward of the above: g_out[R,16] (same row layout; l2 columns act on specular only, the
+ * weights inside l2 are detached as in the reference), g_weights[R,S] optional.  WRITES the
+ * per-sample head gradients (strides gs_*) and grad_rays_d[R,3] (optional). */
+int snrf_composite_bwd(const float* sigma, const float* tint, const float* diffuse, const float* specular,
+                       int s_sigma, int s_tint, int s_diffuse, int s_specular,
+                       const float* z_vals, const float* dists, const float* rays_d, const float* trans,
+                       const float* g_out, const float* g_weights, int R, int S, int infinity,
+                       float* g_sigma, float* g_tint, float* g_diffuse, float* g_specular,
+                       int gs_sigma, int gs_tint, int gs_diffuse, int gs_specular,
+                       float* grad_rays_d, void* stream);
+
+/* ---- mesh ingest (host) ------------------------------------------------------- */
+/* cuda/include/voxelize.h:12-119 (voxelize_mesh): ALL pointers are host pointers.
+ * log2dim[3], corner[3], size[3]; vis / outside: bytes [2^lx * 2^ly * 2^lz]. */
+int snrf_voxelize_mesh_host(const int* log2dim, const float* corner, const float* size,
+                            const char* model_path, unsigned char* vis, int init_out,
+                            unsigned char* outside);
+
 #ifdef __cplusplus
 }
 #endif

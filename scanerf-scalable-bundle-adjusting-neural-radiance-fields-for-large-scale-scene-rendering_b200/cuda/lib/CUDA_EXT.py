@@ -112,3 +112,25 @@ def sample_insideout_block(rays_o, rays_d, num_sample, num_sample_bg, block_cent
     z.done(); zb.done()
     if int(flag.item()) != 0:
         raise RuntimeError("sample_insideout_block: a ray does not intersect the block (reference: device assert)")
+
+
+def voxelize_mesh(log2dim, corner, size, model_path, vis, init_out, outside):
+    """cuda/include/voxelize.h:12-119 -- HOST op (CPU tensors, as in the reference): rasterise
+    every face's 1.5x-inflated AABB into the bool grid `vis`; with init_out, cells outside the
+    geometry AABB are marked in `vis` and `outside`.  An empty path marks everything visible."""
+    for t, n in ((log2dim, "log2dim"), (corner, "corner"), (size, "size"), (vis, "vis"), (outside, "outside")):
+        if t.is_cuda:
+            raise RuntimeError(f"voxelize_mesh: {n} must be a CPU tensor (host-side op in the reference too)")
+    lg = log2dim.to(i32).contiguous()
+    c, s = corner.to(f32).contiguous(), size.to(f32).contiguous()
+    if vis.dtype not in (b8, u8) or outside.dtype not in (b8, u8):
+        raise RuntimeError("voxelize_mesh: vis / outside must be bool tensors")
+    v = vis if vis.is_contiguous() else vis.contiguous()
+    o = outside if outside.is_contiguous() else outside.contiguous()
+    rc = capi.lib().snrf_voxelize_mesh_host(ptr(lg), ptr(c), ptr(s), ctypes.c_char_p(str(model_path).encode()),
+                                            ptr(v), c_int(int(bool(init_out))), ptr(o))
+    capi.check(rc, "snrf_voxelize_mesh_host")
+    if v is not vis:
+        vis.copy_(v)
+    if o is not outside:
+        outside.copy_(o)

@@ -1,0 +1,79 @@
+"""Compositing and (later) fused field evaluation used by HashGrid.render_batch_rays.
+
+The reference does this with a chain of torch ops (hashgrid/__init__.py:344-366,
+564-596); here it is one forward and one backward kernel (csrc/composite.cu) behind
+an autograd.Function.
+"""
+import torch
+
+import scanerf_b200_capi as capi
+from scanerf_b200_capi import c_int, c_void_p, ptr
+
+_ROW = 16   # per-ray output row of snrf_composite_fwd
+
+
+def _strides(sigma, tint, diffuse, specular):
+    return [c_int(1), c_int(3), c_int(3), c_int(3)]
+
+
+class CompositeFn(torch.autograd.Function):
+    """(sigma [R,S,1], tint/diffuse/specular [R,S,3], z_vals, dists [R,S], rays_d [R,3]) ->
+    (row [R,16] = depth, tint3, diffuse3, specular3, l2_3, T_left, pad2 ; weights [R,S])."""
+
+    @staticmethod
+    def forward(ctx, sigma, tint, diffuse, specular, z_vals, dists, rays_d, infinity):
+        R, S = z_vals.shape
+        f32 = torch.float32
+        sigma, tint, diffuse, specular = (t.contiguous().to(f32) for t in (sigma, tint, diffuse, specular))
+        z_vals, dists, rays_d = z_vals.contiguous(), dists.contiguous(), rays_d.contiguous()
+        for t in (sigma, tint, diffuse, specular, z_vals, dists, rays_d):
+            if not t.is_cuda:
+                raise RuntimeError("composite: CUDA tensors required (no CPU fallback)")
+        weights = torch.empty(R, S, dtype=f32, device=z_vals.device)
+        trans = torch.empty(R, S, dtype=f32, device=z_vals.device)
+        row = torch.zeros(R, _ROW, dtype=f32, device=z_vals.device)
+        rc = capi.lib().snrf_composite_fwd(ptr(sigma), ptr(tint), ptr(diffuse), ptr(specular),
+                                           c_int(1), c_int(3), c_int(3), c_int(3),
+                                           ptr(z_vals), ptr(dists), ptr(rays_d), c_int(R), c_int(S),
+                                           c_int(int(bool(infinity))), ptr(weights), ptr(trans), ptr(row), capi.stream())
+        capi.check(rc, "snrf_composite_fwd")
+        ctx.save_for_backward(sigma, tint, diffuse, specular, z_vals, dists, rays_d, trans)
+        ctx.infinity = bool(infinity)
+        return row, weights
+
+    @staticmethod
+    def backward(ctx, g_row, g_weights):
+        sigma, tint, diffuse, specular, z_vals, dists, rays_d, trans = ctx.saved_tensors
+        R, S = z_vals.shape
+        g_row = g_row.contiguous()
+        gw = g_weights.contiguous() if g_weights is not None else None
+        g_sigma = torch.empty_like(sigma)
+        g_tint = torch.empty_like(tint)
+        g_diffuse = torch.empty_like(diffuse)
+        g_specular = torch.empty_like(specular)
+        g_d = torch.empty_like(rays_d) if ctx.needs_input_grad[6] else None
+        rc = capi.lib().snrf_composite_bwd(ptr(sigma), ptr(tint), ptr(diffuse), ptr(specular),
+                                           c_int(1), c_int(3), c_int(3), c_int(3),
+                                           ptr(z_vals), ptr(dists), ptr(rays_d), ptr(trans), ptr(g_row),
+                                           ptr(gw) if gw is not None else c_void_p(0),
+                                           c_int(R), c_int(S), c_int(int(ctx.infinity)),
+                                           ptr(g_sigma), ptr(g_tint), ptr(g_diffuse), ptr(g_specular),
+                                           c_int(1), c_int(3), c_int(3), c_int(3),
+                                           ptr(g_d) if g_d is not None else c_void_p(0), capi.stream())
+        capi.check(rc, "snrf_composite_bwd")
+        return g_sigma, g_tint, g_diffuse, g_specular, None, None, g_d, None
+
+
+def composite(heads, z_vals, dists, rays_d, infinity, train):
+    """Same outputs as the tail of the reference's render_batch_rays (dict keys
+    diffuse, tint, specular, rgb, depth, T_left, weights [, l2_reg_specular])."""
+    row, weights = CompositeFn.apply(heads["sigma"], heads["tint"], heads["diffuse"], heads["specular"],
+                                     z_vals, dists, rays_d, infinity)
+    out = {"diffuse": row[:, 4:7], "tint": row[:, 1:4], "specular": row[:, 7:10]}
+    out["rgb"] = torch.clamp(out["diffuse"] + out["specular"], 0, 1)
+    out["depth"] = row[:, 0:1]
+    out["T_left"] = row[:, 13]
+    out["weights"] = weights[..., None]
+    if train:
+        out["l2_reg_specular"] = torch.mean(row[:, 10:13])
+    return out

@@ -86,3 +86,18 @@ def hash_indices(points, features, resolutions, block_corner=None, block_size=No
     idx = torch.zeros(B, L, 8, dtype=i32, device=points.device)
     _encode_fwd(points, out, features, block_corner, block_size, resolutions, idx_out=idx)
     return idx, out
+
+
+class Sampler:
+    """hashgrid/include/sampler.h:22-190 -- legacy bitmask sampler.  The reference constructs
+    one per HashGrid (hashgrid/__init__.py:68) but its build() call is commented out and
+    samplePoints is never reached; only construction has to work."""
+
+    def __init__(self, *args, **kwargs):
+        self.built = False
+
+    def build(self, *args, **kwargs):
+        raise NotImplementedError("hashgrid Sampler is dead code in the reference (build is never called)")
+
+    rebuild = build
+    samplePoints = build
