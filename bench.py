@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Headline benchmark: single-tile training rays/s (fwd + bwd + optimiser) of the ScaNeRF
+per-tile hot path at config/default.yaml shape, on N B200s (one tile per GPU, weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one pass of the hot path over one batch of 2^14 synthetic rays:
+  pose chain -> ray generation -> occupancy / inverse-z sample placement (128 + 128 per ray)
+  -> contraction -> 16-level hash encode -> decoder MLP -> compositing -> MSE
+  -> backward through all of it (incl. the analytic pose gradient) -> sparse Adam + Adam.
+`value`   : rays/s with the batches already resident in HBM (CUDA-event timed).
+`e2e`     : rays/s through TileStep.step(): pinned host batch in, python float loss out.
+`roofline`: the dominant kernel (hash-encode backward) timed live with CUDA events on its stream.
+`cpu_baseline` / --impl reference: the reference's math restated on the CPU (oracle/), timed on
+            this box's host cores on a bounded sample of the same workload.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = "scanerf-scalable-bundle-adjusting-neural-radiance-fields-for-large-scale-scene-rendering_b200"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+# ----------------------------------------------------------------------------- workload
+WORKLOADS = {
+    # BASELINE.json configs[1]: config/default.yaml single-tile training with pose refinement
+    "default.yaml-single-tile": dict(tile_corner=(0.0, 0.0, 0.0), tile_size=(20.0, 13.0, 30.0), log2T=24,
+                                     grid_resolution=(32, 8192), n_cam=64, H=540, W=960, fx=600.0,
+                                     batch_log2=14, S=128, S_bg=128, sampler_log2dim=4),
+    # BASELINE.json configs[0] shape (used by the CPU legs' bounded sample and by quick checks)
+    "c1-small": dict(tile_corner=(0.0, 0.0, 0.0), tile_size=(20.0, 13.0, 30.0), log2T=19,
+                     grid_resolution=(16, 512), n_cam=16, H=270, W=480, fx=300.0,
+                     batch_log2=12, S=64, S_bg=64, sampler_log2dim=4),
+}
+ENC_FWD_BYTES, ENC_BWD_BYTES = 1164, 2200      # algorithmic bytes per sample point, SURVEY.md section 8(d)
+
+
+def make_batches(cfg, n, gen):
+    """`n` batches of (locs [B,3] i32 = (view, px, py), gt [B,3] f32): the same 2x2-patch pixel
+    set for every camera, as TILE.train_one_step draws it (tile.py:902-915)."""
+    import torch
+    B = 2 ** cfg["batch_log2"]
+    per_cam = B // cfg["n_cam"]
+    n_patch = per_cam // 4
+    out = []
+    for _ in range(n):
+        px = torch.randperm(cfg["W"] - 2, generator=gen)[:n_patch]
+        py = torch.randperm(cfg["H"] - 2, generator=gen)[:n_patch]
+        x = torch.stack([px, px + 1, px, px + 1], -1).reshape(-1)
+        y = torch.stack([py, py, py + 1, py + 1], -1).reshape(-1)
+        view = torch.arange(cfg["n_cam"]).repeat_interleave(x.numel())
+        locs = torch.stack([view, x.repeat(cfg["n_cam"]), y.repeat(cfg["n_cam"])], -1).int()
+        gt = torch.rand(locs.shape[0], 3, generator=gen)
+        out.append((locs.contiguous(), gt.contiguous()))
+    return out
+
+
+def build_tile(cfg, dev, seed):
+    import torch
+    import scenes
+    from tile_step import TileStep
+    gen = torch.Generator().manual_seed(seed)
+    c = [cfg["tile_corner"][i] + cfg["tile_size"][i] * f for i, f in enumerate((0.5, 0.25, 0.5))]
+    Ks, c2w = scenes.camera_rig(cfg["n_cam"], cfg["H"], cfg["W"], gen, center=tuple(c),
+                                radius=0.3 * min(cfg["tile_size"][0], cfg["tile_size"][2]), fx=cfg["fx"])
+    tmp = tempfile.mkdtemp(prefix="snrf_bench_")
+    ply = os.path.join(tmp, "mesh.ply")
+    scenes.write_proxy_mesh_ply(ply, cfg["tile_corner"], cfg["tile_size"], seed=seed)
+    torch.manual_seed(seed)
+    step = TileStep(dev, cfg["tile_corner"], cfg["tile_size"], Ks, c2w, log2_hashmap_size=cfg["log2T"],
+                    grid_resolution=cfg["grid_resolution"], num_sample=cfg["S"], num_bg_sample=cfg["S_bg"],
+                    mesh_path=ply, sampler_log2dim=cfg["sampler_log2dim"], global_step=10000)
+    return step, gen
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def summary(self, t0, t1):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mx = max(mx, int(float(f[1])))
+                if t0 <= t <= t1:
+                    sm.append(int(float(f[0])))
+                    reasons |= {n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")}
+            except ValueError:
+                continue
+        return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU legs
+class CpuPort:
+    """The reference's math on the CPU (oracle/: C hash encode + torch MLP / compositing,
+    fwd + bwd incl. grad_features and grad_points) on `rays` rays of the workload."""
+
+    def __init__(self, cfg, rays, threads):
+        import torch
+        from oracle import torch_ref as tr
+        self.tr, self.cfg, self.rays = tr, cfg, rays
+        os.environ["ORACLE_THREADS"] = str(threads)
+        torch.set_num_threads(threads)
+        gen = torch.Generator().manual_seed(0)
+        L, T = 16, 2 ** cfg["log2T"]
+        size = torch.tensor(cfg["tile_size"]) * 2.0
+        aspect = size / size.min()
+        self.res = tr.resolution_ladder((aspect * cfg["grid_resolution"][0]).int(), (aspect * cfg["grid_resolution"][1]).int())
+        self.table = (torch.randn(L, T, 2, generator=gen) * 1e-2).requires_grad_(True)
+        self.mlp = {k: v.requires_grad_(True) for k, v in tr.init_mlp(gen).items()}
+        center = torch.tensor(cfg["tile_corner"]) + torch.tensor(cfg["tile_size"]) / 2
+        self.size, self.min_bbox = size, center - size / 2
+        self.o = center + (torch.rand(rays, 3, generator=gen) - 0.5) * torch.tensor(cfg["tile_size"]) * 0.5
+        self.d = torch.nn.functional.normalize(torch.randn(rays, 3, generator=gen), dim=-1)
+        S, Sb = cfg["S"], cfg["S_bg"]
+        self.z_f = torch.linspace(0.05, 0.45, S)[None] * float(min(cfg["tile_size"])) * torch.ones(rays, 1)
+        self.d_f = torch.full_like(self.z_f, float(self.z_f[0, 1] - self.z_f[0, 0]))
+        self.z_b, self.d_b, _ = tr.inverse_z_sampling(self.o, self.d, center, size, Sb, False)
+        self.target = torch.rand(rays, 3, generator=gen)
+
+    def step(self):
+        """One fwd+bwd pass; returns seconds."""
+        import torch
+        tr = self.tr
+        t0 = time.perf_counter()
+        o_ = self.o.clone().requires_grad_(True)
+        fg, _ = tr.render_batch_rays(self.table, self.res, self.mlp, o_, self.d, self.z_f, self.d_f, self.min_bbox,
+                                     self.size, 10000, False, False)
+        bg, _ = tr.render_batch_rays(self.table, self.res, self.mlp, o_, self.d, self.z_b, self.d_b, self.min_bbox,
+                                     self.size, 10000, True, True)
+        rgb = fg["rgb"] + fg["T_left"][:, None] * bg["rgb"]
+        loss = torch.mean((rgb - self.target) ** 2) + 0.01 * (fg["l2_reg_specular"] + bg["l2_reg_specular"])
+        loss.backward()
+        dt = time.perf_counter() - t0
+        self.table.grad = None
+        return dt
+
+
+def run_reference(args, cfg, name):
+    """--impl reference: the reference's CUDA extensions have no CPU build, so its CPU arm is the
+    restatement under oracle/ (kind "port"), all host threads, a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    rays = 256
+    from oracle import native as on
+    on.build()
+    port = CpuPort(cfg, rays, cores)
+    ts = []
+    for i in range(args.warmup + args.steps):
+        t = port.step()
+        if i >= args.warmup:
+            ts.append(t)
+    sec = sum(ts) / len(ts)
+    v = rays / sec
+    print(json.dumps({
+        "impl": "reference", "metric": "train rays/s (fwd+bwd)", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "sample": f"{rays} rays x {cfg['S']}+{cfg['S_bg']} samples per step, T=2^{cfg['log2T']}"},
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"{rays} rays x {cfg['S'] + cfg['S_bg']} samples, fwd+bwd, C hash encode + torch MLP/composite"},
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ----------------------------------------------------------------------------- main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="default.yaml-single-tile", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg, name = WORKLOADS[args.workload], args.workload
+    if args.impl == "reference":
+        return run_reference(args, cfg, name)
+
+    import torch
+    import torch.distributed as dist
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = importlib.import_module(PKG)
+    pkg.install()
+    import scanerf_b200_capi as capi
+
+    # one tile per GPU (the reference's own decomposition: admm_trainer.py:74-83); no data-path collective
+    step, gen = build_tile(cfg, dev, seed=rank)
+    K, Wm = args.steps, args.warmup
+    host = [(l.pin_memory(), g.pin_memory()) for l, g in make_batches(cfg, Wm + K, gen)]
+    devb = [(l.to(dev), g.to(dev)) for l, g in host]
+    B = host[0][0].shape[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, batches):
+        for b in batches[:Wm]:
+            fn(*b)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for b in batches[Wm:]:
+            fn(*b)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, t0, time.time()
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    # (1) device-resident inputs
+    capi.launch_count = 0
+    ms_dev, t0, t1 = timed(step.step_device, devb)
+    launches = capi.launch_count
+    # (2) end to end: pinned host in, loss float out
+    ms_e2e, _, t2 = timed(step.step, host)
+    clk = clocks.summary(t0, t2) if clocks else None
+    # (3) the dominant kernel, timed live on its stream over the same steps
+    capi.time_calls("snrf_hash_bwd")
+    for b in devb[Wm:]:
+        step.step_device(*b)
+    torch.cuda.synchronize()
+    k_ms, k_units = capi.timed_results()
+    capi.time_calls(None)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    n_launch = max(len(k_ms), 1)
+    avg_ms = sum(k_ms) / n_launch if k_ms else float("nan")
+    alg_bytes = ENC_BWD_BYTES * (sum(k_units) / n_launch if k_units else 0)
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if k_ms else float("nan")
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("snrf_hash_bwd")
+    except Exception:
+        pass
+    line = {
+        "metric": "train rays/s (fwd+bwd)", "value": world * K * B / (ms_dev * 1e-3), "unit": "rays/s", "n_gpus": world,
+        "steps": K, "warmup": Wm, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "tiles_per_gpu": 1, "rays_per_step": B, "samples_per_ray": cfg["S"] + cfg["S_bg"],
+                   "hash_table": f"16 x 2^{cfg['log2T']} x 2 f32", "cameras": cfg["n_cam"], "pose_refinement": True,
+                   "l2_policy": "inputs larger than L2 (2 GiB table + 2 GiB gradient, random gathers)"},
+        "e2e": {"value": world * K * B / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": B * 3 * 4 * 2,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"kernel": "hash_bwd_kernel (snrf_hash_bwd)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "avg_launch_ms": avg_ms, "launches_timed": len(k_ms), "alg_bytes_per_launch": alg_bytes,
+                     "share_of_step": (sum(k_ms) / K) / (ms_dev / K) if k_ms else None},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        from oracle import native as on
+        on.build()
+        rays = 1024
+        sec = CpuPort(cfg, rays, cores).step()
+        line["cpu_baseline"] = {"value": rays / sec, "unit": "rays/s", "cores": cores, "kind": "port",
+                                "sample": f"{rays} rays x {cfg['S'] + cfg['S_bg']} samples of the same workload, fwd+bwd, "
+                                          f"one pass ({sec:.1f} s)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -95,6 +95,18 @@ int snrf_composite_bwd(const float* sigma, const float* tint, const float* diffu
                        int gs_sigma, int gs_tint, int gs_diffuse, int gs_specular,
                        float* grad_rays_d, void* stream);
 
+/* ---- sparse Adam -------------------------------------------------------------- */
+/* cuda/include/adam.h (adam_step_cuda: half_state=0, adam_step_cuda_fp16: half_state=1; kernels
+ * cuda/adam_kernel.cu:23-69, 97-144).  Element (k,d), k<rows, d<dim, lives at k*row_stride+d
+ * (the reference hard-codes row_stride 8).  Elements whose gradient is exactly 0 are skipped.
+ * exp_avg / exp_avg_sq are f32 (half_state=0) or f16 scaled by 128 / 128^2 (half_state=1).
+ * `step` is the 1-based step used in the bias corrections (the reference passes step+1).
+ * zero_grad != 0 clears every consumed gradient in the same pass (extension). */
+int snrf_adam_step(float* params, float* grads, void* exp_avg, void* exp_avg_sq,
+                   long long rows, int dim, int row_stride, int half_state,
+                   float lr, float beta1, float beta2, float eps, int step, int zero_grad,
+                   void* stream);
+
 /* ---- mesh ingest (host) ------------------------------------------------------- */
 /* cuda/include/voxelize.h:12-119 (voxelize_mesh): ALL pointers are host pointers.
  * log2dim[3], corner[3], size[3]; vis / outside: bytes [2^lx * 2^ly * 2^lz]. */

@@ -123,3 +123,15 @@ def sample_insideout(rays_o, rays_d, S, Sbg, center, size, far):
     miss = lib().oracle_sample_insideout(_p(rays_o), _p(rays_d), ctypes.c_int(S), ctypes.c_int(Sbg), _p(center),
                                          _p(size), ctypes.c_float(far), _p(z), _p(zb), ctypes.c_int(B))
     return z, zb, miss
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, row_stride=None, half_state=False):
+    """In-place on float32 copies; returns (params, exp_avg, exp_avg_sq).  params [K,D]."""
+    p, g = _f32(params).copy(), _f32(grads)
+    m, v = _f32(exp_avg).copy(), _f32(exp_avg_sq).copy()
+    K, D = p.shape
+    rs = D if row_stride is None else row_stride
+    lib().oracle_adam_step(_p(p), _p(g), _p(m), _p(v), ctypes.c_longlong(K), ctypes.c_int(D), ctypes.c_int(rs),
+                           ctypes.c_int(int(half_state)), ctypes.c_float(lr), ctypes.c_float(beta1),
+                           ctypes.c_float(beta2), ctypes.c_float(eps), ctypes.c_int(step))
+    return p, m, v

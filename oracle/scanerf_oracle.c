@@ -467,3 +467,49 @@ ORACLE_API int oracle_sample_insideout(const float *rays_o, const float *rays_d,
     }
     return misses;
 }
+
+/* ------------------------------------------------------------------------- */
+/* 6. sparse Adam                                                             */
+/* ------------------------------------------------------------------------- */
+
+/* cuda/adam_kernel.cu:23-69 (adam_step_kernel): element (k,d) at k*row_stride+d (the reference
+ * hard-codes 8); grad == 0 -> skipped; `step` is the value the kernel sees (host passes step+1).
+ * half_state != 0 restates adam_step_fp16_kernel (:97-144) with the moments passed as floats
+ * that the caller rounds to half (state arrays here are float; rounding is applied in place). */
+static float round_to_half(float x)
+{
+    /* IEEE binary16 round-to-nearest-even of a float, returned as float */
+    _Float16 h = (_Float16)x;
+    return (float)h;
+}
+
+ORACLE_API void oracle_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
+                                 long long rows, int dim, int row_stride, int half_state,
+                                 float lr, float beta1, float beta2, float eps, int step)
+{
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2 = 1.0f - powf(beta2, (float)step);
+    for (long long k = 0; k < rows; ++k)
+        for (int d = 0; d < dim; ++d) {
+            const long long i = k * row_stride + d;
+            if (!half_state) {
+                const float g = grads[i];
+                if (g == 0.0f) continue;
+                const float m = beta1 * exp_avg[i] + (1.0f - beta1) * g;
+                const float v = beta2 * exp_avg_sq[i] + (1.0f - beta2) * g * g;
+                const float denom = sqrtf(v / bc2) + eps;
+                const float step_size = lr / bc1;
+                params[i] = params[i] - step_size * m / denom;
+                exp_avg[i] = m; exp_avg_sq[i] = v;
+            } else {
+                const float g = grads[i] * 128.0f;
+                if (g == 0.0f) continue;
+                const float m = beta1 * exp_avg[i] + (1.0f - beta1) * g;
+                const float v = beta2 * exp_avg_sq[i] + (1.0f - beta2) * g * g;
+                const float denom = sqrtf(v / (bc2 * 128.0f * 128.0f)) + eps;
+                const float step_size = lr / bc1;
+                params[i] = params[i] - step_size * m / (denom * 128.0f);
+                exp_avg[i] = round_to_half(m); exp_avg_sq[i] = round_to_half(v);
+            }
+        }
+}

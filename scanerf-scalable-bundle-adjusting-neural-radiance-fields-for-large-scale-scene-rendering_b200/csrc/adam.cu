@@ -1,0 +1,151 @@
+// Sparse Adam step over the entries that received gradient, sm_100a.
+//
+// Replaces (behaviour, not code) the reference operators
+//   adam_step_cuda / adam_step_cuda_fp16      cuda/adam_kernel.cu:72-94, 147-168
+// whose semantics are: an element whose gradient is exactly 0 is skipped (its moments do
+// not decay); otherwise
+//   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g
+//   p -= (lr / (1-b1^t)) * m / (sqrt(v / (1-b2^t)) + eps)
+// The fp16 variant keeps m, v in half scaled by 128 / 128^2 (LOSS_SCALE).
+//
+// Design (B200): pure HBM streaming, 28 B per touched float (p,g,m,v read; p,m,v written)
+// and 4 B per untouched one.  One thread owns 4 consecutive floats (128-bit accesses when
+// the row layout allows), the two bias corrections are evaluated once per CTA instead of
+// two powf per element, and the gradient can be cleared in the same pass (`zero_grad`) so
+// the next backward needs no 2 GiB memset of the hash-table gradient.  The reference
+// addresses element (k, d) at k*8 + d whatever D is (cuda/adam_kernel.cu:43); the C ABI
+// takes the row stride explicitly so both that layout and dense [.., D] tensors work.
+#include "common.cuh"
+#include <cuda_fp16.h>
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr float kLossScale = 128.0f;
+
+struct Hyper { float lr, b1, b2, eps; int step; };
+
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, const Hyper& h, float bc1, float bc2)
+{
+    const float mi = h.b1 * m + (1.0f - h.b1) * g;
+    const float vi = h.b2 * v + (1.0f - h.b2) * g * g;
+    const float denom = sqrtf(vi / bc2) + h.eps;
+    const float step_size = h.lr / bc1;
+    p = p - step_size * mi / denom;
+    m = mi; v = vi;
+}
+
+// dense, contiguous: n floats, n % 4 == 0 handled by the vector body + scalar tail
+__global__ void __launch_bounds__(kThreads)
+adam_dense_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                  long long n, Hyper h, int zero_grad)
+{
+    __shared__ float s_bc[2];
+    if (threadIdx.x == 0) {
+        s_bc[0] = 1.0f - powf(h.b1, (float)h.step);
+        s_bc[1] = 1.0f - powf(h.b2, (float)h.step);
+    }
+    __syncthreads();
+    const float bc1 = s_bc[0], bc2 = s_bc[1];
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 gg = reinterpret_cast<const float4*>(g)[i];
+        if (gg.x == 0.0f && gg.y == 0.0f && gg.z == 0.0f && gg.w == 0.0f) continue;
+        float4 pp = reinterpret_cast<float4*>(p)[i];
+        float4 mm = reinterpret_cast<float4*>(m)[i];
+        float4 vv = reinterpret_cast<float4*>(v)[i];
+        if (gg.x != 0.0f) adam_elem(pp.x, gg.x, mm.x, vv.x, h, bc1, bc2);
+        if (gg.y != 0.0f) adam_elem(pp.y, gg.y, mm.y, vv.y, h, bc1, bc2);
+        if (gg.z != 0.0f) adam_elem(pp.z, gg.z, mm.z, vv.z, h, bc1, bc2);
+        if (gg.w != 0.0f) adam_elem(pp.w, gg.w, mm.w, vv.w, h, bc1, bc2);
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+        if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // tail
+    for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gi = g[i];
+        if (gi == 0.0f) continue;
+        float pi = p[i], mi = m[i], vi = v[i];
+        adam_elem(pi, gi, mi, vi, h, bc1, bc2);
+        p[i] = pi; m[i] = mi; v[i] = vi;
+        if (zero_grad) g[i] = 0.0f;
+    }
+}
+
+// rows x dim elements at k*row_stride + d (the reference's K x 8 addressing)
+template <bool HALF_STATE>
+__global__ void __launch_bounds__(kThreads)
+adam_strided_kernel(float* __restrict__ p, float* __restrict__ g, void* __restrict__ m_v, void* __restrict__ v_v,
+                    long long rows, int dim, int row_stride, Hyper h, int zero_grad)
+{
+    __shared__ float s_bc[2];
+    if (threadIdx.x == 0) {
+        s_bc[0] = 1.0f - powf(h.b1, (float)h.step);
+        s_bc[1] = 1.0f - powf(h.b2, (float)h.step);
+    }
+    __syncthreads();
+    const float bc1 = s_bc[0], bc2 = s_bc[1];
+    const long long n = rows * dim;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long k = t / dim;
+        const int d = (int)(t - k * dim);
+        const long long i = k * row_stride + d;
+        if (!HALF_STATE) {
+            const float gi = g[i];
+            if (gi == 0.0f) continue;
+            float* m = (float*)m_v; float* v = (float*)v_v;
+            float pi = p[i], mi = m[i], vi = v[i];
+            adam_elem(pi, gi, mi, vi, h, bc1, bc2);
+            p[i] = pi; m[i] = mi; v[i] = vi;
+        } else {
+            // cuda/adam_kernel.cu:97-144: gradient pre-scaled by 128, state stored in half
+            const float gi = g[i] * kLossScale;
+            if (gi == 0.0f) continue;
+            __half* m = (__half*)m_v; __half* v = (__half*)v_v;
+            const float mi = h.b1 * __half2float(m[i]) + (1.0f - h.b1) * gi;
+            const float vi = h.b2 * __half2float(v[i]) + (1.0f - h.b2) * gi * gi;
+            const float denom = sqrtf(vi / (bc2 * kLossScale * kLossScale)) + h.eps;
+            const float step_size = h.lr / bc1;
+            p[i] = p[i] - step_size * mi / (denom * kLossScale);
+            m[i] = __float2half(mi);
+            v[i] = __float2half(vi);
+        }
+        if (zero_grad) g[i] = 0.0f;
+    }
+}
+
+inline int grid_for(long long work)
+{
+    long long gx = (work + kThreads - 1) / kThreads;
+    const long long cap = (long long)snrf_sm_count() * 16;
+    if (gx > cap) gx = cap;
+    return gx > 0 ? (int)gx : 1;
+}
+
+}  // namespace
+
+// ------------------------------- C ABI --------------------------------------
+SNRF_API int snrf_adam_step(float* params, float* grads, void* exp_avg, void* exp_avg_sq,
+                            long long rows, int dim, int row_stride, int half_state,
+                            float lr, float beta1, float beta2, float eps, int step, int zero_grad,
+                            void* stream)
+{
+    SNRF_CHECK_ARG(rows >= 0 && dim > 0 && row_stride >= dim, "snrf_adam_step: need rows>=0, 0<dim<=row_stride (rows=%lld dim=%d stride=%d)", rows, dim, row_stride);
+    SNRF_CHECK_ARG(step >= 1, "snrf_adam_step: step counts from 1 (got %d)", step);
+    if (rows == 0) return 0;
+    const Hyper h{lr, beta1, beta2, eps, step};
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long n = rows * dim;
+    const bool aligned = ((((uintptr_t)params) | ((uintptr_t)grads) | ((uintptr_t)exp_avg) | ((uintptr_t)exp_avg_sq)) & 15) == 0;
+    if (!half_state && row_stride == dim && aligned) {
+        adam_dense_kernel<<<grid_for((n + 3) / 4), kThreads, 0, s>>>(params, grads, (float*)exp_avg, (float*)exp_avg_sq, n, h, zero_grad);
+    } else if (half_state) {
+        adam_strided_kernel<true><<<grid_for(n), kThreads, 0, s>>>(params, grads, exp_avg, exp_avg_sq, rows, dim, row_stride, h, zero_grad);
+    } else {
+        adam_strided_kernel<false><<<grid_for(n), kThreads, 0, s>>>(params, grads, exp_avg, exp_avg_sq, rows, dim, row_stride, h, zero_grad);
+    }
+    SNRF_RETURN_LAUNCH("snrf_adam_step");
+}

@@ -134,3 +134,43 @@ def voxelize_mesh(log2dim, corner, size, model_path, vis, init_out, outside):
         vis.copy_(v)
     if o is not outside:
         outside.copy_(o)
+
+
+def _adam(params, grad_params, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, half_state, zero_grad=False,
+          dense=False):
+    p = Out(params, f32, "params")
+    g = Out(grad_params, f32, "grad_params")
+    st = torch.float16 if half_state else f32
+    m, v = Out(exp_avg, st, "exp_avg"), Out(exp_avg_sq, st, "exp_avg_sq")
+    if dense:
+        rows, dim, stride = params.numel(), 1, 1
+    else:
+        rows, dim = int(params.shape[0]), int(params.shape[1])
+        # the reference addresses element (k, d) at k*8 + d whatever D is (adam_kernel.cu:43);
+        # that is only in-bounds / meaningful for D == 8, any other D is treated as dense rows
+        stride = 8 if dim == 8 else dim
+    capi.check(capi.lib().snrf_adam_step(p.ptr, g.ptr, m.ptr, v.ptr, ctypes.c_longlong(rows), c_int(dim), c_int(stride),
+                                         c_int(int(half_state)), c_float(lr), c_float(beta1), c_float(beta2),
+                                         c_float(eps), c_int(int(step)), c_int(int(zero_grad)), capi.stream()),
+               "snrf_adam_step")
+    p.done(); m.done(); v.done()
+    if zero_grad:
+        g.done()
+
+
+def adam_step_cuda(params, grad_params, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step):
+    """cuda/include/adam.h -- sparse Adam on params [K,D]: elements with grad == 0 are skipped.
+    As in the reference the bias corrections use step+1 and the caller's int is not updated
+    (pybind passes Python ints by value: cuda/adam_kernel.cu:78,83)."""
+    _adam(params, grad_params, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, int(step) + 1, False)
+
+
+def adam_step_cuda_fp16(params, grad_params, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step):
+    """cuda/include/adam.h -- as adam_step_cuda with half moments scaled by 128 / 128^2."""
+    _adam(params, grad_params, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, int(step) + 1, True)
+
+
+def adam_step_sparse(params, grad_params, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, zero_grad=True):
+    """Extension: the same update over a tensor of ANY shape (dense addressing, 128-bit
+    accesses), `step` 1-based, optionally clearing the consumed gradients in the same pass."""
+    _adam(params, grad_params, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, int(step), False, zero_grad, dense=True)

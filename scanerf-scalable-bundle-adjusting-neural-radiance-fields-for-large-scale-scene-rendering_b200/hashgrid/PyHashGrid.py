@@ -7,6 +7,14 @@ from .lib.HASHGRID import embedding_forward_cuda, embedding_backward_cuda  # noq
 class HashEmbeddingAutoGrad(_EncodeFn):
     """autograd.Function(points, features, block_corner, block_size, resolution) -- PyHashGrid.py:9-32."""
 
+    @staticmethod
+    def forward(ctx, points, features, block_corner, block_size, resolution):
+        return _EncodeFn.forward(ctx, points, features, block_corner, block_size, resolution)
+
+    @staticmethod
+    def backward(ctx, grad_in):
+        return _EncodeFn.backward(ctx, grad_in)[:5]
+
 
 def HashEmbedding(points, features, block_corner, block_size, resolution):
     return HashEmbeddingAutoGrad.apply(points, features, block_corner, block_size, resolution)

@@ -13,7 +13,7 @@ class HashEmbeddingBGAutoGrad(_EncodeFn):
 
     @staticmethod
     def backward(ctx, grad_in):
-        gp, gf, _, _, _ = _EncodeFn.backward(ctx, grad_in)
+        gp, gf = _EncodeFn.backward(ctx, grad_in)[:2]
         return gp, gf, None
 
 

@@ -16,11 +16,12 @@ class _EncodeFn(torch.autograd.Function):
     contracted-space (BG) variant."""
 
     @staticmethod
-    def forward(ctx, points, features, block_corner, block_size, resolution):
+    def forward(ctx, points, features, block_corner, block_size, resolution, direct_grad=False):
         out = torch.zeros((points.shape[0], features.shape[0], 2), dtype=torch.float32, device=points.device)
         _ops._encode_fwd(points, out, features, block_corner, block_size, resolution)
         ctx.bbox = block_corner is not None
         ctx.block_size = block_size
+        ctx.direct_grad = bool(direct_grad)
         if ctx.bbox:
             ctx.save_for_backward(points, features, resolution, block_corner)
         else:
@@ -37,9 +38,16 @@ class _EncodeFn(torch.autograd.Function):
             corner = size = None
         need_p = ctx.needs_input_grad[0]
         grad_points = torch.zeros_like(points) if need_p else None
+        if ctx.direct_grad and features.is_leaf and features.requires_grad:
+            # Scatter straight into the parameter's .grad (the kernel accumulates): no 2 GiB
+            # zeros_like + no dense `grad += new` pass per call as in PyHashGridBG.py:27-28.
+            if features.grad is None:
+                features.grad = torch.zeros_like(features)
+            _ops._encode_bwd(points, grad_out.contiguous(), grad_points, features.grad, features, corner, size, resolution)
+            return grad_points, None, None, None, None, None
         grad_features = torch.zeros_like(features)
         _ops._encode_bwd(points, grad_out.contiguous(), grad_points, grad_features, features, corner, size, resolution)
-        return grad_points, grad_features, None, None, None
+        return grad_points, grad_features, None, None, None, None
 
 
 def resolution_ladder(base_resolution, finest_resolution, n_levels):
@@ -54,6 +62,9 @@ def resolution_ladder(base_resolution, finest_resolution, n_levels):
 
 class _HashGridBase(nn.Module):
     _bbox_variant = False
+    # module calls accumulate the table gradient directly into features.grad (see _EncodeFn.backward);
+    # the reference-named autograd Functions keep returning a dense grad_features tensor
+    direct_grad = True
 
     def __init__(self, device, bbox_corner, bbox_size, n_levels=16, n_features_per_level=2,
                  log2_hashmap_size=19, base_resolution=16, finest_resolution=512, init_mode="xavier"):
@@ -94,7 +105,7 @@ class _HashGridBase(nn.Module):
                 size = torch.full((3,), float(size), dtype=torch.float32, device=pts.device)
             elif size.numel() == 1:
                 size = size.reshape(1).repeat(3).to(torch.float32)
-            out = _EncodeFn.apply(pts, self.features, self.bbox_corner, size, self.resolution)
+            out = _EncodeFn.apply(pts, self.features, self.bbox_corner, size, self.resolution, self.direct_grad)
         else:
-            out = _EncodeFn.apply(pts, self.features, None, None, self.resolution)
+            out = _EncodeFn.apply(pts, self.features, None, None, self.resolution, self.direct_grad)
         return out.reshape(*lead, self.out_dim)

@@ -19,8 +19,62 @@ c_int = ctypes.c_int
 c_float = ctypes.c_float
 
 
+# --- instrumentation used by bench.py: launch counter and per-entry-point CUDA-event timing
+launch_count = 0            # C-ABI calls that launched a kernel since last reset
+_timed_name = None          # entry point being timed (None = off)
+_timed_events = []          # [(start_event, end_event, units)]
+_UNITS_ARG = {"snrf_hash_fwd": 7, "snrf_hash_bwd": 8, "snrf_field_fwd": 0, "snrf_field_bwd": 0}
+_HOST_ONLY = {"snrf_last_error", "snrf_version", "snrf_device_sm_count", "snrf_hash_set_levels_per_block",
+              "snrf_voxelize_mesh_host"}
+
+
+class _Lib:
+    """Thin proxy over the CDLL: counts kernel-launching calls and, when asked, brackets one
+    entry point with CUDA events on the current stream."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._cdll, name)
+            if name in _HOST_ONLY:
+                fn = raw
+            else:
+                def fn(*args, _raw=raw, _name=name):
+                    global launch_count
+                    launch_count += 1
+                    if _timed_name == _name:
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record()
+                        rc = _raw(*args)
+                        b.record()
+                        u = args[_UNITS_ARG[_name]] if _name in _UNITS_ARG else 0
+                        _timed_events.append((a, b, int(getattr(u, "value", u))))
+                        return rc
+                    return _raw(*args)
+            self._cache[name] = fn
+        return fn
+
+
+def time_calls(name):
+    """Start (name) or stop (None) CUDA-event timing of one C-ABI entry point."""
+    global _timed_name
+    _timed_name = name
+    if name is not None:
+        _timed_events.clear()
+
+
+def timed_results():
+    """([ms per launch], [units per launch]) of the calls timed since time_calls(name); synchronises."""
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b, _ in _timed_events], [u for _, _, u in _timed_events]
+
+
 def lib():
-    """Load (once) and return the CDLL.  Raises loudly when the build is missing."""
+    """Load (once) and return the library.  Raises loudly when the build is missing."""
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
@@ -28,8 +82,9 @@ def lib():
                 f"scanerf_b200: native library not found at {LIB_PATH}. "
                 "Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(or `make -C <package>/csrc`). There is no CPU / PyTorch fallback.")
-        _lib = ctypes.CDLL(LIB_PATH)
-        _lib.snrf_last_error.restype = ctypes.c_char_p
+        cdll = ctypes.CDLL(LIB_PATH)
+        cdll.snrf_last_error.restype = ctypes.c_char_p
+        _lib = _Lib(cdll)
     return _lib
 
 

@@ -1,0 +1,197 @@
+"""Host-side mirror of the reference's per-tile training step, reduced to the hot path:
+TILE.render_rays (tile.py:639-692) and the RGB-loss part of TILE.train_one_step
+(tile.py:880-1015), with the reference's optimiser settings (tile.py:299-343).
+
+Everything numeric runs in the sm_100a kernels of libscanerf_b200.so:
+  ray generation + analytic pose gradient   csrc/rays.cu       (compute_ray_forward/backward)
+  occupancy-bounded sample placement        csrc/rays.cu       (sample_points_grid, ray_aabb)
+  hash encode fwd/bwd, decoder, compositing HashGrid.render_*_rays (csrc/hash_encode.cu, field, composite)
+  sparse Adam over touched table entries    csrc/adam.cu       (vdbAdam)
+The se(3) chain on the [N_cam, 6] pose parameters stays in torch (a few hundred floats).
+This class is what bench.py and smoke() drive; `tile.py` itself drives the same HashGrid
+methods unchanged.
+"""
+import torch
+import torch.nn as nn
+
+import scanerf_b200_capi as capi  # noqa: F401  (fails loudly when the native library is missing)
+from cuda import compute_ray_backward, compute_ray_forward
+from hashgrid import HashGrid, TRAIN, INFERENCE
+from hashgrid._decoder import ShallowMLP
+from vdbAdam import vdbAdam
+
+
+# ----------------------------------------------------------------------------- se(3)
+def _taylor(x, kind, nth=10):
+    """camera.py:118-141: Taylor series of sin(x)/x, (1-cos x)/x^2, (x-sin x)/x^3."""
+    ans = torch.zeros_like(x)
+    denom = 1.0
+    for i in range(nth + 1):
+        if kind == "A":
+            if i > 0:
+                denom *= (2 * i) * (2 * i + 1)
+        elif kind == "B":
+            denom *= (2 * i + 1) * (2 * i + 2)
+        else:
+            denom *= (2 * i + 2) * (2 * i + 3)
+        ans = ans + (-1) ** i * x ** (2 * i) / denom
+    return ans
+
+
+def se3_to_SE3(wu):
+    """camera.py:84-95: [N,6] (rotation, translation generators) -> [N,3,4]."""
+    w, u = wu.split([3, 3], dim=-1)
+    w0, w1, w2 = w.unbind(-1)
+    O = torch.zeros_like(w0)
+    wx = torch.stack([torch.stack([O, -w2, w1], -1), torch.stack([w2, O, -w0], -1), torch.stack([-w1, w0, O], -1)], -2)
+    theta = w.norm(dim=-1)[..., None, None]
+    eye = torch.eye(3, device=wu.device)
+    A, B, C = _taylor(theta, "A"), _taylor(theta, "B"), _taylor(theta, "C")
+    R = eye + A * wx + B * wx @ wx
+    V = eye + B * wx + C * wx @ wx
+    return torch.cat([R, V @ u[..., None]], -1)
+
+
+def pose_invert(p):
+    """camera.py:37-43"""
+    R, t = p[..., :3], p[..., 3:]
+    Ri = R.transpose(-1, -2)
+    return torch.cat([Ri, -Ri @ t], -1)
+
+
+def pose_compose(a, b):
+    """camera.py:45-60 for two poses: x -> b(a(x))."""
+    Ra, ta, Rb, tb = a[..., :3], a[..., 3:], b[..., :3], b[..., 3:]
+    return torch.cat([Rb @ Ra, Rb @ ta + tb], -1)
+
+
+class RayGenFn(torch.autograd.Function):
+    """(c2w [N,3,4], Ks [N,3,3], locs [B,3] i32 = (view, px, py)) -> rays_o, rays_d [B,3];
+    backward = the analytic bundle-adjustment gradient dL/dc2w (cuda/compute_ray_kernel.cu:45-92
+    semantics with the ray-indexed gradients)."""
+
+    @staticmethod
+    def forward(ctx, c2w, Ks, locs):
+        B = locs.shape[0]
+        rays_o = torch.empty(B, 3, dtype=torch.float32, device=c2w.device)
+        rays_d = torch.empty(B, 3, dtype=torch.float32, device=c2w.device)
+        compute_ray_forward(rays_o, rays_d, Ks.reshape(-1, 9), c2w.reshape(-1, 12), locs)
+        ctx.save_for_backward(Ks, locs)
+        ctx.n = c2w.shape[0]
+        return rays_o, rays_d
+
+    @staticmethod
+    def backward(ctx, g_o, g_d):
+        Ks, locs = ctx.saved_tensors
+        g = torch.zeros(ctx.n, 12, dtype=torch.float32, device=Ks.device)
+        compute_ray_backward(g_o.contiguous(), g_d.contiguous(), Ks.reshape(-1, 9), g, locs)
+        return g.reshape(ctx.n, 3, 4), None, None
+
+
+class Poses(nn.Module):
+    """camera_utils.CAM (camera_utils.py:40-89): w2c = se3_to_SE3(se3_refine) o (noise o ori_w2c)."""
+
+    def __init__(self, Ks, c2ws, device, noise=None):
+        super().__init__()
+        self.device = device
+        self.num_camera = c2ws.shape[0]
+        self.ori_rts = pose_invert(c2ws.to(device))
+        self.se3_refine = nn.Parameter(torch.zeros(self.num_camera, 6, dtype=torch.float32, device=device))
+        self.rts = self.ori_rts.clone() if noise is None else pose_compose(se3_to_SE3(noise.to(device)), self.ori_rts)
+        self.ks = Ks.to(device).contiguous()
+
+    def get_rts(self):
+        return pose_compose(se3_to_SE3(self.se3_refine), self.rts)
+
+    def rays(self, locs):
+        return RayGenFn.apply(pose_invert(self.get_rts()).contiguous(), self.ks, locs)
+
+
+class TileStep:
+    """One tile: field + decoder + poses + optimisers, and the training step over one ray batch."""
+
+    def __init__(self, device, tile_corner, tile_size, Ks, c2ws, log2_hashmap_size=24, grid_resolution=(32, 8192),
+                 num_sample=128, num_bg_sample=128, mesh_path="", sampler_log2dim=4, pose_noise=None,
+                 lr_table=1e-3, lr_decoder=1e-3, lr_cam=1e-4, global_step=10000, invalid_underground=False,
+                 dense_table_adam=False):
+        self.device = device
+        f = lambda v: torch.as_tensor(v, dtype=torch.float32, device=device)
+        self.featureGrid = HashGrid(device, f(tile_corner), f(tile_size), log2_hashmap_size, list(grid_resolution),
+                                    sampler_log2dim, False, mesh_path)
+        self.decoder = ShallowMLP(32).to(device)
+        self.poses = Poses(Ks, c2ws, device, pose_noise)
+        self.num_sample, self.num_bg_sample = num_sample, num_bg_sample
+        self.global_step = global_step
+        self.invalid_underground = invalid_underground
+        if dense_table_adam:     # what tile.py:301 does: dense torch Adam over the whole table
+            self.featureGrid_optimizer = torch.optim.Adam(
+                [{"params": self.featureGrid.parameters(), "lr": lr_table, "betas": (0.9, 0.99), "eps": 1e-15}])
+        else:                    # sparse update of the touched entries only, gradient cleared in the same pass
+            self.featureGrid_optimizer = vdbAdam(list(self.featureGrid.parameters()), lr=lr_table, betas=(0.9, 0.99),
+                                                 eps=1e-15, bias_correction="standard", fused_zero_grad=True)
+        self.optimizer = torch.optim.Adam([
+            {"params": self.decoder.parameters(), "lr": lr_decoder, "weight_decay": 1e-6},
+            {"params": self.poses.se3_refine, "lr": lr_cam}])
+
+    # tile.py:639-692
+    def render_rays(self, rays_o, rays_d, occlusion_mask=None, mode=TRAIN):
+        fg, ret_fg = self.featureGrid.render_fore_rays(rays_o, rays_d, self.num_sample, self.decoder, mode,
+                                                       occlusion_mask=occlusion_mask, global_step=self.global_step)
+        out = {"rays_o": rays_o, "rays_d": rays_d, "ret_fg": ret_fg}
+        if ret_fg:
+            out.update(fg)
+        else:
+            out["fore_valid"] = torch.zeros(rays_d[..., 0].shape, dtype=torch.bool, device=self.device)
+        bg, ret_bg = self.featureGrid.render_bg_rays(rays_o, rays_d, self.num_bg_sample, self.decoder, mode,
+                                                     occlusion_mask=occlusion_mask, global_step=self.global_step,
+                                                     bg_mode="IZ", infinity=True, fmesh=None,
+                                                     invalid_underground=self.invalid_underground)
+        if ret_fg is False and ret_bg is False:
+            return None, False
+        out["ret_bg"] = ret_bg
+        if ret_bg:
+            out["bg_valid"] = bg["valid"]
+            if ret_fg:
+                T = fg["T_left"]
+                out["pred_color"] = out["pred_color"] + T * bg["rgb"]
+                out["pred_depth"] = out["pred_depth"] + T * bg["depth"]
+                out["pred_specular"] = fg["specular"] + T * bg["specular"]
+                out["pred_diffuse"] = fg["diffuse"] + T * bg["diffuse"]
+                if mode == TRAIN:
+                    out["l2_reg_specular"] = out["l2_reg_specular"] + bg["l2_reg_specular"]
+            else:
+                out["pred_color"], out["pred_depth"] = bg["rgb"], bg["depth"]
+                out["pred_specular"], out["pred_diffuse"] = bg["specular"], bg["diffuse"]
+                if mode == TRAIN:
+                    out["l2_reg_specular"] = bg["l2_reg_specular"]
+        else:
+            out["pred_specular"], out["pred_diffuse"] = fg["specular"], fg["diffuse"]
+        return out, True
+
+    def loss(self, locs, gt_color):
+        rays_o, rays_d = self.poses.rays(locs)
+        out, ok = self.render_rays(rays_o, rays_d, None, TRAIN)
+        if not ok:
+            return None, None
+        mse = torch.mean((out["pred_color"] - gt_color) ** 2)            # criterions.py MSE on input/target
+        return mse + 0.01 * out["l2_reg_specular"], out                    # tile.py:999
+
+    def step_device(self, locs, gt_color):
+        """Inputs already on the device.  Returns the loss as a device scalar (no host sync)."""
+        loss, _ = self.loss(locs, gt_color)
+        if loss is None:
+            self.global_step += 1
+            return torch.zeros((), device=self.device)
+        self.featureGrid_optimizer.zero_grad()
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.featureGrid_optimizer.step()
+        self.optimizer.step()
+        self.global_step += 1
+        return loss.detach()
+
+    def step(self, locs_host, gt_host):
+        """The end-to-end call: pinned host batch in, python float loss out."""
+        locs = locs_host.to(self.device, non_blocking=True)
+        gt = gt_host.to(self.device, non_blocking=True)
+        return float(self.step_device(locs, gt).item())
