@@ -95,6 +95,22 @@ int snrf_composite_bwd(const float* sigma, const float* tint, const float* diffu
                        int gs_sigma, int gs_tint, int gs_diffuse, int gs_specular,
                        float* grad_rays_d, void* stream);
 
+/* ---- decoder MLP on the tensor cores (tcgen05 / TMEM) ------------------------- */
+/* Self-test of the tensor-core conventions (no reference counterpart): X[128,64], W[64,64],
+ * G[128,64] f32, rounded to bf16 inside -> Y = X W^T [128,64], DX = G W [128,64],
+ * DW = 2 G^T X [64,64], DWo = G^T X[:,32:48] [64,16], YS = X[:,32:64] W[0:16,0:32]^T [128,16] (f32). */
+int snrf_umma_selftest(const float* X, const float* W, const float* G, float* Y, float* DX, float* DW,
+                       float* DWo, float* YS, void* stream);
+
+/* network.py:151-190 (ShallowMLP.forward): feats[N,32] f32 (hash-encode output), mask32[32] f32
+ * (level mask, NULL = ones), rays_d[R,3] (sample n belongs to ray n / S; normalised inside with the
+ * reference's +1e-8), params = HOST array of 16 DEVICE pointers in network.ShallowMLP state_dict
+ * order (weight, bias per Linear: Spatial_MLP.mlp.0 [64,32], .mlp.2 [64,64], sigma_layer [1,32],
+ * diffuse_layer [3,32], tint_layer [3,32], Directional_MLP.mlp.0 [64,48], .2 [64,64], .4 [3,64]).
+ * -> heads[N,10] f32 = (sigma, tint3, diffuse3, specular3).  bf16 operands, f32 accumulation. */
+int snrf_decoder_fwd(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
+                     float* heads, int N, int S, void* stream);
+
 /* ---- sparse Adam -------------------------------------------------------------- */
 /* cuda/include/adam.h (adam_step_cuda: half_state=0, adam_step_cuda_fp16: half_state=1; kernels
  * cuda/adam_kernel.cu:23-69, 97-144).  Element (k,d), k<rows, d<dim, lives at k*row_stride+d

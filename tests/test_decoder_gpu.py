@@ -1,0 +1,67 @@
+"""GPU: decoder MLP on the tensor cores (tcgen05 / TMEM) -- conventions self-test and parity of
+the fused decoder forward/backward against the torch restatement of network.ShallowMLP
+(oracle/torch_ref.py, pinned by tests/golden/py_golden_mlp.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_pkg
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def test_umma_selftest_three_gemm_shapes():
+    load_pkg()
+    import scanerf_b200_capi as capi
+    from scanerf_b200_capi import ptr
+    g = torch.Generator().manual_seed(0)
+    X, W, G = torch.randn(128, 64, generator=g), torch.randn(64, 64, generator=g), torch.randn(128, 64, generator=g)
+    dev = "cuda:0"
+    Xd, Wd, Gd = X.to(dev), W.to(dev), G.to(dev)
+    Y, DX, DW = torch.zeros(128, 64, device=dev), torch.zeros(128, 64, device=dev), torch.zeros(64, 64, device=dev)
+    DWo, YS = torch.zeros(64, 16, device=dev), torch.zeros(128, 16, device=dev)
+    capi.check(capi.lib().snrf_umma_selftest(ptr(Xd), ptr(Wd), ptr(Gd), ptr(Y), ptr(DX), ptr(DW), ptr(DWo), ptr(YS),
+                                             capi.stream()), "snrf_umma_selftest")
+    torch.cuda.synchronize()
+    Xb, Wb, Gb = _bf16(X).double(), _bf16(W).double(), _bf16(G).double()
+    for name, got, want in (("Y", Y, Xb @ Wb.T), ("DX", DX, Gb @ Wb), ("DW", DW, 2 * Gb.T @ Xb),
+                            ("DWo", DWo, Gb.T @ Xb[:, 32:48]), ("YS", YS, Xb[:, 32:64] @ Wb[0:16, 0:32].T)):
+        err = float((got.cpu().double() - want).abs().max())
+        assert err < 1e-3, f"{name}: max abs err {err}"
+
+
+def _decoder_and_inputs(N, S, seed):
+    from hashgrid._decoder import ShallowMLP, decoder_params
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    dec = ShallowMLP(32)
+    for p in dec.parameters():                      # non-zero biases so that every term is exercised
+        if p.dim() == 1:
+            p.data = torch.randn(p.shape, generator=g) * 0.05
+    feats = torch.randn(N, 32, generator=g) * 0.3
+    mask = torch.rand(32, generator=g)
+    rays_d = torch.randn((N + S - 1) // S, 3, generator=g) * 1.7
+    return dec, decoder_params(dec), feats, mask, rays_d
+
+
+@pytest.mark.parametrize("N,S", [(128, 128), (1000, 8), (128 * 37 + 5, 64)])
+def test_decoder_forward_matches_torch(N, S):
+    load_pkg()
+    from hashgrid import _field
+    dec, params, feats, mask, rays_d = _decoder_and_inputs(N, S, N)
+    dirs = rays_d.repeat_interleave(S, 0)[:N]
+    with torch.no_grad():
+        ref = dec(torch.cat([feats, dirs], -1), weight_feature=mask)
+    dev = "cuda:0"
+    out = _field.decoder_forward(feats.to(dev), mask.to(dev), rays_d.to(dev), S, [p.to(dev) for p in params]).cpu()
+    got = {"sigma": out[:, 0:1], "tint": out[:, 1:4], "diffuse": out[:, 4:7], "specular": out[:, 7:10]}
+    for k in got:                                   # bf16 operands, f32 accumulation: north_star bar 2e-3 (bf16 path)
+        err = float((got[k] - ref[k]).abs().max())
+        mean_rel = float((got[k] - ref[k]).abs().mean() / ref[k].abs().mean())
+        print(f"decoder fwd {k}: max abs err {err:.2e}, mean rel err {mean_rel:.2e}")
+        assert err < 8e-3, f"{k}: max abs err {err}"
+        assert mean_rel < 3e-3, f"{k}: mean relative err {mean_rel}"
