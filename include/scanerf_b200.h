@@ -111,6 +111,14 @@ int snrf_umma_selftest(const float* X, const float* W, const float* G, float* Y,
 int snrf_decoder_fwd(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
                      float* heads, int N, int S, void* stream);
 
+/* Backward of snrf_decoder_fwd (autograd of network.py:151-190).  grad_heads[N,10] (column order
+ * of heads) -> grad_feats[N,32] WRITTEN; grad_rays_d[R,3] ACCUMULATED (may be NULL; the view
+ * direction enters through the SH encoding only); grad_params = HOST array of 16 DEVICE pointers,
+ * shapes/order of params, ACCUMULATED.  The forward is recomputed per 128-sample tile. */
+int snrf_decoder_bwd(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
+                     const float* grad_heads, float* grad_feats, float* grad_rays_d, float* const* grad_params,
+                     int N, int S, void* stream);
+
 /* ---- sparse Adam -------------------------------------------------------------- */
 /* cuda/include/adam.h (adam_step_cuda: half_state=0, adam_step_cuda_fp16: half_state=1; kernels
  * cuda/adam_kernel.cu:23-69, 97-144).  Element (k,d), k<rows, d<dim, lives at k*row_stride+d

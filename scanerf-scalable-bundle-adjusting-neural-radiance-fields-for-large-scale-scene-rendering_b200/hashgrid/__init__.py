@@ -16,7 +16,7 @@ from .PyHashGrid import PyHashGrid
 from .PyHashGridBG import PyHashGridBG
 from .lib.HASHGRID import *  # noqa: F401,F403  (operator surface, incl. Sampler)
 from .lib import HASHGRID as _ops
-from . import _render
+from . import _decoder, _field, _render
 
 from cuda import ray_aabb_intersection, sample_points_grid, voxelize_mesh
 
@@ -35,6 +35,10 @@ def _pow2_shape(log2dim):
 class HashGrid(nn.Module):
     """One tile's field: a 16-level hash grid over the contracted space of the doubled
     tile box, a boolean occupancy grid over the tile itself and the render helpers."""
+
+    # route ShallowMLP-shaped decoders through the tcgen05 decoder kernels (bf16 operands,
+    # f32 accumulation); False keeps the decoder module's own torch forward (fp32)
+    fused_decoder = True
 
     def __init__(self, device, bbox_corner, bbox_size, log2_hashmap_size=24, grid_resolution=[32, 2048],
                  sampler_log2dim=4, init_outside=False, model_path="", near=None, far=None):
@@ -317,11 +321,21 @@ class HashGrid(nn.Module):
             cx, extra_w = contract_func(samples.reshape(-1, 3))
         else:
             cx, extra_w = samples.reshape(-1, 3), None
-        feats = self.HE(cx).reshape(R, S, 32)
-        mask32 = self.weight_feature(kwargs["global_step"])[None, None, :].repeat_interleave(2, dim=-1)
+        feats = self.HE(cx)
+        mask16 = self.weight_feature(kwargs["global_step"])
+        params = _decoder.decoder_params(decoder) if (self.fused_decoder and extra_w is None) else None
+        if params is not None:
+            # stock ShallowMLP: the whole decoder runs on the tensor cores (csrc/decoder.cu) and
+            # hands packed head rows straight to the compositing kernel
+            heads = _field.decoder_apply(feats, rays_d, mask16.repeat_interleave(2), S, params)
+            out = _render.composite_packed(heads, z_vals, dists, rays_d, infinity, train=(mode is TRAIN))
+            if out_normal:
+                raise NotImplementedError("out_normal needs a twice-differentiable decoder: set HashGrid.fused_decoder = False")
+            return out, True
+        mask32 = mask16[None, None, :].repeat_interleave(2, dim=-1)
         if extra_w is not None:
             mask32 = mask32 * extra_w.reshape(R, S, 32)
-        heads = decoder(torch.cat([feats, rays_d[:, None, :].repeat(1, S, 1)], -1), weight_feature=mask32)
+        heads = decoder(torch.cat([feats.reshape(R, S, 32), rays_d[:, None, :].repeat(1, S, 1)], -1), weight_feature=mask32)
         out = _render.composite(heads, z_vals, dists, rays_d, infinity, train=(mode is TRAIN))
         if out_normal:
             ones = torch.ones_like(heads["sigma"], requires_grad=False)

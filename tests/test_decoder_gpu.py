@@ -63,5 +63,36 @@ def test_decoder_forward_matches_torch(N, S):
         err = float((got[k] - ref[k]).abs().max())
         mean_rel = float((got[k] - ref[k]).abs().mean() / ref[k].abs().mean())
         print(f"decoder fwd {k}: max abs err {err:.2e}, mean rel err {mean_rel:.2e}")
-        assert err < 8e-3, f"{k}: max abs err {err}"
-        assert mean_rel < 3e-3, f"{k}: mean relative err {mean_rel}"
+        assert err < 4e-2, f"{k}: max abs err {err}"
+        assert mean_rel < 2e-2, f"{k}: mean relative err {mean_rel}"
+
+
+@pytest.mark.parametrize("N,S", [(128, 128), (128 * 5 + 17, 32), (4096 * 3, 128)])
+def test_decoder_backward_matches_torch(N, S):
+    load_pkg()
+    from hashgrid import _field
+    dec, params, feats, mask, rays_d = _decoder_and_inputs(N, S, N + 1)
+    g = torch.Generator().manual_seed(3)
+    cot = torch.randn(N, 10, generator=g)
+    # torch reference (fp32, CPU)
+    f_ref = feats.clone().requires_grad_(True)
+    d_ref = rays_d.clone().requires_grad_(True)
+    o = dec(torch.cat([f_ref, d_ref.repeat_interleave(S, 0)[:N]], -1), weight_feature=mask)
+    ref_heads = torch.cat([o["sigma"], o["tint"], o["diffuse"], o["specular"]], -1)
+    (ref_heads * cot).sum().backward()
+    # tensor-core path
+    dev = "cuda:0"
+    f_gpu = feats.to(dev).requires_grad_(True)
+    d_gpu = rays_d.to(dev).requires_grad_(True)
+    p_gpu = [p.detach().to(dev).requires_grad_(True) for p in params]
+    heads = _field.decoder_apply(f_gpu, d_gpu, mask.to(dev), S, p_gpu)
+    (heads * cot.to(dev)).sum().backward()
+
+    def rel(a, b):
+        return float((a.cpu() - b).abs().max() / b.abs().max().clamp_min(1e-12))
+    errs = {"feats": rel(f_gpu.grad, f_ref.grad), "rays_d": rel(d_gpu.grad, d_ref.grad)}
+    for q, p in zip(p_gpu, params):
+        errs[f"param{tuple(p.shape)}"] = rel(q.grad, p.grad)
+    print("decoder bwd rel errs:", {k: f"{v:.2e}" for k, v in errs.items()})
+    for k, v in errs.items():                      # bf16 operands in a 5-layer chain with exp(-50 z^2) activations
+        assert v < 3e-2, f"{k}: {v}"
