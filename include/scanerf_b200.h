@@ -107,10 +107,13 @@ int snrf_umma_selftest(const float* X, const float* W, const float* G, float* Y,
  * reference's +1e-8), params = HOST array of 16 DEVICE pointers in network.ShallowMLP state_dict
  * order (weight, bias per Linear: Spatial_MLP.mlp.0 [64,32], .mlp.2 [64,64], sigma_layer [1,32],
  * diffuse_layer [3,32], tint_layer [3,32], Directional_MLP.mlp.0 [64,48], .2 [64,64], .4 [3,64]).
- * -> heads[N,10] f32 = (sigma, tint3, diffuse3, specular3).  bf16 operands, f32 accumulation. */
+ * -> heads[N,10] f32 = (sigma, tint3, diffuse3, specular3).  bf16(x3) operands, f32 accumulation. */
 int snrf_decoder_fwd(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
                      float* heads, int N, int S, void* stream);
 
+/* Operand precision of the decoder GEMMs: 1 (default) = error-compensated bf16x3 split operands in
+ * every forward GEMM (~fp32 accuracy), 0 = plain bf16 operands (fastest). */
+void snrf_decoder_set_precision(int split);
 /* Backward of snrf_decoder_fwd (autograd of network.py:151-190).  grad_heads[N,10] (column order
  * of heads) -> grad_feats[N,32] WRITTEN; grad_rays_d[R,3] ACCUMULATED (may be NULL; the view
  * direction enters through the SH encoding only); grad_params = HOST array of 16 DEVICE pointers,
@@ -130,6 +133,24 @@ int snrf_adam_step(float* params, float* grads, void* exp_avg, void* exp_avg_sq,
                    long long rows, int dim, int row_stride, int half_state,
                    float lr, float beta1, float beta2, float eps, int step, int zero_grad,
                    void* stream);
+
+/* ---- ray <-> proxy mesh (fastMesh) --------------------------------------------- */
+/* fastMesh/include/fastMesh.h:11-57 (class fastMesh).  The handle owns one device allocation on
+ * the current device; queries may run on any stream of that device. */
+int snrf_mesh_create(const char* ply_path, void** handle);                 /* build(path): fastMesh.h:22-26 */
+int snrf_mesh_create_from_arrays(const float* verts_host, int nv, const int* faces_host, int nf, void** handle);
+int snrf_mesh_destroy(void* handle);                                        /* destroy(): fastMesh.h:52-55 */
+int snrf_mesh_bounds(void* handle, float* bound6_host);                     /* getSceneBound(): fastMesh.h:28-38 */
+int snrf_mesh_stats(void* handle, long long* stats3_host);                  /* occupied cells, list entries, faces */
+/* fisrtHit (sic) fastMesh_kernel.cu:230-329: z_depth[B] = nearest t>0 within the first cell that has a
+ * hit, 0 = miss; hit_face[B] i32 optional (extension): that face's index or -1. */
+int snrf_mesh_first_hit(void* handle, const float* rays_o, const float* rays_d, float* z_depth, int* hit_face,
+                        int B, void* stream);
+/* firstEnter fastMesh_kernel.cu:125-227 */
+int snrf_mesh_first_enter(void* handle, const float* rays_o, const float* rays_d, float* z_depth, int B, void* stream);
+/* sample_points fastMesh_kernel.cu:23-122: t_start[B] (-1 = leave the row untouched), z_vals[B,S] */
+int snrf_mesh_sample(void* handle, const float* rays_o, const float* rays_d, const float* t_start, float* z_vals,
+                     int B, int S, void* stream);
 
 /* ---- mesh ingest (host) ------------------------------------------------------- */
 /* cuda/include/voxelize.h:12-119 (voxelize_mesh): ALL pointers are host pointers.

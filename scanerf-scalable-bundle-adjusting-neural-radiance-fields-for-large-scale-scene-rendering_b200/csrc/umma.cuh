@@ -12,6 +12,7 @@
 //   so neither activations nor weights ever need a transposed copy.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace umma {
@@ -148,6 +149,17 @@ __device__ __forceinline__ void tile_store8(unsigned char* tile, int row, int ch
 {
     uint4 q;
     q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tile + tile_chunk_off(row, chunk)) = q;
+}
+// same slot, but 8 fp16 values (element-wise scratch that is never read by the tensor core)
+__device__ __forceinline__ void tile_store8_f16(unsigned char* tile, int row, int chunk, const float* v)
+{
+    uint4 q;
+    __half2 h;
+    h = __floats2half2_rn(v[0], v[1]); q.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2half2_rn(v[2], v[3]); q.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2half2_rn(v[4], v[5]); q.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2half2_rn(v[6], v[7]); q.w = *reinterpret_cast<uint32_t*>(&h);
     *reinterpret_cast<uint4*>(tile + tile_chunk_off(row, chunk)) = q;
 }
 __device__ __forceinline__ void tile_zero8(unsigned char* tile, int row, int chunk)

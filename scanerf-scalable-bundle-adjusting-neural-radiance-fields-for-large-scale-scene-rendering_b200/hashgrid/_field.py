@@ -11,6 +11,12 @@ from scanerf_b200_capi import c_int, c_void_p, ptr
 f32 = torch.float32
 
 
+def set_precision(split=True):
+    """True (default): error-compensated bf16x3 operands in the forward GEMMs (fp32-grade heads);
+    False: plain bf16 operands (fastest, ~1 % error in the directional branch)."""
+    capi.lib().snrf_decoder_set_precision(c_int(1 if split else 0))
+
+
 def _param_array(params):
     ps = [p.detach().contiguous() for p in params]
     for p in ps:

@@ -48,8 +48,9 @@ def _decoder_and_inputs(N, S, seed):
     return dec, decoder_params(dec), feats, mask, rays_d
 
 
+@pytest.mark.parametrize("split", [True, False])
 @pytest.mark.parametrize("N,S", [(128, 128), (1000, 8), (128 * 37 + 5, 64)])
-def test_decoder_forward_matches_torch(N, S):
+def test_decoder_forward_matches_torch(N, S, split):
     load_pkg()
     from hashgrid import _field
     dec, params, feats, mask, rays_d = _decoder_and_inputs(N, S, N)
@@ -57,18 +58,26 @@ def test_decoder_forward_matches_torch(N, S):
     with torch.no_grad():
         ref = dec(torch.cat([feats, dirs], -1), weight_feature=mask)
     dev = "cuda:0"
-    out = _field.decoder_forward(feats.to(dev), mask.to(dev), rays_d.to(dev), S, [p.to(dev) for p in params]).cpu()
+    _field.set_precision(split)
+    try:
+        out = _field.decoder_forward(feats.to(dev), mask.to(dev), rays_d.to(dev), S, [p.to(dev) for p in params]).cpu()
+    finally:
+        _field.set_precision(True)
     got = {"sigma": out[:, 0:1], "tint": out[:, 1:4], "diffuse": out[:, 4:7], "specular": out[:, 7:10]}
-    for k in got:                                   # bf16 operands, f32 accumulation: north_star bar 2e-3 (bf16 path)
+    # split (bf16x3) operands: fp32-grade, bar 1e-4 absolute on every head (so composited RGB stays within 1e-4);
+    # plain bf16 operands: the Gaussian activations amplify the 2^-9 operand rounding to ~1 %
+    max_tol, rel_tol = (1e-4, 5e-5) if split else (4e-2, 2e-2)
+    for k in got:
         err = float((got[k] - ref[k]).abs().max())
         mean_rel = float((got[k] - ref[k]).abs().mean() / ref[k].abs().mean())
-        print(f"decoder fwd {k}: max abs err {err:.2e}, mean rel err {mean_rel:.2e}")
-        assert err < 4e-2, f"{k}: max abs err {err}"
-        assert mean_rel < 2e-2, f"{k}: mean relative err {mean_rel}"
+        print(f"decoder fwd split={split} {k}: max abs err {err:.2e}, mean rel err {mean_rel:.2e}")
+        assert err < max_tol, f"{k}: max abs err {err}"
+        assert mean_rel < rel_tol, f"{k}: mean relative err {mean_rel}"
 
 
+@pytest.mark.parametrize("split", [True, False])
 @pytest.mark.parametrize("N,S", [(128, 128), (128 * 5 + 17, 32), (4096 * 3, 128)])
-def test_decoder_backward_matches_torch(N, S):
+def test_decoder_backward_matches_torch(N, S, split):
     load_pkg()
     from hashgrid import _field
     dec, params, feats, mask, rays_d = _decoder_and_inputs(N, S, N + 1)
@@ -85,14 +94,20 @@ def test_decoder_backward_matches_torch(N, S):
     f_gpu = feats.to(dev).requires_grad_(True)
     d_gpu = rays_d.to(dev).requires_grad_(True)
     p_gpu = [p.detach().to(dev).requires_grad_(True) for p in params]
-    heads = _field.decoder_apply(f_gpu, d_gpu, mask.to(dev), S, p_gpu)
-    (heads * cot.to(dev)).sum().backward()
+    _field.set_precision(split)
+    try:
+        heads = _field.decoder_apply(f_gpu, d_gpu, mask.to(dev), S, p_gpu)
+        (heads * cot.to(dev)).sum().backward()
+        torch.cuda.synchronize()
+    finally:
+        _field.set_precision(True)
 
-    def rel(a, b):
-        return float((a.cpu() - b).abs().max() / b.abs().max().clamp_min(1e-12))
+    def rel(a, b):      # relative error in the L2 sense
+        return float((a.cpu() - b).norm() / b.norm().clamp_min(1e-20))
     errs = {"feats": rel(f_gpu.grad, f_ref.grad), "rays_d": rel(d_gpu.grad, d_ref.grad)}
     for q, p in zip(p_gpu, params):
         errs[f"param{tuple(p.shape)}"] = rel(q.grad, p.grad)
-    print("decoder bwd rel errs:", {k: f"{v:.2e}" for k, v in errs.items()})
-    for k, v in errs.items():                      # bf16 operands in a 5-layer chain with exp(-50 z^2) activations
-        assert v < 3e-2, f"{k}: {v}"
+    print(f"decoder bwd split={split} rel L2 errs:", {k: f"{v:.2e}" for k, v in errs.items()})
+    tol = 4e-3 if split else 2e-1        # gradient GEMMs use plain bf16 operands (2^-9 rounding, not amplified)
+    for k, v in errs.items():
+        assert v < tol, f"{k}: {v}"

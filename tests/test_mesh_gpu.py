@@ -1,0 +1,148 @@
+"""GPU: ray <-> proxy-mesh queries (csrc/mesh.cu behind the reference's `fastMesh` class surface)
+against the UNMODIFIED reference extension rebuilt into oracle/_ref/fastMesh.so, on the same PLY
+and the same rays.  Bars: hit / miss pattern and hit depths identical (the walk and the triangle
+test use the reference's fp32 operation order); sample rows identical."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+import scenes
+from conftest import load_pkg, ref_module
+
+pytestmark = pytest.mark.gpu
+
+CORNER, SIZE = (0.0, 0.0, 0.0), (20.0, 13.0, 30.0)
+
+
+def _mesh(tmp, **kw):
+    ply = os.path.join(tmp, "mesh.ply")
+    V, F = scenes.write_proxy_mesh_ply(ply, CORNER, SIZE, seed=3, **kw)
+    return ply, V, F
+
+
+def _rays(B, seed, V):
+    """Origins inside the vertex AABB (the reference assumes the camera is inside the scene)."""
+    g = torch.Generator().manual_seed(seed)
+    lo, hi = torch.from_numpy(V.min(0)), torch.from_numpy(V.max(0))
+    o = lo + (hi - lo) * (0.02 + 0.96 * torch.rand(B, 3, generator=g))
+    d = torch.randn(B, 3, generator=g)
+    d[: B // 8, 1] = -d[: B // 8, 1].abs() - 0.2           # plenty of rays towards the ground
+    d[B // 8: B // 8 + 16, 0] = 0.0                         # safe_divide paths
+    d = d * (0.5 + torch.rand(B, 1, generator=g))
+    return o.contiguous(), d.contiguous()
+
+
+def _ours(ply):
+    load_pkg()
+    from fastMesh.lib.fastMesh import fastMesh
+    m = fastMesh()
+    m.build(ply)
+    return m
+
+
+def test_build_and_bounds():
+    with tempfile.TemporaryDirectory() as tmp:
+        ply, V, F = _mesh(tmp, n_boxes=8, ground_res=24)
+        m = _ours(ply)
+        b = m.getSceneBound()
+        assert torch.allclose(b[:3], torch.from_numpy(V.min(0))) and torch.allclose(b[3:], torch.from_numpy(V.max(0)))
+        st = m.stats()
+        assert st["faces"] == len(F) and st["occupied_cells"] > 0 and st["list_entries"] >= st["occupied_cells"]
+        m.destroy()
+        with pytest.raises(RuntimeError):
+            m.fisrtHit(torch.zeros(1, 3, device="cuda"), torch.ones(1, 3, device="cuda"), torch.zeros(1, 1, device="cuda"))
+
+
+def test_first_hit_against_brute_force_properties():
+    """Size-independent property: a reported hit is a true ray/triangle intersection (the point
+    lies on the reported face) and a ray with any intersection never reports a miss."""
+    with tempfile.TemporaryDirectory() as tmp:
+        ply, V, F = _mesh(tmp, n_boxes=10, ground_res=20)
+        m = _ours(ply)
+        dev = "cuda:0"
+        o, d = _rays(4096, 1, V)
+        z = torch.zeros(4096, 1, device=dev)
+        face = torch.full((4096,), -2, dtype=torch.int32, device=dev)
+        m.fisrtHit(o.to(dev), d.to(dev), z, face)
+        z, face = z.cpu()[:, 0], face.cpu().long()
+        hit = z > 0
+        assert hit.any() and (~hit).any()
+        assert bool((face[hit] >= 0).all()) and bool((face[~hit] == -1).all())
+        Vt, Ft = torch.from_numpy(V).double(), torch.from_numpy(F).long()
+        p = o[hit].double() + z[hit, None].double() * d[hit].double()
+        A, B_, C = Vt[Ft[face[hit], 0]], Vt[Ft[face[hit], 1]], Vt[Ft[face[hit], 2]]
+        n = torch.cross(B_ - A, C - A, dim=-1)
+        dist = ((p - A) * n).sum(-1).abs() / n.norm(dim=-1)
+        assert float(dist.max()) < 1e-3, "hit point must lie on the reported face"
+        # brute force over all faces (double precision, two-sided)
+        od, dd = o.double(), d.double()
+        e1, e2 = (Vt[Ft[:, 1]] - Vt[Ft[:, 0]])[None], (Vt[Ft[:, 2]] - Vt[Ft[:, 0]])[None]
+        pv = torch.cross(dd[:, None].expand(-1, Ft.shape[0], -1), e2.expand(od.shape[0], -1, -1), dim=-1)
+        det = (e1 * pv).sum(-1)
+        s = od[:, None] - Vt[Ft[:, 0]][None]
+        u = (s * pv).sum(-1) / det
+        q = torch.cross(s, e1.expand_as(s), dim=-1)
+        v = (dd[:, None] * q).sum(-1) / det
+        t = (e2 * q).sum(-1) / det
+        ok = (det.abs() > 1e-7) & (u > 1e-4) & (v > 1e-4) & (u + v < 1 - 1e-4) & (t > 1e-4)
+        any_hit = ok.any(-1)
+        assert bool(hit[any_hit].all()), "a ray that intersects the mesh must report a hit"
+        tmin = torch.where(ok, t, torch.full_like(t, 1e30)).min(-1)[0]
+        assert bool((z[any_hit].double() >= tmin[any_hit] - 1e-3).all()), "no hit in front of the nearest intersection"
+
+
+@pytest.mark.parametrize("B", [1, 1000, 50000])
+def test_against_reference_extension(B):
+    ref = ref_module("fastMesh")
+    if ref is None:
+        pytest.skip("oracle/_ref/fastMesh.so not built")
+    with tempfile.TemporaryDirectory() as tmp:
+        ply, V, F = _mesh(tmp)
+        ours = _ours(ply)
+        theirs = ref.fastMesh()
+        theirs.build(ply)
+        assert torch.equal(ours.getSceneBound(), theirs.getSceneBound().cpu().float())
+        dev = "cuda:0"
+        o, d = _rays(B, B, V)
+        od, dd = o.to(dev), d.to(dev)
+        for name in ("fisrtHit", "firstEnter"):
+            za, zb = torch.zeros(B, 1, device=dev), torch.zeros(B, 1, device=dev)
+            getattr(theirs, name)(od, dd, za)
+            getattr(ours, name)(od, dd, zb)
+            torch.cuda.synchronize()
+            za, zb = za.cpu(), zb.cpu()
+            assert torch.equal(za > 0, zb > 0), f"{name}: hit / miss pattern differs on {int(((za > 0) != (zb > 0)).sum())} rays"
+            assert torch.allclose(za, zb, rtol=1e-6, atol=1e-6), f"{name}: max depth diff {float((za - zb).abs().max())}"
+        S = 32
+        t0 = torch.rand(B, generator=torch.Generator().manual_seed(5)) * 2.0
+        t0[::7] = -1.0
+        za = torch.full((B, S), -1.0, device=dev)
+        zb = torch.full((B, S), -1.0, device=dev)
+        theirs.sample_points(od, dd, t0.to(dev), za)
+        ours.sample_points(od, dd, t0.to(dev), zb)
+        torch.cuda.synchronize()
+        za, zb = za.cpu(), zb.cpu()
+        assert torch.equal(za == -1, zb == -1), "sample_points: untouched-row pattern differs"
+        assert torch.allclose(za, zb, rtol=1e-5, atol=1e-5), f"sample_points: max diff {float((za - zb).abs().max())}"
+        theirs.destroy()
+        ours.destroy()
+
+
+def test_fastmesh_wrapper_masks():
+    """FastMesh.render_mask / render_depth (fastMesh/__init__.py:16-45 of the reference)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        ply, V, F = _mesh(tmp, n_boxes=6, ground_res=16)
+        load_pkg()
+        from fastMesh import FastMesh
+        dev = "cuda:0"
+        fm = FastMesh(ply)
+        fm.set(torch.tensor([10.0, 6.5, 15.0], device=dev), torch.tensor([10.0, 6.5, 15.0], device=dev))
+        o, d = _rays(2048, 9, V)
+        depth = fm.render_depth(o.to(dev), d.to(dev))
+        mask = fm.render_mask(o.to(dev), d.to(dev))
+        assert depth.shape == (2048, 1) and mask.shape == (2048, 1) and mask.dtype == torch.bool
+        inside = torch.all(torch.abs(o - torch.tensor([10.0, 6.5, 15.0])) < torch.tensor([5.0, 3.25, 7.5]), dim=-1)
+        assert bool(mask.cpu()[inside].all()), "origins inside the tile always see it"
