@@ -28,7 +28,10 @@
 // bf16 operands cost ~1 % in the directional branch.  SPLIT mode (the default) therefore feeds the
 // tensor cores error-compensated operands in every forward GEMM: v = hi + lo with hi = bf16(v),
 // lo = bf16(v - hi), and  A W^T ~= A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T  (three MMAs into the
-// same fp32 accumulator, ~16 mantissa bits).  Gradient GEMMs use the hi parts only.
+// same fp32 accumulator, ~16 mantissa bits).  In the backward the input-gradient GEMMs (the chain
+// that ends in d/d features -> table and pose gradients) are compensated the same way, with
+// dz = dz_hi + dz_lo; the weight-gradient GEMMs use the hi parts only (their rounding errors are
+// independent per sample and average out over the batch).
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -37,6 +40,7 @@ namespace {
 constexpr int kRows = 128;                 // samples per tile
 constexpr int kTile = kRows * 128;         // bytes of one operand tile (128 rows x 64 bf16)
 constexpr float kGaussLog2 = -50.0f * 1.4426950408889634f;   // exp(-v^2/0.02) = exp2(v^2 * kGaussLog2)
+constexpr float kInvSH0 = 1.0f / 0.28125f;                   // 1 / bf16(0.28209479): the SH_0 column doubles as the ones column
 
 // parameter tensors in network.ShallowMLP state_dict order (weight, bias per Linear)
 struct DecoderParams {
@@ -417,8 +421,9 @@ decoder_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
 // are one more GEMM against a column of ones.
 //
 // shared-memory tiles (16 KB each): A0 = [x | SH | SH_lo], a1, g1 -> dz1, H, a3, g3 -> dz4, a4,
-// g4 -> dz5, LOa (a1_lo / a3_lo in the forward, then the ones column), LOb (x_lo / H_lo / a4_lo in
-// the forward, then [dz_heads(16) | dz_spec(16)] and finally dH = dz2); g = d(activation)/dz.
+// g4 -> dz5, LOa (a1_lo / a3_lo in the forward, then the lo part of the current dz), LOb (x_lo / H_lo /
+// a4_lo in the forward, then [dz_heads | dz_spec | lo parts] and finally dH = dz2); a4 holds dH_lo after
+// B1; g = d(activation)/dz.
 template <bool SPLIT>
 __global__ void __launch_bounds__(kRows, 1)
 decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ mask32, const float* __restrict__ rays_d,
@@ -430,8 +435,10 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     unsigned char* base = smem + off_tiles<SPLIT>();
     const Tiles T{base, base + kTile, base + 2 * kTile, base + 3 * kTile, base + 4 * kTile, base + 5 * kTile,
                   base + 6 * kTile, base + 7 * kTile, base + 8 * kTile, base + 9 * kTile};
-    unsigned char* Tones = T.LOa;        // backward phase aliases
-    unsigned char* Tdz = T.LOb;
+    // backward-phase aliases of tiles the forward no longer needs
+    unsigned char* Tdz = T.LOb;          // [dz_heads | dz_spec | their lo parts], then dH = dz2 (hi)
+    unsigned char* Tdzlo = T.LOa;        // lo part of the current layer's dz (dz5, dz4, dz1 in turn)
+    unsigned char* Tdhlo = T.a4;         // lo part of dH (a4 is dead once B1 has read it)
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -453,7 +460,11 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     const float* mask = c.mask;
     const uint32_t aA0 = umma::smem_u32(T.A0), aa1 = umma::smem_u32(T.a1), ag1 = umma::smem_u32(T.g1), aH = umma::smem_u32(T.H),
                    aa3 = umma::smem_u32(T.a3), ag3 = umma::smem_u32(T.g3), aa4 = umma::smem_u32(T.a4), ag4 = umma::smem_u32(T.g4),
-                   aones = umma::smem_u32(Tones), adz = umma::smem_u32(Tdz);
+                   adz = umma::smem_u32(Tdz), adzlo = umma::smem_u32(Tdzlo), adhlo = umma::smem_u32(Tdhlo);
+    // bias gradients of the 64-wide layers ride on the weight-gradient GEMMs: column 32 of A0 holds
+    // SH_0 = 0.28209479 (a constant, exactly representable products), so dz^T A0[:, 32:40] column 0
+    // is c0 * sum_n dz_n; the flush divides by c0.  Rows past N have SH = 0 and dz = 0.
+    const uint32_t aones = aA0 + 64;
     const uint32_t aW1 = umma::smem_u32(smem + oW1), aW2 = umma::smem_u32(smem + oW2), aW3 = umma::smem_u32(smem + oW3),
                    aW4 = umma::smem_u32(smem + oW4), aWh = umma::smem_u32(smem + oWh), aW5 = umma::smem_u32(smem + oW5);
     // input-gradient GEMMs: A K-major (dz rows), B MN-major (weight tile: rows = K = out, cols = N = in)
@@ -463,23 +474,40 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
                        idw16 = umma::idesc_bf16(64, 16, 1, 1), idw8 = umma::idesc_bf16(64, 8, 1, 1);
     const uint32_t aW2l = umma::smem_u32(smem + oW2l), aW3l = umma::smem_u32(smem + oW3l), aW4l = umma::smem_u32(smem + oW4l),
                    aW5l = umma::smem_u32(smem + oW5l);
-    // dA = dz W over `nk` k-steps; in SPLIT mode the weight is W_hi + W_lo (the lo tile, or the
-    // lo half of a packed tile at a 64-byte column offset)
-    auto dgrad = [&](int col, uint32_t dz_tile, int dz_k, uint32_t w_hi, uint32_t w_lo, int nk, uint32_t idesc) {
+    // dA = dz W over `nk` k-steps; in SPLIT mode dz = dz_hi + dz_lo and W = W_hi + W_lo (the lo tile,
+    // or the lo half of a packed tile at a 64-byte column offset): dz_hi W_hi + dz_hi W_lo + dz_lo W_hi
+    auto dgrad = [&](int col, uint32_t dz_tile, int dz_k, uint32_t dzlo_tile, int dzlo_k, uint32_t w_hi, uint32_t w_lo, int nk,
+                     uint32_t idesc) {
         for (int k = 0; k < nk; ++k)
             umma::mma_bf16(tmem + col, umma::desc_kmajor(dz_tile, dz_k + k), umma::desc_mnmajor(w_hi, k), idesc, k > 0);
-        if (SPLIT)
+        if (SPLIT) {
             for (int k = 0; k < nk; ++k)
                 umma::mma_bf16(tmem + col, umma::desc_kmajor(dz_tile, dz_k + k), umma::desc_mnmajor(w_lo, k), idesc, 1);
+            for (int k = 0; k < nk; ++k)
+                umma::mma_bf16(tmem + col, umma::desc_kmajor(dzlo_tile, dzlo_k + k), umma::desc_mnmajor(w_hi, k), idesc, 1);
+        }
     };
-    // dW += A^T B over the 128 rows of the tile (8 k-steps); `first` = first tile of this CTA
-    auto wgrad = [&](int col, uint32_t a_tile, uint32_t b_tile_plus_off, uint32_t idesc, bool first) {
+    // dW += dz^T B over the 128 rows of the tile (8 k-steps); `first` = first tile of this CTA.  In SPLIT
+    // mode the dz operand is compensated (dz_hi + dz_lo: `a_lo` = the lo tile, or the packed lo columns);
+    // the activation operand B stays bf16 (its lo part is gone by now).
+    auto wgrad = [&](int col, uint32_t a_tile, uint32_t a_lo, uint32_t b_tile_plus_off, uint32_t idesc, bool first) {
         for (int k = 0; k < 8; ++k)
             umma::mma_bf16(tmem + col, umma::desc_mnmajor(a_tile, k), umma::desc_mnmajor(b_tile_plus_off, k), idesc, (!first) || k > 0);
+        if (SPLIT)
+            for (int k = 0; k < 8; ++k)
+                umma::mma_bf16(tmem + col, umma::desc_mnmajor(a_lo, k), umma::desc_mnmajor(b_tile_plus_off, k), idesc, 1);
+    };
+    // transposed narrow layers (dW^T += A^T dz): the compensated operand is B
+    auto wgrad_t = [&](int col, uint32_t a_tile, uint32_t b_hi, uint32_t b_lo, uint32_t idesc, bool first) {
+        for (int k = 0; k < 8; ++k)
+            umma::mma_bf16(tmem + col, umma::desc_mnmajor(a_tile, k), umma::desc_mnmajor(b_hi, k), idesc, (!first) || k > 0);
+        if (SPLIT)
+            for (int k = 0; k < 8; ++k)
+                umma::mma_bf16(tmem + col, umma::desc_mnmajor(a_tile, k), umma::desc_mnmajor(b_lo, k), idesc, 1);
     };
     float v[32];
-    // dz = dA * g, in place over the g tile (this thread's row only)
-    auto mul_inplace = [&](int col, unsigned char* Tg) {
+    // dz = dA * g: hi part in place over the g tile, lo part (SPLIT) into Tlo (this thread's row only)
+    auto mul_inplace = [&](int col, unsigned char* Tg, unsigned char* Tlo) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             umma::tmem_ld32(tmem + col + lane_addr + 32 * h, v);
@@ -495,7 +523,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
                     o[2 * e] = v[8 * q + 2 * e] * __low2float(h2);
                     o[2 * e + 1] = v[8 * q + 2 * e + 1] * __high2float(h2);
                 }
-                umma::tile_store8(Tg, tid, 4 * h + q, o);
+                store8_hl<SPLIT>(Tg, 4 * h + q, Tlo, 4 * h + q, tid, o);
             }
         }
     };
@@ -534,12 +562,11 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
                 const float s = sigmoidf(z[j] + bias[oB5 + j]);
                 dzs[j] = gh[7 + j] * s * (1.0f - s);                            // specular
             }
-            umma::tile_store8(Tdz, tid, 0, dzh);
-            umma::tile_store8(Tdz, tid, 1, dzh + 8);
-            umma::tile_store8(Tdz, tid, 2, dzs);
-            umma::tile_store8(Tdz, tid, 3, dzs + 8);
-            const float ones[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};      // column 0 of the ones tile
-            umma::tile_store8(Tones, tid, 0, ones);
+            // Tdz = [dz_heads 0..15 | dz_spec 16..31 | dz_heads_lo 32..47 | dz_spec_lo 48..63]
+            store8_hl<SPLIT>(Tdz, 0, Tdz, 4, tid, dzh);
+            store8_hl<SPLIT>(Tdz, 1, Tdz, 5, tid, dzh + 8);
+            store8_hl<SPLIT>(Tdz, 2, Tdz, 6, tid, dzs);
+            store8_hl<SPLIT>(Tdz, 3, Tdz, 7, tid, dzs + 8);
             // bias gradients of the narrow layers: warp reduction, one shared atomic per warp
 #pragma unroll
             for (int j = 0; j < 10; ++j) {
@@ -552,42 +579,42 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         c.sync_operands();
         // ---- B1: dA4 = dz_spec W5 ; dH[0:32] = dz_heads Wh ; dW5^T += a4^T dz_spec ; dWh^T += H^T dz_heads
         if (tid == 0) {
-            dgrad(cDa, adz, 1, aW5, aW5l, 1, idg64);
-            dgrad(cDb, adz, 0, aWh, aWh + 64, 1, idg32);
-            wgrad(cGW5T, aa4, adz + 32, idw16, first);
-            wgrad(cGWhT, aH, adz, idw16, first);
+            dgrad(cDa, adz, 1, adz, 3, aW5, aW5l, 1, idg64);
+            dgrad(cDb, adz, 0, adz, 2, aWh, aWh + 64, 1, idg32);
+            wgrad_t(cGW5T, aa4, adz + 32, adz + 96, idw16, first);
+            wgrad_t(cGWhT, aH, adz, adz + 64, idw16, first);
             umma::mma_commit(&bar);
         }
         c.wait_mma();
-        mul_inplace(cDa, T.g4);                                  // dz5
+        mul_inplace(cDa, T.g4, Tdzlo);                           // dz5
         umma::tmem_ld32(tmem + cDb + lane_addr, v);              // dH[0:32] -> dz2 tile columns 0..31 (over the consumed dz_heads/spec)
         umma::tc_wait_ld();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) umma::tile_store8(Tdz, tid, q, v + 8 * q);
+        for (int q = 0; q < 4; ++q) store8_hl<SPLIT>(Tdz, q, Tdhlo, q, tid, v + 8 * q);
         c.sync_operands();
         // ---- B2: dA3 = dz5 W4 ; dW4 += dz5^T a3 ; db4
         if (tid == 0) {
-            dgrad(cDb, ag4, 0, aW4, aW4l, 4, idg64);
-            wgrad(cGW4, ag4, aa3, idw64, first);
-            wgrad(cGb4, ag4, aones, idw8, first);
+            dgrad(cDb, ag4, 0, adzlo, 0, aW4, aW4l, 4, idg64);
+            wgrad(cGW4, ag4, adzlo, aa3, idw64, first);
+            wgrad(cGb4, ag4, adzlo, aones, idw8, first);
             umma::mma_commit(&bar);
         }
         c.wait_mma();
-        mul_inplace(cDb, T.g3);                                  // dz4
+        mul_inplace(cDb, T.g3, Tdzlo);                           // dz4
         c.sync_operands();
         // ---- B3: d[x2] = dz4 W3 ; dW3 += dz4^T [H[32:64] | SH] ; db3
         if (tid == 0) {
-            dgrad(cDa, ag3, 0, aW3, aW3l, 4, idg64);
-            wgrad(cGW3a, ag3, aH + 64, idw32, first);
-            wgrad(cGW3b, ag3, aA0 + 64, idw16, first);
-            wgrad(cGb3, ag3, aones, idw8, first);
+            dgrad(cDa, ag3, 0, adzlo, 0, aW3, aW3l, 4, idg64);
+            wgrad(cGW3a, ag3, adzlo, aH + 64, idw32, first);
+            wgrad(cGW3b, ag3, adzlo, aA0 + 64, idw16, first);
+            wgrad(cGb3, ag3, adzlo, aones, idw8, first);
             umma::mma_commit(&bar);
         }
         c.wait_mma();
         umma::tmem_ld32(tmem + cDa + lane_addr, v);              // dH[32:64]
         umma::tc_wait_ld();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) umma::tile_store8(Tdz, tid, 4 + q, v + 8 * q);
+        for (int q = 0; q < 4; ++q) store8_hl<SPLIT>(Tdz, 4 + q, Tdhlo, 4 + q, tid, v + 8 * q);
         if (grad_rays_d != nullptr) {                            // d/d(ray direction) through the SH encoding
             float dsh[16];
             umma::tmem_ld16(tmem + cDa + lane_addr + 32, dsh);
@@ -642,19 +669,19 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         c.sync_operands();
         // ---- B4: dA1 = dH W2 ; dW2 += dH^T a1 ; db2
         if (tid == 0) {
-            dgrad(cDb, adz, 0, aW2, aW2l, 4, idg64);
-            wgrad(cGW2, adz, aa1, idw64, first);
-            wgrad(cGb2, adz, aones, idw8, first);
+            dgrad(cDb, adz, 0, adhlo, 0, aW2, aW2l, 4, idg64);
+            wgrad(cGW2, adz, adhlo, aa1, idw64, first);
+            wgrad(cGb2, adz, adhlo, aones, idw8, first);
             umma::mma_commit(&bar);
         }
         c.wait_mma();
-        mul_inplace(cDb, T.g1);                                  // dz1
+        mul_inplace(cDb, T.g1, Tdzlo);                           // dz1
         c.sync_operands();
         // ---- B5: dx = dz1 W1 (32 columns) ; dW1 += dz1^T x ; db1
         if (tid == 0) {
-            dgrad(cDa, ag1, 0, aW1, aW1 + 64, 4, idg32);
-            wgrad(cGW1, ag1, aA0, idw32, first);
-            wgrad(cGb1, ag1, aones, idw8, first);
+            dgrad(cDa, ag1, 0, adzlo, 0, aW1, aW1 + 64, 4, idg32);
+            wgrad(cGW1, ag1, adzlo, aA0, idw32, first);
+            wgrad(cGb1, ag1, adzlo, aones, idw8, first);
             umma::mma_commit(&bar);
         }
         c.wait_mma();
@@ -697,7 +724,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         auto flush_bias = [&](int col, float* dst) {            // column 0 of a [64 x 8] accumulator
             umma::tmem_ld16(tmem + col + lane_addr, b8);
             umma::tc_wait_ld();
-            if (own) atomicAdd(dst + m, b8[0]);
+            if (own) atomicAdd(dst + m, b8[0] * kInvSH0);
         };
         flush_bias(cGb1, gp.b1); flush_bias(cGb2, gp.b2); flush_bias(cGb3, gp.b3); flush_bias(cGb4, gp.b4);
         // transposed narrow layers: accumulator row = input feature k, column = output o

@@ -108,6 +108,10 @@ def test_decoder_backward_matches_torch(N, S, split):
     for q, p in zip(p_gpu, params):
         errs[f"param{tuple(p.shape)}"] = rel(q.grad, p.grad)
     print(f"decoder bwd split={split} rel L2 errs:", {k: f"{v:.2e}" for k, v in errs.items()})
-    tol = 4e-3 if split else 2e-1        # gradient GEMMs use plain bf16 operands (2^-9 rounding, not amplified)
+    # split: the input-gradient chain is error-compensated (bar 2e-3, the north star's bf16-path tolerance;
+    # measured ~4e-4, limited by the fp16 activation derivatives); weight gradients keep bf16 activations
+    # (2^-9 operand rounding, independent per sample: bar 5e-3 on this incoherent random cotangent).
+    # plain bf16: the Gaussian activations amplify operand rounding to ~1e-1.
     for k, v in errs.items():
+        tol = (2e-3 if k in ("feats", "rays_d") else 5e-3) if split else 2e-1
         assert v < tol, f"{k}: {v}"
