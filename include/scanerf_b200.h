@@ -122,6 +122,86 @@ int snrf_decoder_bwd(const float* feats, const float* mask32, const float* rays_
                      const float* grad_heads, float* grad_feats, float* grad_rays_d, float* const* grad_params,
                      int N, int S, void* stream);
 
+/* ---- view selection, neighbour projection, image sampling ------------------------ */
+/* cuda/include/view_selection.h (computeViewcost; kernel cuda/view_selection_kernel.cu:18-76):
+ * rays_o, rays_d, pts [B,3]; ks [N,9]; rts [N,12] world->camera -> costs [N,B]. */
+int snrf_view_cost(const float* rays_o, const float* rays_d, const float* pts, const float* ks, const float* rts,
+                   float* costs, int n_cam, int B, int height, int width, void* stream);
+/* proj2neighbor_forward (cuda/view_selection_kernel.cu:115-212): nei_views [B,K] i32, nei_valid [B,K] bytes
+ * -> nei_origin, nei_direction, grid [B,K,3] (grid = K (R p + t), not dehomogenised); invalid pairs untouched. */
+int snrf_proj2nei_fwd(const float* pts, const float* ks, const float* rts, const int* nei_views,
+                      const unsigned char* nei_valid, float* nei_origin, float* nei_direction, float* grid, int B, int K,
+                      void* stream);
+/* proj2neighbor_backward (cuda/view_selection_kernel.cu:214-352): ACCUMULATES grad_pts [B,3], grad_rts [N,12]. */
+int snrf_proj2nei_bwd(const float* pts, const float* ks, const float* rts, const int* nei_views,
+                      const unsigned char* nei_valid, const float* dL_dgrid, float* grad_pts, float* grad_rts, int B, int K,
+                      int n_cam, void* stream);
+/* grid_sample_forward_cuda / grid_sample_backward_cuda (cuda/grid_sample_kernel.cu:109-213): src [N,H,W,3] u8,
+ * grid [N,B,1,2] in [-1,1] (align-corners) -> out [N,B,1,3] f32, mask [N,B,1,1] bytes; grad_grid [N,B,1,2]. */
+int snrf_grid_sample_fwd(const unsigned char* src, const float* grid, float* out, unsigned char* mask, int n_img, int B,
+                         int height, int width, void* stream);
+int snrf_grid_sample_bwd(const unsigned char* src, const float* grid, const float* grad_in, float* grad_grid, int n_img,
+                         int B, int height, int width, void* stream);
+/* gaussian_grid_sample_forward/backward_cuda (cuda/grid_sample_kernel.cu:216-441) */
+int snrf_gauss_sample_fwd(const unsigned char* src, const float* grid, float* out, unsigned char* mask, int n_img, int B,
+                          int height, int width, float sigma, float max_dis, void* stream);
+int snrf_gauss_sample_bwd(const unsigned char* src, const float* grid, const float* grad_in, float* grad_grid, int n_img,
+                          int B, int height, int width, float sigma, float max_dis, void* stream);
+/* grid_sample_bool_cuda (cuda/grid_sample_kernel.cu:445-493): src [N,H,W] bytes; out-of-image entries keep their value */
+int snrf_grid_sample_bool(const unsigned char* src, const float* grid, unsigned char* out, int n_img, int B, int height,
+                          int width, void* stream);
+/* proj2pixel_and_fetch_color (cuda/helper_kernel.cu:17-104): C2Ws [N,12] camera->world, rgbs [N,H,W,3] f32
+ * -> fetched_pixels, fetched_colors [B,N,3]. */
+int snrf_proj2pixel_fetch(const float* pts, const float* Ks, const float* C2Ws, const float* rgbs, float* fetched_pixels,
+                          float* fetched_colors, int B, int n_cam, int height, int width, void* stream);
+
+/* ---- multi-tile inference renderer (hashgrid/include/rendering.h:20-182) --------- */
+/* "block" = tile.  corners/sizes [nb,3]; grid_occupied = concatenated byte grids, grid_starts [nb] i64,
+ * grid_log2dim [nb,3] i32; intersections [B,nb,2] (1e7 = miss); tracing_blocks [B,nb] i32 = tiles near-to-far. */
+int snrf_ray_block_isect(const float* rays_o, const float* rays_d, const float* corners, const float* sizes,
+                         float* intersections, int B, int nb, void* stream);                         /* ray_block_intersection */
+int snrf_render_sample(const float* rays_o, const float* rays_d, const float* corners, const float* sizes,
+                       const unsigned char* grid_occupied, const long long* grid_starts, const int* grid_log2dim,
+                       const int* tracing_blocks, const float* intersections, int* tracing_idx, float* z_start,
+                       float* z_vals, float* dists, int B, int nb, int S, void* stream);             /* sample_points */
+int snrf_prepare_points(const float* z_vals, const unsigned char* running_mask, const float* intersections,
+                        short* block_idxs, int B, int S, int nb, void* stream);                      /* prepare_points */
+int snrf_accumulate(const float* pts_diffuse, const float* pts_specular, const float* pts_alpha, float* transparency,
+                    const float* z_vals, float* diffuse, float* specular, float* depth, int B, int S, void* stream); /* accumulate_color */
+int snrf_ray_firsthit_block(const float* rays_o, const float* rays_d, const float* corners, const float* sizes,
+                            const unsigned char* grid_occupied, const long long* grid_starts, const int* grid_log2dim,
+                            const int* tracing_blocks, const float* intersections, short* hit_block_idxs, int B, int nb,
+                            void* stream);                                                            /* ray_firsthit_block */
+int snrf_inverse_z(const float* intersections, const short* related_bidx, float* z_vals, float sample_range, int B,
+                   int nb, int S, void* stream);                                                      /* inverse_z_sampling */
+int snrf_get_last_block(const int* tracing_blocks, int* bidxs, const float* intersections, int B, int nb, void* stream);
+int snrf_outgoing_bidx(const float* rays_o, const float* rays_d, const float* corners, const float* sizes,
+                       const int* tracing_blocks, const float* intersections, short* outgoing_bidxs, float* blend_weights,
+                       int skip, int B, int nb, void* stream);                                        /* update_outgoing_bidx */
+int snrf_inside_bidx(const float* rays_o, const float* corners, const float* sizes, short* inside_bidxs,
+                     float* blend_weights, int B, int nb, void* stream);                              /* update_outgoing_bidx_v2 */
+int snrf_process_occupied(int bidx, int total_grid, const float* corners, const float* sizes,
+                          const unsigned char* grid_occupied, const long long* grid_starts, const int* grid_log2dim,
+                          unsigned char* tgt_grid_occupied, int nb, void* stream);                    /* process_occupied_grid */
+/* Fused fp16-table encode + decoder MLP (tensor cores) + alpha + overlap blending.
+ * features_tables [nb,16,T,2] f16; params [nb,13994] f32 in the renderer's flat layout (rendering.py:101-113);
+ * resolution [nb,16,3] i32.  pts_inference: block_idxs [B,S,4] i16, outputs [B,S,3],[B,S,3],[B,S,1]. */
+int snrf_pts_inference(const float* rays_o, const float* rays_d, const float* z_vals, const float* dists,
+                       const short* block_idxs, const void* features_tables, const float* params, const int* resolution,
+                       const unsigned char* grid_occupied, const long long* grid_starts, const int* grid_log2dim,
+                       const float* corners, const float* sizes, float* diffuse, float* specular, float* alpha, int B,
+                       int S, int T, void* stream);
+int snrf_bg_pts_inference(const float* rays_o, const float* rays_d, const float* z_vals, const short* outgoing_bidxs,
+                          const float* blend_weights, const float* corners, const float* sizes, const int* resolution,
+                          const void* features_tables, const float* params, float* diffuse, float* specular, float* alpha,
+                          int B, int S, int T, void* stream);
+int snrf_bg_pts_inference_v2(const float* rays_o, const float* rays_d, const float* z_vals, const short* bg_idxs, int step,
+                             const float* corners, const float* sizes, const int* resolution, const void* features_tables,
+                             const float* params, float* diffuse, float* specular, float* alpha, int B, int S, int T,
+                             void* stream);
+/* operand precision of the inference MLP: 1 (default) bf16x3 split, 0 plain bf16 */
+void snrf_infer_set_precision(int split);
+
 /* ---- sparse Adam -------------------------------------------------------------- */
 /* cuda/include/adam.h (adam_step_cuda: half_state=0, adam_step_cuda_fp16: half_state=1; kernels
  * cuda/adam_kernel.cu:23-69, 97-144).  Element (k,d), k<rows, d<dim, lives at k*row_stride+d

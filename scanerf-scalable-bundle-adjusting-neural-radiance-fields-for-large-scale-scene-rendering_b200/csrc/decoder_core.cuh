@@ -1,0 +1,353 @@
+// Shared device code of the tensor-core decoder kernels (decoder.cu: training forward / backward,
+// infer.cu: the render-side fused encode + decoder): shared-memory plan, weight staging, the
+// per-tile forward pass.  See decoder.cu for the design notes.
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace dec {
+
+constexpr int kRows = 128;                 // samples per tile
+constexpr int kTile = kRows * 128;         // bytes of one operand tile (128 rows x 64 bf16)
+constexpr float kGaussLog2 = -50.0f * 1.4426950408889634f;   // exp(-v^2/0.02) = exp2(v^2 * kGaussLog2)
+constexpr float kInvSH0 = 1.0f / 0.28125f;                   // 1 / bf16(0.28209479): the SH_0 column doubles as the ones column
+
+// parameter tensors in network.ShallowMLP state_dict order (weight, bias per Linear)
+struct DecoderParams {
+    const float *W1, *b1, *W2, *b2, *Ws, *bs, *Wd, *bd, *Wt, *bt, *W3, *b3, *W4, *b4, *W5, *b5;
+    int flat;     // 0: W[out, in] row-major (nn.Linear); 1: W^T flattened input-major (the renderer's flat layout)
+};
+// The renderer's flat parameter vector (13 994 floats per tile, hashgrid/include/decoder.h:48-67,
+// rendering.py:101-113): for each Linear in state_dict order, bias[out] then W^T [in][out].
+__host__ __device__ inline DecoderParams flat_params(const float* p)
+{
+    DecoderParams d;
+    d.b1 = p;         d.W1 = p + 64;            // 32 -> 64
+    d.b2 = p + 2112;  d.W2 = p + 2112 + 64;     // 64 -> 64
+    d.bs = p + 6272;  d.Ws = p + 6272 + 1;      // 32 -> 1
+    d.bd = p + 6305;  d.Wd = p + 6305 + 3;      // 32 -> 3
+    d.bt = p + 6404;  d.Wt = p + 6404 + 3;      // 32 -> 3
+    d.b3 = p + 6503;  d.W3 = p + 6503 + 64;     // 48 -> 64
+    d.b4 = p + 9639;  d.W4 = p + 9639 + 64;     // 64 -> 64
+    d.b5 = p + 13799; d.W5 = p + 13799 + 3;     // 64 -> 3   (ends at 13994)
+    d.flat = 1;
+    return d;
+}
+struct DecoderGrads {
+    float *W1, *b1, *W2, *b2, *Ws, *bs, *Wd, *bd, *Wt, *bt, *W3, *b3, *W4, *b4, *W5, *b5;
+};
+
+// ---- shared-memory plan (byte offsets from the 1024-aligned base)
+// weight tiles: W1 [64 rows: cols 0..31 hi | cols 32..63 lo], W2, W3 (48 cols used: 32 H + 16 SH),
+// W4 [64 x 64], Wh [16 rows = sigma, diffuse3, tint3: cols 0..31 hi | 32..63 lo], W5 [16 rows, 3 used];
+// in SPLIT mode W2, W3, W4, W5 have a second tile holding their lo parts.
+constexpr int oW1 = 0, oW2 = 8192, oW3 = 16384, oW4 = 24576, oWh = 32768, oW5 = 34816;
+constexpr int oW2l = 36864, oW3l = 45056, oW4l = 53248, oW5l = 61440;
+template <bool SPLIT> constexpr int weights_end() { return SPLIT ? 63488 : 36864; }
+// biases (fp32): b1[64] b2[64] bh[16] b3[64] b4[64] b5[16]; then mask[32], small bias grads[16]
+constexpr int nB = 64 + 64 + 16 + 64 + 64 + 16;
+constexpr int oB1 = 0, oB2 = 64, oBh = 128, oB3 = 144, oB4 = 208, oB5 = 272;
+template <bool SPLIT> constexpr int off_bias() { return weights_end<SPLIT>(); }
+template <bool SPLIT> constexpr int off_mask() { return off_bias<SPLIT>() + nB * 4; }
+template <bool SPLIT> constexpr int off_small() { return off_mask<SPLIT>() + 128; }
+template <bool SPLIT> constexpr int off_tiles() { return ((off_small<SPLIT>() + 64 + 1023) / 1024) * 1024; }
+template <bool SPLIT> constexpr int fwd_smem() { return off_tiles<SPLIT>() + (SPLIT ? 5 : 3) * kTile + 1024; }
+template <bool SPLIT> constexpr int bwd_smem() { return off_tiles<SPLIT>() + 10 * kTile + 1024; }
+
+// TMEM columns: working accumulators, then (backward only) the persistent gradient accumulators
+constexpr int cDa = 0, cDb = 64, cDh = 128;
+constexpr int cGW1 = 144, cGW2 = 176, cGW3a = 240, cGW3b = 272, cGW4 = 288, cGWhT = 352, cGW5T = 368,
+              cGb1 = 384, cGb2 = 392, cGb3 = 400, cGb4 = 408;   // last one ends at 416 (+8 slack read)
+
+__device__ __forceinline__ float gauss_act(float v) { return exp2f(v * v * kGaussLog2); }
+__device__ __forceinline__ float sigmoidf(float v) { return 1.0f / (1.0f + __expf(-v)); }
+// torch.nn.Softplus(beta=1, threshold=20)
+__device__ __forceinline__ float softplusf(float v) { return v > 20.0f ? v : log1pf(__expf(v)); }
+
+// Degree-3 real spherical harmonics of a unit vector in the order of network.py:38-77.
+__device__ __forceinline__ void sh16(float x, float y, float z, float* o)
+{
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    o[0] = 0.28209479177387814f;
+    o[1] = 0.4886025119029199f * y; o[2] = 0.4886025119029199f * z; o[3] = 0.4886025119029199f * x;
+    o[4] = 1.0925484305920792f * xy; o[5] = -1.0925484305920792f * yz;
+    o[6] = 0.31539156525252005f * (2.0f * zz - xx - yy);
+    o[7] = -1.0925484305920792f * xz; o[8] = 0.5462742152960396f * (xx - yy);
+    o[9] = -0.5900435899266435f * y * (3.0f * xx - yy); o[10] = 2.890611442640554f * xy * z;
+    o[11] = -0.4570457994644658f * y * (4.0f * zz - xx - yy);
+    o[12] = 0.3731763325901154f * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+    o[13] = -0.4570457994644658f * x * (4.0f * zz - xx - yy);
+    o[14] = 1.445305721320277f * z * (xx - yy); o[15] = -0.5900435899266435f * x * (xx - 3.0f * yy);
+}
+
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// store 8 values as the hi tile chunk and (SPLIT) their bf16 residuals as the lo tile chunk
+template <bool SPLIT>
+__device__ __forceinline__ void store8_hl(unsigned char* Thi, int chi, unsigned char* Tlo, int clo, int row, const float* v)
+{
+    umma::tile_store8(Thi, row, chi, v);
+    if (SPLIT) {
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = v[j] - bf16_round(v[j]);
+        umma::tile_store8(Tlo, row, clo, r);
+    }
+}
+
+// W[out, in] (row-major f32, nn.Linear layout) -> rows [row0, row0+out) of a bf16 tile: hi part in
+// columns [0, in), and in SPLIT mode the lo part either in columns [32, 32+in) of the same tile
+// (lo_tile == tile, needs in <= 32) or in columns [0, in) of `lo_tile`.
+template <bool SPLIT>
+__device__ void stage_weight(unsigned char* tile, unsigned char* lo_tile, int row0, const float* __restrict__ W, int out,
+                             int in, int flat, int tid, int nthreads)
+{
+    const int rs = flat ? 1 : in, cs = flat ? out : 1;      // element (r, col) at W[r * rs + col * cs]
+    const bool packed = (lo_tile == tile);
+    for (int t = tid; t < out * 8; t += nthreads) {
+        const int r = t >> 3, c = t & 7;
+        float hi[8], lo[8];
+        const int src_c = (SPLIT && packed && c >= 4) ? c - 4 : c;     // packed lo chunks mirror chunks 0..3
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = src_c * 8 + j;
+            const float w = col < in ? W[r * rs + col * cs] : 0.0f;
+            hi[j] = w;
+            lo[j] = w - bf16_round(w);
+        }
+        if (SPLIT && packed) {
+            umma::tile_store8(tile, row0 + r, c, c >= 4 ? lo : hi);
+        } else {
+            umma::tile_store8(tile, row0 + r, c, hi);
+            if (SPLIT) umma::tile_store8(lo_tile, row0 + r, c, lo);
+        }
+    }
+}
+__device__ inline void zero_tile_rows(unsigned char* tile, int rows, int tid, int nthreads)
+{
+    for (int t = tid; t < rows * 8; t += nthreads) umma::tile_zero8(tile, t >> 3, t & 7);
+}
+
+template <bool SPLIT>
+__device__ void stage_all_weights(unsigned char* smem, const DecoderParams& p, const float* __restrict__ mask32, int tid, int nthreads)
+{
+    zero_tile_rows(smem + oWh, 16, tid, nthreads);
+    zero_tile_rows(smem + oW5, 16, tid, nthreads);
+    if (SPLIT) zero_tile_rows(smem + oW5l, 16, tid, nthreads);
+    __syncthreads();
+    stage_weight<SPLIT>(smem + oW1, smem + oW1, 0, p.W1, 64, 32, p.flat, tid, nthreads);
+    stage_weight<SPLIT>(smem + oW2, smem + oW2l, 0, p.W2, 64, 64, p.flat, tid, nthreads);
+    stage_weight<SPLIT>(smem + oW3, smem + oW3l, 0, p.W3, 64, 48, p.flat, tid, nthreads);
+    stage_weight<SPLIT>(smem + oW4, smem + oW4l, 0, p.W4, 64, 64, p.flat, tid, nthreads);
+    stage_weight<SPLIT>(smem + oW5, smem + oW5l, 0, p.W5, 3, 64, p.flat, tid, nthreads);
+    stage_weight<SPLIT>(smem + oWh, smem + oWh, 0, p.Ws, 1, 32, p.flat, tid, nthreads);
+    stage_weight<SPLIT>(smem + oWh, smem + oWh, 1, p.Wd, 3, 32, p.flat, tid, nthreads);
+    stage_weight<SPLIT>(smem + oWh, smem + oWh, 4, p.Wt, 3, 32, p.flat, tid, nthreads);
+    float* b = reinterpret_cast<float*>(smem + off_bias<SPLIT>());
+    for (int i = tid; i < nB; i += nthreads) {
+        float v = 0.0f;
+        if (i < 64) v = p.b1[i];
+        else if (i < 128) v = p.b2[i - 64];
+        else if (i < 144) { const int j = i - 128; v = j == 0 ? p.bs[0] : (j < 4 ? p.bd[j - 1] : (j < 7 ? p.bt[j - 4] : 0.0f)); }
+        else if (i < 208) v = p.b3[i - 144];
+        else if (i < 272) v = p.b4[i - 208];
+        else { const int j = i - 272; v = j < 3 ? p.b5[j] : 0.0f; }
+        b[i] = v;
+    }
+    float* m = reinterpret_cast<float*>(smem + off_mask<SPLIT>());
+    for (int i = tid; i < 32; i += nthreads) m[i] = mask32 ? mask32[i] : 1.0f;
+    float* sg = reinterpret_cast<float*>(smem + off_small<SPLIT>());
+    for (int i = tid; i < 16; i += nthreads) sg[i] = 0.0f;
+}
+
+// Forward GEMM D (+)= A W^T over `nk` k-steps, issued by one thread.  A = (a_hi tile from k-step
+// a_hi_k, a_lo tile from a_lo_k), W likewise; in SPLIT mode three MMAs per k-step.
+template <bool SPLIT>
+__device__ __forceinline__ void fwd_gemm(uint32_t d, uint32_t a_hi, int a_hi_k, uint32_t a_lo, int a_lo_k, uint32_t w_hi,
+                                         int w_hi_k, uint32_t w_lo, int w_lo_k, int nk, uint32_t idesc, bool accumulate)
+{
+    for (int k = 0; k < nk; ++k)
+        umma::mma_bf16(d, umma::desc_kmajor(a_hi, a_hi_k + k), umma::desc_kmajor(w_hi, w_hi_k + k), idesc, accumulate || k > 0);
+    if (SPLIT) {
+        for (int k = 0; k < nk; ++k)
+            umma::mma_bf16(d, umma::desc_kmajor(a_lo, a_lo_k + k), umma::desc_kmajor(w_hi, w_hi_k + k), idesc, 1);
+        for (int k = 0; k < nk; ++k)
+            umma::mma_bf16(d, umma::desc_kmajor(a_hi, a_hi_k + k), umma::desc_kmajor(w_lo, w_lo_k + k), idesc, 1);
+    }
+}
+
+// The tiles one forward pass writes.  Forward kernel: a1 == a3, H == a4, g* unused.
+struct Tiles {
+    unsigned char *A0, *a1, *g1, *H, *a3, *g3, *a4, *g4, *LOa, *LOb;
+};
+
+// Per-thread context shared by the forward stages
+template <bool SPLIT>
+struct Ctx {
+    unsigned char* smem;
+    uint64_t* bar;
+    uint32_t tmem, lane_addr, phase;
+    int tid;
+    const float* bias;
+    const float* mask;
+    __device__ __forceinline__ void sync_operands()
+    {   // my shared-memory stores and TMEM loads are done -> the next MMAs may run
+        umma::fence_async_smem();
+        umma::tc_fence_before();
+        __syncthreads();
+        umma::tc_fence_after();
+    }
+    __device__ __forceinline__ void wait_mma()
+    {
+        umma::mbar_wait(bar, phase);
+        phase ^= 1u;
+        umma::tc_fence_after();
+    }
+};
+
+// Operand row of one sample: A0 = [x_hi (0..31) | SH_hi (32..47) | SH_lo (48..63)], LOb = [x_lo (0..31)].
+// x = the 32 (already masked) features, sh = the 16 SH coefficients of the unit view direction.
+template <bool SPLIT>
+__device__ __forceinline__ void store_input_row(const Tiles& T, int tid, const float* x, const float* sh)
+{
+#pragma unroll
+    for (int q = 0; q < 4; ++q) store8_hl<SPLIT>(T.A0, q, T.LOb, q, tid, x + 8 * q);
+    store8_hl<SPLIT>(T.A0, 4, T.A0, 6, tid, sh);
+    store8_hl<SPLIT>(T.A0, 5, T.A0, 7, tid, sh + 8);
+    if (!SPLIT) { umma::tile_zero8(T.A0, tid, 6); umma::tile_zero8(T.A0, tid, 7); }
+}
+
+// The decoder layers of one tile up to (and including) the L5 GEMM, from operand rows already in
+// A0 / LOb.  Writes the operand tiles, returns sigma/diffuse/tint activated in head[0..6]
+// (torch semantics) and their pre-activations in zh[0..6]; the specular pre-activations are left
+// in TMEM columns cDh..cDh+2.
+template <bool SPLIT, bool TRAIN>
+__device__ __forceinline__ void forward_layers(Ctx<SPLIT>& c, const Tiles& T, float* head, float* zh)
+{
+    unsigned char* smem = c.smem;
+    const int tid = c.tid;
+    const uint32_t tmem = c.tmem, lane_addr = c.lane_addr;
+    const float* bias = c.bias;
+    const uint32_t aA0 = umma::smem_u32(T.A0), aa1 = umma::smem_u32(T.a1), aH = umma::smem_u32(T.H), aa3 = umma::smem_u32(T.a3),
+                   aa4 = umma::smem_u32(T.a4), aLOa = umma::smem_u32(T.LOa), aLOb = umma::smem_u32(T.LOb);
+    const uint32_t aW1 = umma::smem_u32(smem + oW1), aW2 = umma::smem_u32(smem + oW2), aW3 = umma::smem_u32(smem + oW3),
+                   aW4 = umma::smem_u32(smem + oW4), aWh = umma::smem_u32(smem + oWh), aW5 = umma::smem_u32(smem + oW5),
+                   aW2l = umma::smem_u32(smem + oW2l), aW3l = umma::smem_u32(smem + oW3l), aW4l = umma::smem_u32(smem + oW4l),
+                   aW5l = umma::smem_u32(smem + oW5l);
+    constexpr uint32_t id64 = umma::idesc_bf16(128, 64, 0, 0), id16 = umma::idesc_bf16(128, 16, 0, 0);
+
+    c.sync_operands();
+    // ---- L1: Da = x W1^T (K = 32)
+    if (tid == 0) {
+        fwd_gemm<SPLIT>(tmem + cDa, aA0, 0, aLOb, 0, aW1, 0, aW1, 2, 2, id64, false);
+        umma::mma_commit(c.bar);
+    }
+    c.wait_mma();
+    float v[32], g[32];
+    // Gaussian layer epilogue: a = exp(-50 z^2) -> (Ta, lo in Tlo);  TRAIN: g = da/dz = -100 z a -> Tg
+    auto gauss_epilogue = [&](int col, int boff, unsigned char* Ta, unsigned char* Tlo, unsigned char* Tg) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            umma::tmem_ld32(tmem + col + lane_addr + 32 * h, v);
+            umma::tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float z = v[j] + bias[boff + 32 * h + j];
+                const float a = gauss_act(z);
+                v[j] = a;
+                if (TRAIN) g[j] = -100.0f * z * a;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                store8_hl<SPLIT>(Ta, 4 * h + q, Tlo, 4 * h + q, tid, v + 8 * q);
+                if (TRAIN) umma::tile_store8_f16(Tg, tid, 4 * h + q, g + 8 * q);   // fp16: |g| <= 6.1, read back element-wise only
+            }
+        }
+    };
+    gauss_epilogue(cDa, oB1, T.a1, T.LOa, T.g1);
+    c.sync_operands();
+    // ---- L2: Db = h1 W2^T (K = 64)
+    if (tid == 0) {
+        fwd_gemm<SPLIT>(tmem + cDb, aa1, 0, aLOa, 0, aW2, 0, aW2l, 0, 4, id64, false);
+        umma::mma_commit(c.bar);
+    }
+    c.wait_mma();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        umma::tmem_ld32(tmem + cDb + lane_addr + 32 * h, v);
+        umma::tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += bias[oB2 + 32 * h + j];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) store8_hl<SPLIT>(T.H, 4 * h + q, T.LOb, 4 * h + q, tid, v + 8 * q);
+    }
+    c.sync_operands();
+    // ---- heads: Dh = H[0:32] Wh^T (K = 32, N = 16);   L3: Da = [H[32:64] | SH] W3^T (K = 48)
+    if (tid == 0) {
+        fwd_gemm<SPLIT>(tmem + cDh, aH, 0, aLOb, 0, aWh, 0, aWh, 2, 2, id16, false);
+        fwd_gemm<SPLIT>(tmem + cDa, aH, 2, aLOb, 2, aW3, 0, aW3l, 0, 2, id64, false);
+        fwd_gemm<SPLIT>(tmem + cDa, aA0, 2, aA0, 3, aW3, 2, aW3l, 2, 1, id64, true);
+        umma::mma_commit(c.bar);
+    }
+    c.wait_mma();
+    {
+        float z[16];
+        umma::tmem_ld16(tmem + cDh + lane_addr, z);
+        umma::tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 7; ++j) zh[j] = z[j] + bias[oBh + j];
+        head[0] = softplusf(zh[0]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            head[4 + j] = sigmoidf(zh[1 + j]);     // diffuse
+            head[1 + j] = sigmoidf(zh[4 + j]);     // tint
+        }
+    }
+    gauss_epilogue(cDa, oB3, T.a3, T.LOa, T.g3);
+    c.sync_operands();
+    // ---- L4: Db = a3 W4^T (K = 64)
+    if (tid == 0) {
+        fwd_gemm<SPLIT>(tmem + cDb, aa3, 0, aLOa, 0, aW4, 0, aW4l, 0, 4, id64, false);
+        umma::mma_commit(c.bar);
+    }
+    c.wait_mma();
+    gauss_epilogue(cDb, oB4, T.a4, T.LOb, T.g4);
+    c.sync_operands();
+    // ---- L5: Dh = a4 W5^T (K = 64, N = 16)
+    if (tid == 0) {
+        fwd_gemm<SPLIT>(tmem + cDh, aa4, 0, aLOb, 0, aW5, 0, aW5l, 0, 4, id16, false);
+        umma::mma_commit(c.bar);
+    }
+    c.wait_mma();
+}
+
+// Training-side input: features from HBM times the level mask, SH of d / (|d| + 1e-8) (network.py:172-190).
+template <bool SPLIT, bool TRAIN>
+__device__ __forceinline__ void forward_tile(Ctx<SPLIT>& c, const Tiles& T, const float* __restrict__ feats,
+                                             const float* __restrict__ rays_d, int n, bool live, int S, float* head, float* zh,
+                                             f3& d, float& dn)
+{
+    const float* mask = c.mask;
+    float x[32], sh[16];
+    if (live) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(feats + (size_t)n * 32 + q * 4));
+            x[4 * q + 0] = a.x * mask[4 * q + 0]; x[4 * q + 1] = a.y * mask[4 * q + 1];
+            x[4 * q + 2] = a.z * mask[4 * q + 2]; x[4 * q + 3] = a.w * mask[4 * q + 3];
+        }
+        d = ld3(rays_d + 3 * (size_t)(n / S));
+        dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+        const float inv = 1.0f / (dn + 1e-8f);
+        sh16(d.x * inv, d.y * inv, d.z * inv, sh);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sh[j] = 0.0f;
+    }
+    store_input_row<SPLIT>(T, c.tid, x, sh);
+    forward_layers<SPLIT, TRAIN>(c, T, head, zh);
+}
+
+}  // namespace dec

@@ -1,0 +1,305 @@
+// Render-side fused field evaluation: fp16 hash-table encode + decoder MLP on the tensor cores +
+// per-sample alpha and tile-overlap blending, one kernel, sm_100a.
+//
+// Replaces (behaviour, not code) the reference's per-thread-MLP kernels
+//   pts_inference        hashgrid/src/rendering_kernel.cu:467-621  (foreground, <= 4 overlapping tiles per sample)
+//   bg_pts_inference     :871-1008, 1172-1208                      (background, blend weights per ray)
+//   bg_pts_inference_v2  :1011-1171                                (background, one tile slot per call)
+// with get_multilevel_features<16> (:79-114) and Decoder::inference (hashgrid/include/decoder.h:169-218).
+//
+// The reference evaluates the 13 994-parameter MLP per thread out of global memory.  Here a CTA owns
+// 128 consecutive samples, walks the distinct tile ids present among them in ascending order (the
+// order in which the reference visits a sample's slots), stages that tile's weights once as bf16(x3)
+// operand tiles (decoder_core.cuh) and runs the layers as tcgen05 MMAs with the accumulators in TMEM;
+// rows whose sample does not belong to the current tile (or whose occupancy cell is empty) carry
+// zeros and are ignored in the epilogue.  Nothing but the three output rows per sample goes to HBM.
+#include "decoder_core.cuh"
+#include <cuda_fp16.h>
+using namespace dec;
+
+namespace {
+
+constexpr int kMaxPts = 4;
+enum Mode { kFore = 0, kBackBlend = 1, kBackSlot = 2 };
+
+__device__ __forceinline__ uint32_t hash3(int x, int y, int z, uint32_t mask)
+{
+    return (((uint32_t)x) ^ ((uint32_t)y * 2654435761u) ^ ((uint32_t)z * 805459861u)) & mask;
+}
+
+// 16-level trilinear encode from an fp16 table (rendering_kernel.cu:79-114): u in [0,1]^3,
+// v = u * (res - 1), corner order c = 4 dx + 2 dy + dz, accumulation in that order.
+__device__ __forceinline__ void encode16(f3 u, const int* __restrict__ res, const __half2* __restrict__ table, uint32_t T, float* x)
+{
+    const uint32_t mask = T - 1u;
+#pragma unroll 2
+    for (int l = 0; l < 16; ++l) {
+        const float vx = u.x * (float)(res[3 * l] - 1), vy = u.y * (float)(res[3 * l + 1] - 1), vz = u.z * (float)(res[3 * l + 2] - 1);
+        const int ix = (int)vx, iy = (int)vy, iz = (int)vz;
+        const float ox = vx - (float)ix, oy = vy - (float)iy, oz = vz - (float)iz;
+        const __half2* tl = table + (size_t)l * T;
+        float2 f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = __half22float2(__ldg(tl + hash3(ix + ((k >> 2) & 1), iy + ((k >> 1) & 1), iz + (k & 1), mask)));
+        const float ax = 1 - ox, ay = 1 - oy, az = 1 - oz;
+        const float w[8] = {ax * ay * az, ax * ay * oz, ax * oy * az, ax * oy * oz, ox * ay * az, ox * ay * oz, ox * oy * az, ox * oy * oz};
+        float a = 0.0f, b = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a += w[k] * f[k].x; b += w[k] * f[k].y; }
+        x[2 * l] = a; x[2 * l + 1] = b;
+    }
+}
+
+struct InferArgs {
+    const float *rays_o, *rays_d, *z_vals, *dists;
+    const short* slots;          // kFore: block_idxs [B*S,4]; kBack*: per-ray ids [B,4]
+    const float* blend;          // kBackBlend: blend weights [B,4]
+    const __half2* tables;       // [nb,16,T]
+    const float* params;         // [nb,13994]
+    const int* resolution;       // [nb,16,3]
+    const unsigned char* grid_occ;
+    const long long* grid_starts;
+    const int* grid_log2dim;
+    const float *corners, *sizes;
+    float *out_diffuse, *out_specular, *out_alpha;
+    int B, S, step;
+    uint32_t T;
+};
+
+template <bool SPLIT, int MODE>
+__global__ void __launch_bounds__(kRows, 1)
+infer_kernel(InferArgs a, int num_tiles)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* T0 = smem + off_tiles<SPLIT>();
+    unsigned char* T1 = T0 + kTile;
+    unsigned char* T2 = T1 + kTile;
+    unsigned char* LOa = SPLIT ? T2 + kTile : T1;
+    unsigned char* LOb = SPLIT ? LOa + kTile : T2;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ int next_id;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0) umma::tmem_alloc<256>(&tmem_slot);
+    if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_fence_init(); }
+    umma::fence_async_smem();
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    Ctx<SPLIT> c;
+    c.smem = smem; c.bar = &bar; c.tmem = tmem_slot; c.lane_addr = (uint32_t)(32 * (warp & 3)) << 16; c.phase = 0; c.tid = tid;
+    c.bias = reinterpret_cast<const float*>(smem + off_bias<SPLIT>());
+    c.mask = reinterpret_cast<const float*>(smem + off_mask<SPLIT>());
+    const Tiles Tl{T0, T1, nullptr, T2, T1, nullptr, T2, nullptr, LOa, LOb};
+    int staged = -1;
+    const long long total = (long long)a.B * a.S;
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long n = (long long)tile * kRows + tid;
+        const bool live = n < total;
+        const int ray = live ? (int)(n / a.S) : 0, k = live ? (int)(n % a.S) : 0;
+        short ids[kMaxPts] = {-1, -1, -1, -1};
+        float zv = -1.0f, step_len = 0.0f;
+        f3 o = mk3(0, 0, 0), d = mk3(0, 0, 1);
+        if (live) {
+            o = ld3(a.rays_o + 3 * (size_t)ray); d = ld3(a.rays_d + 3 * (size_t)ray);
+            zv = a.z_vals[n];
+            if (MODE == kFore) {
+                const short4 s4 = *reinterpret_cast<const short4*>(a.slots + (size_t)n * kMaxPts);
+                ids[0] = s4.x; ids[1] = s4.y; ids[2] = s4.z; ids[3] = s4.w;
+                step_len = a.dists[n];
+            } else {
+                const short* s = a.slots + (size_t)ray * kMaxPts;
+                if (MODE == kBackSlot) ids[0] = s[a.step];
+                else { ids[0] = s[0]; ids[1] = s[1]; ids[2] = s[2]; ids[3] = s[3]; }
+                step_len = (k == a.S - 1) ? 10000000.0f : a.z_vals[n + 1] - zv;
+            }
+            // slots after the first -1 are ignored (the reference breaks out of its slot loop there)
+#pragma unroll
+            for (int i = 1; i < kMaxPts; ++i) if (ids[i - 1] == -1) ids[i] = -1;
+        }
+        const f3 p = o + zv * d;
+        const f3 dn = d * rsqrtf(dot3(d, d));                 // normalize(): decoder.h:201, no epsilon
+        float sh[16];
+        sh16(dn.x, dn.y, dn.z, sh);
+        const float dlen = sqrtf(dot3(d, d));
+        f3 acc_d = mk3(0, 0, 0), acc_s = mk3(0, 0, 0);
+        float acc_a = 0.0f, wsum = 0.0f;
+
+        int cur = -1;
+        while (true) {
+            // next tile id present in this CTA's samples, ascending
+            int mine = 0x7fffffff;
+#pragma unroll
+            for (int i = 0; i < kMaxPts; ++i) if (ids[i] > cur && ids[i] < mine) mine = ids[i];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, off));
+            if (tid == 0) next_id = 0x7fffffff;
+            __syncthreads();
+            if (lane == 0 && mine != 0x7fffffff) atomicMin(&next_id, mine);
+            __syncthreads();
+            const int b = next_id;
+            __syncthreads();                                   // everyone has read next_id before it is reset
+            if (b == 0x7fffffff) break;
+            cur = b;
+            int slot = -1;
+#pragma unroll
+            for (int i = 0; i < kMaxPts; ++i) if (ids[i] == b && slot < 0) slot = i;
+            const bool member = slot >= 0;
+
+            // ---- geometry of this sample in tile b
+            const f3 bc = ld3(a.corners + 3 * b), bs = ld3(a.sizes + 3 * b);
+            f3 u = mk3(0, 0, 0);
+            float w = 0.0f;
+            bool active = false;
+            if (member) {
+                if (MODE == kFore) {
+                    const f3 q = mk3((p.x - bc.x) / bs.x, (p.y - bc.y) / bs.y, (p.z - bc.z) / bs.z);          // [0,1]
+                    const f3 dis = mk3((0.5f - fabsf(q.x - 0.5f)) * bs.x, (0.5f - fabsf(q.y - 0.5f)) * bs.y, (0.5f - fabsf(q.z - 0.5f)) * bs.z);
+                    if (dis.x != 0 && dis.z != 0) w = dis.x * dis.z;
+                    else if (dis.x != 0) w = dis.x;
+                    else if (dis.z != 0) w = dis.z;
+                    const int lx = a.grid_log2dim[3 * b], ly = a.grid_log2dim[3 * b + 1], lz = a.grid_log2dim[3 * b + 2];
+                    const int gx = min(max((int)(q.x * (float)(1 << lx)), 0), (1 << lx) - 1);
+                    const int gy = min(max((int)(q.y * (float)(1 << ly)), 0), (1 << ly) - 1);
+                    const int gz = min(max((int)(q.z * (float)(1 << lz)), 0), (1 << lz) - 1);
+                    active = a.grid_occ[a.grid_starts[b] + ((gx << (ly + lz)) | (gy << lz) | gz)] != 0;
+                    u = mk3(q.x * 0.5f + 0.25f, q.y * 0.5f + 0.25f, q.z * 0.5f + 0.25f);                       // [0.25, 0.75]
+                } else {
+                    // contraction of the 2x-normalised position (rendering_kernel.cu:1060-1095)
+                    float q[3] = {2.0f * (p.x - bc.x) / bs.x - 1.0f, 2.0f * (p.y - bc.y) / bs.y - 1.0f, 2.0f * (p.z - bc.z) / bs.z - 1.0f};
+                    float nrm = fabsf(q[0]);
+                    if (fabsf(q[1]) > nrm) nrm = fabsf(q[1]);
+                    if (fabsf(q[2]) > nrm) nrm = fabsf(q[2]);
+                    const float ratio = (2.0f - 1.0f / nrm) / nrm;
+                    u = mk3((q[0] * ratio + 2.0f) * 0.25f, (q[1] * ratio + 2.0f) * 0.25f, (q[2] * ratio + 2.0f) * 0.25f);
+                    w = MODE == kBackBlend ? a.blend[(size_t)ray * kMaxPts + slot] : 1.0f;
+                    active = true;
+                }
+            }
+            if (!__syncthreads_or(active)) {                   // nobody needs the MLP for this tile
+                if (member) wsum += w;
+                continue;
+            }
+            if (staged != b) {
+                stage_all_weights<SPLIT>(smem, flat_params(a.params + (size_t)b * 13994), nullptr, tid, kRows);
+                staged = b;
+            }
+            float x[32];
+            if (active) {
+                encode16(u, a.resolution + (size_t)b * 48, a.tables + (size_t)b * 16 * a.T, a.T, x);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+            }
+            store_input_row<SPLIT>(Tl, tid, x, sh);
+            float head[10], zh[7];
+            forward_layers<SPLIT, false>(c, Tl, head, zh);
+            float zs[16];
+            umma::tmem_ld16(c.tmem + cDh + c.lane_addr, zs);
+            umma::tc_wait_ld();
+            if (active) {
+                // Decoder::inference activations (decoder.h:134-146): softplus without threshold, expf sigmoids
+                const float sigma = logf(1.0f + expf(zh[0]));
+                const f3 dif = mk3(1.0f / (1.0f + expf(-zh[1])), 1.0f / (1.0f + expf(-zh[2])), 1.0f / (1.0f + expf(-zh[3])));
+                const f3 tint = mk3(1.0f / (1.0f + expf(-zh[4])), 1.0f / (1.0f + expf(-zh[5])), 1.0f / (1.0f + expf(-zh[6])));
+                const f3 spe = mk3(tint.x / (1.0f + expf(-(zs[0] + c.bias[oB5 + 0]))), tint.y / (1.0f + expf(-(zs[1] + c.bias[oB5 + 1]))),
+                                   tint.z / (1.0f + expf(-(zs[2] + c.bias[oB5 + 2]))));
+                const float al = MODE == kFore ? 1.0f - expf(-1.0f * sigma * step_len * dlen) : 1.0f - expf(-1.0f * sigma * step_len);
+                acc_d = acc_d + (w * al) * dif;
+                acc_s = acc_s + (w * al) * spe;
+                acc_a += w * al;
+            }
+            if (member) wsum += w;
+        }
+        if (live) {
+            bool write = true;
+            if (MODE == kBackSlot) {
+                write = ids[0] != -1;                          // rays without a tile in this slot keep the caller's rows
+            } else if (wsum > 0) {
+                const float inv = 1.0f / wsum;                 // float3 /= float: multiply by the reciprocal
+                acc_d = acc_d * inv; acc_s = acc_s * inv; acc_a = acc_a * inv;
+            }
+            if (write) {
+                st3(a.out_diffuse + 3 * (size_t)n, acc_d);
+                st3(a.out_specular + 3 * (size_t)n, acc_s);
+                a.out_alpha[n] = acc_a;
+            }
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free<256>(c.tmem);
+}
+
+int g_infer_split = 1;
+
+template <int MODE>
+int launch(const InferArgs& a, void* stream, const char* name)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(infer_kernel<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<true>());
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(infer_kernel<false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<false>());
+        if (e != cudaSuccess) { snrf_set_error("%s: %s", name, cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    const long long total = (long long)a.B * a.S;
+    const int num_tiles = snrf_div_up(total, kRows);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (g_infer_split) {
+        int grid = snrf_sm_count();
+        if (grid > num_tiles) grid = num_tiles;
+        infer_kernel<true, MODE><<<grid, kRows, fwd_smem<true>(), s>>>(a, num_tiles);
+    } else {
+        int grid = snrf_sm_count() * 2;
+        if (grid > num_tiles) grid = num_tiles;
+        infer_kernel<false, MODE><<<grid, kRows, fwd_smem<false>(), s>>>(a, num_tiles);
+    }
+    SNRF_RETURN_LAUNCH(name);
+}
+
+}  // namespace
+
+// ------------------------------- C ABI --------------------------------------
+SNRF_API void snrf_infer_set_precision(int split) { g_infer_split = split ? 1 : 0; }
+
+SNRF_API int snrf_pts_inference(const float* rays_o, const float* rays_d, const float* z_vals, const float* dists,
+                                const short* block_idxs, const void* features_tables, const float* params, const int* resolution,
+                                const unsigned char* grid_occupied, const long long* grid_starts, const int* grid_log2dim,
+                                const float* corners, const float* sizes, float* diffuse, float* specular, float* alpha, int B,
+                                int S, int T, void* stream)
+{
+    SNRF_CHECK_ARG(T > 0 && (T & (T - 1)) == 0, "snrf_pts_inference: hashmap size must be a power of two (got %d)", T);
+    if (B <= 0 || S <= 0) return 0;
+    InferArgs a{rays_o, rays_d, z_vals, dists, block_idxs, nullptr, (const __half2*)features_tables, params, resolution, grid_occupied,
+                grid_starts, grid_log2dim, corners, sizes, diffuse, specular, alpha, B, S, 0, (uint32_t)T};
+    return launch<kFore>(a, stream, "snrf_pts_inference");
+}
+
+SNRF_API int snrf_bg_pts_inference(const float* rays_o, const float* rays_d, const float* z_vals, const short* outgoing_bidxs,
+                                   const float* blend_weights, const float* corners, const float* sizes, const int* resolution,
+                                   const void* features_tables, const float* params, float* diffuse, float* specular, float* alpha,
+                                   int B, int S, int T, void* stream)
+{
+    SNRF_CHECK_ARG(T > 0 && (T & (T - 1)) == 0, "snrf_bg_pts_inference: hashmap size must be a power of two (got %d)", T);
+    if (B <= 0 || S <= 0) return 0;
+    InferArgs a{rays_o, rays_d, z_vals, nullptr, outgoing_bidxs, blend_weights, (const __half2*)features_tables, params, resolution, nullptr,
+                nullptr, nullptr, corners, sizes, diffuse, specular, alpha, B, S, 0, (uint32_t)T};
+    return launch<kBackBlend>(a, stream, "snrf_bg_pts_inference");
+}
+
+SNRF_API int snrf_bg_pts_inference_v2(const float* rays_o, const float* rays_d, const float* z_vals, const short* bg_idxs, int step,
+                                      const float* corners, const float* sizes, const int* resolution, const void* features_tables,
+                                      const float* params, float* diffuse, float* specular, float* alpha, int B, int S, int T,
+                                      void* stream)
+{
+    SNRF_CHECK_ARG(T > 0 && (T & (T - 1)) == 0, "snrf_bg_pts_inference_v2: hashmap size must be a power of two (got %d)", T);
+    SNRF_CHECK_ARG(step >= 0 && step < kMaxPts, "snrf_bg_pts_inference_v2: step must be in [0,4) (got %d)", step);
+    if (B <= 0 || S <= 0) return 0;
+    InferArgs a{rays_o, rays_d, z_vals, nullptr, bg_idxs, nullptr, (const __half2*)features_tables, params, resolution, nullptr,
+                nullptr, nullptr, corners, sizes, diffuse, specular, alpha, B, S, step, (uint32_t)T};
+    return launch<kBackSlot>(a, stream, "snrf_bg_pts_inference_v2");
+}

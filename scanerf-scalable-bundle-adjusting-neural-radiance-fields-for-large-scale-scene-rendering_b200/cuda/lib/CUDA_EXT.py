@@ -174,3 +174,104 @@ def adam_step_sparse(params, grad_params, exp_avg, exp_avg_sq, lr, beta1, beta2,
     """Extension: the same update over a tensor of ANY shape (dense addressing, 128-bit
     accesses), `step` 1-based, optionally clearing the consumed gradients in the same pass."""
     _adam(params, grad_params, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, int(step), False, zero_grad, dense=True)
+
+
+# ----------------------------------------------------------------------------- view selection
+def computeViewcost(rays_o, rays_d, pts, ks, rts, costs, height, width):
+    """cuda/include/view_selection.h -- costs [N_cam, B]: angle + distance cost of seeing pts[b] from
+    camera n (1 when behind the camera / outside its image).  rts are world->camera [N,3,4]."""
+    N, B = int(costs.shape[0]), int(costs.shape[1])
+    o, d, p = inp(rays_o, f32, "rays_o"), inp(rays_d, f32, "rays_d"), inp(pts, f32, "pts")
+    k, r = inp(ks, f32, "ks"), inp(rts, f32, "rts")
+    c = Out(costs, f32, "costs")
+    capi.check(capi.lib().snrf_view_cost(ptr(o), ptr(d), ptr(p), ptr(k), ptr(r), c.ptr, c_int(N), c_int(B),
+                                         c_int(int(height)), c_int(int(width)), capi.stream()), "snrf_view_cost")
+    c.done()
+
+
+def proj2neighbor_forward(pts, ks, rts, nei_views, nei_valid, nei_origin, nei_direction, grid):
+    """cuda/include/view_selection.h -- project pts [B,3] into their K chosen neighbour views."""
+    B, K = int(pts.shape[0]), int(nei_views.shape[1])
+    p, k, r = inp(pts, f32, "pts"), inp(ks, f32, "ks"), inp(rts, f32, "rts")
+    nv, ok = inp(nei_views, i32, "nei_views"), inp(nei_valid, b8, "nei_valid")
+    no, nd, g = Out(nei_origin, f32, "nei_origin"), Out(nei_direction, f32, "nei_direction"), Out(grid, f32, "grid")
+    capi.check(capi.lib().snrf_proj2nei_fwd(ptr(p), ptr(k), ptr(r), ptr(nv), ptr(ok), no.ptr, nd.ptr, g.ptr, c_int(B), c_int(K),
+                                            capi.stream()), "snrf_proj2nei_fwd")
+    no.done(); nd.done(); g.done()
+
+
+def proj2neighbor_backward(pts, ks, rts, nei_views, nei_valid, dL_dgrid, grad_pts, grad_rts):
+    """cuda/include/view_selection.h -- accumulates grad_pts [B,3] and grad_rts [N,3,4]."""
+    B, K, N = int(pts.shape[0]), int(nei_views.shape[1]), int(ks.shape[0])
+    p, k, r = inp(pts, f32, "pts"), inp(ks, f32, "ks"), inp(rts, f32, "rts")
+    nv, ok, dg = inp(nei_views, i32, "nei_views"), inp(nei_valid, b8, "nei_valid"), inp(dL_dgrid, f32, "dL_dgrid")
+    gp, gr = Out(grad_pts, f32, "grad_pts"), Out(grad_rts, f32, "grad_rts")
+    capi.check(capi.lib().snrf_proj2nei_bwd(ptr(p), ptr(k), ptr(r), ptr(nv), ptr(ok), ptr(dg), gp.ptr, gr.ptr, c_int(B), c_int(K),
+                                            c_int(N), capi.stream()), "snrf_proj2nei_bwd")
+    gp.done(); gr.done()
+
+
+# ----------------------------------------------------------------------------- image sampling
+def _img_dims(src, grid):
+    return int(src.shape[0]), int(grid.shape[1]), int(src.shape[1]), int(src.shape[2])
+
+
+def grid_sample_forward_cuda(src, grid, out, mask):
+    """cuda/include/grid_sample.h -- bilinear (align-corners) fetch from uint8 images [N,H,W,3] at
+    grid [N,B,1,2] in [-1,1]; out [N,B,1,3] f32, mask [N,B,1,1] bool (False + zero colour outside)."""
+    N, B, H, W = _img_dims(src, grid)
+    s, g = inp(src, u8, "src"), inp(grid, f32, "grid")
+    o, m = Out(out, f32, "out"), Out(mask, b8, "mask")
+    capi.check(capi.lib().snrf_grid_sample_fwd(ptr(s), ptr(g), o.ptr, m.ptr, c_int(N), c_int(B), c_int(H), c_int(W),
+                                               capi.stream()), "snrf_grid_sample_fwd")
+    o.done(); m.done()
+
+
+def grid_sample_backward_cuda(src, grid, grad_in, grad_grid):
+    N, B, H, W = _img_dims(src, grid)
+    s, g, gi = inp(src, u8, "src"), inp(grid, f32, "grid"), inp(grad_in, f32, "grad_in")
+    gg = Out(grad_grid, f32, "grad_grid")
+    capi.check(capi.lib().snrf_grid_sample_bwd(ptr(s), ptr(g), ptr(gi), gg.ptr, c_int(N), c_int(B), c_int(H), c_int(W),
+                                               capi.stream()), "snrf_grid_sample_bwd")
+    gg.done()
+
+
+def gaussian_grid_sample_forward_cuda(src, grid, out, mask, sigma, max_dis):
+    """cuda/include/grid_sample.h -- Gaussian-window resampling exp(-d^2/sigma^2) over (2 max_dis + 2)^2 pixels."""
+    N, B, H, W = _img_dims(src, grid)
+    s, g = inp(src, u8, "src"), inp(grid, f32, "grid")
+    o, m = Out(out, f32, "out"), Out(mask, b8, "mask")
+    capi.check(capi.lib().snrf_gauss_sample_fwd(ptr(s), ptr(g), o.ptr, m.ptr, c_int(N), c_int(B), c_int(H), c_int(W),
+                                                c_float(float(sigma)), c_float(float(max_dis)), capi.stream()), "snrf_gauss_sample_fwd")
+    o.done(); m.done()
+
+
+def gaussian_grid_sample_backward_cuda(src, grid, grad_in, grad_grid, sigma, max_dis):
+    N, B, H, W = _img_dims(src, grid)
+    s, g, gi = inp(src, u8, "src"), inp(grid, f32, "grid"), inp(grad_in, f32, "grad_in")
+    gg = Out(grad_grid, f32, "grad_grid")
+    capi.check(capi.lib().snrf_gauss_sample_bwd(ptr(s), ptr(g), ptr(gi), gg.ptr, c_int(N), c_int(B), c_int(H), c_int(W),
+                                                c_float(float(sigma)), c_float(float(max_dis)), capi.stream()), "snrf_gauss_sample_bwd")
+    gg.done()
+
+
+def grid_sample_bool_cuda(src, grid, out):
+    """cuda/include/grid_sample.h -- nearest-pixel fetch from bool images [N,H,W]; entries that fall
+    outside the image keep the caller's value."""
+    N, B, H, W = _img_dims(src, grid)
+    s, g = inp(src, b8, "src"), inp(grid, f32, "grid")
+    o = Out(out, b8, "out")
+    capi.check(capi.lib().snrf_grid_sample_bool(ptr(s), ptr(g), o.ptr, c_int(N), c_int(B), c_int(H), c_int(W), capi.stream()),
+               "snrf_grid_sample_bool")
+    o.done()
+
+
+def proj2pixel_and_fetch_color(pts, Ks, C2Ws, RGBs, fetched_pixels, fetched_colors):
+    """cuda/include/helper.h -- project every point into every view (camera->world poses) and fetch a
+    bilinear colour from float images RGBs [N,H,W,3]; outputs [B,N,3]."""
+    B, N, H, W = int(pts.shape[0]), int(Ks.shape[0]), int(RGBs.shape[1]), int(RGBs.shape[2])
+    p, k, c, im = inp(pts, f32, "pts"), inp(Ks, f32, "Ks"), inp(C2Ws, f32, "C2Ws"), inp(RGBs, f32, "RGBs")
+    fp, fc = Out(fetched_pixels, f32, "fetched_pixels"), Out(fetched_colors, f32, "fetched_colors")
+    capi.check(capi.lib().snrf_proj2pixel_fetch(ptr(p), ptr(k), ptr(c), ptr(im), fp.ptr, fc.ptr, c_int(B), c_int(N), c_int(H),
+                                                c_int(W), capi.stream()), "snrf_proj2pixel_fetch")
+    fp.done(); fc.done()

@@ -54,10 +54,16 @@ def test_cpu_tensor_is_rejected():
                                       torch.ones(16, 3, dtype=torch.int32))
 
 
+# every name the reference's pybind modules export (cuda/binding.cpp:10-53, hashgrid/binding.cpp:9-44)
 REFERENCE_CUDA_EXT = """sample_insideout_block compute_ray_forward compute_ray_backward ray_aabb_intersection
-ray_aabb_intersection_v2 sample_points_contract sample_points_grid""".split()
+ray_aabb_intersection_v2 sample_points_contract sample_points_grid proj2pixel_and_fetch_color computeViewcost voxelize_mesh
+background_sampling_cuda adam_step_cuda adam_step_cuda_fp16 grid_sample_forward_cuda grid_sample_backward_cuda
+gaussian_grid_sample_forward_cuda gaussian_grid_sample_backward_cuda grid_sample_bool_cuda proj2neighbor_forward
+proj2neighbor_backward""".split()
 REFERENCE_HASHGRID = """embedding_forward_cuda embedding_backward_cuda embedding_bg_forward_cuda
-embedding_bg_backward_cuda""".split()
+embedding_bg_backward_cuda rendering_cuda ray_block_intersection sample_points prepare_points sort_by_key pts_inference
+accumulate_color ray_firsthit_block inverse_z_sampling bg_pts_inference bg_pts_inference_v2 get_last_block update_outgoing_bidx
+update_outgoing_bidx_v2 process_occupied_grid Sampler""".split()
 
 
 def test_reference_operator_names_present():

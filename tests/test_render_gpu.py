@@ -1,0 +1,227 @@
+"""GPU: the multi-tile inference renderer ops (csrc/render.cu, csrc/infer.cu behind the reference's
+HASHGRID operator names) against the UNMODIFIED reference extension rebuilt into
+oracle/_ref/HASHGRID.so, stage by stage on the same inputs, plus CPU restatements of the simple
+stages and of the fused field evaluation (C hash-encode oracle + torch decoder restatement).
+Bars: tile ids / tracing state / sample-to-tile assignment bit-exact; depths 1e-6; per-sample
+colours and alpha 1e-4 (the north star's composited-RGB tolerance)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_pkg, ref_module
+from oracle import native as on
+from oracle import torch_ref as tr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+MISS = 1e7
+
+
+def make_scene(nb=2, T=2 ** 14, seed=0, log2dim=(3, 2, 3)):
+    g = torch.Generator().manual_seed(seed)
+    corners = torch.tensor([[0.0, 0.0, 0.0], [8.0, 0.0, 1.0], [3.0, 0.0, 9.0]])[:nb].contiguous()
+    sizes = torch.tensor([[10.0, 6.0, 12.0], [10.0, 6.0, 12.0], [12.0, 6.0, 8.0]])[:nb].contiguous()
+    tables = (torch.randn(nb, 16, T, 2, generator=g) * 0.3).half()
+    res = torch.stack([torch.stack([(torch.tensor([16.0, 12.0, 20.0]) * (1.38 ** l)).int() for l in range(16)]) for _ in range(nb)]).int()
+    mlps = [tr.init_mlp(g) for _ in range(nb)]
+    for m in mlps:
+        for k in m:
+            if k.endswith("bias"):
+                m[k] = 0.05 * torch.randn(m[k].shape, generator=g)
+    params = torch.stack([torch.cat([torch.cat([m[k + ".bias"], m[k + ".weight"].t().flatten()]) for k in tr.MLP_KEYS]) for m in mlps])
+    assert params.shape == (nb, 13994)
+    n_cells = int(np.prod([2 ** v for v in log2dim]))
+    occ = torch.rand(nb * n_cells, generator=g) < 0.45
+    starts = (torch.arange(nb) * n_cells).long()
+    l2d = torch.tensor([list(log2dim)] * nb, dtype=torch.int32)
+    return dict(corners=corners, sizes=sizes, tables=tables, res=res.contiguous(), params=params.contiguous(), occ=occ, starts=starts,
+                l2d=l2d, mlps=mlps, nb=nb, T=T, n_cells=n_cells)
+
+
+def make_rays(B, seed):
+    g = torch.Generator().manual_seed(seed)
+    o = torch.tensor([9.0, 3.0, 6.0]) + torch.randn(B, 3, generator=g) * torch.tensor([6.0, 1.0, 5.0])
+    d = torch.nn.functional.normalize(torch.randn(B, 3, generator=g) * torch.tensor([1.0, 0.25, 1.0]), dim=-1)
+    d = d * (0.6 + torch.rand(B, 1, generator=g))
+    return o.contiguous(), d.contiguous()
+
+
+def dev(sc):
+    return {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in sc.items()}
+
+
+def both(fn_name, ours, ref, make_args):
+    """Run op `fn_name` of both modules on fresh copies of the same arguments; returns the two lists."""
+    a, b = make_args(), make_args()
+    getattr(ours, fn_name)(*a)
+    if ref is not None:
+        getattr(ref, fn_name)(*b)
+    torch.cuda.synchronize()
+    return a, (b if ref is not None else None)
+
+
+def _ops():
+    load_pkg()
+    from hashgrid.lib import HASHGRID as ours
+    return ours, ref_module("HASHGRID")
+
+
+@pytest.mark.parametrize("nb,B", [(1, 500), (3, 6000)])
+def test_render_pipeline_stage_by_stage(nb, B):
+    ours, ref = _ops()
+    sc = dev(make_scene(nb))
+    o, d = (t.to(DEV) for t in make_rays(B, nb * B))
+    S = 32
+    # ---- ray / tile intersections
+    (a, r) = both("ray_block_intersection", ours, ref, lambda: [o, d, sc["corners"], sc["sizes"], torch.full((B, nb, 2), MISS, device=DEV)])
+    isect = a[-1]
+    half = sc["sizes"] / 2
+    want = on.ray_aabb(o.cpu().numpy(), d.cpu().numpy(), (sc["corners"] + half).cpu().numpy(), sc["sizes"].cpu().numpy())
+    want = np.where(want == -1, MISS, want).reshape(B, nb, 2)
+    assert np.allclose(isect.cpu().numpy(), want, rtol=1e-6, atol=1e-6)
+    if r is not None:
+        assert torch.equal(isect, r[-1])
+    tracing_blocks = torch.argsort(isect[..., 0], dim=-1).int().contiguous()
+    # ---- occupancy dilation across overlapping tiles
+    fake = sc["occ"].clone()
+    fake_r = sc["occ"].clone()
+    for i in range(nb):
+        ours.process_occupied_grid(i, sc["n_cells"], sc["corners"], sc["sizes"], sc["occ"], sc["starts"], sc["l2d"], fake)
+        if ref is not None:
+            ref.process_occupied_grid(i, sc["n_cells"], sc["corners"], sc["sizes"], sc["occ"], sc["starts"], sc["l2d"], fake_r)
+    torch.cuda.synchronize()
+    assert bool((fake | ~sc["occ"]).all()), "dilation never clears a cell"
+    if ref is not None:
+        assert torch.equal(fake, fake_r)
+    if nb > 1:
+        assert int(fake.sum()) > int(sc["occ"].sum())
+    # ---- tracing loop: sample -> assign -> evaluate -> accumulate (two rounds exercise the resumable state)
+    tracing_idx = torch.zeros(B, 1, dtype=torch.int32, device=DEV)
+    z_start = torch.zeros(B, 1, device=DEV)
+    T_, dif, spe, dep = torch.ones(B, 1, device=DEV), torch.zeros(B, 3, device=DEV), torch.zeros(B, 3, device=DEV), torch.zeros(B, 1, device=DEV)
+    for rnd in range(2):
+        running = ((tracing_idx < nb) & (T_ > 1e-5)).contiguous()
+        mk = lambda: [o, d, sc["corners"], sc["sizes"], fake, sc["starts"], sc["l2d"], tracing_blocks, isect, tracing_idx.clone(),
+                      z_start.clone(), torch.full((B, S), -1.0, device=DEV), torch.full((B, S), -1.0, device=DEV)]
+        a, r = both("sample_points", ours, ref, mk)
+        ti, zs, z, di = a[-4:]
+        assert ((z == -1).all(-1) | (z != -1).all(-1)).all(), "a ray is sampled completely or not at all"
+        if r is not None:
+            assert torch.equal(ti, r[-4]), "tracing_idx must be bit-exact"
+            assert torch.equal(z == -1, r[-2] == -1)
+            for x, y in zip((zs, z, di), r[-3:]):
+                assert torch.allclose(x, y, rtol=1e-6, atol=1e-6)
+        a, r = both("prepare_points", ours, ref, lambda: [z, running, isect, torch.full((B, S, 4), -1, dtype=torch.int16, device=DEV)])
+        bi = a[-1]
+        zc, ic = z.cpu().numpy(), isect.cpu().numpy()
+        inside = (zc[:, :, None] >= ic[:, None, :, 0]) & (zc[:, :, None] <= ic[:, None, :, 1]) & (zc[:, :, None] != -1) & running.cpu().numpy()[:, :, None]
+        assert np.array_equal((bi.cpu().numpy() >= 0).sum(-1), inside.sum(-1)), "sample-to-tile assignment count"
+        if r is not None:
+            assert torch.equal(bi, r[-1]), "block_idxs must be bit-exact"
+        mk = lambda: [o, d, z, di, bi, sc["tables"], sc["params"], sc["res"], sc["occ"], sc["starts"], sc["l2d"], sc["corners"], sc["sizes"],
+                      torch.zeros(B, S, 3, device=DEV), torch.zeros(B, S, 3, device=DEV), torch.zeros(B, S, 1, device=DEV)]
+        a, r = both("pts_inference", ours, ref, mk)
+        pd, ps, pa = a[-3:]
+        assert (rnd > 0 or float(pa.max()) > 0.01) and float(pa.min()) > -1e-3      # a sample a rounding error outside its tile has a (tiny) negative face weight, as in the reference
+        if r is not None:
+            for name, x, y in zip(("diffuse", "specular", "alpha"), (pd, ps, pa), r[-3:]):
+                err = float((x - y).abs().max())
+                assert err < 1e-4, f"pts_inference {name}: max abs err {err}"
+        mk = lambda: [pd, ps, pa, T_.clone(), z, dif.clone(), spe.clone(), dep.clone()]
+        a, r = both("accumulate_color", ours, ref, mk)
+        if r is not None:
+            for x, y in zip((a[3], a[5], a[6], a[7]), (r[3], r[5], r[6], r[7])):
+                assert torch.allclose(x, y, rtol=1e-5, atol=1e-6)
+        # numpy restatement of the front-to-back accumulation (rendering_kernel.cu:623-674)
+        Tn, dn = T_.cpu().numpy()[:, 0].copy(), dif.cpu().numpy().copy()
+        pdn, pan = pd.cpu().numpy(), pa.cpu().numpy()[..., 0]
+        go = Tn >= 1e-5
+        for k in range(S):
+            dn[go] += Tn[go, None] * pdn[go, k]
+            Tn[go] *= 1 - pan[go, k]
+        assert np.allclose(a[5].cpu().numpy(), dn, rtol=1e-4, atol=1e-5) and np.allclose(a[3].cpu().numpy()[:, 0], Tn, rtol=1e-4, atol=1e-6)
+        T_, dif, spe, dep = a[3], a[5], a[6], a[7]
+        tracing_idx, z_start = ti, zs
+    # ---- background: exit tiles, inverse-z samples, contracted evaluation
+    mk = lambda: [o, d, sc["corners"], sc["sizes"], tracing_blocks, isect, torch.full((B, 4), -1, dtype=torch.int16, device=DEV),
+                  torch.zeros(B, 4, device=DEV), 0.12, False]
+    a, r = both("update_outgoing_bidx", ours, ref, mk)
+    bgb, bgw = a[6], a[7]
+    hit_any = (isect[..., 0] != MISS).any(-1)
+    assert torch.equal(bgb[:, 0] != -1, hit_any)
+    if r is not None:
+        assert torch.equal(bgb, r[6]) and torch.allclose(bgw, r[7], rtol=1e-6, atol=1e-6)
+    Sb = 24
+    slot0 = bgb[..., 0].contiguous()
+    a, r = both("inverse_z_sampling", ours, ref, lambda: [isect, slot0, torch.full((B, Sb), -1.0, device=DEV), 1e6])
+    bz = a[2]
+    far = torch.gather(isect[..., 1], 1, slot0.long().clamp_min(0)[:, None])[:, 0]
+    assert torch.allclose(bz[hit_any, 0], far[hit_any], rtol=1e-5) and bool((bz[~hit_any] == -1).all())
+    if r is not None:
+        assert torch.allclose(bz, r[2], rtol=1e-6, atol=1e-6)
+    mk = lambda: [o, d, bz, bgb, 0, sc["corners"], sc["sizes"], sc["res"], sc["tables"], sc["params"],
+                  torch.full((B, Sb, 3), 0.5, device=DEV), torch.full((B, Sb, 3), 0.5, device=DEV), torch.full((B, Sb, 1), 0.5, device=DEV)]
+    a, r = both("bg_pts_inference_v2", ours, ref, mk)
+    assert bool((a[-1][~hit_any] == 0.5).all()), "rays without an exit tile keep the caller's rows"
+    if r is not None:
+        for name, x, y in zip(("diffuse", "specular", "alpha"), a[-3:], r[-3:]):
+            # a ray that leaves its tile at depth ~0 gets an infinite last sample and NaN there -- in the reference too
+            assert torch.equal(torch.isfinite(x), torch.isfinite(y)), f"bg_pts_inference_v2 {name}: non-finite pattern differs"
+            x, y = torch.nan_to_num(x, nan=0.0, posinf=0.0, neginf=0.0), torch.nan_to_num(y, nan=0.0, posinf=0.0, neginf=0.0)
+            err = float((x - y).abs().max())
+            assert err < 1e-4, f"bg_pts_inference_v2 {name}: max abs err {err}"
+    mk = lambda: [o, d, bz, bgb, torch.where(bgb >= 0, torch.ones_like(bgw), torch.zeros_like(bgw)) * 0.7, sc["corners"], sc["sizes"], sc["res"],
+                  sc["tables"], sc["params"], torch.zeros(B, Sb, 3, device=DEV), torch.zeros(B, Sb, 3, device=DEV), torch.zeros(B, Sb, 1, device=DEV)]
+    a, r = both("bg_pts_inference", ours, ref, mk)
+    if r is not None:
+        for name, x, y in zip(("diffuse", "specular", "alpha"), a[-3:], r[-3:]):
+            assert torch.equal(torch.isfinite(x), torch.isfinite(y)), f"bg_pts_inference {name}: non-finite pattern differs"
+            x, y = torch.nan_to_num(x, nan=0.0, posinf=0.0, neginf=0.0), torch.nan_to_num(y, nan=0.0, posinf=0.0, neginf=0.0)
+            err = float((x[hit_any] - y[hit_any]).abs().max())
+            assert err < 1e-4, f"bg_pts_inference {name}: max abs err {err}"
+    # ---- the small helpers
+    a, r = both("get_last_block", ours, ref, lambda: [tracing_blocks, torch.full((B,), -7, dtype=torch.int32, device=DEV), isect])
+    if r is not None:
+        assert torch.equal(a[1], r[1])
+    a, r = both("ray_firsthit_block", ours, ref, lambda: [o, d, sc["corners"], sc["sizes"], fake, sc["starts"], sc["l2d"], tracing_blocks, isect,
+                                                           torch.full((B, 1), -1, dtype=torch.int16, device=DEV)])
+    if r is not None:
+        assert torch.equal(a[-1], r[-1])
+    a, r = both("update_outgoing_bidx_v2", ours, ref, lambda: [o, d, sc["corners"], sc["sizes"], tracing_blocks, isect,
+                                                                torch.full((B, 4), -1, dtype=torch.int16, device=DEV), torch.zeros(B, 4, device=DEV)])
+    if r is not None:
+        assert torch.equal(a[6], r[6]) and torch.allclose(a[7], r[7], rtol=1e-6, atol=1e-6)
+
+
+def test_pts_inference_against_cpu_restatement():
+    """Single tile, every cell occupied: per-sample outputs = alpha * decoder(encode(u)) with the
+    renderer's conventions (u = q/2 + 0.25, fp16 table, normalised d, no level mask)."""
+    ours, _ = _ops()
+    sc = make_scene(1, T=2 ** 12, seed=3)
+    B, S = 64, 16
+    g = torch.Generator().manual_seed(5)
+    o = sc["corners"][0] + sc["sizes"][0] * (0.2 + 0.6 * torch.rand(B, 3, generator=g))
+    d = torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=-1) * 0.8
+    z = (torch.rand(B, S, generator=g) * 1.5).sort(-1)[0].contiguous()
+    dist = torch.full((B, S), 0.07)
+    bi = torch.full((B, S, 4), -1, dtype=torch.int16)
+    bi[..., 0] = 0
+    occ = torch.ones(sc["n_cells"], dtype=torch.bool)
+    outs = [torch.zeros(B, S, 3, device=DEV), torch.zeros(B, S, 3, device=DEV), torch.zeros(B, S, 1, device=DEV)]
+    ours.pts_inference(o.to(DEV), d.to(DEV), z.to(DEV), dist.to(DEV), bi.to(DEV), sc["tables"].to(DEV), sc["params"].to(DEV), sc["res"].to(DEV),
+                       occ.to(DEV), sc["starts"].to(DEV), sc["l2d"].to(DEV), sc["corners"].to(DEV), sc["sizes"].to(DEV), *outs)
+    p = o[:, None] + z[..., None] * d[:, None]
+    q = (p - sc["corners"][0]) / sc["sizes"][0]
+    inside = ((q > 0.02) & (q < 0.98)).all(-1)
+    cont = (2 * q - 1).reshape(-1, 3).numpy().astype(np.float32)           # (cont + 2) / 4 = q / 2 + 0.25
+    feats = on.hash_encode_fwd(cont, sc["tables"][0].float().numpy(), sc["res"][0].numpy())
+    dirs = d[:, None].expand(B, S, 3).reshape(-1, 3)
+    heads = tr.shallow_mlp(sc["mlps"][0], torch.from_numpy(feats).reshape(-1, 32), dirs, torch.ones(32))
+    alpha = 1 - torch.exp(-heads["sigma"][:, 0] * dist.reshape(-1) * dirs.norm(dim=-1))
+    want_d = (alpha[:, None] * heads["diffuse"]).reshape(B, S, 3)
+    want_s = (alpha[:, None] * heads["tint"] * heads["specular"]).reshape(B, S, 3)
+    m = inside
+    assert m.sum() > B * S // 2
+    assert float((outs[2].cpu()[..., 0][m] - alpha.reshape(B, S)[m]).abs().max()) < 1e-4
+    assert float((outs[0].cpu()[m] - want_d[m]).abs().max()) < 1e-4
+    assert float((outs[1].cpu()[m] - want_s[m]).abs().max()) < 1e-4
