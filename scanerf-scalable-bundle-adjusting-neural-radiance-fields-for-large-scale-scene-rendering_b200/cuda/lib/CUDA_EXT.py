@@ -275,3 +275,12 @@ def proj2pixel_and_fetch_color(pts, Ks, C2Ws, RGBs, fetched_pixels, fetched_colo
     capi.check(capi.lib().snrf_proj2pixel_fetch(ptr(p), ptr(k), ptr(c), ptr(im), fp.ptr, fc.ptr, c_int(B), c_int(N), c_int(H),
                                                 c_int(W), capi.stream()), "snrf_proj2pixel_fetch")
     fp.done(); fc.done()
+
+
+class BlockBuilder:
+    """cuda/include/build_blocks.h:34-246 -- offline tile allocation / view selection helper of
+    preprocess/ (no live Python caller; SURVEY section 2 row 17: out of scope).  The name exists so
+    that `from cuda import *` keeps the reference's surface; using it raises."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("BlockBuilder is a preprocessing helper outside the hot path (not provided)")

@@ -68,8 +68,9 @@ def _worker(rank, world, port, num_camera, n_tiles, q):
         if rnd == 1:
             mine = [(p * 0.5, i, c) for p, i, c in mine]
         out = pc.exchange(mine)
-        res.append((pc.shared_poses.clone(), [(o["shared_poses"], o["overlap_idxs"]) for o in out], float(pc.primal_residual),
-                    float(pc.dual_residual)))
+        # plain numpy through the queue (tensor hand-over by file descriptor races with worker exit)
+        res.append((pc.shared_poses.numpy().copy(), [(o["shared_poses"].numpy().copy(), o["overlap_idxs"].numpy().copy()) for o in out],
+                    float(pc.primal_residual), float(pc.dual_residual)))
     q.put((rank, res))
     dist.barrier()
     dist.destroy_process_group()
@@ -97,6 +98,8 @@ def test_consensus_two_ranks_matches_master_process():
         prev = z
         for rank in range(world):
             zr, per_tile, pr, du = got[rank][rnd]
+            zr = torch.from_numpy(zr)
+            per_tile = [(torch.from_numpy(a), torch.from_numpy(b)) for a, b in per_tile]
             assert torch.allclose(zr, z, atol=1e-6)
             assert abs(pr - float(primal)) < 1e-6 and abs(du - float(dual)) < 1e-6
             for (sp, ov), want in zip(per_tile, outs[rank::world]):
