@@ -263,7 +263,7 @@ def main():
     ms_e2e, _, t2 = timed(step.step, host)
     clk = clocks.summary(t0, t2) if clocks else None
     # (3) the dominant kernel, timed live on its stream over the same steps
-    capi.time_calls("snrf_hash_bwd")
+    capi.time_calls("snrf_field_encode_bwd")
     for b in devb[Wm:]:
         step.step_device(*b)
     torch.cuda.synchronize()
@@ -286,7 +286,7 @@ def main():
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if k_ms else float("nan")
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("snrf_hash_bwd")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("snrf_field_encode_bwd")
     except Exception:
         pass
     line = {
@@ -300,7 +300,7 @@ def main():
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "clocks": clk,
-        "roofline": {"kernel": "hash_bwd_kernel (snrf_hash_bwd)", "bound": "hbm", "achieved": achieved, "peak": peak,
+        "roofline": {"kernel": "field_bwd_kernel (snrf_field_encode_bwd: hash-encode backward)", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "avg_launch_ms": avg_ms, "launches_timed": len(k_ms), "alg_bytes_per_launch": alg_bytes,
                      "share_of_step": (sum(k_ms) / K) / (ms_dev / K) if k_ms else None},

@@ -46,6 +46,32 @@ int snrf_hash_bwd(const float* points, const float* grad_in, const float* table,
 /* tuning hook: force the number of levels walked per CTA row (0 = automatic) */
 void snrf_hash_set_levels_per_block(int lpb);
 
+/* ---- fused training-path field encode -------------------------------------------- */
+/* sample position -> space contraction -> hash encode in one kernel, replacing hashgrid/__init__.py:522
+ * (samples = o + z d), :394-411 (contract_fore / contract_bg) and hashgrid/PyHashGridBG.py:9-30 with
+ * hashgrid/src/hashgrid_bg_kernel.cu:106-275, plus their autograd.
+ * mode 0: points[N,3] already contracted; mode 1 (fore) / 2 (background): sample n = rays_o[n/S] + z_vals[n] rays_d[n/S],
+ * contracted w.r.t. the box (box_min, box_size: device float[3]).
+ * -> out_lm [L][N] float2 (level-major), jac_lm [L][3][N] float2 = d out / d contracted point (NULL: not needed). */
+int snrf_field_encode_fwd(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
+                          const float* box_min, const float* box_size, int mode, const float* table, const int* res,
+                          float* out_lm, float* jac_lm, int N, int S, int L, int T, void* stream);
+/* grad_lm [L][N] float2, jac_lm from the forward (NULL: table gradient only).  ACCUMULATES grad_table [L,T,2] and
+ * grad_rays_o / grad_rays_d [R,3] (modes 1, 2; either may be NULL) or grad_points [N,3] (mode 0). */
+int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
+                          const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
+                          const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points, float* grad_table,
+                          int N, int S, int L, int T, void* stream);
+/* tuning hook: log2 of the number of table index ranges the scatter walks per level (-1 = automatic) */
+void snrf_field_set_passes_log2(int bits);
+
+/* ---- bundle-adjustment pose chain -------------------------------------------------- */
+/* camera_utils.py:86-89 (CAM.get_rts) + camera.py:84-95, 118-141 (Lie.se3_to_SE3, Taylor series) + camera.py:37-60
+ * (Pose.compose_pair / invert): se3_refine [N,6], base_w2c [N,12] -> c2w [N,12] = invert(se3_to_SE3(se3) then base). */
+int snrf_pose_fwd(const float* se3_refine, const float* base_w2c, float* c2w, int n, void* stream);
+/* analytic backward of the above: grad_c2w [N,12] -> grad_se3 [N,6] (written) */
+int snrf_pose_bwd(const float* se3_refine, const float* base_w2c, const float* grad_c2w, float* grad_se3, int n, void* stream);
+
 /* ---- rays, boxes, samplers -------------------------------------------------- */
 /* cuda/include/compute_ray.h (compute_ray_forward): Ks[N,9], C2Ws[N,12], locs[B,3] i32
  * = (view, px, py) -> rays_o, rays_d [B,3]. */
@@ -107,9 +133,10 @@ int snrf_umma_selftest(const float* X, const float* W, const float* G, float* Y,
  * reference's +1e-8), params = HOST array of 16 DEVICE pointers in network.ShallowMLP state_dict
  * order (weight, bias per Linear: Spatial_MLP.mlp.0 [64,32], .mlp.2 [64,64], sigma_layer [1,32],
  * diffuse_layer [3,32], tint_layer [3,32], Directional_MLP.mlp.0 [64,48], .2 [64,64], .4 [3,64]).
- * -> heads[N,10] f32 = (sigma, tint3, diffuse3, specular3).  bf16(x3) operands, f32 accumulation. */
+ * -> heads[N,10] f32 = (sigma, tint3, diffuse3, specular3).  bf16(x3) operands, f32 accumulation.
+ * level_major != 0: feats (and grad_feats in the backward) are [16][N] float2, the layout of snrf_field_encode_*. */
 int snrf_decoder_fwd(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
-                     float* heads, int N, int S, void* stream);
+                     float* heads, int N, int S, int level_major, void* stream);
 
 /* Operand precision of the decoder GEMMs: 1 (default) = error-compensated bf16x3 split operands in
  * every forward GEMM (~fp32 accuracy), 0 = plain bf16 operands (fastest). */
@@ -120,7 +147,7 @@ void snrf_decoder_set_precision(int split);
  * shapes/order of params, ACCUMULATED.  The forward is recomputed per 128-sample tile. */
 int snrf_decoder_bwd(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
                      const float* grad_heads, float* grad_feats, float* grad_rays_d, float* const* grad_params,
-                     int N, int S, void* stream);
+                     int N, int S, int level_major, void* stream);
 
 /* ---- view selection, neighbour projection, image sampling ------------------------ */
 /* cuda/include/view_selection.h (computeViewcost; kernel cuda/view_selection_kernel.cu:18-76):

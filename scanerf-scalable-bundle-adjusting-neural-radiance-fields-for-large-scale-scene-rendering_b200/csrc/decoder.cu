@@ -44,7 +44,7 @@ namespace {
 template <bool SPLIT>
 __global__ void __launch_bounds__(kRows, 1)
 decoder_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ mask32, const float* __restrict__ rays_d,
-                   DecoderParams p, float* __restrict__ out, int N, int S, int num_tiles)
+                   DecoderParams p, float* __restrict__ out, int N, int S, int num_tiles, long long level_stride)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -76,7 +76,7 @@ decoder_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         float head[10], zh[7];
         f3 d = mk3(0.f, 0.f, 1.f);
         float dn = 1.0f;
-        forward_tile<SPLIT, false>(c, T, feats, rays_d, n, live, S, head, zh, d, dn);
+        forward_tile<SPLIT, false>(c, T, feats, rays_d, n, live, S, head, zh, d, dn, level_stride);
         {
             float z[16];
             umma::tmem_ld16(c.tmem + cDh + c.lane_addr, z);
@@ -113,7 +113,7 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(kRows, 1)
 decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ mask32, const float* __restrict__ rays_d,
                    DecoderParams p, const float* __restrict__ grad_heads, float* __restrict__ grad_feats,
-                   float* __restrict__ grad_rays_d, DecoderGrads gp, int N, int S, int num_tiles)
+                   float* __restrict__ grad_rays_d, DecoderGrads gp, int N, int S, int num_tiles, long long level_stride)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -220,7 +220,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         float head[10], zh[7];
         f3 d = mk3(0.f, 0.f, 1.f);
         float dn = 1.0f;
-        forward_tile<SPLIT, true>(c, T, feats, rays_d, n, live, S, head, zh, d, dn);
+        forward_tile<SPLIT, true>(c, T, feats, rays_d, n, live, S, head, zh, d, dn, level_stride);
 
         // ---- d(loss)/d(pre-activations) of the 7 heads and the 3 specular outputs
         float dzh[16], dzs[16];
@@ -373,11 +373,17 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         umma::tmem_ld32(tmem + cDa + lane_addr, v);
         umma::tc_wait_ld();
         if (live) {
-            float4* dst = reinterpret_cast<float4*>(grad_feats + (size_t)n * 32);
+            if (level_stride == 0) {
+                float4* dst = reinterpret_cast<float4*>(grad_feats + (size_t)n * 32);
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                dst[q] = make_float4(v[4 * q] * mask[4 * q], v[4 * q + 1] * mask[4 * q + 1], v[4 * q + 2] * mask[4 * q + 2],
-                                     v[4 * q + 3] * mask[4 * q + 3]);
+                for (int q = 0; q < 8; ++q)
+                    dst[q] = make_float4(v[4 * q] * mask[4 * q], v[4 * q + 1] * mask[4 * q + 1], v[4 * q + 2] * mask[4 * q + 2],
+                                         v[4 * q + 3] * mask[4 * q + 3]);
+            } else {            // level-major [16][N] float2: consecutive samples -> consecutive addresses
+                float2* dst = reinterpret_cast<float2*>(grad_feats) + n;
+#pragma unroll
+                for (int l = 0; l < 16; ++l) dst[(size_t)l * level_stride] = make_float2(v[2 * l] * mask[2 * l], v[2 * l + 1] * mask[2 * l + 1]);
+            }
         }
         // every MMA of this tile has completed (the last commit covers all earlier ones), so the
         // next tile may overwrite the operand tiles
@@ -452,7 +458,7 @@ SNRF_API void snrf_decoder_set_precision(int split) { g_split = split ? 1 : 0; }
 
 // params: HOST array of 16 DEVICE pointers in network.ShallowMLP state_dict order
 SNRF_API int snrf_decoder_fwd(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
-                              float* heads_out, int N, int S, void* stream)
+                              float* heads_out, int N, int S, int level_major, void* stream)
 {
     SNRF_CHECK_ARG(N >= 0 && S > 0, "snrf_decoder_fwd: need N >= 0, S > 0 (N=%d S=%d)", N, S);
     SNRF_CHECK_ARG(params != nullptr, "snrf_decoder_fwd: params is required");
@@ -471,11 +477,11 @@ SNRF_API int snrf_decoder_fwd(const float* feats, const float* mask32, const flo
     if (g_split) {
         int grid = snrf_sm_count();                 // ~145 KB of shared memory: one CTA per SM
         if (grid > num_tiles) grid = num_tiles;
-        decoder_fwd_kernel<true><<<grid, kRows, fwd_smem<true>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles);
+        decoder_fwd_kernel<true><<<grid, kRows, fwd_smem<true>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll);
     } else {
         int grid = snrf_sm_count() * 2;             // 2 x (256 TMEM columns, ~87 KB)
         if (grid > num_tiles) grid = num_tiles;
-        decoder_fwd_kernel<false><<<grid, kRows, fwd_smem<false>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles);
+        decoder_fwd_kernel<false><<<grid, kRows, fwd_smem<false>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll);
     }
     SNRF_RETURN_LAUNCH("snrf_decoder_fwd");
 }
@@ -486,7 +492,7 @@ SNRF_API int snrf_decoder_fwd(const float* feats, const float* mask32, const flo
 // same order and shapes as params (ACCUMULATED).
 SNRF_API int snrf_decoder_bwd(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
                               const float* grad_heads, float* grad_feats, float* grad_rays_d, float* const* grad_params,
-                              int N, int S, void* stream)
+                              int N, int S, int level_major, void* stream)
 {
     SNRF_CHECK_ARG(N >= 0 && S > 0, "snrf_decoder_bwd: need N >= 0, S > 0 (N=%d S=%d)", N, S);
     SNRF_CHECK_ARG(params != nullptr && grad_params != nullptr, "snrf_decoder_bwd: params and grad_params are required");
@@ -508,8 +514,8 @@ SNRF_API int snrf_decoder_bwd(const float* feats, const float* mask32, const flo
     if (grid > num_tiles) grid = num_tiles;
     cudaStream_t s = (cudaStream_t)stream;
     if (g_split)
-        decoder_bwd_kernel<true><<<grid, kRows, bwd_smem<true>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles);
+        decoder_bwd_kernel<true><<<grid, kRows, bwd_smem<true>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll);
     else
-        decoder_bwd_kernel<false><<<grid, kRows, bwd_smem<false>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles);
+        decoder_bwd_kernel<false><<<grid, kRows, bwd_smem<false>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll);
     SNRF_RETURN_LAUNCH("snrf_decoder_bwd");
 }

@@ -325,16 +325,26 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT>& c, const Tiles& T, fl
 template <bool SPLIT, bool TRAIN>
 __device__ __forceinline__ void forward_tile(Ctx<SPLIT>& c, const Tiles& T, const float* __restrict__ feats,
                                              const float* __restrict__ rays_d, int n, bool live, int S, float* head, float* zh,
-                                             f3& d, float& dn)
+                                             f3& d, float& dn, long long level_stride)
 {
+    // feats: [N,32] row-major (level_stride = 0) or level-major [16][N] float2 (level_stride = N)
     const float* mask = c.mask;
     float x[32], sh[16];
     if (live) {
+        if (level_stride == 0) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(feats + (size_t)n * 32 + q * 4));
-            x[4 * q + 0] = a.x * mask[4 * q + 0]; x[4 * q + 1] = a.y * mask[4 * q + 1];
-            x[4 * q + 2] = a.z * mask[4 * q + 2]; x[4 * q + 3] = a.w * mask[4 * q + 3];
+            for (int q = 0; q < 8; ++q) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(feats + (size_t)n * 32 + q * 4));
+                x[4 * q + 0] = a.x * mask[4 * q + 0]; x[4 * q + 1] = a.y * mask[4 * q + 1];
+                x[4 * q + 2] = a.z * mask[4 * q + 2]; x[4 * q + 3] = a.w * mask[4 * q + 3];
+            }
+        } else {
+            const float2* f2 = reinterpret_cast<const float2*>(feats) + n;
+#pragma unroll
+            for (int l = 0; l < 16; ++l) {
+                const float2 a = __ldg(f2 + (size_t)l * level_stride);
+                x[2 * l] = a.x * mask[2 * l]; x[2 * l + 1] = a.y * mask[2 * l + 1];
+            }
         }
         d = ld3(rays_d + 3 * (size_t)(n / S));
         dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);

@@ -1,0 +1,330 @@
+// Fused training-path field encode: sample position -> space contraction -> 16-level hash encode,
+// forward and backward, sm_100a.
+//
+// Replaces (behaviour, not code) this chain of HashGrid.render_batch_rays (hashgrid/__init__.py:512-545):
+//   samples = rays_o + z * rays_d                              (:522)
+//   contract_fore / contract_bg                                (:394-411)
+//   HashEmbeddingBGAutoGrad.forward / .backward                (hashgrid/PyHashGridBG.py:9-30 ->
+//                                                               hashgrid/src/hashgrid_bg_kernel.cu:106-275)
+// and the autograd of all of it back to (rays_o, rays_d) and the table.
+//
+// Data layout in HBM (level-major, so that every access of a warp is one contiguous 256-byte run):
+//   out  [L][N]     float2    encoded features            (the reference operator writes [N][L])
+//   jac  [L][3][N]  float2    d out / d contracted point  (training only)
+//   grad [L][N]     float2    incoming gradient
+// The forward stores the 2x3 Jacobian of every (sample, level) -- 24 bytes -- so that the backward
+// never re-gathers the table (8 random sectors per level in the reference, :195-222): it is a pure
+// gradient scatter.  The scatter walks each level's table slice in `passes` index ranges so that the
+// live part of the gradient table (128 MiB per level at T = 2^24) stays L2-resident while it is
+// being reduced into; every sector then travels to HBM once per range instead of once per touch.
+// d L / d rays is reduced per warp (32 consecutive samples of one ray) before it touches memory.
+#include "hash_common.cuh"
+using namespace hashgrid;
+
+namespace {
+
+constexpr int kThreads = 256;
+enum Contract { kNone = 0, kFore = 1, kBack = 2 };
+
+struct Pt {
+    f3 c;          // contracted point in [-2,2]^3
+    f3 jd;         // diagonal of d c / d x  (affine part times f)
+    f3 u;          // affine-normalised point (background only)
+    float fp;      // f'(n) * a_k   (background only): the rank-one part acts along axis k
+    int k;         // arg-max axis of |u|
+};
+
+// o + z d with separately rounded multiply and add, as torch evaluates it (hashgrid/__init__.py:522):
+// an FMA here could move a sample across a cell boundary relative to the reference path.
+__device__ __forceinline__ f3 sample_pos(f3 o, f3 d, float z)
+{
+    return mk3(__fadd_rn(o.x, __fmul_rn(z, d.x)), __fadd_rn(o.y, __fmul_rn(z, d.y)), __fadd_rn(o.z, __fmul_rn(z, d.z)));
+}
+
+// x -> contracted coordinates.  fore: c = (x - min) / size * 4 - 2 (hashgrid/__init__.py:394-395);
+// back: u = that, n = |u|_inf, c = u (2 - 1/n) / n (:397-411).
+template <int MODE>
+__device__ __forceinline__ Pt contract(f3 x, f3 bmin, f3 bsize)
+{
+    Pt p;
+    const f3 u = mk3((x.x - bmin.x) / bsize.x * 4.0f - 2.0f, (x.y - bmin.y) / bsize.y * 4.0f - 2.0f, (x.z - bmin.z) / bsize.z * 4.0f - 2.0f);
+    const f3 a = mk3(4.0f / bsize.x, 4.0f / bsize.y, 4.0f / bsize.z);
+    if (MODE == kFore) {
+        p.c = u; p.jd = a; p.u = u; p.fp = 0.0f; p.k = 0;
+    } else {
+        const float ax = fabsf(u.x), ay = fabsf(u.y), az = fabsf(u.z);
+        float n = ax; int k = 0;                       // torch.max returns the first maximal index
+        if (ay > n) { n = ay; k = 1; }
+        if (az > n) { n = az; k = 2; }
+        const float f = (2.0f - 1.0f / n) / n;
+        // rounded product: the encode adds 2 next, and an FMA would differ from torch's separately rounded u * f
+        p.c = mk3(__fmul_rn(u.x, f), __fmul_rn(u.y, f), __fmul_rn(u.z, f));
+        p.jd = a * f;
+        p.u = u;
+        const float uk = k == 0 ? u.x : (k == 1 ? u.y : u.z);
+        const float ak = k == 0 ? a.x : (k == 1 ? a.y : a.z);
+        // f(n) = 2/n - 1/n^2, f'(n) = -2/n^2 + 2/n^3; d n / d u_k = sign(u_k)
+        p.fp = (-2.0f / (n * n) + 2.0f / (n * n * n)) * (uk >= 0.0f ? 1.0f : -1.0f) * ak;
+        p.k = k;
+    }
+    return p;
+}
+
+// g_c (gradient w.r.t. the contracted point) -> gradient w.r.t. the world-space sample
+template <int MODE>
+__device__ __forceinline__ f3 contract_bwd(const Pt& p, f3 gc)
+{
+    f3 gx = gc * p.jd;
+    if (MODE == kBack) {
+        const float s = dot3(gc, p.u) * p.fp;          // rank-one term: (g . u) f'(n) dn/du_k a_k on axis k
+        if (p.k == 0) gx.x += s; else if (p.k == 1) gx.y += s; else gx.z += s;
+    }
+    return gx;
+}
+
+template <int MODE, bool JAC>
+__global__ void __launch_bounds__(kThreads)
+field_fwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_vals,
+                 const float* __restrict__ points, const float* __restrict__ bmin_p, const float* __restrict__ bsize_p,
+                 const float2* __restrict__ table, const int* __restrict__ res, float2* __restrict__ out, float2* __restrict__ jac,
+                 int N, int S, int L, uint32_t T, int lpb)
+{
+    const uint32_t mask = T - 1u;
+    f3 bmin = mk3(0, 0, 0), bsize = mk3(1, 1, 1);
+    if (MODE != kNone) { bmin = ld3(bmin_p); bsize = ld3(bsize_p); }
+    const int l_begin = blockIdx.y * lpb, l_end = min(L, l_begin + lpb);
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        f3 c;
+        if (MODE == kNone) {
+            c = ld3(points + 3 * (size_t)n);
+        } else {
+            const int r = n / S;
+            c = contract<MODE>(sample_pos(ld3(rays_o + 3 * (size_t)r), ld3(rays_d + 3 * (size_t)r), z_vals[n]), bmin, bsize).c;
+        }
+        for (int l = l_begin; l < l_end; ++l) {
+            const Cell cell = locate_bg(c, res + 3 * l);
+            uint32_t idx[8];
+            corner_idx(idx, cell, mask);
+            const float2* tl = table + (size_t)l * T;
+            float2 f[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = ldg2(tl + idx[k]);
+            float w[8];
+            corner_w(w, cell);
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { acc.x += w[k] * f[k].x; acc.y += w[k] * f[k].y; }
+            out[(size_t)l * N + n] = acc;
+            if (JAC) {
+                const float ax = 1.0f - cell.ox, ay = 1.0f - cell.oy, az = 1.0f - cell.oz;
+                const float dxw[8] = {-ay * az, -ay * cell.oz, -cell.oy * az, -cell.oy * cell.oz, ay * az, ay * cell.oz, cell.oy * az, cell.oy * cell.oz};
+                const float dyw[8] = {-ax * az, -ax * cell.oz, ax * az, ax * cell.oz, -cell.ox * az, -cell.ox * cell.oz, cell.ox * az, cell.ox * cell.oz};
+                const float dzw[8] = {-ax * ay, ax * ay, -ax * cell.oy, ax * cell.oy, -cell.ox * ay, cell.ox * ay, -cell.ox * cell.oy, cell.ox * cell.oy};
+                float2 dx = make_float2(0.f, 0.f), dy = dx, dz = dx;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    dx.x += f[k].x * dxw[k]; dx.y += f[k].y * dxw[k];
+                    dy.x += f[k].x * dyw[k]; dy.y += f[k].y * dyw[k];
+                    dz.x += f[k].x * dzw[k]; dz.y += f[k].y * dzw[k];
+                }
+                float2* j = jac + (size_t)l * 3 * N + n;
+                j[0] = make_float2(dx.x * cell.sx, dx.y * cell.sx);
+                j[(size_t)N] = make_float2(dy.x * cell.sy, dy.y * cell.sy);
+                j[2 * (size_t)N] = make_float2(dz.x * cell.sz, dz.y * cell.sz);
+            }
+        }
+    }
+}
+
+// Backward: gradient scatter into the table (index range `pass` of `1 << pass_bits` per level) and,
+// on pass 0, d L / d (rays_o, rays_d) or d L / d points from the stored Jacobians.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+field_bwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_vals,
+                 const float* __restrict__ points, const float* __restrict__ bmin_p, const float* __restrict__ bsize_p,
+                 const int* __restrict__ res, const float2* __restrict__ grad, const float2* __restrict__ jac,
+                 float* __restrict__ grad_o, float* __restrict__ grad_d, float* __restrict__ grad_points, float2* __restrict__ grad_table,
+                 int N, int S, int L, uint32_t T, int pass_bits, int range_shift, int aggregate_levels)
+{
+    const uint32_t mask = T - 1u;
+    const int lane = threadIdx.x & 31;
+    const int l = blockIdx.y >> pass_bits;
+    const uint32_t pass = blockIdx.y & ((1u << pass_bits) - 1u);
+    f3 bmin = mk3(0, 0, 0), bsize = mk3(1, 1, 1);
+    if (MODE != kNone) { bmin = ld3(bmin_p); bsize = ld3(bsize_p); }
+    const bool want_rays = (pass == 0) && jac != nullptr && (MODE == kNone ? grad_points != nullptr : (grad_o != nullptr || grad_d != nullptr));
+    float2* gl = grad_table + (size_t)l * T;
+
+    const int warp_base0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31;
+    for (int wb = warp_base0; wb < N; wb += gridDim.x * blockDim.x) {
+        const int n = wb + lane;
+        const bool live = n < N;
+        Pt p;
+        float z = 0.0f;
+        int r = -1;
+        if (MODE == kNone) {
+            p.c = live ? ld3(points + 3 * (size_t)n) : mk3(0, 0, 0);
+        } else {
+            r = live ? n / S : -1;
+            z = live ? z_vals[n] : 0.0f;
+            const f3 x = live ? sample_pos(ld3(rays_o + 3 * (size_t)r), ld3(rays_d + 3 * (size_t)r), z) : mk3(0, 0, 0);
+            p = contract<MODE>(x, bmin, bsize);
+        }
+        const float2 g = live ? __ldg(grad + (size_t)l * N + n) : make_float2(0.f, 0.f);
+        const Cell cell = locate_bg(p.c, res + 3 * l);
+        uint32_t idx[8]; float w[8];
+        corner_idx(idx, cell, mask);
+        corner_w(w, cell);
+
+        // ---- table gradient: only the corners whose index falls into this pass's range
+        bool done = false;
+        if (l < aggregate_levels) {
+            const unsigned long long key = live
+                ? (((unsigned long long)(uint32_t)cell.ix & 0x1fffffull) << 42) | (((unsigned long long)(uint32_t)cell.iy & 0x1fffffull) << 21) |
+                  ((unsigned long long)(uint32_t)cell.iz & 0x1fffffull)
+                : ~0ull;
+            const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+            const bool head = (lane == 0) || (prev != key);
+            const unsigned heads = __ballot_sync(0xffffffffu, head);
+            if (__popc(heads) <= 12) {
+                const int seg = __popc(heads & ((2u << lane) - 1u));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float sx = seg_sum(w[k] * g.x, seg, lane);
+                    const float sy = seg_sum(w[k] * g.y, seg, lane);
+                    if (head && live && (idx[k] >> range_shift) == pass) atomicAdd(gl + idx[k], make_float2(sx, sy));
+                }
+                done = true;
+            }
+        }
+        if (!done && live) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if ((idx[k] >> range_shift) == pass) atomicAdd(gl + idx[k], make_float2(w[k] * g.x, w[k] * g.y));
+        }
+
+        // ---- gradient w.r.t. the sample position, from the stored Jacobian
+        if (want_rays) {
+            f3 gc = mk3(0, 0, 0);
+            if (live) {
+                const float2* j = jac + (size_t)l * 3 * N + n;
+                const float2 jx = __ldg(j), jy = __ldg(j + (size_t)N), jz = __ldg(j + 2 * (size_t)N);
+                gc = mk3(g.x * jx.x + g.y * jx.y, g.x * jy.x + g.y * jy.y, g.x * jz.x + g.y * jz.y);
+            }
+            if (MODE == kNone) {
+                if (live) {
+                    atomicAdd(grad_points + 3 * (size_t)n + 0, gc.x);
+                    atomicAdd(grad_points + 3 * (size_t)n + 1, gc.y);
+                    atomicAdd(grad_points + 3 * (size_t)n + 2, gc.z);
+                }
+            } else {
+                f3 gx = live ? contract_bwd<MODE>(p, gc) : mk3(0, 0, 0);
+                f3 gz = gx * z;
+                // all lanes of the warp usually belong to one ray: reduce first
+                const int r0 = __shfl_sync(0xffffffffu, r, 0);
+                if (__all_sync(0xffffffffu, r == r0 || r < 0)) {
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        gx.x += __shfl_xor_sync(0xffffffffu, gx.x, off); gx.y += __shfl_xor_sync(0xffffffffu, gx.y, off);
+                        gx.z += __shfl_xor_sync(0xffffffffu, gx.z, off);
+                        gz.x += __shfl_xor_sync(0xffffffffu, gz.x, off); gz.y += __shfl_xor_sync(0xffffffffu, gz.y, off);
+                        gz.z += __shfl_xor_sync(0xffffffffu, gz.z, off);
+                    }
+                    if (lane == 0 && r0 >= 0) {
+                        if (grad_o) { atomicAdd(grad_o + 3 * (size_t)r0, gx.x); atomicAdd(grad_o + 3 * (size_t)r0 + 1, gx.y); atomicAdd(grad_o + 3 * (size_t)r0 + 2, gx.z); }
+                        if (grad_d) { atomicAdd(grad_d + 3 * (size_t)r0, gz.x); atomicAdd(grad_d + 3 * (size_t)r0 + 1, gz.y); atomicAdd(grad_d + 3 * (size_t)r0 + 2, gz.z); }
+                    }
+                } else if (live) {
+                    if (grad_o) { atomicAdd(grad_o + 3 * (size_t)r, gx.x); atomicAdd(grad_o + 3 * (size_t)r + 1, gx.y); atomicAdd(grad_o + 3 * (size_t)r + 2, gx.z); }
+                    if (grad_d) { atomicAdd(grad_d + 3 * (size_t)r, gz.x); atomicAdd(grad_d + 3 * (size_t)r + 1, gz.y); atomicAdd(grad_d + 3 * (size_t)r + 2, gz.z); }
+                }
+            }
+        }
+    }
+}
+
+inline int grid_x(int N)
+{
+    const int sms = snrf_sm_count();
+    const int want = snrf_div_up(N, kThreads);
+    const int wave = sms * 8;
+    if (want <= wave) return want > 0 ? want : 1;
+    const int waves = (want + wave - 1) / wave;
+    return wave * (waves > 4 ? 4 : waves);
+}
+
+int g_pass_bits_override = -1;
+inline int pick_lpb(int L, int T)
+{
+    const long long level_bytes = (long long)T * 8;
+    int lpb = 1;
+    while (lpb * 2 <= L && (long long)lpb * 2 * level_bytes <= (16ll << 20)) lpb *= 2;
+    return lpb;
+}
+// index ranges per level for the scatter: keep the live gradient slice <= 32 MiB
+inline int pick_pass_bits(int T)
+{
+    if (g_pass_bits_override >= 0) return g_pass_bits_override;
+    int bits = 0;
+    while (((long long)T * 8) >> bits > (32ll << 20) && bits < 4) ++bits;
+    return bits;
+}
+
+}  // namespace
+
+// ------------------------------- C ABI --------------------------------------
+SNRF_API void snrf_field_set_passes_log2(int bits) { g_pass_bits_override = bits; }
+
+// mode 0: `points` [N,3] are already contracted (rays_o / rays_d / z_vals unused);
+// mode 1 / 2: sample n = rays_o[n / S] + z_vals[n] * rays_d[n / S], contracted with the fore / background map of the
+// box (box_min, box_size: device float[3], the DOUBLED tile box of HashGrid).
+SNRF_API int snrf_field_encode_fwd(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
+                                   const float* box_min, const float* box_size, int mode, const float* table, const int* res,
+                                   float* out_lm, float* jac_lm, int N, int S, int L, int T, void* stream)
+{
+    SNRF_CHECK_ARG(N >= 0 && L > 0 && T > 0 && (T & (T - 1)) == 0, "snrf_field_encode_fwd: T must be a power of two (N=%d L=%d T=%d)", N, L, T);
+    SNRF_CHECK_ARG(mode >= 0 && mode <= 2 && (mode == 0 ? points != nullptr : (rays_o && rays_d && z_vals && box_min && box_size && S > 0)),
+                   "snrf_field_encode_fwd: inconsistent arguments for mode %d", mode);
+    if (N == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int lpb = pick_lpb(L, T);
+    const dim3 grid(grid_x(N), snrf_div_up(L, lpb));
+    const float2* tb = (const float2*)table;
+    float2 *o = (float2*)out_lm, *j = (float2*)jac_lm;
+#define SNRF_FWD(MODE)                                                                                                                   \
+    do {                                                                                                                                 \
+        if (j) field_fwd_kernel<MODE, true><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, tb, res, o, j, N, S, L, (uint32_t)T, lpb); \
+        else   field_fwd_kernel<MODE, false><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, tb, res, o, j, N, S, L, (uint32_t)T, lpb); \
+    } while (0)
+    if (mode == 0) SNRF_FWD(kNone); else if (mode == 1) SNRF_FWD(kFore); else SNRF_FWD(kBack);
+#undef SNRF_FWD
+    SNRF_RETURN_LAUNCH("snrf_field_encode_fwd");
+}
+
+// grad_lm [L,N,2]; jac_lm from the forward (NULL: no position gradient).  ACCUMULATES grad_table [L,T,2] and
+// grad_rays_o / grad_rays_d [R,3] (mode 1, 2; either may be NULL) or grad_points [N,3] (mode 0).
+SNRF_API int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
+                                   const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
+                                   const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points, float* grad_table,
+                                   int N, int S, int L, int T, void* stream)
+{
+    SNRF_CHECK_ARG(N >= 0 && L > 0 && T > 0 && (T & (T - 1)) == 0, "snrf_field_encode_bwd: T must be a power of two (N=%d L=%d T=%d)", N, L, T);
+    SNRF_CHECK_ARG(mode >= 0 && mode <= 2 && (mode == 0 ? points != nullptr : (rays_o && rays_d && z_vals && box_min && box_size && S > 0)),
+                   "snrf_field_encode_bwd: inconsistent arguments for mode %d", mode);
+    SNRF_CHECK_ARG(grad_table != nullptr && grad_lm != nullptr, "snrf_field_encode_bwd: grad_lm and grad_table are required");
+    if (N == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    int pass_bits = pick_pass_bits(T);
+    int log2T = 0;
+    while ((1 << log2T) < T) ++log2T;
+    if (pass_bits > log2T) pass_bits = log2T;
+    const int range_shift = log2T - pass_bits;
+    const dim3 grid(grid_x(N), L << pass_bits);
+    const float2 *g = (const float2*)grad_lm, *j = (const float2*)jac_lm;
+    float2* gt = (float2*)grad_table;
+    const int agg = L / 2;
+#define SNRF_BWD(MODE) field_bwd_kernel<MODE><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, res, g, j, grad_rays_o, grad_rays_d, grad_points, gt, N, S, L, (uint32_t)T, pass_bits, range_shift, agg)
+    if (mode == 0) SNRF_BWD(kNone); else if (mode == 1) SNRF_BWD(kFore); else SNRF_BWD(kBack);
+#undef SNRF_BWD
+    SNRF_RETURN_LAUNCH("snrf_field_encode_bwd");
+}

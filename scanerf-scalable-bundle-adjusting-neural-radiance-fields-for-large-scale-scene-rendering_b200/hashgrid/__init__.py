@@ -39,6 +39,9 @@ class HashGrid(nn.Module):
     # route ShallowMLP-shaped decoders through the tcgen05 decoder kernels (bf16 operands,
     # f32 accumulation); False keeps the decoder module's own torch forward (fp32)
     fused_decoder = True
+    # with fused_decoder: also fuse sample position + contraction + hash encode (csrc/field_encode.cu);
+    # False keeps torch contraction + the reference-shaped encode operator
+    fused_encode = True
 
     def __init__(self, device, bbox_corner, bbox_size, log2_hashmap_size=24, grid_resolution=[32, 2048],
                  sampler_log2dim=4, init_outside=False, model_path="", near=None, far=None):
@@ -316,19 +319,28 @@ class HashGrid(nn.Module):
         if z_vals.shape[0] == 0:
             return None, False
         R, S = z_vals.shape
+        render_mode = mode
+        mask16 = self.weight_feature(kwargs["global_step"])
+        params = _decoder.decoder_params(decoder) if self.fused_decoder else None
+        mode = 1 if contract_func == self.contract_fore else (2 if contract_func == self.contract_bg else 0)
+        if params is not None and mode != 0 and self.fused_encode and not out_normal and self.HE.features.is_cuda:
+            # fully fused path: sample position + contraction + hash encode in one kernel (level-major
+            # features), the stock ShallowMLP on the tensor cores, packed head rows straight into compositing
+            feats = _field.field_encode(rays_o, rays_d, z_vals, self.HE.features, self.HE.resolution, self.min_bbox,
+                                        self.bbox_size, mode)
+            heads = _field.decoder_apply(feats, rays_d, mask16.repeat_interleave(2), S, params)
+            return _render.composite_packed(heads, z_vals, dists, rays_d, infinity, train=(render_mode is TRAIN)), True
         samples = rays_o[:, None, :] + z_vals[..., None] * rays_d[:, None, :]
         if contract_func is not None:
             cx, extra_w = contract_func(samples.reshape(-1, 3))
         else:
             cx, extra_w = samples.reshape(-1, 3), None
         feats = self.HE(cx)
-        mask16 = self.weight_feature(kwargs["global_step"])
-        params = _decoder.decoder_params(decoder) if (self.fused_decoder and extra_w is None) else None
-        if params is not None:
+        if params is not None and extra_w is None:
             # stock ShallowMLP: the whole decoder runs on the tensor cores (csrc/decoder.cu) and
             # hands packed head rows straight to the compositing kernel
             heads = _field.decoder_apply(feats, rays_d, mask16.repeat_interleave(2), S, params)
-            out = _render.composite_packed(heads, z_vals, dists, rays_d, infinity, train=(mode is TRAIN))
+            out = _render.composite_packed(heads, z_vals, dists, rays_d, infinity, train=(render_mode is TRAIN))
             if out_normal:
                 raise NotImplementedError("out_normal needs a twice-differentiable decoder: set HashGrid.fused_decoder = False")
             return out, True
@@ -336,7 +348,7 @@ class HashGrid(nn.Module):
         if extra_w is not None:
             mask32 = mask32 * extra_w.reshape(R, S, 32)
         heads = decoder(torch.cat([feats.reshape(R, S, 32), rays_d[:, None, :].repeat(1, S, 1)], -1), weight_feature=mask32)
-        out = _render.composite(heads, z_vals, dists, rays_d, infinity, train=(mode is TRAIN))
+        out = _render.composite(heads, z_vals, dists, rays_d, infinity, train=(render_mode is TRAIN))
         if out_normal:
             ones = torch.ones_like(heads["sigma"], requires_grad=False)
             n = torch.autograd.grad(outputs=heads["sigma"], inputs=samples, grad_outputs=ones, create_graph=True,

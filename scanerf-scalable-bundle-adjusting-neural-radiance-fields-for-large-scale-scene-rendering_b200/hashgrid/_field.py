@@ -26,11 +26,20 @@ def _param_array(params):
     return arr, ps
 
 
+def _layout(feats):
+    """[N,32] row-major -> (N, 0);  [16,N,2] level-major (snrf_field_encode_* layout) -> (N, 1)."""
+    if feats.dim() == 3:
+        if feats.shape[0] != 16 or feats.shape[2] != 2:
+            raise RuntimeError(f"level-major features must be [16, N, 2], got {tuple(feats.shape)}")
+        return int(feats.shape[1]), 1
+    return int(feats.shape[0]), 0
+
+
 def decoder_forward(feats, mask32, rays_d, S, params):
-    """feats [N,32] f32, mask32 [32] f32 or None, rays_d [R,3] (sample n -> ray n // S),
-    params = the 16 tensors of hashgrid._decoder.decoder_params().  Returns heads [N,10] =
+    """feats [N,32] f32 (or level-major [16,N,2]), mask32 [32] f32 or None, rays_d [R,3] (sample n ->
+    ray n // S), params = the 16 tensors of hashgrid._decoder.decoder_params().  Returns heads [N,10] =
     (sigma, tint3, diffuse3, specular3)."""
-    N = int(feats.shape[0])
+    N, lm = _layout(feats)
     feats = feats.contiguous()
     rays_d = rays_d.contiguous()
     if not feats.is_cuda:
@@ -38,7 +47,7 @@ def decoder_forward(feats, mask32, rays_d, S, params):
     out = torch.empty(N, 10, dtype=f32, device=feats.device)
     arr, keep = _param_array(params)
     m = mask32.contiguous() if mask32 is not None else None
-    rc = capi.lib().snrf_decoder_fwd(ptr(feats), ptr(m), ptr(rays_d), arr, ptr(out), c_int(N), c_int(int(S)), capi.stream())
+    rc = capi.lib().snrf_decoder_fwd(ptr(feats), ptr(m), ptr(rays_d), arr, ptr(out), c_int(N), c_int(int(S)), c_int(lm), capi.stream())
     capi.check(rc, "snrf_decoder_fwd")
     return out
 
@@ -62,7 +71,7 @@ class DecoderFn(torch.autograd.Function):
     def backward(ctx, g_heads):
         feats, rays_d, mask32 = ctx.saved_tensors[:3]
         params = ctx.saved_tensors[3:]
-        N = int(feats.shape[0])
+        N, lm = _layout(feats)
         g_heads = g_heads.contiguous()
         g_feats = torch.empty_like(feats)
         g_d = torch.zeros_like(rays_d) if ctx.needs_input_grad[1] else None
@@ -76,10 +85,67 @@ class DecoderFn(torch.autograd.Function):
         garr = (ctypes.c_void_p * 16)(*[g.data_ptr() for g in g_params])
         m = mask32.contiguous() if ctx.has_mask else None
         rc = capi.lib().snrf_decoder_bwd(ptr(feats), ptr(m), ptr(rays_d), arr, ptr(g_heads), ptr(g_feats), ptr(g_d), garr,
-                                         c_int(N), c_int(ctx.S), capi.stream())
+                                         c_int(N), c_int(ctx.S), c_int(lm), capi.stream())
         capi.check(rc, "snrf_decoder_bwd")
         return (g_feats, g_d, None, None) + tuple(g_params)
 
 
 def decoder_apply(feats, rays_d, mask32, S, params):
     return DecoderFn.apply(feats, rays_d, mask32, S, *params)
+
+
+class FieldEncodeFn(torch.autograd.Function):
+    """(rays_o [R,3], rays_d [R,3], z_vals [R,S], features [16,T,2], resolution, box_min, box_size, mode)
+    -> level-major features [16, R*S, 2]: sample position, space contraction (mode 1 = fore, 2 =
+    background) and hash encode in one kernel (csrc/field_encode.cu).  The forward stores the per-level
+    Jacobians; the backward is a pure gradient scatter into `features.grad` (accumulated in place, no dense
+    temporary) and returns d/d rays_o, d/d rays_d."""
+
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode):
+        R, S = z_vals.shape
+        N, L, T = R * S, int(features.shape[0]), int(features.shape[1])
+        rays_o, rays_d, z_vals = rays_o.contiguous(), rays_d.contiguous(), z_vals.contiguous()
+        for t in (rays_o, rays_d, z_vals, features):
+            if not t.is_cuda or t.dtype != f32:
+                raise RuntimeError("field encode: float32 CUDA tensors required (no CPU fallback)")
+        need_pos = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        out = torch.empty(L, N, 2, dtype=f32, device=z_vals.device)
+        jac = torch.empty(L, 3, N, 2, dtype=f32, device=z_vals.device) if need_pos else None
+        feats = features.detach().contiguous()
+        box_min, box_size = box_min.contiguous(), box_size.contiguous()
+        rc = capi.lib().snrf_field_encode_fwd(ptr(rays_o), ptr(rays_d), ptr(z_vals), c_void_p(0), ptr(box_min), ptr(box_size),
+                                              c_int(int(mode)), ptr(feats), ptr(resolution), ptr(out), ptr(jac), c_int(N), c_int(S),
+                                              c_int(L), c_int(T), capi.stream())
+        capi.check(rc, "snrf_field_encode_fwd")
+        ctx.mode, ctx.dims = int(mode), (N, S, L, T)
+        ctx.features = features
+        ctx.save_for_backward(rays_o, rays_d, z_vals, resolution, box_min, box_size, jac if jac is not None else out.new_empty(0))
+        ctx.has_jac = jac is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        rays_o, rays_d, z_vals, resolution, box_min, box_size, jac = ctx.saved_tensors
+        N, S, L, T = ctx.dims
+        features = ctx.features
+        g_out = g_out.contiguous()
+        g_o = torch.zeros_like(rays_o) if ctx.needs_input_grad[0] else None
+        g_d = torch.zeros_like(rays_d) if ctx.needs_input_grad[1] else None
+        direct = features.is_leaf and features.requires_grad
+        if direct:
+            if features.grad is None:
+                features.grad = torch.zeros_like(features)
+            g_table = features.grad
+        else:
+            g_table = torch.zeros_like(features)
+        rc = capi.lib().snrf_field_encode_bwd(ptr(rays_o), ptr(rays_d), ptr(z_vals), c_void_p(0), ptr(box_min), ptr(box_size),
+                                              c_int(ctx.mode), ptr(resolution), ptr(g_out), ptr(jac) if ctx.has_jac else c_void_p(0),
+                                              ptr(g_o), ptr(g_d), c_void_p(0), ptr(g_table), c_int(N), c_int(S), c_int(L), c_int(T),
+                                              capi.stream())
+        capi.check(rc, "snrf_field_encode_bwd")
+        return g_o, g_d, None, (None if direct else g_table), None, None, None, None
+
+
+def field_encode(rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode):
+    return FieldEncodeFn.apply(rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode)

@@ -88,6 +88,31 @@ class RayGenFn(torch.autograd.Function):
         return g.reshape(ctx.n, 3, 4), None, None
 
 
+class PoseChainFn(torch.autograd.Function):
+    """(se3_refine [N,6], base_w2c [N,3,4]) -> c2w [N,3,4] = invert(compose([se3_to_SE3(se3_refine), base_w2c])):
+    the whole se(3) chain of CAM.get_rts + Pose.invert in one kernel each way (csrc/pose.cu)."""
+
+    @staticmethod
+    def forward(ctx, se3, base):
+        n = se3.shape[0]
+        se3c, basec = se3.detach().contiguous(), base.contiguous()
+        if not se3c.is_cuda:
+            raise RuntimeError("pose chain: CUDA tensors required (no CPU fallback)")
+        out = torch.empty(n, 3, 4, dtype=torch.float32, device=se3.device)
+        capi.check(capi.lib().snrf_pose_fwd(capi.ptr(se3c), capi.ptr(basec), capi.ptr(out), capi.c_int(n), capi.stream()), "snrf_pose_fwd")
+        ctx.save_for_backward(se3c, basec)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        se3c, basec = ctx.saved_tensors
+        n = se3c.shape[0]
+        g = g.contiguous()
+        out = torch.empty(n, 6, dtype=torch.float32, device=g.device)
+        capi.check(capi.lib().snrf_pose_bwd(capi.ptr(se3c), capi.ptr(basec), capi.ptr(g), capi.ptr(out), capi.c_int(n), capi.stream()), "snrf_pose_bwd")
+        return out, None
+
+
 class Poses(nn.Module):
     """camera_utils.CAM (camera_utils.py:40-89): w2c = se3_to_SE3(se3_refine) o (noise o ori_w2c)."""
 
@@ -103,8 +128,11 @@ class Poses(nn.Module):
     def get_rts(self):
         return pose_compose(se3_to_SE3(self.se3_refine), self.rts)
 
+    def c2w(self):
+        return PoseChainFn.apply(self.se3_refine, self.rts)
+
     def rays(self, locs):
-        return RayGenFn.apply(pose_invert(self.get_rts()).contiguous(), self.ks, locs)
+        return RayGenFn.apply(self.c2w(), self.ks, locs)
 
 
 class TileStep:

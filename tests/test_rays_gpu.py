@@ -8,6 +8,7 @@ import torch
 
 from conftest import load_pkg, ref_module
 from oracle import native as on
+from oracle import torch_ref as tr
 import scenes
 
 pytestmark = pytest.mark.gpu
@@ -159,3 +160,25 @@ def test_background_and_insideout_sampling():
         z1 = torch.zeros(B, S, device=DEV)
         ops.background_sampling_cuda(o.to(DEV), d.to(DEV), starts.to(DEV), depth.to(DEV), z1, S, 2.5)
         _close(z1.cpu(), z2.cpu(), what="bg z vs ref")
+
+
+def test_pose_chain_kernel_matches_torch_chain():
+    """csrc/pose.cu against the torch restatement of CAM.get_rts + Pose.invert (pinned by
+    tests/golden/py_golden_poses.npz in test_oracle_golden.py), values and d/d se3."""
+    load_pkg()
+    from tile_step import PoseChainFn
+    g = torch.Generator().manual_seed(0)
+    for n, scale in ((1, 0.0), (5, 0.3), (64, 0.05), (300, 0.8)):       # |w| up to ~2.5 rad: far beyond any pose refinement
+        se3 = scale * torch.randn(n, 6, generator=g)
+        _, c2w0 = scenes.camera_rig(n, 48, 64, g)
+        base = tr.pose_invert(c2w0)
+        a = se3.clone().requires_grad_(True)
+        ref = tr.pose_invert(tr.pose_compose_pair(tr.se3_to_SE3(a), base))
+        cot = torch.randn(n, 3, 4, generator=g)
+        (ref * cot).sum().backward()
+        b = se3.clone().to("cuda:0").requires_grad_(True)
+        out = PoseChainFn.apply(b, base.to("cuda:0"))
+        (out * cot.to("cuda:0")).sum().backward()
+        assert torch.allclose(out.detach().cpu(), ref.detach(), rtol=1e-5, atol=2e-5), n    # alternating 11-term series: rounding grows with |w|
+        scale_g = max(float(a.grad.abs().max()), 1e-6)
+        assert float((b.grad.cpu() - a.grad).abs().max()) / scale_g < 1e-4, (n, float((b.grad.cpu() - a.grad).abs().max()), scale_g)
