@@ -55,13 +55,13 @@ void snrf_hash_set_levels_per_block(int lpb);
  * -> out_lm [L][N] float2 (level-major), jac_lm [L][3][N] float2 = d out / d contracted point (NULL: not needed). */
 int snrf_field_encode_fwd(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
                           const float* box_min, const float* box_size, int mode, const float* table, const int* res,
-                          float* out_lm, float* jac_lm, int N, int S, int L, int T, void* stream);
+                          float* out_lm, float* jac_lm, const unsigned char* ray_valid, int N, int S, int L, int T, void* stream);
 /* grad_lm [L][N] float2, jac_lm from the forward (NULL: table gradient only).  ACCUMULATES grad_table [L,T,2] and
  * grad_rays_o / grad_rays_d [R,3] (modes 1, 2; either may be NULL) or grad_points [N,3] (mode 0). */
 int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
                           const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
                           const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points, float* grad_table,
-                          int N, int S, int L, int T, void* stream);
+                          const unsigned char* ray_valid, int N, int S, int L, int T, void* stream);
 /* tuning hook: log2 of the number of table index ranges the scatter walks per level (-1 = automatic) */
 void snrf_field_set_passes_log2(int bits);
 
@@ -105,18 +105,19 @@ int snrf_sample_insideout(const float* rays_o, const float* rays_d, int S, int S
  * diffuse, specular [R*S,3]; z_vals, dists [R,S]; rays_d [R,3] (|d| scales the step).
  * -> weights[R,S], trans[R,S] (transmittance before each sample; may be NULL in fwd),
  *    out[R,16] = depth, tint3, diffuse3, specular3 (= sum w tint*spec), l2_3 (= sum w spec^2),
- *    T_left, 2 pad.  infinity != 0: last step is 1e10. */
+ *    T_left, 2 pad.  infinity != 0: last step is 1e10.  ray_valid (optional, bytes [R]): rays with a 0 flag get
+ *    zero weights / outputs and T_left = 1 (the defaults HashGrid scatters back for rays it did not render). */
 int snrf_composite_fwd(const float* sigma, const float* tint, const float* diffuse, const float* specular,
                        int s_sigma, int s_tint, int s_diffuse, int s_specular,
-                       const float* z_vals, const float* dists, const float* rays_d, int R, int S,
-                       int infinity, float* weights, float* trans, float* out, void* stream);
+                       const float* z_vals, const float* dists, const float* rays_d, const unsigned char* ray_valid,
+                       int R, int S, int infinity, float* weights, float* trans, float* out, void* stream);
 /* backward of the above: g_out[R,16] (same row layout; l2 columns act on specular only, the
  * weights inside l2 are detached as in the reference), g_weights[R,S] optional.  WRITES the
  * per-sample head gradients (strides gs_*) and grad_rays_d[R,3] (optional). */
 int snrf_composite_bwd(const float* sigma, const float* tint, const float* diffuse, const float* specular,
                        int s_sigma, int s_tint, int s_diffuse, int s_specular,
                        const float* z_vals, const float* dists, const float* rays_d, const float* trans,
-                       const float* g_out, const float* g_weights, int R, int S, int infinity,
+                       const float* g_out, const float* g_weights, const unsigned char* ray_valid, int R, int S, int infinity,
                        float* g_sigma, float* g_tint, float* g_diffuse, float* g_specular,
                        int gs_sigma, int gs_tint, int gs_diffuse, int gs_specular,
                        float* grad_rays_d, void* stream);
@@ -134,9 +135,10 @@ int snrf_umma_selftest(const float* X, const float* W, const float* G, float* Y,
  * order (weight, bias per Linear: Spatial_MLP.mlp.0 [64,32], .mlp.2 [64,64], sigma_layer [1,32],
  * diffuse_layer [3,32], tint_layer [3,32], Directional_MLP.mlp.0 [64,48], .2 [64,64], .4 [3,64]).
  * -> heads[N,10] f32 = (sigma, tint3, diffuse3, specular3).  bf16(x3) operands, f32 accumulation.
- * level_major != 0: feats (and grad_feats in the backward) are [16][N] float2, the layout of snrf_field_encode_*. */
+ * level_major != 0: feats (and grad_feats in the backward) are [16][N] float2, the layout of snrf_field_encode_*.
+ * ray_valid (optional, bytes [R]): samples of rays with a 0 flag are skipped (their output rows are left untouched). */
 int snrf_decoder_fwd(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
-                     float* heads, int N, int S, int level_major, void* stream);
+                     float* heads, int N, int S, int level_major, const unsigned char* ray_valid, void* stream);
 
 /* Operand precision of the decoder GEMMs: 1 (default) = error-compensated bf16x3 split operands in
  * every forward GEMM (~fp32 accuracy), 0 = plain bf16 operands (fastest). */
@@ -147,7 +149,7 @@ void snrf_decoder_set_precision(int split);
  * shapes/order of params, ACCUMULATED.  The forward is recomputed per 128-sample tile. */
 int snrf_decoder_bwd(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
                      const float* grad_heads, float* grad_feats, float* grad_rays_d, float* const* grad_params,
-                     int N, int S, int level_major, void* stream);
+                     int N, int S, int level_major, const unsigned char* ray_valid, void* stream);
 
 /* ---- view selection, neighbour projection, image sampling ------------------------ */
 /* cuda/include/view_selection.h (computeViewcost; kernel cuda/view_selection_kernel.cu:18-76):

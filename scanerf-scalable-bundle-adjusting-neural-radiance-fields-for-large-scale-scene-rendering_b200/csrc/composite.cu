@@ -61,7 +61,7 @@ __device__ __forceinline__ float warp_incl_suffix_sum(float v, int lane)
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_fwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __restrict__ dists,
-                     const float* __restrict__ rays_d, int R, int S, int infinity,
+                     const float* __restrict__ rays_d, const unsigned char* __restrict__ ray_valid, int R, int S, int infinity,
                      float* __restrict__ weights, float* __restrict__ trans, float* __restrict__ out)
 {
     const int lane = threadIdx.x & 31;
@@ -69,6 +69,11 @@ composite_fwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int chunks = (S + 31) >> 5;
     for (int r = warp; r < R; r += nwarps) {
+        if (ray_valid && !ray_valid[r]) {   // masked-out ray: nothing composited, full transmittance (HashGrid._scatter_back defaults)
+            for (int k = lane; k < S; k += 32) weights[(size_t)r * S + k] = 0.0f;
+            if (lane < kOutStride) out[(size_t)r * kOutStride + lane] = lane == 13 ? 1.0f : 0.0f;
+            continue;
+        }
         const f3 d = ld3(rays_d + 3 * (size_t)r);
         const float dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
         float carry = 1.0f;                 // product of beta over all previous chunks
@@ -129,7 +134,7 @@ composite_fwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_bwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __restrict__ dists,
                      const float* __restrict__ rays_d, const float* __restrict__ trans,
-                     const float* __restrict__ g_out, const float* __restrict__ g_weights,
+                     const float* __restrict__ g_out, const float* __restrict__ g_weights, const unsigned char* __restrict__ ray_valid,
                      int R, int S, int infinity, HeadGrads g, float* __restrict__ grad_rays_d)
 {
     const int lane = threadIdx.x & 31;
@@ -137,6 +142,10 @@ composite_bwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int chunks = (S + 31) >> 5;
     for (int r = warp; r < R; r += nwarps) {
+        if (ray_valid && !ray_valid[r]) {   // masked-out ray: its head gradients are never read downstream
+            if (lane == 0 && grad_rays_d) st3(grad_rays_d + 3 * (size_t)r, mk3(0.f, 0.f, 0.f));
+            continue;
+        }
         const f3 d = ld3(rays_d + 3 * (size_t)r);
         const float dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
         const float* go = g_out + (size_t)r * kOutStride;
@@ -206,20 +215,20 @@ inline int grid_rays(int R)
 // ------------------------------- C ABI --------------------------------------
 SNRF_API int snrf_composite_fwd(const float* sigma, const float* tint, const float* diffuse, const float* specular,
                                 int s_sigma, int s_tint, int s_diffuse, int s_specular,
-                                const float* z_vals, const float* dists, const float* rays_d, int R, int S,
-                                int infinity, float* weights, float* trans, float* out, void* stream)
+                                const float* z_vals, const float* dists, const float* rays_d, const unsigned char* ray_valid,
+                                int R, int S, int infinity, float* weights, float* trans, float* out, void* stream)
 {
     SNRF_CHECK_ARG(S > 0, "snrf_composite_fwd: S must be positive");
     if (R <= 0) return 0;
     Heads in{sigma, tint, diffuse, specular, s_sigma, s_tint, s_diffuse, s_specular};
-    composite_fwd_kernel<<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, R, S, infinity, weights, trans, out);
+    composite_fwd_kernel<<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, ray_valid, R, S, infinity, weights, trans, out);
     SNRF_RETURN_LAUNCH("snrf_composite_fwd");
 }
 
 SNRF_API int snrf_composite_bwd(const float* sigma, const float* tint, const float* diffuse, const float* specular,
                                 int s_sigma, int s_tint, int s_diffuse, int s_specular,
                                 const float* z_vals, const float* dists, const float* rays_d, const float* trans,
-                                const float* g_out, const float* g_weights, int R, int S, int infinity,
+                                const float* g_out, const float* g_weights, const unsigned char* ray_valid, int R, int S, int infinity,
                                 float* g_sigma, float* g_tint, float* g_diffuse, float* g_specular,
                                 int gs_sigma, int gs_tint, int gs_diffuse, int gs_specular,
                                 float* grad_rays_d, void* stream)
@@ -228,6 +237,6 @@ SNRF_API int snrf_composite_bwd(const float* sigma, const float* tint, const flo
     if (R <= 0) return 0;
     Heads in{sigma, tint, diffuse, specular, s_sigma, s_tint, s_diffuse, s_specular};
     HeadGrads g{g_sigma, g_tint, g_diffuse, g_specular, gs_sigma, gs_tint, gs_diffuse, gs_specular};
-    composite_bwd_kernel<<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, trans, g_out, g_weights, R, S, infinity, g, grad_rays_d);
+    composite_bwd_kernel<<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, trans, g_out, g_weights, ray_valid, R, S, infinity, g, grad_rays_d);
     SNRF_RETURN_LAUNCH("snrf_composite_bwd");
 }

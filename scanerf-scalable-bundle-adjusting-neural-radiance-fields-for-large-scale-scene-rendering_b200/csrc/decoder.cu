@@ -44,7 +44,8 @@ namespace {
 template <bool SPLIT>
 __global__ void __launch_bounds__(kRows, 1)
 decoder_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ mask32, const float* __restrict__ rays_d,
-                   DecoderParams p, float* __restrict__ out, int N, int S, int num_tiles, long long level_stride)
+                   DecoderParams p, float* __restrict__ out, int N, int S, int num_tiles, long long level_stride,
+                   const unsigned char* __restrict__ ray_valid)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -72,7 +73,8 @@ decoder_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n = tile * kRows + tid;
-        const bool live = n < N;
+        const bool live = n < N && (ray_valid == nullptr || ray_valid[n / S] != 0);
+        if (ray_valid != nullptr && !__syncthreads_or(live)) continue;     // every sample of the tile belongs to a masked-out ray
         float head[10], zh[7];
         f3 d = mk3(0.f, 0.f, 1.f);
         float dn = 1.0f;
@@ -113,7 +115,8 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(kRows, 1)
 decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ mask32, const float* __restrict__ rays_d,
                    DecoderParams p, const float* __restrict__ grad_heads, float* __restrict__ grad_feats,
-                   float* __restrict__ grad_rays_d, DecoderGrads gp, int N, int S, int num_tiles, long long level_stride)
+                   float* __restrict__ grad_rays_d, DecoderGrads gp, int N, int S, int num_tiles, long long level_stride,
+                   const unsigned char* __restrict__ ray_valid)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -213,10 +216,11 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         }
     };
 
-    bool first = true;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, first = false) {
+    bool first = true;      // no tile processed yet: the first one initialises the TMEM gradient accumulators
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n = tile * kRows + tid;
-        const bool live = n < N;
+        const bool live = n < N && (ray_valid == nullptr || ray_valid[n / S] != 0);
+        if (ray_valid != nullptr && !__syncthreads_or(live)) continue;     // tile of masked-out rays only
         float head[10], zh[7];
         f3 d = mk3(0.f, 0.f, 1.f);
         float dn = 1.0f;
@@ -387,11 +391,12 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         }
         // every MMA of this tile has completed (the last commit covers all earlier ones), so the
         // next tile may overwrite the operand tiles
+        first = false;
     }
 
     // ================= flush the weight / bias gradients accumulated in TMEM =================
     umma::tc_fence_after();
-    {
+    if (!first) {           // (a CTA whose tiles were all masked out never initialised its accumulators)
         // M = 64 accumulators: row m lives in TMEM lane 32*(m/16) + m%16 -> warp q, lanes 0..15 hold rows 16q..16q+15
         const int m = 16 * (warp & 3) + lane;
         const bool own = lane < 16;
@@ -458,7 +463,7 @@ SNRF_API void snrf_decoder_set_precision(int split) { g_split = split ? 1 : 0; }
 
 // params: HOST array of 16 DEVICE pointers in network.ShallowMLP state_dict order
 SNRF_API int snrf_decoder_fwd(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
-                              float* heads_out, int N, int S, int level_major, void* stream)
+                              float* heads_out, int N, int S, int level_major, const unsigned char* ray_valid, void* stream)
 {
     SNRF_CHECK_ARG(N >= 0 && S > 0, "snrf_decoder_fwd: need N >= 0, S > 0 (N=%d S=%d)", N, S);
     SNRF_CHECK_ARG(params != nullptr, "snrf_decoder_fwd: params is required");
@@ -477,11 +482,11 @@ SNRF_API int snrf_decoder_fwd(const float* feats, const float* mask32, const flo
     if (g_split) {
         int grid = snrf_sm_count();                 // ~145 KB of shared memory: one CTA per SM
         if (grid > num_tiles) grid = num_tiles;
-        decoder_fwd_kernel<true><<<grid, kRows, fwd_smem<true>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll);
+        decoder_fwd_kernel<true><<<grid, kRows, fwd_smem<true>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
     } else {
         int grid = snrf_sm_count() * 2;             // 2 x (256 TMEM columns, ~87 KB)
         if (grid > num_tiles) grid = num_tiles;
-        decoder_fwd_kernel<false><<<grid, kRows, fwd_smem<false>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll);
+        decoder_fwd_kernel<false><<<grid, kRows, fwd_smem<false>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
     }
     SNRF_RETURN_LAUNCH("snrf_decoder_fwd");
 }
@@ -492,7 +497,7 @@ SNRF_API int snrf_decoder_fwd(const float* feats, const float* mask32, const flo
 // same order and shapes as params (ACCUMULATED).
 SNRF_API int snrf_decoder_bwd(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
                               const float* grad_heads, float* grad_feats, float* grad_rays_d, float* const* grad_params,
-                              int N, int S, int level_major, void* stream)
+                              int N, int S, int level_major, const unsigned char* ray_valid, void* stream)
 {
     SNRF_CHECK_ARG(N >= 0 && S > 0, "snrf_decoder_bwd: need N >= 0, S > 0 (N=%d S=%d)", N, S);
     SNRF_CHECK_ARG(params != nullptr && grad_params != nullptr, "snrf_decoder_bwd: params and grad_params are required");
@@ -514,8 +519,8 @@ SNRF_API int snrf_decoder_bwd(const float* feats, const float* mask32, const flo
     if (grid > num_tiles) grid = num_tiles;
     cudaStream_t s = (cudaStream_t)stream;
     if (g_split)
-        decoder_bwd_kernel<true><<<grid, kRows, bwd_smem<true>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll);
+        decoder_bwd_kernel<true><<<grid, kRows, bwd_smem<true>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
     else
-        decoder_bwd_kernel<false><<<grid, kRows, bwd_smem<false>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll);
+        decoder_bwd_kernel<false><<<grid, kRows, bwd_smem<false>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
     SNRF_RETURN_LAUNCH("snrf_decoder_bwd");
 }

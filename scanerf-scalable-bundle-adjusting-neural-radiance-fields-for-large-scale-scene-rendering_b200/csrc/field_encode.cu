@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kThreads)
 field_fwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_vals,
                  const float* __restrict__ points, const float* __restrict__ bmin_p, const float* __restrict__ bsize_p,
                  const float2* __restrict__ table, const int* __restrict__ res, float2* __restrict__ out, float2* __restrict__ jac,
-                 int N, int S, int L, uint32_t T, int lpb)
+                 const unsigned char* __restrict__ ray_valid, int N, int S, int L, uint32_t T, int lpb)
 {
     const uint32_t mask = T - 1u;
     f3 bmin = mk3(0, 0, 0), bsize = mk3(1, 1, 1);
@@ -99,6 +99,7 @@ field_fwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
             c = ld3(points + 3 * (size_t)n);
         } else {
             const int r = n / S;
+            if (ray_valid != nullptr && !ray_valid[r]) continue;        // masked-out ray: its rows are never read
             c = contract<MODE>(sample_pos(ld3(rays_o + 3 * (size_t)r), ld3(rays_d + 3 * (size_t)r), z_vals[n]), bmin, bsize).c;
         }
         for (int l = l_begin; l < l_end; ++l) {
@@ -144,7 +145,8 @@ field_bwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
                  const float* __restrict__ points, const float* __restrict__ bmin_p, const float* __restrict__ bsize_p,
                  const int* __restrict__ res, const float2* __restrict__ grad, const float2* __restrict__ jac,
                  float* __restrict__ grad_o, float* __restrict__ grad_d, float* __restrict__ grad_points, float2* __restrict__ grad_table,
-                 int N, int S, int L, uint32_t T, int pass_bits, int range_shift, int aggregate_levels)
+                 const unsigned char* __restrict__ ray_valid, int N, int S, int L, uint32_t T, int pass_bits, int range_shift,
+                 int aggregate_levels)
 {
     const uint32_t mask = T - 1u;
     const int lane = threadIdx.x & 31;
@@ -158,7 +160,7 @@ field_bwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
     const int warp_base0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31;
     for (int wb = warp_base0; wb < N; wb += gridDim.x * blockDim.x) {
         const int n = wb + lane;
-        const bool live = n < N;
+        const bool live = n < N && (MODE == kNone || ray_valid == nullptr || ray_valid[n / S] != 0);
         Pt p;
         float z = 0.0f;
         int r = -1;
@@ -280,7 +282,7 @@ SNRF_API void snrf_field_set_passes_log2(int bits) { g_pass_bits_override = bits
 // box (box_min, box_size: device float[3], the DOUBLED tile box of HashGrid).
 SNRF_API int snrf_field_encode_fwd(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
                                    const float* box_min, const float* box_size, int mode, const float* table, const int* res,
-                                   float* out_lm, float* jac_lm, int N, int S, int L, int T, void* stream)
+                                   float* out_lm, float* jac_lm, const unsigned char* ray_valid, int N, int S, int L, int T, void* stream)
 {
     SNRF_CHECK_ARG(N >= 0 && L > 0 && T > 0 && (T & (T - 1)) == 0, "snrf_field_encode_fwd: T must be a power of two (N=%d L=%d T=%d)", N, L, T);
     SNRF_CHECK_ARG(mode >= 0 && mode <= 2 && (mode == 0 ? points != nullptr : (rays_o && rays_d && z_vals && box_min && box_size && S > 0)),
@@ -293,8 +295,8 @@ SNRF_API int snrf_field_encode_fwd(const float* rays_o, const float* rays_d, con
     float2 *o = (float2*)out_lm, *j = (float2*)jac_lm;
 #define SNRF_FWD(MODE)                                                                                                                   \
     do {                                                                                                                                 \
-        if (j) field_fwd_kernel<MODE, true><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, tb, res, o, j, N, S, L, (uint32_t)T, lpb); \
-        else   field_fwd_kernel<MODE, false><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, tb, res, o, j, N, S, L, (uint32_t)T, lpb); \
+        if (j) field_fwd_kernel<MODE, true><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, tb, res, o, j, ray_valid, N, S, L, (uint32_t)T, lpb); \
+        else   field_fwd_kernel<MODE, false><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, tb, res, o, j, ray_valid, N, S, L, (uint32_t)T, lpb); \
     } while (0)
     if (mode == 0) SNRF_FWD(kNone); else if (mode == 1) SNRF_FWD(kFore); else SNRF_FWD(kBack);
 #undef SNRF_FWD
@@ -306,7 +308,7 @@ SNRF_API int snrf_field_encode_fwd(const float* rays_o, const float* rays_d, con
 SNRF_API int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
                                    const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
                                    const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points, float* grad_table,
-                                   int N, int S, int L, int T, void* stream)
+                                   const unsigned char* ray_valid, int N, int S, int L, int T, void* stream)
 {
     SNRF_CHECK_ARG(N >= 0 && L > 0 && T > 0 && (T & (T - 1)) == 0, "snrf_field_encode_bwd: T must be a power of two (N=%d L=%d T=%d)", N, L, T);
     SNRF_CHECK_ARG(mode >= 0 && mode <= 2 && (mode == 0 ? points != nullptr : (rays_o && rays_d && z_vals && box_min && box_size && S > 0)),
@@ -323,7 +325,7 @@ SNRF_API int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, con
     const float2 *g = (const float2*)grad_lm, *j = (const float2*)jac_lm;
     float2* gt = (float2*)grad_table;
     const int agg = L / 2;
-#define SNRF_BWD(MODE) field_bwd_kernel<MODE><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, res, g, j, grad_rays_o, grad_rays_d, grad_points, gt, N, S, L, (uint32_t)T, pass_bits, range_shift, agg)
+#define SNRF_BWD(MODE) field_bwd_kernel<MODE><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, res, g, j, grad_rays_o, grad_rays_d, grad_points, gt, ray_valid, N, S, L, (uint32_t)T, pass_bits, range_shift, agg)
     if (mode == 0) SNRF_BWD(kNone); else if (mode == 1) SNRF_BWD(kFore); else SNRF_BWD(kBack);
 #undef SNRF_BWD
     SNRF_RETURN_LAUNCH("snrf_field_encode_bwd");

@@ -274,11 +274,38 @@ class HashGrid(nn.Module):
         full["diffuse"][valid] = out["diffuse"]
         return {names[k]: v for k, v in full.items()}
 
+    def _fused_ready(self, decoder, out_normal=False):
+        """(decoder parameters | None): the sync-free fused path needs the stock ShallowMLP and a CUDA table."""
+        if not (self.fused_decoder and self.fused_encode) or out_normal or not self.HE.features.is_cuda:
+            return None
+        return _decoder.decoder_params(decoder)
+
+    def render_rays_masked(self, rays_o, rays_d, z_vals, dists, valid, params, mode, contract_mode, infinity, global_step):
+        """The fused render chain over ALL rays with a validity mask instead of the reference's boolean
+        compaction (hashgrid/__init__.py:419-451): masked-out rays are skipped inside every kernel and come
+        back with the values the reference scatters for them (colour 0, depth 0, T_left 1).  Static shapes,
+        no device->host synchronisation anywhere."""
+        R, S = z_vals.shape
+        mask32 = self.weight_feature(global_step).repeat_interleave(2)
+        feats = _field.field_encode(rays_o, rays_d, z_vals, self.HE.features, self.HE.resolution, self.min_bbox,
+                                    self.bbox_size, contract_mode, valid)
+        heads = _field.decoder_apply(feats, rays_d, mask32, S, params, valid)
+        return _render.composite_packed(heads, z_vals, dists, rays_d, infinity, train=(mode is TRAIN), valid=valid)
+
     def render_fore_rays(self, rays_o, rays_d, num_sample, decoder, mode, occlusion_mask=None, infinity=False, **kwargs):
         z_vals, dists = self.samplePoints(rays_o, rays_d, num_sample)
         valid = torch.all(z_vals != -1, dim=-1)
         if occlusion_mask is not None:
             valid = valid & occlusion_mask[..., 0]
+        params = self._fused_ready(decoder)
+        if params is not None:
+            # deviation from the reference: a batch without any valid ray still returns (dict, True) -- all
+            # zeros / T_left = 1 -- instead of (None, False); deciding that on the host would cost a sync
+            out = self.render_rays_masked(rays_o, rays_d, z_vals, dists, valid, params, mode, 1, infinity, kwargs["global_step"])
+            res = dict(out)
+            res.update({"pred_color": out["rgb"], "pred_depth": out["depth"], "T_left": out["T_left"][:, None],
+                        "specular": out["specular"], "diffuse": out["diffuse"], "fore_valid": valid})
+            return res, True
         out, ok = self.render_batch_rays(rays_o[valid], rays_d[valid], z_vals[valid], dists[valid], decoder, mode,
                                          self.contract_fore, out_normal=False, infinity=infinity,
                                          global_step=kwargs["global_step"])
@@ -300,6 +327,12 @@ class HashGrid(nn.Module):
             return None, False
         if occlusion_mask is not None:
             valid = valid & occlusion_mask[..., 0]
+        params = self._fused_ready(decoder)
+        if params is not None:
+            out = self.render_rays_masked(rays_o, rays_d, z_vals, dists, valid, params, mode, 2, infinity, kwargs["global_step"])
+            res = dict(out)
+            res.update({"T_left": out["T_left"][:, None], "valid": valid})
+            return res, True
         out, ok = self.render_batch_rays(rays_o[valid], rays_d[valid], z_vals[valid], dists[valid], decoder, mode,
                                          self.contract_bg, out_normal=False, infinity=infinity,
                                          global_step=kwargs["global_step"])

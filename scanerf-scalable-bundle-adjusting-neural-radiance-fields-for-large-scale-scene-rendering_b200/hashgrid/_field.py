@@ -35,7 +35,7 @@ def _layout(feats):
     return int(feats.shape[0]), 0
 
 
-def decoder_forward(feats, mask32, rays_d, S, params):
+def decoder_forward(feats, mask32, rays_d, S, params, valid=None):
     """feats [N,32] f32 (or level-major [16,N,2]), mask32 [32] f32 or None, rays_d [R,3] (sample n ->
     ray n // S), params = the 16 tensors of hashgrid._decoder.decoder_params().  Returns heads [N,10] =
     (sigma, tint3, diffuse3, specular3)."""
@@ -47,7 +47,7 @@ def decoder_forward(feats, mask32, rays_d, S, params):
     out = torch.empty(N, 10, dtype=f32, device=feats.device)
     arr, keep = _param_array(params)
     m = mask32.contiguous() if mask32 is not None else None
-    rc = capi.lib().snrf_decoder_fwd(ptr(feats), ptr(m), ptr(rays_d), arr, ptr(out), c_int(N), c_int(int(S)), c_int(lm), capi.stream())
+    rc = capi.lib().snrf_decoder_fwd(ptr(feats), ptr(m), ptr(rays_d), arr, ptr(out), c_int(N), c_int(int(S)), c_int(lm), ptr(valid), capi.stream())
     capi.check(rc, "snrf_decoder_fwd")
     return out
 
@@ -58,19 +58,20 @@ class DecoderFn(torch.autograd.Function):
     inputs) and returns d/d feats, d/d rays_d (through the SH view encoding) and d/d params."""
 
     @staticmethod
-    def forward(ctx, feats, rays_d, mask32, S, *params):
+    def forward(ctx, feats, rays_d, mask32, S, valid, *params):
         feats = feats.contiguous()
         rays_d = rays_d.contiguous()
-        heads = decoder_forward(feats, mask32, rays_d, S, params)
+        heads = decoder_forward(feats, mask32, rays_d, S, params, valid)
         ctx.S = int(S)
-        ctx.has_mask = mask32 is not None
-        ctx.save_for_backward(feats, rays_d, mask32 if mask32 is not None else feats.new_empty(0), *params)
+        ctx.has_mask, ctx.has_valid = mask32 is not None, valid is not None
+        ctx.save_for_backward(feats, rays_d, mask32 if mask32 is not None else feats.new_empty(0),
+                              valid if valid is not None else feats.new_empty(0), *params)
         return heads
 
     @staticmethod
     def backward(ctx, g_heads):
-        feats, rays_d, mask32 = ctx.saved_tensors[:3]
-        params = ctx.saved_tensors[3:]
+        feats, rays_d, mask32, valid = ctx.saved_tensors[:4]
+        params = ctx.saved_tensors[4:]
         N, lm = _layout(feats)
         g_heads = g_heads.contiguous()
         g_feats = torch.empty_like(feats)
@@ -85,13 +86,14 @@ class DecoderFn(torch.autograd.Function):
         garr = (ctypes.c_void_p * 16)(*[g.data_ptr() for g in g_params])
         m = mask32.contiguous() if ctx.has_mask else None
         rc = capi.lib().snrf_decoder_bwd(ptr(feats), ptr(m), ptr(rays_d), arr, ptr(g_heads), ptr(g_feats), ptr(g_d), garr,
-                                         c_int(N), c_int(ctx.S), c_int(lm), capi.stream())
+                                         c_int(N), c_int(ctx.S), c_int(lm), ptr(valid) if ctx.has_valid else c_void_p(0), capi.stream())
         capi.check(rc, "snrf_decoder_bwd")
-        return (g_feats, g_d, None, None) + tuple(g_params)
+        return (g_feats, g_d, None, None, None) + tuple(g_params)
 
 
-def decoder_apply(feats, rays_d, mask32, S, params):
-    return DecoderFn.apply(feats, rays_d, mask32, S, *params)
+def decoder_apply(feats, rays_d, mask32, S, params, valid=None):
+    """valid (bool [R] or None): samples of rays flagged False are skipped (rows left unwritten)."""
+    return DecoderFn.apply(feats, rays_d, mask32, S, valid, *params)
 
 
 class FieldEncodeFn(torch.autograd.Function):
@@ -102,7 +104,7 @@ class FieldEncodeFn(torch.autograd.Function):
     temporary) and returns d/d rays_o, d/d rays_d."""
 
     @staticmethod
-    def forward(ctx, rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode):
+    def forward(ctx, rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid):
         R, S = z_vals.shape
         N, L, T = R * S, int(features.shape[0]), int(features.shape[1])
         rays_o, rays_d, z_vals = rays_o.contiguous(), rays_d.contiguous(), z_vals.contiguous()
@@ -115,18 +117,19 @@ class FieldEncodeFn(torch.autograd.Function):
         feats = features.detach().contiguous()
         box_min, box_size = box_min.contiguous(), box_size.contiguous()
         rc = capi.lib().snrf_field_encode_fwd(ptr(rays_o), ptr(rays_d), ptr(z_vals), c_void_p(0), ptr(box_min), ptr(box_size),
-                                              c_int(int(mode)), ptr(feats), ptr(resolution), ptr(out), ptr(jac), c_int(N), c_int(S),
+                                              c_int(int(mode)), ptr(feats), ptr(resolution), ptr(out), ptr(jac), ptr(valid), c_int(N), c_int(S),
                                               c_int(L), c_int(T), capi.stream())
         capi.check(rc, "snrf_field_encode_fwd")
         ctx.mode, ctx.dims = int(mode), (N, S, L, T)
         ctx.features = features
-        ctx.save_for_backward(rays_o, rays_d, z_vals, resolution, box_min, box_size, jac if jac is not None else out.new_empty(0))
-        ctx.has_jac = jac is not None
+        ctx.save_for_backward(rays_o, rays_d, z_vals, resolution, box_min, box_size, jac if jac is not None else out.new_empty(0),
+                              valid if valid is not None else out.new_empty(0))
+        ctx.has_jac, ctx.has_valid = jac is not None, valid is not None
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        rays_o, rays_d, z_vals, resolution, box_min, box_size, jac = ctx.saved_tensors
+        rays_o, rays_d, z_vals, resolution, box_min, box_size, jac, valid = ctx.saved_tensors
         N, S, L, T = ctx.dims
         features = ctx.features
         g_out = g_out.contiguous()
@@ -141,11 +144,12 @@ class FieldEncodeFn(torch.autograd.Function):
             g_table = torch.zeros_like(features)
         rc = capi.lib().snrf_field_encode_bwd(ptr(rays_o), ptr(rays_d), ptr(z_vals), c_void_p(0), ptr(box_min), ptr(box_size),
                                               c_int(ctx.mode), ptr(resolution), ptr(g_out), ptr(jac) if ctx.has_jac else c_void_p(0),
-                                              ptr(g_o), ptr(g_d), c_void_p(0), ptr(g_table), c_int(N), c_int(S), c_int(L), c_int(T),
+                                              ptr(g_o), ptr(g_d), c_void_p(0), ptr(g_table), ptr(valid) if ctx.has_valid else c_void_p(0), c_int(N), c_int(S), c_int(L), c_int(T),
                                               capi.stream())
         capi.check(rc, "snrf_field_encode_bwd")
-        return g_o, g_d, None, (None if direct else g_table), None, None, None, None
+        return g_o, g_d, None, (None if direct else g_table), None, None, None, None, None
 
 
-def field_encode(rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode):
-    return FieldEncodeFn.apply(rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode)
+def field_encode(rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid=None):
+    """valid (bool [R] or None): rays flagged False are skipped (their feature rows are left unwritten)."""
+    return FieldEncodeFn.apply(rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid)

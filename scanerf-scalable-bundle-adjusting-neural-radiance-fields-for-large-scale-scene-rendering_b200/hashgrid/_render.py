@@ -34,7 +34,7 @@ class CompositeFn(torch.autograd.Function):
         row = torch.zeros(R, _ROW, dtype=f32, device=z_vals.device)
         rc = capi.lib().snrf_composite_fwd(ptr(sigma), ptr(tint), ptr(diffuse), ptr(specular),
                                            c_int(1), c_int(3), c_int(3), c_int(3),
-                                           ptr(z_vals), ptr(dists), ptr(rays_d), c_int(R), c_int(S),
+                                           ptr(z_vals), ptr(dists), ptr(rays_d), c_void_p(0), c_int(R), c_int(S),
                                            c_int(int(bool(infinity))), ptr(weights), ptr(trans), ptr(row), capi.stream())
         capi.check(rc, "snrf_composite_fwd")
         ctx.save_for_backward(sigma, tint, diffuse, specular, z_vals, dists, rays_d, trans)
@@ -55,7 +55,7 @@ class CompositeFn(torch.autograd.Function):
         rc = capi.lib().snrf_composite_bwd(ptr(sigma), ptr(tint), ptr(diffuse), ptr(specular),
                                            c_int(1), c_int(3), c_int(3), c_int(3),
                                            ptr(z_vals), ptr(dists), ptr(rays_d), ptr(trans), ptr(g_row),
-                                           ptr(gw) if gw is not None else c_void_p(0),
+                                           ptr(gw) if gw is not None else c_void_p(0), c_void_p(0),
                                            c_int(R), c_int(S), c_int(int(ctx.infinity)),
                                            ptr(g_sigma), ptr(g_tint), ptr(g_diffuse), ptr(g_specular),
                                            c_int(1), c_int(3), c_int(3), c_int(3),
@@ -67,61 +67,69 @@ class CompositeFn(torch.autograd.Function):
 class CompositePackedFn(torch.autograd.Function):
     """Same as CompositeFn for the packed head rows [R*S,10] = (sigma, tint3, diffuse3, specular3)
     written by the tensor-core decoder; the gradient comes back packed the same way, ready for
-    snrf_decoder_bwd -- no strided slicing or re-packing in between."""
+    snrf_decoder_bwd -- no strided slicing or re-packing in between.  `valid` (bool [R] or None):
+    rays flagged False are not composited (zero outputs, T_left = 1) and get no gradient."""
 
     @staticmethod
-    def forward(ctx, heads, z_vals, dists, rays_d, infinity):
+    def forward(ctx, heads, z_vals, dists, rays_d, infinity, valid):
         R, S = z_vals.shape
         f32 = torch.float32
         heads, z_vals, dists, rays_d = heads.contiguous(), z_vals.contiguous(), dists.contiguous(), rays_d.contiguous()
         weights = torch.empty(R, S, dtype=f32, device=z_vals.device)
         trans = torch.empty(R, S, dtype=f32, device=z_vals.device)
-        row = torch.zeros(R, _ROW, dtype=f32, device=z_vals.device)
+        row = torch.empty(R, _ROW, dtype=f32, device=z_vals.device)
         hp = heads.data_ptr()
         rc = capi.lib().snrf_composite_fwd(c_void_p(hp), c_void_p(hp + 4), c_void_p(hp + 16), c_void_p(hp + 28),
                                            c_int(10), c_int(10), c_int(10), c_int(10),
-                                           ptr(z_vals), ptr(dists), ptr(rays_d), c_int(R), c_int(S),
+                                           ptr(z_vals), ptr(dists), ptr(rays_d), ptr(valid), c_int(R), c_int(S),
                                            c_int(int(bool(infinity))), ptr(weights), ptr(trans), ptr(row), capi.stream())
         capi.check(rc, "snrf_composite_fwd")
-        ctx.save_for_backward(heads, z_vals, dists, rays_d, trans)
-        ctx.infinity = bool(infinity)
+        ctx.save_for_backward(heads, z_vals, dists, rays_d, trans, valid if valid is not None else heads.new_empty(0))
+        ctx.infinity, ctx.has_valid = bool(infinity), valid is not None
+        ctx.set_materialize_grads(False)        # an unused `weights` output costs no zero-filled gradient
         return row, weights
 
     @staticmethod
     def backward(ctx, g_row, g_weights):
-        heads, z_vals, dists, rays_d, trans = ctx.saved_tensors
+        heads, z_vals, dists, rays_d, trans, valid = ctx.saved_tensors
         R, S = z_vals.shape
+        if g_row is None:
+            g_row = torch.zeros(R, _ROW, dtype=torch.float32, device=z_vals.device)
         g_row = g_row.contiguous()
         gw = g_weights.contiguous() if g_weights is not None else None
+        # masked-out rows are never read by the decoder backward; valid rows are fully written
         g_heads = torch.empty_like(heads)
         g_d = torch.empty_like(rays_d) if ctx.needs_input_grad[3] else None
         hp, gp = heads.data_ptr(), g_heads.data_ptr()
         rc = capi.lib().snrf_composite_bwd(c_void_p(hp), c_void_p(hp + 4), c_void_p(hp + 16), c_void_p(hp + 28),
                                            c_int(10), c_int(10), c_int(10), c_int(10),
                                            ptr(z_vals), ptr(dists), ptr(rays_d), ptr(trans), ptr(g_row),
-                                           ptr(gw) if gw is not None else c_void_p(0),
+                                           ptr(gw), ptr(valid) if ctx.has_valid else c_void_p(0),
                                            c_int(R), c_int(S), c_int(int(ctx.infinity)),
                                            c_void_p(gp), c_void_p(gp + 4), c_void_p(gp + 16), c_void_p(gp + 28),
                                            c_int(10), c_int(10), c_int(10), c_int(10),
                                            ptr(g_d) if g_d is not None else c_void_p(0), capi.stream())
         capi.check(rc, "snrf_composite_bwd")
-        return g_heads, None, None, g_d, None
+        return g_heads, None, None, g_d, None, None
 
 
-def _finish(row, weights, train):
+def _finish(row, weights, train, valid=None):
     out = {"diffuse": row[:, 4:7], "tint": row[:, 1:4], "specular": row[:, 7:10]}
     out["rgb"] = torch.clamp(out["diffuse"] + out["specular"], 0, 1)
     out["depth"] = row[:, 0:1]
     out["T_left"] = row[:, 13]
     out["weights"] = weights[..., None]
     if train:
-        out["l2_reg_specular"] = torch.mean(row[:, 10:13])
+        if valid is None:
+            out["l2_reg_specular"] = torch.mean(row[:, 10:13])
+        else:       # mean over the rendered rays only (masked rows are zero), no host sync on the count
+            out["l2_reg_specular"] = row[:, 10:13].sum() / (3.0 * valid.sum().clamp_min(1))
     return out
 
 
-def composite_packed(heads, z_vals, dists, rays_d, infinity, train):
-    row, weights = CompositePackedFn.apply(heads, z_vals, dists, rays_d, infinity)
-    return _finish(row, weights, train)
+def composite_packed(heads, z_vals, dists, rays_d, infinity, train, valid=None):
+    row, weights = CompositePackedFn.apply(heads, z_vals, dists, rays_d, infinity, valid)
+    return _finish(row, weights, train, valid)
 
 
 def composite(heads, z_vals, dists, rays_d, infinity, train):

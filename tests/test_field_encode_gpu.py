@@ -116,3 +116,44 @@ def test_hashgrid_fused_and_unfused_render_agree():
         assert torch.allclose(a[0], b[0], atol=1e-6), "rgb"
         for k, name in ((1, "d/d rays_o"), (2, "d/d rays_d"), (3, "table gradient")):
             assert _rel(a[k], b[k]) < 1e-4, f"{name} (infinity={inf}): {_rel(a[k], b[k])}"
+
+
+def test_masked_render_equals_compacted_render():
+    """render_fore_rays / render_bg_rays: the sync-free masked path (every kernel skips masked-out rays)
+    against the reference-style boolean compaction + scatter-back, values and gradients."""
+    load_pkg()
+    from hashgrid import HashGrid, TRAIN
+    from hashgrid._decoder import ShallowMLP
+    dev = torch.device(DEV)
+    torch.manual_seed(0)
+    hg = HashGrid(dev, torch.tensor([0.0, 0.0, 0.0], device=dev), torch.tensor([20.0, 13.0, 30.0], device=dev), 15, [16, 256], 4, False, "")
+    g = torch.Generator().manual_seed(2)
+    hg.occupied_grid = (torch.rand(hg.occupied_grid.shape, generator=g) < 0.5).to(dev)
+    dec = ShallowMLP(32).to(dev)
+    R, S = 300, 32
+    o = torch.tensor([10.0, 6.5, 15.0]) + torch.randn(R, 3, generator=g) * torch.tensor([14.0, 6.0, 20.0])     # many origins outside the tile
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    occl = (torch.rand(R, 1, generator=g) < 0.8).to(dev)
+    res = {}
+    for fused in (True, False):
+        hg.fused_encode = fused
+        hg.HE.features.grad = None
+        dec.zero_grad()
+        oo, dd = o.to(dev).requires_grad_(True), d.to(dev).requires_grad_(True)
+        fg, ok1 = hg.render_fore_rays(oo, dd, S, dec, TRAIN, occlusion_mask=occl, global_step=7000)
+        bg, ok2 = hg.render_bg_rays(oo, dd, S, dec, TRAIN, occlusion_mask=occl, global_step=7000, bg_mode="IZ", invalid_underground=True)
+        assert ok1 and ok2
+        assert 0 < int(fg["fore_valid"].sum()) < R and 0 < int(bg["valid"].sum()) <= R
+        col = fg["pred_color"] + fg["T_left"] * bg["rgb"]
+        loss = (col ** 2).sum() + 0.1 * fg["pred_depth"].sum() + fg["l2_reg_specular"] + bg["l2_reg_specular"]
+        loss.backward()
+        res[fused] = dict(col=col.detach().clone(), T=fg["T_left"].detach().clone(), depth=bg["depth"].detach().clone(),
+                          go=oo.grad.clone(), gd=dd.grad.clone(), gt=hg.HE.features.grad.clone(),
+                          gw=dec.Spatial_MLP.mlp[0].weight.grad.clone(), l2=float(fg["l2_reg_specular"]) + float(bg["l2_reg_specular"]))
+    a, b = res[True], res[False]
+    assert a["T"].shape == b["T"].shape == (R, 1)
+    for k in ("col", "T", "depth"):
+        assert torch.allclose(a[k], b[k], atol=1e-5), k
+    assert abs(a["l2"] - b["l2"]) < 1e-6
+    for k in ("go", "gd", "gt", "gw"):
+        assert _rel(a[k], b[k]) < 2e-4, f"{k}: {_rel(a[k], b[k])}"
