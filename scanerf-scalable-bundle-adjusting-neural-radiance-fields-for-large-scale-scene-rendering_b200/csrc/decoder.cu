@@ -42,7 +42,7 @@ namespace {
 // feats [N,32] f32, rays_d [R,3] (sample n belongs to ray n / S), out [N,10] f32 =
 // (sigma, tint3, diffuse3, specular3).
 template <bool SPLIT>
-__global__ void __launch_bounds__(kRows, 1)
+__global__ void __launch_bounds__(kThreadsDec, 1)
 decoder_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ mask32, const float* __restrict__ rays_d,
                    DecoderParams p, float* __restrict__ out, int N, int S, int num_tiles, long long level_stride,
                    const unsigned char* __restrict__ ray_valid)
@@ -58,7 +58,7 @@ decoder_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
 
-    stage_all_weights<SPLIT>(smem, p, mask32, tid, kRows);
+    stage_all_weights<SPLIT>(smem, p, mask32, tid, kThreadsDec);
     if (warp == 0) umma::tmem_alloc<256>(&tmem_slot);
     if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_fence_init(); }
     umma::fence_async_smem();
@@ -66,30 +66,28 @@ decoder_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     __syncthreads();
     umma::tc_fence_after();
     Ctx<SPLIT> c;
-    c.smem = smem; c.bar = &bar; c.tmem = tmem_slot; c.lane_addr = (uint32_t)(32 * (warp & 3)) << 16; c.phase = 0; c.tid = tid;
-    c.bias = reinterpret_cast<const float*>(smem + off_bias<SPLIT>());
-    c.mask = reinterpret_cast<const float*>(smem + off_mask<SPLIT>());
+    c.init(smem, &bar, tmem_slot);
     const Tiles T{T0, T1, nullptr, T2, T1, nullptr, T2, nullptr, LOa, LOb};
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n = tile * kRows + tid;
+        const int n = tile * kRows + c.row;
         const bool live = n < N && (ray_valid == nullptr || ray_valid[n / S] != 0);
         if (ray_valid != nullptr && !__syncthreads_or(live)) continue;     // every sample of the tile belongs to a masked-out ray
         float head[10], zh[7];
         f3 d = mk3(0.f, 0.f, 1.f);
         float dn = 1.0f;
         forward_tile<SPLIT, false>(c, T, feats, rays_d, n, live, S, head, zh, d, dn, level_stride);
-        {
+        if (c.cg == 0) {
             float z[16];
             umma::tmem_ld16(c.tmem + cDh + c.lane_addr, z);
             umma::tc_wait_ld();
 #pragma unroll
             for (int j = 0; j < 3; ++j) head[7 + j] = sigmoidf(z[j] + c.bias[oB5 + j]);
-        }
-        if (live) {
-            float2* o = reinterpret_cast<float2*>(out + (size_t)n * 10);
+            if (live) {
+                float2* o = reinterpret_cast<float2*>(out + (size_t)n * 10);
 #pragma unroll
-            for (int j = 0; j < 5; ++j) o[j] = make_float2(head[2 * j], head[2 * j + 1]);
+                for (int j = 0; j < 5; ++j) o[j] = make_float2(head[2 * j], head[2 * j + 1]);
+            }
         }
         // every MMA of this tile has completed; the next tile's first sync_operands() orders its
         // operand stores and this tile's TMEM loads before the next accumulator writes
@@ -112,7 +110,7 @@ decoder_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
 // a4_lo in the forward, then [dz_heads | dz_spec | lo parts] and finally dH = dz2); a4 holds dH_lo after
 // B1; g = d(activation)/dz.
 template <bool SPLIT>
-__global__ void __launch_bounds__(kRows, 1)
+__global__ void __launch_bounds__(kThreadsDec, 1)
 decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ mask32, const float* __restrict__ rays_d,
                    DecoderParams p, const float* __restrict__ grad_heads, float* __restrict__ grad_feats,
                    float* __restrict__ grad_rays_d, DecoderGrads gp, int N, int S, int num_tiles, long long level_stride,
@@ -131,7 +129,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    stage_all_weights<SPLIT>(smem, p, mask32, tid, kRows);
+    stage_all_weights<SPLIT>(smem, p, mask32, tid, kThreadsDec);
     float* small_grad = reinterpret_cast<float*>(smem + off_small<SPLIT>());
     if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);
     if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_fence_init(); }
@@ -140,9 +138,8 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     __syncthreads();
     umma::tc_fence_after();
     Ctx<SPLIT> c;
-    c.smem = smem; c.bar = &bar; c.tmem = tmem_slot; c.lane_addr = (uint32_t)(32 * (warp & 3)) << 16; c.phase = 0; c.tid = tid;
-    c.bias = reinterpret_cast<const float*>(smem + off_bias<SPLIT>());
-    c.mask = reinterpret_cast<const float*>(smem + off_mask<SPLIT>());
+    c.init(smem, &bar, tmem_slot);
+    const int row = c.row, cg = c.cg;
     const uint32_t tmem = c.tmem, lane_addr = c.lane_addr;
     const float* bias = c.bias;
     const float* mask = c.mask;
@@ -193,32 +190,35 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
             for (int k = 0; k < 8; ++k)
                 umma::mma_bf16(tmem + col, umma::desc_mnmajor(a_tile, k), umma::desc_mnmajor(b_lo, k), idesc, 1);
     };
-    float v[32];
-    // dz = dA * g: hi part in place over the g tile, lo part (SPLIT) into Tlo (this thread's row only)
+    float v[16];
+    // dz = dA * g on this thread's 16 columns: hi part in place over the g tile, lo part (SPLIT) into Tlo
     auto mul_inplace = [&](int col, unsigned char* Tg, unsigned char* Tlo) {
+        umma::tmem_ld16(tmem + col + lane_addr + 16 * cg, v);
+        umma::tc_wait_ld();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            umma::tmem_ld32(tmem + col + lane_addr + 32 * h, v);
-            umma::tc_wait_ld();
+        for (int q = 0; q < 2; ++q) {
+            const uint4 w4 = *reinterpret_cast<const uint4*>(Tg + umma::tile_chunk_off(row, 2 * cg + q));
+            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+            float o[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint4 w4 = *reinterpret_cast<const uint4*>(Tg + umma::tile_chunk_off(tid, 4 * h + q));
-                const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-                float o[8];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const __half2 h2 = *reinterpret_cast<const __half2*>(&w[e]);
-                    o[2 * e] = v[8 * q + 2 * e] * __low2float(h2);
-                    o[2 * e + 1] = v[8 * q + 2 * e + 1] * __high2float(h2);
-                }
-                store8_hl<SPLIT>(Tg, 4 * h + q, Tlo, 4 * h + q, tid, o);
+            for (int e = 0; e < 4; ++e) {
+                const __half2 h2 = *reinterpret_cast<const __half2*>(&w[e]);
+                o[2 * e] = v[8 * q + 2 * e] * __low2float(h2);
+                o[2 * e + 1] = v[8 * q + 2 * e + 1] * __high2float(h2);
             }
+            store8_hl<SPLIT>(Tg, 2 * cg + q, Tlo, 2 * cg + q, row, o);
         }
+    };
+    // 32 accumulator columns (8 per column group) -> chunk (chunk0 + cg) of a hi / lo tile pair
+    auto store_quarter = [&](int col, unsigned char* Thi, unsigned char* Tlo, int chunk0) {
+        umma::tmem_ld8(tmem + col + lane_addr + 8 * cg, v);
+        umma::tc_wait_ld();
+        store8_hl<SPLIT>(Thi, chunk0 + cg, Tlo, chunk0 + cg, row, v);
     };
 
     bool first = true;      // no tile processed yet: the first one initialises the TMEM gradient accumulators
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n = tile * kRows + tid;
+        const int n = tile * kRows + row;
         const bool live = n < N && (ray_valid == nullptr || ray_valid[n / S] != 0);
         if (ray_valid != nullptr && !__syncthreads_or(live)) continue;     // tile of masked-out rays only
         float head[10], zh[7];
@@ -226,9 +226,9 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         float dn = 1.0f;
         forward_tile<SPLIT, true>(c, T, feats, rays_d, n, live, S, head, zh, d, dn, level_stride);
 
-        // ---- d(loss)/d(pre-activations) of the 7 heads and the 3 specular outputs
-        float dzh[16], dzs[16];
-        {
+        // ---- d(loss)/d(pre-activations) of the 7 heads and the 3 specular outputs (column group 0)
+        if (cg == 0) {
+            float dzh[16], dzs[16];
             float gh[10];
             if (live) {
                 const float2* gsrc = reinterpret_cast<const float2*>(grad_heads + (size_t)n * 10);
@@ -252,10 +252,10 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
                 dzs[j] = gh[7 + j] * s * (1.0f - s);                            // specular
             }
             // Tdz = [dz_heads 0..15 | dz_spec 16..31 | dz_heads_lo 32..47 | dz_spec_lo 48..63]
-            store8_hl<SPLIT>(Tdz, 0, Tdz, 4, tid, dzh);
-            store8_hl<SPLIT>(Tdz, 1, Tdz, 5, tid, dzh + 8);
-            store8_hl<SPLIT>(Tdz, 2, Tdz, 6, tid, dzs);
-            store8_hl<SPLIT>(Tdz, 3, Tdz, 7, tid, dzs + 8);
+            store8_hl<SPLIT>(Tdz, 0, Tdz, 4, row, dzh);
+            store8_hl<SPLIT>(Tdz, 1, Tdz, 5, row, dzh + 8);
+            store8_hl<SPLIT>(Tdz, 2, Tdz, 6, row, dzs);
+            store8_hl<SPLIT>(Tdz, 3, Tdz, 7, row, dzs + 8);
             // bias gradients of the narrow layers: warp reduction, one shared atomic per warp
 #pragma unroll
             for (int j = 0; j < 10; ++j) {
@@ -276,10 +276,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         }
         c.wait_mma();
         mul_inplace(cDa, T.g4, Tdzlo);                           // dz5
-        umma::tmem_ld32(tmem + cDb + lane_addr, v);              // dH[0:32] -> dz2 tile columns 0..31 (over the consumed dz_heads/spec)
-        umma::tc_wait_ld();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) store8_hl<SPLIT>(Tdz, q, Tdhlo, q, tid, v + 8 * q);
+        store_quarter(cDb, Tdz, Tdhlo, 0);                       // dH[0:32] -> dz2 tile columns 0..31 (over the consumed dz_heads/spec)
         c.sync_operands();
         // ---- B2: dA3 = dz5 W4 ; dW4 += dz5^T a3 ; db4
         if (tid == 0) {
@@ -300,11 +297,8 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
             umma::mma_commit(&bar);
         }
         c.wait_mma();
-        umma::tmem_ld32(tmem + cDa + lane_addr, v);              // dH[32:64]
-        umma::tc_wait_ld();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) store8_hl<SPLIT>(Tdz, 4 + q, Tdhlo, 4 + q, tid, v + 8 * q);
-        if (grad_rays_d != nullptr) {                            // d/d(ray direction) through the SH encoding
+        store_quarter(cDa, Tdz, Tdhlo, 4);                       // dH[32:64]
+        if (grad_rays_d != nullptr && cg == 3) {                 // d/d(ray direction) through the SH encoding (one thread per row)
             float dsh[16];
             umma::tmem_ld16(tmem + cDa + lane_addr + 32, dsh);
             umma::tc_wait_ld();
@@ -374,19 +368,19 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
             umma::mma_commit(&bar);
         }
         c.wait_mma();
-        umma::tmem_ld32(tmem + cDa + lane_addr, v);
+        umma::tmem_ld8(tmem + cDa + lane_addr + 8 * cg, v);     // d/d x, columns 8 cg .. 8 cg + 7 = levels 4 cg .. 4 cg + 3
         umma::tc_wait_ld();
         if (live) {
-            if (level_stride == 0) {
-                float4* dst = reinterpret_cast<float4*>(grad_feats + (size_t)n * 32);
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    dst[q] = make_float4(v[4 * q] * mask[4 * q], v[4 * q + 1] * mask[4 * q + 1], v[4 * q + 2] * mask[4 * q + 2],
-                                         v[4 * q + 3] * mask[4 * q + 3]);
+            for (int j = 0; j < 8; ++j) v[j] *= mask[8 * cg + j];
+            if (level_stride == 0) {
+                float4* dst = reinterpret_cast<float4*>(grad_feats + (size_t)n * 32 + 8 * cg);
+                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
             } else {            // level-major [16][N] float2: consecutive samples -> consecutive addresses
                 float2* dst = reinterpret_cast<float2*>(grad_feats) + n;
 #pragma unroll
-                for (int l = 0; l < 16; ++l) dst[(size_t)l * level_stride] = make_float2(v[2 * l] * mask[2 * l], v[2 * l + 1] * mask[2 * l + 1]);
+                for (int l = 0; l < 4; ++l) dst[(size_t)(4 * cg + l) * level_stride] = make_float2(v[2 * l], v[2 * l + 1]);
             }
         }
         // every MMA of this tile has completed (the last commit covers all earlier ones), so the
@@ -399,7 +393,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     if (!first) {           // (a CTA whose tiles were all masked out never initialised its accumulators)
         // M = 64 accumulators: row m lives in TMEM lane 32*(m/16) + m%16 -> warp q, lanes 0..15 hold rows 16q..16q+15
         const int m = 16 * (warp & 3) + lane;
-        const bool own = lane < 16;
+        const bool own = lane < 16 && cg == 0;
         float w[32];
         auto flush = [&](int col, int ncols, float* dst, int ld, int col0) {
             for (int c0 = 0; c0 < ncols; c0 += 32) {
@@ -482,11 +476,11 @@ SNRF_API int snrf_decoder_fwd(const float* feats, const float* mask32, const flo
     if (g_split) {
         int grid = snrf_sm_count();                 // ~145 KB of shared memory: one CTA per SM
         if (grid > num_tiles) grid = num_tiles;
-        decoder_fwd_kernel<true><<<grid, kRows, fwd_smem<true>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
+        decoder_fwd_kernel<true><<<grid, kThreadsDec, fwd_smem<true>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
     } else {
         int grid = snrf_sm_count() * 2;             // 2 x (256 TMEM columns, ~87 KB)
         if (grid > num_tiles) grid = num_tiles;
-        decoder_fwd_kernel<false><<<grid, kRows, fwd_smem<false>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
+        decoder_fwd_kernel<false><<<grid, kThreadsDec, fwd_smem<false>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
     }
     SNRF_RETURN_LAUNCH("snrf_decoder_fwd");
 }
@@ -519,8 +513,8 @@ SNRF_API int snrf_decoder_bwd(const float* feats, const float* mask32, const flo
     if (grid > num_tiles) grid = num_tiles;
     cudaStream_t s = (cudaStream_t)stream;
     if (g_split)
-        decoder_bwd_kernel<true><<<grid, kRows, bwd_smem<true>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
+        decoder_bwd_kernel<true><<<grid, kThreadsDec, bwd_smem<true>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
     else
-        decoder_bwd_kernel<false><<<grid, kRows, bwd_smem<false>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
+        decoder_bwd_kernel<false><<<grid, kThreadsDec, bwd_smem<false>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
     SNRF_RETURN_LAUNCH("snrf_decoder_bwd");
 }

@@ -181,15 +181,33 @@ struct Tiles {
     unsigned char *A0, *a1, *g1, *H, *a3, *g3, *a4, *g4, *LOa, *LOb;
 };
 
+// Thread layout of the decoder kernels: kThreadsDec = 512 threads = 16 warps per 128-row tile.
+// Thread (row, cg): row = 32 * (warp & 3) + lane is the sample / TMEM lane (a warp can only read the
+// TMEM lane quadrant warp % 4), cg = warp >> 2 is the column group: in every 64-wide layer the thread
+// owns columns [16 cg, 16 cg + 16).  Four warps per scheduler hide the latency of the activation /
+// conversion epilogues that a one-thread-per-row layout (one warp per scheduler) leaves exposed.
+constexpr int kThreadsDec = 512;
+
 // Per-thread context shared by the forward stages
 template <bool SPLIT>
 struct Ctx {
     unsigned char* smem;
     uint64_t* bar;
     uint32_t tmem, lane_addr, phase;
-    int tid;
+    int tid, row, cg;
     const float* bias;
     const float* mask;
+    __device__ __forceinline__ void init(unsigned char* smem_, uint64_t* bar_, uint32_t tmem_)
+    {
+        smem = smem_; bar = bar_; tmem = tmem_; phase = 0;
+        tid = threadIdx.x;
+        const int warp = tid >> 5;
+        row = 32 * (warp & 3) + (tid & 31);
+        cg = warp >> 2;
+        lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
+        bias = reinterpret_cast<const float*>(smem + off_bias<SPLIT>());
+        mask = reinterpret_cast<const float*>(smem + off_mask<SPLIT>());
+    }
     __device__ __forceinline__ void sync_operands()
     {   // my shared-memory stores and TMEM loads are done -> the next MMAs may run
         umma::fence_async_smem();
@@ -206,26 +224,27 @@ struct Ctx {
 };
 
 // Operand row of one sample: A0 = [x_hi (0..31) | SH_hi (32..47) | SH_lo (48..63)], LOb = [x_lo (0..31)].
-// x = the 32 (already masked) features, sh = the 16 SH coefficients of the unit view direction.
+// Thread (row, cg) stores feature chunk cg: x8 = the 8 (already masked) features 8 cg .. 8 cg + 7; the
+// threads with cg >= 2 also store SH chunk cg - 2: sh8 = SH coefficients 8 (cg - 2) .. + 7.
 template <bool SPLIT>
-__device__ __forceinline__ void store_input_row(const Tiles& T, int tid, const float* x, const float* sh)
+__device__ __forceinline__ void store_input_row(const Tiles& T, int row, int cg, const float* x8, const float* sh8)
 {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) store8_hl<SPLIT>(T.A0, q, T.LOb, q, tid, x + 8 * q);
-    store8_hl<SPLIT>(T.A0, 4, T.A0, 6, tid, sh);
-    store8_hl<SPLIT>(T.A0, 5, T.A0, 7, tid, sh + 8);
-    if (!SPLIT) { umma::tile_zero8(T.A0, tid, 6); umma::tile_zero8(T.A0, tid, 7); }
+    store8_hl<SPLIT>(T.A0, cg, T.LOb, cg, row, x8);
+    if (cg >= 2) {
+        store8_hl<SPLIT>(T.A0, 2 + cg, T.A0, 4 + cg, row, sh8);
+        if (!SPLIT) umma::tile_zero8(T.A0, row, 4 + cg);
+    }
 }
 
 // The decoder layers of one tile up to (and including) the L5 GEMM, from operand rows already in
-// A0 / LOb.  Writes the operand tiles, returns sigma/diffuse/tint activated in head[0..6]
-// (torch semantics) and their pre-activations in zh[0..6]; the specular pre-activations are left
-// in TMEM columns cDh..cDh+2.
+// A0 / LOb.  Writes the operand tiles; the threads with cg == 0 return sigma/diffuse/tint activated in
+// head[0..6] (torch semantics) and their pre-activations in zh[0..6]; the specular pre-activations are
+// left in TMEM columns cDh..cDh+2.
 template <bool SPLIT, bool TRAIN>
 __device__ __forceinline__ void forward_layers(Ctx<SPLIT>& c, const Tiles& T, float* head, float* zh)
 {
     unsigned char* smem = c.smem;
-    const int tid = c.tid;
+    const int tid = c.tid, row = c.row, cg = c.cg;
     const uint32_t tmem = c.tmem, lane_addr = c.lane_addr;
     const float* bias = c.bias;
     const uint32_t aA0 = umma::smem_u32(T.A0), aa1 = umma::smem_u32(T.a1), aH = umma::smem_u32(T.H), aa3 = umma::smem_u32(T.a3),
@@ -243,25 +262,23 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT>& c, const Tiles& T, fl
         umma::mma_commit(c.bar);
     }
     c.wait_mma();
-    float v[32], g[32];
-    // Gaussian layer epilogue: a = exp(-50 z^2) -> (Ta, lo in Tlo);  TRAIN: g = da/dz = -100 z a -> Tg
+    float v[16], g[16];
+    // Gaussian layer epilogue on this thread's 16 columns: a = exp(-50 z^2) -> (Ta, lo in Tlo);
+    // TRAIN: g = da/dz = -100 z a -> Tg
     auto gauss_epilogue = [&](int col, int boff, unsigned char* Ta, unsigned char* Tlo, unsigned char* Tg) {
+        umma::tmem_ld16(tmem + col + lane_addr + 16 * cg, v);
+        umma::tc_wait_ld();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            umma::tmem_ld32(tmem + col + lane_addr + 32 * h, v);
-            umma::tc_wait_ld();
+        for (int j = 0; j < 16; ++j) {
+            const float z = v[j] + bias[boff + 16 * cg + j];
+            const float a = gauss_act(z);
+            v[j] = a;
+            if (TRAIN) g[j] = -100.0f * z * a;
+        }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float z = v[j] + bias[boff + 32 * h + j];
-                const float a = gauss_act(z);
-                v[j] = a;
-                if (TRAIN) g[j] = -100.0f * z * a;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                store8_hl<SPLIT>(Ta, 4 * h + q, Tlo, 4 * h + q, tid, v + 8 * q);
-                if (TRAIN) umma::tile_store8_f16(Tg, tid, 4 * h + q, g + 8 * q);   // fp16: |g| <= 6.1, read back element-wise only
-            }
+        for (int q = 0; q < 2; ++q) {
+            store8_hl<SPLIT>(Ta, 2 * cg + q, Tlo, 2 * cg + q, row, v + 8 * q);
+            if (TRAIN) umma::tile_store8_f16(Tg, row, 2 * cg + q, g + 8 * q);   // fp16: |g| <= 6.1, read back element-wise only
         }
     };
     gauss_epilogue(cDa, oB1, T.a1, T.LOa, T.g1);
@@ -272,15 +289,12 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT>& c, const Tiles& T, fl
         umma::mma_commit(c.bar);
     }
     c.wait_mma();
+    umma::tmem_ld16(tmem + cDb + lane_addr + 16 * cg, v);
+    umma::tc_wait_ld();
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        umma::tmem_ld32(tmem + cDb + lane_addr + 32 * h, v);
-        umma::tc_wait_ld();
+    for (int j = 0; j < 16; ++j) v[j] += bias[oB2 + 16 * cg + j];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += bias[oB2 + 32 * h + j];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) store8_hl<SPLIT>(T.H, 4 * h + q, T.LOb, 4 * h + q, tid, v + 8 * q);
-    }
+    for (int q = 0; q < 2; ++q) store8_hl<SPLIT>(T.H, 2 * cg + q, T.LOb, 2 * cg + q, row, v + 8 * q);
     c.sync_operands();
     // ---- heads: Dh = H[0:32] Wh^T (K = 32, N = 16);   L3: Da = [H[32:64] | SH] W3^T (K = 48)
     if (tid == 0) {
@@ -290,7 +304,7 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT>& c, const Tiles& T, fl
         umma::mma_commit(c.bar);
     }
     c.wait_mma();
-    {
+    if (cg == 0) {
         float z[16];
         umma::tmem_ld16(tmem + cDh + lane_addr, z);
         umma::tc_wait_ld();
@@ -322,41 +336,43 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT>& c, const Tiles& T, fl
 }
 
 // Training-side input: features from HBM times the level mask, SH of d / (|d| + 1e-8) (network.py:172-190).
+// feats: [N,32] row-major (level_stride = 0) or level-major [16][N] float2 (level_stride = N).
+// d / dn (the ray direction and its norm) are returned to the threads with cg >= 2.
 template <bool SPLIT, bool TRAIN>
 __device__ __forceinline__ void forward_tile(Ctx<SPLIT>& c, const Tiles& T, const float* __restrict__ feats,
                                              const float* __restrict__ rays_d, int n, bool live, int S, float* head, float* zh,
                                              f3& d, float& dn, long long level_stride)
 {
-    // feats: [N,32] row-major (level_stride = 0) or level-major [16][N] float2 (level_stride = N)
     const float* mask = c.mask;
-    float x[32], sh[16];
+    const int cg = c.cg;
+    float x[8], sh[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sh[j] = 0.0f;
     if (live) {
         if (level_stride == 0) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(feats + (size_t)n * 32 + q * 4));
-                x[4 * q + 0] = a.x * mask[4 * q + 0]; x[4 * q + 1] = a.y * mask[4 * q + 1];
-                x[4 * q + 2] = a.z * mask[4 * q + 2]; x[4 * q + 3] = a.w * mask[4 * q + 3];
-            }
+            const float4 a = __ldg(reinterpret_cast<const float4*>(feats + (size_t)n * 32 + 8 * cg));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(feats + (size_t)n * 32 + 8 * cg + 4));
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
         } else {
             const float2* f2 = reinterpret_cast<const float2*>(feats) + n;
 #pragma unroll
-            for (int l = 0; l < 16; ++l) {
-                const float2 a = __ldg(f2 + (size_t)l * level_stride);
-                x[2 * l] = a.x * mask[2 * l]; x[2 * l + 1] = a.y * mask[2 * l + 1];
+            for (int l = 0; l < 4; ++l) {
+                const float2 a = __ldg(f2 + (size_t)(4 * cg + l) * level_stride);
+                x[2 * l] = a.x; x[2 * l + 1] = a.y;
             }
         }
-        d = ld3(rays_d + 3 * (size_t)(n / S));
-        dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
-        const float inv = 1.0f / (dn + 1e-8f);
-        sh16(d.x * inv, d.y * inv, d.z * inv, sh);
-    } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) sh[j] = 0.0f;
+        for (int j = 0; j < 8; ++j) x[j] *= mask[8 * cg + j];
+        if (cg >= 2) {
+            d = ld3(rays_d + 3 * (size_t)(n / S));
+            dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+            const float inv = 1.0f / (dn + 1e-8f);
+            sh16(d.x * inv, d.y * inv, d.z * inv, sh);
+        }
     }
-    store_input_row<SPLIT>(T, c.tid, x, sh);
+    store_input_row<SPLIT>(T, c.row, cg, x, sh + 8 * (cg & 1));
     forward_layers<SPLIT, TRAIN>(c, T, head, zh);
 }
 

@@ -27,13 +27,15 @@ __device__ __forceinline__ uint32_t hash3(int x, int y, int z, uint32_t mask)
     return (((uint32_t)x) ^ ((uint32_t)y * 2654435761u) ^ ((uint32_t)z * 805459861u)) & mask;
 }
 
-// 16-level trilinear encode from an fp16 table (rendering_kernel.cu:79-114): u in [0,1]^3,
-// v = u * (res - 1), corner order c = 4 dx + 2 dy + dz, accumulation in that order.
-__device__ __forceinline__ void encode16(f3 u, const int* __restrict__ res, const __half2* __restrict__ table, uint32_t T, float* x)
+// Trilinear encode of 4 consecutive levels [l0, l0 + 4) from an fp16 table (rendering_kernel.cu:79-114): u in
+// [0,1]^3, v = u * (res - 1), corner order c = 4 dx + 2 dy + dz, accumulation in that order.  x[2 j], x[2 j + 1] =
+// the two features of level l0 + j.  (The four column groups of a row cover the 16 levels.)
+__device__ __forceinline__ void encode4(f3 u, const int* __restrict__ res, const __half2* __restrict__ table, uint32_t T, int l0, float* x)
 {
     const uint32_t mask = T - 1u;
-#pragma unroll 2
-    for (int l = 0; l < 16; ++l) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int l = l0 + j;
         const float vx = u.x * (float)(res[3 * l] - 1), vy = u.y * (float)(res[3 * l + 1] - 1), vz = u.z * (float)(res[3 * l + 2] - 1);
         const int ix = (int)vx, iy = (int)vy, iz = (int)vz;
         const float ox = vx - (float)ix, oy = vy - (float)iy, oz = vz - (float)iz;
@@ -46,7 +48,7 @@ __device__ __forceinline__ void encode16(f3 u, const int* __restrict__ res, cons
         float a = 0.0f, b = 0.0f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) { a += w[k] * f[k].x; b += w[k] * f[k].y; }
-        x[2 * l] = a; x[2 * l + 1] = b;
+        x[2 * j] = a; x[2 * j + 1] = b;
     }
 }
 
@@ -67,7 +69,7 @@ struct InferArgs {
 };
 
 template <bool SPLIT, int MODE>
-__global__ void __launch_bounds__(kRows, 1)
+__global__ void __launch_bounds__(kThreadsDec, 1)
 infer_kernel(InferArgs a, int num_tiles)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -89,15 +91,14 @@ infer_kernel(InferArgs a, int num_tiles)
     __syncthreads();
     umma::tc_fence_after();
     Ctx<SPLIT> c;
-    c.smem = smem; c.bar = &bar; c.tmem = tmem_slot; c.lane_addr = (uint32_t)(32 * (warp & 3)) << 16; c.phase = 0; c.tid = tid;
-    c.bias = reinterpret_cast<const float*>(smem + off_bias<SPLIT>());
-    c.mask = reinterpret_cast<const float*>(smem + off_mask<SPLIT>());
+    c.init(smem, &bar, tmem_slot);
+    const int row = c.row, cg = c.cg;
     const Tiles Tl{T0, T1, nullptr, T2, T1, nullptr, T2, nullptr, LOa, LOb};
     int staged = -1;
     const long long total = (long long)a.B * a.S;
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const long long n = (long long)tile * kRows + tid;
+        const long long n = (long long)tile * kRows + row;
         const bool live = n < total;
         const int ray = live ? (int)(n / a.S) : 0, k = live ? (int)(n % a.S) : 0;
         short ids[kMaxPts] = {-1, -1, -1, -1};
@@ -123,7 +124,7 @@ infer_kernel(InferArgs a, int num_tiles)
         const f3 p = o + zv * d;
         const f3 dn = d * rsqrtf(dot3(d, d));                 // normalize(): decoder.h:201, no epsilon
         float sh[16];
-        sh16(dn.x, dn.y, dn.z, sh);
+        if (cg >= 2) sh16(dn.x, dn.y, dn.z, sh);
         const float dlen = sqrtf(dot3(d, d));
         f3 acc_d = mk3(0, 0, 0), acc_s = mk3(0, 0, 0);
         float acc_a = 0.0f, wsum = 0.0f;
@@ -184,23 +185,25 @@ infer_kernel(InferArgs a, int num_tiles)
                 continue;
             }
             if (staged != b) {
-                stage_all_weights<SPLIT>(smem, flat_params(a.params + (size_t)b * 13994), nullptr, tid, kRows);
+                stage_all_weights<SPLIT>(smem, flat_params(a.params + (size_t)b * 13994), nullptr, tid, kThreadsDec);
                 staged = b;
             }
-            float x[32];
+            float x[8];                                        // this thread's feature chunk: levels 4 cg .. 4 cg + 3
             if (active) {
-                encode16(u, a.resolution + (size_t)b * 48, a.tables + (size_t)b * 16 * a.T, a.T, x);
+                encode4(u, a.resolution + (size_t)b * 48, a.tables + (size_t)b * 16 * a.T, a.T, 4 * cg, x);
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+                for (int j = 0; j < 8; ++j) x[j] = 0.0f;
             }
-            store_input_row<SPLIT>(Tl, tid, x, sh);
+            store_input_row<SPLIT>(Tl, row, cg, x, sh + 8 * (cg & 1));
             float head[10], zh[7];
             forward_layers<SPLIT, false>(c, Tl, head, zh);
             float zs[16];
-            umma::tmem_ld16(c.tmem + cDh + c.lane_addr, zs);
-            umma::tc_wait_ld();
-            if (active) {
+            if (cg == 0) {
+                umma::tmem_ld16(c.tmem + cDh + c.lane_addr, zs);
+                umma::tc_wait_ld();
+            }
+            if (active && cg == 0) {
                 // Decoder::inference activations (decoder.h:134-146): softplus without threshold, expf sigmoids
                 const float sigma = logf(1.0f + expf(zh[0]));
                 const f3 dif = mk3(1.0f / (1.0f + expf(-zh[1])), 1.0f / (1.0f + expf(-zh[2])), 1.0f / (1.0f + expf(-zh[3])));
@@ -214,7 +217,7 @@ infer_kernel(InferArgs a, int num_tiles)
             }
             if (member) wsum += w;
         }
-        if (live) {
+        if (live && cg == 0) {
             bool write = true;
             if (MODE == kBackSlot) {
                 write = ids[0] != -1;                          // rays without a tile in this slot keep the caller's rows
@@ -252,11 +255,11 @@ int launch(const InferArgs& a, void* stream, const char* name)
     if (g_infer_split) {
         int grid = snrf_sm_count();
         if (grid > num_tiles) grid = num_tiles;
-        infer_kernel<true, MODE><<<grid, kRows, fwd_smem<true>(), s>>>(a, num_tiles);
+        infer_kernel<true, MODE><<<grid, kThreadsDec, fwd_smem<true>(), s>>>(a, num_tiles);
     } else {
         int grid = snrf_sm_count() * 2;
         if (grid > num_tiles) grid = num_tiles;
-        infer_kernel<false, MODE><<<grid, kRows, fwd_smem<false>(), s>>>(a, num_tiles);
+        infer_kernel<false, MODE><<<grid, kThreadsDec, fwd_smem<false>(), s>>>(a, num_tiles);
     }
     SNRF_RETURN_LAUNCH(name);
 }
