@@ -196,6 +196,33 @@ def run_reference(args, cfg, name):
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+# ----------------------------------------------------------------------------- render leg
+def bench_render(step, cfg, dev, H=1080, W=1920, frames=5, warm=2):
+    """BASELINE.json configs[2]: full-frame 1920x1080 inference of the trained-from-random tile through the
+    multi-tile render operators (ray/tile intersection -> sample -> fused fp16 encode + tensor-core decoder ->
+    accumulate, foreground + background), Mrays/s.  Device-timed, no host synchronisation inside a frame."""
+    import torch
+    import render_frame as rf
+    ts = rf.TileSet.from_hashgrid(step.featureGrid, step.decoder, dev).finalize()
+    K = step.poses.ks[0].clone()
+    K[0, 0] *= W / cfg["W"]; K[1, 1] *= H / cfg["H"]; K[0, 2] = W / 2.0; K[1, 2] = H / 2.0
+    with torch.no_grad():
+        c2w = step.poses.c2w()[0].detach()
+    for _ in range(warm):
+        rf.render_frame(ts, H, W, K, c2w)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(frames):
+        out = rf.render_frame(ts, H, W, K, c2w)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / frames
+    return {"metric": "render Mrays/s", "value": H * W / ms / 1e3, "unit": "Mrays/s", "ms_per_frame": ms,
+            "config": {"workload": "render 1920x1080, 1 tile, 128 + 128 samples per ray, fp16 table 16 x 2^%d x 2" % cfg["log2T"],
+                       "frames": frames, "finite": bool(torch.isfinite(out[0]).all())}}
+
+
 # ----------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
@@ -205,6 +232,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="default.yaml-single-tile", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-render", action="store_true")
     args = ap.parse_args()
     cfg, name = WORKLOADS[args.workload], args.workload
     if args.impl == "reference":
@@ -305,6 +333,8 @@ def main():
                      "avg_launch_ms": avg_ms, "launches_timed": len(k_ms), "alg_bytes_per_launch": alg_bytes,
                      "share_of_step": (sum(k_ms) / K) / (ms_dev / K) if k_ms else None},
     }
+    if world == 1 and not args.no_render:
+        line["render"] = bench_render(step, cfg, dev)
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         from oracle import native as on

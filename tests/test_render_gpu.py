@@ -225,3 +225,71 @@ def test_pts_inference_against_cpu_restatement():
     assert float((outs[2].cpu()[..., 0][m] - alpha.reshape(B, S)[m]).abs().max()) < 1e-4
     assert float((outs[0].cpu()[m] - want_d[m]).abs().max()) < 1e-4
     assert float((outs[1].cpu()[m] - want_s[m]).abs().max()) < 1e-4
+
+
+def _render_with(mod, sc, o, d, S, Sb):
+    """rendering.RenderingHashGrid.render_rays_base (rendering.py:286-544) sequenced over module `mod`."""
+    B, nb = o.shape[0], sc["nb"]
+    isect = torch.full((B, nb, 2), MISS, device=DEV)
+    mod.ray_block_intersection(o, d, sc["corners"], sc["sizes"], isect)
+    order = torch.argsort(isect[..., 0], dim=-1).int().contiguous()
+    fake = sc["occ"].clone()
+    for i in range(nb):
+        mod.process_occupied_grid(i, sc["n_cells"], sc["corners"], sc["sizes"], sc["occ"], sc["starts"], sc["l2d"], fake)
+    T_, dif, spe, dep = torch.ones(B, 1, device=DEV), torch.zeros(B, 3, device=DEV), torch.zeros(B, 3, device=DEV), torch.zeros(B, 1, device=DEV)
+    ti, zs = torch.zeros(B, 1, dtype=torch.int32, device=DEV), torch.zeros(B, 1, device=DEV)
+    max_tracing = int(torch.mean((isect != MISS).float(), dim=-1).sum(dim=-1).max().cpu())
+    for _ in range(max_tracing):
+        running = (ti < max_tracing) & (T_ > 1e-5)
+        if running.sum() == 0:
+            break
+        z, di = torch.full((B, S), -1.0, device=DEV), torch.full((B, S), -1.0, device=DEV)
+        mod.sample_points(o, d, sc["corners"], sc["sizes"], fake, sc["starts"], sc["l2d"], order, isect, ti, zs, z, di)
+        bi = torch.full((B, S, 4), -1, dtype=torch.int16, device=DEV)
+        mod.prepare_points(z, running, isect, bi)
+        pd, ps, pa = torch.zeros(B, S, 3, device=DEV), torch.zeros(B, S, 3, device=DEV), torch.zeros(B, S, 1, device=DEV)
+        mod.pts_inference(o, d, z, di, bi, sc["tables"], sc["params"], sc["res"], sc["occ"], sc["starts"], sc["l2d"], sc["corners"], sc["sizes"], pd, ps, pa)
+        mod.accumulate_color(pd, ps, pa, T_, z, dif, spe, dep)
+    bgb, bgw = torch.full((B, 4), -1, dtype=torch.int16, device=DEV), torch.zeros(B, 4, device=DEV)
+    mod.update_outgoing_bidx(o, d, sc["corners"], sc["sizes"], order, isect, bgb, bgw, 0.12, False)
+    bgw = bgw / torch.sum(bgw, dim=-1, keepdim=True)
+    bd, bs = torch.zeros(B, 3, device=DEV), torch.zeros(B, 3, device=DEV)
+    for i in range(int((bgw > 0).sum(dim=-1).max().cpu())):
+        bz = torch.full((B, Sb), -1.0, device=DEV)
+        mod.inverse_z_sampling(isect, bgb[..., i].contiguous(), bz, 1e6)
+        pd, ps, pa = torch.zeros(B, Sb, 3, device=DEV), torch.zeros(B, Sb, 3, device=DEV), torch.zeros(B, Sb, 1, device=DEV)
+        mod.bg_pts_inference_v2(o, d, bz, bgb, i, sc["corners"], sc["sizes"], sc["res"], sc["tables"], sc["params"], pd, ps, pa)
+        t, td, tsp, tz = torch.ones(B, 1, device=DEV), torch.zeros(B, 3, device=DEV), torch.zeros(B, 3, device=DEV), torch.zeros(B, 1, device=DEV)
+        mod.accumulate_color(pd, ps, pa, t, bz, td, tsp, tz)
+        bd += td * bgw[:, i:i + 1]
+        bs += tsp * bgw[:, i:i + 1]
+    return dif + T_ * bd, spe + T_ * bs, T_
+
+
+@pytest.mark.parametrize("nb", [1, 3])
+def test_render_rays_driver_matches_reference_sequence(nb):
+    """render_frame.render_rays (our sync-free mirror of render_rays_base) against the reference's own
+    operator sequence run on the rebuilt reference extension; composited colours within 1e-4."""
+    ours, ref = _ops()
+    if ref is None:
+        pytest.skip("oracle/_ref/HASHGRID.so not built")
+    import render_frame as rf
+    raw = make_scene(nb)
+    sc = dev(raw)
+    B, S, Sb = 3000, 32, 24
+    o, d = (t.to(DEV) for t in make_rays(B, 77 + nb))
+    want_d, want_s, want_T = _render_with(ref, sc, o, d, S, Sb)
+    ts = rf.TileSet(DEV)
+    for i in range(nb):       # TileSet takes the exported (doubled) boxes: corner - size/2, 2 size
+        n = raw["n_cells"]
+        ts.add_tile(raw["tables"][i], raw["params"][i], raw["res"][i], raw["occ"][i * n:(i + 1) * n], raw["corners"][i] - raw["sizes"][i] / 2,
+                    raw["sizes"][i] * 2, raw["l2d"][i])
+    ts.finalize()
+    assert torch.allclose(ts.block_corner, sc["corners"]) and torch.allclose(ts.block_size, sc["sizes"])
+    got_d, got_s, _, got_T = rf.render_rays(ts, o, d, num_sample=S, num_bg_sample=Sb)
+    ok = torch.isfinite(want_d).all(-1) & torch.isfinite(want_s).all(-1)    # the reference yields NaN for rays that hit no tile
+    assert int(ok.sum()) > B // 2
+    assert float((got_d[ok] - want_d[ok]).abs().max()) < 1e-4
+    assert float((got_s[ok] - want_s[ok]).abs().max()) < 1e-4
+    assert float((got_T - want_T).abs().max()) < 1e-4
+    assert bool(torch.isfinite(got_d[ok]).all())
