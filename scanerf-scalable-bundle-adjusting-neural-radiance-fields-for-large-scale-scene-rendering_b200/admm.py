@@ -81,6 +81,7 @@ class ConsensusManager:
         self.delta_se3 = torch.zeros(n, 6, dtype=torch.float32, device=self.device)
         self.overlap_flags = torch.zeros(n, dtype=torch.bool, device=self.device)
         self.rho = torch.ones(6, dtype=torch.float32, device=self.device) * float(rho)
+        self.has_overlap = False          # host-side copy of overlap_flags.any(), updated without a device sync
 
     def export_check_point(self):
         f = lambda t: t.detach().cpu().numpy()
@@ -91,19 +92,23 @@ class ConsensusManager:
         f = lambda a: torch.from_numpy(a).to(self.device)
         self.shared_se3, self.delta_se3 = f(ckp["shared_se3"]), f(ckp["delta_se3"])
         self.overlap_flags, self.rho = f(ckp["overlap_flags"]), f(ckp["rho"])
+        self.has_overlap = bool(ckp["overlap_flags"].any())
 
     @torch.no_grad()
     def update(self, shared_se3, overlap_idxs):
         """consensus.py:40-50: z <- shared, u <- u + 1.5 (x - z) (over-relaxed dual step), mark overlap cameras."""
         self.shared_se3 = shared_se3.to(self.device)
         self.delta_se3 = self.delta_se3 + (1 + 0.5) * (self.se3_refine.detach() - self.shared_se3)
-        if overlap_idxs.shape[0] > 0:
+        if overlap_idxs.shape[0] > 0:        # (the shape is known on the host: nonzero() inside exchange() already synchronised)
             self.overlap_flags[overlap_idxs.to(self.device)] = True
+            self.has_overlap = True
 
     def camera_loss(self):
         """consensus.py:70-76: mean over overlap cameras and the 6 generators of rho (x - z + u)^2."""
         c = (self.se3_refine - self.shared_se3 + self.delta_se3) ** 2
-        return torch.mean(self.rho[None, :] * c[self.overlap_flags])
+        # masked mean instead of boolean indexing: same value, no device->host synchronisation per step
+        f = self.overlap_flags[:, None].to(c.dtype)
+        return torch.sum(self.rho[None, :] * c * f) / (6.0 * f.sum().clamp_min(1.0))
 
     def __call__(self):
-        return self.camera_loss() if bool(self.overlap_flags.sum() > 0) else None
+        return self.camera_loss() if self.has_overlap else None

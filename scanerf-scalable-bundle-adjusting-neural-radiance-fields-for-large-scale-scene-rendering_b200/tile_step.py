@@ -160,6 +160,23 @@ class TileStep:
         self.optimizer = torch.optim.Adam([
             {"params": self.decoder.parameters(), "lr": lr_decoder, "weight_decay": 1e-6},
             {"params": self.poses.se3_refine, "lr": lr_cam}])
+        self.consensus = None           # ADMM state, see enable_consensus()
+        self.camera_ids = None
+
+    # ADMM pose consensus across tiles (admm_trainer.py:218-262, tile.py:477-508, consensus.py)
+    def enable_consensus(self, camera_ids, num_camera_global, rho=100.0, group=None):
+        """camera_ids: global ids [n_cam] of this tile's cameras.  Afterwards `synchronize()` exchanges poses with
+        the other ranks (one NCCL all-reduce) and the loss carries the ADMM penalty (criterions.py:107-108)."""
+        from admm import ConsensusManager, PoseConsensus
+        self.camera_ids = torch.as_tensor(camera_ids, dtype=torch.long, device=self.device)
+        self.consensus = ConsensusManager(self.poses.se3_refine, rho, self.device)
+        self.exchange = PoseConsensus(num_camera_global, self.device, group)
+        self.confidence = torch.ones(self.camera_ids.shape[0], dtype=torch.float32, device=self.device)
+
+    def synchronize(self):
+        """TILE.commit + master consensus + TILE.synchronize as one collective (every SYN_ITERS steps)."""
+        out = self.exchange.exchange([(self.poses.se3_refine, self.camera_ids, self.confidence)])[0]
+        self.consensus.update(out["shared_poses"], out["overlap_idxs"])
 
     # tile.py:639-692
     def render_rays(self, rays_o, rays_d, occlusion_mask=None, mode=TRAIN):
@@ -202,7 +219,10 @@ class TileStep:
         if not ok:
             return None, None
         mse = torch.mean((out["pred_color"] - gt_color) ** 2)            # criterions.py MSE on input/target
-        return mse + 0.01 * out["l2_reg_specular"], out                    # tile.py:999
+        loss = mse + 0.01 * out["l2_reg_specular"]                         # tile.py:999
+        if self.consensus is not None and self.consensus.has_overlap:
+            loss = loss + self.consensus.camera_loss()                     # "Admm Loss", weight 1 (criterions.py:107-108)
+        return loss, out
 
     def step_device(self, locs, gt_color):
         """Inputs already on the device.  Returns the loss as a device scalar (no host sync)."""
