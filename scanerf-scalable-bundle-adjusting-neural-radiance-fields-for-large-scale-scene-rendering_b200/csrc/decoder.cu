@@ -146,17 +146,20 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     const uint32_t aA0 = umma::smem_u32(T.A0), aa1 = umma::smem_u32(T.a1), ag1 = umma::smem_u32(T.g1), aH = umma::smem_u32(T.H),
                    aa3 = umma::smem_u32(T.a3), ag3 = umma::smem_u32(T.g3), aa4 = umma::smem_u32(T.a4), ag4 = umma::smem_u32(T.g4),
                    adz = umma::smem_u32(Tdz), adzlo = umma::smem_u32(Tdzlo), adhlo = umma::smem_u32(Tdhlo);
-    // bias gradients of the 64-wide layers ride on the weight-gradient GEMMs: column 32 of A0 holds
-    // SH_0 = 0.28209479 (a constant, exactly representable products), so dz^T A0[:, 32:40] column 0
-    // is c0 * sum_n dz_n; the flush divides by c0.  Rows past N have SH = 0 and dz = 0.
-    const uint32_t aones = aA0 + 64;
+    // Bias gradients of the 64-wide layers.  Layers 1 and 3 read A0, whose column 32 holds SH_0 = bf16(0.28209479)
+    // = 0.28125 in every live row: column 32 of dW1 (N widened to 48) and column 0 of the SH part of dW3 are
+    // c0 * sum_n dz_n, the flush divides by c0.  Layers 2 and 4 (inputs a1 / a3 have no constant column) are summed
+    // per thread in fp32 registers over all the tiles of this CTA and reduced once at the end.
+    float acc_b2[16], acc_b4[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { acc_b2[j] = 0.0f; acc_b4[j] = 0.0f; }
     const uint32_t aW1 = umma::smem_u32(smem + oW1), aW2 = umma::smem_u32(smem + oW2), aW3 = umma::smem_u32(smem + oW3),
                    aW4 = umma::smem_u32(smem + oW4), aWh = umma::smem_u32(smem + oWh), aW5 = umma::smem_u32(smem + oW5);
     // input-gradient GEMMs: A K-major (dz rows), B MN-major (weight tile: rows = K = out, cols = N = in)
     constexpr uint32_t idg64 = umma::idesc_bf16(128, 64, 0, 1), idg32 = umma::idesc_bf16(128, 32, 0, 1);
     // weight-gradient GEMMs: both operands MN-major, M = 64
-    constexpr uint32_t idw64 = umma::idesc_bf16(64, 64, 1, 1), idw32 = umma::idesc_bf16(64, 32, 1, 1),
-                       idw16 = umma::idesc_bf16(64, 16, 1, 1), idw8 = umma::idesc_bf16(64, 8, 1, 1);
+    constexpr uint32_t idw64 = umma::idesc_bf16(64, 64, 1, 1), idw48 = umma::idesc_bf16(64, 48, 1, 1),
+                       idw32 = umma::idesc_bf16(64, 32, 1, 1), idw16 = umma::idesc_bf16(64, 16, 1, 1);
     const uint32_t aW2l = umma::smem_u32(smem + oW2l), aW3l = umma::smem_u32(smem + oW3l), aW4l = umma::smem_u32(smem + oW4l),
                    aW5l = umma::smem_u32(smem + oW5l);
     // dA = dz W over `nk` k-steps; in SPLIT mode dz = dz_hi + dz_lo and W = W_hi + W_lo (the lo tile,
@@ -192,7 +195,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     };
     float v[16];
     // dz = dA * g on this thread's 16 columns: hi part in place over the g tile, lo part (SPLIT) into Tlo
-    auto mul_inplace = [&](int col, unsigned char* Tg, unsigned char* Tlo) {
+    auto mul_inplace = [&](int col, unsigned char* Tg, unsigned char* Tlo, float* bias_acc) {
         umma::tmem_ld16(tmem + col + lane_addr + 16 * cg, v);
         umma::tc_wait_ld();
 #pragma unroll
@@ -206,13 +209,19 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
                 o[2 * e] = v[8 * q + 2 * e] * __low2float(h2);
                 o[2 * e + 1] = v[8 * q + 2 * e + 1] * __high2float(h2);
             }
+            if (bias_acc != nullptr) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bias_acc[8 * q + e] += o[e];
+            }
             store8_hl<SPLIT>(Tg, 2 * cg + q, Tlo, 2 * cg + q, row, o);
         }
     };
     // 32 accumulator columns (8 per column group) -> chunk (chunk0 + cg) of a hi / lo tile pair
-    auto store_quarter = [&](int col, unsigned char* Thi, unsigned char* Tlo, int chunk0) {
+    auto store_quarter = [&](int col, unsigned char* Thi, unsigned char* Tlo, int chunk0, float* bias_acc) {
         umma::tmem_ld8(tmem + col + lane_addr + 8 * cg, v);
         umma::tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bias_acc[e] += v[e];
         store8_hl<SPLIT>(Thi, chunk0 + cg, Tlo, chunk0 + cg, row, v);
     };
 
@@ -275,29 +284,27 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
             umma::mma_commit(&bar);
         }
         c.wait_mma();
-        mul_inplace(cDa, T.g4, Tdzlo);                           // dz5
-        store_quarter(cDb, Tdz, Tdhlo, 0);                       // dH[0:32] -> dz2 tile columns 0..31 (over the consumed dz_heads/spec)
+        mul_inplace(cDa, T.g4, Tdzlo, acc_b4);                   // dz5 (+ its column sums = d/d b4)
+        store_quarter(cDb, Tdz, Tdhlo, 0, acc_b2);               // dH[0:32] -> dz2 tile columns 0..31 (over the consumed dz_heads/spec)
         c.sync_operands();
-        // ---- B2: dA3 = dz5 W4 ; dW4 += dz5^T a3 ; db4
+        // ---- B2: dA3 = dz5 W4 ; dW4 += dz5^T a3
         if (tid == 0) {
             dgrad(cDb, ag4, 0, adzlo, 0, aW4, aW4l, 4, idg64);
             wgrad(cGW4, ag4, adzlo, aa3, idw64, first);
-            wgrad(cGb4, ag4, adzlo, aones, idw8, first);
             umma::mma_commit(&bar);
         }
         c.wait_mma();
-        mul_inplace(cDb, T.g3, Tdzlo);                           // dz4
+        mul_inplace(cDb, T.g3, Tdzlo, nullptr);                  // dz4
         c.sync_operands();
         // ---- B3: d[x2] = dz4 W3 ; dW3 += dz4^T [H[32:64] | SH] ; db3
         if (tid == 0) {
             dgrad(cDa, ag3, 0, adzlo, 0, aW3, aW3l, 4, idg64);
             wgrad(cGW3a, ag3, adzlo, aH + 64, idw32, first);
             wgrad(cGW3b, ag3, adzlo, aA0 + 64, idw16, first);
-            wgrad(cGb3, ag3, adzlo, aones, idw8, first);
             umma::mma_commit(&bar);
         }
         c.wait_mma();
-        store_quarter(cDa, Tdz, Tdhlo, 4);                       // dH[32:64]
+        store_quarter(cDa, Tdz, Tdhlo, 4, acc_b2 + 8);           // dH[32:64]
         if (grad_rays_d != nullptr && cg == 3) {                 // d/d(ray direction) through the SH encoding (one thread per row)
             float dsh[16];
             umma::tmem_ld16(tmem + cDa + lane_addr + 32, dsh);
@@ -354,17 +361,15 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         if (tid == 0) {
             dgrad(cDb, adz, 0, adhlo, 0, aW2, aW2l, 4, idg64);
             wgrad(cGW2, adz, adhlo, aa1, idw64, first);
-            wgrad(cGb2, adz, adhlo, aones, idw8, first);
             umma::mma_commit(&bar);
         }
         c.wait_mma();
-        mul_inplace(cDb, T.g1, Tdzlo);                           // dz1
+        mul_inplace(cDb, T.g1, Tdzlo, nullptr);                  // dz1
         c.sync_operands();
         // ---- B5: dx = dz1 W1 (32 columns) ; dW1 += dz1^T x ; db1
         if (tid == 0) {
             dgrad(cDa, ag1, 0, adzlo, 0, aW1, aW1 + 64, 4, idg32);
-            wgrad(cGW1, ag1, adzlo, aA0, idw32, first);
-            wgrad(cGb1, ag1, adzlo, aones, idw8, first);
+            wgrad(cGW1, ag1, adzlo, aA0, idw48, first);             // N = 48: x (32) | SH (16); column 32 -> d/d b1
             umma::mma_commit(&bar);
         }
         c.wait_mma();
@@ -411,12 +416,13 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         flush(cGW3b, 16, gp.W3, 48, 32);
         flush(cGW4, 64, gp.W4, 64, 0);
         float b8[16];
-        auto flush_bias = [&](int col, float* dst) {            // column 0 of a [64 x 8] accumulator
-            umma::tmem_ld16(tmem + col + lane_addr, b8);
-            umma::tc_wait_ld();
-            if (own) atomicAdd(dst + m, b8[0] * kInvSH0);
-        };
-        flush_bias(cGb1, gp.b1); flush_bias(cGb2, gp.b2); flush_bias(cGb3, gp.b3); flush_bias(cGb4, gp.b4);
+        // d/d b1 = column 32 of the [64 x 48] dW1 accumulator, d/d b3 = column 0 of the SH part of dW3, both / SH_0
+        umma::tmem_ld16(tmem + cGW1 + 32 + lane_addr, b8);
+        umma::tc_wait_ld();
+        if (own) atomicAdd(gp.b1 + m, b8[0] * kInvSH0);
+        umma::tmem_ld16(tmem + cGW3b + lane_addr, b8);
+        umma::tc_wait_ld();
+        if (own) atomicAdd(gp.b3 + m, b8[0] * kInvSH0);
         // transposed narrow layers: accumulator row = input feature k, column = output o
         umma::tmem_ld16(tmem + cGWhT + lane_addr, b8);
         umma::tc_wait_ld();
@@ -428,6 +434,20 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         umma::tc_wait_ld();
         if (own)
             for (int o = 0; o < 3; ++o) atomicAdd(gp.W5 + o * 64 + m, b8[o]);
+    }
+    // d/d b2, d/d b4: per-thread column sums -> sum over the 32 rows of the warp -> one atomic per warp and column
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        float t2 = acc_b2[j], t4 = acc_b4[j];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            t2 += __shfl_xor_sync(0xffffffffu, t2, off);
+            t4 += __shfl_xor_sync(0xffffffffu, t4, off);
+        }
+        if (lane == 0 && !first) {
+            atomicAdd(gp.b2 + (j < 8 ? 8 * cg + j : 32 + 8 * cg + (j - 8)), t2);      // store_quarter column mapping
+            atomicAdd(gp.b4 + 16 * cg + j, t4);
+        }
     }
     __syncthreads();
     if (tid == 0) {

@@ -56,8 +56,9 @@ template <bool SPLIT> constexpr int bwd_smem() { return off_tiles<SPLIT>() + 10 
 
 // TMEM columns: working accumulators, then (backward only) the persistent gradient accumulators
 constexpr int cDa = 0, cDb = 64, cDh = 128;
-constexpr int cGW1 = 144, cGW2 = 176, cGW3a = 240, cGW3b = 272, cGW4 = 288, cGWhT = 352, cGW5T = 368,
-              cGb1 = 384, cGb2 = 392, cGb3 = 400, cGb4 = 408;   // last one ends at 416 (+8 slack read)
+// (cGW1 is 48 wide: x (32) | SH (16) -- its column 32 = SH_0 carries the bias gradient of layer 1, as column 0 of
+// cGW3b does for layer 3)
+constexpr int cGW1 = 144, cGW2 = 192, cGW3a = 256, cGW3b = 288, cGW4 = 304, cGWhT = 368, cGW5T = 384;   // ends at 400
 
 __device__ __forceinline__ float gauss_act(float v) { return exp2f(v * v * kGaussLog2); }
 __device__ __forceinline__ float sigmoidf(float v) { return 1.0f / (1.0f + __expf(-v)); }
@@ -82,16 +83,23 @@ __device__ __forceinline__ void sh16(float x, float y, float z, float* o)
 
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-// store 8 values as the hi tile chunk and (SPLIT) their bf16 residuals as the lo tile chunk
+// store 8 values as the hi tile chunk and (SPLIT) their bf16 residuals as the lo tile chunk.
+// The packed hi words serve both the store and the residual (hi as float = the 16 bits shifted up): 4 + 4 packing
+// conversions per 8 values and no scalar float->bf16 round trips -- those run on the 16-lane XU pipe, which ncu
+// showed saturated (profiles/r1c_top_kernels_full.md) when the residuals were formed with one conversion each.
 template <bool SPLIT>
 __device__ __forceinline__ void store8_hl(unsigned char* Thi, int chi, unsigned char* Tlo, int clo, int row, const float* v)
 {
-    umma::tile_store8(Thi, row, chi, v);
-    if (SPLIT) {
-        float r[8];
+    uint32_t h[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = v[j] - bf16_round(v[j]);
-        umma::tile_store8(Tlo, row, clo, r);
+    for (int i = 0; i < 4; ++i) h[i] = umma::pack_bf16(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(Thi + umma::tile_chunk_off(row, chi)) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (SPLIT) {
+        uint32_t l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            l[i] = umma::pack_bf16(v[2 * i] - __uint_as_float(h[i] << 16), v[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u));
+        *reinterpret_cast<uint4*>(Tlo + umma::tile_chunk_off(row, clo)) = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
