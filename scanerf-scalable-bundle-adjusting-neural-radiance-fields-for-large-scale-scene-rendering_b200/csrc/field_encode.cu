@@ -200,9 +200,24 @@ field_bwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
             }
         }
         if (!done && live) {
+            // The hash is linear in x (h = x ^ ...): the two corners of an x-edge with even x differ in bit 0 only, i.e.
+            // they are the two halves of one aligned 16-byte slot -> one red.v4 instead of two red.v2 (the L2 reduction
+            // units, not HBM, bound this kernel: profiles/r1c_top_kernels_full.md; measured 1.98 -> 1.85 ms).
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if ((idx[k] >> range_shift) == pass) atomicAdd(gl + idx[k], make_float2(w[k] * g.x, w[k] * g.y));
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t i0 = idx[j], i1 = idx[j + 4];
+                const float2 v0 = make_float2(w[j] * g.x, w[j] * g.y), v1 = make_float2(w[j + 4] * g.x, w[j + 4] * g.y);
+                if ((i0 ^ i1) == 1u) {
+                    if ((i0 >> range_shift) == pass) {
+                        const bool swap = (i0 & 1u) != 0u;
+                        atomicAdd(reinterpret_cast<float4*>(gl + (i0 & ~1u)),
+                                  swap ? make_float4(v1.x, v1.y, v0.x, v0.y) : make_float4(v0.x, v0.y, v1.x, v1.y));
+                    }
+                } else {
+                    if ((i0 >> range_shift) == pass) atomicAdd(gl + i0, v0);
+                    if ((i1 >> range_shift) == pass) atomicAdd(gl + i1, v1);
+                }
+            }
         }
 
         // ---- gradient w.r.t. the sample position, from the stored Jacobian
@@ -256,6 +271,7 @@ inline int grid_x(int N)
 }
 
 int g_pass_bits_override = -1;
+int g_aggregate_override = -1;
 inline int pick_lpb(int L, int T)
 {
     const long long level_bytes = (long long)T * 8;
@@ -279,6 +295,7 @@ inline int pick_pass_bits(int T)
 
 // ------------------------------- C ABI --------------------------------------
 SNRF_API void snrf_field_set_passes_log2(int bits) { g_pass_bits_override = bits; }
+SNRF_API void snrf_field_set_aggregate_levels(int n) { g_aggregate_override = n; }
 
 // mode 0: `points` [N,3] are already contracted (rays_o / rays_d / z_vals unused);
 // mode 1 / 2: sample n = rays_o[n / S] + z_vals[n] * rays_d[n / S], contracted with the fore / background map of the
@@ -327,7 +344,7 @@ SNRF_API int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, con
     const dim3 grid(grid_x(N), L << pass_bits);
     const float2 *g = (const float2*)grad_lm, *j = (const float2*)jac_lm;
     float2* gt = (float2*)grad_table;
-    const int agg = L / 2;
+    const int agg = g_aggregate_override >= 0 ? g_aggregate_override : L / 2;
 #define SNRF_BWD(MODE) field_bwd_kernel<MODE><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, res, g, j, grad_rays_o, grad_rays_d, grad_points, gt, ray_valid, N, S, L, (uint32_t)T, pass_bits, range_shift, agg)
     if (mode == 0) SNRF_BWD(kNone); else if (mode == 1) SNRF_BWD(kFore); else SNRF_BWD(kBack);
 #undef SNRF_BWD

@@ -18,9 +18,13 @@ def measure(name):
     ms, units = capi.timed_results()
     capi.time_calls(None)
     return sum(ms) / len(ms), [round(m, 3) for m in ms[:4]]
-for bits in (-1, 0, 1, 2, 3, 4):
+for bits in (-1,):
     capi.lib().snrf_field_set_passes_log2(capi.c_int(bits))
     print("pass_bits", bits, "bwd avg ms", *measure("snrf_field_encode_bwd"))
 capi.lib().snrf_field_set_passes_log2(capi.c_int(-1))
+for agg in (0, 2, 4, 6, 8, 10, 12):
+    capi.lib().snrf_field_set_aggregate_levels(capi.c_int(agg))
+    print("aggregate_levels", agg, "bwd avg ms", *measure("snrf_field_encode_bwd"))
+capi.lib().snrf_field_set_aggregate_levels(capi.c_int(-1))
 print("fwd avg ms", *measure("snrf_field_encode_fwd"))
 print("adam", *measure("snrf_adam_step"))
