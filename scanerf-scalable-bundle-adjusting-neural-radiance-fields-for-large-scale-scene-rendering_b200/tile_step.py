@@ -160,8 +160,15 @@ class TileStep:
         self.optimizer = torch.optim.Adam([
             {"params": self.decoder.parameters(), "lr": lr_decoder, "weight_decay": 1e-6},
             {"params": self.poses.se3_refine, "lr": lr_cam}])
+        self.two_streams = True         # foreground / background chains on two CUDA streams (see render_rays)
+        self._side = None
         self.consensus = None           # ADMM state, see enable_consensus()
         self.camera_ids = None
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     # ADMM pose consensus across tiles (admm_trainer.py:218-262, tile.py:477-508, consensus.py)
     def enable_consensus(self, camera_ids, num_camera_global, rho=100.0, group=None):
@@ -180,6 +187,19 @@ class TileStep:
 
     # tile.py:639-692
     def render_rays(self, rays_o, rays_d, occlusion_mask=None, mode=TRAIN):
+        # The foreground and the background chains (sample -> encode -> decoder -> composite) are independent until the
+        # colours are merged.  They are issued on two CUDA streams: the decoder kernels are latency-bound (one 16-warp CTA
+        # per SM, tensor pipe ~10 % busy) and the encode / scatter kernels are memory-bound, so the two chains fill each
+        # other's gaps -- in the backward too, which autograd runs on the streams of the forward ops.
+        side = self._side_stream() if self.two_streams else None
+        if side is not None:
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                bg, ret_bg = self.featureGrid.render_bg_rays(rays_o, rays_d, self.num_bg_sample, self.decoder, mode,
+                                                             occlusion_mask=occlusion_mask, global_step=self.global_step,
+                                                             bg_mode="IZ", infinity=True, fmesh=None,
+                                                             invalid_underground=self.invalid_underground)
         fg, ret_fg = self.featureGrid.render_fore_rays(rays_o, rays_d, self.num_sample, self.decoder, mode,
                                                        occlusion_mask=occlusion_mask, global_step=self.global_step)
         out = {"rays_o": rays_o, "rays_d": rays_d, "ret_fg": ret_fg}
@@ -187,10 +207,17 @@ class TileStep:
             out.update(fg)
         else:
             out["fore_valid"] = torch.zeros(rays_d[..., 0].shape, dtype=torch.bool, device=self.device)
-        bg, ret_bg = self.featureGrid.render_bg_rays(rays_o, rays_d, self.num_bg_sample, self.decoder, mode,
-                                                     occlusion_mask=occlusion_mask, global_step=self.global_step,
-                                                     bg_mode="IZ", infinity=True, fmesh=None,
-                                                     invalid_underground=self.invalid_underground)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+            if ret_bg:
+                for v in bg.values():             # produced on the side stream, consumed (and freed) on the main one
+                    if torch.is_tensor(v):
+                        v.record_stream(torch.cuda.current_stream())
+        else:
+            bg, ret_bg = self.featureGrid.render_bg_rays(rays_o, rays_d, self.num_bg_sample, self.decoder, mode,
+                                                         occlusion_mask=occlusion_mask, global_step=self.global_step,
+                                                         bg_mode="IZ", infinity=True, fmesh=None,
+                                                         invalid_underground=self.invalid_underground)
         if ret_fg is False and ret_bg is False:
             return None, False
         out["ret_bg"] = ret_bg
