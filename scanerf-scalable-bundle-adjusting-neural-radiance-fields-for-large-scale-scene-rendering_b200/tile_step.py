@@ -168,6 +168,9 @@ class TileStep:
     def _side_stream(self):
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device)
+            # parameter gradients are accumulated from both streams by design (autograd orders them with events)
+            if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         return self._side
 
     # ADMM pose consensus across tiles (admm_trainer.py:218-262, tile.py:477-508, consensus.py)
