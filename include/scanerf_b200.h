@@ -216,22 +216,24 @@ int snrf_process_occupied(int bidx, int total_grid, const float* corners, const 
                           unsigned char* tgt_grid_occupied, int nb, void* stream);                    /* process_occupied_grid */
 /* Fused fp16-table encode + decoder MLP (tensor cores) + alpha + overlap blending.
  * features_tables [nb,16,T,2] f16; params [nb,13994] f32 in the renderer's flat layout (rendering.py:101-113);
- * resolution [nb,16,3] i32.  pts_inference: block_idxs [B,S,4] i16, outputs [B,S,3],[B,S,3],[B,S,1]. */
+ * resolution [nb,16,3] i32; nb = number of tiles.  pts_inference: block_idxs [B,S,4] i16, outputs [B,S,3],[B,S,3],[B,S,1]. */
 int snrf_pts_inference(const float* rays_o, const float* rays_d, const float* z_vals, const float* dists,
                        const short* block_idxs, const void* features_tables, const float* params, const int* resolution,
                        const unsigned char* grid_occupied, const long long* grid_starts, const int* grid_log2dim,
                        const float* corners, const float* sizes, float* diffuse, float* specular, float* alpha, int B,
-                       int S, int T, void* stream);
+                       int S, int T, int nb, void* stream);
 int snrf_bg_pts_inference(const float* rays_o, const float* rays_d, const float* z_vals, const short* outgoing_bidxs,
                           const float* blend_weights, const float* corners, const float* sizes, const int* resolution,
                           const void* features_tables, const float* params, float* diffuse, float* specular, float* alpha,
-                          int B, int S, int T, void* stream);
+                          int B, int S, int T, int nb, void* stream);
 int snrf_bg_pts_inference_v2(const float* rays_o, const float* rays_d, const float* z_vals, const short* bg_idxs, int step,
                              const float* corners, const float* sizes, const int* resolution, const void* features_tables,
                              const float* params, float* diffuse, float* specular, float* alpha, int B, int S, int T,
-                             void* stream);
+                             int nb, void* stream);
 /* operand precision of the inference MLP: 1 (default) bf16x3 split, 0 plain bf16 */
 void snrf_infer_set_precision(int split);
+/* tuning hook: 128-sample tiles in flight per CTA for single-tile scenes (1 or 2, default 1: see csrc/infer.cu) */
+void snrf_infer_set_inflight(int tiles);
 
 /* ---- sparse Adam -------------------------------------------------------------- */
 /* cuda/include/adam.h (adam_step_cuda: half_state=0, adam_step_cuda_fp16: half_state=1; kernels

@@ -49,34 +49,34 @@ decoder_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char* T0 = smem + off_tiles<SPLIT>();
-    unsigned char* T1 = T0 + kTile;
-    unsigned char* T2 = T1 + kTile;
-    unsigned char* LOa = SPLIT ? T2 + kTile : T1;      // never written when !SPLIT
-    unsigned char* LOb = SPLIT ? LOa + kTile : T2;
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bars[2];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5;
 
     stage_all_weights<SPLIT>(smem, p, mask32, tid, kThreadsDec);
-    if (warp == 0) umma::tmem_alloc<256>(&tmem_slot);
-    if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_fence_init(); }
+    if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);
+    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::mbar_fence_init(); }
     umma::fence_async_smem();
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
-    Ctx<SPLIT> c;
-    c.init(smem, &bar, tmem_slot);
+    Ctx<SPLIT, 2> c;                                    // two tiles in flight: group = warp >> 3 owns one
+    c.init(smem, bars, tmem_slot);
+    unsigned char* T0 = smem + off_tiles<SPLIT>() + c.group * fwd_tiles<SPLIT>() * kTile;
+    unsigned char* T1 = T0 + kTile;
+    unsigned char* T2 = T1 + kTile;
+    unsigned char* LOa = SPLIT ? T2 + kTile : T1;      // never written when !SPLIT
+    unsigned char* LOb = SPLIT ? LOa + kTile : T2;
     const Tiles T{T0, T1, nullptr, T2, T1, nullptr, T2, nullptr, LOa, LOb};
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = 2 * blockIdx.x + c.group; tile < num_tiles; tile += 2 * gridDim.x) {
         const int n = tile * kRows + c.row;
         const bool live = n < N && (ray_valid == nullptr || ray_valid[n / S] != 0);
-        if (ray_valid != nullptr && !__syncthreads_or(live)) continue;     // every sample of the tile belongs to a masked-out ray
+        if (ray_valid != nullptr && !c.any(live)) continue;     // every sample of the tile belongs to a masked-out ray
         float head[10], zh[7];
         f3 d = mk3(0.f, 0.f, 1.f);
         float dn = 1.0f;
-        forward_tile<SPLIT, false>(c, T, feats, rays_d, n, live, S, head, zh, d, dn, level_stride);
+        forward_tile<SPLIT, false, 2>(c, T, feats, rays_d, n, live, S, head, zh, d, dn, level_stride);
         if (c.cg == 0) {
             float z[16];
             umma::tmem_ld16(c.tmem + cDh + c.lane_addr, z);
@@ -94,7 +94,7 @@ decoder_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == 0) umma::tmem_free<256>(c.tmem);
+    if (warp == 0) umma::tmem_free<512>(tmem_slot);
 }
 
 // ------------------------------- backward -----------------------------------
@@ -137,7 +137,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
-    Ctx<SPLIT> c;
+    Ctx<SPLIT, 4> c;                                    // one tile per CTA, 4 column groups of 16
     c.init(smem, &bar, tmem_slot);
     const int row = c.row, cg = c.cg;
     const uint32_t tmem = c.tmem, lane_addr = c.lane_addr;
@@ -229,11 +229,11 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n = tile * kRows + row;
         const bool live = n < N && (ray_valid == nullptr || ray_valid[n / S] != 0);
-        if (ray_valid != nullptr && !__syncthreads_or(live)) continue;     // tile of masked-out rays only
+        if (ray_valid != nullptr && !c.any(live)) continue;              // tile of masked-out rays only
         float head[10], zh[7];
         f3 d = mk3(0.f, 0.f, 1.f);
         float dn = 1.0f;
-        forward_tile<SPLIT, true>(c, T, feats, rays_d, n, live, S, head, zh, d, dn, level_stride);
+        forward_tile<SPLIT, true, 4>(c, T, feats, rays_d, n, live, S, head, zh, d, dn, level_stride);
 
         // ---- d(loss)/d(pre-activations) of the 7 heads and the 3 specular outputs (column group 0)
         if (cg == 0) {
@@ -493,15 +493,12 @@ SNRF_API int snrf_decoder_fwd(const float* feats, const float* mask32, const flo
     }
     const int num_tiles = snrf_div_up(N, kRows);
     cudaStream_t s = (cudaStream_t)stream;
-    if (g_split) {
-        int grid = snrf_sm_count();                 // ~145 KB of shared memory: one CTA per SM
-        if (grid > num_tiles) grid = num_tiles;
+    int grid = snrf_sm_count();                     // one 16-warp CTA per SM, two tiles in flight each
+    if (grid > (num_tiles + 1) / 2) grid = (num_tiles + 1) / 2;
+    if (g_split)
         decoder_fwd_kernel<true><<<grid, kThreadsDec, fwd_smem<true>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
-    } else {
-        int grid = snrf_sm_count() * 2;             // 2 x (256 TMEM columns, ~87 KB)
-        if (grid > num_tiles) grid = num_tiles;
+    else
         decoder_fwd_kernel<false><<<grid, kThreadsDec, fwd_smem<false>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
-    }
     SNRF_RETURN_LAUNCH("snrf_decoder_fwd");
 }
 

@@ -51,7 +51,9 @@ template <bool SPLIT> constexpr int off_bias() { return weights_end<SPLIT>(); }
 template <bool SPLIT> constexpr int off_mask() { return off_bias<SPLIT>() + nB * 4; }
 template <bool SPLIT> constexpr int off_small() { return off_mask<SPLIT>() + 128; }
 template <bool SPLIT> constexpr int off_tiles() { return ((off_small<SPLIT>() + 64 + 1023) / 1024) * 1024; }
-template <bool SPLIT> constexpr int fwd_smem() { return off_tiles<SPLIT>() + (SPLIT ? 5 : 3) * kTile + 1024; }
+template <bool SPLIT> constexpr int fwd_tiles() { return SPLIT ? 5 : 3; }     // operand tiles of one in-flight forward tile
+template <bool SPLIT> constexpr int fwd_smem() { return off_tiles<SPLIT>() + 2 * fwd_tiles<SPLIT>() * kTile + 1024; }   // two tiles in flight
+template <bool SPLIT> constexpr int fwd_smem_one() { return off_tiles<SPLIT>() + fwd_tiles<SPLIT>() * kTile + 1024; }   // one tile in flight
 template <bool SPLIT> constexpr int bwd_smem() { return off_tiles<SPLIT>() + 10 * kTile + 1024; }
 
 // TMEM columns: working accumulators, then (backward only) the persistent gradient accumulators
@@ -189,38 +191,68 @@ struct Tiles {
     unsigned char *A0, *a1, *g1, *H, *a3, *g3, *a4, *g4, *LOa, *LOb;
 };
 
-// Thread layout of the decoder kernels: kThreadsDec = 512 threads = 16 warps per 128-row tile.
-// Thread (row, cg): row = 32 * (warp & 3) + lane is the sample / TMEM lane (a warp can only read the
-// TMEM lane quadrant warp % 4), cg = warp >> 2 is the column group: in every 64-wide layer the thread
-// owns columns [16 cg, 16 cg + 16).  Four warps per scheduler hide the latency of the activation /
-// conversion epilogues that a one-thread-per-row layout (one warp per scheduler) leaves exposed.
+// Thread layout of the decoder kernels: kThreadsDec = 512 threads = 16 warps per CTA, in one of two shapes.
+//   NCG = 4 (backward): ONE 128-row tile per CTA; thread (row, cg), row = 32 (warp & 3) + lane is the sample / TMEM lane
+//            (a warp can only read the TMEM lane quadrant warp % 4), cg = warp >> 2 is the column group: in every
+//            64-wide layer the thread owns columns [16 cg, 16 cg + 16).
+//   NCG = 2 (forward, inference): TWO tiles in flight per CTA; group = warp >> 3 owns a tile (own operand tiles, TMEM
+//            columns, mbarrier and named barrier), its 8 warps form 2 column groups of 32 columns.  While one group
+//            waits for its MMAs the other runs its epilogue (and, in the inference kernel, its table gathers).
+// Either way four warps per scheduler hide the latency a one-thread-per-row layout leaves exposed.
 constexpr int kThreadsDec = 512;
+constexpr int kTmemGroup = 160;           // TMEM columns of one in-flight forward tile (cDa, cDb, cDh = 144, padded)
+
+__device__ __forceinline__ void bar_sync(uint32_t id, uint32_t nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// barrier + OR-reduction of a predicate over the threads of a named barrier (group-scoped __syncthreads_or)
+__device__ __forceinline__ bool bar_or(uint32_t id, uint32_t nthreads, bool pred)
+{
+    uint32_t r;
+    asm volatile(
+        "{\n.reg .pred p, q;\nsetp.ne.u32 q, %1, 0;\nbar.red.or.pred p, %2, %3, q;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(r)
+        : "r"((uint32_t)pred), "r"(id), "r"(nthreads)
+        : "memory");
+    return r != 0;
+}
 
 // Per-thread context shared by the forward stages
-template <bool SPLIT>
+template <bool SPLIT, int NCG>
 struct Ctx {
+    static constexpr int W = 64 / NCG;          // accumulator columns per thread in a 64-wide layer
     unsigned char* smem;
     uint64_t* bar;
-    uint32_t tmem, lane_addr, phase;
-    int tid, row, cg;
+    uint32_t tmem, lane_addr, phase, bar_id, nthr;
+    int tid, row, cg, group;
+    bool leader;                                // the thread that issues this group's MMAs
     const float* bias;
     const float* mask;
-    __device__ __forceinline__ void init(unsigned char* smem_, uint64_t* bar_, uint32_t tmem_)
+    // `bars`: one mbarrier per group; `tmem_base`: the CTA's TMEM allocation
+    __device__ __forceinline__ void init(unsigned char* smem_, uint64_t* bars, uint32_t tmem_base)
     {
-        smem = smem_; bar = bar_; tmem = tmem_; phase = 0;
+        smem = smem_; phase = 0;
         tid = threadIdx.x;
         const int warp = tid >> 5;
         row = 32 * (warp & 3) + (tid & 31);
-        cg = warp >> 2;
+        if (NCG == 4) { group = 0; cg = warp >> 2; nthr = kThreadsDec; }
+        else { group = warp >> 3; cg = (warp >> 2) & 1; nthr = kThreadsDec / 2; }
+        bar = bars + group;
+        bar_id = 1 + group;
+        leader = (tid == group * (kThreadsDec / 2));
+        tmem = tmem_base + (NCG == 4 ? 0 : group * kTmemGroup);
         lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
         bias = reinterpret_cast<const float*>(smem + off_bias<SPLIT>());
         mask = reinterpret_cast<const float*>(smem + off_mask<SPLIT>());
     }
+    __device__ __forceinline__ void sync() { bar_sync(bar_id, nthr); }
+    __device__ __forceinline__ bool any(bool pred) { return bar_or(bar_id, nthr, pred); }
     __device__ __forceinline__ void sync_operands()
     {   // my shared-memory stores and TMEM loads are done -> the next MMAs may run
         umma::fence_async_smem();
         umma::tc_fence_before();
-        __syncthreads();
+        bar_sync(bar_id, nthr);
         umma::tc_fence_after();
     }
     __device__ __forceinline__ void wait_mma()
@@ -229,18 +261,28 @@ struct Ctx {
         phase ^= 1u;
         umma::tc_fence_after();
     }
+    // this thread's W accumulator columns [W cg, W cg + W) of the 64-wide accumulator at `col`
+    __device__ __forceinline__ void load_cols(int col, float* v)
+    {
+        if (W == 16) umma::tmem_ld16(tmem + col + lane_addr + 16 * cg, v);
+        else umma::tmem_ld32(tmem + col + lane_addr + 32 * cg, v);
+        umma::tc_wait_ld();
+    }
 };
 
 // Operand row of one sample: A0 = [x_hi (0..31) | SH_hi (32..47) | SH_lo (48..63)], LOb = [x_lo (0..31)].
-// Thread (row, cg) stores feature chunk cg: x8 = the 8 (already masked) features 8 cg .. 8 cg + 7; the
-// threads with cg >= 2 also store SH chunk cg - 2: sh8 = SH coefficients 8 (cg - 2) .. + 7.
-template <bool SPLIT>
-__device__ __forceinline__ void store_input_row(const Tiles& T, int row, int cg, const float* x8, const float* sh8)
+// Thread (row, cg) stores its 32 / NCG (already masked) features x (chunks (4 / NCG) cg ...) and one SH chunk:
+// NCG = 4: the threads with cg >= 2 store SH chunk cg - 2; NCG = 2: cg stores SH chunk cg.  sh8 = that chunk's 8 values.
+template <bool SPLIT, int NCG>
+__device__ __forceinline__ void store_input_row(const Tiles& T, int row, int cg, const float* x, const float* sh8)
 {
-    store8_hl<SPLIT>(T.A0, cg, T.LOb, cg, row, x8);
-    if (cg >= 2) {
-        store8_hl<SPLIT>(T.A0, 2 + cg, T.A0, 4 + cg, row, sh8);
-        if (!SPLIT) umma::tile_zero8(T.A0, row, 4 + cg);
+    constexpr int XC = 4 / NCG;
+#pragma unroll
+    for (int q = 0; q < XC; ++q) store8_hl<SPLIT>(T.A0, XC * cg + q, T.LOb, XC * cg + q, row, x + 8 * q);
+    const int shc = NCG == 4 ? cg - 2 : cg;
+    if (shc >= 0) {
+        store8_hl<SPLIT>(T.A0, 4 + shc, T.A0, 6 + shc, row, sh8);
+        if (!SPLIT) umma::tile_zero8(T.A0, row, 6 + shc);
     }
 }
 
@@ -248,11 +290,12 @@ __device__ __forceinline__ void store_input_row(const Tiles& T, int row, int cg,
 // A0 / LOb.  Writes the operand tiles; the threads with cg == 0 return sigma/diffuse/tint activated in
 // head[0..6] (torch semantics) and their pre-activations in zh[0..6]; the specular pre-activations are
 // left in TMEM columns cDh..cDh+2.
-template <bool SPLIT, bool TRAIN>
-__device__ __forceinline__ void forward_layers(Ctx<SPLIT>& c, const Tiles& T, float* head, float* zh)
+template <bool SPLIT, bool TRAIN, int NCG>
+__device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& T, float* head, float* zh)
 {
+    constexpr int W = 64 / NCG, CH = W / 8;
     unsigned char* smem = c.smem;
-    const int tid = c.tid, row = c.row, cg = c.cg;
+    const int row = c.row, cg = c.cg;
     const uint32_t tmem = c.tmem, lane_addr = c.lane_addr;
     const float* bias = c.bias;
     const uint32_t aA0 = umma::smem_u32(T.A0), aa1 = umma::smem_u32(T.a1), aH = umma::smem_u32(T.H), aa3 = umma::smem_u32(T.a3),
@@ -265,47 +308,45 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT>& c, const Tiles& T, fl
 
     c.sync_operands();
     // ---- L1: Da = x W1^T (K = 32)
-    if (tid == 0) {
+    if (c.leader) {
         fwd_gemm<SPLIT>(tmem + cDa, aA0, 0, aLOb, 0, aW1, 0, aW1, 2, 2, id64, false);
         umma::mma_commit(c.bar);
     }
     c.wait_mma();
-    float v[16], g[16];
-    // Gaussian layer epilogue on this thread's 16 columns: a = exp(-50 z^2) -> (Ta, lo in Tlo);
+    float v[W], g[TRAIN ? W : 1];
+    // Gaussian layer epilogue on this thread's W columns: a = exp(-50 z^2) -> (Ta, lo in Tlo);
     // TRAIN: g = da/dz = -100 z a -> Tg
     auto gauss_epilogue = [&](int col, int boff, unsigned char* Ta, unsigned char* Tlo, unsigned char* Tg) {
-        umma::tmem_ld16(tmem + col + lane_addr + 16 * cg, v);
-        umma::tc_wait_ld();
+        c.load_cols(col, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float z = v[j] + bias[boff + 16 * cg + j];
+        for (int j = 0; j < W; ++j) {
+            const float z = v[j] + bias[boff + W * cg + j];
             const float a = gauss_act(z);
             v[j] = a;
             if (TRAIN) g[j] = -100.0f * z * a;
         }
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            store8_hl<SPLIT>(Ta, 2 * cg + q, Tlo, 2 * cg + q, row, v + 8 * q);
-            if (TRAIN) umma::tile_store8_f16(Tg, row, 2 * cg + q, g + 8 * q);   // fp16: |g| <= 6.1, read back element-wise only
+        for (int q = 0; q < CH; ++q) {
+            store8_hl<SPLIT>(Ta, CH * cg + q, Tlo, CH * cg + q, row, v + 8 * q);
+            if (TRAIN) umma::tile_store8_f16(Tg, row, CH * cg + q, g + 8 * q);   // fp16: |g| <= 6.1, read back element-wise only
         }
     };
     gauss_epilogue(cDa, oB1, T.a1, T.LOa, T.g1);
     c.sync_operands();
     // ---- L2: Db = h1 W2^T (K = 64)
-    if (tid == 0) {
+    if (c.leader) {
         fwd_gemm<SPLIT>(tmem + cDb, aa1, 0, aLOa, 0, aW2, 0, aW2l, 0, 4, id64, false);
         umma::mma_commit(c.bar);
     }
     c.wait_mma();
-    umma::tmem_ld16(tmem + cDb + lane_addr + 16 * cg, v);
-    umma::tc_wait_ld();
+    c.load_cols(cDb, v);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] += bias[oB2 + 16 * cg + j];
+    for (int j = 0; j < W; ++j) v[j] += bias[oB2 + W * cg + j];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) store8_hl<SPLIT>(T.H, 2 * cg + q, T.LOb, 2 * cg + q, row, v + 8 * q);
+    for (int q = 0; q < CH; ++q) store8_hl<SPLIT>(T.H, CH * cg + q, T.LOb, CH * cg + q, row, v + 8 * q);
     c.sync_operands();
     // ---- heads: Dh = H[0:32] Wh^T (K = 32, N = 16);   L3: Da = [H[32:64] | SH] W3^T (K = 48)
-    if (tid == 0) {
+    if (c.leader) {
         fwd_gemm<SPLIT>(tmem + cDh, aH, 0, aLOb, 0, aWh, 0, aWh, 2, 2, id16, false);
         fwd_gemm<SPLIT>(tmem + cDa, aH, 2, aLOb, 2, aW3, 0, aW3l, 0, 2, id64, false);
         fwd_gemm<SPLIT>(tmem + cDa, aA0, 2, aA0, 3, aW3, 2, aW3l, 2, 1, id64, true);
@@ -328,7 +369,7 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT>& c, const Tiles& T, fl
     gauss_epilogue(cDa, oB3, T.a3, T.LOa, T.g3);
     c.sync_operands();
     // ---- L4: Db = a3 W4^T (K = 64)
-    if (tid == 0) {
+    if (c.leader) {
         fwd_gemm<SPLIT>(tmem + cDb, aa3, 0, aLOa, 0, aW4, 0, aW4l, 0, 4, id64, false);
         umma::mma_commit(c.bar);
     }
@@ -336,7 +377,7 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT>& c, const Tiles& T, fl
     gauss_epilogue(cDb, oB4, T.a4, T.LOb, T.g4);
     c.sync_operands();
     // ---- L5: Dh = a4 W5^T (K = 64, N = 16)
-    if (tid == 0) {
+    if (c.leader) {
         fwd_gemm<SPLIT>(tmem + cDh, aa4, 0, aLOb, 0, aW5, 0, aW5l, 0, 4, id16, false);
         umma::mma_commit(c.bar);
     }
@@ -345,43 +386,47 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT>& c, const Tiles& T, fl
 
 // Training-side input: features from HBM times the level mask, SH of d / (|d| + 1e-8) (network.py:172-190).
 // feats: [N,32] row-major (level_stride = 0) or level-major [16][N] float2 (level_stride = N).
-// d / dn (the ray direction and its norm) are returned to the threads with cg >= 2.
-template <bool SPLIT, bool TRAIN>
-__device__ __forceinline__ void forward_tile(Ctx<SPLIT>& c, const Tiles& T, const float* __restrict__ feats,
+// d / dn (the ray direction and its norm) are returned to the threads that hold an SH chunk.
+template <bool SPLIT, bool TRAIN, int NCG>
+__device__ __forceinline__ void forward_tile(Ctx<SPLIT, NCG>& c, const Tiles& T, const float* __restrict__ feats,
                                              const float* __restrict__ rays_d, int n, bool live, int S, float* head, float* zh,
                                              f3& d, float& dn, long long level_stride)
 {
+    constexpr int NX = 32 / NCG;                // features per thread
     const float* mask = c.mask;
     const int cg = c.cg;
-    float x[8], sh[16];
+    const int shc = NCG == 4 ? cg - 2 : cg;
+    float x[NX], sh[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = 0.0f;
+    for (int j = 0; j < NX; ++j) x[j] = 0.0f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) sh[j] = 0.0f;
     if (live) {
         if (level_stride == 0) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(feats + (size_t)n * 32 + 8 * cg));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(feats + (size_t)n * 32 + 8 * cg + 4));
-            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+#pragma unroll
+            for (int q = 0; q < NX / 4; ++q) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(feats + (size_t)n * 32 + NX * cg + 4 * q));
+                x[4 * q] = a.x; x[4 * q + 1] = a.y; x[4 * q + 2] = a.z; x[4 * q + 3] = a.w;
+            }
         } else {
             const float2* f2 = reinterpret_cast<const float2*>(feats) + n;
 #pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                const float2 a = __ldg(f2 + (size_t)(4 * cg + l) * level_stride);
+            for (int l = 0; l < NX / 2; ++l) {
+                const float2 a = __ldg(f2 + (size_t)((NX / 2) * cg + l) * level_stride);
                 x[2 * l] = a.x; x[2 * l + 1] = a.y;
             }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] *= mask[8 * cg + j];
-        if (cg >= 2) {
+        for (int j = 0; j < NX; ++j) x[j] *= mask[NX * cg + j];
+        if (shc >= 0) {
             d = ld3(rays_d + 3 * (size_t)(n / S));
             dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
             const float inv = 1.0f / (dn + 1e-8f);
             sh16(d.x * inv, d.y * inv, d.z * inv, sh);
         }
     }
-    store_input_row<SPLIT>(T, c.row, cg, x, sh + 8 * (cg & 1));
-    forward_layers<SPLIT, TRAIN>(c, T, head, zh);
+    store_input_row<SPLIT, NCG>(T, c.row, cg, x, sh + 8 * (shc & 1));
+    forward_layers<SPLIT, TRAIN, NCG>(c, T, head, zh);
 }
 
 }  // namespace dec

@@ -68,36 +68,44 @@ struct InferArgs {
     uint32_t T;
 };
 
-template <bool SPLIT, int MODE>
+template <bool SPLIT, int MODE, int NCG>
 __global__ void __launch_bounds__(kThreadsDec, 1)
 infer_kernel(InferArgs a, int num_tiles)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char* T0 = smem + off_tiles<SPLIT>();
-    unsigned char* T1 = T0 + kTile;
-    unsigned char* T2 = T1 + kTile;
-    unsigned char* LOa = SPLIT ? T2 + kTile : T1;
-    unsigned char* LOb = SPLIT ? LOa + kTile : T2;
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bars[2];
     __shared__ uint32_t tmem_slot;
-    __shared__ int next_id;
+    __shared__ int next_ids[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    if (warp == 0) umma::tmem_alloc<256>(&tmem_slot);
-    if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_fence_init(); }
+    if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);
+    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::mbar_fence_init(); }
+    // NCG = 2 (a single scene tile: one set of weights, staged once): two 128-sample tiles in flight per CTA, so one
+    // group's table gathers and epilogues overlap the other's MMAs.  NCG = 4 (several scene tiles): one tile per CTA,
+    // weights re-staged whenever the walk reaches another scene tile.
+    if (NCG == 2) stage_all_weights<SPLIT>(smem, flat_params(a.params), nullptr, tid, kThreadsDec);
     umma::fence_async_smem();
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
-    Ctx<SPLIT> c;
-    c.init(smem, &bar, tmem_slot);
+    Ctx<SPLIT, NCG> c;
+    c.init(smem, bars, tmem_slot);
     const int row = c.row, cg = c.cg;
+    int& next_id = next_ids[c.group];
+    unsigned char* T0 = smem + off_tiles<SPLIT>() + c.group * fwd_tiles<SPLIT>() * kTile;
+    unsigned char* T1 = T0 + kTile;
+    unsigned char* T2 = T1 + kTile;
+    unsigned char* LOa = SPLIT ? T2 + kTile : T1;
+    unsigned char* LOb = SPLIT ? LOa + kTile : T2;
     const Tiles Tl{T0, T1, nullptr, T2, T1, nullptr, T2, nullptr, LOa, LOb};
-    int staged = -1;
+    int staged = NCG == 2 ? 0 : -1;
     const long long total = (long long)a.B * a.S;
+    constexpr int NG = NCG == 2 ? 2 : 1;               // tiles in flight
+    constexpr int NX = 32 / NCG;                       // features per thread
+    const int shc = NCG == 4 ? cg - 2 : cg;            // SH chunk held by this thread (< 0: none)
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = NG * blockIdx.x + c.group; tile < num_tiles; tile += NG * gridDim.x) {
         const long long n = (long long)tile * kRows + row;
         const bool live = n < total;
         const int ray = live ? (int)(n / a.S) : 0, k = live ? (int)(n % a.S) : 0;
@@ -124,7 +132,7 @@ infer_kernel(InferArgs a, int num_tiles)
         const f3 p = o + zv * d;
         const f3 dn = d * rsqrtf(dot3(d, d));                 // normalize(): decoder.h:201, no epsilon
         float sh[16];
-        if (cg >= 2) sh16(dn.x, dn.y, dn.z, sh);
+        if (shc >= 0) sh16(dn.x, dn.y, dn.z, sh);
         const float dlen = sqrtf(dot3(d, d));
         f3 acc_d = mk3(0, 0, 0), acc_s = mk3(0, 0, 0);
         float acc_a = 0.0f, wsum = 0.0f;
@@ -137,12 +145,12 @@ infer_kernel(InferArgs a, int num_tiles)
             for (int i = 0; i < kMaxPts; ++i) if (ids[i] > cur && ids[i] < mine) mine = ids[i];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, off));
-            if (tid == 0) next_id = 0x7fffffff;
-            __syncthreads();
+            if (c.leader) next_id = 0x7fffffff;
+            c.sync();
             if (lane == 0 && mine != 0x7fffffff) atomicMin(&next_id, mine);
-            __syncthreads();
+            c.sync();
             const int b = next_id;
-            __syncthreads();                                   // everyone has read next_id before it is reset
+            c.sync();                                          // everyone has read next_id before it is reset
             if (b == 0x7fffffff) break;
             cur = b;
             int slot = -1;
@@ -180,7 +188,7 @@ infer_kernel(InferArgs a, int num_tiles)
                     active = true;
                 }
             }
-            if (!__syncthreads_or(active)) {                   // nobody needs the MLP for this tile
+            if (!c.any(active)) {                              // nobody needs the MLP for this tile
                 if (member) wsum += w;
                 continue;
             }
@@ -188,16 +196,18 @@ infer_kernel(InferArgs a, int num_tiles)
                 stage_all_weights<SPLIT>(smem, flat_params(a.params + (size_t)b * 13994), nullptr, tid, kThreadsDec);
                 staged = b;
             }
-            float x[8];                                        // this thread's feature chunk: levels 4 cg .. 4 cg + 3
+            float x[NX];                                       // this thread's features: levels (16 / NCG) cg ...
             if (active) {
-                encode4(u, a.resolution + (size_t)b * 48, a.tables + (size_t)b * 16 * a.T, a.T, 4 * cg, x);
+#pragma unroll
+                for (int q = 0; q < NX / 8; ++q)
+                    encode4(u, a.resolution + (size_t)b * 48, a.tables + (size_t)b * 16 * a.T, a.T, (NX / 2) * cg + 4 * q, x + 8 * q);
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = 0.0f;
+                for (int j = 0; j < NX; ++j) x[j] = 0.0f;
             }
-            store_input_row<SPLIT>(Tl, row, cg, x, sh + 8 * (cg & 1));
+            store_input_row<SPLIT, NCG>(Tl, row, cg, x, sh + 8 * (shc & 1));
             float head[10], zh[7];
-            forward_layers<SPLIT, false>(c, Tl, head, zh);
+            forward_layers<SPLIT, false, NCG>(c, Tl, head, zh);
             float zs[16];
             if (cg == 0) {
                 umma::tmem_ld16(c.tmem + cDh + c.lane_addr, zs);
@@ -234,75 +244,86 @@ infer_kernel(InferArgs a, int num_tiles)
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == 0) umma::tmem_free<256>(c.tmem);
+    if (warp == 0) umma::tmem_free<512>(tmem_slot);
 }
 
 int g_infer_split = 1;
+// Tiles in flight per CTA for single-tile scenes.  Measured on B200 (1920x1080, tools/dbg/time_render.py): 1 tile in
+// flight 498 ms / frame, 2 tiles 765 ms -- the second tile's operand buffers take 80 KB away from the L1, and the table
+// gathers live on L1 hits between corners that share a sector.  Default 1; 2 stays selectable.
+int g_infer_inflight = 1;
 
-template <int MODE>
-int launch(const InferArgs& a, void* stream, const char* name)
+template <int MODE, int NCG>
+int launch_ncg(const InferArgs& a, void* stream, const char* name)
 {
+    // shared memory not used for operand tiles stays L1: the table gathers need it (x-adjacent corners share sectors)
+    constexpr int smem_t = NCG == 2 ? fwd_smem<true>() : fwd_smem_one<true>();
+    constexpr int smem_f = NCG == 2 ? fwd_smem<false>() : fwd_smem_one<false>();
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(infer_kernel<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<true>());
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(infer_kernel<false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<false>());
+        cudaError_t e = cudaFuncSetAttribute(infer_kernel<true, MODE, NCG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(infer_kernel<false, MODE, NCG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f);
         if (e != cudaSuccess) { snrf_set_error("%s: %s", name, cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
     const long long total = (long long)a.B * a.S;
     const int num_tiles = snrf_div_up(total, kRows);
+    const int per_cta = NCG == 2 ? 2 : 1;
     cudaStream_t s = (cudaStream_t)stream;
-    if (g_infer_split) {
-        int grid = snrf_sm_count();
-        if (grid > num_tiles) grid = num_tiles;
-        infer_kernel<true, MODE><<<grid, kThreadsDec, fwd_smem<true>(), s>>>(a, num_tiles);
-    } else {
-        int grid = snrf_sm_count() * 2;
-        if (grid > num_tiles) grid = num_tiles;
-        infer_kernel<false, MODE><<<grid, kThreadsDec, fwd_smem<false>(), s>>>(a, num_tiles);
-    }
+    int grid = snrf_sm_count();
+    if (grid > (num_tiles + per_cta - 1) / per_cta) grid = (num_tiles + per_cta - 1) / per_cta;
+    if (g_infer_split) infer_kernel<true, MODE, NCG><<<grid, kThreadsDec, smem_t, s>>>(a, num_tiles);
+    else infer_kernel<false, MODE, NCG><<<grid, kThreadsDec, smem_f, s>>>(a, num_tiles);
     SNRF_RETURN_LAUNCH(name);
+}
+
+// nb = number of scene tiles behind `params` / `tables`
+template <int MODE>
+int launch(const InferArgs& a, int nb, void* stream, const char* name)
+{
+    return (nb == 1 && g_infer_inflight == 2) ? launch_ncg<MODE, 2>(a, stream, name) : launch_ncg<MODE, 4>(a, stream, name);
 }
 
 }  // namespace
 
 // ------------------------------- C ABI --------------------------------------
 SNRF_API void snrf_infer_set_precision(int split) { g_infer_split = split ? 1 : 0; }
+SNRF_API void snrf_infer_set_inflight(int tiles) { g_infer_inflight = tiles == 2 ? 2 : 1; }
 
 SNRF_API int snrf_pts_inference(const float* rays_o, const float* rays_d, const float* z_vals, const float* dists,
                                 const short* block_idxs, const void* features_tables, const float* params, const int* resolution,
                                 const unsigned char* grid_occupied, const long long* grid_starts, const int* grid_log2dim,
                                 const float* corners, const float* sizes, float* diffuse, float* specular, float* alpha, int B,
-                                int S, int T, void* stream)
+                                int S, int T, int nb, void* stream)
 {
     SNRF_CHECK_ARG(T > 0 && (T & (T - 1)) == 0, "snrf_pts_inference: hashmap size must be a power of two (got %d)", T);
     if (B <= 0 || S <= 0) return 0;
     InferArgs a{rays_o, rays_d, z_vals, dists, block_idxs, nullptr, (const __half2*)features_tables, params, resolution, grid_occupied,
                 grid_starts, grid_log2dim, corners, sizes, diffuse, specular, alpha, B, S, 0, (uint32_t)T};
-    return launch<kFore>(a, stream, "snrf_pts_inference");
+    return launch<kFore>(a, nb, stream, "snrf_pts_inference");
 }
 
 SNRF_API int snrf_bg_pts_inference(const float* rays_o, const float* rays_d, const float* z_vals, const short* outgoing_bidxs,
                                    const float* blend_weights, const float* corners, const float* sizes, const int* resolution,
                                    const void* features_tables, const float* params, float* diffuse, float* specular, float* alpha,
-                                   int B, int S, int T, void* stream)
+                                   int B, int S, int T, int nb, void* stream)
 {
     SNRF_CHECK_ARG(T > 0 && (T & (T - 1)) == 0, "snrf_bg_pts_inference: hashmap size must be a power of two (got %d)", T);
     if (B <= 0 || S <= 0) return 0;
     InferArgs a{rays_o, rays_d, z_vals, nullptr, outgoing_bidxs, blend_weights, (const __half2*)features_tables, params, resolution, nullptr,
                 nullptr, nullptr, corners, sizes, diffuse, specular, alpha, B, S, 0, (uint32_t)T};
-    return launch<kBackBlend>(a, stream, "snrf_bg_pts_inference");
+    return launch<kBackBlend>(a, nb, stream, "snrf_bg_pts_inference");
 }
 
 SNRF_API int snrf_bg_pts_inference_v2(const float* rays_o, const float* rays_d, const float* z_vals, const short* bg_idxs, int step,
                                       const float* corners, const float* sizes, const int* resolution, const void* features_tables,
                                       const float* params, float* diffuse, float* specular, float* alpha, int B, int S, int T,
-                                      void* stream)
+                                      int nb, void* stream)
 {
     SNRF_CHECK_ARG(T > 0 && (T & (T - 1)) == 0, "snrf_bg_pts_inference_v2: hashmap size must be a power of two (got %d)", T);
     SNRF_CHECK_ARG(step >= 0 && step < kMaxPts, "snrf_bg_pts_inference_v2: step must be in [0,4) (got %d)", step);
     if (B <= 0 || S <= 0) return 0;
     InferArgs a{rays_o, rays_d, z_vals, nullptr, bg_idxs, nullptr, (const __half2*)features_tables, params, resolution, nullptr,
                 nullptr, nullptr, corners, sizes, diffuse, specular, alpha, B, S, step, (uint32_t)T};
-    return launch<kBackSlot>(a, stream, "snrf_bg_pts_inference_v2");
+    return launch<kBackSlot>(a, nb, stream, "snrf_bg_pts_inference_v2");
 }

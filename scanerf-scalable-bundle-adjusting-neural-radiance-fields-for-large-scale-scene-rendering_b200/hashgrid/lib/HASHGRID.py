@@ -177,7 +177,7 @@ def pts_inference(rays_o, rays_d, z_vals, dists, block_idxs, features_tables, pa
     od, os_, oa = Out(diffuse, f32, "diffuse"), Out(specular, f32, "specular"), Out(alpha, f32, "alpha")
     capi.check(capi.lib().snrf_pts_inference(ptr(o), ptr(d), ptr(z), ptr(di), ptr(bi), ptr(ft), ptr(pa), ptr(re), ptr(g), ptr(gs),
                                              ptr(gl), ptr(c), ptr(s), od.ptr, os_.ptr, oa.ptr, c_int(B), c_int(S), c_int(T),
-                                             capi.stream()), "snrf_pts_inference")
+                                             c_int(int(c.shape[0])), capi.stream()), "snrf_pts_inference")
     od.done(); os_.done(); oa.done()
 
 
@@ -224,7 +224,7 @@ def bg_pts_inference(rays_o, rays_d, z_vals, outgoing_bidxs, blend_weights, bloc
     ft, pa = inp(features_tables, f16, "features_tables"), inp(params, f32, "params")
     od, os_, oa = Out(diffuse, f32, "diffuse"), Out(specular, f32, "specular"), Out(alpha, f32, "alpha")
     capi.check(capi.lib().snrf_bg_pts_inference(ptr(o), ptr(d), ptr(z), ptr(ob), ptr(bw), ptr(c), ptr(s), ptr(re), ptr(ft), ptr(pa),
-                                                od.ptr, os_.ptr, oa.ptr, c_int(B), c_int(S), c_int(T), capi.stream()),
+                                                od.ptr, os_.ptr, oa.ptr, c_int(B), c_int(S), c_int(T), c_int(int(c.shape[0])), capi.stream()),
                "snrf_bg_pts_inference")
     od.done(); os_.done(); oa.done()
 
@@ -240,7 +240,7 @@ def bg_pts_inference_v2(rays_o, rays_d, z_vals, bg_idxs, step, block_corners, bl
     ft, pa = inp(features_tables, f16, "features_tables"), inp(params, f32, "params")
     od, os_, oa = Out(diffuse, f32, "diffuse"), Out(specular, f32, "specular"), Out(alpha, f32, "alpha")
     capi.check(capi.lib().snrf_bg_pts_inference_v2(ptr(o), ptr(d), ptr(z), ptr(bi), c_int(int(step)), ptr(c), ptr(s), ptr(re), ptr(ft),
-                                                   ptr(pa), od.ptr, os_.ptr, oa.ptr, c_int(B), c_int(S), c_int(T), capi.stream()),
+                                                   ptr(pa), od.ptr, os_.ptr, oa.ptr, c_int(B), c_int(S), c_int(T), c_int(int(c.shape[0])), capi.stream()),
                "snrf_bg_pts_inference_v2")
     od.done(); os_.done(); oa.done()
 

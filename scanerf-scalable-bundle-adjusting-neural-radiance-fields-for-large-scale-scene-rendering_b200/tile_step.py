@@ -160,7 +160,10 @@ class TileStep:
         self.optimizer = torch.optim.Adam([
             {"params": self.decoder.parameters(), "lr": lr_decoder, "weight_decay": 1e-6},
             {"params": self.poses.se3_refine, "lr": lr_cam}])
-        self.two_streams = True         # foreground / background chains on two CUDA streams (see render_rays)
+        # foreground / background chains on two CUDA streams (see render_rays): measured on B200 at default.yaml shape it
+        # buys nothing at steady state (14.04 vs 14.10 ms / step) and costs allocator growth while the per-stream pools
+        # settle, so it is off by default
+        self.two_streams = False
         self._side = None
         self.consensus = None           # ADMM state, see enable_consensus()
         self.camera_ids = None
@@ -191,9 +194,8 @@ class TileStep:
     # tile.py:639-692
     def render_rays(self, rays_o, rays_d, occlusion_mask=None, mode=TRAIN):
         # The foreground and the background chains (sample -> encode -> decoder -> composite) are independent until the
-        # colours are merged.  They are issued on two CUDA streams: the decoder kernels are latency-bound (one 16-warp CTA
-        # per SM, tensor pipe ~10 % busy) and the encode / scatter kernels are memory-bound, so the two chains fill each
-        # other's gaps -- in the backward too, which autograd runs on the streams of the forward ops.
+        # colours are merged; with two_streams they are issued on two CUDA streams (the backward follows: autograd runs on
+        # the streams of the forward ops).
         side = self._side_stream() if self.two_streams else None
         if side is not None:
             main = torch.cuda.current_stream()
