@@ -146,3 +146,21 @@ def test_fastmesh_wrapper_masks():
         assert depth.shape == (2048, 1) and mask.shape == (2048, 1) and mask.dtype == torch.bool
         inside = torch.all(torch.abs(o - torch.tensor([10.0, 6.5, 15.0])) < torch.tensor([5.0, 3.25, 7.5]), dim=-1)
         assert bool(mask.cpu()[inside].all()), "origins inside the tile always see it"
+
+
+def test_first_hit_against_numpy_oracle():
+    """fisrtHit against the loop-form restatement of the reference's cell walk (oracle/render_ref.py)."""
+    from oracle import render_ref as rr
+    with tempfile.TemporaryDirectory() as tmp:
+        ply, V, F = _mesh(tmp, n_boxes=5, ground_res=10)
+        m = _ours(ply)
+        B = 200
+        o, d = _rays(B, 21, V)
+        z = torch.zeros(B, 1, device="cuda:0")
+        m.fisrtHit(o.to("cuda:0"), d.to("cuda:0"), z)
+        mesh = rr.mesh_build(V, F)
+        want = np.array([rr.mesh_first_hit(mesh, V, F, o[i].numpy(), d[i].numpy()) for i in range(B)], np.float32)
+        got = z.cpu().numpy()[:, 0]
+        same = (got > 0) == (want > 0)
+        assert same.mean() > 0.99, f"hit / miss pattern differs on {int((~same).sum())} of {B} rays"
+        assert np.allclose(got[same], want[same], rtol=1e-4, atol=1e-4)

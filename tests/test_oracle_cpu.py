@@ -93,3 +93,28 @@ def test_ray_backward_is_adjoint():
     lhs = float((o.astype(np.float64) * go).sum() + (d.astype(np.float64) * gd).sum())
     rhs = float((g.astype(np.float64) * C).sum())       # forward is linear in C2W
     assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0)
+
+
+def test_render_oracle_invariants():
+    """oracle/render_ref.py sanity on the CPU: inverse-z samples start at the tile exit, front-to-back accumulation
+    conserves T + sum of alpha T, the cell walk finds a triangle placed in front of the ray."""
+    from oracle import render_ref as rr
+    isect = np.array([[[1.0, 4.0], [1e7, 1e7]]], np.float32)
+    z = rr.inverse_z_sampling(isect, np.array([0], np.int16), 8, 1e6)
+    assert abs(z[0, 0] - 4.0) < 1e-5 and np.all(np.diff(z[0]) > 0) and abs(z[0, -1] - (4.0 + 1e6)) / 1e6 < 1e-2      # fp32: 1 / (1e-6-sized reciprocal)
+    assert np.all(rr.inverse_z_sampling(isect, np.array([-1], np.int16), 8, 1e6) == -1)
+    rng = np.random.RandomState(0)
+    a = rng.rand(3, 9, 1).astype(np.float32) * 0.5
+    ones = np.ones((3, 9, 3), np.float32)
+    T, dif, _, _ = rr.accumulate_color(a * ones, a * ones, a, np.ones((3, 1), np.float32), np.ones((3, 9), np.float32),
+                                       np.zeros((3, 3), np.float32), np.zeros((3, 3), np.float32), np.zeros((3, 1), np.float32))
+    assert np.allclose(dif[:, 0] + T[:, 0], 1.0, atol=1e-5)          # sum_k alpha_k T_k + T_end = 1
+    V = np.array([[0, 0, 1], [4, 0, 1], [0, 4, 1], [4, 4, 1], [0, 0, 0], [4, 4, 4]], np.float32)
+    F = np.array([[0, 1, 2], [1, 3, 2]], np.int32)                     # a quad in the z = 1 plane (faces ON the AABB minimum are skipped by the build, as in the reference)
+    mesh = rr.mesh_build(V, F)
+    t = rr.mesh_first_hit(mesh, V, F, np.array([1.0, 1.0, 3.0], np.float32), np.array([0.0, 0.0, -1.0], np.float32))
+    assert abs(t - 2.0) < 1e-4
+    assert rr.mesh_first_hit(mesh, V, F, np.array([1.0, 1.0, 3.0], np.float32), np.array([0.0, 0.0, 1.0], np.float32)) == 0
+    ids, w = rr.update_outgoing_bidx(np.zeros((1, 3), np.float32), np.array([[1.0, 0, 0]], np.float32), np.zeros((2, 3), np.float32),
+                                     np.ones((2, 3), np.float32), np.array([[0, 1]], np.int32), np.array([[[0, 2.0], [1.0, 3.0]]], np.float32))
+    assert ids[0, 0] == 1 and w[0, 0] == 1.0

@@ -293,3 +293,47 @@ def test_render_rays_driver_matches_reference_sequence(nb):
     assert float((got_s[ok] - want_s[ok]).abs().max()) < 1e-4
     assert float((got_T - want_T).abs().max()) < 1e-4
     assert bool(torch.isfinite(got_d[ok]).all())
+
+
+def test_simple_stages_against_numpy_oracle():
+    """csrc/render.cu stages against the loop-form numpy restatement oracle/render_ref.py (small case)."""
+    from oracle import render_ref as rr
+    ours, _ = _ops()
+    nb, B, S = 3, 300, 16
+    raw = make_scene(nb)
+    sc = dev(raw)
+    o, d = make_rays(B, 123)
+    od, dd = o.to(DEV), d.to(DEV)
+    isect = torch.full((B, nb, 2), MISS, device=DEV)
+    ours.ray_block_intersection(od, dd, sc["corners"], sc["sizes"], isect)
+    want = rr.ray_block_intersection(o.numpy(), d.numpy(), raw["corners"].numpy(), raw["sizes"].numpy())
+    assert np.array_equal(isect.cpu().numpy() == MISS, want == MISS)
+    assert np.allclose(isect.cpu().numpy(), want, rtol=1e-6, atol=1e-6)
+    order = torch.argsort(isect[..., 0], dim=-1).int().contiguous()
+    g = torch.Generator().manual_seed(9)
+    z = (torch.rand(B, S, generator=g) * 25).sort(-1)[0]
+    z[::5] = -1.0
+    running = torch.rand(B, 1, generator=g) < 0.8
+    bi = torch.full((B, S, 4), -1, dtype=torch.int16, device=DEV)
+    ours.prepare_points(z.to(DEV), running.to(DEV), isect, bi)
+    assert np.array_equal(bi.cpu().numpy(), rr.prepare_points(z.numpy(), running.numpy()[:, 0], isect.cpu().numpy()))
+    pd, ps, pa = torch.rand(B, S, 3, generator=g), torch.rand(B, S, 3, generator=g), torch.rand(B, S, 1, generator=g) * 0.3
+    T0 = torch.rand(B, 1, generator=g)
+    T0[::7] = 1e-6
+    acc = [T0.clone().to(DEV), torch.rand(B, 3, generator=g).to(DEV), torch.rand(B, 3, generator=g).to(DEV), torch.rand(B, 1, generator=g).to(DEV)]
+    init = [t.cpu().numpy().copy() for t in acc]
+    ours.accumulate_color(pd.to(DEV), ps.to(DEV), pa.to(DEV), acc[0], z.to(DEV), acc[1], acc[2], acc[3])
+    for got, w in zip(acc, rr.accumulate_color(pd.numpy(), ps.numpy(), pa.numpy(), init[0], z.numpy(), init[1], init[2], init[3])):
+        assert np.allclose(got.cpu().numpy(), w, rtol=1e-5, atol=1e-5)
+    last = torch.full((B,), -7, dtype=torch.int32, device=DEV)
+    ours.get_last_block(order, last, isect)
+    assert np.array_equal(last.cpu().numpy(), rr.get_last_block(order.cpu().numpy(), isect.cpu().numpy()))
+    ob, ow = torch.full((B, 4), -1, dtype=torch.int16, device=DEV), torch.zeros(B, 4, device=DEV)
+    ours.update_outgoing_bidx(od, dd, sc["corners"], sc["sizes"], order, isect, ob, ow, 0.12, False)
+    wb, ww = rr.update_outgoing_bidx(o.numpy(), d.numpy(), raw["corners"].numpy(), raw["sizes"].numpy(), order.cpu().numpy(), isect.cpu().numpy())
+    assert np.array_equal(ob.cpu().numpy(), wb) and np.allclose(ow.cpu().numpy(), ww, rtol=1e-4, atol=1e-5)
+    bz = torch.full((B, 12), -1.0, device=DEV)
+    ours.inverse_z_sampling(isect, ob[:, 0].contiguous(), bz, 1e6)
+    wz = rr.inverse_z_sampling(isect.cpu().numpy(), wb[:, 0], 12, 1e6)
+    fin = np.isfinite(wz)
+    assert np.array_equal(np.isfinite(bz.cpu().numpy()), fin) and np.allclose(bz.cpu().numpy()[fin], wz[fin], rtol=1e-5)
