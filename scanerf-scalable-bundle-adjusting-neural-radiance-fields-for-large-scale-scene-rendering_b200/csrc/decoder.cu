@@ -126,13 +126,15 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     unsigned char* Tdzlo = T.LOa;        // lo part of the current layer's dz (dz5, dz4, dz1 in turn)
     unsigned char* Tdhlo = T.a4;         // lo part of dH (a4 is dead once B1 has read it)
     __shared__ uint64_t bar;
+    __shared__ uint64_t bar_tail;        // completion of the weight-gradient MMAs left in flight behind each stage's commit
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t tail_phase = 0;
 
     stage_all_weights<SPLIT>(smem, p, mask32, tid, kThreadsDec);
     float* small_grad = reinterpret_cast<float*>(smem + off_small<SPLIT>());
     if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);
-    if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_fence_init(); }
+    if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_init(&bar_tail, 1); umma::mbar_fence_init(); }
     umma::fence_async_smem();
     umma::tc_fence_before();
     __syncthreads();
@@ -175,15 +177,22 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
                 umma::mma_bf16(tmem + col, umma::desc_kmajor(dzlo_tile, dzlo_k + k), umma::desc_mnmajor(w_hi, k), idesc, 1);
         }
     };
-    // dW += dz^T B over the 128 rows of the tile (8 k-steps); `first` = first tile of this CTA.  In SPLIT
-    // mode the dz operand is compensated (dz_hi + dz_lo: `a_lo` = the lo tile, or the packed lo columns);
-    // the activation operand B stays bf16 (its lo part is gone by now).
-    auto wgrad = [&](int col, uint32_t a_tile, uint32_t a_lo, uint32_t b_tile_plus_off, uint32_t idesc, bool first) {
+    // dW += dz^T B over the 128 rows of the tile (8 k-steps), one operand part at a time; `init` = this is the first
+    // MMA group ever issued into that accumulator (first tile of the CTA, first part).  In SPLIT mode the dz operand
+    // is compensated (dz_hi + dz_lo = two parts); the activation operand B stays bf16 (its lo part is gone by now).
+    //
+    // Scheduling: a stage's epilogue needs only its input-gradient GEMM, so that one is committed first and the
+    // weight-gradient GEMMs are issued BEHIND the commit: they execute while the CTA runs the epilogue (ncu showed
+    // ~45 % of this kernel waiting for, or issuing, M = 64 weight-gradient MMAs when they sat in front of the commit).
+    // A part may be deferred like that only if the epilogue of its own stage does not overwrite a tile it reads
+    // (the next stage's commit covers every earlier MMA); the tile ends with a commit + wait on `bar_tail`.
+    auto wgrad_part = [&](int col, uint32_t a_tile, uint32_t b_tile_plus_off, uint32_t idesc, bool init) {
         for (int k = 0; k < 8; ++k)
-            umma::mma_bf16(tmem + col, umma::desc_mnmajor(a_tile, k), umma::desc_mnmajor(b_tile_plus_off, k), idesc, (!first) || k > 0);
-        if (SPLIT)
-            for (int k = 0; k < 8; ++k)
-                umma::mma_bf16(tmem + col, umma::desc_mnmajor(a_lo, k), umma::desc_mnmajor(b_tile_plus_off, k), idesc, 1);
+            umma::mma_bf16(tmem + col, umma::desc_mnmajor(a_tile, k), umma::desc_mnmajor(b_tile_plus_off, k), idesc, (!init) || k > 0);
+    };
+    auto wgrad = [&](int col, uint32_t a_tile, uint32_t a_lo, uint32_t b_tile_plus_off, uint32_t idesc, bool first) {
+        wgrad_part(col, a_tile, b_tile_plus_off, idesc, first);
+        if (SPLIT) wgrad_part(col, a_lo, b_tile_plus_off, idesc, false);
     };
     // transposed narrow layers (dW^T += A^T dz): the compensated operand is B
     auto wgrad_t = [&](int col, uint32_t a_tile, uint32_t b_hi, uint32_t b_lo, uint32_t idesc, bool first) {
@@ -290,8 +299,10 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         // ---- B2: dA3 = dz5 W4 ; dW4 += dz5^T a3
         if (tid == 0) {
             dgrad(cDb, ag4, 0, adzlo, 0, aW4, aW4l, 4, idg64);
-            wgrad(cGW4, ag4, adzlo, aa3, idw64, first);
+            // the epilogue overwrites the dz lo tile: its part goes in front of the commit, the hi part behind it
+            if (SPLIT) wgrad_part(cGW4, adzlo, aa3, idw64, first);
             umma::mma_commit(&bar);
+            wgrad_part(cGW4, ag4, aa3, idw64, SPLIT ? false : first);
         }
         c.wait_mma();
         mul_inplace(cDb, T.g3, Tdzlo, nullptr);                  // dz4
@@ -299,9 +310,9 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         // ---- B3: d[x2] = dz4 W3 ; dW3 += dz4^T [H[32:64] | SH] ; db3
         if (tid == 0) {
             dgrad(cDa, ag3, 0, adzlo, 0, aW3, aW3l, 4, idg64);
-            wgrad(cGW3a, ag3, adzlo, aH + 64, idw32, first);
-            wgrad(cGW3b, ag3, adzlo, aA0 + 64, idw16, first);
             umma::mma_commit(&bar);
+            wgrad(cGW3a, ag3, adzlo, aH + 64, idw32, first);        // behind the commit: the epilogue writes dH only
+            wgrad(cGW3b, ag3, adzlo, aA0 + 64, idw16, first);
         }
         c.wait_mma();
         store_quarter(cDa, Tdz, Tdhlo, 4, acc_b2 + 8);           // dH[32:64]
@@ -360,8 +371,8 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         // ---- B4: dA1 = dH W2 ; dW2 += dH^T a1 ; db2
         if (tid == 0) {
             dgrad(cDb, adz, 0, adhlo, 0, aW2, aW2l, 4, idg64);
-            wgrad(cGW2, adz, adhlo, aa1, idw64, first);
             umma::mma_commit(&bar);
+            wgrad(cGW2, adz, adhlo, aa1, idw64, first);             // behind the commit: the epilogue writes g1 / the dz lo tile
         }
         c.wait_mma();
         mul_inplace(cDb, T.g1, Tdzlo, nullptr);                  // dz1
@@ -369,8 +380,9 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         // ---- B5: dx = dz1 W1 (32 columns) ; dW1 += dz1^T x ; db1
         if (tid == 0) {
             dgrad(cDa, ag1, 0, adzlo, 0, aW1, aW1 + 64, 4, idg32);
-            wgrad(cGW1, ag1, adzlo, aA0, idw48, first);             // N = 48: x (32) | SH (16); column 32 -> d/d b1
             umma::mma_commit(&bar);
+            wgrad(cGW1, ag1, adzlo, aA0, idw48, first);             // N = 48: x (32) | SH (16); column 32 -> d/d b1
+            umma::mma_commit(&bar_tail);                            // everything this tile issued
         }
         c.wait_mma();
         umma::tmem_ld8(tmem + cDa + lane_addr + 8 * cg, v);     // d/d x, columns 8 cg .. 8 cg + 7 = levels 4 cg .. 4 cg + 3
@@ -388,8 +400,10 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
                 for (int l = 0; l < 4; ++l) dst[(size_t)(4 * cg + l) * level_stride] = make_float2(v[2 * l], v[2 * l + 1]);
             }
         }
-        // every MMA of this tile has completed (the last commit covers all earlier ones), so the
-        // next tile may overwrite the operand tiles
+        // the next tile overwrites the operand tiles the trailing weight-gradient MMAs read: wait for them
+        umma::mbar_wait(&bar_tail, tail_phase);
+        tail_phase ^= 1u;
+        umma::tc_fence_after();
         first = false;
     }
 
