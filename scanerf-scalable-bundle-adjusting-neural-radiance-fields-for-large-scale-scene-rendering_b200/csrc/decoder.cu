@@ -132,7 +132,6 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     uint32_t tail_phase = 0;
 
     stage_all_weights<SPLIT>(smem, p, mask32, tid, kThreadsDec);
-    float* small_grad = reinterpret_cast<float*>(smem + off_small<SPLIT>());
     if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);
     if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_init(&bar_tail, 1); umma::mbar_fence_init(); }
     umma::fence_async_smem();
@@ -152,9 +151,11 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     // = 0.28125 in every live row: column 32 of dW1 (N widened to 48) and column 0 of the SH part of dW3 are
     // c0 * sum_n dz_n, the flush divides by c0.  Layers 2 and 4 (inputs a1 / a3 have no constant column) are summed
     // per thread in fp32 registers over all the tiles of this CTA and reduced once at the end.
-    float acc_b2[16], acc_b4[16];
+    float acc_b2[16], acc_b4[16], acc_small[10];       // acc_small: sigma, diffuse3, tint3, specular3 biases (column group 0)
 #pragma unroll
     for (int j = 0; j < 16; ++j) { acc_b2[j] = 0.0f; acc_b4[j] = 0.0f; }
+#pragma unroll
+    for (int j = 0; j < 10; ++j) acc_small[j] = 0.0f;
     const uint32_t aW1 = umma::smem_u32(smem + oW1), aW2 = umma::smem_u32(smem + oW2), aW3 = umma::smem_u32(smem + oW3),
                    aW4 = umma::smem_u32(smem + oW4), aWh = umma::smem_u32(smem + oWh), aW5 = umma::smem_u32(smem + oW5);
     // input-gradient GEMMs: A K-major (dz rows), B MN-major (weight tile: rows = K = out, cols = N = in)
@@ -274,14 +275,9 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
             store8_hl<SPLIT>(Tdz, 1, Tdz, 5, row, dzh + 8);
             store8_hl<SPLIT>(Tdz, 2, Tdz, 6, row, dzs);
             store8_hl<SPLIT>(Tdz, 3, Tdz, 7, row, dzs + 8);
-            // bias gradients of the narrow layers: warp reduction, one shared atomic per warp
+            // bias gradients of the narrow layers: summed per thread over the CTA's tiles, reduced once at the end
 #pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                float t = j < 7 ? dzh[j] : dzs[j - 7];
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
-                if (lane == 0) atomicAdd(small_grad + j, t);
-            }
+            for (int j = 0; j < 10; ++j) acc_small[j] += j < 7 ? dzh[j] : dzs[j - 7];
         }
         c.sync_operands();
         // ---- B1: dA4 = dz_spec W5 ; dH[0:32] = dz_heads Wh ; dW5^T += a4^T dz_spec ; dWh^T += H^T dz_heads
@@ -316,6 +312,14 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         }
         c.wait_mma();
         store_quarter(cDa, Tdz, Tdhlo, 4, acc_b2 + 8);           // dH[32:64]
+        c.sync_operands();
+        // ---- B4: dA1 = dH W2 ; dW2 += dH^T a1 ; db2
+        if (tid == 0) {
+            dgrad(cDb, adz, 0, adhlo, 0, aW2, aW2l, 4, idg64);
+            umma::mma_commit(&bar);
+            wgrad(cGW2, adz, adhlo, aa1, idw64, first);             // behind the commit: the epilogue writes g1 / the dz lo tile
+        }
+        // (runs while the B4 MMAs execute: d[SH] sits in accumulator columns cDa + 32.. until B5 overwrites them)
         if (grad_rays_d != nullptr && cg == 3) {                 // d/d(ray direction) through the SH encoding (one thread per row)
             float dsh[16];
             umma::tmem_ld16(tmem + cDa + lane_addr + 32, dsh);
@@ -366,13 +370,6 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
                 atomicAdd(grad_rays_d + 3 * (size_t)ray + 1, gy);
                 atomicAdd(grad_rays_d + 3 * (size_t)ray + 2, gz);
             }
-        }
-        c.sync_operands();
-        // ---- B4: dA1 = dH W2 ; dW2 += dH^T a1 ; db2
-        if (tid == 0) {
-            dgrad(cDb, adz, 0, adhlo, 0, aW2, aW2l, 4, idg64);
-            umma::mma_commit(&bar);
-            wgrad(cGW2, adz, adhlo, aa1, idw64, first);             // behind the commit: the epilogue writes g1 / the dz lo tile
         }
         c.wait_mma();
         mul_inplace(cDb, T.g1, Tdzlo, nullptr);                  // dz1
@@ -463,10 +460,17 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
             atomicAdd(gp.b4 + 16 * cg + j, t4);
         }
     }
-    __syncthreads();
-    if (tid == 0) {
-        atomicAdd(gp.bs, small_grad[0]);
-        for (int o = 0; o < 3; ++o) { atomicAdd(gp.bd + o, small_grad[1 + o]); atomicAdd(gp.bt + o, small_grad[4 + o]); atomicAdd(gp.b5 + o, small_grad[7 + o]); }
+    if (cg == 0) {
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            float t = acc_small[j];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+            if (lane == 0 && !first) {
+                float* dst = j == 0 ? gp.bs : (j < 4 ? gp.bd + (j - 1) : (j < 7 ? gp.bt + (j - 4) : gp.b5 + (j - 7)));
+                atomicAdd(dst, t);
+            }
+        }
     }
     umma::tc_fence_before();
     __syncthreads();
