@@ -51,17 +51,19 @@ void snrf_hash_set_levels_per_block(int lpb);
  * (samples = o + z d), :394-411 (contract_fore / contract_bg) and hashgrid/PyHashGridBG.py:9-30 with
  * hashgrid/src/hashgrid_bg_kernel.cu:106-275, plus their autograd.
  * mode 0: points[N,3] already contracted; mode 1 (fore) / 2 (background): sample n = rays_o[n/S] + z_vals[n] rays_d[n/S],
- * contracted w.r.t. the box (box_min, box_size: device float[3]).
+ * contracted w.r.t. the box (box_min, box_size: device float[3]); mode 3: rays [0, split) fore, rays [split, R) background
+ * (both render chains of a step in one launch: the table streams through L2 once).
  * -> out_lm [L][N] float2 (level-major), jac_lm [L][3][N] float2 = d out / d contracted point (NULL: not needed). */
 int snrf_field_encode_fwd(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
                           const float* box_min, const float* box_size, int mode, const float* table, const int* res,
-                          float* out_lm, float* jac_lm, const unsigned char* ray_valid, int N, int S, int L, int T, void* stream);
+                          float* out_lm, float* jac_lm, const unsigned char* ray_valid, int split, int N, int S, int L, int T,
+                          void* stream);
 /* grad_lm [L][N] float2, jac_lm from the forward (NULL: table gradient only).  ACCUMULATES grad_table [L,T,2] and
  * grad_rays_o / grad_rays_d [R,3] (modes 1, 2; either may be NULL) or grad_points [N,3] (mode 0). */
 int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
                           const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
                           const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points, float* grad_table,
-                          const unsigned char* ray_valid, int N, int S, int L, int T, void* stream);
+                          const unsigned char* ray_valid, int split, int N, int S, int L, int T, void* stream);
 /* tuning hook: log2 of the number of table index ranges the scatter walks per level (-1 = automatic) */
 void snrf_field_set_passes_log2(int bits);
 /* tuning hook: levels [0, n) merge equal-cell lanes of a warp before reducing (-1 = automatic, L / 2) */
@@ -107,12 +109,12 @@ int snrf_sample_insideout(const float* rays_o, const float* rays_d, int S, int S
  * diffuse, specular [R*S,3]; z_vals, dists [R,S]; rays_d [R,3] (|d| scales the step).
  * -> weights[R,S], trans[R,S] (transmittance before each sample; may be NULL in fwd),
  *    out[R,16] = depth, tint3, diffuse3, specular3 (= sum w tint*spec), l2_3 (= sum w spec^2),
- *    T_left, 2 pad.  infinity != 0: last step is 1e10.  ray_valid (optional, bytes [R]): rays with a 0 flag get
+ *    T_left, 2 pad.  infinity != 0: the last step of rays r >= inf_start is 1e10.  ray_valid (optional, bytes [R]): rays with a 0 flag get
  *    zero weights / outputs and T_left = 1 (the defaults HashGrid scatters back for rays it did not render). */
 int snrf_composite_fwd(const float* sigma, const float* tint, const float* diffuse, const float* specular,
                        int s_sigma, int s_tint, int s_diffuse, int s_specular,
                        const float* z_vals, const float* dists, const float* rays_d, const unsigned char* ray_valid,
-                       int R, int S, int infinity, float* weights, float* trans, float* out, void* stream);
+                       int R, int S, int infinity, int inf_start, float* weights, float* trans, float* out, void* stream);
 /* backward of the above: g_out[R,16] (same row layout; l2 columns act on specular only, the
  * weights inside l2 are detached as in the reference), g_weights[R,S] optional.  WRITES the
  * per-sample head gradients (strides gs_*) and grad_rays_d[R,3] (optional). */
@@ -120,7 +122,7 @@ int snrf_composite_bwd(const float* sigma, const float* tint, const float* diffu
                        int s_sigma, int s_tint, int s_diffuse, int s_specular,
                        const float* z_vals, const float* dists, const float* rays_d, const float* trans,
                        const float* g_out, const float* g_weights, const unsigned char* ray_valid, int R, int S, int infinity,
-                       float* g_sigma, float* g_tint, float* g_diffuse, float* g_specular,
+                       int inf_start, float* g_sigma, float* g_tint, float* g_diffuse, float* g_specular,
                        int gs_sigma, int gs_tint, int gs_diffuse, int gs_specular,
                        float* grad_rays_d, void* stream);
 

@@ -62,7 +62,7 @@ __device__ __forceinline__ float warp_incl_suffix_sum(float v, int lane)
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_fwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __restrict__ dists,
                      const float* __restrict__ rays_d, const unsigned char* __restrict__ ray_valid, int R, int S, int infinity,
-                     float* __restrict__ weights, float* __restrict__ trans, float* __restrict__ out)
+                     int inf_start, float* __restrict__ weights, float* __restrict__ trans, float* __restrict__ out)
 {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -76,6 +76,7 @@ composite_fwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
         }
         const f3 d = ld3(rays_d + 3 * (size_t)r);
         const float dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+        const bool inf = infinity != 0 && r >= inf_start;      // last step of this ray reaches to infinity (1e10)
         float carry = 1.0f;                 // product of beta over all previous chunks
         float acc[13];
 #pragma unroll
@@ -88,7 +89,7 @@ composite_fwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
             float beta = 1.0f, alpha = 0.0f;
             if (live) {
                 float delta = dists[n] * dn;
-                if (infinity && k == S - 1) delta = 1e10f;
+                if (inf && k == S - 1) delta = 1e10f;
                 alpha = 1.0f - expf(-in.sigma[n * in.s_sigma] * delta);
                 beta = 1.0f - alpha + 1e-6f;
             }
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_bwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __restrict__ dists,
                      const float* __restrict__ rays_d, const float* __restrict__ trans,
                      const float* __restrict__ g_out, const float* __restrict__ g_weights, const unsigned char* __restrict__ ray_valid,
-                     int R, int S, int infinity, HeadGrads g, float* __restrict__ grad_rays_d)
+                     int R, int S, int infinity, int inf_start, HeadGrads g, float* __restrict__ grad_rays_d)
 {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -148,6 +149,7 @@ composite_bwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
         }
         const f3 d = ld3(rays_d + 3 * (size_t)r);
         const float dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+        const bool inf = infinity != 0 && r >= inf_start;
         const float* go = g_out + (size_t)r * kOutStride;
         const float g_depth = go[0];
         const f3 g_ti = mk3(go[1], go[2], go[3]), g_di = mk3(go[4], go[5], go[6]), g_sp = mk3(go[7], go[8], go[9]);
@@ -165,7 +167,7 @@ composite_bwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
                 T = trans[n];
                 sig = in.sigma[n * in.s_sigma];
                 delta = dists[n] * dn;
-                if (infinity && k == S - 1) delta = 1e10f;
+                if (inf && k == S - 1) delta = 1e10f;
                 e = expf(-sig * delta);                     // 1 - alpha
                 w = (1.0f - e) * T;
                 const f3 ti = ld3(in.tint + n * in.s_tint);
@@ -191,7 +193,7 @@ composite_bwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
                 const float beta = e + 1e-6f;
                 const float g_alpha = G * T - after / beta;
                 g.sigma[n * g.s_sigma] = g_alpha * delta * e;
-                if (!(infinity && k == S - 1)) g_dn += g_alpha * sig * e * dists[n];
+                if (!(inf && k == S - 1)) g_dn += g_alpha * sig * e * dists[n];
             }
             suffix += __shfl_sync(0xffffffffu, incl, 0);
         }
@@ -216,12 +218,12 @@ inline int grid_rays(int R)
 SNRF_API int snrf_composite_fwd(const float* sigma, const float* tint, const float* diffuse, const float* specular,
                                 int s_sigma, int s_tint, int s_diffuse, int s_specular,
                                 const float* z_vals, const float* dists, const float* rays_d, const unsigned char* ray_valid,
-                                int R, int S, int infinity, float* weights, float* trans, float* out, void* stream)
+                                int R, int S, int infinity, int inf_start, float* weights, float* trans, float* out, void* stream)
 {
     SNRF_CHECK_ARG(S > 0, "snrf_composite_fwd: S must be positive");
     if (R <= 0) return 0;
     Heads in{sigma, tint, diffuse, specular, s_sigma, s_tint, s_diffuse, s_specular};
-    composite_fwd_kernel<<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, ray_valid, R, S, infinity, weights, trans, out);
+    composite_fwd_kernel<<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, ray_valid, R, S, infinity, inf_start, weights, trans, out);
     SNRF_RETURN_LAUNCH("snrf_composite_fwd");
 }
 
@@ -229,7 +231,7 @@ SNRF_API int snrf_composite_bwd(const float* sigma, const float* tint, const flo
                                 int s_sigma, int s_tint, int s_diffuse, int s_specular,
                                 const float* z_vals, const float* dists, const float* rays_d, const float* trans,
                                 const float* g_out, const float* g_weights, const unsigned char* ray_valid, int R, int S, int infinity,
-                                float* g_sigma, float* g_tint, float* g_diffuse, float* g_specular,
+                                int inf_start, float* g_sigma, float* g_tint, float* g_diffuse, float* g_specular,
                                 int gs_sigma, int gs_tint, int gs_diffuse, int gs_specular,
                                 float* grad_rays_d, void* stream)
 {
@@ -237,6 +239,6 @@ SNRF_API int snrf_composite_bwd(const float* sigma, const float* tint, const flo
     if (R <= 0) return 0;
     Heads in{sigma, tint, diffuse, specular, s_sigma, s_tint, s_diffuse, s_specular};
     HeadGrads g{g_sigma, g_tint, g_diffuse, g_specular, gs_sigma, gs_tint, gs_diffuse, gs_specular};
-    composite_bwd_kernel<<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, trans, g_out, g_weights, ray_valid, R, S, infinity, g, grad_rays_d);
+    composite_bwd_kernel<<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, trans, g_out, g_weights, ray_valid, R, S, infinity, inf_start, g, grad_rays_d);
     SNRF_RETURN_LAUNCH("snrf_composite_bwd");
 }

@@ -283,14 +283,13 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         // ---- B1: dA4 = dz_spec W5 ; dH[0:32] = dz_heads Wh ; dW5^T += a4^T dz_spec ; dWh^T += H^T dz_heads
         if (tid == 0) {
             dgrad(cDa, adz, 1, adz, 3, aW5, aW5l, 1, idg64);
-            dgrad(cDb, adz, 0, adz, 2, aWh, aWh + 64, 1, idg32);
-            wgrad_t(cGW5T, aa4, adz + 32, adz + 96, idw16, first);
-            wgrad_t(cGWhT, aH, adz, adz + 64, idw16, first);
+            dgrad(cDc, adz, 0, adz, 2, aWh, aWh + 64, 1, idg32);     // dH[0:32] stays in TMEM until the B2 epilogue
             umma::mma_commit(&bar);
+            wgrad_t(cGW5T, aa4, adz + 32, adz + 96, idw16, first);  // behind the commit: this epilogue writes g4 / dz lo only
+            wgrad_t(cGWhT, aH, adz, adz + 64, idw16, first);
         }
         c.wait_mma();
         mul_inplace(cDa, T.g4, Tdzlo, acc_b4);                   // dz5 (+ its column sums = d/d b4)
-        store_quarter(cDb, Tdz, Tdhlo, 0, acc_b2);               // dH[0:32] -> dz2 tile columns 0..31 (over the consumed dz_heads/spec)
         c.sync_operands();
         // ---- B2: dA3 = dz5 W4 ; dW4 += dz5^T a3
         if (tid == 0) {
@@ -300,7 +299,8 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
             umma::mma_commit(&bar);
             wgrad_part(cGW4, ag4, aa3, idw64, SPLIT ? false : first);
         }
-        c.wait_mma();
+        c.wait_mma();                                            // (covers the B1 weight-gradient MMAs that read Tdz and a4)
+        store_quarter(cDc, Tdz, Tdhlo, 0, acc_b2);               // dH[0:32] -> dz2 tile columns 0..31 (over the consumed dz_heads/spec)
         mul_inplace(cDb, T.g3, Tdzlo, nullptr);                  // dz4
         c.sync_operands();
         // ---- B3: d[x2] = dz4 W3 ; dW3 += dz4^T [H[32:64] | SH] ; db3

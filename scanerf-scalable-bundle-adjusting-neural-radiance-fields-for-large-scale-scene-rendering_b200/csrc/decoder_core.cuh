@@ -61,6 +61,7 @@ constexpr int cDa = 0, cDb = 64, cDh = 128;
 // (cGW1 is 48 wide: x (32) | SH (16) -- its column 32 = SH_0 carries the bias gradient of layer 1, as column 0 of
 // cGW3b does for layer 3)
 constexpr int cGW1 = 144, cGW2 = 192, cGW3a = 256, cGW3b = 288, cGW4 = 304, cGWhT = 368, cGW5T = 384;   // ends at 400
+constexpr int cDc = 416;       // backward: dH[0:32], parked until the B2 epilogue (32 columns)
 
 __device__ __forceinline__ float gauss_act(float v) { return exp2f(v * v * kGaussLog2); }
 __device__ __forceinline__ float sigmoidf(float v) { return 1.0f / (1.0f + __expf(-v)); }

@@ -24,7 +24,7 @@ using namespace hashgrid;
 namespace {
 
 constexpr int kThreads = 256;
-enum Contract { kNone = 0, kFore = 1, kBack = 2 };
+enum Contract { kNone = 0, kRays = 1 };      // kRays: samples on rays; rays [0, ray_split) use the fore map, the rest the background map
 
 struct Pt {
     f3 c;          // contracted point in [-2,2]^3
@@ -43,13 +43,12 @@ __device__ __forceinline__ f3 sample_pos(f3 o, f3 d, float z)
 
 // x -> contracted coordinates.  fore: c = (x - min) / size * 4 - 2 (hashgrid/__init__.py:394-395);
 // back: u = that, n = |u|_inf, c = u (2 - 1/n) / n (:397-411).
-template <int MODE>
-__device__ __forceinline__ Pt contract(f3 x, f3 bmin, f3 bsize)
+__device__ __forceinline__ Pt contract(bool back, f3 x, f3 bmin, f3 bsize)
 {
     Pt p;
     const f3 u = mk3((x.x - bmin.x) / bsize.x * 4.0f - 2.0f, (x.y - bmin.y) / bsize.y * 4.0f - 2.0f, (x.z - bmin.z) / bsize.z * 4.0f - 2.0f);
     const f3 a = mk3(4.0f / bsize.x, 4.0f / bsize.y, 4.0f / bsize.z);
-    if (MODE == kFore) {
+    if (!back) {
         p.c = u; p.jd = a; p.u = u; p.fp = 0.0f; p.k = 0;
     } else {
         const float ax = fabsf(u.x), ay = fabsf(u.y), az = fabsf(u.z);
@@ -71,11 +70,10 @@ __device__ __forceinline__ Pt contract(f3 x, f3 bmin, f3 bsize)
 }
 
 // g_c (gradient w.r.t. the contracted point) -> gradient w.r.t. the world-space sample
-template <int MODE>
-__device__ __forceinline__ f3 contract_bwd(const Pt& p, f3 gc)
+__device__ __forceinline__ f3 contract_bwd(bool back, const Pt& p, f3 gc)
 {
     f3 gx = gc * p.jd;
-    if (MODE == kBack) {
+    if (back) {
         const float s = dot3(gc, p.u) * p.fp;          // rank-one term: (g . u) f'(n) dn/du_k a_k on axis k
         if (p.k == 0) gx.x += s; else if (p.k == 1) gx.y += s; else gx.z += s;
     }
@@ -87,7 +85,7 @@ __global__ void __launch_bounds__(kThreads)
 field_fwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_vals,
                  const float* __restrict__ points, const float* __restrict__ bmin_p, const float* __restrict__ bsize_p,
                  const float2* __restrict__ table, const int* __restrict__ res, float2* __restrict__ out, float2* __restrict__ jac,
-                 const unsigned char* __restrict__ ray_valid, int N, int S, int L, uint32_t T, int lpb)
+                 const unsigned char* __restrict__ ray_valid, int ray_split, int N, int S, int L, uint32_t T, int lpb)
 {
     const uint32_t mask = T - 1u;
     f3 bmin = mk3(0, 0, 0), bsize = mk3(1, 1, 1);
@@ -100,7 +98,7 @@ field_fwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
         } else {
             const int r = n / S;
             if (ray_valid != nullptr && !ray_valid[r]) continue;        // masked-out ray: its rows are never read
-            c = contract<MODE>(sample_pos(ld3(rays_o + 3 * (size_t)r), ld3(rays_d + 3 * (size_t)r), z_vals[n]), bmin, bsize).c;
+            c = contract(r >= ray_split, sample_pos(ld3(rays_o + 3 * (size_t)r), ld3(rays_d + 3 * (size_t)r), z_vals[n]), bmin, bsize).c;
         }
         for (int l = l_begin; l < l_end; ++l) {
             const Cell cell = locate_bg(c, res + 3 * l);
@@ -145,8 +143,8 @@ field_bwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
                  const float* __restrict__ points, const float* __restrict__ bmin_p, const float* __restrict__ bsize_p,
                  const int* __restrict__ res, const float2* __restrict__ grad, const float2* __restrict__ jac,
                  float* __restrict__ grad_o, float* __restrict__ grad_d, float* __restrict__ grad_points, float2* __restrict__ grad_table,
-                 const unsigned char* __restrict__ ray_valid, int N, int S, int L, uint32_t T, int pass_bits, int range_shift,
-                 int aggregate_levels)
+                 const unsigned char* __restrict__ ray_valid, int ray_split, int N, int S, int L, uint32_t T, int pass_bits,
+                 int range_shift, int aggregate_levels)
 {
     const uint32_t mask = T - 1u;
     const int lane = threadIdx.x & 31;
@@ -170,7 +168,7 @@ field_bwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
             r = live ? n / S : -1;
             z = live ? z_vals[n] : 0.0f;
             const f3 x = live ? sample_pos(ld3(rays_o + 3 * (size_t)r), ld3(rays_d + 3 * (size_t)r), z) : mk3(0, 0, 0);
-            p = contract<MODE>(x, bmin, bsize);
+            p = contract(r >= ray_split, x, bmin, bsize);
         }
         const float2 g = live ? __ldg(grad + (size_t)l * N + n) : make_float2(0.f, 0.f);
         const Cell cell = locate_bg(p.c, res + 3 * l);
@@ -235,7 +233,7 @@ field_bwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
                     atomicAdd(grad_points + 3 * (size_t)n + 2, gc.z);
                 }
             } else {
-                f3 gx = live ? contract_bwd<MODE>(p, gc) : mk3(0, 0, 0);
+                f3 gx = live ? contract_bwd(r >= ray_split, p, gc) : mk3(0, 0, 0);
                 f3 gz = gx * z;
                 // all lanes of the warp usually belong to one ray: reduce first
                 const int r0 = __shfl_sync(0xffffffffu, r, 0);
@@ -299,13 +297,15 @@ SNRF_API void snrf_field_set_aggregate_levels(int n) { g_aggregate_override = n;
 
 // mode 0: `points` [N,3] are already contracted (rays_o / rays_d / z_vals unused);
 // mode 1 / 2: sample n = rays_o[n / S] + z_vals[n] * rays_d[n / S], contracted with the fore / background map of the
-// box (box_min, box_size: device float[3], the DOUBLED tile box of HashGrid).
+// box (box_min, box_size: device float[3], the DOUBLED tile box of HashGrid); mode 3: rays [0, split) fore, the rest
+// background -- both render chains of a step in one launch, so that the table is streamed through L2 once.
 SNRF_API int snrf_field_encode_fwd(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
                                    const float* box_min, const float* box_size, int mode, const float* table, const int* res,
-                                   float* out_lm, float* jac_lm, const unsigned char* ray_valid, int N, int S, int L, int T, void* stream)
+                                   float* out_lm, float* jac_lm, const unsigned char* ray_valid, int split, int N, int S, int L, int T,
+                                   void* stream)
 {
     SNRF_CHECK_ARG(N >= 0 && L > 0 && T > 0 && (T & (T - 1)) == 0, "snrf_field_encode_fwd: T must be a power of two (N=%d L=%d T=%d)", N, L, T);
-    SNRF_CHECK_ARG(mode >= 0 && mode <= 2 && (mode == 0 ? points != nullptr : (rays_o && rays_d && z_vals && box_min && box_size && S > 0)),
+    SNRF_CHECK_ARG(mode >= 0 && mode <= 3 && (mode == 0 ? points != nullptr : (rays_o && rays_d && z_vals && box_min && box_size && S > 0)),
                    "snrf_field_encode_fwd: inconsistent arguments for mode %d", mode);
     if (N == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
@@ -315,10 +315,11 @@ SNRF_API int snrf_field_encode_fwd(const float* rays_o, const float* rays_d, con
     float2 *o = (float2*)out_lm, *j = (float2*)jac_lm;
 #define SNRF_FWD(MODE)                                                                                                                   \
     do {                                                                                                                                 \
-        if (j) field_fwd_kernel<MODE, true><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, tb, res, o, j, ray_valid, N, S, L, (uint32_t)T, lpb); \
-        else   field_fwd_kernel<MODE, false><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, tb, res, o, j, ray_valid, N, S, L, (uint32_t)T, lpb); \
+        if (j) field_fwd_kernel<MODE, true><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, tb, res, o, j, ray_valid, ray_split, N, S, L, (uint32_t)T, lpb); \
+        else   field_fwd_kernel<MODE, false><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, tb, res, o, j, ray_valid, ray_split, N, S, L, (uint32_t)T, lpb); \
     } while (0)
-    if (mode == 0) SNRF_FWD(kNone); else if (mode == 1) SNRF_FWD(kFore); else SNRF_FWD(kBack);
+    const int ray_split = mode == 1 ? 0x7fffffff : (mode == 2 ? 0 : split);
+    if (mode == 0) SNRF_FWD(kNone); else SNRF_FWD(kRays);
 #undef SNRF_FWD
     SNRF_RETURN_LAUNCH("snrf_field_encode_fwd");
 }
@@ -328,10 +329,10 @@ SNRF_API int snrf_field_encode_fwd(const float* rays_o, const float* rays_d, con
 SNRF_API int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
                                    const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
                                    const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points, float* grad_table,
-                                   const unsigned char* ray_valid, int N, int S, int L, int T, void* stream)
+                                   const unsigned char* ray_valid, int split, int N, int S, int L, int T, void* stream)
 {
     SNRF_CHECK_ARG(N >= 0 && L > 0 && T > 0 && (T & (T - 1)) == 0, "snrf_field_encode_bwd: T must be a power of two (N=%d L=%d T=%d)", N, L, T);
-    SNRF_CHECK_ARG(mode >= 0 && mode <= 2 && (mode == 0 ? points != nullptr : (rays_o && rays_d && z_vals && box_min && box_size && S > 0)),
+    SNRF_CHECK_ARG(mode >= 0 && mode <= 3 && (mode == 0 ? points != nullptr : (rays_o && rays_d && z_vals && box_min && box_size && S > 0)),
                    "snrf_field_encode_bwd: inconsistent arguments for mode %d", mode);
     SNRF_CHECK_ARG(grad_table != nullptr && grad_lm != nullptr, "snrf_field_encode_bwd: grad_lm and grad_table are required");
     if (N == 0) return 0;
@@ -345,8 +346,9 @@ SNRF_API int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, con
     const float2 *g = (const float2*)grad_lm, *j = (const float2*)jac_lm;
     float2* gt = (float2*)grad_table;
     const int agg = g_aggregate_override >= 0 ? g_aggregate_override : L / 2;
-#define SNRF_BWD(MODE) field_bwd_kernel<MODE><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, res, g, j, grad_rays_o, grad_rays_d, grad_points, gt, ray_valid, N, S, L, (uint32_t)T, pass_bits, range_shift, agg)
-    if (mode == 0) SNRF_BWD(kNone); else if (mode == 1) SNRF_BWD(kFore); else SNRF_BWD(kBack);
+#define SNRF_BWD(MODE) field_bwd_kernel<MODE><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, res, g, j, grad_rays_o, grad_rays_d, grad_points, gt, ray_valid, ray_split, N, S, L, (uint32_t)T, pass_bits, range_shift, agg)
+    const int ray_split = mode == 1 ? 0x7fffffff : (mode == 2 ? 0 : split);
+    if (mode == 0) SNRF_BWD(kNone); else SNRF_BWD(kRays);
 #undef SNRF_BWD
     SNRF_RETURN_LAUNCH("snrf_field_encode_bwd");
 }

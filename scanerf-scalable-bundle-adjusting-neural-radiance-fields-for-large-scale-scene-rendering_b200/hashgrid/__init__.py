@@ -292,6 +292,36 @@ class HashGrid(nn.Module):
         heads = _field.decoder_apply(feats, rays_d, mask32, S, params, valid)
         return _render.composite_packed(heads, z_vals, dists, rays_d, infinity, train=(mode is TRAIN), valid=valid)
 
+    def render_fore_bg_rays(self, rays_o, rays_d, num_sample, decoder, mode, occlusion_mask=None, global_step=0,
+                            invalid_underground=True):
+        """render_fore_rays + render_bg_rays ("IZ" background, same sample count) as ONE batch of 2R rays through
+        every kernel: rays [0, R) are the foreground chain, rays [R, 2R) the background chain (the encode kernel
+        switches the contraction, the compositing kernel the infinite last step, at ray R).  Halves the launches
+        and -- the point -- streams the hash table through L2 once per step instead of once per chain.
+        Returns (fore dict, background dict) with the keys of the two separate calls, or None when the fused path
+        is not available (non-stock decoder)."""
+        params = self._fused_ready(decoder)
+        if params is None:
+            return None
+        R = rays_o.shape[0]
+        z_f, d_f = self.samplePoints(rays_o, rays_d, num_sample)
+        v_f = torch.all(z_f != -1, dim=-1)
+        z_b, d_b, v_b = self.inverse_z_sampling(rays_o, rays_d, num_sample, invalid_underground)
+        if occlusion_mask is not None:
+            v_f, v_b = v_f & occlusion_mask[..., 0], v_b & occlusion_mask[..., 0]
+        o2, d2 = torch.cat([rays_o, rays_o], 0), torch.cat([rays_d, rays_d], 0)
+        z2, dist2, valid2 = torch.cat([z_f, z_b], 0), torch.cat([d_f, d_b], 0), torch.cat([v_f, v_b], 0)
+        mask32 = self.weight_feature(global_step).repeat_interleave(2)
+        feats = _field.field_encode(o2, d2, z2, self.HE.features, self.HE.resolution, self.min_bbox, self.bbox_size, 3, valid2, R)
+        heads = _field.decoder_apply(feats, d2, mask32, num_sample, params, valid2)
+        row, weights = _render.CompositePackedFn.apply(heads, z2, dist2, d2, R, valid2)      # rays >= R end at infinity
+        train = mode is TRAIN
+        fg = _render._finish(row[:R], weights[:R], train, v_f)
+        bg = _render._finish(row[R:], weights[R:], train, v_b)
+        fg.update({"pred_color": fg["rgb"], "pred_depth": fg["depth"], "T_left": fg["T_left"][:, None], "fore_valid": v_f})
+        bg.update({"T_left": bg["T_left"][:, None], "valid": v_b})
+        return fg, bg
+
     def render_fore_rays(self, rays_o, rays_d, num_sample, decoder, mode, occlusion_mask=None, infinity=False, **kwargs):
         z_vals, dists = self.samplePoints(rays_o, rays_d, num_sample)
         valid = torch.all(z_vals != -1, dim=-1)

@@ -104,7 +104,7 @@ class FieldEncodeFn(torch.autograd.Function):
     temporary) and returns d/d rays_o, d/d rays_d."""
 
     @staticmethod
-    def forward(ctx, rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid):
+    def forward(ctx, rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid, split=0):
         R, S = z_vals.shape
         N, L, T = R * S, int(features.shape[0]), int(features.shape[1])
         rays_o, rays_d, z_vals = rays_o.contiguous(), rays_d.contiguous(), z_vals.contiguous()
@@ -117,10 +117,10 @@ class FieldEncodeFn(torch.autograd.Function):
         feats = features.detach().contiguous()
         box_min, box_size = box_min.contiguous(), box_size.contiguous()
         rc = capi.lib().snrf_field_encode_fwd(ptr(rays_o), ptr(rays_d), ptr(z_vals), c_void_p(0), ptr(box_min), ptr(box_size),
-                                              c_int(int(mode)), ptr(feats), ptr(resolution), ptr(out), ptr(jac), ptr(valid), c_int(N), c_int(S),
+                                              c_int(int(mode)), ptr(feats), ptr(resolution), ptr(out), ptr(jac), ptr(valid), c_int(int(split)), c_int(N), c_int(S),
                                               c_int(L), c_int(T), capi.stream())
         capi.check(rc, "snrf_field_encode_fwd")
-        ctx.mode, ctx.dims = int(mode), (N, S, L, T)
+        ctx.mode, ctx.split, ctx.dims = int(mode), int(split), (N, S, L, T)
         ctx.features = features
         ctx.save_for_backward(rays_o, rays_d, z_vals, resolution, box_min, box_size, jac if jac is not None else out.new_empty(0),
                               valid if valid is not None else out.new_empty(0))
@@ -144,12 +144,13 @@ class FieldEncodeFn(torch.autograd.Function):
             g_table = torch.zeros_like(features)
         rc = capi.lib().snrf_field_encode_bwd(ptr(rays_o), ptr(rays_d), ptr(z_vals), c_void_p(0), ptr(box_min), ptr(box_size),
                                               c_int(ctx.mode), ptr(resolution), ptr(g_out), ptr(jac) if ctx.has_jac else c_void_p(0),
-                                              ptr(g_o), ptr(g_d), c_void_p(0), ptr(g_table), ptr(valid) if ctx.has_valid else c_void_p(0), c_int(N), c_int(S), c_int(L), c_int(T),
+                                              ptr(g_o), ptr(g_d), c_void_p(0), ptr(g_table), ptr(valid) if ctx.has_valid else c_void_p(0), c_int(ctx.split), c_int(N), c_int(S), c_int(L), c_int(T),
                                               capi.stream())
         capi.check(rc, "snrf_field_encode_bwd")
-        return g_o, g_d, None, (None if direct else g_table), None, None, None, None, None
+        return g_o, g_d, None, (None if direct else g_table), None, None, None, None, None, None
 
 
-def field_encode(rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid=None):
-    """valid (bool [R] or None): rays flagged False are skipped (their feature rows are left unwritten)."""
-    return FieldEncodeFn.apply(rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid)
+def field_encode(rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid=None, split=0):
+    """valid (bool [R] or None): rays flagged False are skipped (their feature rows are left unwritten).
+    mode 3: rays [0, split) are contracted with the fore map, rays [split, R) with the background map."""
+    return FieldEncodeFn.apply(rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid, split)

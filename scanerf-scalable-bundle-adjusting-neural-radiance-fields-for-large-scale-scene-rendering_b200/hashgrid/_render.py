@@ -35,7 +35,7 @@ class CompositeFn(torch.autograd.Function):
         rc = capi.lib().snrf_composite_fwd(ptr(sigma), ptr(tint), ptr(diffuse), ptr(specular),
                                            c_int(1), c_int(3), c_int(3), c_int(3),
                                            ptr(z_vals), ptr(dists), ptr(rays_d), c_void_p(0), c_int(R), c_int(S),
-                                           c_int(int(bool(infinity))), ptr(weights), ptr(trans), ptr(row), capi.stream())
+                                           c_int(int(bool(infinity))), c_int(0), ptr(weights), ptr(trans), ptr(row), capi.stream())
         capi.check(rc, "snrf_composite_fwd")
         ctx.save_for_backward(sigma, tint, diffuse, specular, z_vals, dists, rays_d, trans)
         ctx.infinity = bool(infinity)
@@ -56,7 +56,7 @@ class CompositeFn(torch.autograd.Function):
                                            c_int(1), c_int(3), c_int(3), c_int(3),
                                            ptr(z_vals), ptr(dists), ptr(rays_d), ptr(trans), ptr(g_row),
                                            ptr(gw) if gw is not None else c_void_p(0), c_void_p(0),
-                                           c_int(R), c_int(S), c_int(int(ctx.infinity)),
+                                           c_int(R), c_int(S), c_int(int(ctx.infinity)), c_int(0),
                                            ptr(g_sigma), ptr(g_tint), ptr(g_diffuse), ptr(g_specular),
                                            c_int(1), c_int(3), c_int(3), c_int(3),
                                            ptr(g_d) if g_d is not None else c_void_p(0), capi.stream())
@@ -72,7 +72,9 @@ class CompositePackedFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, heads, z_vals, dists, rays_d, infinity, valid):
+        # infinity: False / True (all rays) or an int r0: the rays r >= r0 end at infinity (joint fore + background batch)
         R, S = z_vals.shape
+        inf_flag, inf_start = (int(infinity), 0) if isinstance(infinity, bool) else (1, int(infinity))
         f32 = torch.float32
         heads, z_vals, dists, rays_d = heads.contiguous(), z_vals.contiguous(), dists.contiguous(), rays_d.contiguous()
         weights = torch.empty(R, S, dtype=f32, device=z_vals.device)
@@ -82,10 +84,10 @@ class CompositePackedFn(torch.autograd.Function):
         rc = capi.lib().snrf_composite_fwd(c_void_p(hp), c_void_p(hp + 4), c_void_p(hp + 16), c_void_p(hp + 28),
                                            c_int(10), c_int(10), c_int(10), c_int(10),
                                            ptr(z_vals), ptr(dists), ptr(rays_d), ptr(valid), c_int(R), c_int(S),
-                                           c_int(int(bool(infinity))), ptr(weights), ptr(trans), ptr(row), capi.stream())
+                                           c_int(inf_flag), c_int(inf_start), ptr(weights), ptr(trans), ptr(row), capi.stream())
         capi.check(rc, "snrf_composite_fwd")
         ctx.save_for_backward(heads, z_vals, dists, rays_d, trans, valid if valid is not None else heads.new_empty(0))
-        ctx.infinity, ctx.has_valid = bool(infinity), valid is not None
+        ctx.infinity, ctx.inf_start, ctx.has_valid = inf_flag, inf_start, valid is not None
         ctx.set_materialize_grads(False)        # an unused `weights` output costs no zero-filled gradient
         return row, weights
 
@@ -105,7 +107,7 @@ class CompositePackedFn(torch.autograd.Function):
                                            c_int(10), c_int(10), c_int(10), c_int(10),
                                            ptr(z_vals), ptr(dists), ptr(rays_d), ptr(trans), ptr(g_row),
                                            ptr(gw), ptr(valid) if ctx.has_valid else c_void_p(0),
-                                           c_int(R), c_int(S), c_int(int(ctx.infinity)),
+                                           c_int(R), c_int(S), c_int(ctx.infinity), c_int(ctx.inf_start),
                                            c_void_p(gp), c_void_p(gp + 4), c_void_p(gp + 16), c_void_p(gp + 28),
                                            c_int(10), c_int(10), c_int(10), c_int(10),
                                            ptr(g_d) if g_d is not None else c_void_p(0), capi.stream())

@@ -164,6 +164,7 @@ class TileStep:
         # buys nothing at steady state (14.04 vs 14.10 ms / step) and costs allocator growth while the per-stream pools
         # settle, so it is off by default
         self.two_streams = False
+        self.joint_chains = True        # foreground + background as one 2R-ray batch per kernel (render_fore_bg_rays)
         self._side = None
         self.consensus = None           # ADMM state, see enable_consensus()
         self.camera_ids = None
@@ -196,33 +197,44 @@ class TileStep:
         # The foreground and the background chains (sample -> encode -> decoder -> composite) are independent until the
         # colours are merged; with two_streams they are issued on two CUDA streams (the backward follows: autograd runs on
         # the streams of the forward ops).
-        side = self._side_stream() if self.two_streams else None
-        if side is not None:
-            main = torch.cuda.current_stream()
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
+        joint = None
+        if self.joint_chains and self.num_sample == self.num_bg_sample:
+            # both chains as one batch of 2R rays through every kernel (HashGrid.render_fore_bg_rays)
+            joint = self.featureGrid.render_fore_bg_rays(rays_o, rays_d, self.num_sample, self.decoder, mode,
+                                                         occlusion_mask=occlusion_mask, global_step=self.global_step,
+                                                         invalid_underground=self.invalid_underground)
+        if joint is not None:
+            (fg, bg), ret_fg, ret_bg = joint, True, True
+            out = {"rays_o": rays_o, "rays_d": rays_d, "ret_fg": True}
+            out.update(fg)
+        else:
+            side = self._side_stream() if self.two_streams else None
+            if side is not None:
+                main = torch.cuda.current_stream()
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    bg, ret_bg = self.featureGrid.render_bg_rays(rays_o, rays_d, self.num_bg_sample, self.decoder, mode,
+                                                                 occlusion_mask=occlusion_mask, global_step=self.global_step,
+                                                                 bg_mode="IZ", infinity=True, fmesh=None,
+                                                                 invalid_underground=self.invalid_underground)
+            fg, ret_fg = self.featureGrid.render_fore_rays(rays_o, rays_d, self.num_sample, self.decoder, mode,
+                                                           occlusion_mask=occlusion_mask, global_step=self.global_step)
+            out = {"rays_o": rays_o, "rays_d": rays_d, "ret_fg": ret_fg}
+            if ret_fg:
+                out.update(fg)
+            else:
+                out["fore_valid"] = torch.zeros(rays_d[..., 0].shape, dtype=torch.bool, device=self.device)
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)
+                if ret_bg:
+                    for v in bg.values():             # produced on the side stream, consumed (and freed) on the main one
+                        if torch.is_tensor(v):
+                            v.record_stream(torch.cuda.current_stream())
+            else:
                 bg, ret_bg = self.featureGrid.render_bg_rays(rays_o, rays_d, self.num_bg_sample, self.decoder, mode,
                                                              occlusion_mask=occlusion_mask, global_step=self.global_step,
                                                              bg_mode="IZ", infinity=True, fmesh=None,
                                                              invalid_underground=self.invalid_underground)
-        fg, ret_fg = self.featureGrid.render_fore_rays(rays_o, rays_d, self.num_sample, self.decoder, mode,
-                                                       occlusion_mask=occlusion_mask, global_step=self.global_step)
-        out = {"rays_o": rays_o, "rays_d": rays_d, "ret_fg": ret_fg}
-        if ret_fg:
-            out.update(fg)
-        else:
-            out["fore_valid"] = torch.zeros(rays_d[..., 0].shape, dtype=torch.bool, device=self.device)
-        if side is not None:
-            torch.cuda.current_stream().wait_stream(side)
-            if ret_bg:
-                for v in bg.values():             # produced on the side stream, consumed (and freed) on the main one
-                    if torch.is_tensor(v):
-                        v.record_stream(torch.cuda.current_stream())
-        else:
-            bg, ret_bg = self.featureGrid.render_bg_rays(rays_o, rays_d, self.num_bg_sample, self.decoder, mode,
-                                                         occlusion_mask=occlusion_mask, global_step=self.global_step,
-                                                         bg_mode="IZ", infinity=True, fmesh=None,
-                                                         invalid_underground=self.invalid_underground)
         if ret_fg is False and ret_bg is False:
             return None, False
         out["ret_bg"] = ret_bg

@@ -157,3 +157,38 @@ def test_masked_render_equals_compacted_render():
     assert abs(a["l2"] - b["l2"]) < 1e-6
     for k in ("go", "gd", "gt", "gw"):
         assert _rel(a[k], b[k]) < 2e-4, f"{k}: {_rel(a[k], b[k])}"
+
+
+def test_joint_fore_background_batch_equals_separate_chains():
+    """HashGrid.render_fore_bg_rays (one 2R-ray batch through every kernel) against render_fore_rays + render_bg_rays."""
+    load_pkg()
+    from hashgrid import HashGrid, TRAIN
+    from hashgrid._decoder import ShallowMLP
+    dev = torch.device(DEV)
+    torch.manual_seed(0)
+    hg = HashGrid(dev, torch.tensor([0.0, 0.0, 0.0], device=dev), torch.tensor([20.0, 13.0, 30.0], device=dev), 15, [16, 256], 4, False, "")
+    g = torch.Generator().manual_seed(4)
+    hg.occupied_grid = (torch.rand(hg.occupied_grid.shape, generator=g) < 0.6).to(dev)
+    dec = ShallowMLP(32).to(dev)
+    R, S = 257, 32
+    o = torch.tensor([10.0, 6.5, 15.0]) + torch.randn(R, 3, generator=g) * torch.tensor([12.0, 5.0, 18.0])
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    res = {}
+    for joint in (True, False):
+        hg.HE.features.grad = None
+        dec.zero_grad()
+        oo, dd = o.to(dev).requires_grad_(True), d.to(dev).requires_grad_(True)
+        if joint:
+            fg, bg = hg.render_fore_bg_rays(oo, dd, S, dec, TRAIN, global_step=8000, invalid_underground=True)
+        else:
+            fg, _ = hg.render_fore_rays(oo, dd, S, dec, TRAIN, global_step=8000)
+            bg, _ = hg.render_bg_rays(oo, dd, S, dec, TRAIN, global_step=8000, bg_mode="IZ", invalid_underground=True)
+        col = fg["pred_color"] + fg["T_left"] * bg["rgb"]
+        ((col ** 2).sum() + 0.1 * (fg["pred_depth"] + fg["T_left"] * bg["depth"]).sum() + fg["l2_reg_specular"] + bg["l2_reg_specular"]).backward()
+        res[joint] = dict(col=col.detach().clone(), fv=fg["fore_valid"].clone(), bv=bg["valid"].clone(), go=oo.grad.clone(), gd=dd.grad.clone(),
+                          gt=hg.HE.features.grad.clone(), gw=dec.Directional_MLP.mlp[2].weight.grad.clone())
+    a, b = res[True], res[False]
+    assert torch.equal(a["fv"], b["fv"]) and torch.equal(a["bv"], b["bv"])
+    assert torch.allclose(a["col"], b["col"], atol=1e-6)
+    for k in ("go", "gd", "gt", "gw"):
+        assert _rel(a[k], b[k]) < 1e-4, f"{k}: {_rel(a[k], b[k])}"
