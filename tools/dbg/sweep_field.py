@@ -18,7 +18,7 @@ def measure(name):
     ms, units = capi.timed_results()
     capi.time_calls(None)
     return sum(ms) / len(ms), [round(m, 3) for m in ms[:4]]
-for bits in (-1,):
+for bits in (-1, 0, 1, 2):
     capi.lib().snrf_field_set_passes_log2(capi.c_int(bits))
     print("pass_bits", bits, "bwd avg ms", *measure("snrf_field_encode_bwd"))
 capi.lib().snrf_field_set_passes_log2(capi.c_int(-1))
