@@ -236,6 +236,8 @@ int snrf_bg_pts_inference_v2(const float* rays_o, const float* rays_d, const flo
 void snrf_infer_set_precision(int split);
 /* tuning hook: 128-sample tiles in flight per CTA for single-tile scenes (1 or 2, default 1: see csrc/infer.cu) */
 void snrf_infer_set_inflight(int tiles);
+/* tuning hook: single-tile scenes use the two-pass (level-major encode + decoder) path (default 1) */
+void snrf_infer_set_two_pass(int on);
 
 /* ---- sparse Adam -------------------------------------------------------------- */
 /* cuda/include/adam.h (adam_step_cuda: half_state=0, adam_step_cuda_fp16: half_state=1; kernels

@@ -247,7 +247,186 @@ infer_kernel(InferArgs a, int num_tiles)
     if (warp == 0) umma::tmem_free<512>(tmem_slot);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Single-tile fast path: the same evaluation as infer_kernel, split into two passes over chunks of samples.
+//   pass 1 (infer_encode_kernel): geometry + fp16 gathers, ONE LEVEL PER CTA ROW -> level-major features [16][Nc].
+//           The whole GPU walks one 64 MiB level slice at a time, which stays L2-resident: the table streams from HBM
+//           once per chunk, whereas the fused kernel (every level of a sample at once) pulls a 32-byte sector per
+//           corner from HBM -- ~4 KB per sample, the floor of a 1080p frame is then ~170 ms per pass.
+//   pass 2 (infer_decode_kernel): decoder layers on the tensor cores, two tiles in flight per CTA (no gathers here,
+//           so the L1 is not needed), inference activations, alpha, the reference's weight normalisation.
+// Per-sample state byte: 0 = write zeros (foreground sample outside occupied space), 1 = evaluate, 2 = leave the
+// caller's rows untouched (background ray without a tile in this slot).
+struct Geom {
+    f3 u;
+    float w;
+    bool member, active;
+};
+
+template <int MODE>
+__device__ __forceinline__ Geom sample_geom(const InferArgs& a, int b, int ray, int slot, f3 p)
+{
+    Geom g;
+    g.u = mk3(0, 0, 0); g.w = 0.0f; g.member = slot >= 0; g.active = false;
+    if (!g.member) return g;
+    const f3 bc = ld3(a.corners + 3 * b), bs = ld3(a.sizes + 3 * b);
+    if (MODE == kFore) {
+        const f3 q = mk3((p.x - bc.x) / bs.x, (p.y - bc.y) / bs.y, (p.z - bc.z) / bs.z);          // [0,1]
+        const f3 dis = mk3((0.5f - fabsf(q.x - 0.5f)) * bs.x, (0.5f - fabsf(q.y - 0.5f)) * bs.y, (0.5f - fabsf(q.z - 0.5f)) * bs.z);
+        if (dis.x != 0 && dis.z != 0) g.w = dis.x * dis.z;
+        else if (dis.x != 0) g.w = dis.x;
+        else if (dis.z != 0) g.w = dis.z;
+        const int lx = a.grid_log2dim[3 * b], ly = a.grid_log2dim[3 * b + 1], lz = a.grid_log2dim[3 * b + 2];
+        const int gx = min(max((int)(q.x * (float)(1 << lx)), 0), (1 << lx) - 1);
+        const int gy = min(max((int)(q.y * (float)(1 << ly)), 0), (1 << ly) - 1);
+        const int gz = min(max((int)(q.z * (float)(1 << lz)), 0), (1 << lz) - 1);
+        g.active = a.grid_occ[a.grid_starts[b] + ((gx << (ly + lz)) | (gy << lz) | gz)] != 0;
+        g.u = mk3(q.x * 0.5f + 0.25f, q.y * 0.5f + 0.25f, q.z * 0.5f + 0.25f);                     // [0.25, 0.75]
+    } else {
+        // contraction of the 2x-normalised position (rendering_kernel.cu:1060-1095)
+        float q[3] = {2.0f * (p.x - bc.x) / bs.x - 1.0f, 2.0f * (p.y - bc.y) / bs.y - 1.0f, 2.0f * (p.z - bc.z) / bs.z - 1.0f};
+        float nrm = fabsf(q[0]);
+        if (fabsf(q[1]) > nrm) nrm = fabsf(q[1]);
+        if (fabsf(q[2]) > nrm) nrm = fabsf(q[2]);
+        const float ratio = (2.0f - 1.0f / nrm) / nrm;
+        g.u = mk3((q[0] * ratio + 2.0f) * 0.25f, (q[1] * ratio + 2.0f) * 0.25f, (q[2] * ratio + 2.0f) * 0.25f);
+        g.w = MODE == kBackBlend ? a.blend[(size_t)ray * kMaxPts + slot] : 1.0f;
+        g.active = true;
+    }
+    return g;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+infer_encode_kernel(InferArgs a, long long n0, int Nc, float2* __restrict__ feats_lm, float2* __restrict__ aux,
+                    unsigned char* __restrict__ state)
+{
+    const int l = blockIdx.y;
+    const uint32_t mask = a.T - 1u;
+    const int rx = a.resolution[3 * l] - 1, ry = a.resolution[3 * l + 1] - 1, rz = a.resolution[3 * l + 2] - 1;
+    const __half2* tl = a.tables + (size_t)l * a.T;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Nc; i += gridDim.x * blockDim.x) {
+        const long long n = n0 + i;
+        const int ray = (int)(n / a.S), k = (int)(n % a.S);
+        const f3 o = ld3(a.rays_o + 3 * (size_t)ray), d = ld3(a.rays_d + 3 * (size_t)ray);
+        const float zv = a.z_vals[n];
+        int id;
+        float step_len;
+        if (MODE == kFore) { id = a.slots[(size_t)n * kMaxPts]; step_len = a.dists[n]; }
+        else {
+            id = a.slots[(size_t)ray * kMaxPts + (MODE == kBackSlot ? a.step : 0)];
+            step_len = (k == a.S - 1) ? 10000000.0f : a.z_vals[n + 1] - zv;
+        }
+        const Geom g = sample_geom<MODE>(a, 0, ray, id == 0 ? 0 : -1, o + zv * d);
+        if (l == 0) {
+            state[i] = g.active ? 1 : ((MODE == kBackSlot && !g.member) ? 2 : 0);
+            aux[i] = make_float2(g.w, MODE == kFore ? step_len * sqrtf(dot3(d, d)) : step_len);
+        }
+        if (!g.active) continue;
+        const float vx = g.u.x * (float)rx, vy = g.u.y * (float)ry, vz = g.u.z * (float)rz;
+        const int ix = (int)vx, iy = (int)vy, iz = (int)vz;
+        const float ox = vx - (float)ix, oy = vy - (float)iy, oz = vz - (float)iz;
+        float2 f[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) f[c] = __half22float2(__ldg(tl + hash3(ix + ((c >> 2) & 1), iy + ((c >> 1) & 1), iz + (c & 1), mask)));
+        const float ax = 1 - ox, ay = 1 - oy, az = 1 - oz;
+        const float w[8] = {ax * ay * az, ax * ay * oz, ax * oy * az, ax * oy * oz, ox * ay * az, ox * ay * oz, ox * oy * az, ox * oy * oz};
+        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { s0 += w[c] * f[c].x; s1 += w[c] * f[c].y; }
+        feats_lm[(size_t)l * Nc + i] = make_float2(s0, s1);
+    }
+}
+
+template <bool SPLIT, int MODE>
+__global__ void __launch_bounds__(kThreadsDec, 1)
+infer_decode_kernel(InferArgs a, long long n0, int Nc, const float2* __restrict__ feats_lm, const float2* __restrict__ aux,
+                    const unsigned char* __restrict__ state, int num_tiles)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    stage_all_weights<SPLIT>(smem, flat_params(a.params), nullptr, tid, kThreadsDec);
+    if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);
+    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::mbar_fence_init(); }
+    umma::fence_async_smem();
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    Ctx<SPLIT, 2> c;
+    c.init(smem, bars, tmem_slot);
+    const int row = c.row, cg = c.cg;
+    unsigned char* T0 = smem + off_tiles<SPLIT>() + c.group * fwd_tiles<SPLIT>() * kTile;
+    unsigned char* T1 = T0 + kTile;
+    unsigned char* T2 = T1 + kTile;
+    unsigned char* LOa = SPLIT ? T2 + kTile : T1;
+    unsigned char* LOb = SPLIT ? LOa + kTile : T2;
+    const Tiles Tl{T0, T1, nullptr, T2, T1, nullptr, T2, nullptr, LOa, LOb};
+
+    for (int tile = 2 * blockIdx.x + c.group; tile < num_tiles; tile += 2 * gridDim.x) {
+        const int i = tile * kRows + row;
+        const bool live = i < Nc;
+        const int st = live ? state[i] : 2;
+        const bool active = st == 1;
+        const long long n = n0 + i;
+        if (c.any(active)) {
+            float x[16], sh[16];
+            if (active) {
+#pragma unroll
+                for (int l = 0; l < 8; ++l) {
+                    const float2 v = __ldg(feats_lm + (size_t)(8 * cg + l) * Nc + i);
+                    x[2 * l] = v.x; x[2 * l + 1] = v.y;
+                }
+                const f3 d = ld3(a.rays_d + 3 * (size_t)(n / a.S));
+                const f3 dn = d * rsqrtf(dot3(d, d));         // normalize(): decoder.h:201, no epsilon
+                sh16(dn.x, dn.y, dn.z, sh);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { x[j] = 0.0f; sh[j] = 0.0f; }
+            }
+            store_input_row<SPLIT, 2>(Tl, row, cg, x, sh + 8 * cg);
+            float head[10], zh[7];
+            forward_layers<SPLIT, false, 2>(c, Tl, head, zh);
+            if (cg == 0) {
+                float zs[16];
+                umma::tmem_ld16(c.tmem + cDh + c.lane_addr, zs);
+                umma::tc_wait_ld();
+                if (active) {
+                    const float2 ws = aux[i];
+                    const float sigma = logf(1.0f + expf(zh[0]));
+                    f3 dif = mk3(1.0f / (1.0f + expf(-zh[1])), 1.0f / (1.0f + expf(-zh[2])), 1.0f / (1.0f + expf(-zh[3])));
+                    const f3 tint = mk3(1.0f / (1.0f + expf(-zh[4])), 1.0f / (1.0f + expf(-zh[5])), 1.0f / (1.0f + expf(-zh[6])));
+                    f3 spe = mk3(tint.x / (1.0f + expf(-(zs[0] + c.bias[oB5 + 0]))), tint.y / (1.0f + expf(-(zs[1] + c.bias[oB5 + 1]))),
+                                 tint.z / (1.0f + expf(-(zs[2] + c.bias[oB5 + 2]))));
+                    const float al = 1.0f - expf(-1.0f * sigma * ws.y);
+                    float wa = ws.x * al;
+                    dif = dif * wa; spe = spe * wa;
+                    if (MODE != kBackSlot && ws.x > 0) {        // the reference divides by the weight sum when it is positive
+                        const float inv = 1.0f / ws.x;
+                        dif = dif * inv; spe = spe * inv; wa *= inv;
+                    }
+                    st3(a.out_diffuse + 3 * (size_t)n, dif);
+                    st3(a.out_specular + 3 * (size_t)n, spe);
+                    a.out_alpha[n] = wa;
+                }
+            }
+        }
+        if (cg == 0 && st == 0) {                              // unoccupied / unassigned foreground sample: zeros
+            st3(a.out_diffuse + 3 * (size_t)n, mk3(0, 0, 0));
+            st3(a.out_specular + 3 * (size_t)n, mk3(0, 0, 0));
+            a.out_alpha[n] = 0.0f;
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free<512>(tmem_slot);
+}
+
 int g_infer_split = 1;
+int g_infer_two_pass = 1;     // single-tile scenes: level-major encode pass + decoder pass (tuning hook)
 // Tiles in flight per CTA for single-tile scenes.  Measured on B200 (1920x1080, tools/dbg/time_render.py): 1 tile in
 // flight 498 ms / frame, 2 tiles 765 ms -- the second tile's operand buffers take 80 KB away from the L1, and the table
 // gathers live on L1 hits between corners that share a sector.  Default 1; 2 stays selectable.
@@ -277,10 +456,52 @@ int launch_ncg(const InferArgs& a, void* stream, const char* name)
     SNRF_RETURN_LAUNCH(name);
 }
 
+
+// single-tile fast path driver: chunks of samples, scratch from the stream-ordered allocator
+template <int MODE>
+int launch_two_pass(const InferArgs& a, void* stream, const char* name)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(infer_decode_kernel<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<true>());
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(infer_decode_kernel<false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<false>());
+        if (e != cudaSuccess) { snrf_set_error("%s: %s", name, cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long total = (long long)a.B * a.S;
+    const long long chunk = 4ll << 20;                          // 4 Mi samples: 512 MiB of features
+    const long long cap = total < chunk ? total : chunk;
+    void* scratch = nullptr;
+    const size_t bytes = (size_t)cap * (16 * 8 + 8 + 1) + 256;
+    cudaError_t e = cudaMallocAsync(&scratch, bytes, s);
+    if (e != cudaSuccess) { snrf_set_error("%s: scratch allocation of %zu bytes: %s", name, bytes, cudaGetErrorString(e)); return (int)e; }
+    float2* feats = (float2*)scratch;
+    float2* aux = feats + (size_t)cap * 16;
+    unsigned char* state = (unsigned char*)(aux + cap);
+    const int sms = snrf_sm_count();
+    for (long long n0 = 0; n0 < total; n0 += chunk) {
+        const int Nc = (int)(total - n0 < chunk ? total - n0 : chunk);
+        int gx = snrf_div_up(Nc, 256);
+        if (gx > sms * 32) gx = sms * 32;
+        infer_encode_kernel<MODE><<<dim3(gx, 16), 256, 0, s>>>(a, n0, Nc, feats, aux, state);
+        const int num_tiles = snrf_div_up(Nc, kRows);
+        int grid = sms;
+        if (grid > (num_tiles + 1) / 2) grid = (num_tiles + 1) / 2;
+        if (g_infer_split) infer_decode_kernel<true, MODE><<<grid, kThreadsDec, fwd_smem<true>(), s>>>(a, n0, Nc, feats, aux, state, num_tiles);
+        else infer_decode_kernel<false, MODE><<<grid, kThreadsDec, fwd_smem<false>(), s>>>(a, n0, Nc, feats, aux, state, num_tiles);
+    }
+    e = cudaGetLastError();
+    cudaFreeAsync(scratch, s);
+    if (e != cudaSuccess) { snrf_set_error("%s: %s", name, cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
 // nb = number of scene tiles behind `params` / `tables`
 template <int MODE>
 int launch(const InferArgs& a, int nb, void* stream, const char* name)
 {
+    if (nb == 1 && g_infer_two_pass && MODE != kBackBlend) return launch_two_pass<MODE>(a, stream, name);
     return (nb == 1 && g_infer_inflight == 2) ? launch_ncg<MODE, 2>(a, stream, name) : launch_ncg<MODE, 4>(a, stream, name);
 }
 
@@ -289,6 +510,7 @@ int launch(const InferArgs& a, int nb, void* stream, const char* name)
 // ------------------------------- C ABI --------------------------------------
 SNRF_API void snrf_infer_set_precision(int split) { g_infer_split = split ? 1 : 0; }
 SNRF_API void snrf_infer_set_inflight(int tiles) { g_infer_inflight = tiles == 2 ? 2 : 1; }
+SNRF_API void snrf_infer_set_two_pass(int on) { g_infer_two_pass = on ? 1 : 0; }
 
 SNRF_API int snrf_pts_inference(const float* rays_o, const float* rays_d, const float* z_vals, const float* dists,
                                 const short* block_idxs, const void* features_tables, const float* params, const int* resolution,
