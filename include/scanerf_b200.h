@@ -238,6 +238,9 @@ void snrf_infer_set_precision(int split);
 void snrf_infer_set_inflight(int tiles);
 /* tuning hook: single-tile scenes use the two-pass (level-major encode + decoder) path (default 1) */
 void snrf_infer_set_two_pass(int on);
+/* The multi-pass inference paths keep their scratch (features of one 4 Mi-sample chunk, <= 3.1 GB) in a private
+ * stream-ordered pool between calls; this synchronises the device and returns that memory to the driver. */
+int snrf_infer_release_scratch(void);
 
 /* ---- sparse Adam -------------------------------------------------------------- */
 /* cuda/include/adam.h (adam_step_cuda: half_state=0, adam_step_cuda_fp16: half_state=1; kernels

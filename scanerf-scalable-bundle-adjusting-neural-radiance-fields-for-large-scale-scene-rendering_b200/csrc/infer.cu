@@ -339,82 +339,99 @@ infer_encode_kernel(InferArgs a, long long n0, int Nc, float2* __restrict__ feat
     }
 }
 
+// Decoder layers + inference activations for one 128-row tile of precomputed level-major features (row r of this
+// thread at f0[level * stride]).  Returns false when no row of the tile is active (nothing evaluated); sigma / dif /
+// spe are valid for the active rows of column group 0.
+template <bool SPLIT>
+__device__ __forceinline__ bool eval_tile(Ctx<SPLIT, 2>& c, const Tiles& Tl, bool active, const float2* __restrict__ f0, size_t stride,
+                                          f3 d, float& sigma, f3& dif, f3& spe)
+{
+    if (!c.any(active)) return false;
+    const int cg = c.cg;
+    float x[16], sh[16];
+    if (active) {
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+            const float2 v = __ldg(f0 + (size_t)(8 * cg + l) * stride);
+            x[2 * l] = v.x; x[2 * l + 1] = v.y;
+        }
+        const f3 dn = d * rsqrtf(dot3(d, d));                 // normalize(): decoder.h:201, no epsilon
+        sh16(dn.x, dn.y, dn.z, sh);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { x[j] = 0.0f; sh[j] = 0.0f; }
+    }
+    store_input_row<SPLIT, 2>(Tl, c.row, cg, x, sh + 8 * cg);
+    float head[10], zh[7];
+    forward_layers<SPLIT, false, 2>(c, Tl, head, zh);
+    if (cg == 0) {
+        float zs[16];
+        umma::tmem_ld16(c.tmem + cDh + c.lane_addr, zs);
+        umma::tc_wait_ld();
+        // Decoder::inference activations (decoder.h:134-146): softplus without threshold, expf sigmoids
+        sigma = logf(1.0f + expf(zh[0]));
+        dif = mk3(1.0f / (1.0f + expf(-zh[1])), 1.0f / (1.0f + expf(-zh[2])), 1.0f / (1.0f + expf(-zh[3])));
+        const f3 tint = mk3(1.0f / (1.0f + expf(-zh[4])), 1.0f / (1.0f + expf(-zh[5])), 1.0f / (1.0f + expf(-zh[6])));
+        spe = mk3(tint.x / (1.0f + expf(-(zs[0] + c.bias[oB5 + 0]))), tint.y / (1.0f + expf(-(zs[1] + c.bias[oB5 + 1]))),
+                  tint.z / (1.0f + expf(-(zs[2] + c.bias[oB5 + 2]))));
+    }
+    return true;
+}
+
+// common prologue of the two decode kernels: TMEM, barriers, operand tile pointers of this thread's group
+#define SNRF_DECODE_PROLOGUE(STAGE_PARAMS)                                                                        \
+    extern __shared__ __align__(1024) unsigned char smem_raw[];                                                  \
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);                      \
+    __shared__ uint64_t bars[2];                                                                                 \
+    __shared__ uint32_t tmem_slot;                                                                               \
+    const int tid = threadIdx.x, warp = tid >> 5;                                                                \
+    if (STAGE_PARAMS) stage_all_weights<SPLIT>(smem, flat_params(STAGE_PARAMS), nullptr, tid, kThreadsDec);       \
+    if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);                                                            \
+    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::mbar_fence_init(); }       \
+    umma::fence_async_smem();                                                                                    \
+    umma::tc_fence_before();                                                                                     \
+    __syncthreads();                                                                                             \
+    umma::tc_fence_after();                                                                                      \
+    Ctx<SPLIT, 2> c;                                                                                             \
+    c.init(smem, bars, tmem_slot);                                                                               \
+    const int row = c.row, cg = c.cg;                                                                            \
+    unsigned char* T0 = smem + off_tiles<SPLIT>() + c.group * fwd_tiles<SPLIT>() * kTile;                        \
+    unsigned char* T1 = T0 + kTile;                                                                              \
+    unsigned char* T2 = T1 + kTile;                                                                              \
+    unsigned char* LOa = SPLIT ? T2 + kTile : T1;                                                                \
+    unsigned char* LOb = SPLIT ? LOa + kTile : T2;                                                               \
+    const Tiles Tl{T0, T1, nullptr, T2, T1, nullptr, T2, nullptr, LOa, LOb};                                     \
+    (void)row; (void)cg;
+
 template <bool SPLIT, int MODE>
 __global__ void __launch_bounds__(kThreadsDec, 1)
 infer_decode_kernel(InferArgs a, long long n0, int Nc, const float2* __restrict__ feats_lm, const float2* __restrict__ aux,
                     const unsigned char* __restrict__ state, int num_tiles)
 {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t bars[2];
-    __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    stage_all_weights<SPLIT>(smem, flat_params(a.params), nullptr, tid, kThreadsDec);
-    if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);
-    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::mbar_fence_init(); }
-    umma::fence_async_smem();
-    umma::tc_fence_before();
-    __syncthreads();
-    umma::tc_fence_after();
-    Ctx<SPLIT, 2> c;
-    c.init(smem, bars, tmem_slot);
-    const int row = c.row, cg = c.cg;
-    unsigned char* T0 = smem + off_tiles<SPLIT>() + c.group * fwd_tiles<SPLIT>() * kTile;
-    unsigned char* T1 = T0 + kTile;
-    unsigned char* T2 = T1 + kTile;
-    unsigned char* LOa = SPLIT ? T2 + kTile : T1;
-    unsigned char* LOb = SPLIT ? LOa + kTile : T2;
-    const Tiles Tl{T0, T1, nullptr, T2, T1, nullptr, T2, nullptr, LOa, LOb};
-
+    SNRF_DECODE_PROLOGUE(a.params)
     for (int tile = 2 * blockIdx.x + c.group; tile < num_tiles; tile += 2 * gridDim.x) {
         const int i = tile * kRows + row;
-        const bool live = i < Nc;
-        const int st = live ? state[i] : 2;
+        const int st = i < Nc ? state[i] : 2;
         const bool active = st == 1;
         const long long n = n0 + i;
-        if (c.any(active)) {
-            float x[16], sh[16];
-            if (active) {
-#pragma unroll
-                for (int l = 0; l < 8; ++l) {
-                    const float2 v = __ldg(feats_lm + (size_t)(8 * cg + l) * Nc + i);
-                    x[2 * l] = v.x; x[2 * l + 1] = v.y;
-                }
-                const f3 d = ld3(a.rays_d + 3 * (size_t)(n / a.S));
-                const f3 dn = d * rsqrtf(dot3(d, d));         // normalize(): decoder.h:201, no epsilon
-                sh16(dn.x, dn.y, dn.z, sh);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { x[j] = 0.0f; sh[j] = 0.0f; }
+        float sigma = 0.0f;
+        f3 dif = mk3(0, 0, 0), spe = mk3(0, 0, 0);
+        const f3 d = active ? ld3(a.rays_d + 3 * (size_t)(n / a.S)) : mk3(0, 0, 1);
+        const bool done = eval_tile<SPLIT>(c, Tl, active, feats_lm + i, (size_t)Nc, d, sigma, dif, spe);
+        if (cg != 0) continue;
+        if (done && active) {
+            const float2 ws = aux[i];
+            const float al = 1.0f - expf(-1.0f * sigma * ws.y);
+            float wa = ws.x * al;
+            dif = dif * wa; spe = spe * wa;
+            if (MODE != kBackSlot && ws.x > 0) {               // the reference divides by the weight sum when it is positive
+                const float inv = 1.0f / ws.x;
+                dif = dif * inv; spe = spe * inv; wa *= inv;
             }
-            store_input_row<SPLIT, 2>(Tl, row, cg, x, sh + 8 * cg);
-            float head[10], zh[7];
-            forward_layers<SPLIT, false, 2>(c, Tl, head, zh);
-            if (cg == 0) {
-                float zs[16];
-                umma::tmem_ld16(c.tmem + cDh + c.lane_addr, zs);
-                umma::tc_wait_ld();
-                if (active) {
-                    const float2 ws = aux[i];
-                    const float sigma = logf(1.0f + expf(zh[0]));
-                    f3 dif = mk3(1.0f / (1.0f + expf(-zh[1])), 1.0f / (1.0f + expf(-zh[2])), 1.0f / (1.0f + expf(-zh[3])));
-                    const f3 tint = mk3(1.0f / (1.0f + expf(-zh[4])), 1.0f / (1.0f + expf(-zh[5])), 1.0f / (1.0f + expf(-zh[6])));
-                    f3 spe = mk3(tint.x / (1.0f + expf(-(zs[0] + c.bias[oB5 + 0]))), tint.y / (1.0f + expf(-(zs[1] + c.bias[oB5 + 1]))),
-                                 tint.z / (1.0f + expf(-(zs[2] + c.bias[oB5 + 2]))));
-                    const float al = 1.0f - expf(-1.0f * sigma * ws.y);
-                    float wa = ws.x * al;
-                    dif = dif * wa; spe = spe * wa;
-                    if (MODE != kBackSlot && ws.x > 0) {        // the reference divides by the weight sum when it is positive
-                        const float inv = 1.0f / ws.x;
-                        dif = dif * inv; spe = spe * inv; wa *= inv;
-                    }
-                    st3(a.out_diffuse + 3 * (size_t)n, dif);
-                    st3(a.out_specular + 3 * (size_t)n, spe);
-                    a.out_alpha[n] = wa;
-                }
-            }
-        }
-        if (cg == 0 && st == 0) {                              // unoccupied / unassigned foreground sample: zeros
+            st3(a.out_diffuse + 3 * (size_t)n, dif);
+            st3(a.out_specular + 3 * (size_t)n, spe);
+            a.out_alpha[n] = wa;
+        } else if (st == 0) {                                  // unoccupied / unassigned foreground sample: zeros
             st3(a.out_diffuse + 3 * (size_t)n, mk3(0, 0, 0));
             st3(a.out_specular + 3 * (size_t)n, mk3(0, 0, 0));
             a.out_alpha[n] = 0.0f;
@@ -425,12 +442,263 @@ infer_decode_kernel(InferArgs a, long long n0, int Nc, const float2* __restrict_
     if (warp == 0) umma::tmem_free<512>(tmem_slot);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Multi-tile path: the (sample, slot) pairs that need the field of a scene tile are grouped by tile id (counting sort,
+// each tile's segment padded to whole 256-row blocks), encoded level-major per tile and decoded block by block -- a
+// decode CTA takes a contiguous run of blocks, so the decoder weights are restaged only when the run crosses into
+// the next scene tile -- and a last pass sums every sample's pairs in slot order (the order of the reference's loop,
+// rendering_kernel.cu:520-600) and applies the weight normalisation.  Cost is proportional to the number of active
+// pairs, not to the number of tiles.
+struct Work {
+    int *counts, *cursor, *offsets, *total_rows;   // [nb] x 3, [1]
+    int* blk_tile;                                 // [max_rows / 256] scene tile of each 256-row block
+    int* row_sample;                               // [max_rows] sample index inside the chunk (-1: padding)
+    float4* row_uw;                                // [max_rows] table coordinate u, blend weight w
+    float* row_scale;                              // [max_rows] alpha scale (step length x |d|, or the bg step)
+    int* pair_row;                                 // [Nc][4] row of the pair in slot s (-1: none)
+    float* wsum;                                   // [Nc] sum of the member weights (< 0: leave the caller's rows alone)
+    float2* feats;                                 // [16][max_rows]
+    float4* rowout;                                // [max_rows][2] w * alpha * (diffuse, specular), w * alpha
+    int max_rows;
+};
+constexpr int kBlockRows = 2 * kRows;
+
+struct Pairs {
+    int id[kMaxPts];
+    f3 u[kMaxPts];
+    float w[kMaxPts];
+    float wsum, scale;
+};
+
+// the slots of sample n that need a field evaluation (id[s] = -1: none), in slot order
+template <int MODE>
+__device__ __forceinline__ void sample_pairs(const InferArgs& a, long long n, bool live, Pairs& P)
+{
+#pragma unroll
+    for (int s = 0; s < kMaxPts; ++s) { P.id[s] = -1; P.u[s] = mk3(0, 0, 0); P.w[s] = 0.0f; }
+    P.wsum = 0.0f; P.scale = 0.0f;
+    if (!live) return;
+    const int ray = (int)(n / a.S), k = (int)(n % a.S);
+    const f3 o = ld3(a.rays_o + 3 * (size_t)ray), d = ld3(a.rays_d + 3 * (size_t)ray);
+    const float zv = a.z_vals[n];
+    short ids[kMaxPts] = {-1, -1, -1, -1};
+    if (MODE == kFore) {
+        const short4 s4 = *reinterpret_cast<const short4*>(a.slots + (size_t)n * kMaxPts);
+        ids[0] = s4.x; ids[1] = s4.y; ids[2] = s4.z; ids[3] = s4.w;
+        P.scale = a.dists[n] * sqrtf(dot3(d, d));
+    } else {
+        const short* sl = a.slots + (size_t)ray * kMaxPts;
+        if (MODE == kBackSlot) ids[0] = sl[a.step];
+        else { ids[0] = sl[0]; ids[1] = sl[1]; ids[2] = sl[2]; ids[3] = sl[3]; }
+        P.scale = (k == a.S - 1) ? 10000000.0f : a.z_vals[n + 1] - zv;
+    }
+    if (MODE == kBackSlot && ids[0] < 0) { P.wsum = -1.0f; return; }
+    const f3 p = o + zv * d;
+    bool open = true;
+#pragma unroll
+    for (int s = 0; s < kMaxPts; ++s) {
+        open = open && ids[s] >= 0;                           // slots after the first -1 are ignored
+        bool first = open;
+#pragma unroll
+        for (int j = 0; j < s; ++j) first = first && ids[j] != ids[s];
+        if (!first) continue;
+        const Geom g = sample_geom<MODE>(a, ids[s], ray, s, p);
+        P.wsum += g.w;
+        if (g.active) { P.id[s] = ids[s]; P.u[s] = g.u; P.w[s] = g.w; }
+    }
+}
+
+template <int MODE, bool FILL>
+__global__ void __launch_bounds__(256)
+work_plan_kernel(InferArgs a, long long n0, int Nc, Work w)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    Pairs P;
+    sample_pairs<MODE>(a, n0 + i, i < Nc, P);
+    int rows[kMaxPts];
+#pragma unroll
+    for (int s = 0; s < kMaxPts; ++s) {
+        // one atomic per warp and distinct tile: the lanes of a warp that want the same tile take consecutive rows
+        const int b = P.id[s];
+        const unsigned m = __match_any_sync(0xffffffffu, b);
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if (b >= 0 && lane == leader) base = atomicAdd((FILL ? w.cursor : w.counts) + b, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        rows[s] = -1;
+        if (FILL && b >= 0) {
+            const int r = w.offsets[b] + base + __popc(m & ((1u << lane) - 1u));
+            rows[s] = r;
+            w.row_sample[r] = i;
+            w.row_uw[r] = make_float4(P.u[s].x, P.u[s].y, P.u[s].z, P.w[s]);
+            w.row_scale[r] = P.scale;
+        }
+    }
+    if (FILL && i < Nc) {
+        *reinterpret_cast<int4*>(w.pair_row + (size_t)i * kMaxPts) = make_int4(rows[0], rows[1], rows[2], rows[3]);
+        w.wsum[i] = P.wsum;
+    }
+}
+
+// exclusive scan of the per-tile row counts, padded to whole blocks; one CTA
+__global__ void __launch_bounds__(256)
+work_scan_kernel(Work w, int nb)
+{
+    __shared__ int warp_sum[8];
+    __shared__ int carry;
+    __shared__ int seg_start[256], seg_blocks[256];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += 256) {
+        const int b = b0 + tid;
+        const int padded = b < nb ? (w.counts[b] + kBlockRows - 1) / kBlockRows * kBlockRows : 0;
+        int incl = padded;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (lane == 31) warp_sum[wid] = incl;
+        __syncthreads();
+        int before = carry;
+        for (int j = 0; j < wid; ++j) before += warp_sum[j];
+        const int start = before + incl - padded;
+        if (b < nb) w.offsets[b] = start;
+        seg_start[tid] = start / kBlockRows;
+        seg_blocks[tid] = padded / kBlockRows;
+        __syncthreads();
+        if (tid == 255) carry = start + padded;
+        for (int q = 0; q < 256 && b0 + q < nb; ++q)           // the whole CTA labels each segment's blocks
+            for (int j = tid; j < seg_blocks[q]; j += 256) w.blk_tile[seg_start[q] + j] = b0 + q;
+        __syncthreads();
+    }
+    if (tid == 0) *w.total_rows = carry;
+}
+
+__global__ void __launch_bounds__(256)
+work_encode_kernel(InferArgs a, Work w)
+{
+    const int l = blockIdx.y, total = *w.total_rows;
+    const uint32_t mask = a.T - 1u;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < total; r += gridDim.x * blockDim.x) {
+        if (w.row_sample[r] < 0) continue;
+        const int b = w.blk_tile[r / kBlockRows];
+        const int* res = a.resolution + (size_t)b * 48 + 3 * l;
+        const __half2* tl = a.tables + ((size_t)b * 16 + l) * a.T;
+        const float4 uw = w.row_uw[r];
+        const float vx = uw.x * (float)(res[0] - 1), vy = uw.y * (float)(res[1] - 1), vz = uw.z * (float)(res[2] - 1);
+        const int ix = (int)vx, iy = (int)vy, iz = (int)vz;
+        const float ox = vx - (float)ix, oy = vy - (float)iy, oz = vz - (float)iz;
+        float2 f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = __half22float2(__ldg(tl + hash3(ix + ((k >> 2) & 1), iy + ((k >> 1) & 1), iz + (k & 1), mask)));
+        const float ax = 1 - ox, ay = 1 - oy, az = 1 - oz;
+        const float wt[8] = {ax * ay * az, ax * ay * oz, ax * oy * az, ax * oy * oz, ox * ay * az, ox * ay * oz, ox * oy * az, ox * oy * oz};
+        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s0 += wt[k] * f[k].x; s1 += wt[k] * f[k].y; }
+        w.feats[(size_t)l * w.max_rows + r] = make_float2(s0, s1);
+    }
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(kThreadsDec, 1)
+work_decode_kernel(InferArgs a, long long n0, Work w)
+{
+    SNRF_DECODE_PROLOGUE((const float*)nullptr)
+    const int blocks = *w.total_rows / kBlockRows;
+    const int per = (blocks + gridDim.x - 1) / gridDim.x;
+    const int blk_end = min(blocks, ((int)blockIdx.x + 1) * per);
+    int staged = -1;
+    for (int blk = blockIdx.x * per; blk < blk_end; ++blk) {
+        const int b = w.blk_tile[blk];
+        if (b != staged) {                                     // CTA-uniform: both groups are done with the old weights
+            __syncthreads();
+            stage_all_weights<SPLIT>(smem, flat_params(a.params + (size_t)b * 13994), nullptr, tid, kThreadsDec);
+            umma::fence_async_smem();
+            __syncthreads();
+            staged = b;
+        }
+        const int r = blk * kBlockRows + c.group * kRows + row;
+        const int i = w.row_sample[r];
+        const bool active = i >= 0;
+        float sigma = 0.0f;
+        f3 dif = mk3(0, 0, 0), spe = mk3(0, 0, 0);
+        const f3 d = active ? ld3(a.rays_d + 3 * (size_t)((n0 + i) / a.S)) : mk3(0, 0, 1);
+        const bool done = eval_tile<SPLIT>(c, Tl, active, w.feats + r, (size_t)w.max_rows, d, sigma, dif, spe);
+        if (done && active && cg == 0) {
+            const float wgt = w.row_uw[r].w;
+            const float wa = wgt * (1.0f - expf(-1.0f * sigma * w.row_scale[r]));
+            w.rowout[2 * (size_t)r] = make_float4(wa * dif.x, wa * dif.y, wa * dif.z, wa);
+            w.rowout[2 * (size_t)r + 1] = make_float4(wa * spe.x, wa * spe.y, wa * spe.z, 0.0f);
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free<512>(tmem_slot);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+work_combine_kernel(InferArgs a, long long n0, int Nc, Work w)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Nc; i += gridDim.x * blockDim.x) {
+        const float wsum = w.wsum[i];
+        if (wsum < 0.0f) continue;                             // background ray without a tile in this slot
+        const int4 rows4 = *reinterpret_cast<const int4*>(w.pair_row + (size_t)i * kMaxPts);
+        const int rows[kMaxPts] = {rows4.x, rows4.y, rows4.z, rows4.w};
+        f3 acc_d = mk3(0, 0, 0), acc_s = mk3(0, 0, 0);
+        float acc_a = 0.0f;
+#pragma unroll
+        for (int s = 0; s < kMaxPts; ++s) {
+            if (rows[s] < 0) continue;
+            const float4 p0 = w.rowout[2 * (size_t)rows[s]], p1 = w.rowout[2 * (size_t)rows[s] + 1];
+            acc_d = acc_d + mk3(p0.x, p0.y, p0.z);
+            acc_s = acc_s + mk3(p1.x, p1.y, p1.z);
+            acc_a += p0.w;
+        }
+        if (MODE != kBackSlot && wsum > 0) {
+            const float inv = 1.0f / wsum;                     // float3 /= float: multiply by the reciprocal
+            acc_d = acc_d * inv; acc_s = acc_s * inv; acc_a = acc_a * inv;
+        }
+        const long long n = n0 + i;
+        st3(a.out_diffuse + 3 * (size_t)n, acc_d);
+        st3(a.out_specular + 3 * (size_t)n, acc_s);
+        a.out_alpha[n] = acc_a;
+    }
+}
+
 int g_infer_split = 1;
 int g_infer_two_pass = 1;     // single-tile scenes: level-major encode pass + decoder pass (tuning hook)
 // Tiles in flight per CTA for single-tile scenes.  Measured on B200 (1920x1080, tools/dbg/time_render.py): 1 tile in
 // flight 498 ms / frame, 2 tiles 765 ms -- the second tile's operand buffers take 80 KB away from the L1, and the table
 // gathers live on L1 hits between corners that share a sector.  Default 1; 2 stays selectable.
 int g_infer_inflight = 1;
+
+// Scratch for the multi-pass paths comes from a private stream-ordered pool that keeps its memory across
+// synchronisations (the default pool hands it back to the driver at every sync; re-mapping 3 GB per call costs tens of
+// milliseconds).  snrf_infer_release_scratch() trims it.
+cudaMemPool_t g_scratch_pool[64] = {};
+cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t s)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaMallocAsync(ptr, bytes, s);
+    if (!g_scratch_pool[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        e = cudaMemPoolCreate(&g_scratch_pool[dev], &props);
+        if (e != cudaSuccess) return e;
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(g_scratch_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    return cudaMallocFromPoolAsync(ptr, bytes, g_scratch_pool[dev], s);
+}
 
 template <int MODE, int NCG>
 int launch_ncg(const InferArgs& a, void* stream, const char* name)
@@ -474,7 +742,7 @@ int launch_two_pass(const InferArgs& a, void* stream, const char* name)
     const long long cap = total < chunk ? total : chunk;
     void* scratch = nullptr;
     const size_t bytes = (size_t)cap * (16 * 8 + 8 + 1) + 256;
-    cudaError_t e = cudaMallocAsync(&scratch, bytes, s);
+    cudaError_t e = scratch_alloc(&scratch, bytes, s);
     if (e != cudaSuccess) { snrf_set_error("%s: scratch allocation of %zu bytes: %s", name, bytes, cudaGetErrorString(e)); return (int)e; }
     float2* feats = (float2*)scratch;
     float2* aux = feats + (size_t)cap * 16;
@@ -497,11 +765,68 @@ int launch_two_pass(const InferArgs& a, void* stream, const char* name)
     return 0;
 }
 
+// multi-tile driver: chunks of samples; worst case every sample holds kMaxPts pairs
+template <int MODE>
+int launch_work(const InferArgs& a, int nb, void* stream, const char* name)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(work_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<true>());
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(work_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<false>());
+        if (e != cudaSuccess) { snrf_set_error("%s: %s", name, cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long total = (long long)a.B * a.S;
+    constexpr int slots = MODE == kBackSlot ? 1 : kMaxPts;
+    // 4 Mi samples per chunk: every chunk streams the level slices of the tiles it touches from HBM once, so small
+    // chunks multiply the table traffic; worst-case scratch (every foreground sample in 4 tiles) = 3.1 GB
+    const long long chunk = 4ll << 20;
+    const long long cap = total < chunk ? total : chunk;
+    // every tile's segment is padded to whole blocks: at most one partial block per tile that has pairs
+    const long long tiles_hit = (long long)nb < cap * slots ? nb : cap * slots;
+    const long long max_rows = (cap * slots + tiles_hit * (kBlockRows - 1) + kBlockRows - 1) / kBlockRows * kBlockRows;
+    if (max_rows > 0x7fffffffll) { snrf_set_error("%s: work list too large", name); return 1; }
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_counts = take((size_t)(3 * nb + 1) * 4), o_blk = take((size_t)(max_rows / kBlockRows) * 4), o_sample = take((size_t)max_rows * 4),
+                 o_uw = take((size_t)max_rows * 16), o_scale = take((size_t)max_rows * 4), o_pair = take((size_t)cap * kMaxPts * 4),
+                 o_wsum = take((size_t)cap * 4), o_feats = take((size_t)max_rows * 16 * 8), o_out = take((size_t)max_rows * 32);
+    unsigned char* base = nullptr;
+    cudaError_t e = scratch_alloc((void**)&base, off, s);
+    if (e != cudaSuccess) { snrf_set_error("%s: scratch allocation of %zu bytes: %s", name, off, cudaGetErrorString(e)); return (int)e; }
+    Work w;
+    w.counts = (int*)(base + o_counts); w.cursor = w.counts + nb; w.offsets = w.cursor + nb; w.total_rows = w.offsets + nb;
+    w.blk_tile = (int*)(base + o_blk); w.row_sample = (int*)(base + o_sample); w.row_uw = (float4*)(base + o_uw);
+    w.row_scale = (float*)(base + o_scale); w.pair_row = (int*)(base + o_pair); w.wsum = (float*)(base + o_wsum);
+    w.feats = (float2*)(base + o_feats); w.rowout = (float4*)(base + o_out); w.max_rows = (int)max_rows;
+    const int sms = snrf_sm_count();
+    for (long long n0 = 0; n0 < total; n0 += chunk) {
+        const int Nc = (int)(total - n0 < chunk ? total - n0 : chunk);
+        const int gp = snrf_div_up(Nc, 256);
+        cudaMemsetAsync(w.counts, 0, (size_t)(3 * nb + 1) * 4, s);
+        cudaMemsetAsync(w.row_sample, 0xff, (size_t)max_rows * 4, s);
+        work_plan_kernel<MODE, false><<<gp, 256, 0, s>>>(a, n0, Nc, w);
+        work_scan_kernel<<<1, 256, 0, s>>>(w, nb);
+        work_plan_kernel<MODE, true><<<gp, 256, 0, s>>>(a, n0, Nc, w);
+        int gx = snrf_div_up((long long)Nc * slots, 256);
+        if (gx > sms * 32) gx = sms * 32;
+        work_encode_kernel<<<dim3(gx, 16), 256, 0, s>>>(a, w);
+        if (g_infer_split) work_decode_kernel<true><<<sms, kThreadsDec, fwd_smem<true>(), s>>>(a, n0, w);
+        else work_decode_kernel<false><<<sms, kThreadsDec, fwd_smem<false>(), s>>>(a, n0, w);
+        work_combine_kernel<MODE><<<gp < sms * 32 ? gp : sms * 32, 256, 0, s>>>(a, n0, Nc, w);
+    }
+    e = cudaGetLastError();
+    cudaFreeAsync(base, s);
+    if (e != cudaSuccess) { snrf_set_error("%s: %s", name, cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
 // nb = number of scene tiles behind `params` / `tables`
 template <int MODE>
 int launch(const InferArgs& a, int nb, void* stream, const char* name)
 {
-    if (nb == 1 && g_infer_two_pass && MODE != kBackBlend) return launch_two_pass<MODE>(a, stream, name);
+    if (g_infer_two_pass) return (nb == 1 && MODE != kBackBlend) ? launch_two_pass<MODE>(a, stream, name) : launch_work<MODE>(a, nb, stream, name);
     return (nb == 1 && g_infer_inflight == 2) ? launch_ncg<MODE, 2>(a, stream, name) : launch_ncg<MODE, 4>(a, stream, name);
 }
 
@@ -511,6 +836,15 @@ int launch(const InferArgs& a, int nb, void* stream, const char* name)
 SNRF_API void snrf_infer_set_precision(int split) { g_infer_split = split ? 1 : 0; }
 SNRF_API void snrf_infer_set_inflight(int tiles) { g_infer_inflight = tiles == 2 ? 2 : 1; }
 SNRF_API void snrf_infer_set_two_pass(int on) { g_infer_two_pass = on ? 1 : 0; }
+SNRF_API int snrf_infer_release_scratch(void)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_scratch_pool[dev]) return 0;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemPoolTrimTo(g_scratch_pool[dev], 0);
+    if (e != cudaSuccess) { snrf_set_error("snrf_infer_release_scratch: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
 
 SNRF_API int snrf_pts_inference(const float* rays_o, const float* rays_d, const float* z_vals, const float* dists,
                                 const short* block_idxs, const void* features_tables, const float* params, const int* resolution,

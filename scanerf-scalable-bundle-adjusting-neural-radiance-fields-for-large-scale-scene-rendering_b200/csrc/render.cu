@@ -151,31 +151,52 @@ prepare_points_kernel(const float* __restrict__ z_vals, const unsigned char* __r
 }
 
 // Front-to-back accumulation of pre-multiplied (alpha * colour) samples; rays below T = 1e-5 are skipped.
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(256)
 accumulate_kernel(const float* __restrict__ pts_diffuse, const float* __restrict__ pts_specular, const float* __restrict__ pts_alpha,
                   float* __restrict__ transparency, const float* __restrict__ z_vals, int S, int B, float* __restrict__ out_diffuse,
                   float* __restrict__ out_specular, float* __restrict__ out_depth)
 {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+    // One warp per ray.  The transmittance chain is sequential in the sample index (and is kept in that order: the
+    // result is defined by it), so the warp stages 32 samples at a time with coalesced loads and lanes 0..6 each carry
+    // one of the seven accumulators (3 diffuse, 3 specular, depth) through the chunk, every lane with its own copy of T.
+    __shared__ float stage[8][256];                       // per warp: 96 diffuse | 96 specular | 32 alpha | 32 depth
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float* s = stage[wib];
+    for (int i = blockIdx.x * 8 + wib; i < B; i += gridDim.x * 8) {
         float T = transparency[i];
         if (T < 0.00001f) continue;
         const float* cd = pts_diffuse + 3 * (size_t)i * S;
         const float* cs = pts_specular + 3 * (size_t)i * S;
         const float* al = pts_alpha + (size_t)i * S;
         const float* zz = z_vals + (size_t)i * S;
-        f3 dif = ld3(out_diffuse + 3 * (size_t)i), spe = ld3(out_specular + 3 * (size_t)i);
-        float depth = out_depth[i];
-        for (int k = 0; k < S; ++k) {
-            const float a = al[k];
-            dif = dif + T * ld3(cd + 3 * k);
-            spe = spe + T * ld3(cs + 3 * k);
-            depth += T * a * zz[k];
-            T = T * (1 - a);
+        float acc = 0.0f;
+        if (lane < 3) acc = out_diffuse[3 * (size_t)i + lane];
+        else if (lane < 6) acc = out_specular[3 * (size_t)i + lane - 3];
+        else if (lane == 6) acc = out_depth[i];
+        for (int k0 = 0; k0 < S; k0 += 32) {
+            const int n = min(32, S - k0);
+            __syncwarp();
+            for (int j = lane; j < 3 * n; j += 32) { s[j] = cd[3 * k0 + j]; s[96 + j] = cs[3 * k0 + j]; }
+            if (lane < n) { s[192 + lane] = al[k0 + lane]; s[224 + lane] = zz[k0 + lane]; }
+            __syncwarp();
+            if (lane < 6) {
+                const float* v = s + (lane < 3 ? lane : 93 + lane);
+                for (int k = 0; k < n; ++k) {
+                    acc = acc + T * v[3 * k];
+                    T = T * (1 - s[192 + k]);
+                }
+            } else if (lane == 6) {
+                for (int k = 0; k < n; ++k) {
+                    const float a = s[192 + k];
+                    acc += T * a * s[224 + k];
+                    T = T * (1 - a);
+                }
+            }
         }
-        transparency[i] = T;
-        st3(out_diffuse + 3 * (size_t)i, dif);
-        st3(out_specular + 3 * (size_t)i, spe);
-        out_depth[i] = depth;
+        if (lane == 0) transparency[i] = T;
+        if (lane < 3) out_diffuse[3 * (size_t)i + lane] = acc;
+        else if (lane < 6) out_specular[3 * (size_t)i + lane - 3] = acc;
+        else if (lane == 6) out_depth[i] = acc;
     }
 }
 
@@ -392,7 +413,7 @@ SNRF_API int snrf_accumulate(const float* pts_diffuse, const float* pts_specular
                              const float* z_vals, float* diffuse, float* specular, float* depth, int B, int S, void* stream)
 {
     if (B <= 0) return 0;
-    accumulate_kernel<<<grid1d(B), kThreads, 0, (cudaStream_t)stream>>>(pts_diffuse, pts_specular, pts_alpha, transparency, z_vals, S, B, diffuse, specular, depth);
+    accumulate_kernel<<<min(snrf_div_up(B, 8), snrf_sm_count() * 64), 256, 0, (cudaStream_t)stream>>>(pts_diffuse, pts_specular, pts_alpha, transparency, z_vals, S, B, diffuse, specular, depth);
     SNRF_RETURN_LAUNCH("snrf_accumulate");
 }
 

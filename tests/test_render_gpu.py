@@ -60,6 +60,17 @@ def both(fn_name, ours, ref, make_args):
     return a, (b if ref is not None else None)
 
 
+@pytest.fixture(params=[1, 0], ids=["grouped", "fused"])
+def infer_path(request):
+    """Both implementations of the field evaluation behind pts_inference / bg_pts_inference*: the grouped
+    multi-pass path (default) and the single fused kernel (snrf_infer_set_two_pass(0))."""
+    load_pkg()
+    import scanerf_b200_capi as capi
+    capi.lib().snrf_infer_set_two_pass(capi.c_int(request.param))
+    yield request.param
+    capi.lib().snrf_infer_set_two_pass(capi.c_int(1))
+
+
 def _ops():
     load_pkg()
     from hashgrid.lib import HASHGRID as ours
@@ -67,7 +78,7 @@ def _ops():
 
 
 @pytest.mark.parametrize("nb,B", [(1, 500), (3, 6000)])
-def test_render_pipeline_stage_by_stage(nb, B):
+def test_render_pipeline_stage_by_stage(nb, B, infer_path):
     ours, ref = _ops()
     sc = dev(make_scene(nb))
     o, d = (t.to(DEV) for t in make_rays(B, nb * B))
@@ -193,7 +204,7 @@ def test_render_pipeline_stage_by_stage(nb, B):
         assert torch.equal(a[6], r[6]) and torch.allclose(a[7], r[7], rtol=1e-6, atol=1e-6)
 
 
-def test_pts_inference_against_cpu_restatement():
+def test_pts_inference_against_cpu_restatement(infer_path):
     """Single tile, every cell occupied: per-sample outputs = alpha * decoder(encode(u)) with the
     renderer's conventions (u = q/2 + 0.25, fp16 table, normalised d, no level mask)."""
     ours, _ = _ops()
@@ -267,7 +278,7 @@ def _render_with(mod, sc, o, d, S, Sb):
 
 
 @pytest.mark.parametrize("nb", [1, 3])
-def test_render_rays_driver_matches_reference_sequence(nb):
+def test_render_rays_driver_matches_reference_sequence(nb, infer_path):
     """render_frame.render_rays (our sync-free mirror of render_rays_base) against the reference's own
     operator sequence run on the rebuilt reference extension; composited colours within 1e-4."""
     ours, ref = _ops()

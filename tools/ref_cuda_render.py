@@ -62,6 +62,7 @@ def render_with(mod, ts, o, d, S, Sb, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=2)
+    ap.add_argument("--tiles", type=int, default=1, help="copies of the tile in a row along x, foreground boxes overlapping by 10 %")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "r1_reference_cuda_render.json"))
     args = ap.parse_args()
     import HASHGRID as REF
@@ -71,7 +72,17 @@ def main():
     cfg = bench.WORKLOADS["default.yaml-single-tile"]
     dev = torch.device("cuda:0")
     step, gen = bench.build_tile(cfg, dev, 0)
-    ts = rf.TileSet.from_hashgrid(step.featureGrid, step.decoder, dev).finalize()
+    if args.tiles == 1:
+        ts = rf.TileSet.from_hashgrid(step.featureGrid, step.decoder, dev).finalize()
+    else:
+        from hashgrid._decoder import flatten_for_inference
+        hg, ts = step.featureGrid, rf.TileSet(dev)
+        flat = flatten_for_inference(step.decoder)
+        for j in range(args.tiles):
+            shift = torch.tensor([0.9 * 0.5 * float(hg.bbox_size[0]) * j, 0.0, 0.0], device=hg.min_bbox.device)
+            ts.add_tile(hg.HE.features.detach().half().roll(j, 1), flat * (1.0 + 0.01 * j), hg.HE.resolution, hg.occupied_grid,
+                        hg.min_bbox + shift, hg.bbox_size, hg.sampler_log2dim)
+        ts.finalize()
     H, W = 1080, 1920
     K = step.poses.ks[0].clone()
     K[0, 0] *= W / cfg["W"]; K[1, 1] *= H / cfg["H"]; K[0, 2] = W / 2.0; K[1, 2] = H / 2.0
@@ -91,7 +102,7 @@ def main():
             res[name] = (e0.elapsed_time(e1) / args.frames, out)
     ok = torch.isfinite(res["reference"][1][0]).all(-1)
     diff = float((res["reference"][1][0][ok] + res["reference"][1][1][ok] - res["ours"][1][0][ok] - res["ours"][1][1][ok]).abs().max())
-    line = {"what": "reference render operators (rebuilt for sm_100a, unmodified) vs this repo, 1920x1080, 1 tile, 128 + 128 samples",
+    line = {"what": f"reference render operators (rebuilt for sm_100a, unmodified) vs this repo, 1920x1080, {args.tiles} tile(s), 128 + 128 samples",
             "reference_ms_per_frame": res["reference"][0], "ours_ms_per_frame": res["ours"][0],
             "reference_mrays_s": H * W / res["reference"][0] / 1e3, "ours_mrays_s": H * W / res["ours"][0] / 1e3,
             "max_abs_rgb_diff": diff}
