@@ -196,6 +196,17 @@ def run_reference(args, cfg, name):
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def measured_peak_gbs():
+    """(HBM GB/s, source): the driver-written measured copy bandwidth, else the profiling recipe's fallback."""
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        if "hbm_gbs" in peaks:
+            return peaks["hbm_gbs"], "measured"
+    except Exception:
+        pass
+    return 6650.0, "fallback"
+
+
 # ----------------------------------------------------------------------------- render leg
 def bench_render(step, cfg, dev, H=1080, W=1920, frames=5, warm=2):
     """BASELINE.json configs[2]: full-frame 1920x1080 inference of the trained-from-random tile through the
@@ -218,9 +229,25 @@ def bench_render(step, cfg, dev, H=1080, W=1920, frames=5, warm=2):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / frames
+    # roofline of the field evaluation (the encode + decode passes behind pts_inference / bg_pts_inference_v2), timed
+    # live on one more frame: algorithmic bytes per sample = 16 levels x 8 corners x 4 B of fp16 table + 28 B of
+    # outputs + the sample's inputs (z 4 B; foreground also dist 4 B + slots 8 B)
+    import scanerf_b200_capi as capi
+    capi.time_calls(("snrf_pts_inference", "snrf_bg_pts_inference_v2"))
+    rf.render_frame(ts, H, W, K, c2w)
+    k_ms, _ = capi.timed_results()
+    capi.time_calls(None)
+    S, Sb = 128, 128
+    alg = H * W * (S * (512 + 28 + 16) + Sb * (512 + 28 + 4))
+    peak, src = measured_peak_gbs()
+    achieved = alg / (sum(k_ms) * 1e-3) / 1e9 if k_ms else None
     return {"metric": "render Mrays/s", "value": H * W / ms / 1e3, "unit": "Mrays/s", "ms_per_frame": ms,
             "config": {"workload": "render 1920x1080, 1 tile, 128 + 128 samples per ray, fp16 table 16 x 2^%d x 2" % cfg["log2T"],
-                       "frames": frames, "finite": bool(torch.isfinite(out[0]).all())}}
+                       "frames": frames, "finite": bool(torch.isfinite(out[0]).all())},
+            "roofline": {"kernel": "field evaluation (snrf_pts_inference + snrf_bg_pts_inference_v2: level-major fp16 encode pass + tcgen05 decode pass)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",
+                         "frac": achieved / peak if achieved else None, "alg_bytes_per_frame": alg, "ms_per_frame": sum(k_ms),
+                         "calls_timed": len(k_ms), "share_of_frame": sum(k_ms) / ms if k_ms else None}}
 
 
 # ----------------------------------------------------------------------------- main arm
@@ -327,12 +354,7 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    peak, peak_src = measured_peak_gbs()
     n_launch = max(len(k_ms), 1)
     avg_ms = sum(k_ms) / n_launch if k_ms else float("nan")
     alg_bytes = ENC_BWD_BYTES * (sum(k_units) / n_launch if k_units else 0)

@@ -46,6 +46,22 @@ class TileSet:
                     hashgrid.occupied_grid, hashgrid.min_bbox, hashgrid.bbox_size, hashgrid.sampler_log2dim)
         return ts
 
+    @classmethod
+    def from_exported(cls, tile_dirs, device):
+        """Trained tiles as TILE.export_tile wrote them (tile.py:509-532), read the way the reference's renderer does
+        (rendering.py:86-174): <dir>/feature.npz + <dir>/decoder.pth, whose Linear weights / biases are taken in
+        state_dict key order (tools/utils.py:399-410) and flattened per layer as bias then W^T."""
+        import os
+        ts = cls(device)
+        for d in tile_dirs:
+            f = np.load(os.path.join(d, "feature.npz"))
+            sd = torch.load(os.path.join(d, "decoder.pth"), map_location="cpu", weights_only=True)
+            weights = [v for k, v in sd.items() if "weight" in k]
+            bias = [v for k, v in sd.items() if "weight" not in k and "bias" in k]
+            flat = torch.cat([t for w, b in zip(weights, bias) for t in (b.flatten(), w.t().contiguous().flatten())]).float()
+            ts.add_tile(f["features"], flat, f["resolution"], f["occupied_grid"], f["block_corner"], f["block_size"], f["grid_log2dim"])
+        return ts.finalize()
+
     def finalize(self):
         dev = self.device
         self.feature_tables = torch.stack(self.tables).to(dev).contiguous()

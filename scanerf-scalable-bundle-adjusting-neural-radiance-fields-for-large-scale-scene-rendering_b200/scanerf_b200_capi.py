@@ -47,7 +47,7 @@ class _Lib:
                 def fn(*args, _raw=raw, _name=name):
                     global launch_count
                     launch_count += 1
-                    if _timed_name == _name:
+                    if _timed_name is not None and _name in _timed_name:
                         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         a.record()
                         rc = _raw(*args)
@@ -61,9 +61,9 @@ class _Lib:
 
 
 def time_calls(name):
-    """Start (name) or stop (None) CUDA-event timing of one C-ABI entry point."""
+    """Start (a name, or a tuple of names) or stop (None) CUDA-event timing of C-ABI entry points."""
     global _timed_name
-    _timed_name = name
+    _timed_name = (name,) if isinstance(name, str) else (tuple(name) if name else None)
     if name is not None:
         _timed_events.clear()
 

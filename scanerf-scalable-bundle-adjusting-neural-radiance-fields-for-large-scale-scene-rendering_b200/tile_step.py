@@ -282,6 +282,54 @@ class TileStep:
         self.global_step += 1
         return loss.detach()
 
+    # ------------------------------------------------------------------ on-disk formats (tile.py:509-572, 35-45, 67-68, 128-136, 302-338)
+    def export_tile(self, output_dir, visible_poses=None):
+        """tile-<idx>/ as the reference's renderer reads it (rendering.py:86-113): feature.npz (fp16 table, occupancy,
+        doubled box, grid_log2dim, resolution), decoder.pth (ShallowMLP state_dict), cams.npz (c2ws, ks, idxs)."""
+        import os
+        import numpy as np
+        os.makedirs(output_dir, exist_ok=True)
+        self.featureGrid.export(output_dir)
+        torch.save(self.decoder.state_dict(), os.path.join(output_dir, "decoder.pth"))
+        with torch.no_grad():
+            c2ws = self.poses.c2w().detach().cpu().numpy()
+        if visible_poses is None:
+            visible_poses = self.camera_ids.cpu().numpy() if self.camera_ids is not None else np.arange(c2ws.shape[0])
+        np.savez(os.path.join(output_dir, "cams.npz"), c2ws=c2ws, ks=self.poses.ks.detach().cpu().numpy(), idxs=np.array(visible_poses))
+        return output_dir
+
+    def export_check_point(self, output_dir, tile_idx=0):
+        """checkpoint-<step>-<tile>.pt with the reference's keys (tile.py:534-572).  `poses` (the refined se(3) offsets)
+        is an extra key: the reference's resume restores the optimiser moments of se3_refine but not its value."""
+        import os
+        ck = {"global_step": self.global_step, "hashgrid": self.featureGrid.export_check_point(),
+              "admm": self.consensus.export_check_point() if self.consensus is not None else None,
+              "decoder": self.decoder.state_dict(), "featureGrid_optimizer": self.featureGrid_optimizer.state_dict(),
+              "optimizer": self.optimizer.state_dict(), "poses": self.poses.se3_refine.detach().cpu()}
+        os.makedirs(output_dir, exist_ok=True)
+        path = os.path.join(output_dir, f"checkpoint-{self.global_step}-{tile_idx}.pt")
+        torch.save(ck, path)
+        return path
+
+    def load_check_point(self, path_or_dict):
+        """Resume from export_check_point() output -- or from a checkpoint the reference wrote (no `poses` key)."""
+        ck = path_or_dict if isinstance(path_or_dict, dict) else torch.load(path_or_dict, map_location=self.device, weights_only=False)
+        self.global_step = int(ck["global_step"])
+        table = self.featureGrid.HE.features
+        self.featureGrid.load_check_point(ck["hashgrid"])
+        if self.featureGrid.HE.features is not table:            # keep the Parameter the optimiser holds
+            with torch.no_grad():
+                table.copy_(self.featureGrid.HE.features)
+            self.featureGrid.HE.features = table
+        self.decoder.load_state_dict(ck["decoder"])
+        self.featureGrid_optimizer.load_state_dict(ck["featureGrid_optimizer"])
+        self.optimizer.load_state_dict(ck["optimizer"])
+        if ck.get("admm") is not None and self.consensus is not None:
+            self.consensus.load_check_point(ck["admm"])
+        if ck.get("poses") is not None:
+            with torch.no_grad():
+                self.poses.se3_refine.copy_(ck["poses"].to(self.device))
+
     def step(self, locs_host, gt_host):
         """The end-to-end call: pinned host batch in, python float loss out."""
         locs = locs_host.to(self.device, non_blocking=True)

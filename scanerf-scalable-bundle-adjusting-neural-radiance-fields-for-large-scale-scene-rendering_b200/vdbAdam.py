@@ -32,6 +32,30 @@ class vdbAdam:
         for item in self.params:
             item[1], item[2] = item[1].to(device), item[2].to(device)
 
+    # Checkpoint interchange with the dense torch.optim.Adam the reference keeps for the table (tile.py:301-303,
+    # 562): same structure and moment names, so either side loads the other's `featureGrid_optimizer` entry.
+    def state_dict(self):
+        g = self.param_groups[0]
+        state = {i: {"step": torch.tensor(float(self.t)), "exp_avg": m, "exp_avg_sq": v} for i, (_, m, v) in enumerate(self.params)}
+        group = {"lr": g["lr"], "betas": (g["beta1"], g["beta2"]), "eps": g["eps"], "weight_decay": g["weight_decay"],
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "decoupled_weight_decay": False, "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        group = sd["param_groups"][0]
+        g = self.param_groups[0]
+        g["lr"], g["eps"], g["weight_decay"] = group["lr"], group["eps"], group.get("weight_decay", 0.0)
+        g["beta1"], g["beta2"] = group["betas"]
+        for i, item in enumerate(self.params):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            item[1] = st["exp_avg"].to(item[0].device, torch.float32).reshape(item[0].shape).contiguous().clone()
+            item[2] = st["exp_avg_sq"].to(item[0].device, torch.float32).reshape(item[0].shape).contiguous().clone()
+            self.t = int(float(st["step"]))
+        self._clean = False
+
     def zero_grad(self):
         if self._clean:           # gradients were cleared by the fused update
             self._clean = False
