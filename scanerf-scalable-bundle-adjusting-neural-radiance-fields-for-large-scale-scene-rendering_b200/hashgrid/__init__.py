@@ -154,11 +154,17 @@ class HashGrid(nn.Module):
         cells_per_batch = max(int(batch_size / torch.prod(per_cell)), 1)
         peak = torch.zeros(locs.shape[0], device=self.device)
         mask32 = self.weight_feature(global_step)[None, :].repeat_interleave(2, dim=-1)
+        params = self._fused_ready(decoder)          # stock ShallowMLP: the density head comes from the tensor-core decoder
+        unit_d = torch.tensor([[0.0, 0.0, 1.0]], device=self.device)
         for i in range(0, locs.shape[0], cells_per_batch):
             pts = (corner[i:i + cells_per_batch, None, :] + inner[None]) * 2 - 1
             n = pts.shape[0]
-            feats = self.HE(pts.reshape(-1, 3)) * mask32
-            alpha = 1 - torch.exp(-1.0 * decoder.inference_sigma(feats))
+            if params is not None:
+                feats = self.HE(pts.reshape(-1, 3)).reshape(-1, 32)
+                sigma = _field.decoder_forward(feats, mask32[0].contiguous(), unit_d, feats.shape[0], params)[:, :1]
+            else:
+                sigma = decoder.inference_sigma(self.HE(pts.reshape(-1, 3)) * mask32)
+            alpha = 1 - torch.exp(-1.0 * sigma)
             peak[i:i + n] = alpha.reshape(n, -1).max(dim=-1)[0]
         keep = locs[peak > pruning_th]
         new_grid = torch.zeros(_pow2_shape(log2dim), dtype=torch.bool, device=self.device)
