@@ -180,6 +180,16 @@ int snrf_gauss_sample_fwd(const unsigned char* src, const float* grid, float* ou
                           int height, int width, float sigma, float max_dis, void* stream);
 int snrf_gauss_sample_bwd(const unsigned char* src, const float* grid, const float* grad_in, float* grad_grid, int n_img,
                           int B, int height, int width, float sigma, float max_dis, void* stream);
+/* Neighbour-view colour fetch of the warp loss (warp_loss.py:441-519, WarpLoss.sample_neighbor_color; the reference
+ * does this with host-resident images and four CPU gathers per step).  images [N,H,W,3] u8 resident on the device,
+ * occlusion [N,H,W] bytes or NULL, grid [B,K,2] pixel coordinates, nei_views [B,K] i32, nei_valid [B,K] bytes ->
+ * color [B,K,3] f32 in [0,1] (bilinear, taps clamped into the image), valid_out [B,K] = nei_valid & occlusion at the
+ * nearest pixel.  The backward writes grad_grid [B,K,2] = d color / d grid contracted with grad_color. */
+int snrf_nei_sample_fwd(const unsigned char* images, const unsigned char* occlusion, const float* grid, const int* nei_views,
+                        const unsigned char* nei_valid, float* color, unsigned char* valid_out, int B, int K, int height,
+                        int width, void* stream);
+int snrf_nei_sample_bwd(const unsigned char* images, const float* grid, const int* nei_views, const unsigned char* nei_valid,
+                        const float* grad_color, float* grad_grid, int B, int K, int height, int width, void* stream);
 /* grid_sample_bool_cuda (cuda/grid_sample_kernel.cu:445-493): src [N,H,W] bytes; out-of-image entries keep their value */
 int snrf_grid_sample_bool(const unsigned char* src, const float* grid, unsigned char* out, int n_img, int B, int height,
                           int width, void* stream);

@@ -159,3 +159,72 @@ def grid_sample_bool(src, grid, out):
         ok = (x >= 0) & (x < W) & (y >= 0) & (y < H)
         out[n, ok, 0, 0] = src[n][y[ok], x[ok]]
     return out
+
+
+# ------------------------------------------------------------------------------------------------ warp loss (torch)
+def sample_neighbor_color(images, grid, nei_views, nei_valid, occlusions):
+    """warp_loss.py:441-519 in torch (autograd through the bilinear weights): images [N,H,W,3] float in [0,1] on any
+    device, grid [B,K,2] pixel coordinates, nei_views [B,K], nei_valid [B,K] bool, occlusions [N,H,W,1] bool.
+    Taps are clamped into the image (the reference would raise at the right / bottom border)."""
+    import torch
+    N, H, W = images.shape[:3]
+    B, K = grid.shape[:2]
+    lt = grid.long()
+    off = grid - lt.float()
+    near = (grid + 0.5).long()
+    v = nei_views.flatten().long()
+    cx = lambda t: t.clamp(0, W - 1).flatten()
+    cy = lambda t: t.clamp(0, H - 1).flatten()
+    valid = nei_valid & occlusions[v, cy(near[..., 1]), cx(near[..., 0])].reshape(B, K)
+    tap = lambda dx, dy: images[v, cy(lt[..., 1] + dy), cx(lt[..., 0] + dx)].reshape(B, K, 3)
+    w = lambda a, b: (a * b)[..., None]
+    color = (w(1 - off[..., 0], 1 - off[..., 1]) * tap(0, 0) + w(off[..., 0], 1 - off[..., 1]) * tap(1, 0)
+             + w(1 - off[..., 0], off[..., 1]) * tap(0, 1) + w(off[..., 0], off[..., 1]) * tap(1, 1))
+    return color, valid
+
+
+def warp_loss(rays_o, rays_d, depth, diffuse, specular, valid, occlusions, images, ks, rts, H, W, alpha, gamma, voxel_size,
+              render, topK=10, selection=None, nei_rays=None):
+    """WarpLoss.__call__ (warp_loss.py:523-665) in the reference's own compaction form, torch ops only; `render`
+    (rays_o, rays_d) -> (depth [n,1], specular [n,3]) stands for block.render_rays(mode=2) (:355-377).
+    view_cost / proj2neighbor are the numpy restatements above wrapped for autograd-free use: the projection is
+    re-derived in torch so that gradients reach pts and rts."""
+    import torch
+    sel = valid
+    rays_o, rays_d, depth, diffuse, specular = rays_o[sel], rays_d[sel], depth[sel], diffuse[sel], specular[sel]
+    B = rays_o.shape[0]
+    if B == 0:
+        return None
+    pts = rays_o + depth * rays_d
+    if selection is None:
+        cost = torch.from_numpy(view_cost(rays_o.detach().cpu().numpy(), rays_d.detach().cpu().numpy(), pts.detach().cpu().numpy(),
+                                          ks.cpu().numpy(), rts.detach().cpu().numpy(), H, W)).to(pts.device)
+        top, nei_views = torch.topk(cost, k=topK, dim=0, largest=False)
+        nei_valid = (top <= 0.176).permute(1, 0).contiguous()
+        nei_views = nei_views.permute(1, 0).contiguous()
+    else:           # (views [B,K], valid [B,K]) of the selected rays, e.g. to pin a comparison on the same neighbours
+        nei_views, nei_valid = selection[0].long(), selection[1]
+    # cuda/view_selection_kernel.cu:115-212: x_cam = R p + t, grid = K x_cam; origin = camera centre, direction = ray through the point
+    Rt = rts[nei_views.flatten()]
+    Kn = ks[nei_views.flatten()].reshape(-1, 3, 3)
+    p = pts[:, None, :].expand(B, topK, 3).reshape(-1, 3)
+    xc = (Rt[:, :, :3] @ p[..., None])[..., 0] + Rt[:, :, 3]
+    g3 = (Kn @ xc[..., None])[..., 0].reshape(B, topK, 3)
+    proj_depth = g3[..., 2:]
+    grid = g3[..., :2] / (proj_depth + 1e-8) - 0.5
+    color, nei_valid = sample_neighbor_color(images, grid, nei_views, nei_valid, occlusions)
+    with torch.no_grad():
+        center = -(Rt[:, :, :3].transpose(1, 2) @ Rt[:, :, 3:])[..., 0]
+        direction = p - center                      # nei_origin + proj_depth * nei_direction = pts
+        direction = direction / proj_depth.reshape(-1, 1)
+        if nei_rays is not None:    # (origin, direction) [B,K,3] of the selected rays: pins the re-render on identical rays
+            center, direction = nei_rays[0].reshape(-1, 3), nei_rays[1].reshape(-1, 3)
+        flat = nei_valid.reshape(-1)
+        d_r, s_r = render(center[flat], direction[flat])
+        vis = torch.exp(-alpha * torch.abs(d_r - proj_depth.reshape(-1, 1)[flat]) / voxel_size)
+        nd = torch.exp(-gamma * s_r.mean(-1, keepdim=True))
+        score = torch.zeros(B * topK, 1, device=pts.device)
+        score[flat] = vis * nd
+        score = score.reshape(B, topK, 1) * torch.exp(-gamma * specular.mean(-1, keepdim=True))[:, None, :]
+    pred = torch.clamp(diffuse + specular, 0, 1)
+    return (torch.mean((pred[:, None, :] - color) ** 2, dim=-1, keepdim=True) * score).mean()

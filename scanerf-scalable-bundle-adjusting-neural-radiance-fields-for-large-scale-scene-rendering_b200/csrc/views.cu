@@ -343,6 +343,87 @@ proj_fetch_kernel(const float* __restrict__ pts, const float* __restrict__ Ks, c
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Neighbour-view colour fetch of the warp loss (warp_loss.py:441-519 WarpLoss.sample_neighbor_color).  The reference
+// keeps the training images on the HOST, builds four index tensors per batch on the GPU, copies them to the CPU,
+// gathers there and copies the four colour tensors back (a D2H + H2D round trip and a synchronisation every step).
+// Here the images stay resident in HBM as uint8 [N,H,W,3] and one kernel does, per (ray, neighbour):
+//   lt = trunc(grid), offset = grid - lt, nearest = trunc(grid + 0.5)
+//   valid_out = valid_in & occlusion[view][nearest]
+//   colour    = bilinear blend of the pixels lt, lt + (1,0), lt + (0,1), lt + (1,1) of image `view`, scaled to [0,1]
+// Pixel coordinates are clamped into the image (the reference indexes out of range at the right / bottom border and
+// wraps around at negative indices); pairs with valid_in = 0 give zeros.
+struct NeiTaps {
+    int x0, y0, x1, y1;
+    float fx, fy;
+};
+__device__ __forceinline__ NeiTaps nei_taps(float2 g, int height, int width)
+{
+    NeiTaps t;
+    const long long lx = (long long)g.x, ly = (long long)g.y;          // .long(): truncation toward zero
+    t.fx = g.x - (float)lx; t.fy = g.y - (float)ly;
+    t.x0 = (int)min(max(lx, 0ll), (long long)width - 1); t.x1 = (int)min(max(lx + 1, 0ll), (long long)width - 1);
+    t.y0 = (int)min(max(ly, 0ll), (long long)height - 1); t.y1 = (int)min(max(ly + 1, 0ll), (long long)height - 1);
+    return t;
+}
+__device__ __forceinline__ f3 pixel_u8(const unsigned char* __restrict__ img, int y, int x, int width)
+{
+    const unsigned char* p = img + 3 * ((size_t)y * width + x);
+    return mk3((float)p[0], (float)p[1], (float)p[2]);
+}
+
+__global__ void __launch_bounds__(kThreads)
+nei_sample_fwd_kernel(const unsigned char* __restrict__ images, const unsigned char* __restrict__ occlusion,
+                      const float2* __restrict__ grid, const int* __restrict__ nei_views, const unsigned char* __restrict__ nei_valid,
+                      float* __restrict__ color, unsigned char* __restrict__ valid_out, int total, int height, int width)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        bool ok = nei_valid[i] != 0;
+        f3 c = mk3(0, 0, 0);
+        if (ok) {
+            const float2 g = grid[i];
+            const size_t view = (size_t)nei_views[i];
+            if (occlusion) {
+                const long long nx = (long long)(g.x + 0.5f), ny = (long long)(g.y + 0.5f);
+                const int cx = (int)min(max(nx, 0ll), (long long)width - 1), cy = (int)min(max(ny, 0ll), (long long)height - 1);
+                ok = occlusion[(view * height + cy) * width + cx] != 0;
+            }
+            const NeiTaps t = nei_taps(g, height, width);
+            const unsigned char* img = images + view * (size_t)height * width * 3;
+            const f3 lt = pixel_u8(img, t.y0, t.x0, width), rt = pixel_u8(img, t.y0, t.x1, width);
+            const f3 lb = pixel_u8(img, t.y1, t.x0, width), rb = pixel_u8(img, t.y1, t.x1, width);
+            const float s = 1.0f / 255.0f;
+            c = ((1.0f - t.fx) * (1.0f - t.fy) * s) * lt + (t.fx * (1.0f - t.fy) * s) * rt + ((1.0f - t.fx) * t.fy * s) * lb + (t.fx * t.fy * s) * rb;
+        }
+        st3(color + 3 * (size_t)i, c);
+        valid_out[i] = ok ? 1 : 0;
+    }
+}
+
+// d colour / d grid: the blend weights are linear in the offsets, the taps are piecewise constant
+__global__ void __launch_bounds__(kThreads)
+nei_sample_bwd_kernel(const unsigned char* __restrict__ images, const float2* __restrict__ grid, const int* __restrict__ nei_views,
+                      const unsigned char* __restrict__ nei_valid, const float* __restrict__ grad_color, float2* __restrict__ grad_grid,
+                      int total, int height, int width)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float2 gg = make_float2(0.0f, 0.0f);
+        if (nei_valid[i]) {
+            const NeiTaps t = nei_taps(grid[i], height, width);
+            const unsigned char* img = images + (size_t)nei_views[i] * (size_t)height * width * 3;
+            const f3 lt = pixel_u8(img, t.y0, t.x0, width), rt = pixel_u8(img, t.y0, t.x1, width);
+            const f3 lb = pixel_u8(img, t.y1, t.x0, width), rb = pixel_u8(img, t.y1, t.x1, width);
+            const f3 g = ld3(grad_color + 3 * (size_t)i);
+            const float s = 1.0f / 255.0f;
+            const f3 dx = (1.0f - t.fy) * (rt - lt) + t.fy * (rb - lb);
+            const f3 dy = (1.0f - t.fx) * (lb - lt) + t.fx * (rb - rt);
+            gg = make_float2(s * dot3(g, dx), s * dot3(g, dy));
+        }
+        grad_grid[i] = gg;
+    }
+}
+
 }  // namespace
 
 // ------------------------------- C ABI --------------------------------------
@@ -435,4 +516,27 @@ SNRF_API int snrf_proj2pixel_fetch(const float* pts, const float* Ks, const floa
     SNRF_CHECK_ARG(n_cam <= 65535, "snrf_proj2pixel_fetch: at most 65535 cameras per call");
     proj_fetch_kernel<<<dim3(grid1d(B), n_cam), kThreads, 0, (cudaStream_t)stream>>>(pts, Ks, C2Ws, rgbs, fetched_pixels, fetched_colors, B, n_cam, height, width);
     SNRF_RETURN_LAUNCH("snrf_proj2pixel_fetch");
+}
+
+SNRF_API int snrf_nei_sample_fwd(const unsigned char* images, const unsigned char* occlusion, const float* grid, const int* nei_views,
+                                 const unsigned char* nei_valid, float* color, unsigned char* valid_out, int B, int K, int height,
+                                 int width, void* stream)
+{
+    if (B <= 0 || K <= 0) return 0;
+    SNRF_CHECK_ARG(height > 0 && width > 0, "snrf_nei_sample_fwd: empty image (%d x %d)", height, width);
+    SNRF_CHECK_ARG((long long)B * K <= 0x7fffffffll, "snrf_nei_sample_fwd: B * K exceeds 2^31");
+    nei_sample_fwd_kernel<<<grid1d(B * K), kThreads, 0, (cudaStream_t)stream>>>(images, occlusion, (const float2*)grid, nei_views, nei_valid, color,
+                                                                               valid_out, B * K, height, width);
+    SNRF_RETURN_LAUNCH("snrf_nei_sample_fwd");
+}
+
+SNRF_API int snrf_nei_sample_bwd(const unsigned char* images, const float* grid, const int* nei_views, const unsigned char* nei_valid,
+                                 const float* grad_color, float* grad_grid, int B, int K, int height, int width, void* stream)
+{
+    if (B <= 0 || K <= 0) return 0;
+    SNRF_CHECK_ARG(height > 0 && width > 0, "snrf_nei_sample_bwd: empty image (%d x %d)", height, width);
+    SNRF_CHECK_ARG((long long)B * K <= 0x7fffffffll, "snrf_nei_sample_bwd: B * K exceeds 2^31");
+    nei_sample_bwd_kernel<<<grid1d(B * K), kThreads, 0, (cudaStream_t)stream>>>(images, (const float2*)grid, nei_views, nei_valid, grad_color,
+                                                                               (float2*)grad_grid, B * K, height, width);
+    SNRF_RETURN_LAUNCH("snrf_nei_sample_bwd");
 }

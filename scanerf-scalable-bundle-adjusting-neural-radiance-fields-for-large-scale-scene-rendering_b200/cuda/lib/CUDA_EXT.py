@@ -211,6 +211,34 @@ def proj2neighbor_backward(pts, ks, rts, nei_views, nei_valid, dL_dgrid, grad_pt
     gp.done(); gr.done()
 
 
+def neighbor_sample_forward(images, occlusions, grid, nei_views, nei_valid, color, valid_out):
+    """NOT in the reference binding: the device-side form of WarpLoss.sample_neighbor_color (warp_loss.py:441-519),
+    which the reference does with host-resident images and four CPU gathers per step.  images [N,H,W,3] uint8 on the
+    device, occlusions [N,H,W(,1)] bool or None, grid [B,K,2] pixel coordinates, nei_views [B,K] int32, nei_valid
+    [B,K] bool -> color [B,K,3] in [0,1], valid_out [B,K] = nei_valid & occlusions[view, nearest pixel]."""
+    B, K = int(grid.shape[0]), int(grid.shape[1])
+    H, W = int(images.shape[1]), int(images.shape[2])
+    im, g = inp(images, u8, "images"), inp(grid, f32, "grid")
+    oc = inp(occlusions, b8, "occlusions") if occlusions is not None else None
+    nv, ok = inp(nei_views, i32, "nei_views"), inp(nei_valid, b8, "nei_valid")
+    c, vo = Out(color, f32, "color"), Out(valid_out, b8, "valid_out")
+    capi.check(capi.lib().snrf_nei_sample_fwd(ptr(im), ptr(oc), ptr(g), ptr(nv), ptr(ok), c.ptr, vo.ptr, c_int(B), c_int(K), c_int(H),
+                                              c_int(W), capi.stream()), "snrf_nei_sample_fwd")
+    c.done(); vo.done()
+
+
+def neighbor_sample_backward(images, grid, nei_views, nei_valid, grad_color, grad_grid):
+    """grad_grid [B,K,2] = d color / d grid contracted with grad_color [B,K,3] (written, not accumulated)."""
+    B, K = int(grid.shape[0]), int(grid.shape[1])
+    H, W = int(images.shape[1]), int(images.shape[2])
+    im, g = inp(images, u8, "images"), inp(grid, f32, "grid")
+    nv, ok, gc = inp(nei_views, i32, "nei_views"), inp(nei_valid, b8, "nei_valid"), inp(grad_color, f32, "grad_color")
+    gg = Out(grad_grid, f32, "grad_grid")
+    capi.check(capi.lib().snrf_nei_sample_bwd(ptr(im), ptr(g), ptr(nv), ptr(ok), ptr(gc), gg.ptr, c_int(B), c_int(K), c_int(H), c_int(W),
+                                              capi.stream()), "snrf_nei_sample_bwd")
+    gg.done()
+
+
 # ----------------------------------------------------------------------------- image sampling
 def _img_dims(src, grid):
     return int(src.shape[0]), int(grid.shape[1]), int(src.shape[1]), int(src.shape[2])
