@@ -168,6 +168,7 @@ class TileStep:
         self._side = None
         self.consensus = None           # ADMM state, see enable_consensus()
         self.camera_ids = None
+        self.warp = None                # multi-view warp loss, see enable_warp_loss()
 
     def _side_stream(self):
         if self._side is None:
@@ -186,6 +187,14 @@ class TileStep:
         self.consensus = ConsensusManager(self.poses.se3_refine, rho, self.device)
         self.exchange = PoseConsensus(num_camera_global, self.device, group)
         self.confidence = torch.ones(self.camera_ids.shape[0], dtype=torch.float32, device=self.device)
+
+    def enable_warp_loss(self, images, alpha, gamma, weight=1.0, start_step=0, occlusions=None, topK=10):
+        """criterions.py:92-97: adds the multi-view warp loss (warp_loss.WarpLoss) to the step.  images [N,H,W,3] uint8
+        (or float in [0,1]) become device-resident; occlusions [N,H,W,1] bool or None."""
+        from warp_loss import WarpLoss
+        self.warp = WarpLoss(self, images, alpha, gamma, topK=topK)
+        self.warp_weight, self.warp_start = float(weight), int(start_step)
+        self.warp_occlusions = occlusions.to(self.device).contiguous() if occlusions is not None else None
 
     def synchronize(self):
         """TILE.commit + master consensus + TILE.synchronize as one collective (every SYN_ITERS steps)."""
@@ -262,8 +271,19 @@ class TileStep:
         out, ok = self.render_rays(rays_o, rays_d, None, TRAIN)
         if not ok:
             return None, None
-        mse = torch.mean((out["pred_color"] - gt_color) ** 2)            # criterions.py MSE on input/target
+        # criterions.py:126-147: MSE over the rays that were rendered at all (fore_valid | bg_valid) -- as a masked mean,
+        # the reference's boolean indexing would synchronise with the host
+        valid = out["fore_valid"] if out["ret_fg"] else None
+        if out["ret_bg"]:
+            valid = out["bg_valid"] if valid is None else valid | out["bg_valid"]
+        sq = (out["pred_color"] - gt_color) ** 2
+        mse = (sq * valid[:, None]).sum() / (3.0 * valid.sum().clamp_min(1))
         loss = mse + 0.01 * out["l2_reg_specular"]                         # tile.py:999
+        if self.warp is not None and self.global_step >= self.warp_start and self.warp_weight > 0:
+            # "Warp Loss" item (criterions.py:92-97, 148-163) with its warming schedule (:19-22)
+            w = self.warp_weight * max(min(self.global_step / 10000.0, 1.0), 0.0)
+            loss = loss + w * self.warp(self.global_step, out["rays_o"], out["rays_d"], out["pred_depth"], out["pred_diffuse"],
+                                        out["pred_specular"], gt_color, valid, self.warp_occlusions)
         if self.consensus is not None and self.consensus.has_overlap:
             loss = loss + self.consensus.camera_loss()                     # "Admm Loss", weight 1 (criterions.py:107-108)
         return loss, out

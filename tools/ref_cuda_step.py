@@ -141,6 +141,7 @@ def main():
     step.poses = RefPoses(Ks, c2w, dev, None)
     step.num_sample, step.num_bg_sample, step.global_step, step.invalid_underground = cfg["S"], cfg["S_bg"], 10000, False
     step.consensus = None
+    step.warp = None
     step.two_streams = False
     step.joint_chains = False
     step.featureGrid_optimizer = torch.optim.Adam([{"params": step.featureGrid.parameters(), "lr": 1e-3, "betas": (0.9, 0.99), "eps": 1e-15}])
