@@ -68,6 +68,8 @@ int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, const float*
 void snrf_field_set_passes_log2(int bits);
 /* tuning hook: levels [0, n) merge equal-cell lanes of a warp before reducing (-1 = automatic, L / 2) */
 void snrf_field_set_aggregate_levels(int n);
+/* tuning hook: samples per thread of the run-merging scatter kernel (2, 4 or 8; 0 selects the cross-lane kernel) */
+void snrf_field_set_run_length(int r);
 
 /* ---- bundle-adjustment pose chain -------------------------------------------------- */
 /* camera_utils.py:86-89 (CAM.get_rts) + camera.py:84-95, 118-141 (Lie.se3_to_SE3, Taylor series) + camera.py:37-60

@@ -113,7 +113,7 @@ field_fwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
             float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
             for (int k = 0; k < 8; ++k) { acc.x += w[k] * f[k].x; acc.y += w[k] * f[k].y; }
-            out[(size_t)l * N + n] = acc;
+            __stcs(out + (size_t)l * N + n, acc);          // streaming: the table, not the outputs, should stay in L2
             if (JAC) {
                 const float ax = 1.0f - cell.ox, ay = 1.0f - cell.oy, az = 1.0f - cell.oz;
                 const float dxw[8] = {-ay * az, -ay * cell.oz, -cell.oy * az, -cell.oy * cell.oz, ay * az, ay * cell.oz, cell.oy * az, cell.oy * cell.oz};
@@ -127,9 +127,9 @@ field_fwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
                     dz.x += f[k].x * dzw[k]; dz.y += f[k].y * dzw[k];
                 }
                 float2* j = jac + (size_t)l * 3 * N + n;
-                j[0] = make_float2(dx.x * cell.sx, dx.y * cell.sx);
-                j[(size_t)N] = make_float2(dy.x * cell.sy, dy.y * cell.sy);
-                j[2 * (size_t)N] = make_float2(dz.x * cell.sz, dz.y * cell.sz);
+                __stcs(j, make_float2(dx.x * cell.sx, dx.y * cell.sx));
+                __stcs(j + (size_t)N, make_float2(dy.x * cell.sy, dy.y * cell.sy));
+                __stcs(j + 2 * (size_t)N, make_float2(dz.x * cell.sz, dz.y * cell.sz));
             }
         }
     }
@@ -170,7 +170,7 @@ field_bwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
             const f3 x = live ? sample_pos(ld3(rays_o + 3 * (size_t)r), ld3(rays_d + 3 * (size_t)r), z) : mk3(0, 0, 0);
             p = contract(r >= ray_split, x, bmin, bsize);
         }
-        const float2 g = live ? __ldg(grad + (size_t)l * N + n) : make_float2(0.f, 0.f);
+        const float2 g = live ? __ldcs(grad + (size_t)l * N + n) : make_float2(0.f, 0.f);
         const Cell cell = locate_bg(p.c, res + 3 * l);
         uint32_t idx[8]; float w[8];
         corner_idx(idx, cell, mask);
@@ -223,7 +223,7 @@ field_bwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
             f3 gc = mk3(0, 0, 0);
             if (live) {
                 const float2* j = jac + (size_t)l * 3 * N + n;
-                const float2 jx = __ldg(j), jy = __ldg(j + (size_t)N), jz = __ldg(j + 2 * (size_t)N);
+                const float2 jx = __ldcs(j), jy = __ldcs(j + (size_t)N), jz = __ldcs(j + 2 * (size_t)N);
                 gc = mk3(g.x * jx.x + g.y * jx.y, g.x * jy.x + g.y * jy.y, g.x * jz.x + g.y * jz.y);
             }
             if (MODE == kNone) {
@@ -258,6 +258,136 @@ field_bwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
     }
 }
 
+// Backward, second form: every thread owns R consecutive samples of the level-major arrays (consecutive samples of one
+// ray) and merges the samples that fall into the same cell IN REGISTERS before it touches the table: a run of samples in
+// one cell costs 16 FMAs per sample and one set of 8 corner reductions per run.  On the coarse and middle levels runs
+// are long (the cell is larger than the sample spacing), on the fine levels every sample is its own run and the kernel
+// degenerates to the plain scatter.  An alternative to the cross-lane segmented sums of field_bwd_kernel, which spend ~320
+// shuffle / select instructions per sample on the aggregated levels (ncu, profiles/r1e_top_kernels_full.md: 60 % of the
+// issue slots busy, 613 instructions per sample-level, L2 reduction units at 29 %); see g_run_length for the measurement.
+template <int MODE, int R>
+__global__ void __launch_bounds__(kThreads)
+field_bwd_runs_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_vals,
+                      const float* __restrict__ points, const float* __restrict__ bmin_p, const float* __restrict__ bsize_p,
+                      const int* __restrict__ res, const float2* __restrict__ grad, const float2* __restrict__ jac,
+                      float* __restrict__ grad_o, float* __restrict__ grad_d, float* __restrict__ grad_points, float2* __restrict__ grad_table,
+                      const unsigned char* __restrict__ ray_valid, int ray_split, int N, int S, int L, uint32_t T, int pass_bits,
+                      int range_shift)
+{
+    const uint32_t mask = T - 1u;
+    const int lane = threadIdx.x & 31;
+    const int l = blockIdx.y >> pass_bits;
+    const uint32_t pass = blockIdx.y & ((1u << pass_bits) - 1u);
+    f3 bmin = mk3(0, 0, 0), bsize = mk3(1, 1, 1);
+    if (MODE != kNone) { bmin = ld3(bmin_p); bsize = ld3(bsize_p); }
+    const bool want_rays = (pass == 0) && jac != nullptr && (MODE == kNone ? grad_points != nullptr : (grad_o != nullptr || grad_d != nullptr));
+    float2* gl = grad_table + (size_t)l * T;
+    const int* rl = res + 3 * l;
+
+    uint32_t ridx[8];
+    float ax[8], ay[8];
+    int cx = 0, cy = 0, cz = 0;
+    bool have = false;
+    auto flush = [&]() {
+        // x-adjacent corners that share an aligned 16-byte slot go out as one red.v4 (see field_bwd_kernel)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t i0 = ridx[j], i1 = ridx[j + 4];
+            if ((i0 ^ i1) == 1u) {
+                if ((i0 >> range_shift) == pass) {
+                    const bool swap = (i0 & 1u) != 0u;
+                    atomicAdd(reinterpret_cast<float4*>(gl + (i0 & ~1u)),
+                              swap ? make_float4(ax[j + 4], ay[j + 4], ax[j], ay[j]) : make_float4(ax[j], ay[j], ax[j + 4], ay[j + 4]));
+                }
+            } else {
+                if ((i0 >> range_shift) == pass) atomicAdd(gl + i0, make_float2(ax[j], ay[j]));
+                if ((i1 >> range_shift) == pass) atomicAdd(gl + i1, make_float2(ax[j + 4], ay[j + 4]));
+            }
+        }
+    };
+
+    const long long warp0 = (long long)(blockIdx.x * blockDim.x + threadIdx.x) & ~31ll;
+    for (long long wb = warp0; wb * R < N; wb += (long long)gridDim.x * blockDim.x) {
+        const long long n0 = (wb + lane) * R;
+        int r0 = -1, rem0 = 0;
+        if (MODE != kNone && n0 < N) { r0 = (int)(n0 / S); rem0 = (int)(n0 - (long long)r0 * S); }
+        f3 sum_x = mk3(0, 0, 0), sum_z = mk3(0, 0, 0);         // d L / d rays_o, d L / d rays_d of ray r0 from this thread's samples
+        have = false;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const long long n = n0 + i;
+            if (n >= N) break;
+            int r = r0;
+            if (MODE != kNone) {
+                int rem = rem0 + i;
+                while (rem >= S) { rem -= S; ++r; }
+                if (ray_valid != nullptr && !ray_valid[r]) continue;
+            }
+            Pt p;
+            float z = 0.0f;
+            if (MODE == kNone) {
+                p.c = ld3(points + 3 * (size_t)n);
+            } else {
+                z = z_vals[n];
+                p = contract(r >= ray_split, sample_pos(ld3(rays_o + 3 * (size_t)r), ld3(rays_d + 3 * (size_t)r), z), bmin, bsize);
+            }
+            const float2 g = __ldcs(grad + (size_t)l * N + n);
+            const Cell cell = locate_bg(p.c, rl);
+            float w[8];
+            corner_w(w, cell);
+            if (have && cell.ix == cx && cell.iy == cy && cell.iz == cz) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { ax[k] += w[k] * g.x; ay[k] += w[k] * g.y; }
+            } else {
+                if (have) flush();
+                corner_idx(ridx, cell, mask);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { ax[k] = w[k] * g.x; ay[k] = w[k] * g.y; }
+                cx = cell.ix; cy = cell.iy; cz = cell.iz;
+                have = true;
+            }
+            if (want_rays) {
+                const float2* j = jac + (size_t)l * 3 * N + n;
+                const float2 jx = __ldcs(j), jy = __ldcs(j + (size_t)N), jz = __ldcs(j + 2 * (size_t)N);
+                const f3 gc = mk3(g.x * jx.x + g.y * jx.y, g.x * jy.x + g.y * jy.y, g.x * jz.x + g.y * jz.y);
+                if (MODE == kNone) {
+                    atomicAdd(grad_points + 3 * (size_t)n + 0, gc.x);
+                    atomicAdd(grad_points + 3 * (size_t)n + 1, gc.y);
+                    atomicAdd(grad_points + 3 * (size_t)n + 2, gc.z);
+                } else {
+                    const f3 gx = contract_bwd(r >= ray_split, p, gc);
+                    if (r == r0) { sum_x = sum_x + gx; sum_z = sum_z + gx * z; }
+                    else {                                      // the thread's samples straddle two rays (S not a multiple of R)
+                        if (grad_o) { atomicAdd(grad_o + 3 * (size_t)r, gx.x); atomicAdd(grad_o + 3 * (size_t)r + 1, gx.y); atomicAdd(grad_o + 3 * (size_t)r + 2, gx.z); }
+                        if (grad_d) { atomicAdd(grad_d + 3 * (size_t)r, gx.x * z); atomicAdd(grad_d + 3 * (size_t)r + 1, gx.y * z); atomicAdd(grad_d + 3 * (size_t)r + 2, gx.z * z); }
+                    }
+                }
+            }
+        }
+        if (have) flush();
+        if (want_rays && MODE != kNone) {
+            // the 32 R samples of a warp usually belong to one ray: reduce across the warp first
+            const int rl0 = __shfl_sync(0xffffffffu, r0, 0);
+            if (__all_sync(0xffffffffu, r0 == rl0 || r0 < 0)) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    sum_x.x += __shfl_xor_sync(0xffffffffu, sum_x.x, off); sum_x.y += __shfl_xor_sync(0xffffffffu, sum_x.y, off);
+                    sum_x.z += __shfl_xor_sync(0xffffffffu, sum_x.z, off);
+                    sum_z.x += __shfl_xor_sync(0xffffffffu, sum_z.x, off); sum_z.y += __shfl_xor_sync(0xffffffffu, sum_z.y, off);
+                    sum_z.z += __shfl_xor_sync(0xffffffffu, sum_z.z, off);
+                }
+                if (lane == 0 && rl0 >= 0) {
+                    if (grad_o) { atomicAdd(grad_o + 3 * (size_t)rl0, sum_x.x); atomicAdd(grad_o + 3 * (size_t)rl0 + 1, sum_x.y); atomicAdd(grad_o + 3 * (size_t)rl0 + 2, sum_x.z); }
+                    if (grad_d) { atomicAdd(grad_d + 3 * (size_t)rl0, sum_z.x); atomicAdd(grad_d + 3 * (size_t)rl0 + 1, sum_z.y); atomicAdd(grad_d + 3 * (size_t)rl0 + 2, sum_z.z); }
+                }
+            } else if (r0 >= 0) {
+                if (grad_o) { atomicAdd(grad_o + 3 * (size_t)r0, sum_x.x); atomicAdd(grad_o + 3 * (size_t)r0 + 1, sum_x.y); atomicAdd(grad_o + 3 * (size_t)r0 + 2, sum_x.z); }
+                if (grad_d) { atomicAdd(grad_d + 3 * (size_t)r0, sum_z.x); atomicAdd(grad_d + 3 * (size_t)r0 + 1, sum_z.y); atomicAdd(grad_d + 3 * (size_t)r0 + 2, sum_z.z); }
+            }
+        }
+    }
+}
+
 inline int grid_x(int N)
 {
     const int sms = snrf_sm_count();
@@ -270,6 +400,11 @@ inline int grid_x(int N)
 
 int g_pass_bits_override = -1;
 int g_aggregate_override = -1;
+// Samples per thread of field_bwd_runs_kernel; 0 = the cross-lane kernel (default).  Measured on B200 at C2 (4.19 M samples,
+// tools/dbg/sweep_field.py): cross-lane 3.69 ms, run-merging 4.15 / 4.35 / 4.39 ms at R = 2 / 4 / 8 -- merging R samples
+// leaves 32 / R times more same-address reductions on the coarse levels than the cross-lane sums do, and that costs
+// more than the shuffles it saves.  Kept selectable (and parity-tested) for tables / sample densities where runs are longer.
+int g_run_length = 0;
 inline int pick_lpb(int L, int T)
 {
     const long long level_bytes = (long long)T * 8;
@@ -294,6 +429,7 @@ inline int pick_pass_bits(int T)
 // ------------------------------- C ABI --------------------------------------
 SNRF_API void snrf_field_set_passes_log2(int bits) { g_pass_bits_override = bits; }
 SNRF_API void snrf_field_set_aggregate_levels(int n) { g_aggregate_override = n; }
+SNRF_API void snrf_field_set_run_length(int r) { g_run_length = (r == 2 || r == 4 || r == 8) ? r : 0; }
 
 // mode 0: `points` [N,3] are already contracted (rays_o / rays_d / z_vals unused);
 // mode 1 / 2: sample n = rays_o[n / S] + z_vals[n] * rays_d[n / S], contracted with the fore / background map of the
@@ -348,7 +484,12 @@ SNRF_API int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, con
     const int agg = g_aggregate_override >= 0 ? g_aggregate_override : L / 2;
 #define SNRF_BWD(MODE) field_bwd_kernel<MODE><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, res, g, j, grad_rays_o, grad_rays_d, grad_points, gt, ray_valid, ray_split, N, S, L, (uint32_t)T, pass_bits, range_shift, agg)
     const int ray_split = mode == 1 ? 0x7fffffff : (mode == 2 ? 0 : split);
-    if (mode == 0) SNRF_BWD(kNone); else SNRF_BWD(kRays);
+#define SNRF_RUNS(MODE, R) field_bwd_runs_kernel<MODE, R><<<dim3(grid_x((N + R - 1) / R), L << pass_bits), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, res, g, j, grad_rays_o, grad_rays_d, grad_points, gt, ray_valid, ray_split, N, S, L, (uint32_t)T, pass_bits, range_shift)
+    if (g_run_length == 2) { if (mode == 0) SNRF_RUNS(kNone, 2); else SNRF_RUNS(kRays, 2); }
+    else if (g_run_length == 4) { if (mode == 0) SNRF_RUNS(kNone, 4); else SNRF_RUNS(kRays, 4); }
+    else if (g_run_length == 8) { if (mode == 0) SNRF_RUNS(kNone, 8); else SNRF_RUNS(kRays, 8); }
+    else if (mode == 0) SNRF_BWD(kNone); else SNRF_BWD(kRays);
+#undef SNRF_RUNS
 #undef SNRF_BWD
     SNRF_RETURN_LAUNCH("snrf_field_encode_bwd");
 }

@@ -86,6 +86,33 @@ def test_scatter_passes_are_equivalent(bits):
     assert _rel(grads[1], grads[0]) < 1e-6
 
 
+@pytest.mark.parametrize("S", [32, 7, 1])
+@pytest.mark.parametrize("run", [2, 4, 8])
+def test_run_merging_scatter_equals_cross_lane_scatter(run, S):
+    """The scatter kernel that merges runs of samples in one cell in registers (R samples per thread) against the
+    cross-lane kernel: same table gradient and same d/d rays_o, d/d rays_d, for sample counts that are and are not
+    multiples of R (a thread's samples then straddle two rays), with masked rays and a fore/background split."""
+    load_pkg()
+    import scanerf_b200_capi as capi
+    from hashgrid import _field
+    Rn = 301
+    table, res, bmin, bsize, o, d, z_fg, _, g = _case(Rn, S, 14, 5 + S)
+    cot = torch.randn(16, Rn * S, 2, generator=g).to(DEV)
+    valid = (torch.rand(Rn, generator=g) < 0.8).to(DEV)
+    out = []
+    for r in (0, run):
+        capi.lib().snrf_field_set_run_length(capi.c_int(r))
+        t = torch.nn.Parameter(table.to(DEV).clone())
+        oo, dd = o.to(DEV).clone().requires_grad_(True), d.to(DEV).clone().requires_grad_(True)
+        enc = _field.field_encode(oo, dd, z_fg.to(DEV), t, res.to(DEV), bmin.to(DEV), bsize.to(DEV), 3, valid, 120)
+        (enc * cot * valid.repeat_interleave(S)[None, :, None]).sum().backward()
+        out.append((t.grad.clone(), oo.grad.clone(), dd.grad.clone()))
+    capi.lib().snrf_field_set_run_length(capi.c_int(4))
+    for name, a, b in zip(("table", "rays_o", "rays_d"), out[1], out[0]):
+        assert _rel(a, b) < 2e-6, name
+    assert float(out[1][0].abs().max()) > 0 and float(out[1][1].abs().max()) > 0
+
+
 def test_hashgrid_fused_and_unfused_render_agree():
     """HashGrid.render_batch_rays with and without the fused encode gives the same composited colours and gradients."""
     load_pkg()
