@@ -107,7 +107,7 @@ def test_run_merging_scatter_equals_cross_lane_scatter(run, S):
         enc = _field.field_encode(oo, dd, z_fg.to(DEV), t, res.to(DEV), bmin.to(DEV), bsize.to(DEV), 3, valid, 120)
         (enc * cot * valid.repeat_interleave(S)[None, :, None]).sum().backward()
         out.append((t.grad.clone(), oo.grad.clone(), dd.grad.clone()))
-    capi.lib().snrf_field_set_run_length(capi.c_int(4))
+    capi.lib().snrf_field_set_run_length(capi.c_int(0))
     for name, a, b in zip(("table", "rays_o", "rays_d"), out[1], out[0]):
         assert _rel(a, b) < 2e-6, name
     assert float(out[1][0].abs().max()) > 0 and float(out[1][1].abs().max()) > 0

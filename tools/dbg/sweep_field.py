@@ -21,7 +21,7 @@ def measure(name):
 for run in (0, 2, 4, 8, 0, 4):
     capi.lib().snrf_field_set_run_length(capi.c_int(run))
     print("run_length", run, "bwd avg ms", *measure("snrf_field_encode_bwd"), flush=True)
-capi.lib().snrf_field_set_run_length(capi.c_int(4))
+capi.lib().snrf_field_set_run_length(capi.c_int(0))
 for bits in (-1, 0, 1, 2):
     capi.lib().snrf_field_set_passes_log2(capi.c_int(bits))
     print("pass_bits", bits, "bwd avg ms", *measure("snrf_field_encode_bwd"))
@@ -31,6 +31,6 @@ for agg in (0, 4, 8):
     capi.lib().snrf_field_set_aggregate_levels(capi.c_int(agg))
     print("aggregate_levels", agg, "bwd avg ms", *measure("snrf_field_encode_bwd"))
 capi.lib().snrf_field_set_aggregate_levels(capi.c_int(-1))
-capi.lib().snrf_field_set_run_length(capi.c_int(4))
+capi.lib().snrf_field_set_run_length(capi.c_int(0))
 print("fwd avg ms", *measure("snrf_field_encode_fwd"))
 print("adam", *measure("snrf_adam_step"))
