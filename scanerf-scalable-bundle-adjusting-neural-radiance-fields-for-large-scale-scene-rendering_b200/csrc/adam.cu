@@ -49,20 +49,43 @@ adam_dense_kernel(float* __restrict__ p, float* __restrict__ g, float* __restric
     const float bc1 = s_bc[0], bc2 = s_bc[1];
     const long long n4 = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const float4 gg = reinterpret_cast<const float4*>(g)[i];
-        if (gg.x == 0.0f && gg.y == 0.0f && gg.z == 0.0f && gg.w == 0.0f) continue;
-        float4 pp = reinterpret_cast<float4*>(p)[i];
-        float4 mm = reinterpret_cast<float4*>(m)[i];
-        float4 vv = reinterpret_cast<float4*>(v)[i];
-        if (gg.x != 0.0f) adam_elem(pp.x, gg.x, mm.x, vv.x, h, bc1, bc2);
-        if (gg.y != 0.0f) adam_elem(pp.y, gg.y, mm.y, vv.y, h, bc1, bc2);
-        if (gg.z != 0.0f) adam_elem(pp.z, gg.z, mm.z, vv.z, h, bc1, bc2);
-        if (gg.w != 0.0f) adam_elem(pp.w, gg.w, mm.w, vv.w, h, bc1, bc2);
-        reinterpret_cast<float4*>(p)[i] = pp;
-        reinterpret_cast<float4*>(m)[i] = mm;
-        reinterpret_cast<float4*>(v)[i] = vv;
-        if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // kUnroll float4 groups per thread and trip, in two phases: all gradient loads first, then the (conditional) loads of
+    // the parameter and the two moments of every touched group, so that independent loads overlap instead of forming a
+    // dependent pair.  Measured on B200 at C2 (2 GiB table, ~60 % of the groups touched): 1 group 2.35 ms, 2 groups
+    // 2.14 ms, 4 groups 2.62 ms (112 registers: the occupancy lost costs more than the overlap gains); streaming
+    // cache hints (ld.cs / st.cs) on top made it slower still.
+    constexpr int kUnroll = 2;
+    float4* p4 = reinterpret_cast<float4*>(p);
+    float4* g4 = reinterpret_cast<float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    for (long long base = (long long)blockIdx.x * blockDim.x * kUnroll + threadIdx.x; base < n4; base += stride * kUnroll) {
+        float4 gg[kUnroll], pp[kUnroll], mm[kUnroll], vv[kUnroll];
+        bool act[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long i = base + (long long)u * blockDim.x;
+            gg[u] = i < n4 ? g4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long i = base + (long long)u * blockDim.x;
+            act[u] = !(gg[u].x == 0.0f && gg[u].y == 0.0f && gg[u].z == 0.0f && gg[u].w == 0.0f);
+            if (act[u]) { pp[u] = p4[i]; mm[u] = m4[i]; vv[u] = v4[i]; }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (!act[u]) continue;
+            const long long i = base + (long long)u * blockDim.x;
+            if (gg[u].x != 0.0f) adam_elem(pp[u].x, gg[u].x, mm[u].x, vv[u].x, h, bc1, bc2);
+            if (gg[u].y != 0.0f) adam_elem(pp[u].y, gg[u].y, mm[u].y, vv[u].y, h, bc1, bc2);
+            if (gg[u].z != 0.0f) adam_elem(pp[u].z, gg[u].z, mm[u].z, vv[u].z, h, bc1, bc2);
+            if (gg[u].w != 0.0f) adam_elem(pp[u].w, gg[u].w, mm[u].w, vv[u].w, h, bc1, bc2);
+            p4[i] = pp[u];
+            m4[i] = mm[u];
+            v4[i] = vv[u];
+            if (zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     // tail
     for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
