@@ -387,7 +387,7 @@ def main():
         cores = os.cpu_count() or 1
         from oracle import native as on
         on.build()
-        rays, passes = 2048, 5
+        rays, passes = 2048, 8
         port = CpuPort(cfg, rays, cores)
         port.step()                                           # untimed: thread pools, allocator
         sec = sum(port.step() for _ in range(passes)) / passes
