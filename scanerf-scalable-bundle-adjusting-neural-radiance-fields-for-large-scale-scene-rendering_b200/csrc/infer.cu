@@ -804,8 +804,9 @@ int launch_work(const InferArgs& a, int nb, void* stream, const char* name)
     for (long long n0 = 0; n0 < total; n0 += chunk) {
         const int Nc = (int)(total - n0 < chunk ? total - n0 : chunk);
         const int gp = snrf_div_up(Nc, 256);
-        cudaMemsetAsync(w.counts, 0, (size_t)(3 * nb + 1) * 4, s);
-        cudaMemsetAsync(w.row_sample, 0xff, (size_t)max_rows * 4, s);
+        e = cudaMemsetAsync(w.counts, 0, (size_t)(3 * nb + 1) * 4, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(w.row_sample, 0xff, (size_t)max_rows * 4, s);
+        if (e != cudaSuccess) break;
         work_plan_kernel<MODE, false><<<gp, 256, 0, s>>>(a, n0, Nc, w);
         work_scan_kernel<<<1, 256, 0, s>>>(w, nb);
         work_plan_kernel<MODE, true><<<gp, 256, 0, s>>>(a, n0, Nc, w);
@@ -816,7 +817,7 @@ int launch_work(const InferArgs& a, int nb, void* stream, const char* name)
         else work_decode_kernel<false><<<sms, kThreadsDec, fwd_smem<false>(), s>>>(a, n0, w);
         work_combine_kernel<MODE><<<gp < sms * 32 ? gp : sms * 32, 256, 0, s>>>(a, n0, Nc, w);
     }
-    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
     cudaFreeAsync(base, s);
     if (e != cudaSuccess) { snrf_set_error("%s: %s", name, cudaGetErrorString(e)); return (int)e; }
     return 0;
