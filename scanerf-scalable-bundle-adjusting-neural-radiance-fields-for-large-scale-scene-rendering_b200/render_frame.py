@@ -95,9 +95,13 @@ def pinhole_rays(H, W, K, c2w, device):
 
 
 @torch.no_grad()
-def render_rays(ts, rays_o, rays_d, num_sample=128, num_bg_sample=128, sample_range=1e6, max_tracing=None):
+def render_rays(ts, rays_o, rays_d, num_sample=128, num_bg_sample=128, sample_range=1e6, max_tracing=None, adaptive=True):
     """render_rays_base (rendering.py:286-544) for a flat batch of rays.  Returns per-ray
-    (diffuse [B,3], specular [B,3], depth [B,1], transparency [B,1])."""
+    (diffuse [B,3], specular [B,3], depth [B,1], transparency [B,1]).
+    adaptive (scenes of several tiles): read the number of tracing rounds (the most tiles any ray crosses) and of
+    background slots in use back from the device, as the reference does (rendering.py:318-320, 470) -- two host
+    synchronisations per call that save the empty rounds.  adaptive=False runs the worst-case counts and never
+    synchronises (for callers that pipeline frames or capture the call in a CUDA graph)."""
     dev, B, nb = rays_o.device, rays_o.shape[0], ts.num_tiles
     f32 = torch.float32
     intersections = torch.full((B, nb, 2), MISS, dtype=f32, device=dev)
@@ -112,8 +116,10 @@ def render_rays(ts, rays_o, rays_d, num_sample=128, num_bg_sample=128, sample_ra
     block_idxs = torch.empty(B, num_sample, 4, dtype=torch.int16, device=dev)
     pts_d, pts_s = torch.empty(B, num_sample, 3, dtype=f32, device=dev), torch.empty(B, num_sample, 3, dtype=f32, device=dev)
     pts_a = torch.empty(B, num_sample, 1, dtype=f32, device=dev)
-    # a ray meets each tile at most once: nb rounds always suffice (the reference asks the device for the max)
-    for _ in range(nb if max_tracing is None else max_tracing):
+    if max_tracing is None:
+        # a ray meets each tile at most once: nb rounds always suffice
+        max_tracing = int((intersections[..., 0] != MISS).sum(-1).max()) if (adaptive and nb > 1) else nb
+    for _ in range(max_tracing):
         running = (tracing_idx < nb) & (transparency > 1e-5)
         z_vals.fill_(-1.0); dists.fill_(-1.0); block_idxs.fill_(-1)
         ops.sample_points(rays_o, rays_d, ts.block_corner, ts.block_size, ts.fake_occupied_grid, ts.grid_starts, ts.grid_log2dim,
@@ -132,7 +138,10 @@ def render_rays(ts, rays_o, rays_d, num_sample=128, num_bg_sample=128, sample_ra
         pts_d, pts_s = torch.empty(B, num_bg_sample, 3, dtype=f32, device=dev), torch.empty(B, num_bg_sample, 3, dtype=f32, device=dev)
         pts_a = torch.empty(B, num_bg_sample, 1, dtype=f32, device=dev)
     bg_zv = torch.empty(B, num_bg_sample, dtype=f32, device=dev)
-    for i in range(min(4, nb)):           # at most min(4, tiles) exit tiles share the farthest face
+    n_bg = min(4, nb)                     # at most min(4, tiles) exit tiles share the farthest face
+    if adaptive and nb > 1:
+        n_bg = int((bg_w > 0).sum(-1).max())
+    for i in range(n_bg):
         bg_zv.fill_(-1.0); pts_d.zero_(); pts_s.zero_(); pts_a.zero_()
         ops.inverse_z_sampling(intersections, bg_bidxs[..., i].contiguous(), bg_zv, sample_range)
         ops.bg_pts_inference_v2(rays_o, rays_d, bg_zv, bg_bidxs, i, ts.block_corner, ts.block_size, ts.resolution, ts.feature_tables,
