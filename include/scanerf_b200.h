@@ -248,7 +248,8 @@ int snrf_bg_pts_inference_v2(const float* rays_o, const float* rays_d, const flo
 void snrf_infer_set_precision(int split);
 /* tuning hook: 128-sample tiles in flight per CTA for single-tile scenes (1 or 2, default 1: see csrc/infer.cu) */
 void snrf_infer_set_inflight(int tiles);
-/* tuning hook: single-tile scenes use the two-pass (level-major encode + decoder) path (default 1) */
+/* tuning hook: 1 (default) = multi-pass paths (single-tile two-pass, multi-tile grouped), 0 = the fused kernel,
+ * 2 = the grouped (compacting) path also for single-tile scenes */
 void snrf_infer_set_two_pass(int on);
 /* The multi-pass inference paths keep their scratch (features of one 4 Mi-sample chunk, <= 3.1 GB) in a private
  * stream-ordered pool between calls; this synchronises the device and returns that memory to the driver. */

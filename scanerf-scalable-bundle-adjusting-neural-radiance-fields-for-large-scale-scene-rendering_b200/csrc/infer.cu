@@ -827,7 +827,7 @@ int launch_work(const InferArgs& a, int nb, void* stream, const char* name)
 template <int MODE>
 int launch(const InferArgs& a, int nb, void* stream, const char* name)
 {
-    if (g_infer_two_pass) return (nb == 1 && MODE != kBackBlend) ? launch_two_pass<MODE>(a, stream, name) : launch_work<MODE>(a, nb, stream, name);
+    if (g_infer_two_pass) return (nb == 1 && MODE != kBackBlend && g_infer_two_pass != 2) ? launch_two_pass<MODE>(a, stream, name) : launch_work<MODE>(a, nb, stream, name);
     return (nb == 1 && g_infer_inflight == 2) ? launch_ncg<MODE, 2>(a, stream, name) : launch_ncg<MODE, 4>(a, stream, name);
 }
 
@@ -836,7 +836,7 @@ int launch(const InferArgs& a, int nb, void* stream, const char* name)
 // ------------------------------- C ABI --------------------------------------
 SNRF_API void snrf_infer_set_precision(int split) { g_infer_split = split ? 1 : 0; }
 SNRF_API void snrf_infer_set_inflight(int tiles) { g_infer_inflight = tiles == 2 ? 2 : 1; }
-SNRF_API void snrf_infer_set_two_pass(int on) { g_infer_two_pass = on ? 1 : 0; }
+SNRF_API void snrf_infer_set_two_pass(int on) { g_infer_two_pass = on == 2 ? 2 : (on ? 1 : 0); }
 SNRF_API int snrf_infer_release_scratch(void)
 {
     int dev = 0;
