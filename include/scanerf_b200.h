@@ -91,6 +91,13 @@ int snrf_compute_ray_bwd(const float* grad_o, const float* grad_d, const float* 
  * centers[K,3], sizes[K,3] (full extents) -> bounds[B,K,2] = (near,far) or (-1,-1). */
 int snrf_ray_aabb(const float* rays_o, const float* rays_d, const float* centers, const float* sizes,
                   float* bounds, int B, int K, void* stream);
+/* HashGrid.inverse_z_sampling + invalid_sampling_underground (hashgrid/__init__.py:287-293, 305-337; torch ops in
+ * the reference): background samples z = 1 / (1 / (far + 1e-6) (1 - t) + t / 1e6) from the exit of the box
+ * (center[3], size[3] full extents; far = 0.1 when the ray misses it), t_lin [S] = linspace(0, 1, S);
+ * dists = forward differences (last 1e-6); valid [B] bytes (optional) = the exit is not on the floor face
+ * (invalid_underground != 0) or all ones.  Bit-identical to the torch expression. */
+int snrf_bg_inverse_z(const float* rays_o, const float* rays_d, const float* center, const float* size, const float* t_lin,
+                      float* z_vals, float* dists, unsigned char* valid, int B, int S, int invalid_underground, void* stream);
 /* cuda/include/helper.h (sample_points_grid): occupied[2^lx,2^ly,2^lz] bytes, log2dim[3] i32
  * (device) -> z_vals, dists [B,S]; counts[B] i32 optional (occupied segments per ray). */
 int snrf_sample_grid(const float* rays_o, const float* rays_d, float* z_vals, float* dists,

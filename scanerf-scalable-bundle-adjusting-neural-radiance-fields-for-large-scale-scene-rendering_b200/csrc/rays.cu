@@ -117,6 +117,41 @@ ray_aabb_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays
     }
 }
 
+
+// ----------------------------- background inverse-depth samples -----------------------------
+// HashGrid.inverse_z_sampling + invalid_sampling_underground (hashgrid/__init__.py:287-293, 305-337) as one kernel;
+// the reference evaluates it as ~25 small torch launches per step.  Every operation is rounded separately, in the order
+// torch evaluates the expression  1 / (1 / (far + 1e-6) * (1 - t) + 1 / 1e6 * t), so the depths are bit-identical to it.
+// t_lin = torch.linspace(0, 1, S) (an input: its construction is torch's).  One thread per sample.
+__global__ void __launch_bounds__(kThreads)
+bg_inverse_z_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ center_p,
+                    const float* __restrict__ size_p, const float* __restrict__ t_lin, float* __restrict__ z_vals,
+                    float* __restrict__ dists, unsigned char* __restrict__ valid, int B, int S, int invalid_underground)
+{
+    const f3 c = ld3(center_p), h = ld3(size_p) * 0.5f;
+    const float floor_y = c.y - h.y;
+    const long long total = (long long)B * S;
+    for (long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x; n < total; n += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(n / S), k = (int)(n - (long long)i * S);
+        const f3 o = ld3(rays_o + 3 * (size_t)i), d = ld3(rays_d + 3 * (size_t)i);
+        const float2 tb = ray_aabb(o, d, c, h);
+        if (k == 0 && valid != nullptr) {
+            bool ok = true;
+            if (invalid_underground) ok = !(fabsf(__fadd_rn(o.y, __fmul_rn(tb.y, d.y)) - floor_y) < 0.0001f);
+            valid[i] = ok ? 1 : 0;
+        }
+        const float far = (tb.x == -1.0f || tb.y == -1.0f) ? 0.1f : tb.y;
+        const float inv_far = __fdiv_rn(1.0f, __fadd_rn(far, 1e-6f));
+        auto depth = [&](int kk) {
+            const float t = t_lin[kk];
+            return __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(inv_far, __fsub_rn(1.0f, t)), __fmul_rn(1e-6f, t)));
+        };
+        const float z = depth(k);
+        z_vals[n] = z;
+        dists[n] = (k == S - 1) ? 1e-6f : __fsub_rn(depth(k + 1), z);
+    }
+}
+
 // ----------------------------- occupancy DDA --------------------------------
 // One thread per ray, two passes of the walk (total occupied length, then
 // proportional placement) exactly like cuda/helper_kernel.cu:539-615.  Output rows
@@ -275,4 +310,14 @@ SNRF_API int snrf_sample_insideout(const float* rays_o, const float* rays_d, int
     if (B <= 0) return 0;
     insideout_kernel<<<grid1d(B), kThreads, 0, (cudaStream_t)stream>>>(rays_o, rays_d, S, Sbg, center, size, B, far, z_vals, z_vals_bg, miss_flag);
     SNRF_RETURN_LAUNCH("snrf_sample_insideout");
+}
+
+SNRF_API int snrf_bg_inverse_z(const float* rays_o, const float* rays_d, const float* center, const float* size, const float* t_lin,
+                               float* z_vals, float* dists, unsigned char* valid, int B, int S, int invalid_underground, void* stream)
+{
+    SNRF_CHECK_ARG(S > 0 && t_lin != nullptr, "snrf_bg_inverse_z: S must be positive and t_lin given (S=%d)", S);
+    if (B <= 0) return 0;
+    bg_inverse_z_kernel<<<grid1d((long long)B * S), kThreads, 0, (cudaStream_t)stream>>>(rays_o, rays_d, center, size, t_lin, z_vals, dists, valid,
+                                                                                      B, S, invalid_underground);
+    SNRF_RETURN_LAUNCH("snrf_bg_inverse_z");
 }

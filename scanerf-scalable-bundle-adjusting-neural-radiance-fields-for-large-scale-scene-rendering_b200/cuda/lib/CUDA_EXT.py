@@ -97,6 +97,24 @@ def background_sampling_cuda(rays_o, rays_d, starts, bg_depth, z_vals, num_sampl
     z.done()
 
 
+def bg_inverse_z_sampling(rays_o, rays_d, aabb_center, aabb_size, t_lin, z_vals, dists, valid=None, invalid_underground=False):
+    """NOT in the reference binding: HashGrid.inverse_z_sampling (hashgrid/__init__.py:305-337, ~25 torch launches in the
+    reference) as one kernel, bit-identical to the torch expression.  t_lin [S] = torch.linspace(0, 1, S); writes
+    z_vals, dists [B,S] and (optionally) valid [B] bool."""
+    B, S = int(z_vals.shape[0]), int(z_vals.shape[1])
+    o, d = inp(rays_o, f32, "rays_o"), inp(rays_d, f32, "rays_d")
+    c, s, t = inp(aabb_center, f32, "aabb_center"), inp(aabb_size, f32, "aabb_size"), inp(t_lin, f32, "t_lin")
+    if int(t.numel()) != S:
+        raise RuntimeError(f"bg_inverse_z_sampling: t_lin must hold {S} values (got {int(t.numel())})")
+    z, di = Out(z_vals, f32, "z_vals"), Out(dists, f32, "dists")
+    v = Out(valid, b8, "valid") if valid is not None else None
+    capi.check(capi.lib().snrf_bg_inverse_z(ptr(o), ptr(d), ptr(c), ptr(s), ptr(t), z.ptr, di.ptr, v.ptr if v is not None else c_void_p(0),
+                                            c_int(B), c_int(S), c_int(int(bool(invalid_underground))), capi.stream()), "snrf_bg_inverse_z")
+    z.done(); di.done()
+    if v is not None:
+        v.done()
+
+
 def sample_insideout_block(rays_o, rays_d, num_sample, num_sample_bg, block_center, block_size, far,
                            z_vals, z_vals_bg):
     """cuda/include/sample.h -- uniform inside the box + inverse-z beyond it.  A ray

@@ -18,7 +18,7 @@ from .lib.HASHGRID import *  # noqa: F401,F403  (operator surface, incl. Sampler
 from .lib import HASHGRID as _ops
 from . import _decoder, _field, _render
 
-from cuda import ray_aabb_intersection, sample_points_grid, voxelize_mesh
+from cuda import bg_inverse_z_sampling, ray_aabb_intersection, sample_points_grid, voxelize_mesh
 
 try:                      # the reference does `from cfg import *` (TRAIN = 0, INFERENCE = 1)
     from cfg import TRAIN, INFERENCE
@@ -186,8 +186,18 @@ class HashGrid(nn.Module):
     def weight_feature(self, global_step):
         """Coarse-to-fine level weights [16] (hashgrid/__init__.py:228-235)."""
         alpha = max(min(global_step / 10000 * 8 + 8, 16), 0)
+        cached = getattr(self, "_level_weights", None)
+        if cached is not None and cached[0] == alpha:       # constant once the schedule has saturated: no launches
+            return cached[1]
         k = torch.arange(N_LEVELS, dtype=torch.float32, device=self.device)
-        return (1 - torch.cos((alpha - k).clamp(min=0, max=1) * np.pi)) / 2
+        w = (1 - torch.cos((alpha - k).clamp(min=0, max=1) * np.pi)) / 2
+        self._level_weights = (alpha, w, w.repeat_interleave(2))
+        return w
+
+    def level_mask32(self, global_step):
+        """weight_feature repeated per feature channel [32] (cached with it)."""
+        self.weight_feature(global_step)
+        return self._level_weights[2]
 
     def weight_bg_feature(self, ratio):
         alpha = torch.clamp(ratio * 8 + 8, 0, 16)
@@ -196,13 +206,26 @@ class HashGrid(nn.Module):
         return w.repeat_interleave(2, dim=-1)
 
     # ------------------------------------------------------------------ sampling
-    def samplePoints(self, rays_o, rays_d, num_sample):
-        """Occupancy-proportional foreground samples; -1 rows = ray sees nothing."""
-        shape = (rays_o.shape[0], num_sample)
-        z_vals = torch.full(shape, -1, dtype=torch.float32, device=self.device)
-        dists = torch.full(shape, -1, dtype=torch.float32, device=self.device)
-        sample_points_grid(rays_o, rays_d, z_vals, dists, self.min_bbox + self.bbox_size / 4.0,
-                           self.bbox_size / 2.0, self.occupied_grid, self.sampler_log2dim)
+    def _inner_box(self):
+        """(corner, size, centre) of the foreground box = the inner half of the doubled tile box (cached constants)."""
+        box = getattr(self, "_inner_box_cache", None)
+        if box is None or box[3] is not self.min_bbox or box[4] is not self.bbox_size:
+            box = ((self.min_bbox + self.bbox_size / 4.0).contiguous(), (self.bbox_size / 2.0).contiguous(), self.bbox_center.contiguous(),
+                   self.min_bbox, self.bbox_size)
+            self._inner_box_cache = box
+        return box
+
+    def samplePoints(self, rays_o, rays_d, num_sample, out=None):
+        """Occupancy-proportional foreground samples; -1 rows = ray sees nothing.  out = (z_vals, dists) buffers to fill."""
+        if out is None:
+            shape = (rays_o.shape[0], num_sample)
+            z_vals = torch.empty(shape, dtype=torch.float32, device=self.device)
+            dists = torch.empty(shape, dtype=torch.float32, device=self.device)
+        else:
+            z_vals, dists = out
+        z_vals.fill_(-1.0); dists.fill_(-1.0)
+        corner, size, _, _, _ = self._inner_box()
+        sample_points_grid(rays_o, rays_d, z_vals, dists, corner, size, self.occupied_grid, self.sampler_log2dim)
         return z_vals, dists
 
     def invalid_sampling_underground(self, rays_o, rays_d, bound):
@@ -217,8 +240,20 @@ class HashGrid(nn.Module):
         return z_vals, dists, valid
 
     @torch.no_grad()
-    def inverse_z_sampling(self, rays_o, rays_d, num_sample, invalid_underground=True, perturb=False):
-        """Inverse-depth samples from the tile exit to 1e6 (hashgrid/__init__.py:305-337)."""
+    def inverse_z_sampling(self, rays_o, rays_d, num_sample, invalid_underground=True, perturb=False, out=None):
+        """Inverse-depth samples from the tile exit to 1e6 (hashgrid/__init__.py:305-337).  On the device the whole
+        expression is one kernel (bit-identical to the torch ops below); out = (z_vals, dists) buffers to fill."""
+        if rays_o.is_cuda and self.fused_encode:
+            lin = getattr(self, "_linspace", None)
+            if lin is None or lin.numel() != num_sample:
+                lin = self._linspace = torch.linspace(0.0, 1.0, steps=num_sample, device=self.device)
+            R = rays_o.shape[0]
+            z_vals, dists = out if out is not None else (torch.empty(R, num_sample, dtype=torch.float32, device=self.device),
+                                                         torch.empty(R, num_sample, dtype=torch.float32, device=self.device))
+            valid = torch.empty(R, dtype=torch.bool, device=self.device)
+            _, size, center, _, _ = self._inner_box()
+            bg_inverse_z_sampling(rays_o, rays_d, center, size, lin, z_vals, dists, valid, invalid_underground)
+            return z_vals, dists, valid
         bounds = torch.full((rays_o.shape[0], 2), -1, dtype=torch.float32, device=rays_o.device)
         ray_aabb_intersection(rays_o, rays_d, self.bbox_center, self.bbox_size / 2.0, bounds)
         if invalid_underground:
@@ -292,7 +327,7 @@ class HashGrid(nn.Module):
         back with the values the reference scatters for them (colour 0, depth 0, T_left 1).  Static shapes,
         no device->host synchronisation anywhere."""
         R, S = z_vals.shape
-        mask32 = self.weight_feature(global_step).repeat_interleave(2)
+        mask32 = self.level_mask32(global_step)
         feats = _field.field_encode(rays_o, rays_d, z_vals, self.HE.features, self.HE.resolution, self.min_bbox,
                                     self.bbox_size, contract_mode, valid)
         heads = _field.decoder_apply(feats, rays_d, mask32, S, params, valid)
@@ -310,14 +345,17 @@ class HashGrid(nn.Module):
         if params is None:
             return None
         R = rays_o.shape[0]
-        z_f, d_f = self.samplePoints(rays_o, rays_d, num_sample)
+        # both samplers write straight into the halves of the joint [2R, S] buffers
+        z2 = torch.empty(2 * R, num_sample, dtype=torch.float32, device=self.device)
+        dist2 = torch.empty(2 * R, num_sample, dtype=torch.float32, device=self.device)
+        z_f, d_f = self.samplePoints(rays_o, rays_d, num_sample, out=(z2[:R], dist2[:R]))
         v_f = torch.all(z_f != -1, dim=-1)
-        z_b, d_b, v_b = self.inverse_z_sampling(rays_o, rays_d, num_sample, invalid_underground)
+        z_b, d_b, v_b = self.inverse_z_sampling(rays_o, rays_d, num_sample, invalid_underground, out=(z2[R:], dist2[R:]))
         if occlusion_mask is not None:
             v_f, v_b = v_f & occlusion_mask[..., 0], v_b & occlusion_mask[..., 0]
         o2, d2 = torch.cat([rays_o, rays_o], 0), torch.cat([rays_d, rays_d], 0)
-        z2, dist2, valid2 = torch.cat([z_f, z_b], 0), torch.cat([d_f, d_b], 0), torch.cat([v_f, v_b], 0)
-        mask32 = self.weight_feature(global_step).repeat_interleave(2)
+        valid2 = torch.cat([v_f, v_b], 0)
+        mask32 = self.level_mask32(global_step)
         feats = _field.field_encode(o2, d2, z2, self.HE.features, self.HE.resolution, self.min_bbox, self.bbox_size, 3, valid2, R)
         heads = _field.decoder_apply(feats, d2, mask32, num_sample, params, valid2)
         row, weights = _render.CompositePackedFn.apply(heads, z2, dist2, d2, R, valid2)      # rays >= R end at infinity

@@ -182,3 +182,39 @@ def test_pose_chain_kernel_matches_torch_chain():
         assert torch.allclose(out.detach().cpu(), ref.detach(), rtol=1e-5, atol=2e-5), n    # alternating 11-term series: rounding grows with |w|
         scale_g = max(float(a.grad.abs().max()), 1e-6)
         assert float((b.grad.cpu() - a.grad).abs().max()) / scale_g < 1e-4, (n, float((b.grad.cpu() - a.grad).abs().max()), scale_g)
+
+
+@pytest.mark.parametrize("S", [128, 33, 2])
+@pytest.mark.parametrize("underground", [False, True])
+def test_background_inverse_z_kernel_is_bit_identical_to_the_torch_expression(S, underground):
+    """HashGrid.inverse_z_sampling: the one-kernel form against the torch op sequence of the reference
+    (hashgrid/__init__.py:305-337), including rays that miss the box and rays that leave through the floor."""
+    load_pkg()
+    import os
+    import tempfile
+    import scenes
+    from hashgrid import HashGrid
+    dev = torch.device("cuda:0")
+    ply = os.path.join(tempfile.mkdtemp(), "mesh.ply")
+    scenes.write_proxy_mesh_ply(ply, (0, 0, 0), (20, 13, 30), seed=0, ground_res=8, n_boxes=3)
+    f = lambda v: torch.tensor(v, dtype=torch.float32, device=dev)
+    hg = HashGrid(dev, f([0.0, 0.0, 0.0]), f([20.0, 13.0, 30.0]), 12, [16, 256], 3, False, ply)
+    g = torch.Generator().manual_seed(S)
+    B = 5000
+    o = (torch.tensor([10.0, 6.5, 15.0]) + (torch.rand(B, 3, generator=g) - 0.5) * torch.tensor([30.0, 20.0, 45.0])).to(dev)   # some outside the box
+    d = torch.randn(B, 3, generator=g)
+    d[:500, 1] = -d[:500, 1].abs() - 0.5                       # towards the floor
+    d[500:520, 0] = 0.0
+    d = (d * (0.3 + torch.rand(B, 1, generator=g))).to(dev)
+    z1, di1, v1 = hg.inverse_z_sampling(o, d, S, invalid_underground=underground)
+    hg.fused_encode = False
+    z0, di0, v0 = hg.inverse_z_sampling(o, d, S, invalid_underground=underground)
+    hg.fused_encode = True
+    assert torch.equal(v1, v0)
+    assert underground is False or (bool((~v0).any()) and bool(v0.any()))
+    assert torch.equal(z1, z0.contiguous()), float((z1 - z0).abs().max())
+    assert torch.equal(di1, di0), float((di1 - di0).abs().max())
+    # writing into caller buffers (the joint fore/background batch)
+    zb, db = torch.full((2 * B, S), 7.0, device=dev), torch.full((2 * B, S), 7.0, device=dev)
+    hg.inverse_z_sampling(o, d, S, invalid_underground=underground, out=(zb[B:], db[B:]))
+    assert torch.equal(zb[B:], z1) and torch.equal(db[B:], di1) and bool((zb[:B] == 7.0).all())
