@@ -38,22 +38,15 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_reference_cuda_step.json"))
-    args = ap.parse_args()
+def build_reference_step(dev, tile_corner, tile_size, Ks, c2w, log2T, grid_resolution, sampler_log2dim, S, S_bg, ply, global_step=10000,
+                         lr_table=1e-3, lr_decoder=1e-3, lr_cam=1e-4):
+    """A TileStep whose render path is the reference's op-by-op graph on the REFERENCE's kernels (oracle/_ref), with the
+    reference's optimisers (dense torch Adam over the table).  pkg.install() must have run."""
     import CUDA_EXT as REF_CUDA  # noqa: the rebuilt reference modules
     import HASHGRID_EMBED as REF_HASH
-    pkg = importlib.import_module(bench.PKG)
-    pkg.install()
     import tile_step as ts
     from hashgrid import HashGrid, TRAIN
     from hashgrid._decoder import ShallowMLP
-
-    cfg = bench.WORKLOADS["default.yaml-single-tile"]
-    dev = torch.device("cuda:0")
 
     class RefEncode(torch.autograd.Function):          # hashgrid/PyHashGridBG.py:9-30, literally
         @staticmethod
@@ -76,14 +69,14 @@ def main():
         fused_decoder = False
         fused_encode = False
 
-        def samplePoints(self, rays_o, rays_d, num_sample):
+        def samplePoints(self, rays_o, rays_d, num_sample, out=None):
             z = torch.full((rays_o.shape[0], num_sample), -1, dtype=torch.float32, device=self.device)
             d = torch.full((rays_o.shape[0], num_sample), -1, dtype=torch.float32, device=self.device)
             REF_CUDA.sample_points_grid(rays_o, rays_d, z, d, self.min_bbox + self.bbox_size / 4.0, self.bbox_size / 2.0,
                                         self.occupied_grid, self.sampler_log2dim)
             return z, d
 
-        def inverse_z_sampling(self, rays_o, rays_d, num_sample, invalid_underground=True, perturb=False):
+        def inverse_z_sampling(self, rays_o, rays_d, num_sample, invalid_underground=True, perturb=False, out=None):
             bounds = torch.full((rays_o.shape[0], 2), -1, dtype=torch.float32, device=rays_o.device)
             REF_CUDA.ray_aabb_intersection(rays_o, rays_d, self.bbox_center, self.bbox_size / 2.0, bounds)
             valid = torch.ones_like(rays_d[..., 0]).bool()
@@ -97,12 +90,12 @@ def main():
         def render_batch_rays(self, rays_o, rays_d, z_vals, dists, decoder, mode, contract_func, out_normal=False, infinity=False, **kw):
             if z_vals.shape[0] == 0:
                 return None, False
-            R, S = z_vals.shape
+            R, S_ = z_vals.shape
             samples = rays_o[:, None, :] + z_vals[..., None] * rays_d[:, None, :]
             cx, _ = contract_func(samples.reshape(-1, 3))
-            feats = RefEncode.apply(cx.contiguous(), self.HE.features, self.HE.resolution).reshape(R, S, 32)
+            feats = RefEncode.apply(cx.contiguous(), self.HE.features, self.HE.resolution).reshape(R, S_, 32)
             mask32 = self.weight_feature(kw["global_step"])[None, None, :].repeat_interleave(2, dim=-1)
-            heads = decoder(torch.cat([feats, rays_d[:, None, :].repeat(1, S, 1)], -1), weight_feature=mask32)
+            heads = decoder(torch.cat([feats, rays_d[:, None, :].repeat(1, S_, 1)], -1), weight_feature=mask32)
             weights, T_left = self.cal_integrate_weight(heads["sigma"], z_vals, dists.clone(), rays_d, infinity=infinity)
             out = {"depth": self.accumulate(weights, z_vals[..., None]), "tint": self.accumulate(weights, heads["tint"]),
                    "diffuse": self.accumulate(weights, heads["diffuse"]),
@@ -114,39 +107,54 @@ def main():
 
     class RefPoses(ts.Poses):
         def rays(self, locs):                           # camera.py:259-281 in torch, autograd to se3_refine
-            c2w = ts.pose_invert(self.get_rts())
+            c2w_ = ts.pose_invert(self.get_rts())
             v = locs[:, 0].long()
             K = self.ks[v]
             x = (locs[:, 1].float() + 0.5 - K[:, 0, 2]) / K[:, 0, 0]
             y = (locs[:, 2].float() + 0.5 - K[:, 1, 2]) / K[:, 1, 1]
             d_cam = torch.stack([x, y, torch.ones_like(x)], -1)
-            M = c2w[v]
+            M = c2w_[v]
             return M[:, :, 3].contiguous(), (M[:, :, :3] @ d_cam[..., None])[..., 0].contiguous()
 
+    f = lambda v: torch.as_tensor(v, dtype=torch.float32, device=dev)
+    step = ts.TileStep.__new__(ts.TileStep)
+    step.device = dev
+    step.featureGrid = RefGrid(dev, f(tile_corner), f(tile_size), log2T, list(grid_resolution), sampler_log2dim, False, ply)
+    step.decoder = ShallowMLP(32).to(dev)
+    step.poses = RefPoses(Ks, c2w, dev, None)
+    step.num_sample, step.num_bg_sample, step.global_step, step.invalid_underground = S, S_bg, global_step, False
+    step.consensus = None
+    step.warp = None
+    step.camera_ids = None
+    step.two_streams = False
+    step.joint_chains = False
+    step.featureGrid_optimizer = torch.optim.Adam([{"params": step.featureGrid.parameters(), "lr": lr_table, "betas": (0.9, 0.99), "eps": 1e-15}])
+    step.optimizer = torch.optim.Adam([{"params": step.decoder.parameters(), "lr": lr_decoder, "weight_decay": 1e-6},
+                                       {"params": step.poses.se3_refine, "lr": lr_cam}])
+    return step
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r1_reference_cuda_step.json"))
+    args = ap.parse_args()
+    pkg = importlib.import_module(bench.PKG)
+    pkg.install()
+    cfg = bench.WORKLOADS["default.yaml-single-tile"]
+    dev = torch.device("cuda:0")
     import scenes
+    import tempfile
     gen = torch.Generator().manual_seed(0)
     c = [cfg["tile_corner"][i] + cfg["tile_size"][i] * f for i, f in enumerate((0.5, 0.25, 0.5))]
     Ks, c2w = scenes.camera_rig(cfg["n_cam"], cfg["H"], cfg["W"], gen, center=tuple(c),
                                 radius=0.3 * min(cfg["tile_size"][0], cfg["tile_size"][2]), fx=cfg["fx"])
-    import tempfile
     ply = os.path.join(tempfile.mkdtemp(prefix="snrf_ref_"), "mesh.ply")
     scenes.write_proxy_mesh_ply(ply, cfg["tile_corner"], cfg["tile_size"], seed=0)
     torch.manual_seed(0)
-    f = lambda v: torch.as_tensor(v, dtype=torch.float32, device=dev)
-    step = ts.TileStep.__new__(ts.TileStep)
-    step.device = dev
-    step.featureGrid = RefGrid(dev, f(cfg["tile_corner"]), f(cfg["tile_size"]), cfg["log2T"], list(cfg["grid_resolution"]),
-                               cfg["sampler_log2dim"], False, ply)
-    step.decoder = ShallowMLP(32).to(dev)
-    step.poses = RefPoses(Ks, c2w, dev, None)
-    step.num_sample, step.num_bg_sample, step.global_step, step.invalid_underground = cfg["S"], cfg["S_bg"], 10000, False
-    step.consensus = None
-    step.warp = None
-    step.two_streams = False
-    step.joint_chains = False
-    step.featureGrid_optimizer = torch.optim.Adam([{"params": step.featureGrid.parameters(), "lr": 1e-3, "betas": (0.9, 0.99), "eps": 1e-15}])
-    step.optimizer = torch.optim.Adam([{"params": step.decoder.parameters(), "lr": 1e-3, "weight_decay": 1e-6},
-                                       {"params": step.poses.se3_refine, "lr": 1e-4}])
+    step = build_reference_step(dev, cfg["tile_corner"], cfg["tile_size"], Ks, c2w, cfg["log2T"], cfg["grid_resolution"],
+                                cfg["sampler_log2dim"], cfg["S"], cfg["S_bg"], ply)
     batches = [(l.to(dev), g.to(dev)) for l, g in bench.make_batches(cfg, args.warmup + args.steps, gen)]
     for b in batches[:args.warmup]:
         step.step_device(*b)
