@@ -161,8 +161,10 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     // input-gradient GEMMs: A K-major (dz rows), B MN-major (weight tile: rows = K = out, cols = N = in)
     constexpr uint32_t idg64 = umma::idesc_bf16(128, 64, 0, 1), idg32 = umma::idesc_bf16(128, 32, 0, 1);
     // weight-gradient GEMMs: both operands MN-major, M = 64
-    constexpr uint32_t idw64 = umma::idesc_bf16(64, 64, 1, 1), idw48 = umma::idesc_bf16(64, 48, 1, 1),
-                       idw32 = umma::idesc_bf16(64, 32, 1, 1), idw16 = umma::idesc_bf16(64, 16, 1, 1);
+    // (A = dz^T, bf16; B = the layer's input activations, fp16 -- and the other way round for the transposed narrow layers)
+    constexpr uint32_t idw64 = umma::idesc_f16(64, 64, 1, 1, 1, kActBf16), idw48 = umma::idesc_f16(64, 48, 1, 1, 1, kActBf16),
+                       idw32 = umma::idesc_f16(64, 32, 1, 1, 1, kActBf16), idw16 = umma::idesc_f16(64, 16, 1, 1, 1, kActBf16),
+                       idwt16 = umma::idesc_f16(64, 16, 1, 1, kActBf16, 1);
     const uint32_t aW2l = umma::smem_u32(smem + oW2l), aW3l = umma::smem_u32(smem + oW3l), aW4l = umma::smem_u32(smem + oW4l),
                    aW5l = umma::smem_u32(smem + oW5l);
     // dA = dz W over `nk` k-steps; in SPLIT mode dz = dz_hi + dz_lo and W = W_hi + W_lo (the lo tile,
@@ -285,8 +287,8 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
             dgrad(cDa, adz, 1, adz, 3, aW5, aW5l, 1, idg64);
             dgrad(cDc, adz, 0, adz, 2, aWh, aWh + 64, 1, idg32);     // dH[0:32] stays in TMEM until the B2 epilogue
             umma::mma_commit(&bar);
-            wgrad_t(cGW5T, aa4, adz + 32, adz + 96, idw16, first);  // behind the commit: this epilogue writes g4 / dz lo only
-            wgrad_t(cGWhT, aH, adz, adz + 64, idw16, first);
+            wgrad_t(cGW5T, aa4, adz + 32, adz + 96, idwt16, first);  // behind the commit: this epilogue writes g4 / dz lo only
+            wgrad_t(cGWhT, aH, adz, adz + 64, idwt16, first);
         }
         c.wait_mma();
         mul_inplace(cDa, T.g4, Tdzlo, acc_b4);                   // dz5 (+ its column sums = d/d b4)

@@ -10,7 +10,13 @@ namespace dec {
 constexpr int kRows = 128;                 // samples per tile
 constexpr int kTile = kRows * 128;         // bytes of one operand tile (128 rows x 64 bf16)
 constexpr float kGaussLog2 = -50.0f * 1.4426950408889634f;   // exp(-v^2/0.02) = exp2(v^2 * kGaussLog2)
-constexpr float kInvSH0 = 1.0f / 0.28125f;                   // 1 / bf16(0.28209479): the SH_0 column doubles as the ones column
+// Operand formats.  Everything the tensor core reads is bf16 hi + bf16 lo.  Storing the ACTIVATION operands as fp16 hi / lo
+// instead (3 more mantissa bits in the hi part, which is all the weight-gradient GEMMs can still read when they run)
+// would cut their rounding from 2^-9 to 2^-12, but it needs fp16 x bf16 MMAs (gradients need bf16's exponent range),
+// and tcgen05.mma kind::f16 with a_format != b_format faults with "illegal instruction" on sm_100a (tried on B200,
+// round 1).  kActBf16 = 0 selects that (non-working) variant; it is kept as the record of the experiment.
+constexpr int kActBf16 = 1;
+constexpr float kInvSH0 = kActBf16 ? 1.0f / 0.28125f : 1.0f / 0.281982421875f;   // 1 / round(0.28209479): the SH_0 column doubles as the ones column
 
 // parameter tensors in network.ShallowMLP state_dict order (weight, bias per Linear)
 struct DecoderParams {
@@ -103,6 +109,29 @@ __device__ __forceinline__ void store8_hl(unsigned char* Thi, int chi, unsigned 
         for (int i = 0; i < 4; ++i)
             l[i] = umma::pack_bf16(v[2 * i] - __uint_as_float(h[i] << 16), v[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u));
         *reinterpret_cast<uint4*>(Tlo + umma::tile_chunk_off(row, clo)) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+// the same for an ACTIVATION operand (fp16 hi / lo unless kActBf16)
+template <bool SPLIT>
+__device__ __forceinline__ void store8_act(unsigned char* Thi, int chi, unsigned char* Tlo, int clo, int row, const float* v)
+{
+    if constexpr (kActBf16 != 0) {
+        store8_hl<SPLIT>(Thi, chi, Tlo, clo, row, v);
+    } else {
+        uint32_t h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = umma::pack_f16(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(Thi + umma::tile_chunk_off(row, chi)) = make_uint4(h[0], h[1], h[2], h[3]);
+        if (SPLIT) {
+            uint32_t l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+                l[i] = umma::pack_f16(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+            }
+            *reinterpret_cast<uint4*>(Tlo + umma::tile_chunk_off(row, clo)) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
     }
 }
 
@@ -279,10 +308,10 @@ __device__ __forceinline__ void store_input_row(const Tiles& T, int row, int cg,
 {
     constexpr int XC = 4 / NCG;
 #pragma unroll
-    for (int q = 0; q < XC; ++q) store8_hl<SPLIT>(T.A0, XC * cg + q, T.LOb, XC * cg + q, row, x + 8 * q);
+    for (int q = 0; q < XC; ++q) store8_act<SPLIT>(T.A0, XC * cg + q, T.LOb, XC * cg + q, row, x + 8 * q);
     const int shc = NCG == 4 ? cg - 2 : cg;
     if (shc >= 0) {
-        store8_hl<SPLIT>(T.A0, 4 + shc, T.A0, 6 + shc, row, sh8);
+        store8_act<SPLIT>(T.A0, 4 + shc, T.A0, 6 + shc, row, sh8);
         if (!SPLIT) umma::tile_zero8(T.A0, row, 6 + shc);
     }
 }
@@ -305,7 +334,8 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
                    aW4 = umma::smem_u32(smem + oW4), aWh = umma::smem_u32(smem + oWh), aW5 = umma::smem_u32(smem + oW5),
                    aW2l = umma::smem_u32(smem + oW2l), aW3l = umma::smem_u32(smem + oW3l), aW4l = umma::smem_u32(smem + oW4l),
                    aW5l = umma::smem_u32(smem + oW5l);
-    constexpr uint32_t id64 = umma::idesc_bf16(128, 64, 0, 0), id16 = umma::idesc_bf16(128, 16, 0, 0);
+    // forward GEMMs: A = activations (fp16), B = weights (bf16), both K-major
+    constexpr uint32_t id64 = umma::idesc_f16(128, 64, 0, 0, kActBf16, 1), id16 = umma::idesc_f16(128, 16, 0, 0, kActBf16, 1);
 
     c.sync_operands();
     // ---- L1: Da = x W1^T (K = 32)
@@ -328,7 +358,7 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
         }
 #pragma unroll
         for (int q = 0; q < CH; ++q) {
-            store8_hl<SPLIT>(Ta, CH * cg + q, Tlo, CH * cg + q, row, v + 8 * q);
+            store8_act<SPLIT>(Ta, CH * cg + q, Tlo, CH * cg + q, row, v + 8 * q);
             if (TRAIN) umma::tile_store8_f16(Tg, row, CH * cg + q, g + 8 * q);   // fp16: |g| <= 6.1, read back element-wise only
         }
     };
@@ -344,7 +374,7 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
 #pragma unroll
     for (int j = 0; j < W; ++j) v[j] += bias[oB2 + W * cg + j];
 #pragma unroll
-    for (int q = 0; q < CH; ++q) store8_hl<SPLIT>(T.H, CH * cg + q, T.LOb, CH * cg + q, row, v + 8 * q);
+    for (int q = 0; q < CH; ++q) store8_act<SPLIT>(T.H, CH * cg + q, T.LOb, CH * cg + q, row, v + 8 * q);
     c.sync_operands();
     // ---- heads: Dh = H[0:32] Wh^T (K = 32, N = 16);   L3: Da = [H[32:64] | SH] W3^T (K = 48)
     if (c.leader) {

@@ -6,8 +6,10 @@ tile is trained for a few hundred steps twice from the same initialisation on th
 both with the reference's dense Adam over the table, and the PSNR on held-out rays is compared.  Training is chaotic in
 the last bits (the atomic gradient scatter of either path sums in a different order every run: two runs of ONE path
 differ by up to ~0.1 dB after 300 steps), so each path is trained twice and the run-to-run spread is allowed on top of
-the 0.05 dB between the means.  Observed on B200 over several runs: this repo 35.48-35.62 dB, reference path
-35.41-35.49 dB, i.e. this repo ends ~0.1 dB ABOVE the reference path; the test therefore
+the 0.05 dB between the means.  Observed on B200 (tools/dbg/psnr_variants.py, two runs each): reference path 36.88 / 36.92 dB;
+this repo with the fp32 torch decoder (HashGrid.fused_decoder = False) 36.92 / 36.91 dB, with the fused encode switched off as
+well 36.94 / 36.93 dB; with the tensor-core decoder 36.80-36.86 dB, i.e. ~0.07 dB below (the weight-gradient GEMMs read
+bf16-rounded activations).  With pose refinement off: 35.75-35.77 vs 35.72 dB.  The test
 bounds the deficit at 0.05 dB + spread and the absolute difference at 0.25 dB."""
 import importlib.util
 import math
@@ -41,7 +43,10 @@ def test_psnr_delta_against_reference_path():
     spec.loader.exec_module(rcs)
     H, W, n_cam, S, log2T, steps = 48, 64, 8, 32, 15, 300
     gen = torch.Generator().manual_seed(0)
-    Ks, c2w = scenes.camera_rig(n_cam, H, W, gen, center=(10.0, 3.0, 15.0), radius=5.0, fx=60.0)
+    # (not the round numbers of the other tests: cameras that sit exactly ON a face of the occupancy grid make the sample
+    # placement of all their rays depend on the last bit of the ray origin -- two correct pose implementations that differ
+    # by 2e-6 in the origin then train to PSNRs 0.1 dB apart, every run)
+    Ks, c2w = scenes.camera_rig(n_cam, H, W, gen, center=(10.37, 3.21, 15.53), radius=4.83, fx=60.0)
     ply = os.path.join(tempfile.mkdtemp(), "mesh.ply")
     scenes.write_proxy_mesh_ply(ply, (0, 0, 0), (20, 13, 30), seed=0, ground_res=16, n_boxes=6)
     batches = []

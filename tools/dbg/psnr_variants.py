@@ -9,7 +9,7 @@ import test_psnr_gpu as T
 DEV = torch.device("cuda:0")
 H, W, n_cam, S, log2T, steps = 48, 64, 8, 32, 15, 300
 gen = torch.Generator().manual_seed(0)
-Ks, c2w = scenes.camera_rig(n_cam, H, W, gen, center=(10.0, 3.0, 15.0), radius=5.0, fx=60.0)
+Ks, c2w = scenes.camera_rig(n_cam, H, W, gen, center=(10.37, 3.21, 15.53), radius=4.83, fx=60.0)
 ply = os.path.join(tempfile.mkdtemp(), "mesh.ply")
 scenes.write_proxy_mesh_ply(ply, (0, 0, 0), (20, 13, 30), seed=0, ground_res=16, n_boxes=6)
 batches = []
