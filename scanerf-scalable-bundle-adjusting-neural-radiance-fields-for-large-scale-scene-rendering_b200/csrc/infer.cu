@@ -250,7 +250,8 @@ infer_kernel(InferArgs a, int num_tiles)
 
 // ------------------------------------------------------------------------------------------------------------------
 // Single-tile fast path: the same evaluation as infer_kernel, split into two passes over chunks of samples.
-//   pass 1 (infer_encode_kernel): geometry + fp16 gathers, ONE LEVEL PER CTA ROW -> level-major features [16][Nc].
+//   pass 0 (infer_geometry_kernel): per-sample table coordinate / weight / alpha scale / state, once.
+//   pass 1 (infer_encode_kernel): fp16 gathers, ONE LEVEL PER CTA ROW -> level-major features [16][Nc].
 //           The whole GPU walks one 64 MiB level slice at a time, which stays L2-resident: the table streams from HBM
 //           once per chunk, whereas the fused kernel (every level of a sample at once) pulls a 32-byte sector per
 //           corner from HBM -- ~4 KB per sample, the floor of a 1080p frame is then ~170 ms per pass.
@@ -297,15 +298,14 @@ __device__ __forceinline__ Geom sample_geom(const InferArgs& a, int b, int ray, 
     return g;
 }
 
+// pass 0 of the single-tile path: the geometry of every sample ONCE (table coordinate, blend weight, alpha scale, state);
+// the encode pass below then costs a coalesced 16-byte load per (sample, level) instead of recomputing the ray / box
+// arithmetic and the occupancy lookup 16 times (ncu: that kernel ran at 61 % of the issue slots, 314 instructions per
+// sample-level)
 template <int MODE>
 __global__ void __launch_bounds__(256)
-infer_encode_kernel(InferArgs a, long long n0, int Nc, float2* __restrict__ feats_lm, float2* __restrict__ aux,
-                    unsigned char* __restrict__ state)
+infer_geometry_kernel(InferArgs a, long long n0, int Nc, float4* __restrict__ uw, float2* __restrict__ aux, unsigned char* __restrict__ state)
 {
-    const int l = blockIdx.y;
-    const uint32_t mask = a.T - 1u;
-    const int rx = a.resolution[3 * l] - 1, ry = a.resolution[3 * l + 1] - 1, rz = a.resolution[3 * l + 2] - 1;
-    const __half2* tl = a.tables + (size_t)l * a.T;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Nc; i += gridDim.x * blockDim.x) {
         const long long n = n0 + i;
         const int ray = (int)(n / a.S), k = (int)(n % a.S);
@@ -319,12 +319,23 @@ infer_encode_kernel(InferArgs a, long long n0, int Nc, float2* __restrict__ feat
             step_len = (k == a.S - 1) ? 10000000.0f : a.z_vals[n + 1] - zv;
         }
         const Geom g = sample_geom<MODE>(a, 0, ray, id == 0 ? 0 : -1, o + zv * d);
-        if (l == 0) {
-            state[i] = g.active ? 1 : ((MODE == kBackSlot && !g.member) ? 2 : 0);
-            aux[i] = make_float2(g.w, MODE == kFore ? step_len * sqrtf(dot3(d, d)) : step_len);
-        }
-        if (!g.active) continue;
-        const float vx = g.u.x * (float)rx, vy = g.u.y * (float)ry, vz = g.u.z * (float)rz;
+        state[i] = g.active ? 1 : ((MODE == kBackSlot && !g.member) ? 2 : 0);
+        aux[i] = make_float2(g.w, MODE == kFore ? step_len * sqrtf(dot3(d, d)) : step_len);
+        uw[i] = make_float4(g.u.x, g.u.y, g.u.z, g.w);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+infer_encode_kernel(InferArgs a, int Nc, const float4* __restrict__ uw, const unsigned char* __restrict__ state, float2* __restrict__ feats_lm)
+{
+    const int l = blockIdx.y;
+    const uint32_t mask = a.T - 1u;
+    const int rx = a.resolution[3 * l] - 1, ry = a.resolution[3 * l + 1] - 1, rz = a.resolution[3 * l + 2] - 1;
+    const __half2* tl = a.tables + (size_t)l * a.T;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Nc; i += gridDim.x * blockDim.x) {
+        if (state[i] != 1) continue;
+        const float4 u = __ldg(uw + i);
+        const float vx = u.x * (float)rx, vy = u.y * (float)ry, vz = u.z * (float)rz;
         const int ix = (int)vx, iy = (int)vy, iz = (int)vz;
         const float ox = vx - (float)ix, oy = vy - (float)iy, oz = vz - (float)iz;
         float2 f[8];
@@ -741,18 +752,20 @@ int launch_two_pass(const InferArgs& a, void* stream, const char* name)
     const long long chunk = 4ll << 20;                          // 4 Mi samples: 512 MiB of features
     const long long cap = total < chunk ? total : chunk;
     void* scratch = nullptr;
-    const size_t bytes = (size_t)cap * (16 * 8 + 8 + 1) + 256;
+    const size_t bytes = (size_t)cap * (16 * 8 + 16 + 8 + 1) + 256;
     cudaError_t e = scratch_alloc(&scratch, bytes, s);
     if (e != cudaSuccess) { snrf_set_error("%s: scratch allocation of %zu bytes: %s", name, bytes, cudaGetErrorString(e)); return (int)e; }
     float2* feats = (float2*)scratch;
-    float2* aux = feats + (size_t)cap * 16;
+    float4* uw = (float4*)(feats + (size_t)cap * 16);
+    float2* aux = (float2*)(uw + cap);
     unsigned char* state = (unsigned char*)(aux + cap);
     const int sms = snrf_sm_count();
     for (long long n0 = 0; n0 < total; n0 += chunk) {
         const int Nc = (int)(total - n0 < chunk ? total - n0 : chunk);
         int gx = snrf_div_up(Nc, 256);
         if (gx > sms * 32) gx = sms * 32;
-        infer_encode_kernel<MODE><<<dim3(gx, 16), 256, 0, s>>>(a, n0, Nc, feats, aux, state);
+        infer_geometry_kernel<MODE><<<gx, 256, 0, s>>>(a, n0, Nc, uw, aux, state);
+        infer_encode_kernel<<<dim3(gx, 16), 256, 0, s>>>(a, Nc, uw, state, feats);
         const int num_tiles = snrf_div_up(Nc, kRows);
         int grid = sms;
         if (grid > (num_tiles + 1) / 2) grid = (num_tiles + 1) / 2;
