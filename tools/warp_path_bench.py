@@ -30,7 +30,6 @@ def main():
     args = ap.parse_args()
     pkg = importlib.import_module(bench.PKG)
     pkg.install()
-    from oracle import views_ref as vr
     from warp_loss import SampleNeighborColorFn
     cfg = bench.WORKLOADS["default.yaml-single-tile"]
     dev = torch.device("cuda:0")
