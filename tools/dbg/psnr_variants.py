@@ -38,6 +38,27 @@ def build(variant):
         st.optimizer = torch.optim.Adam([{"params": st.decoder.parameters(), "lr": 1e-3, "weight_decay": 1e-6}, {"params": st.poses.se3_refine, "lr": 1e-4}])
     if "nopose" in variant:
         st.optimizer = torch.optim.Adam([{"params": st.decoder.parameters(), "lr": 1e-3, "weight_decay": 1e-6}], fused=True)
+    if "round" in variant:
+        # emulate, on the fp32 torch decoder, the one uncompensated piece of the tensor-core backward: the weight-gradient
+        # GEMM reads its activation operand as a single bf16 value (layers selected by digits after "round": 1..6 in
+        # state_dict order; "roundall" = every Linear)
+        st.featureGrid.fused_decoder = False
+        class RoundedLinearFn(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, x, w, b):
+                ctx.save_for_backward(x, w)
+                return torch.nn.functional.linear(x, w, b)
+            @staticmethod
+            def backward(ctx, gy):
+                x, w = ctx.saved_tensors
+                xr = x.to(torch.bfloat16).float()
+                g2, x2 = gy.reshape(-1, gy.shape[-1]), xr.reshape(-1, xr.shape[-1])
+                return gy @ w, g2.t() @ x2, g2.sum(0)
+        lins = [m for m in st.decoder.modules() if isinstance(m, torch.nn.Linear)]
+        sel = range(len(lins)) if "roundall" in variant else [int(c) - 1 for c in variant.split("round")[1] if c.isdigit()]
+        for i in sel:
+            lin = lins[i]
+            lin.forward = (lambda x, lin=lin: RoundedLinearFn.apply(x, lin.weight, lin.bias))
     if "plainbf16" in variant:
         import scanerf_b200_capi as capi
         capi.lib().snrf_decoder_set_precision(capi.c_int(0))
