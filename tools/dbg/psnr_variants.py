@@ -40,25 +40,28 @@ def build(variant):
         st.optimizer = torch.optim.Adam([{"params": st.decoder.parameters(), "lr": 1e-3, "weight_decay": 1e-6}], fused=True)
     if "round" in variant:
         # emulate, on the fp32 torch decoder, the one uncompensated piece of the tensor-core backward: the weight-gradient
-        # GEMM reads its activation operand as a single bf16 value (layers selected by digits after "round": 1..6 in
-        # state_dict order; "roundall" = every Linear)
+        # GEMM reads its activation operand as a single bf16 value (layers selected by digits after "round": 1..8 in
+        # module order; "roundall" = every Linear).  "affine": inputs that are Gaussian activations in (0, 1] are stored
+        # as bf16(a - 0.5) instead (the 0.5 folds into the bias / bias gradient exactly).
         st.featureGrid.fused_decoder = False
         class RoundedLinearFn(torch.autograd.Function):
             @staticmethod
-            def forward(ctx, x, w, b):
+            def forward(ctx, x, w, b, shift):
                 ctx.save_for_backward(x, w)
+                ctx.shift = shift
                 return torch.nn.functional.linear(x, w, b)
             @staticmethod
             def backward(ctx, gy):
                 x, w = ctx.saved_tensors
-                xr = x.to(torch.bfloat16).float()
+                xr = (x - ctx.shift).to(torch.bfloat16).float() + ctx.shift
                 g2, x2 = gy.reshape(-1, gy.shape[-1]), xr.reshape(-1, xr.shape[-1])
-                return gy @ w, g2.t() @ x2, g2.sum(0)
+                return gy @ w, g2.t() @ x2, g2.sum(0), None
         lins = [m for m in st.decoder.modules() if isinstance(m, torch.nn.Linear)]
         sel = range(len(lins)) if "roundall" in variant else [int(c) - 1 for c in variant.split("round")[1] if c.isdigit()]
         for i in sel:
             lin = lins[i]
-            lin.forward = (lambda x, lin=lin: RoundedLinearFn.apply(x, lin.weight, lin.bias))
+            shift = 0.5 if ("affine" in variant and i in (1, 6, 7)) else 0.0
+            lin.forward = (lambda x, lin=lin, shift=shift: RoundedLinearFn.apply(x, lin.weight, lin.bias, shift))
     if "plainbf16" in variant:
         import scanerf_b200_capi as capi
         capi.lib().snrf_decoder_set_precision(capi.c_int(0))
