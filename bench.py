@@ -175,7 +175,9 @@ def run_reference(args, cfg, name):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    rays = 2048          # per step: large enough that the threaded C encode and torch's MLP run at their best rate (~1.5 s / step)
+    # per step: large enough that the threaded C encode and torch's MLP run at their best rate (~1.5 s / step);
+    # SNRF_REF_RAYS shrinks it for the contract test of this arm
+    rays = int(os.environ.get("SNRF_REF_RAYS", "2048"))
     from oracle import native as on
     on.build()
     port = CpuPort(cfg, rays, cores)
