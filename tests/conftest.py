@@ -30,13 +30,27 @@ def pkg():
     return load_pkg()
 
 
+_REF_CACHE = {}
+
+
 def ref_module(name):
-    """Import one of the reference extension modules rebuilt by oracle/build_ref.py
-    (oracle/_ref/<name>.so) or return None when it was not built."""
+    """Load one of the reference extension modules rebuilt by oracle/build_ref.py BY PATH
+    (oracle/_ref/<name>.so) or return None when it was not built.  Never goes through sys.path /
+    sys.modules: after `install()` the names `fastMesh`, `hashgrid`, `cuda` resolve to the drop-in
+    packages, and a by-name import would hand the test the product instead of the reference."""
     d = os.path.join(ROOT, "oracle", "_ref")
-    if not os.path.exists(os.path.join(d, name + ".so")):
+    so = os.path.join(d, name + ".so")
+    if not os.path.exists(so):
         return None
+    if name in _REF_CACHE:
+        return _REF_CACHE[name]
+    import importlib.machinery
+    import importlib.util
     import torch  # noqa: F401  (libtorch must be loaded first)
-    if d not in sys.path:
-        sys.path.append(d)
-    return importlib.import_module(name)
+    loader = importlib.machinery.ExtensionFileLoader(name, so)
+    spec = importlib.util.spec_from_file_location(name, so, loader=loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    assert mod.__file__.endswith(".so") and os.path.dirname(os.path.abspath(mod.__file__)) == d, mod.__file__
+    _REF_CACHE[name] = mod
+    return mod
