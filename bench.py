@@ -252,6 +252,80 @@ def bench_render(step, cfg, dev, H=1080, W=1920, frames=5, warm=2):
                          "calls_timed": len(k_ms), "share_of_frame": sum(k_ms) / ms if k_ms else None}}
 
 
+
+# ----------------------------------------------------------------------------- further legs (outside the headline's timed region)
+def _time_steps(step, batches, warm):
+    import torch
+    for b in batches[:warm]:
+        step.step_device(*b)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for b in batches[warm:]:
+        loss = step.step_device(*b)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (len(batches) - warm), float(loss)
+
+
+def bench_variants(step, cfg, dev, gen, devb, plain_ms):
+    """(a) the default.yaml step WITH its multi-view warp loss (config/default.yaml:32-45 has
+    WEIGHT_WARP_LOSS 1.0: view selection, projection into 10 neighbour views, colour fetch, masked re-render of the
+    neighbour rays), (b) BASELINE.json configs[0] (C1: 2^19 table, 4096 rays x 64 + 64 samples) on the GPU path."""
+    import torch
+    out = {}
+    # (b) first: its tile is small and is freed again
+    c1 = WORKLOADS["c1-small"]
+    s1, g1 = build_tile(c1, dev, seed=1)
+    b1 = [(l.to(dev), t.to(dev)) for l, t in make_batches(c1, 25, g1)]
+    ms, _ = _time_steps(s1, b1, 5)
+    B1 = b1[0][0].shape[0]
+    out["c1"] = {"workload": "c1-small: 16 x 2^19 x 2 table, %d rays x %d samples" % (B1, c1["S"] + c1["S_bg"]),
+                 "ms_per_step": ms, "value": B1 / (ms * 1e-3), "unit": "rays/s", "steps": 20}
+    del s1, b1
+    # (a) the warp loss on the headline tile (kept last: it changes the step's configuration)
+    N, H, W = cfg["n_cam"], cfg["H"], cfg["W"]
+    images = torch.randint(0, 256, (N, H, W, 3), generator=gen, dtype=torch.uint8)
+    occl = torch.ones(N, H, W, 1, dtype=torch.bool)
+    step.enable_warp_loss(images, alpha=0.5, gamma=2.0, weight=1.0, occlusions=occl)
+    ms, loss = _time_steps(step, devb[:14], 4)
+    step.warp = None
+    B = devb[0][0].shape[0]
+    out["warp_loss"] = {"workload": "default.yaml single tile + warp loss (10 neighbour views per ray re-rendered)",
+                        "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "rays/s", "steps": 10, "loss_finite": loss == loss,
+                        "ms_per_step_without": plain_ms,
+                        "table_update": "gradient table + sparse Adam (two encodes of the table per step)"}
+    return out
+
+
+def bench_reference_cuda(cfg, dev, steps=10, warm=3):
+    """The north star's real denominator: the REFERENCE's own CUDA extensions (unmodified sources rebuilt for sm_100a into
+    oracle/_ref by oracle/build_ref.py) in the reference's own op-by-op torch graph with its dense table Adam
+    (tools/ref_cuda_step.py), same workload, same box, outside the headline's timed region.  None when oracle/_ref is
+    not there."""
+    import torch
+    import oracle
+    if oracle.ref_module("CUDA_EXT") is None or oracle.ref_module("HASHGRID_EMBED") is None:
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ref_cuda_step
+    import scenes
+    gen = torch.Generator().manual_seed(0)
+    c = [cfg["tile_corner"][i] + cfg["tile_size"][i] * f for i, f in enumerate((0.5, 0.25, 0.5))]
+    Ks, c2w = scenes.camera_rig(cfg["n_cam"], cfg["H"], cfg["W"], gen, center=tuple(c),
+                                radius=0.3 * min(cfg["tile_size"][0], cfg["tile_size"][2]), fx=cfg["fx"])
+    ply = os.path.join(tempfile.mkdtemp(prefix="snrf_ref_"), "mesh.ply")
+    scenes.write_proxy_mesh_ply(ply, cfg["tile_corner"], cfg["tile_size"], seed=0)
+    torch.manual_seed(0)
+    ref = ref_cuda_step.build_reference_step(dev, cfg["tile_corner"], cfg["tile_size"], Ks, c2w, cfg["log2T"], cfg["grid_resolution"],
+                                             cfg["sampler_log2dim"], cfg["S"], cfg["S_bg"], ply)
+    batches = [(l.to(dev), g.to(dev)) for l, g in make_batches(cfg, warm + steps, gen)]
+    ms, loss = _time_steps(ref, batches, warm)
+    B = batches[0][0].shape[0]
+    return {"what": "reference CUDA extensions (hashgrid_bg_kernel.cu, helper_kernel.cu ... rebuilt unmodified for sm_100a) in the "
+                    "reference's torch graph (torch MLP / compositing / pose chain, dense torch Adam over the table), same workload",
+            "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "rays/s", "steps": steps, "warmup": warm, "loss": loss}
+
 # ----------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
@@ -262,6 +336,7 @@ def main():
     ap.add_argument("--workload", default="default.yaml-single-tile", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-render", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the warp-loss / C1 / reference-CUDA legs")
     args = ap.parse_args()
     cfg, name = WORKLOADS[args.workload], args.workload
     if args.impl == "reference":
@@ -344,47 +419,104 @@ def main():
     # (2) end to end: pinned host in, loss float out
     ms_e2e, _, t2 = timed(run_e2e, host)
     clk = clocks.summary(t0, t2) if clocks else None
-    # (3) the dominant kernel, timed live on its stream over the same steps
-    capi.time_calls("snrf_field_encode_bwd")
+    # (3) the dominant kernels, timed live on their stream over the same steps: the encode forward through CUDA events
+    #     around its C-ABI call; the encode backward -- now a sequence of launches (geometry + ray gradient, then per
+    #     L2-resident table slice: scatter, sparse Adam) -- through the library's own per-class event timing
+    #     (snrf_field_set_profile: events between the launches on the launching stream, one synchronise at the end).
+    import ctypes
+    opt = step.featureGrid_optimizer
+    fused = bool(getattr(step, "fused_table_update", False)) and hasattr(opt, "begin_fused")
+    capi.time_calls(("snrf_field_encode_fwd", "snrf_field_encode_bwd"))
+    prof = []
+    if fused:
+        capi.lib().snrf_field_set_profile(ctypes.c_int(1))
     for b in devb[Wm:]:
         step.step_device(*b)
+        if fused:
+            out3 = (ctypes.c_float * 3)()
+            capi.lib().snrf_field_last_profile(out3)
+            prof.append(tuple(out3))
+    if fused:
+        capi.lib().snrf_field_set_profile(ctypes.c_int(0))
     torch.cuda.synchronize()
     k_ms, k_units = capi.timed_results()
     capi.time_calls(None)
+    N_pts = B * (cfg["S"] + cfg["S_bg"])
+    fwd_ms = k_ms if fused else k_ms[0::2]
+    # touched table floats of one step (what the sparse update moves): entries whose second moment changed
+    touched = None
+    if hasattr(opt, "params"):
+        v_before = opt.params[0][2].clone()
+        step.step_device(*devb[-1])
+        touched = int((opt.params[0][2] != v_before).sum().item())
+        del v_before
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peak_gbs()
-    n_launch = max(len(k_ms), 1)
-    avg_ms = sum(k_ms) / n_launch if k_ms else float("nan")
-    alg_bytes = ENC_BWD_BYTES * (sum(k_units) / n_launch if k_units else 0)
-    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if k_ms else float("nan")
-    traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("snrf_field_encode_bwd")
+        traffic_file = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
-        pass
+        traffic_file = {}
+
+    def roof(kernel, ms_list, alg_bytes, traffic_key, extra=None):
+        n = max(len(ms_list), 1)
+        avg = sum(ms_list) / n if ms_list else float("nan")
+        ach = alg_bytes / (avg * 1e-3) / 1e9 if ms_list else float("nan")
+        t = traffic_file.get(traffic_key)
+        r = {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+             "frac": ach / peak, "traffic": t.get("bytes") if isinstance(t, dict) else t,
+             "traffic_source": (t.get("source") if isinstance(t, dict) else None),
+             "avg_launch_ms": avg, "launches_timed": len(ms_list), "alg_bytes_per_launch": alg_bytes,
+             "share_of_step": avg / (ms_dev / K) if ms_list else None}
+        if extra:
+            r.update(extra)
+        return r
+    if fused:
+        bwd_ms = [p0 + p1 for p0, p1, _ in prof]
+        adam_ms = [p2 for _, _, p2 in prof]
+        roofline = roof("encode backward = field_geom_raygrad_kernel + field_scatter_slice_kernel x slices (inside snrf_field_encode_bwd_adam)",
+                        bwd_ms, ENC_BWD_BYTES * N_pts, "encode_bwd",
+                        {"note": "timed per kernel class by CUDA events between the launches (snrf_field_set_profile); "
+                                 "the sparse Adam slices interleaved with the scatter are in roofline_update"})
+        roofline_update = roof("adam_slice_kernel x slices (sparse Adam over touched entries, gradient read from the L2-resident scratch)",
+                               adam_ms, 28 * (touched or 0), "adam_slices",
+                               {"touched_floats_per_step": touched, "alg_bytes_per_touched_float": 28})
+    else:
+        bwd_only = k_ms[1::2]
+        roofline = roof("field_bwd_kernel (snrf_field_encode_bwd: hash-encode backward)", bwd_only, ENC_BWD_BYTES * N_pts, "snrf_field_encode_bwd")
+        roofline_update = None
+    roofline_fwd = roof("field_fwd_kernel (snrf_field_encode_fwd: position + contraction + 16-level encode + Jacobian store)",
+                        fwd_ms, ENC_FWD_BYTES * N_pts, "encode_fwd")
     line = {
         "metric": "train rays/s (fwd+bwd)", "value": world * K * B / (ms_dev * 1e-3), "unit": "rays/s", "n_gpus": world,
         "steps": K, "warmup": Wm, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": name, "tiles_per_gpu": 1, "rays_per_step": B, "samples_per_ray": cfg["S"] + cfg["S_bg"],
                    "hash_table": f"16 x 2^{cfg['log2T']} x 2 f32", "cameras": cfg["n_cam"], "pose_refinement": True,
+                   "table_update": "scatter + sparse Adam fused per L2-resident slice" if fused else "gradient table + sparse Adam",
                    "parallelism": f"tile-parallel x{world}" + (", NCCL pose consensus every 100 steps (1 exchange in the timed region)" if world > 1 else ""),
-                   "l2_policy": "inputs larger than L2 (2 GiB table + 2 GiB gradient, random gathers)"},
+                   "l2_policy": "inputs larger than L2 (2 GiB table + 4 GiB Adam moments, random gathers)"},
         "e2e": {"value": world * K * B / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": B * 3 * 4 * 2,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "clocks": clk,
-        "roofline": {"kernel": "field_bwd_kernel (snrf_field_encode_bwd: hash-encode backward)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "avg_launch_ms": avg_ms, "launches_timed": len(k_ms), "alg_bytes_per_launch": alg_bytes,
-                     "share_of_step": (sum(k_ms) / K) / (ms_dev / K) if k_ms else None},
+        "roofline": roofline,
+        "roofline_fwd": roofline_fwd,
     }
+    if roofline_update is not None:
+        line["roofline_update"] = roofline_update
     if world == 1 and not args.no_render:
         line["render"] = bench_render(step, cfg, dev)
+    if world == 1 and not args.no_variants:
+        line["variants"] = bench_variants(step, cfg, dev, gen, devb, ms_dev / K)
+        ref = bench_reference_cuda(cfg, dev)
+        if ref is not None:
+            ref["ratio_value"] = line["value"] / ref["value"]
+            ref["ratio_e2e"] = line["e2e"]["value"] / ref["value"]
+        line["reference_cuda"] = ref
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         from oracle import native as on

@@ -64,6 +64,27 @@ int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, const float*
                           const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
                           const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points, float* grad_table,
                           const unsigned char* ray_valid, int split, int N, int S, int L, int T, void* stream);
+/* The same backward FUSED with the sparse Adam update of the table (cuda/adam_kernel.cu:23-94 semantics: elements whose
+ * gradient is exactly zero are skipped): the gradient of one L2-resident slice of the table at a time is scattered into
+ * grad_scratch and consumed by the update on the spot, so no [L,T,2] gradient ever exists in HBM.  Equivalent to
+ * snrf_field_encode_bwd into a zeroed gradient table followed by snrf_adam_step(..., step, zero_grad = 1).
+ * table / exp_avg / exp_avg_sq [L,T,2] UPDATED in place; grad_rays_o / grad_rays_d / grad_points ACCUMULATED.
+ * grad_scratch: scratch_entries float2 (a power of two; 2^23 = 64 MiB stays L2-resident), ALL ZERO on entry, left all zero;
+ * cpts_scratch: 3 * N floats, overwritten (contracted sample positions, SoA). */
+int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
+                               const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
+                               const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points,
+                               float* table, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                               int step, float* grad_scratch, long long scratch_entries, float* cpts_scratch,
+                               const unsigned char* ray_valid, int split, int N, int S, int L, int T, void* stream);
+/* measurement hook: when on, snrf_field_encode_bwd_adam times its three kernel classes with CUDA events (and SYNCHRONISES
+ * the stream); snrf_field_last_profile -> out3 = milliseconds {geometry + ray gradient, scatter slices, Adam slices} */
+void snrf_field_set_profile(int on);
+void snrf_field_last_profile(float* out3);
+/* kernels launched by the last snrf_field_encode_bwd_adam call (1 + 2 per table slice) */
+int snrf_field_last_launch_count(void);
+/* tuning hook: cap on whole levels per scatter / update pair of snrf_field_encode_bwd_adam (0 = as many as fit the scratch) */
+void snrf_field_set_levels_per_group(int n);
 /* tuning hook: log2 of the number of table index ranges the scatter walks per level (-1 = automatic) */
 void snrf_field_set_passes_log2(int bits);
 /* tuning hook: levels [0, n) merge equal-cell lanes of a warp before reducing (-1 = automatic, L / 2) */

@@ -15,7 +15,7 @@
 // the next backward needs no 2 GiB memset of the hash-table gradient.  The reference
 // addresses element (k, d) at k*8 + d whatever D is (cuda/adam_kernel.cu:43); the C ABI
 // takes the row stride explicitly so both that layout and dense [.., D] tensors work.
-#include "common.cuh"
+#include "adam_core.cuh"
 #include <cuda_fp16.h>
 
 namespace {
@@ -23,17 +23,8 @@ namespace {
 constexpr int kThreads = 256;
 constexpr float kLossScale = 128.0f;
 
-struct Hyper { float lr, b1, b2, eps; int step; };
-
-__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, const Hyper& h, float bc1, float bc2)
-{
-    const float mi = h.b1 * m + (1.0f - h.b1) * g;
-    const float vi = h.b2 * v + (1.0f - h.b2) * g * g;
-    const float denom = sqrtf(vi / bc2) + h.eps;
-    const float step_size = h.lr / bc1;
-    p = p - step_size * mi / denom;
-    m = mi; v = vi;
-}
+using adamcore::Hyper;
+using adamcore::adam_elem;
 
 // dense, contiguous: n floats, n % 4 == 0 handled by the vector body + scalar tail
 __global__ void __launch_bounds__(kThreads)

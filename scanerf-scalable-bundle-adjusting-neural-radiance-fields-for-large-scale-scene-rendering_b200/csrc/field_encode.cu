@@ -19,6 +19,7 @@
 // being reduced into; every sector then travels to HBM once per range instead of once per touch.
 // d L / d rays is reduced per warp (32 consecutive samples of one ray) before it touches memory.
 #include "hash_common.cuh"
+#include "adam_core.cuh"
 using namespace hashgrid;
 
 namespace {
@@ -388,6 +389,231 @@ field_bwd_runs_kernel(const float* __restrict__ rays_o, const float* __restrict_
     }
 }
 
+// =====================================================================================================================
+// Backward, third form: the scatter fused with the sparse Adam update of the table ("scatter + update").
+//
+// The table gradient never exists as a [L][T] array in HBM.  The backward runs as a short sequence of launches:
+//   (1) geometry + ray gradient, once per sample: contracted point c -> cpts [3][N] (SoA, NaN = masked-out sample),
+//       g_c = sum_l g_l . J_l over all levels, the contraction's backward, one warp reduction and one set of atomics per
+//       32 samples (field_bwd_kernel redoes the contraction -- ~10 IEEE divisions -- and the warp reduction for every
+//       (level, index range); that prologue was 60 % of its issue slots, profiles/r1f_top_kernels_full.md);
+//   (2) for every index-range slice of the table that fits the L2-resident scratch (2^23 entries = 64 MiB: half a level at
+//       T = 2^24, several whole levels at small T):  scatter the slice's gradient into the scratch (reductions hit L2 --
+//       the scratch is reused by every slice and stays resident, so no sector is fetched from / evicted to HBM), then
+//   (3) apply Adam to the slice: read the scratch (L2), update p / m / v where the gradient is non-zero (the only HBM
+//       traffic: 24 B per touched float), clear the scratch behind it.
+// Semantics = snrf_field_encode_bwd into a zeroed gradient table followed by snrf_adam_step(zero_grad = 1).
+// =====================================================================================================================
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+field_geom_raygrad_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_vals,
+                          const float* __restrict__ points, const float* __restrict__ bmin_p, const float* __restrict__ bsize_p,
+                          const float2* __restrict__ grad, const float2* __restrict__ jac,
+                          float* __restrict__ grad_o, float* __restrict__ grad_d, float* __restrict__ grad_points,
+                          float* __restrict__ cpts, const unsigned char* __restrict__ ray_valid, int ray_split, int N, int S, int L)
+{
+    const int lane = threadIdx.x & 31;
+    f3 bmin = mk3(0, 0, 0), bsize = mk3(1, 1, 1);
+    if (MODE != kNone) { bmin = ld3(bmin_p); bsize = ld3(bsize_p); }
+    const bool want_rays = jac != nullptr && (MODE == kNone ? grad_points != nullptr : (grad_o != nullptr || grad_d != nullptr));
+    const float qnan = __int_as_float(0x7fc00000);
+    const int warp_base0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31;
+    for (int wb = warp_base0; wb < N; wb += gridDim.x * blockDim.x) {
+        const int n = wb + lane;
+        const bool live = n < N && (MODE == kNone || ray_valid == nullptr || ray_valid[n / S] != 0);
+        Pt p;
+        float z = 0.0f;
+        int r = -1;
+        if (MODE == kNone) {
+            p.c = live ? ld3(points + 3 * (size_t)n) : mk3(0, 0, 0);
+        } else {
+            r = live ? n / S : -1;
+            z = live ? z_vals[n] : 0.0f;
+            const f3 x = live ? sample_pos(ld3(rays_o + 3 * (size_t)r), ld3(rays_d + 3 * (size_t)r), z) : mk3(0, 0, 0);
+            p = contract(r >= ray_split, x, bmin, bsize);
+        }
+        if (n < N) {
+            __stcg(cpts + n, live ? p.c.x : qnan);
+            __stcg(cpts + (size_t)N + n, live ? p.c.y : qnan);
+            __stcg(cpts + 2 * (size_t)N + n, live ? p.c.z : qnan);
+        }
+        if (!want_rays) continue;
+        f3 gc = mk3(0, 0, 0);
+        if (live) {
+#pragma unroll 4
+            for (int l = 0; l < L; ++l) {
+                const float2 g = __ldcs(grad + (size_t)l * N + n);
+                const float2* j = jac + (size_t)l * 3 * N + n;
+                const float2 jx = __ldcs(j), jy = __ldcs(j + (size_t)N), jz = __ldcs(j + 2 * (size_t)N);
+                gc.x += g.x * jx.x + g.y * jx.y;
+                gc.y += g.x * jy.x + g.y * jy.y;
+                gc.z += g.x * jz.x + g.y * jz.y;
+            }
+        }
+        if (MODE == kNone) {
+            if (live) {       // ACCUMULATES, as snrf_field_encode_bwd does
+                atomicAdd(grad_points + 3 * (size_t)n + 0, gc.x);
+                atomicAdd(grad_points + 3 * (size_t)n + 1, gc.y);
+                atomicAdd(grad_points + 3 * (size_t)n + 2, gc.z);
+            }
+        } else {
+            f3 gx = live ? contract_bwd(r >= ray_split, p, gc) : mk3(0, 0, 0);
+            f3 gz = gx * z;
+            const int r0 = __shfl_sync(0xffffffffu, r, 0);
+            if (__all_sync(0xffffffffu, r == r0 || r < 0)) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    gx.x += __shfl_xor_sync(0xffffffffu, gx.x, off); gx.y += __shfl_xor_sync(0xffffffffu, gx.y, off);
+                    gx.z += __shfl_xor_sync(0xffffffffu, gx.z, off);
+                    gz.x += __shfl_xor_sync(0xffffffffu, gz.x, off); gz.y += __shfl_xor_sync(0xffffffffu, gz.y, off);
+                    gz.z += __shfl_xor_sync(0xffffffffu, gz.z, off);
+                }
+                if (lane == 0 && r0 >= 0) {
+                    if (grad_o) { atomicAdd(grad_o + 3 * (size_t)r0, gx.x); atomicAdd(grad_o + 3 * (size_t)r0 + 1, gx.y); atomicAdd(grad_o + 3 * (size_t)r0 + 2, gx.z); }
+                    if (grad_d) { atomicAdd(grad_d + 3 * (size_t)r0, gz.x); atomicAdd(grad_d + 3 * (size_t)r0 + 1, gz.y); atomicAdd(grad_d + 3 * (size_t)r0 + 2, gz.z); }
+                }
+            } else if (live) {
+                if (grad_o) { atomicAdd(grad_o + 3 * (size_t)r, gx.x); atomicAdd(grad_o + 3 * (size_t)r + 1, gx.y); atomicAdd(grad_o + 3 * (size_t)r + 2, gx.z); }
+                if (grad_d) { atomicAdd(grad_d + 3 * (size_t)r, gz.x); atomicAdd(grad_d + 3 * (size_t)r + 1, gz.y); atomicAdd(grad_d + 3 * (size_t)r + 2, gz.z); }
+            }
+        }
+    }
+}
+
+// Scatter of levels [l0, l0 + gridDim.y), index range `pass` (of 1 << pass_bits per level), into the scratch:
+// entry idx of level l lands at scratch[(l - l0) * slice + (idx & (slice - 1))], slice = T >> pass_bits.
+// Reads only cpts (12 B) and the incoming gradient (8 B) per sample and level.
+__global__ void __launch_bounds__(kThreads)
+field_scatter_slice_kernel(const float* __restrict__ cpts, const int* __restrict__ res, const float2* __restrict__ grad,
+                           float2* __restrict__ scratch, int N, int l0, uint32_t T, uint32_t pass, int range_shift, int aggregate_levels)
+{
+    const uint32_t mask = T - 1u;
+    const uint32_t slice_mask = (1u << range_shift) - 1u;
+    const int lane = threadIdx.x & 31;
+    const int l = l0 + blockIdx.y;
+    float2* gl = scratch + ((size_t)blockIdx.y << range_shift);
+    const float2* gin = grad + (size_t)l * N;
+    const int* rl = res + 3 * l;
+    const bool aggregate = l < aggregate_levels;
+    const int warp_base0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31;
+    for (int wb = warp_base0; wb < N; wb += gridDim.x * blockDim.x) {
+        const int n = wb + lane;
+        f3 c = mk3(0, 0, 0);
+        float2 g = make_float2(0.f, 0.f);
+        bool live = false;
+        if (n < N) {
+            c = mk3(__ldcg(cpts + n), __ldcg(cpts + (size_t)N + n), __ldcg(cpts + 2 * (size_t)N + n));
+            live = c.x == c.x;                         // NaN marks a sample of a masked-out ray
+            if (live) g = __ldcs(gin + n);
+        }
+        const Cell cell = locate_bg(c, rl);
+        uint32_t idx[8]; float w[8];
+        corner_idx(idx, cell, mask);
+        corner_w(w, cell);
+        bool done = false;
+        if (aggregate) {
+            const unsigned long long key = live
+                ? (((unsigned long long)(uint32_t)cell.ix & 0x1fffffull) << 42) | (((unsigned long long)(uint32_t)cell.iy & 0x1fffffull) << 21) |
+                  ((unsigned long long)(uint32_t)cell.iz & 0x1fffffull)
+                : ~0ull;
+            const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+            const bool head = (lane == 0) || (prev != key);
+            const unsigned heads = __ballot_sync(0xffffffffu, head);
+            if (__popc(heads) <= 12) {
+                // segmented sums of the 16 products over runs of equal cells in consecutive lanes.  The lane's run ends
+                // right before the next head above it: lane + off is inside the run iff it is below that bound -- one
+                // comparison per step instead of a second shuffle of the run id.
+                const unsigned above = heads & ~((2u << lane) - 1u);            // heads in lanes > lane
+                const int run_end = above ? __ffs(above) - 1 : 32;               // first lane past my run
+                float vx[8], vy[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { vx[k] = w[k] * g.x; vy[k] = w[k] * g.y; }
+                const int longest = 32;                                          // (all five steps: the longest run is not known per lane)
+#pragma unroll
+                for (int off = 1; off < longest; off <<= 1) {
+                    const bool take = lane + off < run_end;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float ox = __shfl_down_sync(0xffffffffu, vx[k], off);
+                        const float oy = __shfl_down_sync(0xffffffffu, vy[k], off);
+                        if (take) { vx[k] += ox; vy[k] += oy; }
+                    }
+                }
+                if (head && live) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if ((idx[k] >> range_shift) == pass) atomicAdd(gl + (idx[k] & slice_mask), make_float2(vx[k], vy[k]));
+                }
+                done = true;
+            }
+        }
+        if (!done && live) {
+            // x-adjacent corners that share an aligned 16-byte slot go out as one red.v4 (see field_bwd_kernel)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t i0 = idx[j], i1 = idx[j + 4];
+                const float2 v0 = make_float2(w[j] * g.x, w[j] * g.y), v1 = make_float2(w[j + 4] * g.x, w[j + 4] * g.y);
+                if ((i0 ^ i1) == 1u) {
+                    if ((i0 >> range_shift) == pass) {
+                        const bool swap = (i0 & 1u) != 0u;
+                        atomicAdd(reinterpret_cast<float4*>(gl + ((i0 & slice_mask) & ~1u)),
+                                  swap ? make_float4(v1.x, v1.y, v0.x, v0.y) : make_float4(v0.x, v0.y, v1.x, v1.y));
+                    }
+                } else {
+                    if ((i0 >> range_shift) == pass) atomicAdd(gl + (i0 & slice_mask), v0);
+                    if ((i1 >> range_shift) == pass) atomicAdd(gl + (i1 & slice_mask), v1);
+                }
+            }
+        }
+    }
+}
+
+// Adam over one contiguous slice of the table: n4 float4 groups (two entries each) of p / m / v starting at the slice
+// base, gradient from the scratch (cleared behind the read).  Elements whose gradient is exactly zero are skipped
+// (cuda/adam_kernel.cu:43-51).
+__global__ void __launch_bounds__(kThreads)
+adam_slice_kernel(float4* __restrict__ p4, float4* __restrict__ m4, float4* __restrict__ v4, float4* __restrict__ g4, long long n4,
+                  adamcore::Hyper h)
+{
+    __shared__ float s_bc[2];
+    if (threadIdx.x == 0) {
+        s_bc[0] = 1.0f - powf(h.b1, (float)h.step);
+        s_bc[1] = 1.0f - powf(h.b2, (float)h.step);
+    }
+    __syncthreads();
+    const float bc1 = s_bc[0], bc2 = s_bc[1];
+    constexpr int kUnroll = 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x * kUnroll + threadIdx.x; base < n4; base += stride * kUnroll) {
+        float4 gg[kUnroll], pp[kUnroll], mm[kUnroll], vv[kUnroll];
+        bool act[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long i = base + (long long)u * blockDim.x;
+            gg[u] = i < n4 ? __ldcg(g4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const long long i = base + (long long)u * blockDim.x;
+            act[u] = !(gg[u].x == 0.0f && gg[u].y == 0.0f && gg[u].z == 0.0f && gg[u].w == 0.0f);
+            if (act[u]) { pp[u] = p4[i]; mm[u] = m4[i]; vv[u] = v4[i]; }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (!act[u]) continue;
+            const long long i = base + (long long)u * blockDim.x;
+            if (gg[u].x != 0.0f) adamcore::adam_elem(pp[u].x, gg[u].x, mm[u].x, vv[u].x, h, bc1, bc2);
+            if (gg[u].y != 0.0f) adamcore::adam_elem(pp[u].y, gg[u].y, mm[u].y, vv[u].y, h, bc1, bc2);
+            if (gg[u].z != 0.0f) adamcore::adam_elem(pp[u].z, gg[u].z, mm[u].z, vv[u].z, h, bc1, bc2);
+            if (gg[u].w != 0.0f) adamcore::adam_elem(pp[u].w, gg[u].w, mm[u].w, vv[u].w, h, bc1, bc2);
+            __stcs(p4 + i, pp[u]);          // streaming: p / m / v are not read again this step; the scratch should stay in L2
+            __stcs(m4 + i, mm[u]);
+            __stcs(v4 + i, vv[u]);
+            g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
 inline int grid_x(int N)
 {
     const int sms = snrf_sm_count();
@@ -405,6 +631,10 @@ int g_aggregate_override = -1;
 // leaves 32 / R times more same-address reductions on the coarse levels than the cross-lane sums do, and that costs
 // more than the shuffles it saves.  Kept selectable (and parity-tested) for tables / sample densities where runs are longer.
 int g_run_length = 0;
+int g_levels_per_group = 0;
+int g_last_launches = 0;       // kernels launched by the last snrf_field_encode_bwd_adam call
+int g_profile = 0;             // snrf_field_encode_bwd_adam: time the three kernel classes with CUDA events (synchronises!)
+float g_profile_ms[3] = {0.f, 0.f, 0.f};     // geometry + ray gradient, scatter slices, Adam slices of the last profiled call   // snrf_field_encode_bwd_adam: cap on whole levels per scatter / update pair (0 = as many as fit the scratch)
 inline int pick_lpb(int L, int T)
 {
     const long long level_bytes = (long long)T * 8;
@@ -429,6 +659,13 @@ inline int pick_pass_bits(int T)
 // ------------------------------- C ABI --------------------------------------
 SNRF_API void snrf_field_set_passes_log2(int bits) { g_pass_bits_override = bits; }
 SNRF_API void snrf_field_set_aggregate_levels(int n) { g_aggregate_override = n; }
+// measurement hook (bench.py's roofline): when on, snrf_field_encode_bwd_adam brackets each of its launches with CUDA
+// events, SYNCHRONISES the stream at the end and keeps the summed milliseconds per kernel class for
+// snrf_field_last_profile(out[3]) = {geometry + ray gradient, scatter, Adam}.  Off by default.
+SNRF_API int snrf_field_last_launch_count() { return g_last_launches; }
+SNRF_API void snrf_field_set_profile(int on) { g_profile = on ? 1 : 0; }
+SNRF_API void snrf_field_last_profile(float* out3) { for (int i = 0; i < 3; ++i) out3[i] = g_profile_ms[i]; }
+SNRF_API void snrf_field_set_levels_per_group(int n) { g_levels_per_group = n > 0 ? n : 0; }
 SNRF_API void snrf_field_set_run_length(int r) { g_run_length = (r == 2 || r == 4 || r == 8) ? r : 0; }
 
 // mode 0: `points` [N,3] are already contracted (rays_o / rays_d / z_vals unused);
@@ -492,4 +729,83 @@ SNRF_API int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, con
 #undef SNRF_RUNS
 #undef SNRF_BWD
     SNRF_RETURN_LAUNCH("snrf_field_encode_bwd");
+}
+
+// Backward of snrf_field_encode_fwd fused with the sparse Adam update of the table (see the kernels above).
+// table / exp_avg / exp_avg_sq [L,T,2] are UPDATED in place with the step-`step` Adam rule on every element that received a
+// non-zero gradient; grad_rays_o / grad_rays_d / grad_points are ACCUMULATED as by snrf_field_encode_bwd.
+// grad_scratch: caller-owned device buffer of scratch_entries float2 (a power of two; 2^23 = 64 MiB keeps it L2-resident),
+// ALL ZERO on entry and left all zero on exit; cpts_scratch: [3][N] floats, overwritten.
+SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
+                                        const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
+                                        const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points,
+                                        float* table, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                                        int step, float* grad_scratch, long long scratch_entries, float* cpts_scratch,
+                                        const unsigned char* ray_valid, int split, int N, int S, int L, int T, void* stream)
+{
+    SNRF_CHECK_ARG(N >= 0 && L > 0 && T > 1 && (T & (T - 1)) == 0, "snrf_field_encode_bwd_adam: T must be a power of two (N=%d L=%d T=%d)", N, L, T);
+    SNRF_CHECK_ARG(mode >= 0 && mode <= 3 && (mode == 0 ? points != nullptr : (rays_o && rays_d && z_vals && box_min && box_size && S > 0)),
+                   "snrf_field_encode_bwd_adam: inconsistent arguments for mode %d", mode);
+    SNRF_CHECK_ARG(grad_lm && table && exp_avg && exp_avg_sq && grad_scratch && cpts_scratch, "snrf_field_encode_bwd_adam: NULL argument");
+    SNRF_CHECK_ARG(scratch_entries >= 2 && (scratch_entries & (scratch_entries - 1)) == 0, "snrf_field_encode_bwd_adam: scratch_entries must be a power of two");
+    SNRF_CHECK_ARG(step >= 1, "snrf_field_encode_bwd_adam: step counts from 1 (got %d)", step);
+    if (N == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const float2 *g = (const float2*)grad_lm, *j = (const float2*)jac_lm;
+    const int ray_split = mode == 1 ? 0x7fffffff : (mode == 2 ? 0 : split);
+    // profiling mode: events[k] after the k-th launch, class of launch k in cls[]
+    constexpr int kMaxEv = 160;
+    cudaEvent_t ev[kMaxEv];
+    int cls[kMaxEv], n_ev = 0;
+    const bool prof = g_profile != 0;
+    auto mark = [&](int c) {
+        if (!prof || n_ev >= kMaxEv) return;
+        cudaEventCreate(&ev[n_ev]);
+        cudaEventRecord(ev[n_ev], s);
+        cls[n_ev++] = c;
+    };
+    mark(-1);
+    if (mode == 0)
+        field_geom_raygrad_kernel<kNone><<<grid_x(N), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, g, j, grad_rays_o, grad_rays_d, grad_points, cpts_scratch, ray_valid, ray_split, N, S, L);
+    else
+        field_geom_raygrad_kernel<kRays><<<grid_x(N), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, g, j, grad_rays_o, grad_rays_d, grad_points, cpts_scratch, ray_valid, ray_split, N, S, L);
+    mark(0);
+    int log2T = 0;
+    while ((1 << log2T) < T) ++log2T;
+    int pass_bits = 0;                                   // index ranges per level: the slice must fit the scratch
+    while (((long long)T >> pass_bits) > scratch_entries) ++pass_bits;
+    if (g_pass_bits_override > pass_bits && g_pass_bits_override <= log2T - 1) pass_bits = g_pass_bits_override;
+    const int range_shift = log2T - pass_bits;
+    const long long slice = 1ll << range_shift;
+    int lpg = pass_bits > 0 ? 1 : (int)(scratch_entries / slice);     // whole levels per scatter / update pair
+    if (lpg > L) lpg = L;
+    if (g_levels_per_group > 0 && g_levels_per_group < lpg) lpg = g_levels_per_group;
+    const int agg = g_aggregate_override >= 0 ? g_aggregate_override : L / 2;
+    const adamcore::Hyper h{lr, beta1, beta2, eps, step};
+    const int sms = snrf_sm_count();
+    for (int l0 = 0; l0 < L; l0 += lpg) {
+        const int nl = l0 + lpg <= L ? lpg : L - l0;
+        for (int pass = 0; pass < (1 << pass_bits); ++pass) {
+            field_scatter_slice_kernel<<<dim3(grid_x(N), nl), kThreads, 0, s>>>(cpts_scratch, res, g, (float2*)grad_scratch, N, l0, (uint32_t)T, (uint32_t)pass, range_shift, agg);
+            mark(1);
+            const size_t base = ((size_t)l0 * T + (size_t)pass * slice) * 2;            // floats
+            const long long n4 = (long long)nl * slice / 2;                              // float4 groups (two entries each)
+            long long gx = (n4 + kThreads * 2 - 1) / (kThreads * 2);
+            if (gx > (long long)sms * 16) gx = (long long)sms * 16;
+            adam_slice_kernel<<<(int)gx, kThreads, 0, s>>>((float4*)(table + base), (float4*)(exp_avg + base), (float4*)(exp_avg_sq + base), (float4*)grad_scratch, n4, h);
+            mark(2);
+        }
+    }
+    g_last_launches = 1 + 2 * ((L + lpg - 1) / lpg) * (1 << pass_bits);
+    if (prof) {
+        cudaStreamSynchronize(s);
+        g_profile_ms[0] = g_profile_ms[1] = g_profile_ms[2] = 0.f;
+        for (int k = 1; k < n_ev; ++k) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[k - 1], ev[k]);
+            g_profile_ms[cls[k]] += ms;
+        }
+        for (int k = 0; k < n_ev; ++k) cudaEventDestroy(ev[k]);
+    }
+    SNRF_RETURN_LAUNCH("snrf_field_encode_bwd_adam");
 }

@@ -8,6 +8,7 @@ zeros, backward returns dense grad_points / grad_features, None for the rest).
 import torch
 import torch.nn as nn
 
+from . import _gradmode
 from .lib import HASHGRID as _ops
 
 
@@ -38,9 +39,10 @@ class _EncodeFn(torch.autograd.Function):
             corner = size = None
         need_p = ctx.needs_input_grad[0]
         grad_points = torch.zeros_like(points) if need_p else None
-        if ctx.direct_grad and features.is_leaf and features.requires_grad:
-            # Scatter straight into the parameter's .grad (the kernel accumulates): no 2 GiB
-            # zeros_like + no dense `grad += new` pass per call as in PyHashGridBG.py:27-28.
+        if ctx.direct_grad and _gradmode.mode() is not None and features.is_leaf and features.requires_grad:
+            # Inside `table_backward(...)` (the training step's explicit opt-in): scatter straight into the
+            # parameter's .grad (the kernel accumulates): no 2 GiB zeros_like + no dense `grad += new` pass per
+            # call as in PyHashGridBG.py:27-28.  Outside of it the dense gradient is returned, as the reference does.
             if features.grad is None:
                 features.grad = torch.zeros_like(features)
             _ops._encode_bwd(points, grad_out.contiguous(), grad_points, features.grad, features, corner, size, resolution)
@@ -62,8 +64,9 @@ def resolution_ladder(base_resolution, finest_resolution, n_levels):
 
 class _HashGridBase(nn.Module):
     _bbox_variant = False
-    # module calls accumulate the table gradient directly into features.grad (see _EncodeFn.backward);
-    # the reference-named autograd Functions keep returning a dense grad_features tensor
+    # module calls may accumulate the table gradient directly into features.grad, but only inside an explicit
+    # `_gradmode.table_backward(...)` context (see _EncodeFn.backward); otherwise -- and always for the
+    # reference-named autograd Functions -- a dense grad_features tensor is returned
     direct_grad = True
 
     def __init__(self, device, bbox_corner, bbox_size, n_levels=16, n_features_per_level=2,

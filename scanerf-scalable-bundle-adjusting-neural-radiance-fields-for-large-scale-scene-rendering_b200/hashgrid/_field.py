@@ -6,7 +6,8 @@ import ctypes
 import torch
 
 import scanerf_b200_capi as capi
-from scanerf_b200_capi import c_int, c_void_p, ptr
+from . import _gradmode
+from scanerf_b200_capi import c_float, c_int, c_void_p, ptr
 
 f32 = torch.float32
 
@@ -101,7 +102,9 @@ class FieldEncodeFn(torch.autograd.Function):
     -> level-major features [16, R*S, 2]: sample position, space contraction (mode 1 = fore, 2 =
     background) and hash encode in one kernel (csrc/field_encode.cu).  The forward stores the per-level
     Jacobians; the backward is a pure gradient scatter into `features.grad` (accumulated in place, no dense
-    temporary) and returns d/d rays_o, d/d rays_d."""
+    temporary) and returns d/d rays_o, d/d rays_d.  Where the table gradient goes is decided by
+    `_gradmode`: returned densely (default, autograd-conformant), accumulated into `features.grad` ("direct"), or
+    consumed on the spot by the sparse Adam update ("fused": snrf_field_encode_bwd_adam)."""
 
     @staticmethod
     def forward(ctx, rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid, split=0):
@@ -135,17 +138,30 @@ class FieldEncodeFn(torch.autograd.Function):
         g_out = g_out.contiguous()
         g_o = torch.zeros_like(rays_o) if ctx.needs_input_grad[0] else None
         g_d = torch.zeros_like(rays_d) if ctx.needs_input_grad[1] else None
-        direct = features.is_leaf and features.requires_grad
+        mode = _gradmode.mode() if (features.is_leaf and features.requires_grad) else None
+        common = (ptr(rays_o), ptr(rays_d), ptr(z_vals), c_void_p(0), ptr(box_min), ptr(box_size), c_int(ctx.mode), ptr(resolution),
+                  ptr(g_out), ptr(jac) if ctx.has_jac else c_void_p(0), ptr(g_o), ptr(g_d), c_void_p(0))
+        tail = (ptr(valid) if ctx.has_valid else c_void_p(0), c_int(ctx.split), c_int(N), c_int(S), c_int(L), c_int(T), capi.stream())
+        if mode == "fused" and _gradmode.optimizer().owns(features):
+            # scatter + sparse Adam in one pass: the table gradient never exists in HBM
+            opt = _gradmode.optimizer()
+            m, v, hyper, step, scratch = opt.begin_fused(features)
+            cpts = torch.empty(3, N, dtype=f32, device=g_out.device)
+            rc = capi.lib().snrf_field_encode_bwd_adam(*common, ptr(features.data), ptr(m), ptr(v), c_float(hyper["lr"]), c_float(hyper["beta1"]),
+                                                       c_float(hyper["beta2"]), c_float(hyper["eps"]), c_int(step), ptr(scratch),
+                                                       ctypes.c_longlong(scratch.shape[0]), ptr(cpts), *tail)
+            capi.check(rc, "snrf_field_encode_bwd_adam")
+            capi.launch_count += int(capi.lib().snrf_field_last_launch_count()) - 1     # one C call, many kernels
+            return g_o, g_d, None, None, None, None, None, None, None, None
+        direct = mode is not None
         if direct:
+            # the training step's explicit opt-in (_gradmode.table_backward): accumulate in place, no dense temporary
             if features.grad is None:
                 features.grad = torch.zeros_like(features)
             g_table = features.grad
         else:
             g_table = torch.zeros_like(features)
-        rc = capi.lib().snrf_field_encode_bwd(ptr(rays_o), ptr(rays_d), ptr(z_vals), c_void_p(0), ptr(box_min), ptr(box_size),
-                                              c_int(ctx.mode), ptr(resolution), ptr(g_out), ptr(jac) if ctx.has_jac else c_void_p(0),
-                                              ptr(g_o), ptr(g_d), c_void_p(0), ptr(g_table), ptr(valid) if ctx.has_valid else c_void_p(0), c_int(ctx.split), c_int(N), c_int(S), c_int(L), c_int(T),
-                                              capi.stream())
+        rc = capi.lib().snrf_field_encode_bwd(*common, ptr(g_table), *tail)
         capi.check(rc, "snrf_field_encode_bwd")
         return g_o, g_d, None, (None if direct else g_table), None, None, None, None, None, None
 

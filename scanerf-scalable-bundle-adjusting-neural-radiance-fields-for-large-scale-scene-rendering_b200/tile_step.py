@@ -166,6 +166,7 @@ class TileStep:
         # buys nothing at steady state (14.04 vs 14.10 ms / step) and costs allocator growth while the per-stream pools
         # settle, so it is off by default
         self.two_streams = False
+        self.fused_table_update = True  # encode backward applies the sparse Adam slice by slice (see _table_backward)
         self.joint_chains = True        # foreground + background as one 2R-ray batch per kernel (render_fore_bg_rays)
         self._side = None
         self.consensus = None           # ADMM state, see enable_consensus()
@@ -290,6 +291,16 @@ class TileStep:
             loss = loss + self.consensus.camera_loss()                     # "Admm Loss", weight 1 (criterions.py:107-108)
         return loss, out
 
+    def _table_backward(self):
+        """The explicit opt-in for where the table gradient goes (hashgrid/_gradmode.py).  vdbAdam + one encode per
+        step (no warp loss, which re-renders neighbour rays through the same table): scatter + update fusion, the
+        gradient table never exists.  Otherwise: accumulate into `.grad` in place."""
+        from hashgrid import _gradmode
+        opt = self.featureGrid_optimizer
+        if isinstance(opt, vdbAdam):
+            return opt.table_backward(fused=self.fused_table_update and self.warp is None)
+        return _gradmode.table_backward("direct")
+
     def step_device(self, locs, gt_color):
         """Inputs already on the device.  Returns the loss as a device scalar (no host sync)."""
         loss, _ = self.loss(locs, gt_color)
@@ -298,7 +309,8 @@ class TileStep:
             return torch.zeros((), device=self.device)
         self.featureGrid_optimizer.zero_grad()
         self.optimizer.zero_grad()
-        loss.backward()
+        with self._table_backward():
+            loss.backward()
         self.featureGrid_optimizer.step()
         self.optimizer.step()
         self.global_step += 1

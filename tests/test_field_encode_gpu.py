@@ -113,6 +113,92 @@ def test_run_merging_scatter_equals_cross_lane_scatter(run, S):
     assert float(out[1][0].abs().max()) > 0 and float(out[1][1].abs().max()) > 0
 
 
+@pytest.mark.parametrize("mode,S,log2T,bits,lpg", [(1, 32, 14, -1, 0), (3, 7, 12, 2, 0), (2, 16, 10, -1, 3), (3, 33, 16, 1, 0)])
+def test_scatter_update_fusion_equals_scatter_then_adam(mode, S, log2T, bits, lpg):
+    """snrf_field_encode_bwd_adam (gradient slices scattered into the L2-resident scratch and consumed by the sparse Adam
+    on the spot) against snrf_field_encode_bwd into a gradient table followed by snrf_adam_step, over two steps (the second
+    with non-trivial moments): same parameters, moments, ray gradients; untouched entries bit-identical; the scratch is
+    left all-zero; index ranges (bits) and ragged level groups (lpg) included."""
+    load_pkg()
+    import scanerf_b200_capi as capi
+    from hashgrid import _field, _gradmode
+    from vdbAdam import vdbAdam
+    Rn = 301
+    table, res, bmin, bsize, o, d, z_fg, z_bg, g = _case(Rn, S, log2T, 11 + S)
+    z = z_bg if mode == 2 else z_fg
+    cots = [torch.randn(16, Rn * S, 2, generator=g).to(DEV) for _ in range(2)]
+    valid = (torch.rand(Rn, generator=g) < 0.8).to(DEV)
+    vmask = valid.repeat_interleave(S)[None, :, None]
+    results = []
+    for fused in (False, True):
+        t = torch.nn.Parameter(table.to(DEV).clone())
+        opt = vdbAdam([t], lr=1e-2, betas=(0.9, 0.99), eps=1e-15, bias_correction="standard", fused_zero_grad=True)
+        capi.lib().snrf_field_set_passes_log2(capi.c_int(bits if fused else -1))
+        capi.lib().snrf_field_set_levels_per_group(capi.c_int(lpg if fused else 0))
+        grads = []
+        for cot in cots:
+            oo, dd = o.to(DEV).clone().requires_grad_(True), d.to(DEV).clone().requires_grad_(True)
+            enc = _field.field_encode(oo, dd, z.to(DEV), t, res.to(DEV), bmin.to(DEV), bsize.to(DEV), mode, valid, 120)
+            opt.zero_grad()
+            with opt.table_backward(fused=fused):
+                (enc * cot * vmask).sum().backward()
+            opt.step()
+            grads.append((oo.grad.clone(), dd.grad.clone()))
+        capi.lib().snrf_field_set_passes_log2(capi.c_int(-1))
+        capi.lib().snrf_field_set_levels_per_group(capi.c_int(0))
+        if fused:
+            assert t.grad is None, "the fused path must not materialise a gradient table"
+            assert float(opt._scratch.abs().max()) == 0.0, "scratch must be left all-zero"
+        results.append((t.detach().clone(), opt.params[0][1].clone(), opt.params[0][2].clone(), grads, opt.t))
+    (p0, m0, v0, g0, t0), (p1, m1, v1, g1, t1) = results
+    assert t0 == t1 == 2
+    orig = table.to(DEV)
+    assert torch.equal(p0 == orig, p1 == orig), "the same entries are touched"
+    assert 0 < int((p1 != orig).sum()) < p1.numel()
+    assert _rel(m1, m0) < 1e-5 and _rel(v1, v0) < 1e-5
+    # the update is lr * m / sqrt(v): compare where the gradient is not a cancellation residue
+    assert float(((p1 - p0).abs() > 1e-5).float().mean()) < 1e-4, float(((p1 - p0).abs() > 1e-5).float().mean())
+    for (a_o, a_d), (b_o, b_d) in zip(g1, g0):
+        assert _rel(a_o, b_o) < 2e-5 and _rel(a_d, b_d) < 2e-5
+
+
+def test_second_encode_in_fused_backward_raises():
+    load_pkg()
+    from hashgrid import _field
+    from vdbAdam import vdbAdam
+    table, res, bmin, bsize, o, d, z_fg, _, g = _case(8, 4, 10, 2)
+    t = torch.nn.Parameter(table.to(DEV).clone())
+    opt = vdbAdam([t], bias_correction="standard", fused_zero_grad=True)
+    args = (o.to(DEV), d.to(DEV), z_fg.to(DEV), t, res.to(DEV), bmin.to(DEV), bsize.to(DEV), 1)
+    loss = _field.field_encode(*args).sum() + _field.field_encode(*args).sum()
+    with pytest.raises(RuntimeError, match="more than once"):
+        with opt.table_backward(fused=True):
+            loss.backward()
+
+
+def test_encode_backward_has_no_side_effect_outside_the_training_context():
+    """a backward outside `table_backward` (normal / validation pass, torch.autograd.grad) returns the dense
+    table gradient through autograd and leaves `.grad` alone; one that lands in `.grad` between step() and zero_grad() is
+    cleared by zero_grad() even though the fused update had left the tensor clean."""
+    load_pkg()
+    from hashgrid import _field
+    from vdbAdam import vdbAdam
+    table, res, bmin, bsize, o, d, z_fg, _, g = _case(16, 8, 10, 4)
+    t = torch.nn.Parameter(table.to(DEV).clone())
+    args = (o.to(DEV), d.to(DEV), z_fg.to(DEV), t, res.to(DEV), bmin.to(DEV), bsize.to(DEV), 1)
+    (gt,) = torch.autograd.grad(_field.field_encode(*args).sum(), t)
+    assert t.grad is None and float(gt.abs().max()) > 0
+    opt = vdbAdam([t], bias_correction="standard", fused_zero_grad=True)
+    with opt.table_backward(fused=False):
+        _field.field_encode(*args).sum().backward()
+    opt.step()
+    assert float(t.grad.abs().max()) == 0.0
+    _field.field_encode(*args).sum().backward()           # e.g. a validation pass: autograd accumulates into .grad
+    assert float(t.grad.abs().max()) > 0
+    opt.zero_grad()
+    assert float(t.grad.abs().max()) == 0.0, "zero_grad must not trust the clean flag after a foreign backward"
+
+
 def test_hashgrid_fused_and_unfused_render_agree():
     """HashGrid.render_batch_rays with and without the fused encode gives the same composited colours and gradients."""
     load_pkg()

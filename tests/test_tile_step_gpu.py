@@ -98,4 +98,20 @@ def test_training_reduces_loss_and_touches_only_sampled_entries():
     assert losses[-1] < losses[0], losses
     changed = (step.featureGrid.HE.features.detach() != before).any(-1)
     assert 0 < int(changed.sum()) < changed.numel(), "sparse Adam must leave untouched entries alone"
-    assert float(step.featureGrid.HE.features.grad.abs().max()) == 0.0, "fused zero-grad leaves a clean gradient table"
+    assert step.featureGrid.HE.features.grad is None, "scatter + update fusion: no gradient table is ever materialised"
+
+
+def test_fused_table_update_equals_unfused_step():
+    """TileStep with the scatter + update fusion (default) against the same step with the gradient table + vdbAdam.step."""
+    load_pkg()
+    dev = torch.device("cuda:0")
+    tables = []
+    for fused in (True, False):
+        step, locs, gt = _tile(dev, log2T=15)
+        step.fused_table_update = fused
+        losses = [step.step(locs.pin_memory(), gt.pin_memory()) for _ in range(3)]
+        tables.append((step.featureGrid.HE.features.detach().clone(), losses, step.featureGrid_optimizer.params[0][2].clone()))
+    (pa, la, va), (pb, lb, vb) = tables
+    assert abs(la[0] - lb[0]) < 1e-6 and abs(la[-1] - lb[-1]) < 1e-3 * abs(lb[-1])
+    assert float((va - vb).abs().max()) <= 1e-3 * float(vb.abs().max())
+    assert float(((pa - pb).abs() > 1e-4).float().mean()) < 1e-3

@@ -99,8 +99,8 @@ def bench_encode(a):
     t = timeit(lambda: gt.zero_(), a.iters, flush)
     r["zero_table_ms"] = t
     if a.ref:
-        d = os.path.join(ROOT, "oracle", "_ref"); sys.path.append(d)
-        import HASHGRID_EMBED as ref
+        import oracle
+        ref = oracle.ref_module("HASHGRID_EMBED")
         t = timeit(lambda: ref.embedding_bg_forward_cuda(pts, out, table, res), a.iters, flush)
         r["ref_fwd_ms"] = t
         t = timeit(lambda: ref.embedding_bg_backward_cuda(pts, gin, gp, gt, table, res), a.iters, flush)

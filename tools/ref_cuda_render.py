@@ -14,7 +14,6 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
 import torch  # noqa: E402
 
 import bench  # noqa: E402
@@ -65,7 +64,8 @@ def main():
     ap.add_argument("--tiles", type=int, default=1, help="copies of the tile in a row along x, foreground boxes overlapping by 10 %")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "r1_reference_cuda_render.json"))
     args = ap.parse_args()
-    import HASHGRID as REF
+    import oracle
+    REF = oracle.ref_module("HASHGRID")
     pkg = importlib.import_module(bench.PKG)
     pkg.install()
     import render_frame as rf

@@ -30,7 +30,6 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -42,8 +41,10 @@ def build_reference_step(dev, tile_corner, tile_size, Ks, c2w, log2T, grid_resol
                          lr_table=1e-3, lr_decoder=1e-3, lr_cam=1e-4):
     """A TileStep whose render path is the reference's op-by-op graph on the REFERENCE's kernels (oracle/_ref), with the
     reference's optimisers (dense torch Adam over the table).  pkg.install() must have run."""
-    import CUDA_EXT as REF_CUDA  # noqa: the rebuilt reference modules
-    import HASHGRID_EMBED as REF_HASH
+    import oracle
+    REF_CUDA, REF_HASH = oracle.ref_module("CUDA_EXT"), oracle.ref_module("HASHGRID_EMBED")   # the rebuilt reference modules
+    if REF_CUDA is None or REF_HASH is None:
+        raise RuntimeError("oracle/_ref/{CUDA_EXT,HASHGRID_EMBED}.so not built (python oracle/build_ref.py)")
     import tile_step as ts
     from hashgrid import HashGrid, TRAIN
     from hashgrid._decoder import ShallowMLP
