@@ -433,9 +433,9 @@ def main():
     for b in devb[Wm:]:
         step.step_device(*b)
         if fused:
-            out3 = (ctypes.c_float * 3)()
-            capi.lib().snrf_field_last_profile(out3)
-            prof.append(tuple(out3))
+            out4 = (ctypes.c_float * 4)()
+            capi.lib().snrf_field_last_profile(out4)
+            prof.append(tuple(out4))
     if fused:
         capi.lib().snrf_field_set_profile(ctypes.c_int(0))
     torch.cuda.synchronize()
@@ -475,15 +475,34 @@ def main():
             r.update(extra)
         return r
     if fused:
-        bwd_ms = [p0 + p1 for p0, p1, _ in prof]
-        adam_ms = [p2 for _, _, p2 in prof]
-        roofline = roof("encode backward = field_geom_raygrad_kernel + field_scatter_slice_kernel x slices (inside snrf_field_encode_bwd_adam)",
-                        bwd_ms, ENC_BWD_BYTES * N_pts, "encode_bwd",
-                        {"note": "timed per kernel class by CUDA events between the launches (snrf_field_set_profile); "
-                                 "the sparse Adam slices interleaved with the scatter are in roofline_update"})
-        roofline_update = roof("adam_slice_kernel x slices (sparse Adam over touched entries, gradient read from the L2-resident scratch)",
-                               adam_ms, 28 * (touched or 0), "adam_slices",
-                               {"touched_floats_per_step": touched, "alg_bytes_per_touched_float": 28})
+        # the whole fused sequence as the step runs it (scatter of slice k+1 overlapped with the Adam of slice k):
+        # algorithmic bytes = encode backward (2200 B / sample) + sparse update (28 B / touched float)
+        both_ms = [p[0] + p[3] for p in prof]
+        roofline = roof("encode backward + table update = field_geom_raygrad_kernel, then per L2-resident table slice "
+                        "field_scatter_slice_kernel || adam_slice_kernel (snrf_field_encode_bwd_adam)",
+                        both_ms, ENC_BWD_BYTES * N_pts + 28 * (touched or 0), "encode_bwd_adam",
+                        {"alg_bytes_encode_bwd": ENC_BWD_BYTES * N_pts, "alg_bytes_update": 28 * (touched or 0),
+                         "touched_floats_per_step": touched, "geom_raygrad_ms": sum(p[0] for p in prof) / max(len(prof), 1),
+                         "note": "timed by CUDA events on the launching stream inside the C call (snrf_field_set_profile)"})
+        # per-class breakdown: the same steps with the overlap off (serial launches, one event after each)
+        capi.lib().snrf_field_set_overlap(ctypes.c_int(0))
+        capi.lib().snrf_field_set_profile(ctypes.c_int(1))
+        serial = []
+        for b_ in devb[Wm:Wm + 5]:
+            step.step_device(*b_)
+            out4 = (ctypes.c_float * 4)()
+            capi.lib().snrf_field_last_profile(out4)
+            serial.append(tuple(out4))
+        capi.lib().snrf_field_set_profile(ctypes.c_int(0))
+        capi.lib().snrf_field_set_overlap(ctypes.c_int(1))
+        roofline_update = {
+            "what": "per-class times of the same sequence run serially (overlap off), mean of 5 steps",
+            "geom_raygrad_ms": sum(p[0] for p in serial) / 5, "scatter_ms": sum(p[1] for p in serial) / 5,
+            "adam_ms": sum(p[2] for p in serial) / 5,
+            "encode_bwd_only": {"alg_bytes": ENC_BWD_BYTES * N_pts,
+                                "frac": ENC_BWD_BYTES * N_pts / ((sum(p[0] + p[1] for p in serial) / 5) * 1e-3) / 1e9 / peak},
+            "adam_only": {"alg_bytes": 28 * (touched or 0),
+                          "frac": 28 * (touched or 0) / ((sum(p[2] for p in serial) / 5) * 1e-3) / 1e9 / peak}}
     else:
         bwd_only = k_ms[1::2]
         roofline = roof("field_bwd_kernel (snrf_field_encode_bwd: hash-encode backward)", bwd_only, ENC_BWD_BYTES * N_pts, "snrf_field_encode_bwd")

@@ -78,9 +78,12 @@ int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d, const f
                                int step, float* grad_scratch, long long scratch_entries, float* cpts_scratch,
                                const unsigned char* ray_valid, int split, int N, int S, int L, int T, void* stream);
 /* measurement hook: when on, snrf_field_encode_bwd_adam times its three kernel classes with CUDA events (and SYNCHRONISES
- * the stream); snrf_field_last_profile -> out3 = milliseconds {geometry + ray gradient, scatter slices, Adam slices} */
+ * the stream); snrf_field_last_profile -> out4 = milliseconds {geometry + ray gradient, scatter slices, Adam slices, both} */
 void snrf_field_set_profile(int on);
-void snrf_field_last_profile(float* out3);
+void snrf_field_last_profile(float* out4);   /* [3] = the scatter + Adam phase as a whole (the only split available with the overlap on) */
+/* tuning hook: 1 (default) = the scatter of slice k+1 runs concurrently with the Adam of slice k (private side stream, the
+ * scratch used as two halves); 0 = strictly serial on the caller's stream */
+void snrf_field_set_overlap(int on);
 /* kernels launched by the last snrf_field_encode_bwd_adam call (1 + 2 per table slice) */
 int snrf_field_last_launch_count(void);
 /* tuning hook: cap on whole levels per scatter / update pair of snrf_field_encode_bwd_adam (0 = as many as fit the scratch) */

@@ -634,7 +634,8 @@ int g_run_length = 0;
 int g_levels_per_group = 0;
 int g_last_launches = 0;       // kernels launched by the last snrf_field_encode_bwd_adam call
 int g_profile = 0;             // snrf_field_encode_bwd_adam: time the three kernel classes with CUDA events (synchronises!)
-float g_profile_ms[3] = {0.f, 0.f, 0.f};     // geometry + ray gradient, scatter slices, Adam slices of the last profiled call   // snrf_field_encode_bwd_adam: cap on whole levels per scatter / update pair (0 = as many as fit the scratch)
+float g_profile_ms[4] = {0.f, 0.f, 0.f, 0.f};
+int g_overlap = 1;             // snrf_field_encode_bwd_adam: scatter of slice k+1 overlaps the Adam of slice k (two streams, split scratch)     // geometry + ray gradient, scatter slices, Adam slices of the last profiled call   // snrf_field_encode_bwd_adam: cap on whole levels per scatter / update pair (0 = as many as fit the scratch)
 inline int pick_lpb(int L, int T)
 {
     const long long level_bytes = (long long)T * 8;
@@ -661,10 +662,12 @@ SNRF_API void snrf_field_set_passes_log2(int bits) { g_pass_bits_override = bits
 SNRF_API void snrf_field_set_aggregate_levels(int n) { g_aggregate_override = n; }
 // measurement hook (bench.py's roofline): when on, snrf_field_encode_bwd_adam brackets each of its launches with CUDA
 // events, SYNCHRONISES the stream at the end and keeps the summed milliseconds per kernel class for
-// snrf_field_last_profile(out[3]) = {geometry + ray gradient, scatter, Adam}.  Off by default.
+// snrf_field_last_profile(out[4]) = {geometry + ray gradient, scatter, Adam, scatter-and-Adam phase as a whole}.  With the
+// two-stream overlap on, the two classes run concurrently and only [0] and [3] are meaningful.  Off by default.
 SNRF_API int snrf_field_last_launch_count() { return g_last_launches; }
 SNRF_API void snrf_field_set_profile(int on) { g_profile = on ? 1 : 0; }
-SNRF_API void snrf_field_last_profile(float* out3) { for (int i = 0; i < 3; ++i) out3[i] = g_profile_ms[i]; }
+SNRF_API void snrf_field_last_profile(float* out4) { for (int i = 0; i < 4; ++i) out4[i] = g_profile_ms[i]; }
+SNRF_API void snrf_field_set_overlap(int on) { g_overlap = on ? 1 : 0; }
 SNRF_API void snrf_field_set_levels_per_group(int n) { g_levels_per_group = n > 0 ? n : 0; }
 SNRF_API void snrf_field_set_run_length(int r) { g_run_length = (r == 2 || r == 4 || r == 8) ? r : 0; }
 
@@ -731,11 +734,37 @@ SNRF_API int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, con
     SNRF_RETURN_LAUNCH("snrf_field_encode_bwd");
 }
 
+// Private side stream + dependency events of the scatter / update pipeline, one set per device.
+struct FusedSide {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t scat[2] = {nullptr, nullptr}, adam[2] = {nullptr, nullptr};
+};
+static FusedSide g_side[64];
+static FusedSide* fused_side()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    FusedSide& f = g_side[dev];
+    if (f.stream == nullptr) {
+        if (cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 2; ++i) {
+            cudaEventCreateWithFlags(&f.scat[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&f.adam[i], cudaEventDisableTiming);
+        }
+    }
+    return &f;
+}
+
 // Backward of snrf_field_encode_fwd fused with the sparse Adam update of the table (see the kernels above).
 // table / exp_avg / exp_avg_sq [L,T,2] are UPDATED in place with the step-`step` Adam rule on every element that received a
 // non-zero gradient; grad_rays_o / grad_rays_d / grad_points are ACCUMULATED as by snrf_field_encode_bwd.
 // grad_scratch: caller-owned device buffer of scratch_entries float2 (a power of two; 2^23 = 64 MiB keeps it L2-resident),
 // ALL ZERO on entry and left all zero on exit; cpts_scratch: [3][N] floats, overwritten.
+//
+// Pipeline (g_overlap, default on): the scratch is used as two halves; the scatter of slice k+1 (issue / L2-reduction
+// bound) runs on the caller's stream while the Adam of slice k (HBM-streaming bound) runs on a private side stream --
+// the two kernel classes need different resources and neither uses shared memory, so they share the SMs.  The caller's
+// stream waits for the last update before the function's work counts as done (plain stream semantics for the caller).
 SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
                                         const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
                                         const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points,
@@ -747,20 +776,24 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
     SNRF_CHECK_ARG(mode >= 0 && mode <= 3 && (mode == 0 ? points != nullptr : (rays_o && rays_d && z_vals && box_min && box_size && S > 0)),
                    "snrf_field_encode_bwd_adam: inconsistent arguments for mode %d", mode);
     SNRF_CHECK_ARG(grad_lm && table && exp_avg && exp_avg_sq && grad_scratch && cpts_scratch, "snrf_field_encode_bwd_adam: NULL argument");
-    SNRF_CHECK_ARG(scratch_entries >= 2 && (scratch_entries & (scratch_entries - 1)) == 0, "snrf_field_encode_bwd_adam: scratch_entries must be a power of two");
+    SNRF_CHECK_ARG(scratch_entries >= 4 && (scratch_entries & (scratch_entries - 1)) == 0, "snrf_field_encode_bwd_adam: scratch_entries must be a power of two >= 4");
     SNRF_CHECK_ARG(step >= 1, "snrf_field_encode_bwd_adam: step counts from 1 (got %d)", step);
     if (N == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     const float2 *g = (const float2*)grad_lm, *j = (const float2*)jac_lm;
     const int ray_split = mode == 1 ? 0x7fffffff : (mode == 2 ? 0 : split);
-    // profiling mode: events[k] after the k-th launch, class of launch k in cls[]
-    constexpr int kMaxEv = 160;
-    cudaEvent_t ev[kMaxEv];
+    FusedSide* side = g_overlap ? fused_side() : nullptr;
+    const bool overlap = side != nullptr;
+    // profiling mode: serial -> one event after every launch (class of launch k in cls[]); overlapped -> first / last only
+    constexpr int kMaxEv = 600;
+    static cudaEvent_t ev[kMaxEv];
+    static int n_ev_created = 0;
     int cls[kMaxEv], n_ev = 0;
     const bool prof = g_profile != 0;
     auto mark = [&](int c) {
         if (!prof || n_ev >= kMaxEv) return;
-        cudaEventCreate(&ev[n_ev]);
+        if (overlap && c > 0) return;                    // concurrent kernel classes cannot be told apart by stream events
+        if (n_ev >= n_ev_created) { cudaEventCreate(&ev[n_ev]); n_ev_created = n_ev + 1; }
         cudaEventRecord(ev[n_ev], s);
         cls[n_ev++] = c;
     };
@@ -772,40 +805,61 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
     mark(0);
     int log2T = 0;
     while ((1 << log2T) < T) ++log2T;
-    int pass_bits = 0;                                   // index ranges per level: the slice must fit the scratch
-    while (((long long)T >> pass_bits) > scratch_entries) ++pass_bits;
+    const long long capacity = overlap ? scratch_entries / 2 : scratch_entries;     // entries per in-flight slice
+    int pass_bits = 0;                                   // index ranges per level: the slice must fit its half of the scratch
+    while (((long long)T >> pass_bits) > capacity) ++pass_bits;
     if (g_pass_bits_override > pass_bits && g_pass_bits_override <= log2T - 1) pass_bits = g_pass_bits_override;
     const int range_shift = log2T - pass_bits;
     const long long slice = 1ll << range_shift;
-    int lpg = pass_bits > 0 ? 1 : (int)(scratch_entries / slice);     // whole levels per scatter / update pair
+    int lpg = pass_bits > 0 ? 1 : (int)(capacity / slice);            // whole levels per scatter / update pair
     if (lpg > L) lpg = L;
     if (g_levels_per_group > 0 && g_levels_per_group < lpg) lpg = g_levels_per_group;
     const int agg = g_aggregate_override >= 0 ? g_aggregate_override : L / 2;
     const adamcore::Hyper h{lr, beta1, beta2, eps, step};
     const int sms = snrf_sm_count();
+    int k = 0;                                            // slice counter
     for (int l0 = 0; l0 < L; l0 += lpg) {
         const int nl = l0 + lpg <= L ? lpg : L - l0;
-        for (int pass = 0; pass < (1 << pass_bits); ++pass) {
-            field_scatter_slice_kernel<<<dim3(grid_x(N), nl), kThreads, 0, s>>>(cpts_scratch, res, g, (float2*)grad_scratch, N, l0, (uint32_t)T, (uint32_t)pass, range_shift, agg);
+        for (int pass = 0; pass < (1 << pass_bits); ++pass, ++k) {
+            const int b = overlap ? (k & 1) : 0;
+            float* buf = grad_scratch + (size_t)b * capacity * 2;
+            if (overlap && k >= 2) cudaStreamWaitEvent(s, side->adam[b], 0);         // the half is free again
+            field_scatter_slice_kernel<<<dim3(grid_x(N), nl), kThreads, 0, s>>>(cpts_scratch, res, g, (float2*)buf, N, l0, (uint32_t)T, (uint32_t)pass, range_shift, agg);
             mark(1);
             const size_t base = ((size_t)l0 * T + (size_t)pass * slice) * 2;            // floats
             const long long n4 = (long long)nl * slice / 2;                              // float4 groups (two entries each)
             long long gx = (n4 + kThreads * 2 - 1) / (kThreads * 2);
             if (gx > (long long)sms * 16) gx = (long long)sms * 16;
-            adam_slice_kernel<<<(int)gx, kThreads, 0, s>>>((float4*)(table + base), (float4*)(exp_avg + base), (float4*)(exp_avg_sq + base), (float4*)grad_scratch, n4, h);
+            cudaStream_t sa = s;
+            if (overlap) {
+                cudaEventRecord(side->scat[b], s);
+                cudaStreamWaitEvent(side->stream, side->scat[b], 0);
+                sa = side->stream;
+            }
+            adam_slice_kernel<<<(int)gx, kThreads, 0, sa>>>((float4*)(table + base), (float4*)(exp_avg + base), (float4*)(exp_avg_sq + base), (float4*)buf, n4, h);
+            if (overlap) cudaEventRecord(side->adam[b], sa);
             mark(2);
         }
     }
-    g_last_launches = 1 + 2 * ((L + lpg - 1) / lpg) * (1 << pass_bits);
+    if (overlap) {
+        cudaStreamWaitEvent(s, side->adam[0], 0);
+        if (k >= 2) cudaStreamWaitEvent(s, side->adam[1], 0);
+    }
+    g_last_launches = 1 + 2 * k;
     if (prof) {
-        cudaStreamSynchronize(s);
-        g_profile_ms[0] = g_profile_ms[1] = g_profile_ms[2] = 0.f;
-        for (int k = 1; k < n_ev; ++k) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ev[k - 1], ev[k]);
-            g_profile_ms[cls[k]] += ms;
+        if (overlap && n_ev < kMaxEv) {                   // closing event on the caller's stream (after the joins)
+            if (n_ev >= n_ev_created) { cudaEventCreate(&ev[n_ev]); n_ev_created = n_ev + 1; }
+            cudaEventRecord(ev[n_ev], s);
+            cls[n_ev++] = 3;
         }
-        for (int k = 0; k < n_ev; ++k) cudaEventDestroy(ev[k]);
+        cudaStreamSynchronize(s);
+        for (int i = 0; i < 4; ++i) g_profile_ms[i] = 0.f;
+        for (int i = 1; i < n_ev; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            g_profile_ms[cls[i]] += ms;
+        }
+        if (!overlap) g_profile_ms[3] = g_profile_ms[1] + g_profile_ms[2];
     }
     SNRF_RETURN_LAUNCH("snrf_field_encode_bwd_adam");
 }

@@ -32,6 +32,8 @@ class vdbAdam:
         self._stepped = False
         self._applied = set()        # id(p) of parameters already updated inside this step's backward (fused mode)
         self._scratch = None
+        # gradient scratch of the in-backward update: 2^23 entries = 64 MiB (two 32 MiB halves in flight, L2-resident)
+        self.scratch_log2 = 23
         self._grad_versions = {}
         self.t = 0
         self.bias_correction = bias_correction
@@ -105,11 +107,11 @@ class vdbAdam:
                                "needs exactly one encode per step (use table_backward(fused=False))")
         self._applied.add(id(p))
         m, v = next((m, v) for q, m, v in self.params if q is p)
-        if self._scratch is None or self._scratch.device != p.device:
-            n = 1
-            while n < min(p.numel() // 2, 1 << 23):
-                n *= 2
-            self._scratch = torch.zeros(max(n, 2), 2, dtype=torch.float32, device=p.device)   # stays all-zero between calls
+        n = 4
+        while n < min(p.numel() // 2, 1 << self.scratch_log2):
+            n *= 2
+        if self._scratch is None or self._scratch.device != p.device or self._scratch.shape[0] != n:
+            self._scratch = torch.zeros(n, 2, dtype=torch.float32, device=p.device)   # stays all-zero between calls
         step = self.t + 1 if self.bias_correction == "standard" else max(self.t, 1)
         return m, v, self.param_groups[0], step, self._scratch
 

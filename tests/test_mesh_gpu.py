@@ -137,7 +137,13 @@ def test_against_reference_extension(B):
             t = ((A - o[hit].double()) * n).sum(-1) / (d[hit].double() * n).sum(-1)
             assert torch.allclose(t, zr[hit], rtol=1e-4, atol=1e-4), float((t - zr[hit]).abs().max())
         S = 32
-        t0 = torch.rand(B, generator=torch.Generator().manual_seed(5)) * 2.0
+        # start depths INSIDE the vertex box, as the reference's callers produce them (firstEnter depths): a start point
+        # beyond a corner of the cell grid clamps all three boundary distances to the same value, and the reference's
+        # tie rule (dda.h:100-103) then never advances -- its kernel spins forever there (ours steps in z)
+        lo, hi = torch.from_numpy(V.min(0)), torch.from_numpy(V.max(0))
+        inv = 1.0 / torch.where(d == 0, torch.full_like(d, 1e-30), d)
+        t_exit = torch.maximum((lo - o) * inv, (hi - o) * inv).min(-1)[0].clamp_min(0.0)
+        t0 = torch.rand(B, generator=torch.Generator().manual_seed(5)) * 0.9 * t_exit
         t0[::7] = -1.0
         za = torch.full((B, S), -1.0, device=dev)
         zb = torch.full((B, S), -1.0, device=dev)

@@ -1,0 +1,33 @@
+#!/usr/bin/env python
+"""One training step of the bench workload between cudaProfilerStart / Stop, for
+  ncu --profile-from-start off --set full -k regex:'field_|adam_slice|decoder_|composite' ... python tools/profile_step.py
+SNRF_PROFILE_OVERLAP=0 runs the scatter / Adam slices serially (default here: ncu serialises kernels anyway)."""
+import ctypes
+import importlib
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+pkg = importlib.import_module(bench.PKG)
+pkg.install()
+import scanerf_b200_capi as capi  # noqa: E402
+
+cfg = bench.WORKLOADS[os.environ.get("SNRF_PROFILE_WORKLOAD", "default.yaml-single-tile")]
+dev = torch.device("cuda:0")
+step, gen = bench.build_tile(cfg, dev, 0)
+capi.lib().snrf_field_set_overlap(ctypes.c_int(int(os.environ.get("SNRF_PROFILE_OVERLAP", "0"))))
+batches = [(l.to(dev), g.to(dev)) for l, g in bench.make_batches(cfg, 4, gen)]
+for b in batches[:3]:
+    step.step_device(*b)
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+loss = step.step_device(*batches[3])
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
+print("profiled step ok, loss", float(loss))
