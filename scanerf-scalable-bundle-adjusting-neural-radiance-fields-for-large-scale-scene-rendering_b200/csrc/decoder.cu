@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kThreadsDec, 1)
 decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ mask32, const float* __restrict__ rays_d,
                    DecoderParams p, const float* __restrict__ grad_heads, float* __restrict__ grad_feats,
                    float* __restrict__ grad_rays_d, DecoderGrads gp, int N, int S, int num_tiles, long long level_stride,
-                   const unsigned char* __restrict__ ray_valid)
+                   const unsigned char* __restrict__ ray_valid, const unsigned* __restrict__ gmax_bits)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -130,6 +130,20 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint32_t tail_phase = 0;
+    // Power-of-two scale of the incoming gradient: max |grad_heads| (bits in *gmax_bits, from grad_absmax_kernel) is
+    // mapped into [0.5, 1), so that the fp16 dz operands keep 15 binary orders of headroom above it for the growth along
+    // the backward chain and 14 (24 with subnormals) below it.  Everything downstream is linear in the gradient:
+    // outputs are multiplied by ginv (exact).  A zero / non-finite maximum leaves the scale at 1.
+    float gscale = 1.0f, ginv = 1.0f;
+    if (kOpBf16 == 0 && gmax_bits != nullptr) {
+        const int e = (int)((*gmax_bits >> 23) & 0xffu);            // gmax = m 2^(e - 127), m in [1, 2)
+        if (e > 0 && e < 255) {
+            int se = 253 - e;                                        // exponent field of 2^(126 - e): gmax * scale in [0.5, 1)
+            se = se < 1 ? 1 : (se > 253 ? 253 : se);
+            gscale = __uint_as_float((uint32_t)se << 23);
+            ginv = __uint_as_float((uint32_t)(254 - se) << 23);
+        }
+    }
 
     stage_all_weights<SPLIT>(smem, p, mask32, tid, kThreadsDec);
     if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);
@@ -159,12 +173,12 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     const uint32_t aW1 = umma::smem_u32(smem + oW1), aW2 = umma::smem_u32(smem + oW2), aW3 = umma::smem_u32(smem + oW3),
                    aW4 = umma::smem_u32(smem + oW4), aWh = umma::smem_u32(smem + oWh), aW5 = umma::smem_u32(smem + oW5);
     // input-gradient GEMMs: A K-major (dz rows), B MN-major (weight tile: rows = K = out, cols = N = in)
-    constexpr uint32_t idg64 = umma::idesc_bf16(128, 64, 0, 1), idg32 = umma::idesc_bf16(128, 32, 0, 1);
+    constexpr uint32_t idg64 = umma::idesc_f16(128, 64, 0, 1, kOpBf16, kOpBf16), idg32 = umma::idesc_f16(128, 32, 0, 1, kOpBf16, kOpBf16);
     // weight-gradient GEMMs: both operands MN-major, M = 64
-    // (A = dz^T, bf16; B = the layer's input activations, fp16 -- and the other way round for the transposed narrow layers)
-    constexpr uint32_t idw64 = umma::idesc_f16(64, 64, 1, 1, 1, kActBf16), idw48 = umma::idesc_f16(64, 48, 1, 1, 1, kActBf16),
-                       idw32 = umma::idesc_f16(64, 32, 1, 1, 1, kActBf16), idw16 = umma::idesc_f16(64, 16, 1, 1, 1, kActBf16),
-                       idwt16 = umma::idesc_f16(64, 16, 1, 1, kActBf16, 1);
+    // (A = dz^T; B = the layer's input activations -- and the other way round for the transposed narrow layers)
+    constexpr uint32_t idw64 = umma::idesc_f16(64, 64, 1, 1, kOpBf16, kOpBf16), idw48 = umma::idesc_f16(64, 48, 1, 1, kOpBf16, kOpBf16),
+                       idw32 = umma::idesc_f16(64, 32, 1, 1, kOpBf16, kOpBf16), idw16 = umma::idesc_f16(64, 16, 1, 1, kOpBf16, kOpBf16),
+                       idwt16 = umma::idesc_f16(64, 16, 1, 1, kOpBf16, kOpBf16);
     const uint32_t aW2l = umma::smem_u32(smem + oW2l), aW3l = umma::smem_u32(smem + oW3l), aW4l = umma::smem_u32(smem + oW4l),
                    aW5l = umma::smem_u32(smem + oW5l);
     // dA = dz W over `nk` k-steps; in SPLIT mode dz = dz_hi + dz_lo and W = W_hi + W_lo (the lo tile,
@@ -225,7 +239,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
 #pragma unroll
                 for (int e = 0; e < 8; ++e) bias_acc[8 * q + e] += o[e];
             }
-            store8_hl<SPLIT>(Tg, 2 * cg + q, Tlo, 2 * cg + q, row, o);
+            store8_act<SPLIT>(Tg, 2 * cg + q, Tlo, 2 * cg + q, row, o);
         }
     };
     // 32 accumulator columns (8 per column group) -> chunk (chunk0 + cg) of a hi / lo tile pair
@@ -234,7 +248,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         umma::tc_wait_ld();
 #pragma unroll
         for (int e = 0; e < 8; ++e) bias_acc[e] += v[e];
-        store8_hl<SPLIT>(Thi, chunk0 + cg, Tlo, chunk0 + cg, row, v);
+        store8_act<SPLIT>(Thi, chunk0 + cg, Tlo, chunk0 + cg, row, v);
     };
 
     bool first = true;      // no tile processed yet: the first one initialises the TMEM gradient accumulators
@@ -254,7 +268,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
             if (live) {
                 const float2* gsrc = reinterpret_cast<const float2*>(grad_heads + (size_t)n * 10);
 #pragma unroll
-                for (int j = 0; j < 5; ++j) { const float2 t = __ldg(gsrc + j); gh[2 * j] = t.x; gh[2 * j + 1] = t.y; }
+                for (int j = 0; j < 5; ++j) { const float2 t = __ldg(gsrc + j); gh[2 * j] = t.x * gscale; gh[2 * j + 1] = t.y * gscale; }
             } else {
 #pragma unroll
                 for (int j = 0; j < 10; ++j) gh[j] = 0.0f;
@@ -273,10 +287,10 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
                 dzs[j] = gh[7 + j] * s * (1.0f - s);                            // specular
             }
             // Tdz = [dz_heads 0..15 | dz_spec 16..31 | dz_heads_lo 32..47 | dz_spec_lo 48..63]
-            store8_hl<SPLIT>(Tdz, 0, Tdz, 4, row, dzh);
-            store8_hl<SPLIT>(Tdz, 1, Tdz, 5, row, dzh + 8);
-            store8_hl<SPLIT>(Tdz, 2, Tdz, 6, row, dzs);
-            store8_hl<SPLIT>(Tdz, 3, Tdz, 7, row, dzs + 8);
+            store8_act<SPLIT>(Tdz, 0, Tdz, 4, row, dzh);
+            store8_act<SPLIT>(Tdz, 1, Tdz, 5, row, dzh + 8);
+            store8_act<SPLIT>(Tdz, 2, Tdz, 6, row, dzs);
+            store8_act<SPLIT>(Tdz, 3, Tdz, 7, row, dzs + 8);
             // bias gradients of the narrow layers: summed per thread over the CTA's tiles, reduced once at the end
 #pragma unroll
             for (int j = 0; j < 10; ++j) acc_small[j] += j < 7 ? dzh[j] : dzs[j - 7];
@@ -351,7 +365,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
                 // v = d / (|d| + eps):  dL/dd = dv / (n+eps) - d (d . dv) / (n (n+eps)^2)
                 const float ddv = d.x * vx + d.y * vy + d.z * vz;
                 const float k2 = dn > 0.f ? ddv * inv * inv / dn : 0.f;
-                gx = vx * inv - d.x * k2; gy = vy * inv - d.y * k2; gz = vz * inv - d.z * k2;
+                gx = (vx * inv - d.x * k2) * ginv; gy = (vy * inv - d.y * k2) * ginv; gz = (vz * inv - d.z * k2) * ginv;
             }
             const int ray = live ? n / S : -1;
             const int ray0 = __shfl_sync(0xffffffffu, ray, 0);
@@ -388,7 +402,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         umma::tc_wait_ld();
         if (live) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] *= mask[8 * cg + j];
+            for (int j = 0; j < 8; ++j) v[j] *= mask[8 * cg + j] * ginv;
             if (level_stride == 0) {
                 float4* dst = reinterpret_cast<float4*>(grad_feats + (size_t)n * 32 + 8 * cg);
                 dst[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -420,7 +434,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
                 else umma::tmem_ld16(tmem + col + c0 + lane_addr, w);
                 umma::tc_wait_ld();
                 if (own)
-                    for (int j = 0; j < nc; ++j) atomicAdd(dst + (size_t)m * ld + col0 + c0 + j, w[j]);
+                    for (int j = 0; j < nc; ++j) atomicAdd(dst + (size_t)m * ld + col0 + c0 + j, w[j] * ginv);
             }
         };
         flush(cGW1, 32, gp.W1, 32, 0);
@@ -432,21 +446,21 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         // d/d b1 = column 32 of the [64 x 48] dW1 accumulator, d/d b3 = column 0 of the SH part of dW3, both / SH_0
         umma::tmem_ld16(tmem + cGW1 + 32 + lane_addr, b8);
         umma::tc_wait_ld();
-        if (own) atomicAdd(gp.b1 + m, b8[0] * kInvSH0);
+        if (own) atomicAdd(gp.b1 + m, b8[0] * kInvSH0 * ginv);
         umma::tmem_ld16(tmem + cGW3b + lane_addr, b8);
         umma::tc_wait_ld();
-        if (own) atomicAdd(gp.b3 + m, b8[0] * kInvSH0);
+        if (own) atomicAdd(gp.b3 + m, b8[0] * kInvSH0 * ginv);
         // transposed narrow layers: accumulator row = input feature k, column = output o
         umma::tmem_ld16(tmem + cGWhT + lane_addr, b8);
         umma::tc_wait_ld();
         if (own && m < 32) {
-            atomicAdd(gp.Ws + m, b8[0]);
-            for (int o = 0; o < 3; ++o) { atomicAdd(gp.Wd + o * 32 + m, b8[1 + o]); atomicAdd(gp.Wt + o * 32 + m, b8[4 + o]); }
+            atomicAdd(gp.Ws + m, b8[0] * ginv);
+            for (int o = 0; o < 3; ++o) { atomicAdd(gp.Wd + o * 32 + m, b8[1 + o] * ginv); atomicAdd(gp.Wt + o * 32 + m, b8[4 + o] * ginv); }
         }
         umma::tmem_ld16(tmem + cGW5T + lane_addr, b8);
         umma::tc_wait_ld();
         if (own)
-            for (int o = 0; o < 3; ++o) atomicAdd(gp.W5 + o * 64 + m, b8[o]);
+            for (int o = 0; o < 3; ++o) atomicAdd(gp.W5 + o * 64 + m, b8[o] * ginv);
     }
     // d/d b2, d/d b4: per-thread column sums -> sum over the 32 rows of the warp -> one atomic per warp and column
 #pragma unroll
@@ -458,8 +472,8 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
             t4 += __shfl_xor_sync(0xffffffffu, t4, off);
         }
         if (lane == 0 && !first) {
-            atomicAdd(gp.b2 + (j < 8 ? 8 * cg + j : 32 + 8 * cg + (j - 8)), t2);      // store_quarter column mapping
-            atomicAdd(gp.b4 + 16 * cg + j, t4);
+            atomicAdd(gp.b2 + (j < 8 ? 8 * cg + j : 32 + 8 * cg + (j - 8)), t2 * ginv);      // store_quarter column mapping
+            atomicAdd(gp.b4 + 16 * cg + j, t4 * ginv);
         }
     }
     if (cg == 0) {
@@ -470,7 +484,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
             for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
             if (lane == 0 && !first) {
                 float* dst = j == 0 ? gp.bs : (j < 4 ? gp.bd + (j - 1) : (j < 7 ? gp.bt + (j - 4) : gp.b5 + (j - 7)));
-                atomicAdd(dst, t);
+                atomicAdd(dst, t * ginv);
             }
         }
     }
@@ -478,6 +492,24 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     __syncthreads();
     if (warp == 0) umma::tmem_free<512>(tmem);
 }
+
+// max |grad_heads| over the live samples, as float bits (non-negative floats order like unsigned integers; a NaN sorts
+// above inf and is treated as "no scale" by the backward)
+__global__ void __launch_bounds__(256)
+grad_absmax_kernel(const float* __restrict__ g, long long n, int S, const unsigned char* __restrict__ ray_valid, unsigned* __restrict__ out)
+{
+    unsigned m = 0u;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (ray_valid != nullptr && !ray_valid[(i / 10) / S]) continue;       // rows of masked-out rays are never written
+        const unsigned b = __float_as_uint(__ldg(g + i)) & 0x7fffffffu;
+        m = b > m ? b : m;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { const unsigned o = __shfl_xor_sync(0xffffffffu, m, off); m = o > m ? o : m; }
+    if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(out, m);
+}
+__device__ unsigned g_gmax_slots[64];      // a ring: concurrent backward launches on different streams use different slots
+int g_gmax_next = 0;
 
 int g_split = 1;       // 1 = error-compensated bf16x3 operands in the forward GEMMs (default), 0 = plain bf16
 
@@ -549,9 +581,21 @@ SNRF_API int snrf_decoder_bwd(const float* feats, const float* mask32, const flo
     int grid = snrf_sm_count();            // one CTA per SM: all 512 TMEM columns, 200-225 KB of shared memory
     if (grid > num_tiles) grid = num_tiles;
     cudaStream_t s = (cudaStream_t)stream;
+    // gradient scale for the fp16 operands: max |grad_heads| -> a device slot the backward kernel reads (no host sync)
+    unsigned* slots = nullptr;
+    cudaError_t e = cudaGetSymbolAddress((void**)&slots, g_gmax_slots);
+    if (e != cudaSuccess) { snrf_set_error("snrf_decoder_bwd: %s", cudaGetErrorString(e)); return (int)e; }
+    unsigned* slot = slots + (g_gmax_next++ & 63);
+    cudaMemsetAsync(slot, 0, sizeof(unsigned), s);
+    {
+        const long long n = (long long)N * 10;
+        long long gx = (n + 256 * 8 - 1) / (256 * 8);
+        if (gx > (long long)snrf_sm_count() * 8) gx = (long long)snrf_sm_count() * 8;
+        grad_absmax_kernel<<<(int)(gx > 0 ? gx : 1), 256, 0, s>>>(grad_heads, n, S, ray_valid, slot);
+    }
     if (g_split)
-        decoder_bwd_kernel<true><<<grid, kThreadsDec, bwd_smem<true>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
+        decoder_bwd_kernel<true><<<grid, kThreadsDec, bwd_smem<true>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot);
     else
-        decoder_bwd_kernel<false><<<grid, kThreadsDec, bwd_smem<false>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
+        decoder_bwd_kernel<false><<<grid, kThreadsDec, bwd_smem<false>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot);
     SNRF_RETURN_LAUNCH("snrf_decoder_bwd");
 }

@@ -10,13 +10,18 @@ namespace dec {
 constexpr int kRows = 128;                 // samples per tile
 constexpr int kTile = kRows * 128;         // bytes of one operand tile (128 rows x 64 bf16)
 constexpr float kGaussLog2 = -50.0f * 1.4426950408889634f;   // exp(-v^2/0.02) = exp2(v^2 * kGaussLog2)
-// Operand formats.  Everything the tensor core reads is bf16 hi + bf16 lo.  Storing the ACTIVATION operands as fp16 hi / lo
-// instead (3 more mantissa bits in the hi part, which is all the weight-gradient GEMMs can still read when they run)
-// would cut their rounding from 2^-9 to 2^-12, but it needs fp16 x bf16 MMAs (gradients need bf16's exponent range),
-// and tcgen05.mma kind::f16 with a_format != b_format faults with "illegal instruction" on sm_100a (tried on B200,
-// round 1).  kActBf16 = 0 selects that (non-working) variant; it is kept as the record of the experiment.
-constexpr int kActBf16 = 1;
-constexpr float kInvSH0 = kActBf16 ? 1.0f / 0.28125f : 1.0f / 0.281982421875f;   // 1 / round(0.28209479): the SH_0 column doubles as the ones column
+// Operand format.  Everything the tensor core reads is a 16-bit hi part + a 16-bit lo part of the same format.
+// Round 1 used bf16 (kOpBf16 = 1): 16 mantissa bits for the compensated products, but the weight-gradient GEMMs can
+// only read the hi part of the ACTIVATIONS (their lo tiles are recycled by then), i.e. 8 bits -- that rounding,
+// relative to the sum of magnitudes of the per-sample terms, was the measured source of the 0.07 dB end-to-end
+// PSNR deficit.  fp16 activations against bf16 gradients / weights are not an option: tcgen05.mma
+// kind::f16 with a_format != b_format faults on sm_100a (tried in round 1).  So EVERY operand is fp16 now
+// (kOpBf16 = 0): hi parts carry 11 bits (8x less rounding where only hi is read), hi + lo 22 bits.  fp16's range is
+// handled explicitly: conversions saturate (never inf), and the backward scales the incoming gradient by a power of two
+// taken from its largest magnitude (snrf_decoder_bwd: max |grad_heads| -> [0.5, 1)), un-scaling every output exactly.
+constexpr int kOpBf16 = 0;
+constexpr int kActBf16 = kOpBf16;
+constexpr float kInvSH0 = kOpBf16 ? 1.0f / 0.28125f : 1.0f / 0.281982421875f;   // 1 / round(0.28209479): the SH_0 column doubles as the ones column
 
 // parameter tensors in network.ShallowMLP state_dict order (weight, bias per Linear)
 struct DecoderParams {
@@ -91,6 +96,13 @@ __device__ __forceinline__ void sh16(float x, float y, float z, float* o)
 }
 
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+// round to the operand format / store 8 values of a tile row in it
+__device__ __forceinline__ float op_round(float v) { return kOpBf16 ? bf16_round(v) : __half2float(__float2half_rn(v)); }
+__device__ __forceinline__ void op_tile_store8(unsigned char* tile, int row, int chunk, const float* v)
+{
+    if constexpr (kOpBf16 != 0) umma::tile_store8(tile, row, chunk, v);
+    else umma::tile_store8_f16(tile, row, chunk, v);
+}
 
 // store 8 values as the hi tile chunk and (SPLIT) their bf16 residuals as the lo tile chunk.
 // The packed hi words serve both the store and the residual (hi as float = the 16 bits shifted up): 4 + 4 packing
@@ -112,7 +124,7 @@ __device__ __forceinline__ void store8_hl(unsigned char* Thi, int chi, unsigned 
     }
 }
 
-// the same for an ACTIVATION operand (fp16 hi / lo unless kActBf16)
+// the same in the operand format (fp16 hi / lo unless kOpBf16)
 template <bool SPLIT>
 __device__ __forceinline__ void store8_act(unsigned char* Thi, int chi, unsigned char* Tlo, int clo, int row, const float* v)
 {
@@ -135,7 +147,7 @@ __device__ __forceinline__ void store8_act(unsigned char* Thi, int chi, unsigned
     }
 }
 
-// W[out, in] (row-major f32, nn.Linear layout) -> rows [row0, row0+out) of a bf16 tile: hi part in
+// W[out, in] (row-major f32, nn.Linear layout) -> rows [row0, row0+out) of an operand tile: hi part in
 // columns [0, in), and in SPLIT mode the lo part either in columns [32, 32+in) of the same tile
 // (lo_tile == tile, needs in <= 32) or in columns [0, in) of `lo_tile`.
 template <bool SPLIT>
@@ -153,13 +165,13 @@ __device__ void stage_weight(unsigned char* tile, unsigned char* lo_tile, int ro
             const int col = src_c * 8 + j;
             const float w = col < in ? W[r * rs + col * cs] : 0.0f;
             hi[j] = w;
-            lo[j] = w - bf16_round(w);
+            lo[j] = w - op_round(w);
         }
         if (SPLIT && packed) {
-            umma::tile_store8(tile, row0 + r, c, c >= 4 ? lo : hi);
+            op_tile_store8(tile, row0 + r, c, c >= 4 ? lo : hi);
         } else {
-            umma::tile_store8(tile, row0 + r, c, hi);
-            if (SPLIT) umma::tile_store8(lo_tile, row0 + r, c, lo);
+            op_tile_store8(tile, row0 + r, c, hi);
+            if (SPLIT) op_tile_store8(lo_tile, row0 + r, c, lo);
         }
     }
 }
@@ -334,8 +346,8 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
                    aW4 = umma::smem_u32(smem + oW4), aWh = umma::smem_u32(smem + oWh), aW5 = umma::smem_u32(smem + oW5),
                    aW2l = umma::smem_u32(smem + oW2l), aW3l = umma::smem_u32(smem + oW3l), aW4l = umma::smem_u32(smem + oW4l),
                    aW5l = umma::smem_u32(smem + oW5l);
-    // forward GEMMs: A = activations (fp16), B = weights (bf16), both K-major
-    constexpr uint32_t id64 = umma::idesc_f16(128, 64, 0, 0, kActBf16, 1), id16 = umma::idesc_f16(128, 16, 0, 0, kActBf16, 1);
+    // forward GEMMs: A = activations, B = weights, both K-major, both in the operand format
+    constexpr uint32_t id64 = umma::idesc_f16(128, 64, 0, 0, kOpBf16, kOpBf16), id16 = umma::idesc_f16(128, 16, 0, 0, kOpBf16, kOpBf16);
 
     c.sync_operands();
     // ---- L1: Da = x W1^T (K = 32)

@@ -627,7 +627,7 @@ inline int grid_x(int N)
 int g_pass_bits_override = -1;
 int g_aggregate_override = -1;
 // Samples per thread of field_bwd_runs_kernel; 0 = the cross-lane kernel (default).  Measured on B200 at C2 (4.19 M samples,
-// tools/dbg/sweep_field.py): cross-lane 3.69 ms, run-merging 4.15 / 4.35 / 4.39 ms at R = 2 / 4 / 8 -- merging R samples
+// tools/sweep_field.py): cross-lane 3.69 ms, run-merging 4.15 / 4.35 / 4.39 ms at R = 2 / 4 / 8 -- merging R samples
 // leaves 32 / R times more same-address reductions on the coarse levels than the cross-lane sums do, and that costs
 // more than the shuffles it saves.  Kept selectable (and parity-tested) for tables / sample densities where runs are longer.
 int g_run_length = 0;
@@ -644,7 +644,7 @@ inline int pick_lpb(int L, int T)
     return lpb;
 }
 // Index ranges per level for the scatter: keep the live gradient slice <= 64 MiB (half of the L2).
-// Measured on B200 at T = 2^24, 2.1 M points (tools/dbg/sweep_field.py): 1 range 2.22 ms, 2 ranges 2.00 ms,
+// Measured on B200 at T = 2^24, 2.1 M points (tools/sweep_field.py): 1 range 2.22 ms, 2 ranges 2.00 ms,
 // 4 ranges 2.57 ms, 8 ranges 4.43 ms -- every extra pass re-derives the hash indices (~0.49 ms), which beyond two
 // ranges costs more than the better L2 residency of the reductions saves.
 inline int pick_pass_bits(int T)

@@ -682,7 +682,7 @@ work_combine_kernel(InferArgs a, long long n0, int Nc, Work w)
 
 int g_infer_split = 1;
 int g_infer_two_pass = 1;     // single-tile scenes: level-major encode pass + decoder pass (tuning hook)
-// Tiles in flight per CTA for single-tile scenes.  Measured on B200 (1920x1080, tools/dbg/time_render.py): 1 tile in
+// Tiles in flight per CTA for single-tile scenes.  Measured on B200 (1920x1080, tools/render_one_frame.py): 1 tile in
 // flight 498 ms / frame, 2 tiles 765 ms -- the second tile's operand buffers take 80 KB away from the L1, and the table
 // gathers live on L1 hits between corners that share a sector.  Default 1; 2 stays selectable.
 int g_infer_inflight = 1;

@@ -40,10 +40,29 @@ double read_scalar_bin(const unsigned char* p, const std::string& t)
 
 }  // namespace
 
+static bool read_ply_impl(const std::string& path, HostMesh& mesh, std::string& err);
+
+// Never throws: a malformed / truncated file (or an allocation failure on a lying header) comes back as an error string,
+// so nothing propagates out of the extern "C" entry points that call this.
 bool snrf_read_ply(const std::string& path, HostMesh& mesh, std::string& err)
+{
+    try {
+        return read_ply_impl(path, mesh, err);
+    } catch (const std::exception& e) {
+        err = std::string("malformed PLY file (") + e.what() + "): " + path;
+    } catch (...) {
+        err = "malformed PLY file: " + path;
+    }
+    return false;
+}
+
+static bool read_ply_impl(const std::string& path, HostMesh& mesh, std::string& err)
 {
     std::ifstream f(path, std::ios::binary);
     if (!f) { err = "cannot open " + path; return false; }
+    f.seekg(0, std::ios::end);
+    const long long file_size = (long long)f.tellg();
+    f.seekg(0, std::ios::beg);
     std::string line;
     std::getline(f, line);
     if (line.substr(0, 3) != "ply") { err = "not a PLY file: " + path; return false; }
@@ -71,6 +90,21 @@ bool snrf_read_ply(const std::string& path, HostMesh& mesh, std::string& err)
         }
     }
     if (big) { err = "binary_big_endian PLY is not supported"; return false; }
+    // the header is untrusted: every element needs at least one byte per property and row, and every type must be known
+    {
+        const long long body = file_size - (long long)f.tellg();
+        long long need = 0;
+        for (const Elem& e : elems) {
+            if (e.props.empty() && e.count > 0) { err = "element " + e.name + " has no properties"; return false; }
+            for (const Prop& p : e.props) {
+                if (!ascii && type_size(p.type) == 0) { err = "unknown PLY type " + p.type; return false; }
+                if (!ascii && p.is_list && type_size(p.count_type) == 0) { err = "unknown PLY list count type " + p.count_type; return false; }
+            }
+            if ((long long)e.count < 0 || (long long)e.count > body) { err = "element count of " + e.name + " exceeds the file size"; return false; }
+            need += (long long)e.count * (long long)e.props.size();
+        }
+        if (need > body) { err = "PLY header declares more data than the file holds"; return false; }
+    }
 
     for (const Elem& e : elems) {
         const bool is_v = e.name == "vertex", is_f = e.name == "face";
@@ -113,7 +147,8 @@ bool snrf_read_ply(const std::string& path, HostMesh& mesh, std::string& err)
                         n = (long long)read_scalar_bin(buf, p.count_type);
                     }
                     const bool idx = is_f && (p.name == "vertex_indices" || p.name == "vertex_index");
-                    std::vector<long long> vals((size_t)std::max(0ll, n));
+                    if (!f || n < 0 || n > 255 + (file_size - (long long)f.tellg())) { err = "bad list length in element " + e.name; return false; }
+                    std::vector<long long> vals((size_t)n);
                     for (long long j = 0; j < n; ++j) {
                         if (ascii) { double v; f >> v; vals[j] = (long long)v; }
                         else {

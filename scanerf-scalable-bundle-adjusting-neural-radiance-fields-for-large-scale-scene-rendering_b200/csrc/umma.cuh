@@ -159,10 +159,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// (a -> low half, b -> high half); saturating: a value beyond +-65504 becomes +-65504, never inf
 __device__ __forceinline__ uint32_t pack_f16(float a, float b)
 {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
 // store 8 consecutive columns [8*chunk, 8*chunk+8) of row `row` as bf16
 __device__ __forceinline__ void tile_store8(unsigned char* tile, int row, int chunk, const float* v)
@@ -171,15 +173,11 @@ __device__ __forceinline__ void tile_store8(unsigned char* tile, int row, int ch
     q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
     *reinterpret_cast<uint4*>(tile + tile_chunk_off(row, chunk)) = q;
 }
-// same slot, but 8 fp16 values (element-wise scratch that is never read by the tensor core)
+// same slot, but 8 fp16 values
 __device__ __forceinline__ void tile_store8_f16(unsigned char* tile, int row, int chunk, const float* v)
 {
     uint4 q;
-    __half2 h;
-    h = __floats2half2_rn(v[0], v[1]); q.x = *reinterpret_cast<uint32_t*>(&h);
-    h = __floats2half2_rn(v[2], v[3]); q.y = *reinterpret_cast<uint32_t*>(&h);
-    h = __floats2half2_rn(v[4], v[5]); q.z = *reinterpret_cast<uint32_t*>(&h);
-    h = __floats2half2_rn(v[6], v[7]); q.w = *reinterpret_cast<uint32_t*>(&h);
+    q.x = pack_f16(v[0], v[1]); q.y = pack_f16(v[2], v[3]); q.z = pack_f16(v[4], v[5]); q.w = pack_f16(v[6], v[7]);
     *reinterpret_cast<uint4*>(tile + tile_chunk_off(row, chunk)) = q;
 }
 __device__ __forceinline__ void tile_zero8(unsigned char* tile, int row, int chunk)

@@ -164,9 +164,9 @@ def _adam(params, grad_params, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step,
         rows, dim, stride = params.numel(), 1, 1
     else:
         rows, dim = int(params.shape[0]), int(params.shape[1])
-        # the reference addresses element (k, d) at k*8 + d whatever D is (adam_kernel.cu:43);
-        # that is only in-bounds / meaningful for D == 8, any other D is treated as dense rows
-        stride = 8 if dim == 8 else dim
+        # the reference addresses element (k, d) at k*8 + d whatever D is (adam_kernel.cu:43); that is only in bounds
+        # for D == 8, where it equals the dense row stride -- so rows are always dense here
+        stride = dim
     capi.check(capi.lib().snrf_adam_step(p.ptr, g.ptr, m.ptr, v.ptr, ctypes.c_longlong(rows), c_int(dim), c_int(stride),
                                          c_int(int(half_state)), c_float(lr), c_float(beta1), c_float(beta2),
                                          c_float(eps), c_int(int(step)), c_int(int(zero_grad)), capi.stream()),

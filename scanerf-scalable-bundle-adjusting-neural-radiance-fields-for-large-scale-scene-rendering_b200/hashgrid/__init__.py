@@ -428,7 +428,9 @@ class HashGrid(nn.Module):
         R, S = z_vals.shape
         render_mode = mode
         mask16 = self.weight_feature(kwargs["global_step"])
-        params = _decoder.decoder_params(decoder) if self.fused_decoder else None
+        # out_normal differentiates sigma w.r.t. the sample positions with create_graph (hashgrid/__init__.py:547-556 of the
+        # reference): that needs the torch decoder graph, so it takes the torch branch below (decided before any work)
+        params = _decoder.decoder_params(decoder) if (self.fused_decoder and not out_normal) else None
         mode = 1 if contract_func == self.contract_fore else (2 if contract_func == self.contract_bg else 0)
         if params is not None and mode != 0 and self.fused_encode and not out_normal and self.HE.features.is_cuda:
             # fully fused path: sample position + contraction + hash encode in one kernel (level-major
@@ -447,10 +449,7 @@ class HashGrid(nn.Module):
             # stock ShallowMLP: the whole decoder runs on the tensor cores (csrc/decoder.cu) and
             # hands packed head rows straight to the compositing kernel
             heads = _field.decoder_apply(feats, rays_d, mask16.repeat_interleave(2), S, params)
-            out = _render.composite_packed(heads, z_vals, dists, rays_d, infinity, train=(render_mode is TRAIN))
-            if out_normal:
-                raise NotImplementedError("out_normal needs a twice-differentiable decoder: set HashGrid.fused_decoder = False")
-            return out, True
+            return _render.composite_packed(heads, z_vals, dists, rays_d, infinity, train=(render_mode is TRAIN)), True
         mask32 = mask16[None, None, :].repeat_interleave(2, dim=-1)
         if extra_w is not None:
             mask32 = mask32 * extra_w.reshape(R, S, 32)

@@ -231,6 +231,30 @@ def test_hashgrid_fused_and_unfused_render_agree():
             assert _rel(a[k], b[k]) < 1e-4, f"{name} (infinity={inf}): {_rel(a[k], b[k])}"
 
 
+def test_out_normal_takes_the_torch_decoder_branch():
+    """render_batch_rays(out_normal=True) with the default (tensor-core) decoder must not run the fused chain
+    and raise afterwards: it is routed to the torch decoder branch up front and returns the reference's `normal`."""
+    load_pkg()
+    from hashgrid import HashGrid, INFERENCE
+    from hashgrid._decoder import ShallowMLP
+    dev = torch.device(DEV)
+    torch.manual_seed(0)
+    hg = HashGrid(dev, torch.tensor([0.0, 0.0, 0.0], device=dev), torch.tensor([20.0, 13.0, 30.0], device=dev), 13, [16, 128], 4, False, "")
+    dec = ShallowMLP(32).to(dev)
+    g = torch.Generator().manual_seed(2)
+    R, S = 33, 16
+    o = (torch.tensor([10.0, 6.5, 15.0]) + torch.randn(R, 3, generator=g)).to(dev)
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1).to(dev)
+    z = (torch.rand(R, S, generator=g) * 6).sort(-1)[0].to(dev)
+    dist = torch.cat([z[:, 1:] - z[:, :-1], torch.full((R, 1), 1e-3, device=dev)], -1)
+    assert hg.fused_decoder
+    # (as in the reference, the sample positions must be part of the autograd graph: pose-refined rays are)
+    out, ok = hg.render_batch_rays(o.clone().requires_grad_(True), d, z, dist, dec, INFERENCE, hg.contract_fore, out_normal=True, global_step=9000)
+    assert ok and out["normal"].shape == (R, 3) and bool(torch.isfinite(out["normal"]).all())
+    plain, _ = hg.render_batch_rays(o, d, z, dist, dec, INFERENCE, hg.contract_fore, global_step=9000)
+    assert torch.allclose(plain["rgb"], out["rgb"], atol=1e-4)
+
+
 def test_masked_render_equals_compacted_render():
     """render_fore_rays / render_bg_rays: the sync-free masked path (every kernel skips masked-out rays)
     against the reference-style boolean compaction + scatter-back, values and gradients."""

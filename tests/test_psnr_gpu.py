@@ -6,7 +6,7 @@ tile is trained for a few hundred steps twice from the same initialisation on th
 both with the reference's dense Adam over the table, and the PSNR on held-out rays is compared.  Training is chaotic in
 the last bits (the atomic gradient scatter of either path sums in a different order every run: two runs of ONE path
 differ by up to ~0.1 dB after 300 steps), so each path is trained twice and the run-to-run spread is allowed on top of
-the 0.05 dB between the means.  Observed on B200 (tools/dbg/psnr_variants.py, two runs each): reference path 36.88 / 36.92 dB;
+the 0.05 dB between the means.  Observed on B200 (tools/psnr_variants.py, two runs each): reference path 36.88 / 36.92 dB;
 this repo with the fp32 torch decoder (HashGrid.fused_decoder = False) 36.92 / 36.91 dB, with the fused encode switched off as
 well 36.94 / 36.93 dB; with the tensor-core decoder 36.80-36.86 dB, i.e. ~0.07 dB below (the weight-gradient GEMMs read
 bf16-rounded activations).  With pose refinement off: 35.75-35.77 vs 35.72 dB.  The test
@@ -104,6 +104,6 @@ def test_psnr_delta_against_reference_path():
     print(f"PSNR before {p0:.3f} dB; after {len(train)} steps: this repo {pa1:.3f} / {pa2:.3f} dB, reference path {pb1:.3f} / {pb2:.3f} dB (two runs each)")
     assert min(pb1, pb2) > p0 + 3.0, "the reference path must learn the target for the comparison to mean something"
     delta = 0.5 * (pa1 + pa2) - 0.5 * (pb1 + pb2)
-    # measured deficit of the tensor-core decoder: 0.06-0.07 dB; the bound leaves that plus the noise
-    assert delta > -(0.10 + spread), (pa1, pa2, pb1, pb2)
+    # the north star's bar: PSNR delta under 0.05 dB (plus the measured run-to-run noise of training itself)
+    assert delta > -(0.05 + spread), (pa1, pa2, pb1, pb2)
     assert abs(delta) < 0.25, (pa1, pa2, pb1, pb2)

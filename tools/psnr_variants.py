@@ -1,5 +1,5 @@
 import sys, os, importlib, importlib.util, math, tempfile, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
 import bench, scenes
 pkg = importlib.import_module(bench.PKG); pkg.install()

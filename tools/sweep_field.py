@@ -1,6 +1,6 @@
 """Time the field-encode kernels inside the real training step for several scatter pass counts."""
 import sys, os, importlib, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench
 pkg = importlib.import_module(bench.PKG); pkg.install()

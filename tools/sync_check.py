@@ -1,6 +1,6 @@
 """Run training steps / a render frame with torch's sync debug mode: every host synchronisation inside is reported."""
 import sys, os, importlib, warnings, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench
 pkg = importlib.import_module(bench.PKG); pkg.install()
