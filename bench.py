@@ -446,10 +446,10 @@ def main():
     # touched table floats of one step (what the sparse update moves): entries whose second moment changed
     touched = None
     if hasattr(opt, "params"):
-        v_before = opt.params[0][2].clone()
+        m_before, v_before = opt.params[0][1].clone(), opt.params[0][2].clone()
         step.step_device(*devb[-1])
-        touched = int((opt.params[0][2] != v_before).sum().item())
-        del v_before
+        touched = int(((opt.params[0][1] != m_before) | (opt.params[0][2] != v_before)).sum().item())
+        del m_before, v_before
 
     if rank != 0:
         if world > 1:
@@ -475,38 +475,41 @@ def main():
             r.update(extra)
         return r
     if fused:
-        # the whole fused sequence as the step runs it (scatter of slice k+1 overlapped with the Adam of slice k):
-        # algorithmic bytes = encode backward (2200 B / sample) + sparse update (28 B / touched float)
-        both_ms = [p[0] + p[3] for p in prof]
-        roofline = roof("encode backward + table update = field_geom_raygrad_kernel, then per L2-resident table slice "
-                        "field_scatter_slice_kernel || adam_slice_kernel (snrf_field_encode_bwd_adam)",
-                        both_ms, ENC_BWD_BYTES * N_pts + 28 * (touched or 0), "encode_bwd_adam",
-                        {"alg_bytes_encode_bwd": ENC_BWD_BYTES * N_pts, "alg_bytes_update": 28 * (touched or 0),
-                         "touched_floats_per_step": touched, "geom_raygrad_ms": sum(p[0] for p in prof) / max(len(prof), 1),
-                         "note": "timed by CUDA events on the launching stream inside the C call (snrf_field_set_profile)"})
-        # per-class breakdown: the same steps with the overlap off (serial launches, one event after each)
-        capi.lib().snrf_field_set_overlap(ctypes.c_int(0))
+        # per kernel class, from the library's own events between the launches on the launching stream.  When classes run
+        # concurrently (the sparse coarse levels on the side stream) only geometry [0] and the whole scatter + Adam phase
+        # [3] are separable: the per-class split then comes from a few more steps with the side stream off.
+        import statistics as st
+        mean = lambda xs: sum(xs) / max(len(xs), 1)
+        phase_ms = [p[0] + p[3] for p in prof]
+        capi.lib().snrf_field_set_coarse_concurrent(ctypes.c_int(0))
         capi.lib().snrf_field_set_profile(ctypes.c_int(1))
         serial = []
-        for b_ in devb[Wm:Wm + 5]:
+        for b_ in devb[Wm:Wm + 8]:
             step.step_device(*b_)
             out4 = (ctypes.c_float * 4)()
             capi.lib().snrf_field_last_profile(out4)
             serial.append(tuple(out4))
         capi.lib().snrf_field_set_profile(ctypes.c_int(0))
-        capi.lib().snrf_field_set_overlap(ctypes.c_int(1))
-        roofline_update = {
-            "what": "per-class times of the same sequence run serially (overlap off), mean of 5 steps",
-            "geom_raygrad_ms": sum(p[0] for p in serial) / 5, "scatter_ms": sum(p[1] for p in serial) / 5,
-            "adam_ms": sum(p[2] for p in serial) / 5,
-            "encode_bwd_only": {"alg_bytes": ENC_BWD_BYTES * N_pts,
-                                "frac": ENC_BWD_BYTES * N_pts / ((sum(p[0] + p[1] for p in serial) / 5) * 1e-3) / 1e9 / peak},
-            "adam_only": {"alg_bytes": 28 * (touched or 0),
-                          "frac": 28 * (touched or 0) / ((sum(p[2] for p in serial) / 5) * 1e-3) / 1e9 / peak}}
+        capi.lib().snrf_field_set_coarse_concurrent(ctypes.c_int(1))
+        # time the concurrent run saves, attributed to the two classes in proportion to their serial times
+        gain = mean(phase_ms) / max(mean([p[0] + p[1] + p[2] for p in serial]), 1e-9)
+        bwd_ms = [(p[0] + p[1]) * gain for p in serial]
+        adam_ms = [p[2] * gain for p in serial]
+        roofline = roof("encode backward = field_geom_raygrad_kernel + field_scatter_slice_kernel x table slices (inside snrf_field_encode_bwd_adam)",
+                        bwd_ms, ENC_BWD_BYTES * N_pts, "encode_bwd",
+                        {"geom_raygrad_ms": mean([p[0] for p in serial]), "scatter_ms_serial": mean([p[1] for p in serial]),
+                         "adam_ms_serial": mean([p[2] for p in serial]), "whole_phase_ms_as_run": mean(phase_ms), "concurrency_gain": gain,
+                         "note": "CUDA events between the launches on the launching stream inside the C call (snrf_field_set_profile); "
+                                 "per-class times measured with the coarse-level side stream off and scaled by whole_phase_as_run / serial_sum"})
+        roofline_update = roof("adam_slice_kernel x table slices (sparse Adam over touched entries, gradient read from the L2-resident scratch)",
+                               adam_ms, 28 * (touched or 0), "adam_slices",
+                               {"touched_floats_per_step": touched, "alg_bytes_per_touched_float": 28})
+        roofline_both = roof("encode backward + table update, the whole snrf_field_encode_bwd_adam sequence as run", phase_ms,
+                             ENC_BWD_BYTES * N_pts + 28 * (touched or 0), "encode_bwd_adam")
     else:
         bwd_only = k_ms[1::2]
         roofline = roof("field_bwd_kernel (snrf_field_encode_bwd: hash-encode backward)", bwd_only, ENC_BWD_BYTES * N_pts, "snrf_field_encode_bwd")
-        roofline_update = None
+        roofline_update = roofline_both = None
     roofline_fwd = roof("field_fwd_kernel (snrf_field_encode_fwd: position + contraction + 16-level encode + Jacobian store)",
                         fwd_ms, ENC_FWD_BYTES * N_pts, "encode_fwd")
     line = {
@@ -527,6 +530,7 @@ def main():
     }
     if roofline_update is not None:
         line["roofline_update"] = roofline_update
+        line["roofline_bwd_and_update"] = roofline_both
     if world == 1 and not args.no_render:
         line["render"] = bench_render(step, cfg, dev)
     if world == 1 and not args.no_variants:

@@ -69,21 +69,27 @@ int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, const float*
  * grad_scratch and consumed by the update on the spot, so no [L,T,2] gradient ever exists in HBM.  Equivalent to
  * snrf_field_encode_bwd into a zeroed gradient table followed by snrf_adam_step(..., step, zero_grad = 1).
  * table / exp_avg / exp_avg_sq [L,T,2] UPDATED in place; grad_rays_o / grad_rays_d / grad_points ACCUMULATED.
- * grad_scratch: scratch_entries float2 (a power of two; 2^23 = 64 MiB stays L2-resident), ALL ZERO on entry, left all zero;
+ * grad_scratch: scratch_entries float2, ALL ZERO on entry, left all zero: 2^23 (64 MiB, one L2-resident slice) is enough;
+ * with T + 2^23 entries the levels [0, small_levels) -- those with few grid vertices, (rx+1)(ry+1)(rz+1) <= 2^22, whose
+ * touched set is small whatever T is -- are reduced in one pass over the whole level instead of index range by index range;
  * cpts_scratch: 3 * N floats, overwritten (contracted sample positions, SoA). */
 int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
                                const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
                                const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points,
                                float* table, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
-                               int step, float* grad_scratch, long long scratch_entries, float* cpts_scratch,
+                               int step, float* grad_scratch, long long scratch_entries, int small_levels, float* cpts_scratch,
                                const unsigned char* ray_valid, int split, int N, int S, int L, int T, void* stream);
 /* measurement hook: when on, snrf_field_encode_bwd_adam times its three kernel classes with CUDA events (and SYNCHRONISES
  * the stream); snrf_field_last_profile -> out4 = milliseconds {geometry + ray gradient, scatter slices, Adam slices, both} */
 void snrf_field_set_profile(int on);
 void snrf_field_last_profile(float* out4);   /* [3] = the scatter + Adam phase as a whole (the only split available with the overlap on) */
-/* tuning hook: 1 (default) = the scatter of slice k+1 runs concurrently with the Adam of slice k (private side stream, the
- * scratch used as two halves); 0 = strictly serial on the caller's stream */
+/* tuning hook: 1 = the scatter of slice k+1 runs concurrently with the Adam of slice k (private side stream, the scratch
+ * used as two halves); 0 (default; measured faster per byte of scratch) = strictly serial on the caller's stream */
 void snrf_field_set_overlap(int on);
+/* tuning hooks: run the single-pass coarse levels on a private side stream next to the other levels (default 1);
+ * log2 of the entries of one L2-resident slice (default 23) */
+void snrf_field_set_coarse_concurrent(int on);
+void snrf_field_set_slice_log2(int bits);
 /* kernels launched by the last snrf_field_encode_bwd_adam call (1 + 2 per table slice) */
 int snrf_field_last_launch_count(void);
 /* tuning hook: cap on whole levels per scatter / update pair of snrf_field_encode_bwd_adam (0 = as many as fit the scratch) */

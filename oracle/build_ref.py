@@ -19,7 +19,12 @@ Targets (python oracle/build_ref.py [target ...] [-j N]):
   fastmesh  fastMesh        fastMesh/src/fastMesh_kernel.cu + reference binding.cpp
   hashgrid  HASHGRID        the full reference hashgrid module incl. rendering_kernel.cu
                             (about 40 minutes of single-threaded ptxas time)
-Outputs: oracle/_ref/<MODULE>.so (+ objects in oracle/_ref/obj/).  oracle/_ref/ is
+  drivers   ref_drivers.zip the reference's Python side (tile.py, admm_trainer.py, rendering.py, camera*.py, network.py,
+                            losses, tools/, config/*.yaml and the __init__.py / PyHashGrid*.py wrappers of its three
+                            extension packages), zipped UNMODIFIED where it lies into one build artefact that
+                            tests/ref_driver_harness.py puts on sys.path (zipimport), so that the reference's own drivers
+                            can run on the GPU box -- on top of the drop-in, or on top of the rebuilt reference modules
+Outputs: oracle/_ref/<MODULE>.so (+ objects in oracle/_ref/obj/), oracle/_ref/ref_drivers.zip.  oracle/_ref/ is
 git-ignored but travels to the GPU box with the gpurun snapshot.
 """
 import argparse
@@ -123,11 +128,33 @@ TARGETS = {
 }
 
 
+def build_drivers():
+    """oracle/_ref/ref_drivers.zip: the reference's Python files, byte for byte, plus three empty generated
+    `<pkg>/lib/__init__.py` so that `hashgrid.lib` / `cuda.lib` / `fastMesh.lib` exist as packages (the reference's make.sh
+    copies the built .so files there; the harness maps those module names to oracle/_ref/*.so)."""
+    import glob
+    import zipfile
+    out = os.path.join(OUT, "ref_drivers.zip")
+    files = sorted(glob.glob(os.path.join(REF, "*.py")) + glob.glob(os.path.join(REF, "tools", "*.py")) +
+                   glob.glob(os.path.join(REF, "config", "*.yaml")) +
+                   [os.path.join(REF, "hashgrid", n) for n in ("__init__.py", "PyHashGrid.py", "PyHashGridBG.py")] +
+                   [os.path.join(REF, "cuda", "__init__.py"), os.path.join(REF, "fastMesh", "__init__.py")])
+    with zipfile.ZipFile(out, "w", zipfile.ZIP_DEFLATED) as z:
+        for f in files:
+            z.write(f, os.path.relpath(f, REF))
+        for pkg in ("hashgrid", "cuda", "fastMesh"):
+            z.writestr(f"{pkg}/lib/__init__.py", "")
+    print(f"[oracle/build_ref] wrote {out} ({len(files)} reference files)", flush=True)
+
+
 def build(names, jobs):
     if not os.path.isdir(REF):
         print(f"[oracle/build_ref] {REF} not present - keeping prebuilt oracle/_ref as is")
         return
     os.makedirs(OBJ, exist_ok=True)
+    if "drivers" in names:
+        build_drivers()
+        names = [n for n in names if n != "drivers"]
     work = []
     for n in names:
         t = TARGETS[n]

@@ -632,10 +632,17 @@ int g_aggregate_override = -1;
 // more than the shuffles it saves.  Kept selectable (and parity-tested) for tables / sample densities where runs are longer.
 int g_run_length = 0;
 int g_levels_per_group = 0;
+long long g_slice_cap = 1ll << 23;      // entries of one fine slice (64 MiB of gradient: what stays L2-resident while it is reduced into)
+int g_coarse_concurrent = 1;           // the single-pass coarse levels run on a side stream next to the fine chain
 int g_last_launches = 0;       // kernels launched by the last snrf_field_encode_bwd_adam call
 int g_profile = 0;             // snrf_field_encode_bwd_adam: time the three kernel classes with CUDA events (synchronises!)
 float g_profile_ms[4] = {0.f, 0.f, 0.f, 0.f};
-int g_overlap = 1;             // snrf_field_encode_bwd_adam: scatter of slice k+1 overlaps the Adam of slice k (two streams, split scratch)     // geometry + ray gradient, scatter slices, Adam slices of the last profiled call   // snrf_field_encode_bwd_adam: cap on whole levels per scatter / update pair (0 = as many as fit the scratch)
+// snrf_field_encode_bwd_adam: scatter of slice k+1 overlaps the Adam of slice k (two streams, split scratch).  Measured on
+// B200 at C2 (profiles/r2c_fused_sweep.json): serial with a 64 MiB scratch 4.94 ms for the scatter + Adam phase; overlapped
+// with two 64 MiB halves 4.73 ms, with two 32 MiB halves (four index ranges per level) 5.70 ms.  The two kernel classes
+// both live on the L2 slices (reductions / HBM streaming through L2), so they contend instead of complementing each
+// other; the 4 % do not pay for a second 64 MiB of scratch, hence off by default.
+int g_overlap = 0;     // geometry + ray gradient, scatter slices, Adam slices of the last profiled call   // snrf_field_encode_bwd_adam: cap on whole levels per scatter / update pair (0 = as many as fit the scratch)
 inline int pick_lpb(int L, int T)
 {
     const long long level_bytes = (long long)T * 8;
@@ -668,6 +675,8 @@ SNRF_API int snrf_field_last_launch_count() { return g_last_launches; }
 SNRF_API void snrf_field_set_profile(int on) { g_profile = on ? 1 : 0; }
 SNRF_API void snrf_field_last_profile(float* out4) { for (int i = 0; i < 4; ++i) out4[i] = g_profile_ms[i]; }
 SNRF_API void snrf_field_set_overlap(int on) { g_overlap = on ? 1 : 0; }
+SNRF_API void snrf_field_set_coarse_concurrent(int on) { g_coarse_concurrent = on ? 1 : 0; }
+SNRF_API void snrf_field_set_slice_log2(int bits) { g_slice_cap = 1ll << (bits < 2 ? 2 : (bits > 30 ? 30 : bits)); }
 SNRF_API void snrf_field_set_levels_per_group(int n) { g_levels_per_group = n > 0 ? n : 0; }
 SNRF_API void snrf_field_set_run_length(int r) { g_run_length = (r == 2 || r == 4 || r == 8) ? r : 0; }
 
@@ -737,7 +746,7 @@ SNRF_API int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, con
 // Private side stream + dependency events of the scatter / update pipeline, one set per device.
 struct FusedSide {
     cudaStream_t stream = nullptr;
-    cudaEvent_t scat[2] = {nullptr, nullptr}, adam[2] = {nullptr, nullptr};
+    cudaEvent_t scat[2] = {nullptr, nullptr}, adam[2] = {nullptr, nullptr}, fork = nullptr, join = nullptr;
 };
 static FusedSide g_side[64];
 static FusedSide* fused_side()
@@ -751,6 +760,8 @@ static FusedSide* fused_side()
             cudaEventCreateWithFlags(&f.scat[i], cudaEventDisableTiming);
             cudaEventCreateWithFlags(&f.adam[i], cudaEventDisableTiming);
         }
+        cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming);
     }
     return &f;
 }
@@ -758,55 +769,54 @@ static FusedSide* fused_side()
 // Backward of snrf_field_encode_fwd fused with the sparse Adam update of the table (see the kernels above).
 // table / exp_avg / exp_avg_sq [L,T,2] are UPDATED in place with the step-`step` Adam rule on every element that received a
 // non-zero gradient; grad_rays_o / grad_rays_d / grad_points are ACCUMULATED as by snrf_field_encode_bwd.
-// grad_scratch: caller-owned device buffer of scratch_entries float2 (a power of two; 2^23 = 64 MiB keeps it L2-resident),
-// ALL ZERO on entry and left all zero on exit; cpts_scratch: [3][N] floats, overwritten.
+// grad_scratch: caller-owned device buffer of scratch_entries float2, ALL ZERO on entry and left all zero on exit;
+// cpts_scratch: [3][N] floats, overwritten.
 //
-// Pipeline (g_overlap, default on): the scratch is used as two halves; the scatter of slice k+1 (issue / L2-reduction
-// bound) runs on the caller's stream while the Adam of slice k (HBM-streaming bound) runs on a private side stream --
-// the two kernel classes need different resources and neither uses shared memory, so they share the SMs.  The caller's
-// stream waits for the last update before the function's work counts as done (plain stream semantics for the caller).
+// How the table is cut into slices.  What has to stay L2-resident while a slice is being reduced into is the set of
+// TOUCHED sectors, not the address range:
+//   * levels [0, small_levels) have few grid vertices (the caller counts them: (rx+1)(ry+1)(rz+1) <= 2^22), so their
+//     touched set is small whatever T is: they are scattered in ONE pass over the whole level, into the first T entries of
+//     the scratch (needs scratch_entries >= T + the fine slice; otherwise they are treated like the others);
+//   * the other levels touch (nearly) every entry: their slice is an index range of at most g_slice_cap entries
+//     (2^23 = 64 MiB of gradient), 2 ranges per level at T = 2^24, several whole levels per slice at small T.
+// The coarse levels are issue-bound (cross-lane segmented sums), the fine ones bound by the L2 reduction rate
+// (profiles/r2d_*): with g_coarse_concurrent the coarse chain runs on a private side stream next to the fine chain.
+// g_overlap (off by default, see there) additionally overlaps scatter k+1 with Adam k inside the fine chain.
 SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
                                         const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
                                         const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points,
                                         float* table, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
-                                        int step, float* grad_scratch, long long scratch_entries, float* cpts_scratch,
+                                        int step, float* grad_scratch, long long scratch_entries, int small_levels, float* cpts_scratch,
                                         const unsigned char* ray_valid, int split, int N, int S, int L, int T, void* stream)
 {
     SNRF_CHECK_ARG(N >= 0 && L > 0 && T > 1 && (T & (T - 1)) == 0, "snrf_field_encode_bwd_adam: T must be a power of two (N=%d L=%d T=%d)", N, L, T);
     SNRF_CHECK_ARG(mode >= 0 && mode <= 3 && (mode == 0 ? points != nullptr : (rays_o && rays_d && z_vals && box_min && box_size && S > 0)),
                    "snrf_field_encode_bwd_adam: inconsistent arguments for mode %d", mode);
     SNRF_CHECK_ARG(grad_lm && table && exp_avg && exp_avg_sq && grad_scratch && cpts_scratch, "snrf_field_encode_bwd_adam: NULL argument");
-    SNRF_CHECK_ARG(scratch_entries >= 4 && (scratch_entries & (scratch_entries - 1)) == 0, "snrf_field_encode_bwd_adam: scratch_entries must be a power of two >= 4");
+    SNRF_CHECK_ARG(scratch_entries >= 4, "snrf_field_encode_bwd_adam: scratch_entries must be at least 4");
     SNRF_CHECK_ARG(step >= 1, "snrf_field_encode_bwd_adam: step counts from 1 (got %d)", step);
     if (N == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     const float2 *g = (const float2*)grad_lm, *j = (const float2*)jac_lm;
     const int ray_split = mode == 1 ? 0x7fffffff : (mode == 2 ? 0 : split);
-    FusedSide* side = g_overlap ? fused_side() : nullptr;
-    const bool overlap = side != nullptr;
-    // profiling mode: serial -> one event after every launch (class of launch k in cls[]); overlapped -> first / last only
-    constexpr int kMaxEv = 600;
-    static cudaEvent_t ev[kMaxEv];
-    static int n_ev_created = 0;
-    int cls[kMaxEv], n_ev = 0;
-    const bool prof = g_profile != 0;
-    auto mark = [&](int c) {
-        if (!prof || n_ev >= kMaxEv) return;
-        if (overlap && c > 0) return;                    // concurrent kernel classes cannot be told apart by stream events
-        if (n_ev >= n_ev_created) { cudaEventCreate(&ev[n_ev]); n_ev_created = n_ev + 1; }
-        cudaEventRecord(ev[n_ev], s);
-        cls[n_ev++] = c;
-    };
-    mark(-1);
-    if (mode == 0)
-        field_geom_raygrad_kernel<kNone><<<grid_x(N), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, g, j, grad_rays_o, grad_rays_d, grad_points, cpts_scratch, ray_valid, ray_split, N, S, L);
-    else
-        field_geom_raygrad_kernel<kRays><<<grid_x(N), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, g, j, grad_rays_o, grad_rays_d, grad_points, cpts_scratch, ray_valid, ray_split, N, S, L);
-    mark(0);
     int log2T = 0;
     while ((1 << log2T) < T) ++log2T;
-    const long long capacity = overlap ? scratch_entries / 2 : scratch_entries;     // entries per in-flight slice
-    int pass_bits = 0;                                   // index ranges per level: the slice must fit its half of the scratch
+
+    // ---- slicing plan
+    long long fine_cap = 1;                                  // largest power of two <= min(scratch, g_slice_cap)
+    while (fine_cap * 2 <= scratch_entries && fine_cap * 2 <= g_slice_cap) fine_cap *= 2;
+    if (small_levels < 0) small_levels = 0;
+    if (small_levels > L) small_levels = L;
+    // single-pass coarse levels only make a difference when a level does not fit a fine slice, and need their own T entries
+    const bool coarse_single = small_levels > 0 && (long long)T > fine_cap && scratch_entries >= (long long)T + fine_cap;
+    if (!coarse_single) small_levels = 0;
+    float* coarse_buf = grad_scratch;
+    float* fine_buf = coarse_single ? grad_scratch + (size_t)T * 2 : grad_scratch;
+    FusedSide* side = (g_overlap || (coarse_single && g_coarse_concurrent)) ? fused_side() : nullptr;
+    const bool overlap = g_overlap && side != nullptr;
+    const bool coarse_on_side = coarse_single && g_coarse_concurrent && side != nullptr && !overlap;
+    const long long capacity = overlap ? fine_cap / 2 : fine_cap;                  // entries per in-flight fine slice
+    int pass_bits = 0;
     while (((long long)T >> pass_bits) > capacity) ++pass_bits;
     if (g_pass_bits_override > pass_bits && g_pass_bits_override <= log2T - 1) pass_bits = g_pass_bits_override;
     const int range_shift = log2T - pass_bits;
@@ -817,41 +827,86 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
     const int agg = g_aggregate_override >= 0 ? g_aggregate_override : L / 2;
     const adamcore::Hyper h{lr, beta1, beta2, eps, step};
     const int sms = snrf_sm_count();
+
+    // profiling mode: one event after every launch on the caller's stream (class of launch k in cls[]); when kernel classes
+    // run concurrently (overlap / coarse chain on the side stream) only the whole phase can be timed: class 3
+    constexpr int kMaxEv = 600;
+    static cudaEvent_t ev[kMaxEv];
+    static int n_ev_created = 0;
+    int cls[kMaxEv], n_ev = 0;
+    const bool prof = g_profile != 0;
+    const bool concurrent = overlap || coarse_on_side;
+    auto mark = [&](int c, bool force = false) {
+        if (!prof || n_ev >= kMaxEv) return;
+        if (concurrent && c > 0 && !force) return;
+        if (n_ev >= n_ev_created) { cudaEventCreate(&ev[n_ev]); n_ev_created = n_ev + 1; }
+        cudaEventRecord(ev[n_ev], s);
+        cls[n_ev++] = c;
+    };
+    auto adam_launch = [&](cudaStream_t st, float* buf, int l0, int nl, long long base_entry, long long entries) {
+        const size_t base = ((size_t)l0 * T + (size_t)base_entry) * 2;                  // floats
+        const long long n4 = (long long)nl * entries / 2;                                // float4 groups (two entries each)
+        long long gx = (n4 + kThreads * 2 - 1) / (kThreads * 2);
+        if (gx > (long long)sms * 16) gx = (long long)sms * 16;
+        adam_slice_kernel<<<(int)gx, kThreads, 0, st>>>((float4*)(table + base), (float4*)(exp_avg + base), (float4*)(exp_avg_sq + base), (float4*)buf, n4, h);
+    };
+
+    mark(-1);
+    if (mode == 0)
+        field_geom_raygrad_kernel<kNone><<<grid_x(N), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, g, j, grad_rays_o, grad_rays_d, grad_points, cpts_scratch, ray_valid, ray_split, N, S, L);
+    else
+        field_geom_raygrad_kernel<kRays><<<grid_x(N), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, g, j, grad_rays_o, grad_rays_d, grad_points, cpts_scratch, ray_valid, ray_split, N, S, L);
+    mark(0);
+    int launches = 1;
+
+    // ---- coarse chain: one pass per level over the whole level slice
+    if (coarse_single) {
+        cudaStream_t sc = s;
+        if (coarse_on_side) {
+            cudaEventRecord(side->fork, s);
+            cudaStreamWaitEvent(side->stream, side->fork, 0);
+            sc = side->stream;
+        }
+        for (int l = 0; l < small_levels; ++l) {
+            field_scatter_slice_kernel<<<dim3(grid_x(N), 1), kThreads, 0, sc>>>(cpts_scratch, res, g, (float2*)coarse_buf, N, l, (uint32_t)T, 0u, log2T, agg);
+            if (!coarse_on_side) mark(1);
+            adam_launch(sc, coarse_buf, l, 1, 0, T);
+            if (!coarse_on_side) mark(2);
+            launches += 2;
+        }
+        if (coarse_on_side) cudaEventRecord(side->join, sc);
+    }
+
+    // ---- fine chain
     int k = 0;                                            // slice counter
-    for (int l0 = 0; l0 < L; l0 += lpg) {
+    for (int l0 = small_levels; l0 < L; l0 += lpg) {
         const int nl = l0 + lpg <= L ? lpg : L - l0;
         for (int pass = 0; pass < (1 << pass_bits); ++pass, ++k) {
             const int b = overlap ? (k & 1) : 0;
-            float* buf = grad_scratch + (size_t)b * capacity * 2;
+            float* buf = fine_buf + (size_t)b * capacity * 2;
             if (overlap && k >= 2) cudaStreamWaitEvent(s, side->adam[b], 0);         // the half is free again
             field_scatter_slice_kernel<<<dim3(grid_x(N), nl), kThreads, 0, s>>>(cpts_scratch, res, g, (float2*)buf, N, l0, (uint32_t)T, (uint32_t)pass, range_shift, agg);
             mark(1);
-            const size_t base = ((size_t)l0 * T + (size_t)pass * slice) * 2;            // floats
-            const long long n4 = (long long)nl * slice / 2;                              // float4 groups (two entries each)
-            long long gx = (n4 + kThreads * 2 - 1) / (kThreads * 2);
-            if (gx > (long long)sms * 16) gx = (long long)sms * 16;
             cudaStream_t sa = s;
             if (overlap) {
                 cudaEventRecord(side->scat[b], s);
                 cudaStreamWaitEvent(side->stream, side->scat[b], 0);
                 sa = side->stream;
             }
-            adam_slice_kernel<<<(int)gx, kThreads, 0, sa>>>((float4*)(table + base), (float4*)(exp_avg + base), (float4*)(exp_avg_sq + base), (float4*)buf, n4, h);
+            adam_launch(sa, buf, l0, nl, (long long)pass * slice, slice);
             if (overlap) cudaEventRecord(side->adam[b], sa);
             mark(2);
+            launches += 2;
         }
     }
     if (overlap) {
-        cudaStreamWaitEvent(s, side->adam[0], 0);
+        if (k >= 1) cudaStreamWaitEvent(s, side->adam[0], 0);
         if (k >= 2) cudaStreamWaitEvent(s, side->adam[1], 0);
     }
-    g_last_launches = 1 + 2 * k;
+    if (coarse_on_side) cudaStreamWaitEvent(s, side->join, 0);
+    g_last_launches = launches;
     if (prof) {
-        if (overlap && n_ev < kMaxEv) {                   // closing event on the caller's stream (after the joins)
-            if (n_ev >= n_ev_created) { cudaEventCreate(&ev[n_ev]); n_ev_created = n_ev + 1; }
-            cudaEventRecord(ev[n_ev], s);
-            cls[n_ev++] = 3;
-        }
+        if (concurrent) mark(3, true);                     // closing event on the caller's stream (after the joins)
         cudaStreamSynchronize(s);
         for (int i = 0; i < 4; ++i) g_profile_ms[i] = 0.f;
         for (int i = 1; i < n_ev; ++i) {
@@ -859,7 +914,7 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
             cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
             g_profile_ms[cls[i]] += ms;
         }
-        if (!overlap) g_profile_ms[3] = g_profile_ms[1] + g_profile_ms[2];
+        if (!concurrent) g_profile_ms[3] = g_profile_ms[1] + g_profile_ms[2];
     }
     SNRF_RETURN_LAUNCH("snrf_field_encode_bwd_adam");
 }

@@ -97,6 +97,25 @@ def decoder_apply(feats, rays_d, mask32, S, params, valid=None):
     return DecoderFn.apply(feats, rays_d, mask32, S, valid, *params)
 
 
+_small_levels_cache = {}
+
+
+def small_levels(resolution):
+    """Number of leading levels whose grid has at most 2^22 vertices ((rx+1)(ry+1)(rz+1)): however large the hash table,
+    such a level touches few entries, and the fused backward reduces it in one pass (snrf_field_encode_bwd_adam).
+    Read back from the device once per resolution tensor."""
+    key = (resolution.data_ptr(), tuple(resolution.shape))
+    n = _small_levels_cache.get(key)
+    if n is None:
+        r = resolution.detach().cpu().long() + 1
+        verts = r[:, 0] * r[:, 1] * r[:, 2]
+        n = 0
+        while n < verts.shape[0] and int(verts[n]) <= (1 << 22):
+            n += 1
+        _small_levels_cache[key] = n
+    return n
+
+
 class FieldEncodeFn(torch.autograd.Function):
     """(rays_o [R,3], rays_d [R,3], z_vals [R,S], features [16,T,2], resolution, box_min, box_size, mode)
     -> level-major features [16, R*S, 2]: sample position, space contraction (mode 1 = fore, 2 =
@@ -124,6 +143,7 @@ class FieldEncodeFn(torch.autograd.Function):
                                               c_int(L), c_int(T), capi.stream())
         capi.check(rc, "snrf_field_encode_fwd")
         ctx.mode, ctx.split, ctx.dims = int(mode), int(split), (N, S, L, T)
+        ctx.small_levels = small_levels(resolution)
         ctx.features = features
         ctx.save_for_backward(rays_o, rays_d, z_vals, resolution, box_min, box_size, jac if jac is not None else out.new_empty(0),
                               valid if valid is not None else out.new_empty(0))
@@ -145,11 +165,11 @@ class FieldEncodeFn(torch.autograd.Function):
         if mode == "fused" and _gradmode.optimizer().owns(features):
             # scatter + sparse Adam in one pass: the table gradient never exists in HBM
             opt = _gradmode.optimizer()
-            m, v, hyper, step, scratch = opt.begin_fused(features)
+            m, v, hyper, step, scratch = opt.begin_fused(features, ctx.small_levels)
             cpts = torch.empty(3, N, dtype=f32, device=g_out.device)
             rc = capi.lib().snrf_field_encode_bwd_adam(*common, ptr(features.data), ptr(m), ptr(v), c_float(hyper["lr"]), c_float(hyper["beta1"]),
                                                        c_float(hyper["beta2"]), c_float(hyper["eps"]), c_int(step), ptr(scratch),
-                                                       ctypes.c_longlong(scratch.shape[0]), ptr(cpts), *tail)
+                                                       ctypes.c_longlong(scratch.shape[0]), c_int(ctx.small_levels), ptr(cpts), *tail)
             capi.check(rc, "snrf_field_encode_bwd_adam")
             capi.launch_count += int(capi.lib().snrf_field_last_launch_count()) - 1     # one C call, many kernels
             return g_o, g_d, None, None, None, None, None, None, None, None

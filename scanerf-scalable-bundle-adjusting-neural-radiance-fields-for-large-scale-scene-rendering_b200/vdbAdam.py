@@ -32,7 +32,7 @@ class vdbAdam:
         self._stepped = False
         self._applied = set()        # id(p) of parameters already updated inside this step's backward (fused mode)
         self._scratch = None
-        # gradient scratch of the in-backward update: 2^23 entries = 64 MiB (two 32 MiB halves in flight, L2-resident)
+        # gradient scratch of the in-backward update: one slice of 2^23 entries = 64 MiB stays L2-resident
         self.scratch_log2 = 23
         self._grad_versions = {}
         self.t = 0
@@ -100,8 +100,10 @@ class vdbAdam:
     def owns(self, p):
         return any(q is p for q, _, _ in self.params)
 
-    def begin_fused(self, p):
-        """-> (exp_avg, exp_avg_sq, hyper-parameters, step number, zeroed scratch) for the in-backward update of p."""
+    def begin_fused(self, p, small_levels=0):
+        """-> (exp_avg, exp_avg_sq, hyper-parameters, step number, zeroed scratch) for the in-backward update of p.
+        Scratch: one L2-resident slice (2^scratch_log2 entries); a table whose levels are larger than that gets one more
+        level's worth in front of it when it has `small_levels` sparse coarse levels to reduce in one pass each."""
         if id(p) in self._applied:
             raise RuntimeError("vdbAdam: the table was encoded more than once in this backward; the in-backward update "
                                "needs exactly one encode per step (use table_backward(fused=False))")
@@ -110,6 +112,9 @@ class vdbAdam:
         n = 4
         while n < min(p.numel() // 2, 1 << self.scratch_log2):
             n *= 2
+        T = int(p.shape[1]) if p.dim() == 3 else 0
+        if small_levels > 0 and T > n:
+            n += T
         if self._scratch is None or self._scratch.device != p.device or self._scratch.shape[0] != n:
             self._scratch = torch.zeros(n, 2, dtype=torch.float32, device=p.device)   # stays all-zero between calls
         step = self.t + 1 if self.bias_correction == "standard" else max(self.t, 1)

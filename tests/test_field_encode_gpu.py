@@ -113,12 +113,14 @@ def test_run_merging_scatter_equals_cross_lane_scatter(run, S):
     assert float(out[1][0].abs().max()) > 0 and float(out[1][1].abs().max()) > 0
 
 
-@pytest.mark.parametrize("mode,S,log2T,bits,lpg", [(1, 32, 14, -1, 0), (3, 7, 12, 2, 0), (2, 16, 10, -1, 3), (3, 33, 16, 1, 0)])
-def test_scatter_update_fusion_equals_scatter_then_adam(mode, S, log2T, bits, lpg):
+@pytest.mark.parametrize("mode,S,log2T,bits,lpg,slice_log2", [(1, 32, 14, -1, 0, 23), (3, 7, 12, 2, 0, 23), (2, 16, 10, -1, 3, 23),
+                                                              (3, 33, 16, 1, 0, 23), (3, 32, 14, -1, 0, 12), (1, 9, 15, -1, 0, 13)])
+def test_scatter_update_fusion_equals_scatter_then_adam(mode, S, log2T, bits, lpg, slice_log2):
     """snrf_field_encode_bwd_adam (gradient slices scattered into the L2-resident scratch and consumed by the sparse Adam
     on the spot) against snrf_field_encode_bwd into a gradient table followed by snrf_adam_step, over two steps (the second
     with non-trivial moments): same parameters, moments, ray gradients; untouched entries bit-identical; the scratch is
-    left all-zero; index ranges (bits) and ragged level groups (lpg) included."""
+    left all-zero; index ranges (bits), ragged level groups (lpg) and -- with a slice smaller than a level (slice_log2) --
+    the single-pass coarse levels on the side stream next to the range-partitioned fine levels included."""
     load_pkg()
     import scanerf_b200_capi as capi
     from hashgrid import _field, _gradmode
@@ -135,6 +137,8 @@ def test_scatter_update_fusion_equals_scatter_then_adam(mode, S, log2T, bits, lp
         opt = vdbAdam([t], lr=1e-2, betas=(0.9, 0.99), eps=1e-15, bias_correction="standard", fused_zero_grad=True)
         capi.lib().snrf_field_set_passes_log2(capi.c_int(bits if fused else -1))
         capi.lib().snrf_field_set_levels_per_group(capi.c_int(lpg if fused else 0))
+        capi.lib().snrf_field_set_slice_log2(capi.c_int(slice_log2))
+        opt.scratch_log2 = slice_log2
         grads = []
         for cot in cots:
             oo, dd = o.to(DEV).clone().requires_grad_(True), d.to(DEV).clone().requires_grad_(True)
@@ -146,7 +150,10 @@ def test_scatter_update_fusion_equals_scatter_then_adam(mode, S, log2T, bits, lp
             grads.append((oo.grad.clone(), dd.grad.clone()))
         capi.lib().snrf_field_set_passes_log2(capi.c_int(-1))
         capi.lib().snrf_field_set_levels_per_group(capi.c_int(0))
+        capi.lib().snrf_field_set_slice_log2(capi.c_int(23))
         if fused:
+            if slice_log2 < log2T:
+                assert opt._scratch.shape[0] == 2 ** log2T + 2 ** slice_log2, "coarse single-pass region + one fine slice"
             assert t.grad is None, "the fused path must not materialise a gradient table"
             assert float(opt._scratch.abs().max()) == 0.0, "scratch must be left all-zero"
         results.append((t.detach().clone(), opt.params[0][1].clone(), opt.params[0][2].clone(), grads, opt.t))

@@ -1,0 +1,60 @@
+"""GPU: the reference's OWN drivers, unmodified, on top of the drop-in (VERDICT r1 "missing" #1).
+
+tests/ref_driver_harness.py imports the reference's tile.py / camera*.py / network.py / criterions.py / warp_loss.py byte for
+byte from oracle/_ref/ref_drivers.zip (a build artefact: /root/reference does not exist on the GPU box), writes a synthetic
+scene in the reference's on-disk layout (camera.log, images/, mesh/mesh.ply, tiles/*.txt, scene yaml), builds a TILE the way
+admm_trainer.py does and calls TILE.train_one_step (tile.py:880-1015) 20 times -- once with `hashgrid` / `cuda` / `fastMesh`
+resolving to this repo's packages, once with them resolving to the reference's own wrappers over its CUDA extensions
+rebuilt into oracle/_ref/*.so.  Same initial table / decoder, same RNG seeds: the loss curves must agree."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+HARNESS = os.path.join(ROOT, "tests", "ref_driver_harness.py")
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _run(arm, out, steps, extra, tmp):
+    cmd = [sys.executable, HARNESS, "--arm", arm, "--steps", str(steps), "--out", out] + extra
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(tmp))
+    assert r.returncode == 0, f"{arm} arm failed:\n{r.stdout[-3000:]}\n{r.stderr[-6000:]}"
+    return json.load(open(out))
+
+
+def _need(*names):
+    for n in names:
+        if not os.path.exists(os.path.join(REFDIR, n)):
+            pytest.skip(f"oracle/_ref/{n} not built (python oracle/build_ref.py drivers hashgrid cuda fastmesh)")
+
+
+@pytest.mark.parametrize("warp", [False, True])
+def test_reference_tile_trains_on_the_dropin_like_on_the_reference_extensions(tmp_path, warp):
+    _need("ref_drivers.zip", "HASHGRID.so", "CUDA_EXT.so", "fastMesh.so")
+    steps = 20
+    extra = ["--warp"] if warp else []
+    init = str(tmp_path / "init.pt")
+    ref = _run("reference", str(tmp_path / "ref.json"), steps, extra + ["--init-out", init], tmp_path)
+    ours = _run("dropin", str(tmp_path / "ours.json"), steps, extra + ["--init-in", init], tmp_path)
+    # the drivers are the reference's in both arms; the extension packages differ
+    assert ref["modules"]["tile"].endswith("ref_drivers.zip/tile.py") and ours["modules"]["tile"] == ref["modules"]["tile"]
+    assert "ref_drivers.zip" in ref["modules"]["hashgrid"] and "_b200" in ours["modules"]["hashgrid"]
+    la, lb = ours["losses"], ref["losses"]
+    print(f"warp={warp}: drop-in {ours['ms_per_step']:.2f} ms/step, reference extensions {ref['ms_per_step']:.2f} ms/step")
+    print("drop-in  :", " ".join(f"{v:.5f}" for v in la))
+    print("reference:", " ".join(f"{v:.5f}" for v in lb))
+    assert len(la) == len(lb) == steps and ours["global_step"] == ref["global_step"] == steps + 1
+    assert ours["table_changed"] and ours["pose_grad_finite"]
+    # first step: same parameters, same rays -> same maths up to kernel rounding
+    assert abs(la[0] - lb[0]) <= 2e-4 * abs(lb[0]), (la[0], lb[0])
+    # the curve: both learn, and stay together (different summation orders / 16-bit tensor-core operands drift apart slowly)
+    assert lb[-1] < lb[0] and la[-1] < la[0]
+    worst = max(abs(a - b) / abs(b) for a, b in zip(la, lb))
+    assert worst < 2e-2, worst
+    with open(os.path.join(ROOT, "gpurun_out", f"ref_drivers_{'warp' if warp else 'rgb'}.json") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else str(tmp_path / "summary.json"), "w") as fh:
+        json.dump({"warp": warp, "dropin": ours, "reference": ref, "worst_rel_loss_diff": worst}, fh)

