@@ -42,6 +42,8 @@ WORKLOADS = {
                      grid_resolution=(16, 512), n_cam=16, H=270, W=480, fx=300.0,
                      batch_log2=12, S=64, S_bg=64, sampler_log2dim=4),
 }
+# BASELINE.json configs[4] shape (8-GPU run: 64 tiles x 2^22-entry tables, 8 resident tiles per rank)
+WORKLOADS["city-64-tiles"] = dict(WORKLOADS["default.yaml-single-tile"], log2T=22, tiles_total=64, n_cam=32, shared_cams=8)
 ENC_FWD_BYTES, ENC_BWD_BYTES = 1164, 2200      # algorithmic bytes per sample point, SURVEY.md section 8(d)
 
 
@@ -82,6 +84,49 @@ def build_tile(cfg, dev, seed):
                     mesh_path=ply, sampler_log2dim=cfg["sampler_log2dim"], global_step=10000)
     return step, gen
 
+
+
+def build_tile_row(cfg, dev, n_tiles, mine, overlap=0.2):
+    """BASELINE configs[3] shape (config/community.yaml:5-12: TILE_SIZE [20,13,30], OVERLAP_RATIO 0.2): `n_tiles` tiles in a
+    row along x, neighbours overlapping by 20 %.  Every tile has its own ring of cfg['n_cam'] cameras; the `shared` ring
+    cameras of tile t nearest to tile t+1 are ALSO training views of tile t+1, where they replace that tile's `shared`
+    cameras nearest to tile t -- so only the boundary cameras are seen by two tiles (the overlap set of the ADMM consensus).
+    Builds the tiles listed in `mine`; returns ([TileStep], [generator], global camera count)."""
+    import torch
+    import scenes
+    from tile_step import TileStep
+    n_cam, shared = cfg["n_cam"], cfg.get("shared_cams", 16)
+    size = cfg["tile_size"]
+    rigs = []
+    for t in range(n_tiles):                      # every rank derives the same global rig
+        gen = torch.Generator().manual_seed(1000 + t)
+        corner = (cfg["tile_corner"][0] + t * (1.0 - overlap) * size[0], cfg["tile_corner"][1], cfg["tile_corner"][2])
+        c = [corner[i] + size[i] * f for i, f in enumerate((0.5, 0.25, 0.5))]
+        Ks, c2w = scenes.camera_rig(n_cam, cfg["H"], cfg["W"], gen, center=tuple(c), radius=0.3 * min(size[0], size[2]), fx=cfg["fx"])
+        order = torch.argsort(c2w[:, 0, 3])        # by camera x position
+        rigs.append(dict(corner=corner, Ks=Ks, c2w=c2w, low=order[:shared], high=order[-shared:], ids=torch.arange(n_cam) + t * n_cam))
+    steps, gens = [], []
+    for t in mine:
+        r = rigs[t]
+        keep = torch.ones(n_cam, dtype=torch.bool)
+        Ks, c2w, ids = r["Ks"], r["c2w"], r["ids"]
+        if t > 0:                                  # swap my cameras nearest to the left neighbour for its cameras nearest to me
+            keep[r["low"]] = False
+            left = rigs[t - 1]
+            Ks = torch.cat([Ks[keep], left["Ks"][left["high"]]])
+            c2w = torch.cat([c2w[keep], left["c2w"][left["high"]]])
+            ids = torch.cat([ids[keep], left["ids"][left["high"]]])
+        tmp = tempfile.mkdtemp(prefix="snrf_bench_")
+        ply = os.path.join(tmp, "mesh.ply")
+        scenes.write_proxy_mesh_ply(ply, r["corner"], size, seed=t)
+        torch.manual_seed(t)
+        st = TileStep(dev, r["corner"], size, Ks, c2w, log2_hashmap_size=cfg["log2T"], grid_resolution=cfg["grid_resolution"],
+                      num_sample=cfg["S"], num_bg_sample=cfg["S_bg"], mesh_path=ply, sampler_log2dim=cfg["sampler_log2dim"],
+                      global_step=10000)
+        st.enable_consensus(ids.tolist(), n_tiles * n_cam, rho=100.0)
+        steps.append(st)
+        gens.append(torch.Generator().manual_seed(2000 + t))
+    return steps, gens, n_tiles * n_cam
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
@@ -356,31 +401,52 @@ def main():
     pkg.install()
     import scanerf_b200_capi as capi
 
-    # one tile per GPU (the reference's own decomposition: admm_trainer.py:74-83); no data-path collective
-    step, gen = build_tile(cfg, dev, seed=rank)
     K, Wm = args.steps, args.warmup
-    SYN_ITERS = 100                       # config/default.yaml:5
-    if world > 1:
-        # the tiles of all ranks see the same cfg["n_cam"] cameras: every camera is an overlap camera, the ADMM
-        # penalty is active and the pose consensus is one NCCL all-reduce of [n_cam, 8] floats every SYN_ITERS steps
-        step.enable_consensus(list(range(cfg["n_cam"])), cfg["n_cam"], rho=100.0)
-        step.synchronize()                # first synchronisation before training (admm_trainer.py:218-231)
+    if world == 1:
+        # BASELINE configs[1]: one tile, no exchange
+        step, gen = build_tile(cfg, dev, seed=rank)
+        steps, gens, n_cam_global, tiles_total = [step], [gen], cfg["n_cam"], 1
+        SYN = 0
+    else:
+        # BASELINE configs[3] / [4]: a row of tiles with 20 % overlap sharded round-robin over the ranks
+        # (admm_trainer.py:74-83), several resident tiles per rank trained in turn (:241-250), only the boundary cameras
+        # shared between neighbouring tiles, ADMM pose consensus = one NCCL all-reduce for all resident tiles
+        tiles_total = world * cfg.get("tiles_per_rank", 2) if "tiles_total" not in cfg else cfg["tiles_total"]
+        mine = list(range(rank, tiles_total, world))
+        steps, gens, n_cam_global = build_tile_row(cfg, dev, tiles_total, mine)
+        step, gen = steps[0], gens[0]
+        # config/default.yaml:5 has SYN_ITERS 100 over 40 000 steps; the driver times 20 steps, so the bench exchanges every
+        # 10 (two exchanges inside the timed region) and reports the share of the step time they take
+        SYN = cfg.get("syn_iters_bench", 10)
+        from admm import PoseConsensus, synchronize_tiles
+        exchange = PoseConsensus(n_cam_global, dev)
+        synchronize_tiles(exchange, steps)        # first synchronisation before training (admm_trainer.py:218-231)
     counter = {"i": 0}
+    sync_events = []
 
-    def run_device(locs, gt):
-        if world > 1 and counter["i"] % SYN_ITERS == 0:
-            step.synchronize()
+    def maybe_sync():
+        if SYN and counter["i"] % SYN == 0:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            synchronize_tiles(exchange, steps)
+            e1.record()
+            sync_events.append((e0, e1))
         counter["i"] += 1
-        return step.step_device(locs, gt)
 
-    def run_e2e(locs, gt):
-        if world > 1 and counter["i"] % SYN_ITERS == 0:
-            step.synchronize()
-        counter["i"] += 1
-        return step.step(locs, gt)
-    host = [(l.pin_memory(), g.pin_memory()) for l, g in make_batches(cfg, Wm + K, gen)]
-    devb = [(l.to(dev), g.to(dev)) for l, g in host]
-    B = host[0][0].shape[0]
+    def run_device(batch):
+        maybe_sync()
+        return [st.step_device(*b) for st, b in zip(steps, batch)]
+
+    def run_e2e(batch):
+        maybe_sync()
+        return [st.step(*b) for st, b in zip(steps, batch)]
+    per_tile = [make_batches(cfg, Wm + K, g) for g in gens]
+    host = [[(l.pin_memory(), g.pin_memory()) for l, g in pt] for pt in per_tile]
+    host = [[h[i] for h in host] for i in range(Wm + K)]                      # [step][tile]
+    devb_all = [[(l.to(dev), g.to(dev)) for l, g in batch] for batch in host]
+    devb = [batch[0] for batch in devb_all]                                    # the first resident tile's batches
+    B = host[0][0][0].shape[0]
+    T_res = len(steps)
 
     def barrier():
         if world > 1:
@@ -389,35 +455,38 @@ def main():
 
     def timed(fn, batches):
         for b in batches[:Wm]:
-            fn(*b)
+            fn(b)
         counter["i"] = 0                  # the timed region starts with a consensus exchange (world > 1)
+        sync_events.clear()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         e0.record()
         for b in batches[Wm:]:
-            fn(*b)
+            fn(b)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        sync_ms = sum(a.elapsed_time(b_) for a, b_ in sync_events)
         if world > 1:
-            t = torch.tensor([ms], device=dev)
+            t = torch.tensor([ms, sync_ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, t0, time.time()
+            ms, sync_ms = float(t[0].item()), float(t[1].item())
+        return ms, t0, time.time(), sync_ms, len(sync_events)
 
     # setup, before any measurement: a few steps on throw-away batches so that CUDA context, kernel attributes and the
-    # caching allocator's per-stream pools reach steady state (the step runs its two render chains on two streams)
-    for l, g in make_batches(cfg, 8, gen):
-        step.step_device(l.to(dev), g.to(dev))
+    # caching allocator reach steady state
+    for st, g in zip(steps, gens):
+        for l, t in make_batches(cfg, 6, g):
+            st.step_device(l.to(dev), t.to(dev))
     torch.cuda.synchronize()
     clocks = ClockSampler(local) if rank == 0 else None
     # (1) device-resident inputs
     capi.launch_count = 0
-    ms_dev, t0, t1 = timed(run_device, devb)
+    ms_dev, t0, t1, sync_ms, n_sync = timed(run_device, devb_all)
     launches = capi.launch_count
     # (2) end to end: pinned host in, loss float out
-    ms_e2e, _, t2 = timed(run_e2e, host)
+    ms_e2e, _, t2, _, _ = timed(run_e2e, host)
     clk = clocks.summary(t0, t2) if clocks else None
     # (3) the dominant kernels, timed live on their stream over the same steps: the encode forward through CUDA events
     #     around its C-ABI call; the encode backward -- now a sequence of launches (geometry + ray gradient, then per
@@ -470,7 +539,7 @@ def main():
              "frac": ach / peak, "traffic": t.get("bytes") if isinstance(t, dict) else t,
              "traffic_source": (t.get("source") if isinstance(t, dict) else None),
              "avg_launch_ms": avg, "launches_timed": len(ms_list), "alg_bytes_per_launch": alg_bytes,
-             "share_of_step": avg / (ms_dev / K) if ms_list else None}
+             "share_of_step": avg / (ms_dev / K / T_res) if ms_list else None}
         if extra:
             r.update(extra)
         return r
@@ -512,17 +581,21 @@ def main():
         roofline_update = roofline_both = None
     roofline_fwd = roof("field_fwd_kernel (snrf_field_encode_fwd: position + contraction + 16-level encode + Jacobian store)",
                         fwd_ms, ENC_FWD_BYTES * N_pts, "encode_fwd")
+    rays_per_step = world * T_res * B                   # one step = one training step of every resident tile of every rank
     line = {
-        "metric": "train rays/s (fwd+bwd)", "value": world * K * B / (ms_dev * 1e-3), "unit": "rays/s", "n_gpus": world,
+        "metric": "train rays/s (fwd+bwd)", "value": K * rays_per_step / (ms_dev * 1e-3), "unit": "rays/s", "n_gpus": world,
         "steps": K, "warmup": Wm, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "tiles_per_gpu": 1, "rays_per_step": B, "samples_per_ray": cfg["S"] + cfg["S_bg"],
-                   "hash_table": f"16 x 2^{cfg['log2T']} x 2 f32", "cameras": cfg["n_cam"], "pose_refinement": True,
+        "config": {"workload": name if world == 1 else (name + ": row of %d tiles with 20 %% overlap, %d boundary cameras shared per neighbour pair" % (tiles_total, cfg.get("shared_cams", 16))),
+                   "tiles_per_gpu": T_res, "tiles_total": tiles_total, "rays_per_step": rays_per_step, "rays_per_tile_step": B,
+                   "samples_per_ray": cfg["S"] + cfg["S_bg"],
+                   "hash_table": f"16 x 2^{cfg['log2T']} x 2 f32 per tile", "cameras_per_tile": cfg["n_cam"], "cameras_global": n_cam_global,
+                   "pose_refinement": True,
                    "table_update": "scatter + sparse Adam fused per L2-resident slice" if fused else "gradient table + sparse Adam",
-                   "parallelism": f"tile-parallel x{world}" + (", NCCL pose consensus every 100 steps (1 exchange in the timed region)" if world > 1 else ""),
-                   "l2_policy": "inputs larger than L2 (2 GiB table + 4 GiB Adam moments, random gathers)"},
-        "e2e": {"value": world * K * B / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": B * 3 * 4 * 2,
-                "d2h_bytes_per_step": 4},
+                   "parallelism": f"tile-parallel x{world}" + (f", {T_res} resident tiles per rank trained in turn, NCCL pose consensus (one all-reduce of [{n_cam_global}, 8] f32 for all resident tiles) every {SYN} steps" if world > 1 else ""),
+                   "l2_policy": "inputs larger than L2 (2 GiB table + 4 GiB Adam moments per tile, random gathers)"},
+        "e2e": {"value": K * rays_per_step / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": T_res * B * 3 * 4 * 2,
+                "d2h_bytes_per_step": 4 * T_res},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": roofline,
@@ -531,6 +604,12 @@ def main():
     if roofline_update is not None:
         line["roofline_update"] = roofline_update
         line["roofline_bwd_and_update"] = roofline_both
+    if world > 1:
+        line["consensus"] = {"exchanges_in_timed_region": n_sync, "ms_total": sync_ms, "consensus_ms_share": sync_ms / ms_dev,
+                             "every_steps": SYN, "payload_bytes": n_cam_global * 8 * 4,
+                             "share_at_reference_SYN_ITERS_100": (sync_ms / max(n_sync, 1)) / (100 * ms_dev / K),
+                             "what": "commit + consensus + synchronize of every resident tile (tile.py:477-508, admm_trainer.py:124-179) "
+                                     "as one NCCL all-reduce + the per-tile dual update, CUDA-event timed, max over ranks"}
     if world == 1 and not args.no_render:
         line["render"] = bench_render(step, cfg, dev)
     if world == 1 and not args.no_variants:

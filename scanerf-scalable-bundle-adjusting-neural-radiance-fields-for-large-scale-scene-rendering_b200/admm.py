@@ -112,3 +112,13 @@ class ConsensusManager:
 
     def __call__(self):
         return self.camera_loss() if self.has_overlap else None
+
+
+def synchronize_tiles(exchange, steps):
+    """TILE.commit + the master's consensus + TILE.synchronize (tile.py:477-508, admm_trainer.py:124-179, 241-262) for ALL
+    tiles resident on this rank at once: one all-reduce, then every tile's dual update.  `steps`: TileStep objects with
+    enable_consensus() done."""
+    outs = exchange.exchange([(st.poses.se3_refine, st.camera_ids, st.confidence) for st in steps])
+    for st, o in zip(steps, outs):
+        st.consensus.update(o["shared_poses"], o["overlap_idxs"])
+    return outs

@@ -180,6 +180,11 @@ def main():
     t = ref_tile.TILE(cfg, 0, 0, [], [], fmesh, device, False)
     t.build_training_context()
     t.set(None)
+    # tile.py:939-940 index the CPU-resident image / occlusion stacks with a CUDA index tensor, which torch 1.9 (the
+    # reference's pin, scanerf.yaml) accepted and torch >= 2 rejects ("indices should be either on cpu or on the same
+    # device"): keep the driver unmodified and place the two stacks on the device instead (same values)
+    t.train_data.images = t.train_data.images.to(device)
+    t.train_data.occlusions = t.train_data.occlusions.to(device)
     where = {"tile": ref_tile.__file__, "hashgrid": hashgrid.__file__, "FastMesh": sys.modules["fastMesh"].__file__}
 
     # ---- identical starting point in both arms
