@@ -114,6 +114,61 @@ class ConsensusManager:
         return self.camera_loss() if self.has_overlap else None
 
 
+class DepthExchange:
+    """The `shared_depth` exchange (tile.py:432-475 render_shared_depth, :366-430 update_occlusion_mask,
+    admm_trainer.py:31-32, 117-118).  In the reference every tile renders a half-resolution depth map for each of its
+    overlap cameras whose centre lies inside the tile and stores it in a Manager().list indexed by the global camera id;
+    afterwards every tile reads the maps of ITS cameras to rebuild its occlusion masks.  Here the tiles live on different
+    ranks: one padded all_gather of (camera id, writer tile, map) over NCCL.  Where two tiles wrote the same camera the
+    reference keeps whichever process stored last; here the higher tile index wins (deterministic)."""
+
+    def __init__(self, h, w, device, group=None):
+        self.h, self.w = int(h), int(w)
+        self.device = torch.device(device)
+        self.group = group
+
+    @torch.no_grad()
+    def exchange(self, entries, want_ids):
+        """entries: list of (tile index, global camera ids int64 [k], depth maps [k, h, w] f32) written by the tiles THIS
+        rank owns (k may be 0); want_ids: int64 [m] global camera ids this rank wants back.
+        Returns (have bool [m], maps f32 [m, h, w]): the map of every wanted camera somebody rendered."""
+        dev = self.device
+        ids = [e[1].to(dev).long() for e in entries] or [torch.zeros(0, dtype=torch.long, device=dev)]
+        pri = [torch.full_like(e[1].to(dev).long(), int(e[0])) for e in entries] or [torch.zeros(0, dtype=torch.long, device=dev)]
+        maps = [e[2].to(dev, torch.float32).reshape(-1, self.h, self.w) for e in entries] or [torch.zeros(0, self.h, self.w, device=dev)]
+        ids, pri, maps = torch.cat(ids), torch.cat(pri), torch.cat(maps)
+        world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+        if world > 1:
+            n = torch.tensor([ids.shape[0]], dtype=torch.long, device=dev)
+            counts = [torch.zeros_like(n) for _ in range(world)]
+            dist.all_gather(counts, n, group=self.group)
+            counts = [int(c.item()) for c in counts]
+            cap = max(max(counts), 1)
+            pad = cap - ids.shape[0]
+            meta = torch.cat([torch.stack([ids, pri], -1), torch.full((pad, 2), -1, dtype=torch.long, device=dev)])
+            body = torch.cat([maps, torch.zeros(pad, self.h, self.w, device=dev)])
+            metas = [torch.empty_like(meta) for _ in range(world)]
+            bodies = [torch.empty_like(body) for _ in range(world)]
+            dist.all_gather(metas, meta, group=self.group)
+            dist.all_gather(bodies, body, group=self.group)
+            ids = torch.cat([m[:c, 0] for m, c in zip(metas, counts)])
+            pri = torch.cat([m[:c, 1] for m, c in zip(metas, counts)])
+            maps = torch.cat([b[:c] for b, c in zip(bodies, counts)])
+        want = want_ids.to(dev).long()
+        have = torch.zeros(want.shape[0], dtype=torch.bool, device=dev)
+        out = torch.zeros(want.shape[0], self.h, self.w, dtype=torch.float32, device=dev)
+        if ids.numel() == 0 or want.numel() == 0:
+            return have, out
+        # for every wanted camera: the entry with the highest writer tile
+        order = torch.argsort(pri, stable=True)                     # ascending: later (higher-tile) entries overwrite
+        ids, maps = ids[order], maps[order]
+        hit = ids[None, :] == want[:, None]                         # [m, n]
+        have = hit.any(1)
+        last = (hit.long() * torch.arange(1, ids.shape[0] + 1, device=dev)[None, :]).max(1)[0] - 1
+        out[have] = maps[last[have]]
+        return have, out
+
+
 def synchronize_tiles(exchange, steps):
     """TILE.commit + the master's consensus + TILE.synchronize (tile.py:477-508, admm_trainer.py:124-179, 241-262) for ALL
     tiles resident on this rank at once: one all-reduce, then every tile's dual update.  `steps`: TileStep objects with

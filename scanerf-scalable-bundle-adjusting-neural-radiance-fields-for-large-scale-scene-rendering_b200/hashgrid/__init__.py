@@ -377,7 +377,9 @@ class HashGrid(nn.Module):
             # zeros / T_left = 1 -- instead of (None, False); deciding that on the host would cost a sync
             out = self.render_rays_masked(rays_o, rays_d, z_vals, dists, valid, params, mode, 1, infinity, kwargs["global_step"])
             res = dict(out)
-            res.update({"pred_color": out["rgb"], "pred_depth": out["depth"], "T_left": out["T_left"][:, None],
+            # pred_depth is its own tensor (not a view of the packed output row): TILE.render_rays accumulates the background
+            # into it IN PLACE (tile.py:673), and a view would invalidate the row's other columns for autograd
+            res.update({"pred_color": out["rgb"], "pred_depth": out["depth"].clone(), "T_left": out["T_left"][:, None],
                         "specular": out["specular"], "diffuse": out["diffuse"], "fore_valid": valid})
             return res, True
         out, ok = self.render_batch_rays(rays_o[valid], rays_d[valid], z_vals[valid], dists[valid], decoder, mode,

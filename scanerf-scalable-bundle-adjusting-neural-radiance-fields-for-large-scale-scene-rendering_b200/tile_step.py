@@ -194,7 +194,7 @@ class TileStep:
     def enable_warp_loss(self, images, alpha, gamma, weight=1.0, start_step=0, occlusions=None, topK=10):
         """criterions.py:92-97: adds the multi-view warp loss (warp_loss.WarpLoss) to the step.  images [N,H,W,3] uint8
         (or float in [0,1]) become device-resident; occlusions [N,H,W,1] bool or None."""
-        from warp_loss import WarpLoss
+        from warp_loss_fused import WarpLoss
         self.warp = WarpLoss(self, images, alpha, gamma, topK=topK)
         self.warp_weight, self.warp_start = float(weight), int(start_step)
         self.warp_occlusions = occlusions.to(self.device).contiguous() if occlusions is not None else None
@@ -203,6 +203,61 @@ class TileStep:
         """TILE.commit + master consensus + TILE.synchronize as one collective (every SYN_ITERS steps)."""
         out = self.exchange.exchange([(self.poses.se3_refine, self.camera_ids, self.confidence)])[0]
         self.consensus.update(out["shared_poses"], out["overlap_idxs"])
+
+    # ---- shared depth / occlusion masks (tile.py:432-475, 366-430)
+    def full_image_rays(self, view, H, W, stride=1):
+        """All pixel rays of one camera (CAM.getRays(H, W, view_idx=[i]), camera_utils.py:91-141), every `stride`-th pixel."""
+        ys, xs = torch.meshgrid(torch.arange(0, H, stride, device=self.device), torch.arange(0, W, stride, device=self.device), indexing="ij")
+        locs = torch.stack([torch.full_like(xs, int(view)), xs, ys], -1).reshape(-1, 3).int().contiguous()
+        with torch.no_grad():
+            return self.poses.rays(locs)
+
+    @torch.no_grad()
+    def render_shared_depth(self, H, W, batch=1 << 16):
+        """TILE.render_shared_depth: for every overlap camera of this tile whose centre lies INSIDE the tile's (doubled) box,
+        the half-resolution depth map of the tile's current field.  -> (global camera ids [k], maps [k, H//2, W//2])."""
+        if self.consensus is None:
+            raise RuntimeError("render_shared_depth: enable_consensus() first (the overlap cameras come from the exchange)")
+        center, half = self.featureGrid.bbox_center, self.featureGrid.bbox_size / 2.0
+        ids, maps = [], []
+        for i in torch.nonzero(self.consensus.overlap_flags)[:, 0].tolist():
+            rays_o, rays_d = self.full_image_rays(i, H, W, stride=2)
+            if not bool(torch.all(torch.abs(rays_o[0] - center) < half / 2.0)):           # tile.py:445-448
+                continue
+            depth = torch.zeros(rays_o.shape[0], 1, device=self.device)
+            for b in range(0, rays_o.shape[0], batch):                                     # TILE.render_depth_rays, tile.py:714-722
+                out, ok = self.render_rays(rays_o[b:b + batch].contiguous(), rays_d[b:b + batch].contiguous(), None, INFERENCE)
+                if ok:
+                    depth[b:b + batch] = out["pred_depth"]
+            ids.append(int(self.camera_ids[i]))
+            maps.append(depth.reshape((H + 1) // 2, (W + 1) // 2))
+        if not ids:
+            return torch.zeros(0, dtype=torch.long, device=self.device), torch.zeros(0, (H + 1) // 2, (W + 1) // 2, device=self.device)
+        return torch.tensor(ids, dtype=torch.long, device=self.device), torch.stack(maps)
+
+    @torch.no_grad()
+    def update_occlusion_mask(self, have, maps, H, W, kernel_size=91):
+        """TILE.update_occlusion_mask: have [n_cam] bool, maps [n_cam, H//2, W//2] = the exchanged depth of this tile's cameras
+        (DepthExchange.exchange(..., want_ids=self.camera_ids)).  A pixel of a camera OUTSIDE the tile stays a training pixel
+        only where the shared depth lies behind the ray's entry into the tile box; the kept region is eroded by a
+        kernel_size box filter.  -> occlusions [n_cam, H, W, 1] bool (True = use the pixel)."""
+        n = self.poses.num_camera
+        occl = torch.ones(n, H, W, 1, dtype=torch.bool, device=self.device)
+        center, half = self.featureGrid.bbox_center, self.featureGrid.bbox_size / 2.0
+        kernel = torch.ones(1, 1, kernel_size, kernel_size, device=self.device)
+        from cuda import ray_aabb_intersection
+        for i in torch.nonzero(have)[:, 0].tolist():
+            rays_o, rays_d = self.full_image_rays(i, H, W)
+            if bool(torch.all(torch.abs(rays_o[0] - center) < half / 2.0)):               # camera inside the tile: nothing hides it
+                continue
+            depth = maps[i].repeat_interleave(2, 0).repeat_interleave(2, 1)[:H, :W].reshape(-1, 1)
+            bounds = torch.full((rays_o.shape[0], 2), -1.0, device=self.device)
+            ray_aabb_intersection(rays_o.contiguous(), rays_d.contiguous(), center, half, bounds)
+            vis = ((depth > bounds[:, :1]) & (bounds[:, :1] != -1)).reshape(1, 1, H, W).float()
+            vis = 1.0 - torch.nn.functional.conv2d(1.0 - vis, kernel, padding=kernel_size // 2).clamp(0, 1)
+            occl[i] = vis.bool().reshape(H, W, 1)
+        self.shared_occlusions = occl
+        return occl
 
     # tile.py:639-692
     def render_rays(self, rays_o, rays_d, occlusion_mask=None, mode=TRAIN):

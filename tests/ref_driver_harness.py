@@ -153,8 +153,10 @@ def main():
     ap.add_argument("--log2T", type=int, default=17)
     ap.add_argument("--bs-log2", type=int, default=11)
     ap.add_argument("--samples", type=int, default=32)
-    ap.add_argument("--cams", type=int, default=8)
+    ap.add_argument("--cams", type=int, default=16, help="more than the warp loss's topK = 10 neighbour views")
     args = ap.parse_args()
+    args.out = os.path.abspath(args.out)
+    args.init_in, args.init_out = (os.path.abspath(v) if v else "" for v in (args.init_in, args.init_out))
     setup_imports(args.arm)
     import numpy as np
     import torch

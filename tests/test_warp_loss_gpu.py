@@ -22,7 +22,7 @@ DEV = torch.device("cuda:0")
 
 def test_neighbor_sample_forward_backward():
     load_pkg()
-    from warp_loss import SampleNeighborColorFn
+    from warp_loss_fused import SampleNeighborColorFn
     g = torch.Generator().manual_seed(0)
     N, H, W, B, K = 5, 37, 53, 2000, 6
     images = torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8)
@@ -69,7 +69,7 @@ def test_warp_loss_matches_compaction_form():
     load_pkg()
     from hashgrid import INFERENCE
     from tile_step import pose_invert
-    from warp_loss import WarpLoss
+    from warp_loss_fused import WarpLoss
     step, locs, images, occl, H, W = _tile()
     with torch.no_grad():
         step.poses.se3_refine.add_(0.01 * torch.randn(step.poses.se3_refine.shape, device=DEV))
@@ -130,7 +130,7 @@ def test_warp_loss_matches_compaction_form():
 
 def test_warp_loss_without_valid_rays_is_zero():
     load_pkg()
-    from warp_loss import WarpLoss
+    from warp_loss_fused import WarpLoss
     step, locs, images, occl, H, W = _tile(n_cam=12)
     wl = WarpLoss(step, images, alpha=0.5, gamma=2.0, topK=4)
     with torch.no_grad():

@@ -30,7 +30,7 @@ def main():
     args = ap.parse_args()
     pkg = importlib.import_module(bench.PKG)
     pkg.install()
-    from warp_loss import SampleNeighborColorFn
+    from warp_loss_fused import SampleNeighborColorFn
     cfg = bench.WORKLOADS["default.yaml-single-tile"]
     dev = torch.device("cuda:0")
     step, gen = bench.build_tile(cfg, dev, 0)
