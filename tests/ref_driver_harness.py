@@ -142,6 +142,38 @@ def write_scene(root, n_cam, H, W, log2T, bs_log2, S, warp):
     return data, yml
 
 
+def render_frame(args, cfg, data):
+    """One frame of an exported tile through the reference's own renderer (rendering.py:28-44 sets it up from
+    DATADIR/demo/<name>/tile-*/, refined_camera.log and val_new.txt; RenderingHashGrid.render_rays_base renders)."""
+    import shutil
+    import numpy as np
+    import torch
+    import rendering
+    name = "harness"
+    demo = os.path.join(data, "demo", name)
+    os.makedirs(demo, exist_ok=True)
+    shutil.copytree(args.render_tile, os.path.join(demo, "tile-0"), dirs_exist_ok=True)
+    shutil.copy(os.path.join(data, "camera.log"), os.path.join(demo, "refined_camera.log"))
+    open(os.path.join(data, "val_new.txt"), "w").write("0\n3\n")
+    rendering.cfg = cfg                                       # rendering.py reads a module-global `cfg` its __main__ block sets
+    sr = rendering.RenderingHashGrid(cfg.DATADIR, name, 0, "val")
+    frames = []
+    t0 = time.perf_counter()
+    for i in range(sr.ks.shape[0]):
+        diffuse, specular, depth, transparency = sr.render_rays_base(sr.H, sr.W, sr.ks[i], sr.c2ws[i])
+        frames.append([x.detach().float().cpu().numpy() for x in (diffuse, specular, depth, transparency)])
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / len(frames) * 1e3
+    np.savez(args.render_out, diffuse=np.stack([f[0] for f in frames]), specular=np.stack([f[1] for f in frames]),
+             depth=np.stack([f[2] for f in frames]), transparency=np.stack([f[3] for f in frames]))
+    import hashgrid
+    out = {"arm": args.arm, "rendered": len(frames), "ms_per_frame": ms, "H": int(sr.H), "W": int(sr.W),
+           "modules": {"rendering": rendering.__file__, "hashgrid": hashgrid.__file__}}
+    with open(args.out, "w") as fh:
+        json.dump(out, fh)
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--arm", required=True, choices=["dropin", "reference"])
@@ -154,9 +186,14 @@ def main():
     ap.add_argument("--bs-log2", type=int, default=11)
     ap.add_argument("--samples", type=int, default=32)
     ap.add_argument("--cams", type=int, default=16, help="more than the warp loss's topK = 10 neighbour views")
+    ap.add_argument("--export-tile", default="", help="after training: TILE.export_tile() (tile.py:510-532), copied to this directory")
+    ap.add_argument("--render-tile", default="", help="do not train: render one frame of this exported tile directory through the "
+                                                      "reference's rendering.py (RenderingHashGrid.render_rays_base, rendering.py:286-544)")
+    ap.add_argument("--render-out", default="", help="npz of the rendered frame (with --render-tile)")
     args = ap.parse_args()
     args.out = os.path.abspath(args.out)
     args.init_in, args.init_out = (os.path.abspath(v) if v else "" for v in (args.init_in, args.init_out))
+    args.export_tile, args.render_tile, args.render_out = (os.path.abspath(v) if v else "" for v in (args.export_tile, args.render_tile, args.render_out))
     setup_imports(args.arm)
     import numpy as np
     import torch
@@ -165,8 +202,10 @@ def main():
     os.chdir(root)
     data, yml = write_scene(root, args.cams, 96, 128, args.log2T, args.bs_log2, args.samples, args.warp)
 
-    # ---- what admm_trainer.py does before it creates a TILE (admm_trainer.py:19-24, 96-121, 187-218, 322-327)
     from tools import utils
+    if args.render_tile:
+        return render_frame(args, utils.parse_yaml(yml), data)
+    # ---- what admm_trainer.py does before it creates a TILE (admm_trainer.py:19-24, 96-121, 187-218, 322-327)
     import hashgrid
     import tile as ref_tile
     from fastMesh import FastMesh
@@ -215,6 +254,11 @@ def main():
            "table_changed": bool((t.featureGrid.HE.features.detach().cpu() != (torch.load(args.init_in)["table"] if args.init_in else 0)).any()),
            "pose_grad_finite": bool(torch.isfinite(t.poses.se3_refine.grad).all()) if t.poses.se3_refine.grad is not None else None,
            "config": {"log2T": args.log2T, "batch": 2 ** args.bs_log2, "samples": args.samples, "cams": args.cams}}
+    if args.export_tile:
+        import shutil
+        t.export_tile()                                       # feature.npz (fp16 table + occupancy), decoder.pth, cams.npz
+        shutil.copytree(os.path.join(cfg.LOGDIR, "tile-0"), args.export_tile, dirs_exist_ok=True)
+        out["exported"] = sorted(os.listdir(args.export_tile))
     with open(args.out, "w") as fh:
         json.dump(out, fh)
     print(json.dumps({k: out[k] for k in ("arm", "ms_per_step", "modules")}), flush=True)

@@ -58,3 +58,34 @@ def test_reference_tile_trains_on_the_dropin_like_on_the_reference_extensions(tm
     assert worst < 2e-2, worst
     with open(os.path.join(ROOT, "gpurun_out", f"ref_drivers_{'warp' if warp else 'rgb'}.json") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else str(tmp_path / "summary.json"), "w") as fh:
         json.dump({"warp": warp, "dropin": ours, "reference": ref, "worst_rel_loss_diff": worst}, fh)
+
+
+def test_reference_renderer_on_the_dropin_matches_the_reference_extensions(tmp_path):
+    """rendering.py (RenderingHashGrid.__init__ + render_rays_base, rendering.py:28-180, 286-544), unmodified, renders the
+    SAME exported tile once on the drop-in's render ops and once on the reference's HASHGRID.so: the frames agree to 1e-4.
+    The tile is written by the reference's TILE.export_tile (tile.py:510-532) in the reference arm; the drop-in arm's own
+    export (same reference code over the drop-in's HashGrid.export) is read back by the reference arm."""
+    import numpy as np
+    _need("ref_drivers.zip", "HASHGRID.so", "CUDA_EXT.so", "fastMesh.so")
+    tile_ref, tile_ours = str(tmp_path / "tile_ref"), str(tmp_path / "tile_ours")
+    init = str(tmp_path / "init.pt")
+    r = _run("reference", str(tmp_path / "t_ref.json"), 3, ["--init-out", init, "--export-tile", tile_ref], tmp_path)
+    o = _run("dropin", str(tmp_path / "t_ours.json"), 3, ["--init-in", init, "--export-tile", tile_ours], tmp_path)
+    assert r["exported"] == o["exported"] == ["cams.npz", "decoder.pth", "feature.npz"]
+    fa, fb = np.load(os.path.join(tile_ref, "feature.npz")), np.load(os.path.join(tile_ours, "feature.npz"))
+    assert set(fa.files) == set(fb.files) and all(fa[k].shape == fb[k].shape and fa[k].dtype == fb[k].dtype for k in fa.files)
+    frames = {}
+    for arm, tile, tag in (("reference", tile_ref, "ref_on_ref"), ("dropin", tile_ref, "ours_on_ref"), ("reference", tile_ours, "ref_on_ours")):
+        out = str(tmp_path / f"{tag}.npz")
+        info = _run(arm, str(tmp_path / f"{tag}.json"), 0, ["--render-tile", tile, "--render-out", out], tmp_path)
+        assert info["rendered"] == 2 and info["modules"]["rendering"].endswith("ref_drivers.zip/rendering.py")
+        frames[tag] = (np.load(out), info)
+        print(f"{tag}: {info['ms_per_frame']:.1f} ms per {info['W']}x{info['H']} frame")
+    a, b = frames["ref_on_ref"][0], frames["ours_on_ref"][0]
+    rgb_a, rgb_b = np.clip(a["diffuse"] + a["specular"], 0, 1), np.clip(b["diffuse"] + b["specular"], 0, 1)
+    assert np.isfinite(rgb_b).all() and float(rgb_a.std()) > 1e-3, "the frame must show something"
+    assert float(np.abs(rgb_a - rgb_b).max()) <= 1e-4, float(np.abs(rgb_a - rgb_b).max())
+    assert float(np.abs(a["depth"] - b["depth"]).max()) <= 1e-3 * max(float(np.abs(a["depth"]).max()), 1.0)
+    assert float(np.abs(a["transparency"] - b["transparency"]).max()) <= 1e-4
+    c = frames["ref_on_ours"][0]
+    assert np.isfinite(c["diffuse"]).all() and np.isfinite(c["depth"]).all(), "a tile exported through the drop-in must be readable by the reference"
