@@ -186,6 +186,8 @@ int snrf_decoder_fwd(const float* feats, const float* mask32, const float* rays_
 /* Operand precision of the decoder GEMMs: 1 (default) = error-compensated bf16x3 split operands in
  * every forward GEMM (~fp32 accuracy), 0 = plain bf16 operands (fastest). */
 void snrf_decoder_set_precision(int split);
+/* tuning hook: forward tiles in flight per CTA (4 = default: in-place operand tiles + per-ray SH term, S >= 16; 2 = round-1 kernel) */
+void snrf_decoder_set_inflight(int n);
 /* Backward of snrf_decoder_fwd (autograd of network.py:151-190).  grad_heads[N,10] (column order
  * of heads) -> grad_feats[N,32] WRITTEN; grad_rays_d[R,3] ACCUMULATED (may be NULL; the view
  * direction enters through the SH encoding only); grad_params = HOST array of 16 DEVICE pointers,

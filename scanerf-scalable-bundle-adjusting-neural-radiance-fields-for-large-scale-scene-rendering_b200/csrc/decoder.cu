@@ -97,6 +97,92 @@ decoder_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     if (warp == 0) umma::tmem_free<512>(tmem_slot);
 }
 
+
+// ------------------------------- forward, four tiles in flight ---------------
+// (decoder_core.cuh: forward_layers4; same results as decoder_fwd_kernel, S >= kMinS4)
+template <bool SPLIT>
+__global__ void __launch_bounds__(kThreadsDec, 1)
+decoder_fwd4_kernel(const float* __restrict__ feats, const float* __restrict__ mask32, const float* __restrict__ rays_d,
+                    DecoderParams p, float* __restrict__ out, int N, int S, int num_tiles, long long level_stride,
+                    const unsigned char* __restrict__ ray_valid)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bars[kGroups4];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    stage_all_weights<SPLIT>(smem, p, mask32, tid, kThreadsDec);
+    float* w3sh = reinterpret_cast<float*>(smem + off_w3sh<SPLIT>());
+    stage_w3sh(w3sh, p, tid, kThreadsDec);
+    if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);
+    if (tid == 0) {
+        for (int g = 0; g < kGroups4; ++g) umma::mbar_init(&bars[g], 1);
+        umma::mbar_fence_init();
+    }
+    umma::fence_async_smem();
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    Ctx4 c;
+    c.init(bars, tmem_slot);
+    unsigned char* P = smem + off_tiles4<SPLIT>() + c.group * 2 * kTile;
+    unsigned char* Q = P + kTile;
+    float* rb = reinterpret_cast<float*>(smem + off_raybias4<SPLIT>()) + c.group * kMaxRays4 * 64;
+    const float* mask = reinterpret_cast<const float*>(smem + off_mask<SPLIT>());
+    const float* bias = reinterpret_cast<const float*>(smem + off_bias<SPLIT>());
+
+    for (int tile = kGroups4 * blockIdx.x + c.group; tile < num_tiles; tile += kGroups4 * gridDim.x) {
+        const int n0 = tile * kRows, n = n0 + c.row;
+        const bool live = n < N && (ray_valid == nullptr || ray_valid[n / S] != 0);
+        if (ray_valid != nullptr && !c.any(live)) continue;     // every sample of the tile belongs to a masked-out ray
+        float x[32];
+        if (live) {
+            if (level_stride == 0) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(feats + (size_t)n * 32 + 4 * q));
+                    x[4 * q] = a.x; x[4 * q + 1] = a.y; x[4 * q + 2] = a.z; x[4 * q + 3] = a.w;
+                }
+            } else {
+                const float2* f2 = reinterpret_cast<const float2*>(feats) + n;
+#pragma unroll
+                for (int l = 0; l < 16; ++l) {
+                    const float2 a = __ldg(f2 + (size_t)l * level_stride);
+                    x[2 * l] = a.x; x[2 * l + 1] = a.y;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] *= mask[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+        }
+        // the rays of this tile (the previous tile's epilogues are done with rb: every thread passed its last wait_mma,
+        // and the first sync_operands of forward_layers4 orders these writes before any read)
+        const int ray0 = n0 / S;
+        const int last = (n0 + kRows - 1 < N ? n0 + kRows - 1 : N - 1) / S;
+        c.sync();
+        ray_vectors4(rb, w3sh, rays_d, ray0, last - ray0 + 1, c.gtid);
+        const int my_ray = (live ? n / S : ray0) - ray0;
+        float head[10];
+        forward_layers4<SPLIT>(c, smem, P, Q, x, rb + my_ray * 64, head);
+        float z[16];
+        umma::tmem_ld16(c.tmem + c4Dh + c.lane_addr, z);
+        umma::tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 3; ++j) head[7 + j] = sigmoidf(z[j] + bias[oB5 + j]);
+        if (live) {
+            float2* o = reinterpret_cast<float2*>(out + (size_t)n * 10);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) o[j] = make_float2(head[2 * j], head[2 * j + 1]);
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free<512>(tmem_slot);
+}
+
 // ------------------------------- backward -----------------------------------
 // Per tile: recompute the forward keeping every intermediate in shared memory, then walk the
 // layers backwards.  Each backward stage is one commit group holding the input-gradient GEMM
@@ -511,6 +597,7 @@ grad_absmax_kernel(const float* __restrict__ g, long long n, int S, const unsign
 __device__ unsigned g_gmax_slots[64];      // a ring: concurrent backward launches on different streams use different slots
 int g_gmax_next = 0;
 
+int g_fwd_inflight = 4; // forward tiles in flight per CTA: 4 (in-place operands, per-ray SH term; S >= kMinS4) or 2
 int g_split = 1;       // 1 = error-compensated bf16x3 operands in the forward GEMMs (default), 0 = plain bf16
 
 template <typename K>
@@ -526,6 +613,8 @@ int set_smem(K kernel, int bytes, const char* name)
 // ------------------------------- C ABI --------------------------------------
 // 0 = plain bf16 operands (fastest), 1 = bf16x3 split operands in the forward GEMMs (default)
 SNRF_API void snrf_decoder_set_precision(int split) { g_split = split ? 1 : 0; }
+// tuning hook: forward tiles in flight per CTA (4 = default, 2 = the round-1 kernel)
+SNRF_API void snrf_decoder_set_inflight(int n) { g_fwd_inflight = n == 2 ? 2 : 4; }
 
 // params: HOST array of 16 DEVICE pointers in network.ShallowMLP state_dict order
 SNRF_API int snrf_decoder_fwd(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
@@ -540,13 +629,23 @@ SNRF_API int snrf_decoder_fwd(const float* feats, const float* mask32, const flo
     if (!configured) {
         int rc = set_smem(decoder_fwd_kernel<true>, fwd_smem<true>(), "snrf_decoder_fwd");
         if (rc == 0) rc = set_smem(decoder_fwd_kernel<false>, fwd_smem<false>(), "snrf_decoder_fwd");
+        if (rc == 0) rc = set_smem(decoder_fwd4_kernel<true>, fwd4_smem<true>(), "snrf_decoder_fwd");
+        if (rc == 0) rc = set_smem(decoder_fwd4_kernel<false>, fwd4_smem<false>(), "snrf_decoder_fwd");
         if (rc) return rc;
         configured = true;
     }
     const int num_tiles = snrf_div_up(N, kRows);
     cudaStream_t s = (cudaStream_t)stream;
-    int grid = snrf_sm_count();                     // one 16-warp CTA per SM, two tiles in flight each
-    if (grid > (num_tiles + 1) / 2) grid = (num_tiles + 1) / 2;
+    int grid = snrf_sm_count();                     // one 16-warp CTA per SM
+    if (g_fwd_inflight == 4 && S >= kMinS4) {       // four tiles in flight each
+        if (grid > (num_tiles + 3) / 4) grid = (num_tiles + 3) / 4;
+        if (g_split)
+            decoder_fwd4_kernel<true><<<grid, kThreadsDec, fwd4_smem<true>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
+        else
+            decoder_fwd4_kernel<false><<<grid, kThreadsDec, fwd4_smem<false>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
+        SNRF_RETURN_LAUNCH("snrf_decoder_fwd");
+    }
+    if (grid > (num_tiles + 1) / 2) grid = (num_tiles + 1) / 2;   // two tiles in flight each
     if (g_split)
         decoder_fwd_kernel<true><<<grid, kThreadsDec, fwd_smem<true>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
     else

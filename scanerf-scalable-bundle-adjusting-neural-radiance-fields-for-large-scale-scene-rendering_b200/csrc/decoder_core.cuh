@@ -472,4 +472,177 @@ __device__ __forceinline__ void forward_tile(Ctx<SPLIT, NCG>& c, const Tiles& T,
     forward_layers<SPLIT, TRAIN, NCG>(c, T, head, zh);
 }
 
+// =====================================================================================================================
+// Forward with FOUR tiles in flight per CTA (training forward; the render-side single-tile decode pass).
+//
+// The two-tile forward above is bound by the dependent chain of its five stages (operands -> MMAs -> commit -> TMEM load
+// -> epilogue): 36 % of the issue slots busy, 13 % tensor pipe (profiles/r2d_encode_fwd_decoder_full.md), two tiles are
+// too few to fill the gaps, and five 16 KB operand tiles per in-flight tile leave no room for more.  Two observations
+// shrink an in-flight tile to TWO operand tiles (hi, lo):
+//   * every MMA of a stage has completed before its epilogue starts (the commit was waited for), and the epilogue reads its
+//     inputs from TMEM, not from shared memory: a layer's output can overwrite the layer's input tiles IN PLACE;
+//   * the SH view encoding is a function of the RAY: its contribution W3[:, 32:48] SH(d) to the pre-activation of layer 3
+//     is one 64-vector per ray, computed once per ray in fp32 on the CUDA cores and added like a bias in the epilogue --
+//     no SH columns in any operand tile, three MMAs less per tile, and that term exact instead of split-compensated.
+// One group = 4 consecutive warps = 128 threads = one thread per sample row (all four TMEM lane quadrants), 64
+// accumulator columns per thread, handled as two halves of 32.  TMEM: one 64-column accumulator + 16 head columns per
+// group.  Shared memory: weights (as above) + 4 KB W3_sh (fp32, transposed) + 4 x (32 KB tiles + 2.5 KB ray vectors).
+// Needs S >= kMinS4 (a 128-sample tile then spans at most kMaxRays4 rays); smaller S keeps the two-tile kernel.
+constexpr int kGroups4 = 4, kGroupThreads4 = 128, kTmemGroup4 = 128;
+constexpr int kMinS4 = 16, kMaxRays4 = 128 / kMinS4 + 1;
+constexpr int c4D = 0, c4Dh = 64;
+template <bool SPLIT> constexpr int off_w3sh() { return off_small<SPLIT>() + 64; }                       // float [16][64]
+template <bool SPLIT> constexpr int off_raybias4() { return off_w3sh<SPLIT>() + 16 * 64 * 4; }           // float [4][kMaxRays4][64]
+template <bool SPLIT> constexpr int off_tiles4() { return ((off_raybias4<SPLIT>() + kGroups4 * kMaxRays4 * 64 * 4 + 1023) / 1024) * 1024; }
+template <bool SPLIT> constexpr int fwd4_smem() { return off_tiles4<SPLIT>() + kGroups4 * 2 * kTile + 1024; }
+
+struct Ctx4 {
+    uint64_t* bar;
+    uint32_t tmem, lane_addr, phase, bar_id;
+    int tid, row, group, gtid;
+    bool leader;
+    __device__ __forceinline__ void init(uint64_t* bars, uint32_t tmem_base)
+    {
+        phase = 0;
+        tid = threadIdx.x;
+        const int warp = tid >> 5;
+        group = warp >> 2;
+        row = 32 * (warp & 3) + (tid & 31);
+        gtid = tid - group * kGroupThreads4;
+        bar = bars + group;
+        bar_id = 1 + group;
+        leader = gtid == 0;
+        tmem = tmem_base + group * kTmemGroup4;
+        lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
+    }
+    __device__ __forceinline__ void sync() { bar_sync(bar_id, kGroupThreads4); }
+    __device__ __forceinline__ bool any(bool pred) { return bar_or(bar_id, kGroupThreads4, pred); }
+    __device__ __forceinline__ void sync_operands()
+    {
+        umma::fence_async_smem();
+        umma::tc_fence_before();
+        bar_sync(bar_id, kGroupThreads4);
+        umma::tc_fence_after();
+    }
+    __device__ __forceinline__ void wait_mma()
+    {
+        umma::mbar_wait(bar, phase);
+        phase ^= 1u;
+        umma::tc_fence_after();
+    }
+};
+
+// W3[:, 32:48] (the SH columns of the first directional layer) as fp32, transposed to [16][64]
+__device__ inline void stage_w3sh(float* dst, const DecoderParams& p, int tid, int nthreads)
+{
+    for (int i = tid; i < 16 * 64; i += nthreads) {
+        const int k = i >> 6, o = i & 63;                       // dst[k][o] = W3[o][32 + k]
+        dst[i] = p.flat ? p.W3[(32 + k) * 64 + o] : p.W3[o * 48 + 32 + k];
+    }
+}
+
+// The layers of one tile, operands in place in (P, Q) = (hi, lo).  x (already masked) is this thread's whole input row;
+// rb = this row's ray vector W3_sh SH(d) (64 floats in shared memory).  Returns sigma / diffuse / tint activated in
+// head[0..6] and leaves the specular pre-activations in TMEM columns c4Dh .. c4Dh + 2 (after the last wait).
+template <bool SPLIT>
+__device__ __forceinline__ void forward_layers4(Ctx4& c, unsigned char* smem, unsigned char* P, unsigned char* Q, const float* x,
+                                                const float* rb, float* head)
+{
+    const int row = c.row;
+    const uint32_t tmem = c.tmem, lane_addr = c.lane_addr;
+    const float* bias = reinterpret_cast<const float*>(smem + off_bias<SPLIT>());
+    const uint32_t aP = umma::smem_u32(P), aQ = umma::smem_u32(Q);
+    const uint32_t aW1 = umma::smem_u32(smem + oW1), aW2 = umma::smem_u32(smem + oW2), aW3 = umma::smem_u32(smem + oW3),
+                   aW4 = umma::smem_u32(smem + oW4), aWh = umma::smem_u32(smem + oWh), aW5 = umma::smem_u32(smem + oW5),
+                   aW2l = umma::smem_u32(smem + oW2l), aW3l = umma::smem_u32(smem + oW3l), aW4l = umma::smem_u32(smem + oW4l),
+                   aW5l = umma::smem_u32(smem + oW5l);
+    constexpr uint32_t id64 = umma::idesc_f16(128, 64, 0, 0, kOpBf16, kOpBf16), id16 = umma::idesc_f16(128, 16, 0, 0, kOpBf16, kOpBf16);
+    // input row, packed: x_hi in columns 0..31 of P, x_lo in columns 32..63 of P
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        store8_act<SPLIT>(P, q, P, 4 + q, row, x + 8 * q);
+        if (!SPLIT) umma::tile_zero8(P, row, 4 + q);
+    }
+    c.sync_operands();
+    if (c.leader) {          // L1: D = x W1^T (K = 32)
+        fwd_gemm<SPLIT>(tmem + c4D, aP, 0, aP, 2, aW1, 0, aW1, 2, 2, id64, false);
+        umma::mma_commit(c.bar);
+    }
+    c.wait_mma();
+    float v[32];
+    // epilogue of a 64-wide layer on this thread's row, 32 columns at a time: v = D + bias (+ extra) -> f(v) -> (P, Q)
+    auto epilogue = [&](int boff, const float* extra, bool gaussian) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            umma::tmem_ld32(tmem + c4D + lane_addr + 32 * half, v);
+            umma::tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float z = v[j] + bias[boff + 32 * half + j];
+                if (extra != nullptr) z += extra[32 * half + j];
+                v[j] = gaussian ? gauss_act(z) : z;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) store8_act<SPLIT>(P, 4 * half + q, Q, 4 * half + q, row, v + 8 * q);
+        }
+    };
+    epilogue(oB1, nullptr, true);                                         // a1
+    c.sync_operands();
+    if (c.leader) {          // L2: D = a1 W2^T (K = 64)
+        fwd_gemm<SPLIT>(tmem + c4D, aP, 0, aQ, 0, aW2, 0, aW2l, 0, 4, id64, false);
+        umma::mma_commit(c.bar);
+    }
+    c.wait_mma();
+    epilogue(oB2, nullptr, false);                                        // H
+    c.sync_operands();
+    if (c.leader) {          // heads: Dh = H[0:32] Wh^T (K = 32, N = 16);  L3: D = H[32:64] W3[:, 0:32]^T (K = 32)
+        fwd_gemm<SPLIT>(tmem + c4Dh, aP, 0, aQ, 0, aWh, 0, aWh, 2, 2, id16, false);
+        fwd_gemm<SPLIT>(tmem + c4D, aP, 2, aQ, 2, aW3, 0, aW3l, 0, 2, id64, false);
+        umma::mma_commit(c.bar);
+    }
+    c.wait_mma();
+    {
+        float z[16];
+        umma::tmem_ld16(tmem + c4Dh + lane_addr, z);
+        umma::tc_wait_ld();
+        head[0] = softplusf(z[0] + bias[oBh]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            head[4 + j] = sigmoidf(z[1 + j] + bias[oBh + 1 + j]);      // diffuse
+            head[1 + j] = sigmoidf(z[4 + j] + bias[oBh + 4 + j]);      // tint
+        }
+    }
+    epilogue(oB3, rb, true);                                              // a3 (+ the ray's SH term)
+    c.sync_operands();
+    if (c.leader) {          // L4: D = a3 W4^T (K = 64)
+        fwd_gemm<SPLIT>(tmem + c4D, aP, 0, aQ, 0, aW4, 0, aW4l, 0, 4, id64, false);
+        umma::mma_commit(c.bar);
+    }
+    c.wait_mma();
+    epilogue(oB4, nullptr, true);                                         // a4
+    c.sync_operands();
+    if (c.leader) {          // L5: Dh = a4 W5^T (K = 64, N = 16)
+        fwd_gemm<SPLIT>(tmem + c4Dh, aP, 0, aQ, 0, aW5, 0, aW5l, 0, 4, id16, false);
+        umma::mma_commit(c.bar);
+    }
+    c.wait_mma();
+}
+
+// Ray vectors of one tile: rays [ray0, ray0 + nrays) -> rb[i][0..63] = W3_sh SH(d_i / (|d_i| + 1e-8)), by the group's 128 threads.
+__device__ __forceinline__ void ray_vectors4(float* rb, const float* __restrict__ w3sh, const float* __restrict__ rays_d, int ray0,
+                                             int nrays, int gtid)
+{
+    for (int i = gtid; i < nrays * 64; i += kGroupThreads4) {
+        const int r = i >> 6, o = i & 63;
+        const f3 d = ld3(rays_d + 3 * (size_t)(ray0 + r));
+        const float inv = 1.0f / (sqrtf(d.x * d.x + d.y * d.y + d.z * d.z) + 1e-8f);
+        float sh[16];
+        sh16(d.x * inv, d.y * inv, d.z * inv, sh);
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc += w3sh[k * 64 + o] * sh[k];
+        rb[r * 64 + o] = acc;
+    }
+}
+
 }  // namespace dec

@@ -48,6 +48,37 @@ def _decoder_and_inputs(N, S, seed):
     return dec, decoder_params(dec), feats, mask, rays_d
 
 
+@pytest.mark.parametrize("N,S,masked", [(128, 128, False), (128 * 37 + 5, 64, True), (4096 * 5 + 77, 16, True), (128 * 9, 100, False),
+                                        (128 * 700 + 3, 128, False)])
+def test_four_tiles_in_flight_forward_equals_two_tile_forward(N, S, masked):
+    """The forward with four tiles in flight (in-place operand tiles, the SH term of layer 3 added per ray in fp32) against
+    the round-1 two-tile kernel: same heads (the SH term is exact instead of split-compensated, everything else is the same
+    arithmetic), level-major and row-major inputs, ragged last tile, rays masked out, tiles that straddle many rays."""
+    load_pkg()
+    import scanerf_b200_capi as capi
+    from hashgrid import _field
+    dec, params, feats, mask, rays_d = _decoder_and_inputs(N, S, N + 3)
+    dev = "cuda:0"
+    valid = (torch.rand(rays_d.shape[0], generator=torch.Generator().manual_seed(1)) < 0.7).to(dev) if masked else None
+    pd = [p.to(dev) for p in params]
+    for lm in (False, True):
+        f = feats.to(dev)
+        if lm:
+            f = f.reshape(N, 16, 2).permute(1, 0, 2).contiguous()
+        outs = []
+        for inflight in (2, 4):
+            capi.lib().snrf_decoder_set_inflight(capi.c_int(inflight))
+            outs.append(_field.decoder_forward(f, mask.to(dev), rays_d.to(dev), S, pd, valid))
+        capi.lib().snrf_decoder_set_inflight(capi.c_int(4))
+        torch.cuda.synchronize()
+        a, b = outs
+        if valid is not None:
+            keep = valid.repeat_interleave(S)[:N]
+            a, b = a[keep], b[keep]
+        assert bool(torch.isfinite(b).all())
+        assert float((a - b).abs().max()) < 2e-5, (lm, float((a - b).abs().max()))
+
+
 @pytest.mark.parametrize("split", [True, False])
 @pytest.mark.parametrize("N,S", [(128, 128), (1000, 8), (128 * 37 + 5, 64)])
 def test_decoder_forward_matches_torch(N, S, split):
