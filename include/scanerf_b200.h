@@ -287,6 +287,8 @@ int snrf_bg_pts_inference_v2(const float* rays_o, const float* rays_d, const flo
 void snrf_infer_set_precision(int split);
 /* tuning hook: 128-sample tiles in flight per CTA for single-tile scenes (1 or 2, default 1: see csrc/infer.cu) */
 void snrf_infer_set_inflight(int tiles);
+/* tuning hook: tiles in flight per CTA of the single-tile decode pass (4 = default, 2 = the round-1 kernel) */
+void snrf_infer_set_decode_inflight(int n);
 /* tuning hook: 1 (default) = multi-pass paths (single-tile two-pass, multi-tile grouped), 0 = the fused kernel,
  * 2 = the grouped (compacting) path also for single-tile scenes */
 void snrf_infer_set_two_pass(int on);

@@ -163,10 +163,10 @@ decoder_fwd4_kernel(const float* __restrict__ feats, const float* __restrict__ m
         const int ray0 = n0 / S;
         const int last = (n0 + kRows - 1 < N ? n0 + kRows - 1 : N - 1) / S;
         c.sync();
-        ray_vectors4(rb, w3sh, rays_d, ray0, last - ray0 + 1, c.gtid);
+        ray_vectors4<false>(rb, w3sh, rays_d, ray0, last - ray0 + 1, c.gtid);
         const int my_ray = (live ? n / S : ray0) - ray0;
-        float head[10];
-        forward_layers4<SPLIT>(c, smem, P, Q, x, rb + my_ray * 64, head);
+        float head[10], zh[7];
+        forward_layers4<SPLIT>(c, smem, P, Q, x, rb + my_ray * 64, head, zh);
         float z[16];
         umma::tmem_ld16(c.tmem + c4Dh + c.lane_addr, z);
         umma::tc_wait_ld();

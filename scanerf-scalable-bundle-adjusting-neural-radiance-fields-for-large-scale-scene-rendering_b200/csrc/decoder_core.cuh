@@ -546,7 +546,7 @@ __device__ inline void stage_w3sh(float* dst, const DecoderParams& p, int tid, i
 // head[0..6] and leaves the specular pre-activations in TMEM columns c4Dh .. c4Dh + 2 (after the last wait).
 template <bool SPLIT>
 __device__ __forceinline__ void forward_layers4(Ctx4& c, unsigned char* smem, unsigned char* P, unsigned char* Q, const float* x,
-                                                const float* rb, float* head)
+                                                const float* rb, float* head, float* zh)
 {
     const int row = c.row;
     const uint32_t tmem = c.tmem, lane_addr = c.lane_addr;
@@ -605,11 +605,13 @@ __device__ __forceinline__ void forward_layers4(Ctx4& c, unsigned char* smem, un
         float z[16];
         umma::tmem_ld16(tmem + c4Dh + lane_addr, z);
         umma::tc_wait_ld();
-        head[0] = softplusf(z[0] + bias[oBh]);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) zh[j] = z[j] + bias[oBh + j];
+        head[0] = softplusf(zh[0]);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            head[4 + j] = sigmoidf(z[1 + j] + bias[oBh + 1 + j]);      // diffuse
-            head[1 + j] = sigmoidf(z[4 + j] + bias[oBh + 4 + j]);      // tint
+            head[4 + j] = sigmoidf(zh[1 + j]);      // diffuse
+            head[1 + j] = sigmoidf(zh[4 + j]);      // tint
         }
     }
     epilogue(oB3, rb, true);                                              // a3 (+ the ray's SH term)
@@ -628,14 +630,16 @@ __device__ __forceinline__ void forward_layers4(Ctx4& c, unsigned char* smem, un
     c.wait_mma();
 }
 
-// Ray vectors of one tile: rays [ray0, ray0 + nrays) -> rb[i][0..63] = W3_sh SH(d_i / (|d_i| + 1e-8)), by the group's 128 threads.
+// Ray vectors of one tile: rays [ray0, ray0 + nrays) -> rb[i][0..63] = W3_sh SH(unit(d_i)), by the group's 128 threads.
+// unit(d) = d / (|d| + 1e-8) in training (network.py:172-176), d * rsqrt(d.d) in the renderer (decoder.h:201).
+template <bool RENDER_NORM>
 __device__ __forceinline__ void ray_vectors4(float* rb, const float* __restrict__ w3sh, const float* __restrict__ rays_d, int ray0,
                                              int nrays, int gtid)
 {
     for (int i = gtid; i < nrays * 64; i += kGroupThreads4) {
         const int r = i >> 6, o = i & 63;
         const f3 d = ld3(rays_d + 3 * (size_t)(ray0 + r));
-        const float inv = 1.0f / (sqrtf(d.x * d.x + d.y * d.y + d.z * d.z) + 1e-8f);
+        const float inv = RENDER_NORM ? rsqrtf(d.x * d.x + d.y * d.y + d.z * d.z) : 1.0f / (sqrtf(d.x * d.x + d.y * d.y + d.z * d.z) + 1e-8f);
         float sh[16];
         sh16(d.x * inv, d.y * inv, d.z * inv, sh);
         float acc = 0.0f;

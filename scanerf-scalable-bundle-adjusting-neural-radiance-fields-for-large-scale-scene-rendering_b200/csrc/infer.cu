@@ -453,6 +453,99 @@ infer_decode_kernel(InferArgs a, long long n0, int Nc, const float2* __restrict_
     if (warp == 0) umma::tmem_free<512>(tmem_slot);
 }
 
+
+// The same decode pass with FOUR tiles in flight per CTA (decoder_core.cuh: forward_layers4 -- operand tiles in place, the
+// SH term of the first directional layer added per ray in fp32): one thread per sample row.  Needs a.S >= kMinS4.
+template <bool SPLIT, int MODE>
+__global__ void __launch_bounds__(kThreadsDec, 1)
+infer_decode4_kernel(InferArgs a, long long n0, int Nc, const float2* __restrict__ feats_lm, const float2* __restrict__ aux,
+                     const unsigned char* __restrict__ state, int num_tiles)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bars[kGroups4];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const DecoderParams prm = flat_params(a.params);
+    stage_all_weights<SPLIT>(smem, prm, nullptr, tid, kThreadsDec);
+    float* w3sh = reinterpret_cast<float*>(smem + off_w3sh<SPLIT>());
+    stage_w3sh(w3sh, prm, tid, kThreadsDec);
+    if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);
+    if (tid == 0) {
+        for (int g = 0; g < kGroups4; ++g) umma::mbar_init(&bars[g], 1);
+        umma::mbar_fence_init();
+    }
+    umma::fence_async_smem();
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    Ctx4 c;
+    c.init(bars, tmem_slot);
+    unsigned char* P = smem + off_tiles4<SPLIT>() + c.group * 2 * kTile;
+    unsigned char* Q = P + kTile;
+    float* rb = reinterpret_cast<float*>(smem + off_raybias4<SPLIT>()) + c.group * kMaxRays4 * 64;
+    const float* bias = reinterpret_cast<const float*>(smem + off_bias<SPLIT>());
+    const int row = c.row;
+
+    for (int tile = kGroups4 * blockIdx.x + c.group; tile < num_tiles; tile += kGroups4 * gridDim.x) {
+        const int i0 = tile * kRows, i = i0 + row;
+        const int st = i < Nc ? state[i] : 2;
+        const bool active = st == 1;
+        const long long n = n0 + i;
+        if (c.any(active)) {
+            float x[32];
+            if (active) {
+#pragma unroll
+                for (int l = 0; l < 16; ++l) {
+                    const float2 v = __ldg(feats_lm + i + (size_t)l * Nc);
+                    x[2 * l] = v.x; x[2 * l + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = 0.0f;
+            }
+            const int ray0 = (int)((n0 + i0) / a.S);
+            const long long last_n = n0 + (i0 + kRows - 1 < Nc ? i0 + kRows - 1 : Nc - 1);
+            const int nrays = (int)(last_n / a.S) - ray0 + 1;
+            c.sync();
+            ray_vectors4<true>(rb, w3sh, a.rays_d, ray0, nrays, c.gtid);
+            const int my_ray = active ? (int)(n / a.S) - ray0 : 0;
+            float head[10], zh[7];
+            forward_layers4<SPLIT>(c, smem, P, Q, x, rb + my_ray * 64, head, zh);
+            float zs[16];
+            umma::tmem_ld16(c.tmem + c4Dh + c.lane_addr, zs);
+            umma::tc_wait_ld();
+            if (active) {
+                // Decoder::inference activations (decoder.h:134-146): softplus without threshold, expf sigmoids
+                const float sigma = logf(1.0f + expf(zh[0]));
+                f3 dif = mk3(1.0f / (1.0f + expf(-zh[1])), 1.0f / (1.0f + expf(-zh[2])), 1.0f / (1.0f + expf(-zh[3])));
+                const f3 tint = mk3(1.0f / (1.0f + expf(-zh[4])), 1.0f / (1.0f + expf(-zh[5])), 1.0f / (1.0f + expf(-zh[6])));
+                f3 spe = mk3(tint.x / (1.0f + expf(-(zs[0] + bias[oB5 + 0]))), tint.y / (1.0f + expf(-(zs[1] + bias[oB5 + 1]))),
+                             tint.z / (1.0f + expf(-(zs[2] + bias[oB5 + 2]))));
+                const float2 ws = aux[i];
+                const float al = 1.0f - expf(-1.0f * sigma * ws.y);
+                float wa = ws.x * al;
+                dif = dif * wa; spe = spe * wa;
+                if (MODE != kBackSlot && ws.x > 0) {               // the reference divides by the weight sum when it is positive
+                    const float inv = 1.0f / ws.x;
+                    dif = dif * inv; spe = spe * inv; wa *= inv;
+                }
+                st3(a.out_diffuse + 3 * (size_t)n, dif);
+                st3(a.out_specular + 3 * (size_t)n, spe);
+                a.out_alpha[n] = wa;
+            }
+        }
+        if (st == 0) {                                         // unoccupied / unassigned foreground sample: zeros
+            st3(a.out_diffuse + 3 * (size_t)n, mk3(0, 0, 0));
+            st3(a.out_specular + 3 * (size_t)n, mk3(0, 0, 0));
+            a.out_alpha[n] = 0.0f;
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) umma::tmem_free<512>(tmem_slot);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Multi-tile path: the (sample, slot) pairs that need the field of a scene tile are grouped by tile id (counting sort,
 // each tile's segment padded to whole 256-row blocks), encoded level-major per tile and decoded block by block -- a
@@ -680,6 +773,7 @@ work_combine_kernel(InferArgs a, long long n0, int Nc, Work w)
     }
 }
 
+int g_decode_inflight = 4;   // tiles in flight per CTA of the single-tile decode pass (4: infer_decode4_kernel, 2: infer_decode_kernel)
 int g_infer_split = 1;
 int g_infer_two_pass = 1;     // single-tile scenes: level-major encode pass + decoder pass (tuning hook)
 // Tiles in flight per CTA for single-tile scenes.  Measured on B200 (1920x1080, tools/render_one_frame.py): 1 tile in
@@ -744,6 +838,8 @@ int launch_two_pass(const InferArgs& a, void* stream, const char* name)
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(infer_decode_kernel<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<true>());
         if (e == cudaSuccess) e = cudaFuncSetAttribute(infer_decode_kernel<false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<false>());
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(infer_decode4_kernel<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd4_smem<true>());
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(infer_decode4_kernel<false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd4_smem<false>());
         if (e != cudaSuccess) { snrf_set_error("%s: %s", name, cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
@@ -768,6 +864,12 @@ int launch_two_pass(const InferArgs& a, void* stream, const char* name)
         infer_encode_kernel<<<dim3(gx, 16), 256, 0, s>>>(a, Nc, uw, state, feats);
         const int num_tiles = snrf_div_up(Nc, kRows);
         int grid = sms;
+        if (g_decode_inflight == 4 && a.S >= kMinS4) {           // four tiles in flight per CTA
+            if (grid > (num_tiles + 3) / 4) grid = (num_tiles + 3) / 4;
+            if (g_infer_split) infer_decode4_kernel<true, MODE><<<grid, kThreadsDec, fwd4_smem<true>(), s>>>(a, n0, Nc, feats, aux, state, num_tiles);
+            else infer_decode4_kernel<false, MODE><<<grid, kThreadsDec, fwd4_smem<false>(), s>>>(a, n0, Nc, feats, aux, state, num_tiles);
+            continue;
+        }
         if (grid > (num_tiles + 1) / 2) grid = (num_tiles + 1) / 2;
         if (g_infer_split) infer_decode_kernel<true, MODE><<<grid, kThreadsDec, fwd_smem<true>(), s>>>(a, n0, Nc, feats, aux, state, num_tiles);
         else infer_decode_kernel<false, MODE><<<grid, kThreadsDec, fwd_smem<false>(), s>>>(a, n0, Nc, feats, aux, state, num_tiles);
@@ -847,6 +949,8 @@ int launch(const InferArgs& a, int nb, void* stream, const char* name)
 }  // namespace
 
 // ------------------------------- C ABI --------------------------------------
+// tiles in flight per CTA of the single-tile decode pass: 4 (default) or 2 (round-1 kernel)
+SNRF_API void snrf_infer_set_decode_inflight(int n) { g_decode_inflight = n == 2 ? 2 : 4; }
 SNRF_API void snrf_infer_set_precision(int split) { g_infer_split = split ? 1 : 0; }
 SNRF_API void snrf_infer_set_inflight(int tiles) { g_infer_inflight = tiles == 2 ? 2 : 1; }
 SNRF_API void snrf_infer_set_two_pass(int on) { g_infer_two_pass = on == 2 ? 2 : (on ? 1 : 0); }
