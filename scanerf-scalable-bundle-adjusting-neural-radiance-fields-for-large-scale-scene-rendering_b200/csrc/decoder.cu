@@ -337,6 +337,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         store8_act<SPLIT>(Thi, chunk0 + cg, Tlo, chunk0 + cg, row, v);
     };
 
+    const bool lead_warp = umma::warp_uniform() == 0;      // the MMAs of this kernel are issued by one elected lane of warp 0
     bool first = true;      // no tile processed yet: the first one initialises the TMEM gradient accumulators
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n = tile * kRows + row;
@@ -383,7 +384,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         }
         c.sync_operands();
         // ---- B1: dA4 = dz_spec W5 ; dH[0:32] = dz_heads Wh ; dW5^T += a4^T dz_spec ; dWh^T += H^T dz_heads
-        if (tid == 0) {
+        if (lead_warp && umma::elect_one()) {
             dgrad(cDa, adz, 1, adz, 3, aW5, aW5l, 1, idg64);
             dgrad(cDc, adz, 0, adz, 2, aWh, aWh + 64, 1, idg32);     // dH[0:32] stays in TMEM until the B2 epilogue
             umma::mma_commit(&bar);
@@ -394,7 +395,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         mul_inplace(cDa, T.g4, Tdzlo, acc_b4);                   // dz5 (+ its column sums = d/d b4)
         c.sync_operands();
         // ---- B2: dA3 = dz5 W4 ; dW4 += dz5^T a3
-        if (tid == 0) {
+        if (lead_warp && umma::elect_one()) {
             dgrad(cDb, ag4, 0, adzlo, 0, aW4, aW4l, 4, idg64);
             // the epilogue overwrites the dz lo tile: its part goes in front of the commit, the hi part behind it
             if (SPLIT) wgrad_part(cGW4, adzlo, aa3, idw64, first);
@@ -406,7 +407,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         mul_inplace(cDb, T.g3, Tdzlo, nullptr);                  // dz4
         c.sync_operands();
         // ---- B3: d[x2] = dz4 W3 ; dW3 += dz4^T [H[32:64] | SH] ; db3
-        if (tid == 0) {
+        if (lead_warp && umma::elect_one()) {
             dgrad(cDa, ag3, 0, adzlo, 0, aW3, aW3l, 4, idg64);
             umma::mma_commit(&bar);
             wgrad(cGW3a, ag3, adzlo, aH + 64, idw32, first);        // behind the commit: the epilogue writes dH only
@@ -416,7 +417,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         store_quarter(cDa, Tdz, Tdhlo, 4, acc_b2 + 8);           // dH[32:64]
         c.sync_operands();
         // ---- B4: dA1 = dH W2 ; dW2 += dH^T a1 ; db2
-        if (tid == 0) {
+        if (lead_warp && umma::elect_one()) {
             dgrad(cDb, adz, 0, adhlo, 0, aW2, aW2l, 4, idg64);
             umma::mma_commit(&bar);
             wgrad(cGW2, adz, adhlo, aa1, idw64, first);             // behind the commit: the epilogue writes g1 / the dz lo tile
@@ -477,7 +478,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         mul_inplace(cDb, T.g1, Tdzlo, nullptr);                  // dz1
         c.sync_operands();
         // ---- B5: dx = dz1 W1 (32 columns) ; dW1 += dz1^T x ; db1
-        if (tid == 0) {
+        if (lead_warp && umma::elect_one()) {
             dgrad(cDa, ag1, 0, adzlo, 0, aW1, aW1 + 64, 4, idg32);
             umma::mma_commit(&bar);
             wgrad(cGW1, ag1, adzlo, aA0, idw48, first);             // N = 48: x (32) | SH (16); column 32 -> d/d b1

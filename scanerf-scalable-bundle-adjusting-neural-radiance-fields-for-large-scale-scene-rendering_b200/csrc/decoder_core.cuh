@@ -268,7 +268,7 @@ struct Ctx {
     uint64_t* bar;
     uint32_t tmem, lane_addr, phase, bar_id, nthr;
     int tid, row, cg, group;
-    bool leader;                                // the thread that issues this group's MMAs
+    bool leader_warp;                           // (warp-uniform) this warp holds the thread that issues this group's MMAs
     const float* bias;
     const float* mask;
     // `bars`: one mbarrier per group; `tmem_base`: the CTA's TMEM allocation
@@ -282,12 +282,13 @@ struct Ctx {
         else { group = warp >> 3; cg = (warp >> 2) & 1; nthr = kThreadsDec / 2; }
         bar = bars + group;
         bar_id = 1 + group;
-        leader = (tid == group * (kThreadsDec / 2));
+        leader_warp = umma::warp_uniform() == group * (kThreadsDec / 64);
         tmem = tmem_base + (NCG == 4 ? 0 : group * kTmemGroup);
         lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
         bias = reinterpret_cast<const float*>(smem + off_bias<SPLIT>());
         mask = reinterpret_cast<const float*>(smem + off_mask<SPLIT>());
     }
+    __device__ __forceinline__ bool leader() const { return leader_warp && umma::elect_one(); }
     __device__ __forceinline__ void sync() { bar_sync(bar_id, nthr); }
     __device__ __forceinline__ bool any(bool pred) { return bar_or(bar_id, nthr, pred); }
     __device__ __forceinline__ void sync_operands()
@@ -351,7 +352,7 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
 
     c.sync_operands();
     // ---- L1: Da = x W1^T (K = 32)
-    if (c.leader) {
+    if (c.leader()) {
         fwd_gemm<SPLIT>(tmem + cDa, aA0, 0, aLOb, 0, aW1, 0, aW1, 2, 2, id64, false);
         umma::mma_commit(c.bar);
     }
@@ -377,7 +378,7 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
     gauss_epilogue(cDa, oB1, T.a1, T.LOa, T.g1);
     c.sync_operands();
     // ---- L2: Db = h1 W2^T (K = 64)
-    if (c.leader) {
+    if (c.leader()) {
         fwd_gemm<SPLIT>(tmem + cDb, aa1, 0, aLOa, 0, aW2, 0, aW2l, 0, 4, id64, false);
         umma::mma_commit(c.bar);
     }
@@ -389,7 +390,7 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
     for (int q = 0; q < CH; ++q) store8_act<SPLIT>(T.H, CH * cg + q, T.LOb, CH * cg + q, row, v + 8 * q);
     c.sync_operands();
     // ---- heads: Dh = H[0:32] Wh^T (K = 32, N = 16);   L3: Da = [H[32:64] | SH] W3^T (K = 48)
-    if (c.leader) {
+    if (c.leader()) {
         fwd_gemm<SPLIT>(tmem + cDh, aH, 0, aLOb, 0, aWh, 0, aWh, 2, 2, id16, false);
         fwd_gemm<SPLIT>(tmem + cDa, aH, 2, aLOb, 2, aW3, 0, aW3l, 0, 2, id64, false);
         fwd_gemm<SPLIT>(tmem + cDa, aA0, 2, aA0, 3, aW3, 2, aW3l, 2, 1, id64, true);
@@ -412,7 +413,7 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
     gauss_epilogue(cDa, oB3, T.a3, T.LOa, T.g3);
     c.sync_operands();
     // ---- L4: Db = a3 W4^T (K = 64)
-    if (c.leader) {
+    if (c.leader()) {
         fwd_gemm<SPLIT>(tmem + cDb, aa3, 0, aLOa, 0, aW4, 0, aW4l, 0, 4, id64, false);
         umma::mma_commit(c.bar);
     }
@@ -420,7 +421,7 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
     gauss_epilogue(cDb, oB4, T.a4, T.LOb, T.g4);
     c.sync_operands();
     // ---- L5: Dh = a4 W5^T (K = 64, N = 16)
-    if (c.leader) {
+    if (c.leader()) {
         fwd_gemm<SPLIT>(tmem + cDh, aa4, 0, aLOb, 0, aW5, 0, aW5l, 0, 4, id16, false);
         umma::mma_commit(c.bar);
     }
@@ -500,7 +501,7 @@ struct Ctx4 {
     uint64_t* bar;
     uint32_t tmem, lane_addr, phase, bar_id;
     int tid, row, group, gtid;
-    bool leader;
+    bool leader_warp;
     __device__ __forceinline__ void init(uint64_t* bars, uint32_t tmem_base)
     {
         phase = 0;
@@ -511,10 +512,11 @@ struct Ctx4 {
         gtid = tid - group * kGroupThreads4;
         bar = bars + group;
         bar_id = 1 + group;
-        leader = gtid == 0;
+        leader_warp = umma::warp_uniform() == 4 * group;
         tmem = tmem_base + group * kTmemGroup4;
         lane_addr = (uint32_t)(32 * (warp & 3)) << 16;
     }
+    __device__ __forceinline__ bool leader() const { return leader_warp && umma::elect_one(); }
     __device__ __forceinline__ void sync() { bar_sync(bar_id, kGroupThreads4); }
     __device__ __forceinline__ bool any(bool pred) { return bar_or(bar_id, kGroupThreads4, pred); }
     __device__ __forceinline__ void sync_operands()
@@ -564,7 +566,7 @@ __device__ __forceinline__ void forward_layers4(Ctx4& c, unsigned char* smem, un
         if (!SPLIT) umma::tile_zero8(P, row, 4 + q);
     }
     c.sync_operands();
-    if (c.leader) {          // L1: D = x W1^T (K = 32)
+    if (c.leader()) {          // L1: D = x W1^T (K = 32)
         fwd_gemm<SPLIT>(tmem + c4D, aP, 0, aP, 2, aW1, 0, aW1, 2, 2, id64, false);
         umma::mma_commit(c.bar);
     }
@@ -588,14 +590,14 @@ __device__ __forceinline__ void forward_layers4(Ctx4& c, unsigned char* smem, un
     };
     epilogue(oB1, nullptr, true);                                         // a1
     c.sync_operands();
-    if (c.leader) {          // L2: D = a1 W2^T (K = 64)
+    if (c.leader()) {          // L2: D = a1 W2^T (K = 64)
         fwd_gemm<SPLIT>(tmem + c4D, aP, 0, aQ, 0, aW2, 0, aW2l, 0, 4, id64, false);
         umma::mma_commit(c.bar);
     }
     c.wait_mma();
     epilogue(oB2, nullptr, false);                                        // H
     c.sync_operands();
-    if (c.leader) {          // heads: Dh = H[0:32] Wh^T (K = 32, N = 16);  L3: D = H[32:64] W3[:, 0:32]^T (K = 32)
+    if (c.leader()) {          // heads: Dh = H[0:32] Wh^T (K = 32, N = 16);  L3: D = H[32:64] W3[:, 0:32]^T (K = 32)
         fwd_gemm<SPLIT>(tmem + c4Dh, aP, 0, aQ, 0, aWh, 0, aWh, 2, 2, id16, false);
         fwd_gemm<SPLIT>(tmem + c4D, aP, 2, aQ, 2, aW3, 0, aW3l, 0, 2, id64, false);
         umma::mma_commit(c.bar);
@@ -616,14 +618,14 @@ __device__ __forceinline__ void forward_layers4(Ctx4& c, unsigned char* smem, un
     }
     epilogue(oB3, rb, true);                                              // a3 (+ the ray's SH term)
     c.sync_operands();
-    if (c.leader) {          // L4: D = a3 W4^T (K = 64)
+    if (c.leader()) {          // L4: D = a3 W4^T (K = 64)
         fwd_gemm<SPLIT>(tmem + c4D, aP, 0, aQ, 0, aW4, 0, aW4l, 0, 4, id64, false);
         umma::mma_commit(c.bar);
     }
     c.wait_mma();
     epilogue(oB4, nullptr, true);                                         // a4
     c.sync_operands();
-    if (c.leader) {          // L5: Dh = a4 W5^T (K = 64, N = 16)
+    if (c.leader()) {          // L5: Dh = a4 W5^T (K = 64, N = 16)
         fwd_gemm<SPLIT>(tmem + c4Dh, aP, 0, aQ, 0, aW5, 0, aW5l, 0, 4, id16, false);
         umma::mma_commit(c.bar);
     }

@@ -145,7 +145,7 @@ infer_kernel(InferArgs a, int num_tiles)
             for (int i = 0; i < kMaxPts; ++i) if (ids[i] > cur && ids[i] < mine) mine = ids[i];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, off));
-            if (c.leader) next_id = 0x7fffffff;
+            if (c.leader_warp && lane == 0) next_id = 0x7fffffff;
             c.sync();
             if (lane == 0 && mine != 0x7fffffff) atomicMin(&next_id, mine);
             c.sync();

@@ -74,10 +74,13 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t smem_addr)
     d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
     return d;
 }
+// The start-address field sits in the low 14 bits and shared memory ends below 256 KB, so stepping an operand is a plain
+// addition to the descriptor of the tile base -- which the compiler computes once per tile (the ~10 shift / mask / or
+// instructions per descriptor in front of every tcgen05.mma were ~30 % of the one issuing thread's time in the backward).
 // K-major operand: one MMA consumes 16 columns = 32 bytes of every row -> advance inside the row
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int kstep) { return desc_sw128(tile_addr + kstep * 32); }
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int kstep) { return desc_sw128(tile_addr) + (uint64_t)(uint32_t)(kstep * 2); }
 // MN-major operand: one MMA consumes 16 rows = 2048 bytes -> advance by whole row groups
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int kstep) { return desc_sw128(tile_addr + kstep * 2048); }
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int kstep) { return desc_sw128(tile_addr) + (uint64_t)(uint32_t)(kstep * 128); }
 
 // Instruction descriptor for kind::f16, bf16 x bf16 -> f32 (c_format F32 = 1 at [4,6), a/b format
 // BF16 = 1 at [7,10)/[10,13), a_major at 15, b_major at 16 (0 = K-major, 1 = MN-major),
@@ -96,6 +99,23 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, i
 }
 
 // ---------------------------------------------------------------- MMA issue / completion (one thread)
+// One elected lane of a fully converged warp (the same lane every time for a full member mask).  Issuing the MMAs under
+// `if (warp-uniform condition && elect_one())` instead of `if (tid == leader)` lets ptxas keep descriptors and issue on the
+// uniform datapath without wrapping every tcgen05.mma in an elect / branch loop.
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "elect.sync _|P1, 0xFFFFFFFF;\n"
+        "selp.b32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// warp index as a warp-uniform value
+__device__ __forceinline__ int warp_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
