@@ -186,6 +186,8 @@ def main():
     ap.add_argument("--bs-log2", type=int, default=11)
     ap.add_argument("--samples", type=int, default=32)
     ap.add_argument("--cams", type=int, default=16, help="more than the warp loss's topK = 10 neighbour views")
+    ap.add_argument("--prune-out", default="", help="before training: HashGrid.pruning_tile_grid (hashgrid/__init__.py:138-214) at several "
+                                                    "thresholds on a copy of the field with amplified features; occupancy grids -> npz")
     ap.add_argument("--export-tile", default="", help="after training: TILE.export_tile() (tile.py:510-532), copied to this directory")
     ap.add_argument("--render-tile", default="", help="do not train: render one frame of this exported tile directory through the "
                                                       "reference's rendering.py (RenderingHashGrid.render_rays_base, rendering.py:286-544)")
@@ -193,7 +195,7 @@ def main():
     args = ap.parse_args()
     args.out = os.path.abspath(args.out)
     args.init_in, args.init_out = (os.path.abspath(v) if v else "" for v in (args.init_in, args.init_out))
-    args.export_tile, args.render_tile, args.render_out = (os.path.abspath(v) if v else "" for v in (args.export_tile, args.render_tile, args.render_out))
+    args.export_tile, args.render_tile, args.render_out, args.prune_out = (os.path.abspath(v) if v else "" for v in (args.export_tile, args.render_tile, args.render_out, args.prune_out))
     setup_imports(args.arm)
     import numpy as np
     import torch
@@ -237,6 +239,26 @@ def main():
     if args.init_out:
         torch.save({"table": t.featureGrid.HE.features.detach().cpu(), "decoder": {k: v.cpu() for k, v in t.decoder.state_dict().items()}},
                    args.init_out)
+    if args.prune_out:
+        # occupancy pruning through the tile's own HashGrid (reference code in the reference arm, the drop-in's in the other):
+        # the density of every occupied cell is probed on a lattice, cells whose largest alpha stays under the threshold are
+        # dropped.  A random-init field is nearly uniform, so the features are amplified (same factor in both arms) and
+        # the threshold is swept across the resulting alpha range.
+        hg = t.featureGrid
+        keep = (hg.HE.features.detach().clone(), hg.occupied_grid.clone(), hg.sampler_log2dim.clone(), hg.grid_resolution.clone())
+        grids = {}
+        with torch.no_grad():
+            hg.HE.features.mul_(200.0)
+            for th in (0.3, 0.5, 0.6, 0.7, 0.8, 0.9):
+                hg.occupied_grid, hg.sampler_log2dim = keep[1].clone(), keep[2].clone()
+                hg.pruning_tile_grid(10000, t.decoder, sub_split=False, pruning_th=th, batch_size=32 ** 3)
+                grids[f"th_{th}"] = hg.occupied_grid.detach().cpu().numpy().copy()
+            hg.occupied_grid, hg.sampler_log2dim = keep[1].clone(), keep[2].clone()
+            hg.pruning_tile_grid(10000, t.decoder, sub_split=True, pruning_th=0.6, batch_size=32 ** 3)      # the grid refinement step
+            grids["split_0.6"] = hg.occupied_grid.detach().cpu().numpy().copy()
+            hg.HE.features.copy_(keep[0])
+        hg.occupied_grid, hg.sampler_log2dim, hg.grid_resolution = keep[1], keep[2], keep[3]
+        np.savez(args.prune_out, **grids)
     torch.manual_seed(1234)
     torch.cuda.manual_seed_all(1234)
     t.batch_size = 2 ** cfg.TRAINING.BS_LOG2DIM                # TILE.train sets this (tile.py:761)

@@ -89,3 +89,24 @@ def test_reference_renderer_on_the_dropin_matches_the_reference_extensions(tmp_p
     assert float(np.abs(a["transparency"] - b["transparency"]).max()) <= 1e-4
     c = frames["ref_on_ours"][0]
     assert np.isfinite(c["diffuse"]).all() and np.isfinite(c["depth"]).all(), "a tile exported through the drop-in must be readable by the reference"
+
+
+def test_occupancy_pruning_through_the_reference_tile_matches(tmp_path):
+    """SURVEY 8f-2 pinned to the reference: HashGrid.pruning_tile_grid (hashgrid/__init__.py:138-214) of the reference's own
+    hashgrid package over its CUDA encode, against the drop-in's (density head on the tensor-core decoder), on the same
+    field, swept over thresholds that cut through the alpha range, plus the sub-split refinement step."""
+    import numpy as np
+    _need("ref_drivers.zip", "HASHGRID.so", "CUDA_EXT.so", "fastMesh.so")
+    init = str(tmp_path / "init.pt")
+    _run("reference", str(tmp_path / "r.json"), 1, ["--init-out", init, "--prune-out", str(tmp_path / "r.npz")], tmp_path)
+    _run("dropin", str(tmp_path / "o.json"), 1, ["--init-in", init, "--prune-out", str(tmp_path / "o.npz")], tmp_path)
+    a, b = np.load(str(tmp_path / "r.npz")), np.load(str(tmp_path / "o.npz"))
+    assert set(a.files) == set(b.files)
+    kept = []
+    for k in a.files:
+        assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype, k
+        differ = int((a[k] != b[k]).sum())
+        kept.append(int(a[k].sum()))
+        print(f"{k}: {int(a[k].sum())} / {a[k].size} cells kept by the reference, {differ} differ")
+        assert differ <= max(2, a[k].size // 500), (k, differ)        # cells whose largest alpha sits on the threshold
+    assert min(kept) < max(kept), "the threshold sweep must cut through the alpha range"
