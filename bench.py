@@ -495,7 +495,10 @@ def main():
     import ctypes
     opt = step.featureGrid_optimizer
     fused = bool(getattr(step, "fused_table_update", False)) and hasattr(opt, "begin_fused")
-    capi.time_calls(("snrf_field_encode_fwd", "snrf_field_encode_bwd"))
+    TIMED = ("snrf_field_encode_fwd", "snrf_field_encode_bwd", "snrf_decoder_fwd", "snrf_decoder_bwd", "snrf_composite_fwd",
+             "snrf_composite_bwd", "snrf_field_encode_bwd_adam", "snrf_adam_step", "snrf_sample_grid", "snrf_bg_inverse_z",
+             "snrf_compute_ray_fwd", "snrf_compute_ray_bwd", "snrf_pose_fwd", "snrf_pose_bwd")
+    capi.time_calls(TIMED)
     prof = []
     if fused:
         capi.lib().snrf_field_set_profile(ctypes.c_int(1))
@@ -508,10 +511,14 @@ def main():
     if fused:
         capi.lib().snrf_field_set_profile(ctypes.c_int(0))
     torch.cuda.synchronize()
-    k_ms, k_units = capi.timed_results()
+    by_name = capi.timed_by_name()
     capi.time_calls(None)
     N_pts = B * (cfg["S"] + cfg["S_bg"])
-    fwd_ms = k_ms if fused else k_ms[0::2]
+    fwd_ms = by_name.get("snrf_field_encode_fwd", [])
+    k_ms = by_name.get("snrf_field_encode_bwd", [])
+    # mean CUDA-event time of every C-ABI entry point of the step (one call each per step; the fused backward + update is
+    # timed with its profiling synchronisation on, so its figure here is an upper bound -- roofline has the exact split)
+    kernel_ms = {k: sum(v) / len(v) for k, v in sorted(by_name.items()) if v}
     # touched table floats of one step (what the sparse update moves): entries whose second moment changed
     touched = None
     if hasattr(opt, "params"):
@@ -576,7 +583,7 @@ def main():
         roofline_both = roof("encode backward + table update, the whole snrf_field_encode_bwd_adam sequence as run", phase_ms,
                              ENC_BWD_BYTES * N_pts + 28 * (touched or 0), "encode_bwd_adam")
     else:
-        bwd_only = k_ms[1::2]
+        bwd_only = k_ms
         roofline = roof("field_bwd_kernel (snrf_field_encode_bwd: hash-encode backward)", bwd_only, ENC_BWD_BYTES * N_pts, "snrf_field_encode_bwd")
         roofline_update = roofline_both = None
     roofline_fwd = roof("field_fwd_kernel (snrf_field_encode_fwd: position + contraction + 16-level encode + Jacobian store)",
@@ -600,7 +607,21 @@ def main():
         "clocks": clk,
         "roofline": roofline,
         "roofline_fwd": roofline_fwd,
+        "kernel_ms": kernel_ms,
     }
+    try:
+        tf_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1397.7)
+    except Exception:
+        tf_peak = 1397.7
+    if "snrf_decoder_fwd" in kernel_ms and "snrf_decoder_bwd" in kernel_ms:
+        dec_ms = kernel_ms["snrf_decoder_fwd"] + kernel_ms["snrf_decoder_bwd"]
+        ach = 82368.0 * N_pts / (dec_ms * 1e-3) / 1e12
+        line["roofline_decoder"] = {"kernel": "decoder_fwd4_kernel + grad_absmax_kernel + decoder_bwd_kernel (tcgen05 / TMEM)", "bound": "tensor",
+                                    "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                                    "useful_flop_per_sample": 82368, "fwd_ms": kernel_ms["snrf_decoder_fwd"], "bwd_ms": kernel_ms["snrf_decoder_bwd"],
+                                    "share_of_step": dec_ms / (ms_dev / K / T_res),
+                                    "note": "useful fp32-equivalent FLOPs (SURVEY 8d); the kernels issue 3 fp16 MMAs per product (hi/lo split) "
+                                            "and the backward recomputes the forward, so the tensor pipe does ~4x this"}
     if roofline_update is not None:
         line["roofline_update"] = roofline_update
         line["roofline_bwd_and_update"] = roofline_both

@@ -54,7 +54,7 @@ class _Lib:
                         rc = _raw(*args)
                         b.record()
                         u = args[_UNITS_ARG[_name]] if _name in _UNITS_ARG else 0
-                        _timed_events.append((a, b, int(getattr(u, "value", u))))
+                        _timed_events.append((a, b, int(getattr(u, "value", u)), _name))
                         return rc
                     return _raw(*args)
             self._cache[name] = fn
@@ -72,7 +72,16 @@ def time_calls(name):
 def timed_results():
     """([ms per launch], [units per launch]) of the calls timed since time_calls(name); synchronises."""
     torch.cuda.synchronize()
-    return [a.elapsed_time(b) for a, b, _ in _timed_events], [u for _, _, u in _timed_events]
+    return [a.elapsed_time(b) for a, b, _, _ in _timed_events], [u for _, _, u, _ in _timed_events]
+
+
+def timed_by_name():
+    """{entry point: [ms per call]} of the calls timed since time_calls(names); synchronises."""
+    torch.cuda.synchronize()
+    out = {}
+    for a, b, _, name in _timed_events:
+        out.setdefault(name, []).append(a.elapsed_time(b))
+    return out
 
 
 def lib():
