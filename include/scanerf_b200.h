@@ -89,6 +89,8 @@ void snrf_field_set_overlap(int on);
 /* tuning hooks: run the single-pass coarse levels on a private side stream next to the other levels (default 1);
  * log2 of the entries of one L2-resident slice (default 23) */
 void snrf_field_set_coarse_concurrent(int on);
+/* tuning hook: L2 evict_last cache policy on the scratch accesses of the scatter + update fusion (default 1) */
+void snrf_field_set_l2_hints(int on);
 void snrf_field_set_slice_log2(int bits);
 /* kernels launched by the last snrf_field_encode_bwd_adam call (1 + 2 per table slice) */
 int snrf_field_last_launch_count(void);

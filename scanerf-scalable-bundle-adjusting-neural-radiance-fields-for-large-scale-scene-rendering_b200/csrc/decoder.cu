@@ -337,7 +337,9 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         store8_act<SPLIT>(Thi, chunk0 + cg, Tlo, chunk0 + cg, row, v);
     };
 
-    const bool lead_warp = umma::warp_uniform() == 0;      // the MMAs of this kernel are issued by one elected lane of warp 0
+    // the MMAs of this kernel are issued by one elected lane of warp 4 (column group 1): the warps of column group 0 also
+    // form the head gradients and those of column group 3 the SH backward, so a warp of group 1 / 2 reaches the issue first
+    const bool lead_warp = umma::warp_uniform() == 4;
     bool first = true;      // no tile processed yet: the first one initialises the TMEM gradient accumulators
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n = tile * kRows + row;
@@ -583,13 +585,20 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
 // max |grad_heads| over the live samples, as float bits (non-negative floats order like unsigned integers; a NaN sorts
 // above inf and is treated as "no scale" by the backward)
 __global__ void __launch_bounds__(256)
-grad_absmax_kernel(const float* __restrict__ g, long long n, int S, const unsigned char* __restrict__ ray_valid, unsigned* __restrict__ out)
+grad_absmax_kernel(const float* __restrict__ g, int N, int S, const unsigned char* __restrict__ ray_valid, unsigned* __restrict__ out)
 {
+    // one head row (10 floats = 5 float2) per thread and trip: 32-bit index arithmetic, one division per row
     unsigned m = 0u;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        if (ray_valid != nullptr && !ray_valid[(i / 10) / S]) continue;       // rows of masked-out rays are never written
-        const unsigned b = __float_as_uint(__ldg(g + i)) & 0x7fffffffu;
-        m = b > m ? b : m;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        if (ray_valid != nullptr && !ray_valid[n / S]) continue;              // rows of masked-out rays are never written
+        const float2* row = reinterpret_cast<const float2*>(g + (size_t)n * 10);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const float2 t = __ldg(row + j);
+            const unsigned a = __float_as_uint(t.x) & 0x7fffffffu, b = __float_as_uint(t.y) & 0x7fffffffu;
+            m = a > m ? a : m;
+            m = b > m ? b : m;
+        }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) { const unsigned o = __shfl_xor_sync(0xffffffffu, m, off); m = o > m ? o : m; }
@@ -688,10 +697,9 @@ SNRF_API int snrf_decoder_bwd(const float* feats, const float* mask32, const flo
     unsigned* slot = slots + (g_gmax_next++ & 63);
     cudaMemsetAsync(slot, 0, sizeof(unsigned), s);
     {
-        const long long n = (long long)N * 10;
-        long long gx = (n + 256 * 8 - 1) / (256 * 8);
-        if (gx > (long long)snrf_sm_count() * 8) gx = (long long)snrf_sm_count() * 8;
-        grad_absmax_kernel<<<(int)(gx > 0 ? gx : 1), 256, 0, s>>>(grad_heads, n, S, ray_valid, slot);
+        int gx = snrf_div_up(N, 256 * 4);
+        if (gx > snrf_sm_count() * 8) gx = snrf_sm_count() * 8;
+        grad_absmax_kernel<<<gx > 0 ? gx : 1, 256, 0, s>>>(grad_heads, N, S, ray_valid, slot);
     }
     if (g_split)
         decoder_bwd_kernel<true><<<grid, kThreadsDec, bwd_smem<true>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot);

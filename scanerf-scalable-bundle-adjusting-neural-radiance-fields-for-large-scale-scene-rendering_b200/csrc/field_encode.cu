@@ -404,6 +404,40 @@ field_bwd_runs_kernel(const float* __restrict__ rays_o, const float* __restrict_
 //       traffic: 24 B per touched float), clear the scratch behind it.
 // Semantics = snrf_field_encode_bwd into a zeroed gradient table followed by snrf_adam_step(zero_grad = 1).
 // =====================================================================================================================
+
+// L2 residency hints for the scratch of the scatter + update fusion: reductions into it and the Adam pass's read / clear of
+// it carry an evict_last cache policy, the streams that pass by once (gradients, p / m / v) an evict-first one, so that the
+// 64 MiB slice being reduced into is what the L2 keeps (without hints a fine-level slice wrote 95 MB to and re-read 68 MB
+// from DRAM per scatter, and the Adam pass fetched its 67 MB again: profiles/r2d_fused_bwd_full.md).
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void red_add2(float2* a, float x, float y, uint64_t pol, bool hint)
+{
+    if (hint) asm volatile("red.global.add.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(a), "f"(x), "f"(y), "l"(pol) : "memory");
+    else atomicAdd(a, make_float2(x, y));
+}
+__device__ __forceinline__ void red_add4(float4* a, float x, float y, float z, float w, uint64_t pol, bool hint)
+{
+    if (hint) asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(a), "f"(x), "f"(y), "f"(z), "f"(w), "l"(pol) : "memory");
+    else atomicAdd(a, make_float4(x, y, z, w));
+}
+__device__ __forceinline__ float4 ld4_hint(const float4* a, uint64_t pol, bool hint)
+{
+    float4 v;
+    if (hint) asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a), "l"(pol));
+    else v = __ldcg(a);
+    return v;
+}
+__device__ __forceinline__ void st4_hint(float4* a, float4 v, uint64_t pol, bool hint)
+{
+    if (hint) asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+    else *a = v;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 field_geom_raygrad_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_vals,
@@ -485,9 +519,12 @@ field_geom_raygrad_kernel(const float* __restrict__ rays_o, const float* __restr
 // Reads only cpts (12 B) and the incoming gradient (8 B) per sample and level.
 __global__ void __launch_bounds__(kThreads)
 field_scatter_slice_kernel(const float* __restrict__ cpts, const int* __restrict__ res, const float2* __restrict__ grad,
-                           float2* __restrict__ scratch, int N, int l0, uint32_t T, uint32_t pass, int range_shift, int aggregate_levels)
+                           float2* __restrict__ scratch, int N, int l0, uint32_t T, uint32_t pass, int range_shift, int aggregate_levels,
+                           int l2_hints)
 {
     const uint32_t mask = T - 1u;
+    const bool hint = l2_hints != 0;
+    const uint64_t pol = l2_policy_evict_last();
     const uint32_t slice_mask = (1u << range_shift) - 1u;
     const int lane = threadIdx.x & 31;
     const int l = l0 + blockIdx.y;
@@ -542,7 +579,7 @@ field_scatter_slice_kernel(const float* __restrict__ cpts, const int* __restrict
                 if (head && live) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        if ((idx[k] >> range_shift) == pass) atomicAdd(gl + (idx[k] & slice_mask), make_float2(vx[k], vy[k]));
+                        if ((idx[k] >> range_shift) == pass) red_add2(gl + (idx[k] & slice_mask), vx[k], vy[k], pol, hint);
                 }
                 done = true;
             }
@@ -556,12 +593,13 @@ field_scatter_slice_kernel(const float* __restrict__ cpts, const int* __restrict
                 if ((i0 ^ i1) == 1u) {
                     if ((i0 >> range_shift) == pass) {
                         const bool swap = (i0 & 1u) != 0u;
-                        atomicAdd(reinterpret_cast<float4*>(gl + ((i0 & slice_mask) & ~1u)),
-                                  swap ? make_float4(v1.x, v1.y, v0.x, v0.y) : make_float4(v0.x, v0.y, v1.x, v1.y));
+                        float4* dst = reinterpret_cast<float4*>(gl + ((i0 & slice_mask) & ~1u));
+                        if (swap) red_add4(dst, v1.x, v1.y, v0.x, v0.y, pol, hint);
+                        else red_add4(dst, v0.x, v0.y, v1.x, v1.y, pol, hint);
                     }
                 } else {
-                    if ((i0 >> range_shift) == pass) atomicAdd(gl + (i0 & slice_mask), v0);
-                    if ((i1 >> range_shift) == pass) atomicAdd(gl + (i1 & slice_mask), v1);
+                    if ((i0 >> range_shift) == pass) red_add2(gl + (i0 & slice_mask), v0.x, v0.y, pol, hint);
+                    if ((i1 >> range_shift) == pass) red_add2(gl + (i1 & slice_mask), v1.x, v1.y, pol, hint);
                 }
             }
         }
@@ -573,8 +611,10 @@ field_scatter_slice_kernel(const float* __restrict__ cpts, const int* __restrict
 // (cuda/adam_kernel.cu:43-51).
 __global__ void __launch_bounds__(kThreads)
 adam_slice_kernel(float4* __restrict__ p4, float4* __restrict__ m4, float4* __restrict__ v4, float4* __restrict__ g4, long long n4,
-                  adamcore::Hyper h)
+                  adamcore::Hyper h, int l2_hints)
 {
+    const bool hint = l2_hints != 0;
+    const uint64_t pol = l2_policy_evict_last();
     __shared__ float s_bc[2];
     if (threadIdx.x == 0) {
         s_bc[0] = 1.0f - powf(h.b1, (float)h.step);
@@ -590,13 +630,13 @@ adam_slice_kernel(float4* __restrict__ p4, float4* __restrict__ m4, float4* __re
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const long long i = base + (long long)u * blockDim.x;
-            gg[u] = i < n4 ? __ldcg(g4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gg[u] = i < n4 ? ld4_hint(g4 + i, pol, hint) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const long long i = base + (long long)u * blockDim.x;
             act[u] = !(gg[u].x == 0.0f && gg[u].y == 0.0f && gg[u].z == 0.0f && gg[u].w == 0.0f);
-            if (act[u]) { pp[u] = p4[i]; mm[u] = m4[i]; vv[u] = v4[i]; }
+            if (act[u]) { pp[u] = __ldcs(p4 + i); mm[u] = __ldcs(m4 + i); vv[u] = __ldcs(v4 + i); }
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
@@ -609,7 +649,7 @@ adam_slice_kernel(float4* __restrict__ p4, float4* __restrict__ m4, float4* __re
             __stcs(p4 + i, pp[u]);          // streaming: p / m / v are not read again this step; the scratch should stay in L2
             __stcs(m4 + i, mm[u]);
             __stcs(v4 + i, vv[u]);
-            g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            st4_hint(g4 + i, make_float4(0.f, 0.f, 0.f, 0.f), pol, hint);
         }
     }
 }
@@ -633,6 +673,7 @@ int g_aggregate_override = -1;
 int g_run_length = 0;
 int g_levels_per_group = 0;
 long long g_slice_cap = 1ll << 23;      // entries of one fine slice (64 MiB of gradient: what stays L2-resident while it is reduced into)
+int g_l2_hints = 1;                    // evict_last policy on the scratch accesses of the scatter + update fusion (see l2_policy_evict_last)
 int g_coarse_concurrent = 1;           // the single-pass coarse levels run on a side stream next to the fine chain
 int g_last_launches = 0;       // kernels launched by the last snrf_field_encode_bwd_adam call
 int g_profile = 0;             // snrf_field_encode_bwd_adam: time the three kernel classes with CUDA events (synchronises!)
@@ -675,6 +716,7 @@ SNRF_API int snrf_field_last_launch_count() { return g_last_launches; }
 SNRF_API void snrf_field_set_profile(int on) { g_profile = on ? 1 : 0; }
 SNRF_API void snrf_field_last_profile(float* out4) { for (int i = 0; i < 4; ++i) out4[i] = g_profile_ms[i]; }
 SNRF_API void snrf_field_set_overlap(int on) { g_overlap = on ? 1 : 0; }
+SNRF_API void snrf_field_set_l2_hints(int on) { g_l2_hints = on ? 1 : 0; }
 SNRF_API void snrf_field_set_coarse_concurrent(int on) { g_coarse_concurrent = on ? 1 : 0; }
 SNRF_API void snrf_field_set_slice_log2(int bits) { g_slice_cap = 1ll << (bits < 2 ? 2 : (bits > 30 ? 30 : bits)); }
 SNRF_API void snrf_field_set_levels_per_group(int n) { g_levels_per_group = n > 0 ? n : 0; }
@@ -848,7 +890,7 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
         const long long n4 = (long long)nl * entries / 2;                                // float4 groups (two entries each)
         long long gx = (n4 + kThreads * 2 - 1) / (kThreads * 2);
         if (gx > (long long)sms * 16) gx = (long long)sms * 16;
-        adam_slice_kernel<<<(int)gx, kThreads, 0, st>>>((float4*)(table + base), (float4*)(exp_avg + base), (float4*)(exp_avg_sq + base), (float4*)buf, n4, h);
+        adam_slice_kernel<<<(int)gx, kThreads, 0, st>>>((float4*)(table + base), (float4*)(exp_avg + base), (float4*)(exp_avg_sq + base), (float4*)buf, n4, h, g_l2_hints);
     };
 
     mark(-1);
@@ -868,7 +910,7 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
             sc = side->stream;
         }
         for (int l = 0; l < small_levels; ++l) {
-            field_scatter_slice_kernel<<<dim3(grid_x(N), 1), kThreads, 0, sc>>>(cpts_scratch, res, g, (float2*)coarse_buf, N, l, (uint32_t)T, 0u, log2T, agg);
+            field_scatter_slice_kernel<<<dim3(grid_x(N), 1), kThreads, 0, sc>>>(cpts_scratch, res, g, (float2*)coarse_buf, N, l, (uint32_t)T, 0u, log2T, agg, g_l2_hints);
             if (!coarse_on_side) mark(1);
             adam_launch(sc, coarse_buf, l, 1, 0, T);
             if (!coarse_on_side) mark(2);
@@ -885,7 +927,7 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
             const int b = overlap ? (k & 1) : 0;
             float* buf = fine_buf + (size_t)b * capacity * 2;
             if (overlap && k >= 2) cudaStreamWaitEvent(s, side->adam[b], 0);         // the half is free again
-            field_scatter_slice_kernel<<<dim3(grid_x(N), nl), kThreads, 0, s>>>(cpts_scratch, res, g, (float2*)buf, N, l0, (uint32_t)T, (uint32_t)pass, range_shift, agg);
+            field_scatter_slice_kernel<<<dim3(grid_x(N), nl), kThreads, 0, s>>>(cpts_scratch, res, g, (float2*)buf, N, l0, (uint32_t)T, (uint32_t)pass, range_shift, agg, g_l2_hints);
             mark(1);
             cudaStream_t sa = s;
             if (overlap) {
