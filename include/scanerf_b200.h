@@ -196,7 +196,7 @@ void snrf_decoder_set_inflight(int n);
  * shapes/order of params, ACCUMULATED.  The forward is recomputed per 128-sample tile. */
 int snrf_decoder_bwd(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
                      const float* grad_heads, float* grad_feats, float* grad_rays_d, float* const* grad_params,
-                     int N, int S, int level_major, const unsigned char* ray_valid, void* stream);
+                     int N, int S, int level_major, const unsigned char* ray_valid, const float* heads_fwd, void* stream);
 
 /* ---- view selection, neighbour projection, image sampling ------------------------ */
 /* cuda/include/view_selection.h (computeViewcost; kernel cuda/view_selection_kernel.cu:18-76):

@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(kThreadsDec, 1)
 decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ mask32, const float* __restrict__ rays_d,
                    DecoderParams p, const float* __restrict__ grad_heads, float* __restrict__ grad_feats,
                    float* __restrict__ grad_rays_d, DecoderGrads gp, int N, int S, int num_tiles, long long level_stride,
-                   const unsigned char* __restrict__ ray_valid, const unsigned* __restrict__ gmax_bits)
+                   const unsigned char* __restrict__ ray_valid, const unsigned* __restrict__ gmax_bits,
+                   const float* __restrict__ heads_fwd)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -348,7 +349,12 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         float head[10], zh[7];
         f3 d = mk3(0.f, 0.f, 1.f);
         float dn = 1.0f;
-        forward_tile<SPLIT, true, 4>(c, T, feats, rays_d, n, live, S, head, zh, d, dn, level_stride);
+        // with the forward's head values at hand (heads_fwd) the recompute stops after layer 4: one dependent stage less
+        const bool have_heads = heads_fwd != nullptr;
+        forward_tile<SPLIT, true, 4>(c, T, feats, rays_d, n, live, S, head, zh, d, dn, level_stride, !have_heads);
+        // (the L4 epilogue of every column group wrote a4_lo into the tile the head gradients go to next: without the L5
+        // stage in between, order those stores before column group 0 overwrites the rows)
+        if (have_heads) c.sync();
 
         // ---- d(loss)/d(pre-activations) of the 7 heads and the 3 specular outputs (column group 0)
         if (cg == 0) {
@@ -362,18 +368,37 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
 #pragma unroll
                 for (int j = 0; j < 10; ++j) gh[j] = 0.0f;
             }
-            float z[16];
-            umma::tmem_ld16(tmem + cDh + lane_addr, z);
-            umma::tc_wait_ld();
+            float spec[3], dsig;
+            if (have_heads) {
+                // activations as the forward stored them: sigma = softplus(z) -> softplus' = sigmoid(z) = 1 - exp(-sigma)
+                float hv[10];
+                if (live) {
+                    const float2* hsrc = reinterpret_cast<const float2*>(heads_fwd + (size_t)n * 10);
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) { const float2 t = __ldg(hsrc + j); hv[2 * j] = t.x; hv[2 * j + 1] = t.y; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) hv[j] = 0.0f;
+                }
+                dsig = hv[0] > 20.0f ? 1.0f : -expm1f(-hv[0]);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { head[1 + j] = hv[1 + j]; head[4 + j] = hv[4 + j]; spec[j] = hv[7 + j]; }
+            } else {
+                float z[16];
+                umma::tmem_ld16(tmem + cDh + lane_addr, z);
+                umma::tc_wait_ld();
+                dsig = zh[0] > 20.0f ? 1.0f : sigmoidf(zh[0]);                  // softplus' = sigmoid
+#pragma unroll
+                for (int j = 0; j < 3; ++j) spec[j] = sigmoidf(z[j] + bias[oB5 + j]);
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) { dzh[j] = 0.0f; dzs[j] = 0.0f; }
-            dzh[0] = gh[0] * (zh[0] > 20.0f ? 1.0f : sigmoidf(zh[0]));          // softplus' = sigmoid
+            dzh[0] = gh[0] * dsig;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 dzh[1 + j] = gh[4 + j] * head[4 + j] * (1.0f - head[4 + j]);    // diffuse
                 dzh[4 + j] = gh[1 + j] * head[1 + j] * (1.0f - head[1 + j]);    // tint
-                const float s = sigmoidf(z[j] + bias[oB5 + j]);
-                dzs[j] = gh[7 + j] * s * (1.0f - s);                            // specular
+                dzs[j] = gh[7 + j] * spec[j] * (1.0f - spec[j]);                // specular
             }
             // Tdz = [dz_heads 0..15 | dz_spec 16..31 | dz_heads_lo 32..47 | dz_spec_lo 48..63]
             store8_act<SPLIT>(Tdz, 0, Tdz, 4, row, dzh);
@@ -663,13 +688,14 @@ SNRF_API int snrf_decoder_fwd(const float* feats, const float* mask32, const flo
     SNRF_RETURN_LAUNCH("snrf_decoder_fwd");
 }
 
-// Backward of snrf_decoder_fwd.  grad_heads[N,10] (same column order as heads) ->
+// Backward of snrf_decoder_fwd.  heads_fwd: the [N,10] output of the forward (NULL: recomputed; with it the per-tile
+// recompute skips the last layer).  grad_heads[N,10] (same column order as heads) ->
 // grad_feats[N,32] (WRITTEN), grad_rays_d[R,3] (ACCUMULATED; may be NULL: the view direction
 // only enters through the SH encoding), grad_params = HOST array of 16 DEVICE pointers,
 // same order and shapes as params (ACCUMULATED).
 SNRF_API int snrf_decoder_bwd(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
                               const float* grad_heads, float* grad_feats, float* grad_rays_d, float* const* grad_params,
-                              int N, int S, int level_major, const unsigned char* ray_valid, void* stream)
+                              int N, int S, int level_major, const unsigned char* ray_valid, const float* heads_fwd, void* stream)
 {
     SNRF_CHECK_ARG(N >= 0 && S > 0, "snrf_decoder_bwd: need N >= 0, S > 0 (N=%d S=%d)", N, S);
     SNRF_CHECK_ARG(params != nullptr && grad_params != nullptr, "snrf_decoder_bwd: params and grad_params are required");
@@ -702,8 +728,8 @@ SNRF_API int snrf_decoder_bwd(const float* feats, const float* mask32, const flo
         grad_absmax_kernel<<<gx > 0 ? gx : 1, 256, 0, s>>>(grad_heads, N, S, ray_valid, slot);
     }
     if (g_split)
-        decoder_bwd_kernel<true><<<grid, kThreadsDec, bwd_smem<true>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot);
+        decoder_bwd_kernel<true><<<grid, kThreadsDec, bwd_smem<true>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot, heads_fwd);
     else
-        decoder_bwd_kernel<false><<<grid, kThreadsDec, bwd_smem<false>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot);
+        decoder_bwd_kernel<false><<<grid, kThreadsDec, bwd_smem<false>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot, heads_fwd);
     SNRF_RETURN_LAUNCH("snrf_decoder_bwd");
 }

@@ -333,8 +333,10 @@ __device__ __forceinline__ void store_input_row(const Tiles& T, int row, int cg,
 // A0 / LOb.  Writes the operand tiles; the threads with cg == 0 return sigma/diffuse/tint activated in
 // head[0..6] (torch semantics) and their pre-activations in zh[0..6]; the specular pre-activations are
 // left in TMEM columns cDh..cDh+2.
+// with_l5 = false (backward, when the forward's head values are at hand): stop after the L4 epilogue -- the last layer's
+// output is only needed for the specular sigmoid, whose derivative follows from the saved head value.
 template <bool SPLIT, bool TRAIN, int NCG>
-__device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& T, float* head, float* zh)
+__device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& T, float* head, float* zh, bool with_l5 = true)
 {
     constexpr int W = 64 / NCG, CH = W / 8;
     unsigned char* smem = c.smem;
@@ -419,6 +421,7 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
     }
     c.wait_mma();
     gauss_epilogue(cDb, oB4, T.a4, T.LOb, T.g4);
+    if (!with_l5) return;
     c.sync_operands();
     // ---- L5: Dh = a4 W5^T (K = 64, N = 16)
     if (c.leader()) {
@@ -434,7 +437,7 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
 template <bool SPLIT, bool TRAIN, int NCG>
 __device__ __forceinline__ void forward_tile(Ctx<SPLIT, NCG>& c, const Tiles& T, const float* __restrict__ feats,
                                              const float* __restrict__ rays_d, int n, bool live, int S, float* head, float* zh,
-                                             f3& d, float& dn, long long level_stride)
+                                             f3& d, float& dn, long long level_stride, bool with_l5 = true)
 {
     constexpr int NX = 32 / NCG;                // features per thread
     const float* mask = c.mask;
@@ -470,7 +473,7 @@ __device__ __forceinline__ void forward_tile(Ctx<SPLIT, NCG>& c, const Tiles& T,
         }
     }
     store_input_row<SPLIT, NCG>(T, c.row, cg, x, sh + 8 * (shc & 1));
-    forward_layers<SPLIT, TRAIN, NCG>(c, T, head, zh);
+    forward_layers<SPLIT, TRAIN, NCG>(c, T, head, zh, with_l5);
 }
 
 // =====================================================================================================================

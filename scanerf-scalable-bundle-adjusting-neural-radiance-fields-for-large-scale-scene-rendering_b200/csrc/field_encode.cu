@@ -517,13 +517,13 @@ field_geom_raygrad_kernel(const float* __restrict__ rays_o, const float* __restr
 // Scatter of levels [l0, l0 + gridDim.y), index range `pass` (of 1 << pass_bits per level), into the scratch:
 // entry idx of level l lands at scratch[(l - l0) * slice + (idx & (slice - 1))], slice = T >> pass_bits.
 // Reads only cpts (12 B) and the incoming gradient (8 B) per sample and level.
+template <bool HINT>
 __global__ void __launch_bounds__(kThreads)
 field_scatter_slice_kernel(const float* __restrict__ cpts, const int* __restrict__ res, const float2* __restrict__ grad,
-                           float2* __restrict__ scratch, int N, int l0, uint32_t T, uint32_t pass, int range_shift, int aggregate_levels,
-                           int l2_hints)
+                           float2* __restrict__ scratch, int N, int l0, uint32_t T, uint32_t pass, int range_shift, int aggregate_levels)
 {
     const uint32_t mask = T - 1u;
-    const bool hint = l2_hints != 0;
+    constexpr bool hint = HINT;
     const uint64_t pol = l2_policy_evict_last();
     const uint32_t slice_mask = (1u << range_shift) - 1u;
     const int lane = threadIdx.x & 31;
@@ -609,11 +609,12 @@ field_scatter_slice_kernel(const float* __restrict__ cpts, const int* __restrict
 // Adam over one contiguous slice of the table: n4 float4 groups (two entries each) of p / m / v starting at the slice
 // base, gradient from the scratch (cleared behind the read).  Elements whose gradient is exactly zero are skipped
 // (cuda/adam_kernel.cu:43-51).
+template <bool HINT>
 __global__ void __launch_bounds__(kThreads)
 adam_slice_kernel(float4* __restrict__ p4, float4* __restrict__ m4, float4* __restrict__ v4, float4* __restrict__ g4, long long n4,
-                  adamcore::Hyper h, int l2_hints)
+                  adamcore::Hyper h)
 {
-    const bool hint = l2_hints != 0;
+    constexpr bool hint = HINT;
     const uint64_t pol = l2_policy_evict_last();
     __shared__ float s_bc[2];
     if (threadIdx.x == 0) {
@@ -636,7 +637,8 @@ adam_slice_kernel(float4* __restrict__ p4, float4* __restrict__ m4, float4* __re
         for (int u = 0; u < kUnroll; ++u) {
             const long long i = base + (long long)u * blockDim.x;
             act[u] = !(gg[u].x == 0.0f && gg[u].y == 0.0f && gg[u].z == 0.0f && gg[u].w == 0.0f);
-            if (act[u]) { pp[u] = __ldcs(p4 + i); mm[u] = __ldcs(m4 + i); vv[u] = __ldcs(v4 + i); }
+            // (plain loads: evict-first hints on p / m / v were measured slower, 1.69 -> 2.2 ms per step)
+            if (act[u]) { pp[u] = p4[i]; mm[u] = m4[i]; vv[u] = v4[i]; }
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
@@ -890,7 +892,8 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
         const long long n4 = (long long)nl * entries / 2;                                // float4 groups (two entries each)
         long long gx = (n4 + kThreads * 2 - 1) / (kThreads * 2);
         if (gx > (long long)sms * 16) gx = (long long)sms * 16;
-        adam_slice_kernel<<<(int)gx, kThreads, 0, st>>>((float4*)(table + base), (float4*)(exp_avg + base), (float4*)(exp_avg_sq + base), (float4*)buf, n4, h, g_l2_hints);
+        if (g_l2_hints) adam_slice_kernel<true><<<(int)gx, kThreads, 0, st>>>((float4*)(table + base), (float4*)(exp_avg + base), (float4*)(exp_avg_sq + base), (float4*)buf, n4, h);
+        else adam_slice_kernel<false><<<(int)gx, kThreads, 0, st>>>((float4*)(table + base), (float4*)(exp_avg + base), (float4*)(exp_avg_sq + base), (float4*)buf, n4, h);
     };
 
     mark(-1);
@@ -910,7 +913,8 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
             sc = side->stream;
         }
         for (int l = 0; l < small_levels; ++l) {
-            field_scatter_slice_kernel<<<dim3(grid_x(N), 1), kThreads, 0, sc>>>(cpts_scratch, res, g, (float2*)coarse_buf, N, l, (uint32_t)T, 0u, log2T, agg, g_l2_hints);
+            if (g_l2_hints) field_scatter_slice_kernel<true><<<dim3(grid_x(N), 1), kThreads, 0, sc>>>(cpts_scratch, res, g, (float2*)coarse_buf, N, l, (uint32_t)T, 0u, log2T, agg);
+            else field_scatter_slice_kernel<false><<<dim3(grid_x(N), 1), kThreads, 0, sc>>>(cpts_scratch, res, g, (float2*)coarse_buf, N, l, (uint32_t)T, 0u, log2T, agg);
             if (!coarse_on_side) mark(1);
             adam_launch(sc, coarse_buf, l, 1, 0, T);
             if (!coarse_on_side) mark(2);
@@ -927,7 +931,8 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
             const int b = overlap ? (k & 1) : 0;
             float* buf = fine_buf + (size_t)b * capacity * 2;
             if (overlap && k >= 2) cudaStreamWaitEvent(s, side->adam[b], 0);         // the half is free again
-            field_scatter_slice_kernel<<<dim3(grid_x(N), nl), kThreads, 0, s>>>(cpts_scratch, res, g, (float2*)buf, N, l0, (uint32_t)T, (uint32_t)pass, range_shift, agg, g_l2_hints);
+            if (g_l2_hints) field_scatter_slice_kernel<true><<<dim3(grid_x(N), nl), kThreads, 0, s>>>(cpts_scratch, res, g, (float2*)buf, N, l0, (uint32_t)T, (uint32_t)pass, range_shift, agg);
+            else field_scatter_slice_kernel<false><<<dim3(grid_x(N), nl), kThreads, 0, s>>>(cpts_scratch, res, g, (float2*)buf, N, l0, (uint32_t)T, (uint32_t)pass, range_shift, agg);
             mark(1);
             cudaStream_t sa = s;
             if (overlap) {

@@ -66,13 +66,13 @@ class DecoderFn(torch.autograd.Function):
         ctx.S = int(S)
         ctx.has_mask, ctx.has_valid = mask32 is not None, valid is not None
         ctx.save_for_backward(feats, rays_d, mask32 if mask32 is not None else feats.new_empty(0),
-                              valid if valid is not None else feats.new_empty(0), *params)
+                              valid if valid is not None else feats.new_empty(0), heads, *params)
         return heads
 
     @staticmethod
     def backward(ctx, g_heads):
-        feats, rays_d, mask32, valid = ctx.saved_tensors[:4]
-        params = ctx.saved_tensors[4:]
+        feats, rays_d, mask32, valid, heads = ctx.saved_tensors[:5]
+        params = ctx.saved_tensors[5:]
         N, lm = _layout(feats)
         g_heads = g_heads.contiguous()
         g_feats = torch.empty_like(feats)
@@ -87,7 +87,7 @@ class DecoderFn(torch.autograd.Function):
         garr = (ctypes.c_void_p * 16)(*[g.data_ptr() for g in g_params])
         m = mask32.contiguous() if ctx.has_mask else None
         rc = capi.lib().snrf_decoder_bwd(ptr(feats), ptr(m), ptr(rays_d), arr, ptr(g_heads), ptr(g_feats), ptr(g_d), garr,
-                                         c_int(N), c_int(ctx.S), c_int(lm), ptr(valid) if ctx.has_valid else c_void_p(0), capi.stream())
+                                         c_int(N), c_int(ctx.S), c_int(lm), ptr(valid) if ctx.has_valid else c_void_p(0), ptr(heads), capi.stream())
         capi.check(rc, "snrf_decoder_bwd")
         return (g_feats, g_d, None, None, None) + tuple(g_params)
 
