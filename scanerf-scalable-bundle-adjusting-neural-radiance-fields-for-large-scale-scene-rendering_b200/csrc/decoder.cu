@@ -38,6 +38,13 @@ using namespace dec;
 
 namespace {
 
+// Weight-gradient GEMMs dW += dz^T a: the activation operand can only be read as its fp16 hi part (11 bits; its lo tile is
+// recycled by then).  With kWgradDzLo the dz operand is compensated (hi + lo: two MMA groups per layer); without it dz is
+// read as hi only as well -- the two roundings are then symmetric (both 2^-12, unbiased, independent per sample), the
+// weight-gradient error grows by ~sqrt(2) (measured: see tests/test_decoder_gpu.py) and half of the backward's
+// weight-gradient MMAs disappear, together with the one group that had to sit in front of a commit.
+constexpr bool kWgradDzLo = false;
+
 // ------------------------------- forward ------------------------------------
 // feats [N,32] f32, rays_d [R,3] (sample n belongs to ray n / S), out [N,10] f32 =
 // (sigma, tint3, diffuse3, specular3).
@@ -296,13 +303,13 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     };
     auto wgrad = [&](int col, uint32_t a_tile, uint32_t a_lo, uint32_t b_tile_plus_off, uint32_t idesc, bool first) {
         wgrad_part(col, a_tile, b_tile_plus_off, idesc, first);
-        if (SPLIT) wgrad_part(col, a_lo, b_tile_plus_off, idesc, false);
+        if (SPLIT && kWgradDzLo) wgrad_part(col, a_lo, b_tile_plus_off, idesc, false);
     };
     // transposed narrow layers (dW^T += A^T dz): the compensated operand is B
     auto wgrad_t = [&](int col, uint32_t a_tile, uint32_t b_hi, uint32_t b_lo, uint32_t idesc, bool first) {
         for (int k = 0; k < 8; ++k)
             umma::mma_bf16(tmem + col, umma::desc_mnmajor(a_tile, k), umma::desc_mnmajor(b_hi, k), idesc, (!first) || k > 0);
-        if (SPLIT)
+        if (SPLIT && kWgradDzLo)
             for (int k = 0; k < 8; ++k)
                 umma::mma_bf16(tmem + col, umma::desc_mnmajor(a_tile, k), umma::desc_mnmajor(b_lo, k), idesc, 1);
     };
@@ -425,9 +432,9 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         if (lead_warp && umma::elect_one()) {
             dgrad(cDb, ag4, 0, adzlo, 0, aW4, aW4l, 4, idg64);
             // the epilogue overwrites the dz lo tile: its part goes in front of the commit, the hi part behind it
-            if (SPLIT) wgrad_part(cGW4, adzlo, aa3, idw64, first);
+            if (SPLIT && kWgradDzLo) wgrad_part(cGW4, adzlo, aa3, idw64, first);
             umma::mma_commit(&bar);
-            wgrad_part(cGW4, ag4, aa3, idw64, SPLIT ? false : first);
+            wgrad_part(cGW4, ag4, aa3, idw64, (SPLIT && kWgradDzLo) ? false : first);
         }
         c.wait_mma();                                            // (covers the B1 weight-gradient MMAs that read Tdz and a4)
         store_quarter(cDc, Tdz, Tdhlo, 0, acc_b2);               // dH[0:32] -> dz2 tile columns 0..31 (over the consumed dz_heads/spec)
