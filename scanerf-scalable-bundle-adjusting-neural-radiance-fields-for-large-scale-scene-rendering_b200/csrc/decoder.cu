@@ -38,6 +38,8 @@ using namespace dec;
 
 namespace {
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // Weight-gradient GEMMs dW += dz^T a: the activation operand can only be read as its fp16 hi part (11 bits; its lo tile is
 // recycled by then).  With kWgradDzLo the dz operand is compensated (hi + lo: two MMA groups per layer); without it dz is
 // read as hi only as well -- the two roundings are then symmetric (both 2^-12, unbiased, independent per sample), the
@@ -224,6 +226,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint32_t tail_phase = 0;
+    bool tail_pending = false;
     // Power-of-two scale of the incoming gradient: max |grad_heads| (bits in *gmax_bits, from grad_absmax_kernel) is
     // mapped into [0.5, 1), so that the fp16 dz operands keep 15 binary orders of headroom above it for the growth along
     // the backward chain and 14 (24 with subnormals) below it.  Everything downstream is linear in the gradient:
@@ -358,7 +361,25 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         float dn = 1.0f;
         // with the forward's head values at hand (heads_fwd) the recompute stops after layer 4: one dependent stage less
         const bool have_heads = heads_fwd != nullptr;
-        forward_tile<SPLIT, true, 4>(c, T, feats, rays_d, n, live, S, head, zh, d, dn, level_stride, !have_heads);
+        // L2 prefetches: this tile's head gradients / head values (needed five stages from now) and the next tile's features
+        if (cg == 0 && live) {
+            prefetch_l2(grad_heads + (size_t)n * 10);
+            prefetch_l2(grad_heads + (size_t)n * 10 + 8);
+            if (have_heads) { prefetch_l2(heads_fwd + (size_t)n * 10); prefetch_l2(heads_fwd + (size_t)n * 10 + 8); }
+        }
+        {
+            const long long nn = (long long)(tile + gridDim.x) * kRows + row;
+            if (nn < N) {
+                if (level_stride == 0) prefetch_l2(feats + (size_t)nn * 32 + 8 * cg);
+                else {
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) if ((row & 3) == 0) prefetch_l2(reinterpret_cast<const float2*>(feats) + nn + (size_t)(4 * cg + l) * level_stride);
+                }
+            }
+        }
+        forward_tile<SPLIT, true, 4>(c, T, feats, rays_d, n, live, S, head, zh, d, dn, level_stride, !have_heads,
+                                     tail_pending ? &bar_tail : nullptr, tail_phase);
+        if (tail_pending) { tail_phase ^= 1u; tail_pending = false; }
         // (the L4 epilogue of every column group wrote a4_lo into the tile the head gradients go to next: without the L5
         // stage in between, order those stores before column group 0 overwrites the rows)
         if (have_heads) c.sync();
@@ -534,11 +555,14 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
                 for (int l = 0; l < 4; ++l) dst[(size_t)(4 * cg + l) * level_stride] = make_float2(v[2 * l], v[2 * l + 1]);
             }
         }
-        // the next tile overwrites the operand tiles the trailing weight-gradient MMAs read: wait for them
-        umma::mbar_wait(&bar_tail, tail_phase);
-        tail_phase ^= 1u;
-        umma::tc_fence_after();
+        // the next tile overwrites the operand tiles the trailing weight-gradient MMAs read: they are waited for inside the
+        // next forward_tile (after its global loads), or right after the loop
+        tail_pending = true;
         first = false;
+    }
+    if (tail_pending) {
+        umma::mbar_wait(&bar_tail, tail_phase);
+        umma::tc_fence_after();
     }
 
     // ================= flush the weight / bias gradients accumulated in TMEM =================

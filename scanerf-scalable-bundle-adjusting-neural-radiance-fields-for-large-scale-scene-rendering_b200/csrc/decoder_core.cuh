@@ -437,7 +437,8 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
 template <bool SPLIT, bool TRAIN, int NCG>
 __device__ __forceinline__ void forward_tile(Ctx<SPLIT, NCG>& c, const Tiles& T, const float* __restrict__ feats,
                                              const float* __restrict__ rays_d, int n, bool live, int S, float* head, float* zh,
-                                             f3& d, float& dn, long long level_stride, bool with_l5 = true)
+                                             f3& d, float& dn, long long level_stride, bool with_l5 = true,
+                                             uint64_t* pending_bar = nullptr, uint32_t pending_phase = 0)
 {
     constexpr int NX = 32 / NCG;                // features per thread
     const float* mask = c.mask;
@@ -471,6 +472,12 @@ __device__ __forceinline__ void forward_tile(Ctx<SPLIT, NCG>& c, const Tiles& T,
             const float inv = 1.0f / (dn + 1e-8f);
             sh16(d.x * inv, d.y * inv, d.z * inv, sh);
         }
+    }
+    // (backward: the previous tile's trailing weight-gradient MMAs still read the operand tiles; they are waited for HERE,
+    // after this tile's global loads have been issued, so the two latencies overlap)
+    if (pending_bar != nullptr) {
+        umma::mbar_wait(pending_bar, pending_phase);
+        umma::tc_fence_after();
     }
     store_input_row<SPLIT, NCG>(T, c.row, cg, x, sh + 8 * (shc & 1));
     forward_layers<SPLIT, TRAIN, NCG>(c, T, head, zh, with_l5);
