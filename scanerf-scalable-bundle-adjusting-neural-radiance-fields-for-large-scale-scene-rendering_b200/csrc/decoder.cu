@@ -38,8 +38,6 @@ using namespace dec;
 
 namespace {
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // Weight-gradient GEMMs dW += dz^T a: the activation operand can only be read as its fp16 hi part (11 bits; its lo tile is
 // recycled by then).  With kWgradDzLo the dz operand is compensated (hi + lo: two MMA groups per layer); without it dz is
 // read as hi only as well -- the two roundings are then symmetric (both 2^-12, unbiased, independent per sample), the
@@ -145,6 +143,16 @@ decoder_fwd4_kernel(const float* __restrict__ feats, const float* __restrict__ m
         const int n0 = tile * kRows, n = n0 + c.row;
         const bool live = n < N && (ray_valid == nullptr || ray_valid[n / S] != 0);
         if (ray_valid != nullptr && !c.any(live)) continue;     // every sample of the tile belongs to a masked-out ray
+        {   // L2 prefetch of this group's next tile (one 32-byte sector holds four rows of a level)
+            const long long nn = (long long)(tile + kGroups4 * gridDim.x) * kRows + c.row;
+            if (nn < N) {
+                if (level_stride == 0) { prefetch_l2(feats + (size_t)nn * 32); prefetch_l2(feats + (size_t)nn * 32 + 16); }
+                else if ((c.row & 3) == 0) {
+#pragma unroll
+                    for (int l = 0; l < 16; ++l) prefetch_l2(reinterpret_cast<const float2*>(feats) + nn + (size_t)l * level_stride);
+                }
+            }
+        }
         float x[32];
         if (live) {
             if (level_stride == 0) {

@@ -507,6 +507,8 @@ template <bool SPLIT> constexpr int off_raybias4() { return off_w3sh<SPLIT>() + 
 template <bool SPLIT> constexpr int off_tiles4() { return ((off_raybias4<SPLIT>() + kGroups4 * kMaxRays4 * 64 * 4 + 1023) / 1024) * 1024; }
 template <bool SPLIT> constexpr int fwd4_smem() { return off_tiles4<SPLIT>() + kGroups4 * 2 * kTile + 1024; }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 struct Ctx4 {
     uint64_t* bar;
     uint32_t tmem, lane_addr, phase, bar_id;

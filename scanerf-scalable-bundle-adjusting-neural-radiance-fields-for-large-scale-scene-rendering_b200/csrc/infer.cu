@@ -492,6 +492,13 @@ infer_decode4_kernel(InferArgs a, long long n0, int Nc, const float2* __restrict
         const int st = i < Nc ? state[i] : 2;
         const bool active = st == 1;
         const long long n = n0 + i;
+        {   // L2 prefetch of this group's next tile (one 32-byte sector holds four rows of a level)
+            const int in = i + kGroups4 * (int)gridDim.x * kRows;
+            if (in < Nc && (row & 3) == 0) {
+#pragma unroll
+                for (int l = 0; l < 16; ++l) prefetch_l2(feats_lm + in + (size_t)l * Nc);
+            }
+        }
         if (c.any(active)) {
             float x[32];
             if (active) {
