@@ -100,6 +100,9 @@ void snrf_field_set_levels_per_group(int n);
 void snrf_field_set_passes_log2(int bits);
 /* tuning hook: levels [0, n) merge equal-cell lanes of a warp before reducing (-1 = automatic, L / 2) */
 void snrf_field_set_aggregate_levels(int n);
+/* tuning hook: kernels behind snrf_field_encode_bwd: 1 (default) = geometry / ray-gradient kernel + slim scatter per level and index
+ * range (the pair of snrf_field_encode_bwd_adam, writing into grad_table), 0 = the round-1 single kernel */
+void snrf_field_set_bwd_impl(int v);
 /* tuning hook: samples per thread of the run-merging scatter kernel (2, 4 or 8; 0 selects the cross-lane kernel) */
 void snrf_field_set_run_length(int r);
 

@@ -27,6 +27,10 @@ void snrf_set_error(const char* fmt, ...);
         return 0;                                                             \
     } while (0)
 
+// Stream-ordered scratch from a private pool that keeps its memory (core.cu); snrf_scratch_release() trims it.
+cudaError_t snrf_scratch_alloc(void** ptr, size_t bytes, cudaStream_t s);
+int snrf_scratch_release();
+
 // Number of SMs of the current device (cached).
 int snrf_sm_count();
 

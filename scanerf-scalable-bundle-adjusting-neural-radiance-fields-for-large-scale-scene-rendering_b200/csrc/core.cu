@@ -27,6 +27,39 @@ int snrf_sm_count()
     return cached;
 }
 
+// Scratch for the multi-pass paths (render passes, the unfused encode backward) comes from a private stream-ordered pool that
+// keeps its memory across synchronisations (the default pool hands it back to the driver at every sync; re-mapping GBs per
+// call costs tens of milliseconds).  snrf_infer_release_scratch() trims it.
+static cudaMemPool_t g_scratch_pool[64] = {};
+cudaError_t snrf_scratch_alloc(void** ptr, size_t bytes, cudaStream_t s)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaMallocAsync(ptr, bytes, s);
+    if (!g_scratch_pool[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        e = cudaMemPoolCreate(&g_scratch_pool[dev], &props);
+        if (e != cudaSuccess) return e;
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(g_scratch_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    return cudaMallocFromPoolAsync(ptr, bytes, g_scratch_pool[dev], s);
+}
+int snrf_scratch_release()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_scratch_pool[dev]) return 0;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemPoolTrimTo(g_scratch_pool[dev], 0);
+    if (e != cudaSuccess) { snrf_set_error("snrf_infer_release_scratch: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
 SNRF_API const char* snrf_last_error(void) { return g_err; }
 SNRF_API int snrf_version(void) { return 100; }
 SNRF_API int snrf_device_sm_count(void) { return snrf_sm_count(); }

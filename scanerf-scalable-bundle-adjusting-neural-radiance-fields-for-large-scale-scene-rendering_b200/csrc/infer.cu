@@ -791,26 +791,7 @@ int g_infer_inflight = 1;
 // Scratch for the multi-pass paths comes from a private stream-ordered pool that keeps its memory across
 // synchronisations (the default pool hands it back to the driver at every sync; re-mapping 3 GB per call costs tens of
 // milliseconds).  snrf_infer_release_scratch() trims it.
-cudaMemPool_t g_scratch_pool[64] = {};
-cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t s)
-{
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64) return cudaMallocAsync(ptr, bytes, s);
-    if (!g_scratch_pool[dev]) {
-        cudaMemPoolProps props = {};
-        props.allocType = cudaMemAllocationTypePinned;
-        props.handleTypes = cudaMemHandleTypeNone;
-        props.location.type = cudaMemLocationTypeDevice;
-        props.location.id = dev;
-        e = cudaMemPoolCreate(&g_scratch_pool[dev], &props);
-        if (e != cudaSuccess) return e;
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(g_scratch_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    return cudaMallocFromPoolAsync(ptr, bytes, g_scratch_pool[dev], s);
-}
+inline cudaError_t scratch_alloc(void** ptr, size_t bytes, cudaStream_t s) { return snrf_scratch_alloc(ptr, bytes, s); }
 
 template <int MODE, int NCG>
 int launch_ncg(const InferArgs& a, void* stream, const char* name)
@@ -961,15 +942,7 @@ SNRF_API void snrf_infer_set_decode_inflight(int n) { g_decode_inflight = n == 2
 SNRF_API void snrf_infer_set_precision(int split) { g_infer_split = split ? 1 : 0; }
 SNRF_API void snrf_infer_set_inflight(int tiles) { g_infer_inflight = tiles == 2 ? 2 : 1; }
 SNRF_API void snrf_infer_set_two_pass(int on) { g_infer_two_pass = on == 2 ? 2 : (on ? 1 : 0); }
-SNRF_API int snrf_infer_release_scratch(void)
-{
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_scratch_pool[dev]) return 0;
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaMemPoolTrimTo(g_scratch_pool[dev], 0);
-    if (e != cudaSuccess) { snrf_set_error("snrf_infer_release_scratch: %s", cudaGetErrorString(e)); return (int)e; }
-    return 0;
-}
+SNRF_API int snrf_infer_release_scratch(void) { return snrf_scratch_release(); }
 
 SNRF_API int snrf_pts_inference(const float* rays_o, const float* rays_d, const float* z_vals, const float* dists,
                                 const short* block_idxs, const void* features_tables, const float* params, const int* resolution,
