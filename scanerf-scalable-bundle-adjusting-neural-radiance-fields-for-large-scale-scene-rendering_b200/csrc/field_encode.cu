@@ -547,7 +547,12 @@ field_scatter_slice_kernel(const float* __restrict__ cpts, const int* __restrict
         uint32_t idx[8]; float w[8];
         corner_idx(idx, cell, mask);
         corner_w(w, cell);
-        bool done = false;
+        // per-corner contributions of this lane; on the aggregated levels lanes of one cell are merged first (segmented
+        // warp sums over runs of equal cells in consecutive lanes) and only the run's first lane emits
+        float vx[8], vy[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { vx[k] = w[k] * g.x; vy[k] = w[k] * g.y; }
+        bool emit = live;
         if (aggregate) {
             const unsigned long long key = live
                 ? (((unsigned long long)(uint32_t)cell.ix & 0x1fffffull) << 42) | (((unsigned long long)(uint32_t)cell.iy & 0x1fffffull) << 21) |
@@ -556,17 +561,13 @@ field_scatter_slice_kernel(const float* __restrict__ cpts, const int* __restrict
             const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
             const bool head = (lane == 0) || (prev != key);
             const unsigned heads = __ballot_sync(0xffffffffu, head);
-            if (__popc(heads) <= 12) {
-                // segmented sums of the 16 products over runs of equal cells in consecutive lanes.  The lane's run ends
-                // right before the next head above it: lane + off is inside the run iff it is below that bound -- one
-                // comparison per step instead of a second shuffle of the run id.
+            if (__popc(heads) <= 16) {
+                // The lane's run ends right before the next head above it: lane + off is inside the run iff it is below that
+                // bound -- one comparison per step instead of a second shuffle of the run id; as many doubling steps as the
+                // longest run of the warp needs (warp-uniform): the mid levels have runs of 1-4 samples.
                 const unsigned above = heads & ~((2u << lane) - 1u);            // heads in lanes > lane
                 const int run_end = above ? __ffs(above) - 1 : 32;               // first lane past my run
-                float vx[8], vy[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) { vx[k] = w[k] * g.x; vy[k] = w[k] * g.y; }
-                const int longest = 32;                                          // (all five steps: the longest run is not known per lane)
-#pragma unroll
+                const int longest = __reduce_max_sync(0xffffffffu, run_end - lane);
                 for (int off = 1; off < longest; off <<= 1) {
                     const bool take = lane + off < run_end;
 #pragma unroll
@@ -576,30 +577,24 @@ field_scatter_slice_kernel(const float* __restrict__ cpts, const int* __restrict
                         if (take) { vx[k] += ox; vy[k] += oy; }
                     }
                 }
-                if (head && live) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if ((idx[k] >> range_shift) == pass) red_add2(gl + (idx[k] & slice_mask), vx[k], vy[k], pol, hint);
-                }
-                done = true;
+                emit = head && live;
             }
         }
-        if (!done && live) {
+        if (emit) {
             // x-adjacent corners that share an aligned 16-byte slot go out as one red.v4 (see field_bwd_kernel)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t i0 = idx[j], i1 = idx[j + 4];
-                const float2 v0 = make_float2(w[j] * g.x, w[j] * g.y), v1 = make_float2(w[j + 4] * g.x, w[j + 4] * g.y);
                 if ((i0 ^ i1) == 1u) {
                     if ((i0 >> range_shift) == pass) {
                         const bool swap = (i0 & 1u) != 0u;
                         float4* dst = reinterpret_cast<float4*>(gl + ((i0 & slice_mask) & ~1u));
-                        if (swap) red_add4(dst, v1.x, v1.y, v0.x, v0.y, pol, hint);
-                        else red_add4(dst, v0.x, v0.y, v1.x, v1.y, pol, hint);
+                        if (swap) red_add4(dst, vx[j + 4], vy[j + 4], vx[j], vy[j], pol, hint);
+                        else red_add4(dst, vx[j], vy[j], vx[j + 4], vy[j + 4], pol, hint);
                     }
                 } else {
-                    if ((i0 >> range_shift) == pass) red_add2(gl + (i0 & slice_mask), v0.x, v0.y, pol, hint);
-                    if ((i1 >> range_shift) == pass) red_add2(gl + (i1 & slice_mask), v1.x, v1.y, pol, hint);
+                    if ((i0 >> range_shift) == pass) red_add2(gl + (i0 & slice_mask), vx[j], vy[j], pol, hint);
+                    if ((i1 >> range_shift) == pass) red_add2(gl + (i1 & slice_mask), vx[j + 4], vy[j + 4], pol, hint);
                 }
             }
         }
