@@ -541,7 +541,7 @@ def main():
         n = max(len(ms_list), 1)
         avg = sum(ms_list) / n if ms_list else float("nan")
         ach = alg_bytes / (avg * 1e-3) / 1e9 if ms_list else float("nan")
-        t = traffic_file.get(traffic_key)
+        t = traffic_file.get(traffic_key) if cfg["log2T"] == 24 else None      # the ncu capture is of the 2^24-entry workload
         r = {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
              "frac": ach / peak, "traffic": t.get("bytes") if isinstance(t, dict) else t,
              "traffic_source": (t.get("source") if isinstance(t, dict) else None),
@@ -593,14 +593,14 @@ def main():
         "metric": "train rays/s (fwd+bwd)", "value": K * rays_per_step / (ms_dev * 1e-3), "unit": "rays/s", "n_gpus": world,
         "steps": K, "warmup": Wm, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name if world == 1 else (name + ": row of %d tiles with 20 %% overlap, %d boundary cameras shared per neighbour pair" % (tiles_total, cfg.get("shared_cams", 16))),
+        "config": {"workload": name if world == 1 else (("community.yaml-tile-row" if name == "default.yaml-single-tile" else name) + ": row of %d tiles of default.yaml size with 20 %% overlap, %d boundary cameras shared per neighbour pair" % (tiles_total, cfg.get("shared_cams", 16))),
                    "tiles_per_gpu": T_res, "tiles_total": tiles_total, "rays_per_step": rays_per_step, "rays_per_tile_step": B,
                    "samples_per_ray": cfg["S"] + cfg["S_bg"],
                    "hash_table": f"16 x 2^{cfg['log2T']} x 2 f32 per tile", "cameras_per_tile": cfg["n_cam"], "cameras_global": n_cam_global,
                    "pose_refinement": True,
                    "table_update": "scatter + sparse Adam fused per L2-resident slice" if fused else "gradient table + sparse Adam",
                    "parallelism": f"tile-parallel x{world}" + (f", {T_res} resident tiles per rank trained in turn, NCCL pose consensus (one all-reduce of [{n_cam_global}, 8] f32 for all resident tiles) every {SYN} steps" if world > 1 else ""),
-                   "l2_policy": "inputs larger than L2 (2 GiB table + 4 GiB Adam moments per tile, random gathers)"},
+                   "l2_policy": "inputs larger than L2 (%.1f GiB table + %.1f GiB Adam moments per tile, random gathers)" % (2.0 ** (cfg["log2T"] - 23), 2.0 ** (cfg["log2T"] - 22))},
         "e2e": {"value": K * rays_per_step / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": T_res * B * 3 * 4 * 2,
                 "d2h_bytes_per_step": 4 * T_res},
         "gpu_launches": launches,
