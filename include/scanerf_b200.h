@@ -103,6 +103,8 @@ void snrf_field_set_aggregate_levels(int n);
 /* tuning hook: kernels behind snrf_field_encode_bwd: 1 (default) = geometry / ray-gradient kernel + slim scatter per level and index
  * range (the pair of snrf_field_encode_bwd_adam, writing into grad_table), 0 = the round-1 single kernel */
 void snrf_field_set_bwd_impl(int v);
+/* tuning hook (experiment): the forward's CTA rows walk level pairs (y, L-1-y) instead of single levels (default 0) */
+void snrf_field_set_fwd_pairing(int on);
 /* tuning hook: samples per thread of the run-merging scatter kernel (2, 4 or 8; 0 selects the cross-lane kernel) */
 void snrf_field_set_run_length(int r);
 

@@ -91,7 +91,10 @@ field_fwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
     const uint32_t mask = T - 1u;
     f3 bmin = mk3(0, 0, 0), bsize = mk3(1, 1, 1);
     if (MODE != kNone) { bmin = ld3(bmin_p); bsize = ld3(bsize_p); }
-    const int l_begin = blockIdx.y * lpb, l_end = min(L, l_begin + lpb);
+    // lpb < 0: CTA row y walks the level PAIR (y, L - 1 - y): a coarse level (few vertices, L2 hits) next to a fine one (one
+    // DRAM sector per corner), so that the two kinds of latency overlap inside a thread instead of running as separate waves
+    const bool paired = lpb < 0;
+    const int l_begin = paired ? (int)blockIdx.y : blockIdx.y * lpb, l_end = paired ? l_begin + 2 : min(L, l_begin + lpb);
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
         f3 c;
         if (MODE == kNone) {
@@ -101,7 +104,9 @@ field_fwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
             if (ray_valid != nullptr && !ray_valid[r]) continue;        // masked-out ray: its rows are never read
             c = contract(r >= ray_split, sample_pos(ld3(rays_o + 3 * (size_t)r), ld3(rays_d + 3 * (size_t)r), z_vals[n]), bmin, bsize).c;
         }
-        for (int l = l_begin; l < l_end; ++l) {
+        for (int li = l_begin; li < l_end; ++li) {
+            const int l = (paired && li > l_begin) ? L - 1 - l_begin : li;
+            if (paired && li > l_begin && l == l_begin) break;         // odd L: the middle level once
             const Cell cell = locate_bg(c, res + 3 * l);
             uint32_t idx[8];
             corner_idx(idx, cell, mask);
@@ -667,6 +672,7 @@ int g_aggregate_override = -1;
 // tools/sweep_field.py): cross-lane 3.69 ms, run-merging 4.15 / 4.35 / 4.39 ms at R = 2 / 4 / 8 -- merging R samples
 // leaves 32 / R times more same-address reductions on the coarse levels than the cross-lane sums do, and that costs
 // more than the shuffles it saves.  Kept selectable (and parity-tested) for tables / sample densities where runs are longer.
+int g_fwd_pairing = 0;         // snrf_field_encode_fwd: CTA rows walk level pairs (y, L-1-y) (experiment)
 int g_run_length = 0;
 int g_bwd_impl = 1;            // snrf_field_encode_bwd: 1 = geometry / ray-gradient kernel + slim scatter per level and range (round 2), 0 = field_bwd_kernel (round 1)
 int g_levels_per_group = 0;
@@ -718,6 +724,7 @@ SNRF_API void snrf_field_set_l2_hints(int on) { g_l2_hints = on ? 1 : 0; }
 SNRF_API void snrf_field_set_coarse_concurrent(int on) { g_coarse_concurrent = on ? 1 : 0; }
 SNRF_API void snrf_field_set_slice_log2(int bits) { g_slice_cap = 1ll << (bits < 2 ? 2 : (bits > 30 ? 30 : bits)); }
 SNRF_API void snrf_field_set_levels_per_group(int n) { g_levels_per_group = n > 0 ? n : 0; }
+SNRF_API void snrf_field_set_fwd_pairing(int on) { g_fwd_pairing = on ? 1 : 0; }
 SNRF_API void snrf_field_set_bwd_impl(int v) { g_bwd_impl = v ? 1 : 0; }
 SNRF_API void snrf_field_set_run_length(int r) { g_run_length = (r == 2 || r == 4 || r == 8) ? r : 0; }
 
@@ -735,8 +742,9 @@ SNRF_API int snrf_field_encode_fwd(const float* rays_o, const float* rays_d, con
                    "snrf_field_encode_fwd: inconsistent arguments for mode %d", mode);
     if (N == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    const int lpb = pick_lpb(L, T);
-    const dim3 grid(grid_x(N), snrf_div_up(L, lpb));
+    const bool pair_levels = g_fwd_pairing && pick_lpb(L, T) == 1 && L >= 2;
+    const int lpb = pair_levels ? -1 : pick_lpb(L, T);
+    const dim3 grid(grid_x(N), pair_levels ? (L + 1) / 2 : snrf_div_up(L, lpb));
     const float2* tb = (const float2*)table;
     float2 *o = (float2*)out_lm, *j = (float2*)jac_lm;
 #define SNRF_FWD(MODE)                                                                                                                   \
