@@ -26,6 +26,10 @@ extern "C" {
 const char* snrf_last_error(void);
 int snrf_version(void);
 int snrf_device_sm_count(void);
+/* L2 fetch granularity of the current device (cudaLimitMaxL2FetchGranularity; 32 / 64 / 128 bytes, a hint): bytes > 0 sets it,
+ * bytes <= 0 only queries; returns the value in effect or a negative CUDA error code.  No reference counterpart: the
+ * reference never touches the limit (hash-table gathers fetch one 32-byte sector per corner) */
+int snrf_l2_fetch_granularity(int bytes);
 
 /* ---- hash-grid encode ------------------------------------------------------- */
 /* hashgrid/include/hashgrid.h:19-25 (embedding_forward_cuda, corner/size != NULL) and
@@ -105,6 +109,16 @@ void snrf_field_set_aggregate_levels(int n);
 void snrf_field_set_bwd_impl(int v);
 /* tuning hook (experiment): the forward's CTA rows walk level pairs (y, L-1-y) instead of single levels (default 0) */
 void snrf_field_set_fwd_pairing(int on);
+/* tuning hook: L2 eviction policy of the forward's table gathers when a CTA row walks one level (large tables).
+ * mode 0 = default policy; 1 = evict_last on every gather; 2 = the first pin_mib MiB of each level slice evict_last, the
+ * rest evict_first; 3 = evict_last on the fraction pin_mib / 128 of the gathers, evict_first on the rest */
+void snrf_field_set_fwd_l2_policy(int mode, int pin_mib);
+/* tuning hook: x-pair gathers of the forward on levels >= first_level.  mode 0 = eight 8-byte loads per sample and level; 1 = one
+ * 16-byte load for an x-pair in an aligned 16-byte slot; 2 = one 32-byte sector load per x-pair, the second corner fetched by
+ * itself when it lies in another sector.  Results are bit-identical in every mode */
+void snrf_field_set_fwd_pair_loads(int mode, int first_level);
+/* measurement hook: one forward launch per level, so that ncu reports L2 hit rate / DRAM bytes per level (default 0) */
+void snrf_field_set_fwd_split_levels(int on);
 /* tuning hook: samples per thread of the run-merging scatter kernel (2, 4 or 8; 0 selects the cross-lane kernel) */
 void snrf_field_set_run_length(int r);
 

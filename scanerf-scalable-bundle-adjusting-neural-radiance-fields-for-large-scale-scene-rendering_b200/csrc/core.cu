@@ -63,3 +63,20 @@ int snrf_scratch_release()
 SNRF_API const char* snrf_last_error(void) { return g_err; }
 SNRF_API int snrf_version(void) { return 100; }
 SNRF_API int snrf_device_sm_count(void) { return snrf_sm_count(); }
+
+// L2 fetch granularity of the current device (cudaLimitMaxL2FetchGranularity: 32, 64 or 128 bytes; a hint to the driver).
+// The gather / scatter kernels touch one 32-byte sector per hash-table corner at addresses the hash scatters over the
+// whole level slice: a larger granularity drags the neighbouring sector(s) in with every miss, which costs DRAM bandwidth
+// and L2 capacity for data that is evicted before its own touches arrive.  bytes <= 0 only queries.  Returns the value in
+// effect after the call, or a negative CUDA error code.
+SNRF_API int snrf_l2_fetch_granularity(int bytes)
+{
+    if (bytes > 0) {
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); snrf_set_error("snrf_l2_fetch_granularity(%d): %s", bytes, cudaGetErrorString(e)); return -(int)e; }
+    }
+    size_t v = 0;
+    cudaError_t e = cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity);
+    if (e != cudaSuccess) { cudaGetLastError(); snrf_set_error("snrf_l2_fetch_granularity: %s", cudaGetErrorString(e)); return -(int)e; }
+    return (int)v;
+}

@@ -81,12 +81,66 @@ __device__ __forceinline__ f3 contract_bwd(bool back, const Pt& p, f3 gc)
     return gx;
 }
 
-template <int MODE, bool JAC>
-__global__ void __launch_bounds__(kThreads)
+// L2 eviction policy of the forward's table gathers (snrf_field_set_fwd_l2_policy).  A level slice at T = 2^24 is 128 MiB
+// against 126 MB of L2 that the kernel's own output streams also pass through: under the default policy the slice thrashes
+// (lts hit rate 27 %, every sector fetched ~3x per launch).  mode 1: every gather evict_last; mode 2: the first `pin_bytes`
+// of the level slice evict_last and the rest evict_first (a pinned part that does fit, instead of an LRU cycle over a
+// working set that does not); mode 3: the same split as a fraction of the accesses (`pin_bytes` / 2^16).
+__device__ __forceinline__ uint64_t fwd_table_policy(int mode, const float2* slice, uint32_t slice_bytes, uint32_t pin_bytes)
+{
+    uint64_t p = 0;
+    if (mode == 1) {
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    } else if (mode == 2) {
+        asm volatile("createpolicy.range.global.L2::evict_last.L2::evict_first.b64 %0, [%1], %2, %3;" : "=l"(p) : "l"(slice), "r"(pin_bytes), "r"(slice_bytes));
+    } else if (mode == 3) {
+        const float frac = (float)pin_bytes * (1.0f / 65536.0f);
+        asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(p) : "f"(frac));
+    }
+    return p;
+}
+__device__ __forceinline__ float2 ldg2_policy(const float2* a, uint64_t pol)
+{
+    float2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(a), "l"(pol));
+    return v;
+}
+
+// x-pair gathers (snrf_field_set_fwd_pair_loads).  The hash is linear in x, so the two corners of an x-edge sit in one
+// aligned 16-byte slot when the cell's x is even, and in one 32-byte sector three times out of four.  Issued as two 8-byte
+// loads they arrive at the L2 as two sector requests (the L1 does not merge them: ncu counts exactly 8 sector requests per
+// sample and level on the fine levels).  mode 1: one 16-byte load for an aligned pair; mode 2: one 32-byte load of the
+// sector of the first corner, the second corner picked from it when it lies in the same sector, fetched by itself otherwise.
+__device__ __forceinline__ float2 pick2(const float v[8], uint32_t s)
+{
+    const float ax = (s & 1u) ? v[2] : v[0], ay = (s & 1u) ? v[3] : v[1];
+    const float bx = (s & 1u) ? v[6] : v[4], by = (s & 1u) ? v[7] : v[5];
+    return make_float2((s & 2u) ? bx : ax, (s & 2u) ? by : ay);
+}
+__device__ __forceinline__ void ld_sector(const float2* a, uint64_t pol, bool hint, float v[8])
+{
+    if (hint)
+        asm volatile("ld.global.nc.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(a), "l"(pol));
+    else
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(a));
+}
+__device__ __forceinline__ float4 ld_pair16(const float2* a, uint64_t pol, bool hint)
+{
+    float4 v;
+    if (hint) asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a), "l"(pol));
+    else v = __ldg(reinterpret_cast<const float4*>(a));
+    return v;
+}
+
+template <int MODE, bool JAC, bool POLICY, int PAIR>
+__global__ void __launch_bounds__(kThreads, (PAIR == 0 ? 5 : 4))
 field_fwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_vals,
                  const float* __restrict__ points, const float* __restrict__ bmin_p, const float* __restrict__ bsize_p,
                  const float2* __restrict__ table, const int* __restrict__ res, float2* __restrict__ out, float2* __restrict__ jac,
-                 const unsigned char* __restrict__ ray_valid, int ray_split, int N, int S, int L, uint32_t T, int lpb)
+                 const unsigned char* __restrict__ ray_valid, int ray_split, int N, int S, int L, uint32_t T, int lpb, int l_base,
+                 int l2_mode, uint32_t pin_bytes, int pair_level)
 {
     const uint32_t mask = T - 1u;
     f3 bmin = mk3(0, 0, 0), bsize = mk3(1, 1, 1);
@@ -94,7 +148,9 @@ field_fwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
     // lpb < 0: CTA row y walks the level PAIR (y, L - 1 - y): a coarse level (few vertices, L2 hits) next to a fine one (one
     // DRAM sector per corner), so that the two kinds of latency overlap inside a thread instead of running as separate waves
     const bool paired = lpb < 0;
-    const int l_begin = paired ? (int)blockIdx.y : blockIdx.y * lpb, l_end = paired ? l_begin + 2 : min(L, l_begin + lpb);
+    const int l_begin = paired ? (int)blockIdx.y : l_base + blockIdx.y * lpb, l_end = paired ? l_begin + 2 : min(L, l_begin + lpb);
+    uint64_t pol = 0;
+    if (POLICY) pol = fwd_table_policy(l2_mode, table + (size_t)l_begin * T, T * 8u, pin_bytes);   // POLICY: one level per CTA row
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
         f3 c;
         if (MODE == kNone) {
@@ -112,8 +168,40 @@ field_fwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ ray
             corner_idx(idx, cell, mask);
             const float2* tl = table + (size_t)l * T;
             float2 f[8];
+            if (PAIR == 2 && l >= pair_level) {
+                float v[4][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] = ldg2(tl + idx[k]);
+                for (int j = 0; j < 4; ++j) ld_sector(tl + (idx[j] & ~3u), pol, POLICY, v[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((idx[j] >> 2) != (idx[j + 4] >> 2)) f[j + 4] = POLICY ? ldg2_policy(tl + idx[j + 4], pol) : ldg2(tl + idx[j + 4]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    f[j] = pick2(v[j], idx[j] & 3u);
+                    if ((idx[j] >> 2) == (idx[j + 4] >> 2)) f[j + 4] = pick2(v[j], idx[j + 4] & 3u);
+                }
+            } else if (PAIR == 1 && l >= pair_level) {
+                float4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool paired16 = (idx[j] ^ idx[j + 4]) == 1u;
+                    if (paired16) v[j] = ld_pair16(tl + (idx[j] & ~1u), pol, POLICY);
+                    else {
+                        f[j] = POLICY ? ldg2_policy(tl + idx[j], pol) : ldg2(tl + idx[j]);
+                        f[j + 4] = POLICY ? ldg2_policy(tl + idx[j + 4], pol) : ldg2(tl + idx[j + 4]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((idx[j] ^ idx[j + 4]) == 1u) {
+                        const bool odd = (idx[j] & 1u) != 0u;
+                        f[j] = odd ? make_float2(v[j].z, v[j].w) : make_float2(v[j].x, v[j].y);
+                        f[j + 4] = odd ? make_float2(v[j].x, v[j].y) : make_float2(v[j].z, v[j].w);
+                    }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = POLICY ? ldg2_policy(tl + idx[k], pol) : ldg2(tl + idx[k]);
+            }
             float w[8];
             corner_w(w, cell);
             float2 acc = make_float2(0.f, 0.f);
@@ -673,6 +761,11 @@ int g_aggregate_override = -1;
 // leaves 32 / R times more same-address reductions on the coarse levels than the cross-lane sums do, and that costs
 // more than the shuffles it saves.  Kept selectable (and parity-tested) for tables / sample densities where runs are longer.
 int g_fwd_pairing = 0;         // snrf_field_encode_fwd: CTA rows walk level pairs (y, L-1-y) (experiment)
+int g_fwd_l2_mode = 1;         // snrf_field_set_fwd_l2_policy (1: measured 1.725 -> 1.653 ms at C2, profiles/r3a_fwd_sweep.json)
+int g_fwd_pin_mib = 0;
+int g_fwd_split_levels = 0;    // one forward launch per level (measurement hook)
+int g_fwd_pair_mode = 0;       // snrf_field_set_fwd_pair_loads
+int g_fwd_pair_level = 0;
 int g_run_length = 0;
 int g_bwd_impl = 1;            // snrf_field_encode_bwd: 1 = geometry / ray-gradient kernel + slim scatter per level and range (round 2), 0 = field_bwd_kernel (round 1)
 int g_levels_per_group = 0;
@@ -725,6 +818,15 @@ SNRF_API void snrf_field_set_coarse_concurrent(int on) { g_coarse_concurrent = o
 SNRF_API void snrf_field_set_slice_log2(int bits) { g_slice_cap = 1ll << (bits < 2 ? 2 : (bits > 30 ? 30 : bits)); }
 SNRF_API void snrf_field_set_levels_per_group(int n) { g_levels_per_group = n > 0 ? n : 0; }
 SNRF_API void snrf_field_set_fwd_pairing(int on) { g_fwd_pairing = on ? 1 : 0; }
+// mode 0: default policy; 1: evict_last on every table gather; 2: the first `pin_mib` MiB of each level slice evict_last,
+// the rest evict_first; 3: evict_last on the fraction pin_mib / 128 of the gathers, evict_first on the rest.  Applies when a
+// CTA row walks ONE level (large tables); see fwd_table_policy.
+SNRF_API void snrf_field_set_fwd_l2_policy(int mode, int pin_mib) { g_fwd_l2_mode = (mode >= 0 && mode <= 3) ? mode : 0; g_fwd_pin_mib = pin_mib > 0 ? pin_mib : 0; }
+// x-pair gathers of the forward on levels >= first_level: 0 = eight 8-byte loads, 1 = one 16-byte load per aligned pair,
+// 2 = one 32-byte sector load per pair + the second corner by itself when it lies in another sector
+SNRF_API void snrf_field_set_fwd_pair_loads(int mode, int first_level) { g_fwd_pair_mode = (mode >= 0 && mode <= 2) ? mode : 0; g_fwd_pair_level = first_level > 0 ? first_level : 0; }
+// measurement hook: one launch per level (ncu then reports L2 hit rate / DRAM bytes per level)
+SNRF_API void snrf_field_set_fwd_split_levels(int on) { g_fwd_split_levels = on ? 1 : 0; }
 SNRF_API void snrf_field_set_bwd_impl(int v) { g_bwd_impl = v ? 1 : 0; }
 SNRF_API void snrf_field_set_run_length(int r) { g_run_length = (r == 2 || r == 4 || r == 8) ? r : 0; }
 
@@ -734,7 +836,7 @@ SNRF_API void snrf_field_set_run_length(int r) { g_run_length = (r == 2 || r == 
 // background -- both render chains of a step in one launch, so that the table is streamed through L2 once.
 SNRF_API int snrf_field_encode_fwd(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
                                    const float* box_min, const float* box_size, int mode, const float* table, const int* res,
-                                   float* out_lm, float* jac_lm, const unsigned char* ray_valid, int split, int N, int S, int L, int T,
+                                   float* out_lm, float* jac_lm, const unsigned char* ray_valid, int split_ray, int N, int S, int L, int T,
                                    void* stream)
 {
     SNRF_CHECK_ARG(N >= 0 && L > 0 && T > 0 && (T & (T - 1)) == 0, "snrf_field_encode_fwd: T must be a power of two (N=%d L=%d T=%d)", N, L, T);
@@ -744,17 +846,40 @@ SNRF_API int snrf_field_encode_fwd(const float* rays_o, const float* rays_d, con
     cudaStream_t s = (cudaStream_t)stream;
     const bool pair_levels = g_fwd_pairing && pick_lpb(L, T) == 1 && L >= 2;
     const int lpb = pair_levels ? -1 : pick_lpb(L, T);
-    const dim3 grid(grid_x(N), pair_levels ? (L + 1) / 2 : snrf_div_up(L, lpb));
     const float2* tb = (const float2*)table;
     float2 *o = (float2*)out_lm, *j = (float2*)jac_lm;
-#define SNRF_FWD(MODE)                                                                                                                   \
-    do {                                                                                                                                 \
-        if (j) field_fwd_kernel<MODE, true><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, tb, res, o, j, ray_valid, ray_split, N, S, L, (uint32_t)T, lpb); \
-        else   field_fwd_kernel<MODE, false><<<grid, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, tb, res, o, j, ray_valid, ray_split, N, S, L, (uint32_t)T, lpb); \
+    // the eviction policy needs one level per CTA row and a slice the 32-bit range operands can describe
+    const bool policy = g_fwd_l2_mode != 0 && lpb == 1 && (long long)T * 8 < (1ll << 32);
+    uint32_t pin = 0;
+    if (policy && g_fwd_l2_mode == 2) { const long long b = (long long)g_fwd_pin_mib << 20; pin = (uint32_t)(b < (long long)T * 8 ? b : (long long)T * 8); }
+    if (policy && g_fwd_l2_mode == 3) pin = (uint32_t)(g_fwd_pin_mib >= 128 ? 65536 : g_fwd_pin_mib * 512);
+    const bool split = g_fwd_split_levels && lpb == 1;
+    const int ray_split = mode == 1 ? 0x7fffffff : (mode == 2 ? 0 : split_ray);
+    const int pair = (lpb >= 1 && T >= 4) ? g_fwd_pair_mode : 0;
+#define SNRF_FWD_K(MODE, JAC, POL, PAIR, GRID, LBASE) field_fwd_kernel<MODE, JAC, POL, PAIR><<<GRID, kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, tb, res, o, j, ray_valid, ray_split, N, S, L, (uint32_t)T, lpb, LBASE, g_fwd_l2_mode, pin, g_fwd_pair_level)
+#define SNRF_FWD_P(MODE, JAC, POL, GRID, LBASE)                                              \
+    do {                                                                                     \
+        if (pair == 2) SNRF_FWD_K(MODE, JAC, POL, 2, GRID, LBASE);                            \
+        else if (pair == 1) SNRF_FWD_K(MODE, JAC, POL, 1, GRID, LBASE);                       \
+        else SNRF_FWD_K(MODE, JAC, POL, 0, GRID, LBASE);                                      \
     } while (0)
-    const int ray_split = mode == 1 ? 0x7fffffff : (mode == 2 ? 0 : split);
-    if (mode == 0) SNRF_FWD(kNone); else SNRF_FWD(kRays);
+#define SNRF_FWD(MODE, GRID, LBASE)                                                          \
+    do {                                                                                     \
+        if (j) { if (policy) SNRF_FWD_P(MODE, true, true, GRID, LBASE); else SNRF_FWD_P(MODE, true, false, GRID, LBASE); }   \
+        else   { if (policy) SNRF_FWD_P(MODE, false, true, GRID, LBASE); else SNRF_FWD_P(MODE, false, false, GRID, LBASE); } \
+    } while (0)
+    if (split) {
+        for (int l = 0; l < L; ++l) {
+            const dim3 grid(grid_x(N), 1);
+            if (mode == 0) SNRF_FWD(kNone, grid, l); else SNRF_FWD(kRays, grid, l);
+        }
+    } else {
+        const dim3 grid(grid_x(N), pair_levels ? (L + 1) / 2 : snrf_div_up(L, lpb));
+        if (mode == 0) SNRF_FWD(kNone, grid, 0); else SNRF_FWD(kRays, grid, 0);
+    }
 #undef SNRF_FWD
+#undef SNRF_FWD_P
+#undef SNRF_FWD_K
     SNRF_RETURN_LAUNCH("snrf_field_encode_fwd");
 }
 

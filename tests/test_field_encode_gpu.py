@@ -67,6 +67,42 @@ def test_fused_encode_matches_unfused_chain(R, S, log2T, mode):
     assert np.allclose(out.detach().permute(1, 0, 2).cpu().numpy(), want, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("pair,first_level,l2", [(1, 0, 0), (2, 0, 0), (2, 9, 0), (1, 0, 1), (2, 0, 1), (0, 0, 1)])
+@pytest.mark.parametrize("R,S,log2T,mode", [(37, 5, 12, 1), (512, 64, 19, 2), (256, 32, 21, 3)])
+def test_forward_load_variants_are_bit_identical(R, S, log2T, mode, pair, first_level, l2):
+    """snrf_field_set_fwd_pair_loads / snrf_field_set_fwd_l2_policy change how the table is fetched (16-byte x-pairs, whole
+    32-byte sectors, L2 eviction policy), never what is computed: features and ray gradients (through the stored
+    Jacobians) equal to the bit.  log2T = 21 is a table large enough for one level per CTA row (where the policy applies)."""
+    import ctypes
+    load_pkg()
+    import scanerf_b200_capi as capi
+    from hashgrid import _field
+    table, res, bmin, bsize, o, d, z_fg, z_bg, g = _case(R, S, log2T, R + S + 1)
+    z = torch.cat([z_fg[: R // 2], z_bg[R // 2:]]) if mode == 3 else (z_fg if mode == 1 else z_bg)
+    cot = torch.randn(16, R * S, 2, generator=g).to(DEV)
+    lib = capi.lib()
+
+    def run():
+        o2, d2 = o.to(DEV).requires_grad_(True), d.to(DEV).requires_grad_(True)
+        t2 = torch.nn.Parameter(table.to(DEV).clone())
+        out = _field.field_encode(o2, d2, z.to(DEV), t2, res.to(DEV), bmin.to(DEV), bsize.to(DEV), mode, split=R // 2)
+        (out * cot).sum().backward()
+        torch.cuda.synchronize()
+        return out.detach().clone(), o2.grad.clone(), d2.grad.clone()
+
+    want = run()
+    try:
+        lib.snrf_field_set_fwd_pair_loads(ctypes.c_int(pair), ctypes.c_int(first_level))
+        lib.snrf_field_set_fwd_l2_policy(ctypes.c_int(l2), ctypes.c_int(0))
+        got = run()
+    finally:
+        lib.snrf_field_set_fwd_pair_loads(ctypes.c_int(0), ctypes.c_int(0))
+        lib.snrf_field_set_fwd_l2_policy(ctypes.c_int(0), ctypes.c_int(0))
+    assert torch.equal(got[0], want[0]), "features"
+    # (the ray gradients are sums of atomics: same values, run-to-run order)
+    assert _rel(got[1], want[1]) < 1e-5 and _rel(got[2], want[2]) < 1e-5
+
+
 @pytest.mark.parametrize("bits", [0, 1, 3])
 def test_scatter_passes_are_equivalent(bits):
     """The range-partitioned scatter is a cache optimisation only: any number of passes gives the same table gradient."""

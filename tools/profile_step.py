@@ -22,6 +22,14 @@ cfg = bench.WORKLOADS[os.environ.get("SNRF_PROFILE_WORKLOAD", "default.yaml-sing
 dev = torch.device("cuda:0")
 step, gen = bench.build_tile(cfg, dev, 0)
 capi.lib().snrf_field_set_overlap(ctypes.c_int(int(os.environ.get("SNRF_PROFILE_OVERLAP", "0"))))
+# SNRF_FWD_SPLIT=1: one encode-forward launch per level (per-level L2 hit rate); SNRF_FWD_L2="mode,pin_mib": its L2 policy
+capi.lib().snrf_field_set_fwd_split_levels(ctypes.c_int(int(os.environ.get("SNRF_FWD_SPLIT", "0"))))
+if os.environ.get("SNRF_FWD_L2"):
+    _m, _p = (int(v) for v in os.environ["SNRF_FWD_L2"].split(","))
+    capi.lib().snrf_field_set_fwd_l2_policy(ctypes.c_int(_m), ctypes.c_int(_p))
+if os.environ.get("SNRF_FWD_PAIR"):
+    _m, _p = (int(v) for v in os.environ["SNRF_FWD_PAIR"].split(","))
+    capi.lib().snrf_field_set_fwd_pair_loads(ctypes.c_int(_m), ctypes.c_int(_p))
 batches = [(l.to(dev), g.to(dev)) for l, g in bench.make_batches(cfg, 4, gen)]
 for b in batches[:3]:
     step.step_device(*b)

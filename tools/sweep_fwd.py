@@ -28,18 +28,27 @@ def main():
     step, gen = bench.build_tile(cfg, dev, 0)
     batches = [(l.to(dev), g.to(dev)) for l, g in bench.make_batches(cfg, 14, gen)]
     rows = []
-    for pairing in (0, 1, 0, 1):
-        capi.lib().snrf_field_set_fwd_pairing(ctypes.c_int(pairing))
+    lib = capi.lib()
+    # (L2 policy mode, pin MiB, x-pair load mode, first level of the pair loads), interleaved with the default
+    variants = [(0, 0, 0, 0), (1, 0, 0, 0), (1, 0, 1, 0), (1, 0, 2, 0), (1, 0, 1, 6), (1, 0, 2, 6), (1, 0, 1, 9), (1, 0, 2, 9), (1, 0, 2, 11),
+                (0, 0, 2, 9), (0, 0, 0, 0), (1, 0, 0, 0), (1, 0, 2, 9), (1, 0, 2, 6)]
+    for mode, pin, pair, first in variants:
+        lib.snrf_field_set_fwd_l2_policy(ctypes.c_int(mode), ctypes.c_int(pin))
+        lib.snrf_field_set_fwd_pair_loads(ctypes.c_int(pair), ctypes.c_int(first))
         ms, _ = bench._time_steps(step, batches, 4)
-        capi.time_calls(("snrf_field_encode_fwd",))
-        for b in batches[:6]:
+        capi.time_calls(("snrf_field_encode_fwd", "snrf_field_encode_bwd_adam", "snrf_decoder_fwd"))
+        for b in batches[:8]:
             step.step_device(*b)
-        fwd = capi.timed_by_name().get("snrf_field_encode_fwd", [])
+        t = capi.timed_by_name()
         capi.time_calls(None)
-        row = {"fwd_pairing": pairing, "ms_per_step": ms, "encode_fwd_ms": sum(fwd) / max(len(fwd), 1)}
+        mean = lambda k: sum(t.get(k, [])) / max(len(t.get(k, [])), 1)
+        row = {"l2_mode": mode, "pin_mib": pin, "pair_loads": pair, "pair_first_level": first, "ms_per_step": ms,
+               "encode_fwd_ms": mean("snrf_field_encode_fwd"), "bwd_adam_ms": mean("snrf_field_encode_bwd_adam"),
+               "decoder_fwd_ms": mean("snrf_decoder_fwd")}
         rows.append(row)
         print(json.dumps(row), flush=True)
-    capi.lib().snrf_field_set_fwd_pairing(ctypes.c_int(0))
+    lib.snrf_field_set_fwd_pair_loads(ctypes.c_int(0), ctypes.c_int(0))
+    lib.snrf_field_set_fwd_l2_policy(ctypes.c_int(0), ctypes.c_int(0))
     with open(args.out, "w") as fh:
         fh.write(json.dumps(rows) + "\n")
 
