@@ -212,7 +212,10 @@ decoder_fwd4_kernel(const float* __restrict__ feats, const float* __restrict__ m
 // g4 -> dz5, LOa (a1_lo / a3_lo in the forward, then the lo part of the current dz), LOb (x_lo / H_lo /
 // a4_lo in the forward, then [dz_heads | dz_spec | lo parts] and finally dH = dz2); a4 holds dH_lo after
 // B1; g = d(activation)/dz.
-template <bool SPLIT>
+// HEADS: the forward's head values are at hand (heads_fwd): the recompute skips the heads GEMM and layer 5, and layer 4
+// shares ONE commit group with the first backward stage (its epilogue forms dz5 = dA4 * g'(z4) straight from registers):
+// eight dependent stages per tile instead of ten.
+template <bool SPLIT, bool HEADS>
 __global__ void __launch_bounds__(kThreadsDec, 1)
 decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ mask32, const float* __restrict__ rays_d,
                    DecoderParams p, const float* __restrict__ grad_heads, float* __restrict__ grad_feats,
@@ -277,6 +280,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     for (int j = 0; j < 10; ++j) acc_small[j] = 0.0f;
     const uint32_t aW1 = umma::smem_u32(smem + oW1), aW2 = umma::smem_u32(smem + oW2), aW3 = umma::smem_u32(smem + oW3),
                    aW4 = umma::smem_u32(smem + oW4), aWh = umma::smem_u32(smem + oWh), aW5 = umma::smem_u32(smem + oW5);
+    constexpr uint32_t idf64 = umma::idesc_f16(128, 64, 0, 0, kOpBf16, kOpBf16);       // forward GEMM of layer 4 (HEADS path)
     // input-gradient GEMMs: A K-major (dz rows), B MN-major (weight tile: rows = K = out, cols = N = in)
     constexpr uint32_t idg64 = umma::idesc_f16(128, 64, 0, 1, kOpBf16, kOpBf16), idg32 = umma::idesc_f16(128, 32, 0, 1, kOpBf16, kOpBf16);
     // weight-gradient GEMMs: both operands MN-major, M = 64
@@ -367,9 +371,10 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
         float head[10], zh[7];
         f3 d = mk3(0.f, 0.f, 1.f);
         float dn = 1.0f;
-        // with the forward's head values at hand (heads_fwd) the recompute stops after layer 4: one dependent stage less
-        const bool have_heads = heads_fwd != nullptr;
-        // L2 prefetches: this tile's head gradients / head values (needed five stages from now) and the next tile's features
+        // with the forward's head values at hand (heads_fwd) the recompute stops after layer 3; layer 4 joins the first
+        // backward stage below
+        constexpr bool have_heads = HEADS;
+        // L2 prefetches: this tile's head gradients / head values (needed a few stages from now) and the next tile's features
         if (cg == 0 && live) {
             prefetch_l2(grad_heads + (size_t)n * 10);
             prefetch_l2(grad_heads + (size_t)n * 10 + 8);
@@ -385,14 +390,12 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
                 }
             }
         }
-        forward_tile<SPLIT, true, 4>(c, T, feats, rays_d, n, live, S, head, zh, d, dn, level_stride, !have_heads,
+        forward_tile<SPLIT, true, 4>(c, T, feats, rays_d, n, live, S, head, zh, d, dn, level_stride, have_heads ? 1 : 3,
                                      tail_pending ? &bar_tail : nullptr, tail_phase);
         if (tail_pending) { tail_phase ^= 1u; tail_pending = false; }
-        // (the L4 epilogue of every column group wrote a4_lo into the tile the head gradients go to next: without the L5
-        // stage in between, order those stores before column group 0 overwrites the rows)
-        if (have_heads) c.sync();
 
-        // ---- d(loss)/d(pre-activations) of the 7 heads and the 3 specular outputs (column group 0)
+        // ---- d(loss)/d(pre-activations) of the 7 heads and the 3 specular outputs (column group 0) -> Tdz (= LOb: H_lo /
+        // a4_lo, dead by now: with HEADS every MMA that read H_lo completed before the L3 epilogue and a4_lo is never formed)
         if (cg == 0) {
             float dzh[16], dzs[16];
             float gh[10];
@@ -446,24 +449,65 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
             for (int j = 0; j < 10; ++j) acc_small[j] += j < 7 ? dzh[j] : dzs[j - 7];
         }
         c.sync_operands();
-        // ---- B1: dA4 = dz_spec W5 ; dH[0:32] = dz_heads Wh ; dW5^T += a4^T dz_spec ; dWh^T += H^T dz_heads
-        if (lead_warp && umma::elect_one()) {
-            dgrad(cDa, adz, 1, adz, 3, aW5, aW5l, 1, idg64);
-            dgrad(cDc, adz, 0, adz, 2, aWh, aWh + 64, 1, idg32);     // dH[0:32] stays in TMEM until the B2 epilogue
-            umma::mma_commit(&bar);
-            wgrad_t(cGW5T, aa4, adz + 32, adz + 96, idwt16, first);  // behind the commit: this epilogue writes g4 / dz lo only
-            wgrad_t(cGWhT, aH, adz, adz + 64, idwt16, first);
-        }
-        c.wait_mma();
-        mul_inplace(cDa, T.g4, Tdzlo, acc_b4);                   // dz5 (+ its column sums = d/d b4)
-        c.sync_operands();
-        // ---- B2: dA3 = dz5 W4 ; dW4 += dz5^T a3
-        if (lead_warp && umma::elect_one()) {
-            dgrad(cDb, ag4, 0, adzlo, 0, aW4, aW4l, 4, idg64);
-            // the epilogue overwrites the dz lo tile: its part goes in front of the commit, the hi part behind it
-            if (SPLIT && kWgradDzLo) wgrad_part(cGW4, adzlo, aa3, idw64, first);
-            umma::mma_commit(&bar);
-            wgrad_part(cGW4, ag4, aa3, idw64, (SPLIT && kWgradDzLo) ? false : first);
+        if constexpr (HEADS) {
+            // ---- L4 + B1 in one commit group: Db = a3 W4^T ; dA4 = dz_spec W5 ; dH[0:32] = dz_heads Wh ; dWh^T += H^T dz_heads
+            if (lead_warp && umma::elect_one()) {
+                fwd_gemm<SPLIT>(tmem + cDb, aa3, 0, adzlo, 0, aW4, 0, aW4l, 0, 4, idf64, false);      // (adzlo = LOa holds a3_lo)
+                dgrad(cDa, adz, 1, adz, 3, aW5, aW5l, 1, idg64);
+                dgrad(cDc, adz, 0, adz, 2, aWh, aWh + 64, 1, idg32);     // dH[0:32] stays in TMEM until the B2 epilogue
+                umma::mma_commit(&bar);
+                wgrad_t(cGWhT, aH, adz, adz + 64, idwt16, first);        // behind the commit: this epilogue writes a4 / g4 / LOa only
+            }
+            c.wait_mma();
+            {   // a4 = g(z4) (hi part only: no layer reads a4_lo here), dz5 = dA4 * g'(z4) with g' still in registers
+                float z4[16];
+                umma::tmem_ld16(tmem + cDb + lane_addr + 16 * cg, z4);
+                umma::tmem_ld16(tmem + cDa + lane_addr + 16 * cg, v);
+                umma::tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float z = z4[j] + bias[oB4 + 16 * cg + j];
+                    const float a = gauss_act(z);
+                    z4[j] = a;
+                    v[j] *= -100.0f * z * a;
+                    acc_b4[j] += v[j];
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    umma::tile_store8_f16(T.a4, row, 2 * cg + q, z4 + 8 * q);
+                    store8_act<SPLIT>(T.g4, 2 * cg + q, Tdzlo, 2 * cg + q, row, v + 8 * q);
+                }
+            }
+            c.sync_operands();
+            // ---- B2: dA3 = dz5 W4 ; dW4 += dz5^T a3 ; dW5^T += a4^T dz_spec
+            if (lead_warp && umma::elect_one()) {
+                dgrad(cDb, ag4, 0, adzlo, 0, aW4, aW4l, 4, idg64);
+                // in FRONT of the commit: the epilogue overwrites what they read (Tdz with dH, a4 with dH_lo / the dz lo tile)
+                wgrad_t(cGW5T, aa4, adz + 32, adz + 96, idwt16, first);
+                if (SPLIT && kWgradDzLo) wgrad_part(cGW4, adzlo, aa3, idw64, first);
+                umma::mma_commit(&bar);
+                wgrad_part(cGW4, ag4, aa3, idw64, (SPLIT && kWgradDzLo) ? false : first);
+            }
+        } else {
+            // ---- B1: dA4 = dz_spec W5 ; dH[0:32] = dz_heads Wh ; dW5^T += a4^T dz_spec ; dWh^T += H^T dz_heads
+            if (lead_warp && umma::elect_one()) {
+                dgrad(cDa, adz, 1, adz, 3, aW5, aW5l, 1, idg64);
+                dgrad(cDc, adz, 0, adz, 2, aWh, aWh + 64, 1, idg32);     // dH[0:32] stays in TMEM until the B2 epilogue
+                umma::mma_commit(&bar);
+                wgrad_t(cGW5T, aa4, adz + 32, adz + 96, idwt16, first);  // behind the commit: this epilogue writes g4 / dz lo only
+                wgrad_t(cGWhT, aH, adz, adz + 64, idwt16, first);
+            }
+            c.wait_mma();
+            mul_inplace(cDa, T.g4, Tdzlo, acc_b4);                   // dz5 (+ its column sums = d/d b4)
+            c.sync_operands();
+            // ---- B2: dA3 = dz5 W4 ; dW4 += dz5^T a3
+            if (lead_warp && umma::elect_one()) {
+                dgrad(cDb, ag4, 0, adzlo, 0, aW4, aW4l, 4, idg64);
+                // the epilogue overwrites the dz lo tile: its part goes in front of the commit, the hi part behind it
+                if (SPLIT && kWgradDzLo) wgrad_part(cGW4, adzlo, aa3, idw64, first);
+                umma::mma_commit(&bar);
+                wgrad_part(cGW4, ag4, aa3, idw64, (SPLIT && kWgradDzLo) ? false : first);
+            }
         }
         c.wait_mma();                                            // (covers the B1 weight-gradient MMAs that read Tdz and a4)
         store_quarter(cDc, Tdz, Tdhlo, 0, acc_b2);               // dH[0:32] -> dz2 tile columns 0..31 (over the consumed dz_heads/spec)
@@ -672,6 +716,7 @@ __device__ unsigned g_gmax_slots[64];      // a ring: concurrent backward launch
 int g_gmax_next = 0;
 
 int g_fwd_inflight = 4; // forward tiles in flight per CTA: 4 (in-place operands, per-ray SH term; S >= kMinS4) or 2
+int g_bwd_merged = 1;   // backward with heads_fwd: layer 4 of the recompute shares a commit group with the first backward stage
 int g_split = 1;       // 1 = error-compensated bf16x3 operands in the forward GEMMs (default), 0 = plain bf16
 
 template <typename K>
@@ -687,6 +732,9 @@ int set_smem(K kernel, int bytes, const char* name)
 // ------------------------------- C ABI --------------------------------------
 // 0 = plain bf16 operands (fastest), 1 = bf16x3 split operands in the forward GEMMs (default)
 SNRF_API void snrf_decoder_set_precision(int split) { g_split = split ? 1 : 0; }
+// tuning hook: 1 (default) = the backward uses heads_fwd when given (no heads GEMM / layer 5 in the recompute, layer 4 merged
+// with the first backward stage); 0 = ignore heads_fwd and recompute everything (the round-1 stage sequence)
+SNRF_API void snrf_decoder_set_bwd_merged(int on) { g_bwd_merged = on ? 1 : 0; }
 // tuning hook: forward tiles in flight per CTA (4 = default, 2 = the round-1 kernel)
 SNRF_API void snrf_decoder_set_inflight(int n) { g_fwd_inflight = n == 2 ? 2 : 4; }
 
@@ -746,8 +794,10 @@ SNRF_API int snrf_decoder_bwd(const float* feats, const float* mask32, const flo
                    grad_params[12], grad_params[13], grad_params[14], grad_params[15]};
     static bool configured = false;
     if (!configured) {
-        int rc = set_smem(decoder_bwd_kernel<true>, bwd_smem<true>(), "snrf_decoder_bwd");
-        if (rc == 0) rc = set_smem(decoder_bwd_kernel<false>, bwd_smem<false>(), "snrf_decoder_bwd");
+        int rc = set_smem(decoder_bwd_kernel<true, true>, bwd_smem<true>(), "snrf_decoder_bwd");
+        if (rc == 0) rc = set_smem(decoder_bwd_kernel<true, false>, bwd_smem<true>(), "snrf_decoder_bwd");
+        if (rc == 0) rc = set_smem(decoder_bwd_kernel<false, true>, bwd_smem<false>(), "snrf_decoder_bwd");
+        if (rc == 0) rc = set_smem(decoder_bwd_kernel<false, false>, bwd_smem<false>(), "snrf_decoder_bwd");
         if (rc) return rc;
         configured = true;
     }
@@ -766,9 +816,10 @@ SNRF_API int snrf_decoder_bwd(const float* feats, const float* mask32, const flo
         if (gx > snrf_sm_count() * 8) gx = snrf_sm_count() * 8;
         grad_absmax_kernel<<<gx > 0 ? gx : 1, 256, 0, s>>>(grad_heads, N, S, ray_valid, slot);
     }
-    if (g_split)
-        decoder_bwd_kernel<true><<<grid, kThreadsDec, bwd_smem<true>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot, heads_fwd);
-    else
-        decoder_bwd_kernel<false><<<grid, kThreadsDec, bwd_smem<false>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot, heads_fwd);
+    const bool merged = heads_fwd != nullptr && g_bwd_merged;
+#define SNRF_DEC_BWD(SPLIT, HEADS) decoder_bwd_kernel<SPLIT, HEADS><<<grid, kThreadsDec, bwd_smem<SPLIT>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot, merged ? heads_fwd : nullptr)
+    if (g_split) { if (merged) SNRF_DEC_BWD(true, true); else SNRF_DEC_BWD(true, false); }
+    else         { if (merged) SNRF_DEC_BWD(false, true); else SNRF_DEC_BWD(false, false); }
+#undef SNRF_DEC_BWD
     SNRF_RETURN_LAUNCH("snrf_decoder_bwd");
 }

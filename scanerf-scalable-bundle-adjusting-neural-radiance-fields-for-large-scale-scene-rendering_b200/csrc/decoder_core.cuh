@@ -333,10 +333,11 @@ __device__ __forceinline__ void store_input_row(const Tiles& T, int row, int cg,
 // A0 / LOb.  Writes the operand tiles; the threads with cg == 0 return sigma/diffuse/tint activated in
 // head[0..6] (torch semantics) and their pre-activations in zh[0..6]; the specular pre-activations are
 // left in TMEM columns cDh..cDh+2.
-// with_l5 = false (backward, when the forward's head values are at hand): stop after the L4 epilogue -- the last layer's
+// stages = 3: everything; 2: stop after the L4 epilogue; 1 (backward, when the forward's head values are at hand): stop after
+// the L3 epilogue and skip the heads GEMM -- the caller runs layer 4 together with the first backward stage, the last layer's
 // output is only needed for the specular sigmoid, whose derivative follows from the saved head value.
 template <bool SPLIT, bool TRAIN, int NCG>
-__device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& T, float* head, float* zh, bool with_l5 = true)
+__device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& T, float* head, float* zh, int stages = 3)
 {
     constexpr int W = 64 / NCG, CH = W / 8;
     unsigned char* smem = c.smem;
@@ -393,13 +394,13 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
     c.sync_operands();
     // ---- heads: Dh = H[0:32] Wh^T (K = 32, N = 16);   L3: Da = [H[32:64] | SH] W3^T (K = 48)
     if (c.leader()) {
-        fwd_gemm<SPLIT>(tmem + cDh, aH, 0, aLOb, 0, aWh, 0, aWh, 2, 2, id16, false);
+        if (stages != 1) fwd_gemm<SPLIT>(tmem + cDh, aH, 0, aLOb, 0, aWh, 0, aWh, 2, 2, id16, false);
         fwd_gemm<SPLIT>(tmem + cDa, aH, 2, aLOb, 2, aW3, 0, aW3l, 0, 2, id64, false);
         fwd_gemm<SPLIT>(tmem + cDa, aA0, 2, aA0, 3, aW3, 2, aW3l, 2, 1, id64, true);
         umma::mma_commit(c.bar);
     }
     c.wait_mma();
-    if (cg == 0) {
+    if (cg == 0 && stages != 1) {
         float z[16];
         umma::tmem_ld16(tmem + cDh + lane_addr, z);
         umma::tc_wait_ld();
@@ -413,6 +414,7 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
         }
     }
     gauss_epilogue(cDa, oB3, T.a3, T.LOa, T.g3);
+    if (stages == 1) return;
     c.sync_operands();
     // ---- L4: Db = a3 W4^T (K = 64)
     if (c.leader()) {
@@ -421,7 +423,7 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
     }
     c.wait_mma();
     gauss_epilogue(cDb, oB4, T.a4, T.LOb, T.g4);
-    if (!with_l5) return;
+    if (stages == 2) return;
     c.sync_operands();
     // ---- L5: Dh = a4 W5^T (K = 64, N = 16)
     if (c.leader()) {
@@ -437,7 +439,7 @@ __device__ __forceinline__ void forward_layers(Ctx<SPLIT, NCG>& c, const Tiles& 
 template <bool SPLIT, bool TRAIN, int NCG>
 __device__ __forceinline__ void forward_tile(Ctx<SPLIT, NCG>& c, const Tiles& T, const float* __restrict__ feats,
                                              const float* __restrict__ rays_d, int n, bool live, int S, float* head, float* zh,
-                                             f3& d, float& dn, long long level_stride, bool with_l5 = true,
+                                             f3& d, float& dn, long long level_stride, int stages = 3,
                                              uint64_t* pending_bar = nullptr, uint32_t pending_phase = 0)
 {
     constexpr int NX = 32 / NCG;                // features per thread
@@ -480,7 +482,7 @@ __device__ __forceinline__ void forward_tile(Ctx<SPLIT, NCG>& c, const Tiles& T,
         umma::tc_fence_after();
     }
     store_input_row<SPLIT, NCG>(T, c.row, cg, x, sh + 8 * (shc & 1));
-    forward_layers<SPLIT, TRAIN, NCG>(c, T, head, zh, with_l5);
+    forward_layers<SPLIT, TRAIN, NCG>(c, T, head, zh, stages);
 }
 
 // =====================================================================================================================

@@ -106,11 +106,17 @@ def test_decoder_forward_matches_torch(N, S, split):
         assert mean_rel < rel_tol, f"{k}: mean relative err {mean_rel}"
 
 
+@pytest.mark.parametrize("merged", [1, 0])
 @pytest.mark.parametrize("split", [True, False])
 @pytest.mark.parametrize("N,S", [(128, 128), (128 * 5 + 17, 32), (4096 * 3, 128)])
-def test_decoder_backward_matches_torch(N, S, split):
+def test_decoder_backward_matches_torch(N, S, split, merged):
+    """merged = 1 (default): the backward uses the forward's head values (no heads GEMM / layer 5 in the recompute, layer 4 in
+    one commit group with the first backward stage); merged = 0: everything recomputed, the round-1 stage sequence."""
+    import ctypes
     load_pkg()
+    import scanerf_b200_capi as capi
     from hashgrid import _field
+    capi.lib().snrf_decoder_set_bwd_merged(ctypes.c_int(merged))
     dec, params, feats, mask, rays_d = _decoder_and_inputs(N, S, N + 1)
     g = torch.Generator().manual_seed(3)
     cot = torch.randn(N, 10, generator=g)
@@ -132,6 +138,7 @@ def test_decoder_backward_matches_torch(N, S, split):
         torch.cuda.synchronize()
     finally:
         _field.set_precision(True)
+        capi.lib().snrf_decoder_set_bwd_merged(ctypes.c_int(1))
 
     def rel(a, b):      # relative error in the L2 sense
         return float((a.cpu() - b).norm() / b.norm().clamp_min(1e-20))
