@@ -209,8 +209,10 @@ int snrf_decoder_fwd(const float* feats, const float* mask32, const float* rays_
 void snrf_decoder_set_precision(int split);
 /* tuning hook: forward tiles in flight per CTA (4 = default: in-place operand tiles + per-ray SH term, S >= 16; 2 = round-1 kernel) */
 void snrf_decoder_set_inflight(int n);
-/* tuning hook: 1 (default) = snrf_decoder_bwd uses heads_fwd when given (the recompute skips the heads GEMM and layer 5, layer 4
- * shares a commit group with the first backward stage); 0 = recompute everything */
+/* tuning hook: how snrf_decoder_bwd uses heads_fwd when given.  2 (default) = layer 2 (linear, no activation) folded into its
+ * consumers: six dependent stages per tile, dW2 / dW3[:, :32] / dW_heads / db2 composed once per CTA from two accumulators;
+ * 1 = the recompute skips the heads GEMM and layer 5 and layer 4 shares a commit group with the first backward stage;
+ * 0 = recompute everything (the round-1 stage sequence) */
 void snrf_decoder_set_bwd_merged(int on);
 /* Backward of snrf_decoder_fwd (autograd of network.py:151-190).  grad_heads[N,10] (column order
  * of heads) -> grad_feats[N,32] WRITTEN; grad_rays_d[R,3] ACCUMULATED (may be NULL; the view

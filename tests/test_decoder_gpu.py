@@ -106,12 +106,13 @@ def test_decoder_forward_matches_torch(N, S, split):
         assert mean_rel < rel_tol, f"{k}: mean relative err {mean_rel}"
 
 
-@pytest.mark.parametrize("merged", [1, 0])
+@pytest.mark.parametrize("merged", [2, 1, 0])
 @pytest.mark.parametrize("split", [True, False])
 @pytest.mark.parametrize("N,S", [(128, 128), (128 * 5 + 17, 32), (4096 * 3, 128)])
 def test_decoder_backward_matches_torch(N, S, split, merged):
-    """merged = 1 (default): the backward uses the forward's head values (no heads GEMM / layer 5 in the recompute, layer 4 in
-    one commit group with the first backward stage); merged = 0: everything recomputed, the round-1 stage sequence."""
+    """merged = 2 (default): layer 2 folded into its consumers (six dependent stages, dW2 / dW3a / dW_heads / db2 composed per
+    CTA); 1: the backward uses the forward's head values (no heads GEMM / layer 5 in the recompute, layer 4 in one commit group
+    with the first backward stage); 0: everything recomputed, the round-1 stage sequence."""
     import ctypes
     load_pkg()
     import scanerf_b200_capi as capi
@@ -138,7 +139,7 @@ def test_decoder_backward_matches_torch(N, S, split, merged):
         torch.cuda.synchronize()
     finally:
         _field.set_precision(True)
-        capi.lib().snrf_decoder_set_bwd_merged(ctypes.c_int(1))
+        capi.lib().snrf_decoder_set_bwd_merged(ctypes.c_int(2))
 
     def rel(a, b):      # relative error in the L2 sense
         return float((a.cpu() - b).norm() / b.norm().clamp_min(1e-20))

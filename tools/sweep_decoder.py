@@ -30,7 +30,7 @@ def main():
     lib = capi.lib()
     rows = []
     names = ("snrf_decoder_fwd", "snrf_decoder_bwd", "snrf_field_encode_fwd", "snrf_field_encode_bwd_adam")
-    for merged in (1, 0, 1, 0, 1):
+    for merged in (2, 1, 0, 2, 1, 2):
         lib.snrf_decoder_set_bwd_merged(ctypes.c_int(merged))
         ms, loss = bench._time_steps(step, batches, 4)
         capi.time_calls(names)
@@ -43,7 +43,7 @@ def main():
             row[k + "_ms"] = sum(t.get(k, [])) / max(len(t.get(k, [])), 1)
         rows.append(row)
         print(json.dumps(row), flush=True)
-    lib.snrf_decoder_set_bwd_merged(ctypes.c_int(1))
+    lib.snrf_decoder_set_bwd_merged(ctypes.c_int(2))
     with open(args.out, "w") as fh:
         fh.write(json.dumps(rows) + "\n")
 
