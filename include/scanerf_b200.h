@@ -209,6 +209,9 @@ int snrf_decoder_fwd(const float* feats, const float* mask32, const float* rays_
 void snrf_decoder_set_precision(int split);
 /* tuning hook: forward tiles in flight per CTA (4 = default: in-place operand tiles + per-ray SH term, S >= 16; 2 = round-1 kernel) */
 void snrf_decoder_set_inflight(int n);
+/* tuning hook: 1 (default) = the four-tile forward composes layer 2 (linear, no activation) into its consumers when it
+ * stages the weights: z3 and the heads come straight from a1, four dependent stages per tile instead of five */
+void snrf_decoder_set_fwd_fold(int on);
 /* tuning hook: how snrf_decoder_bwd uses heads_fwd when given.  2 (default) = layer 2 (linear, no activation) folded into its
  * consumers: six dependent stages per tile, dW2 / dW3[:, :32] / dW_heads / db2 composed once per CTA from two accumulators;
  * 1 = the recompute skips the heads GEMM and layer 5 and layer 4 shares a commit group with the first backward stage;
@@ -315,6 +318,8 @@ void snrf_infer_set_precision(int split);
 void snrf_infer_set_inflight(int tiles);
 /* tuning hook: tiles in flight per CTA of the single-tile decode pass (4 = default, 2 = the round-1 kernel) */
 void snrf_infer_set_decode_inflight(int n);
+/* tuning hook: 1 (default) = the four-tile decode pass composes decoder layer 2 into its consumers (as snrf_decoder_set_fwd_fold) */
+void snrf_infer_set_fold(int on);
 /* tuning hook: 1 (default) = multi-pass paths (single-tile two-pass, multi-tile grouped), 0 = the fused kernel,
  * 2 = the grouped (compacting) path also for single-tile scenes */
 void snrf_infer_set_two_pass(int on);

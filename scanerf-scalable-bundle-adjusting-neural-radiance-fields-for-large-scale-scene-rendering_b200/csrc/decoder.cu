@@ -107,7 +107,7 @@ decoder_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
 
 // ------------------------------- forward, four tiles in flight ---------------
 // (decoder_core.cuh: forward_layers4; same results as decoder_fwd_kernel, S >= kMinS4)
-template <bool SPLIT>
+template <bool SPLIT, bool FOLD>
 __global__ void __launch_bounds__(kThreadsDec, 1)
 decoder_fwd4_kernel(const float* __restrict__ feats, const float* __restrict__ mask32, const float* __restrict__ rays_d,
                     DecoderParams p, float* __restrict__ out, int N, int S, int num_tiles, long long level_stride,
@@ -122,6 +122,7 @@ decoder_fwd4_kernel(const float* __restrict__ feats, const float* __restrict__ m
     stage_all_weights<SPLIT>(smem, p, mask32, tid, kThreadsDec);
     float* w3sh = reinterpret_cast<float*>(smem + off_w3sh<SPLIT>());
     stage_w3sh(w3sh, p, tid, kThreadsDec);
+    if (FOLD) stage_fold_weights4<SPLIT>(smem, p, reinterpret_cast<float*>(smem + off_tiles4<SPLIT>()), tid, kThreadsDec);
     if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);
     if (tid == 0) {
         for (int g = 0; g < kGroups4; ++g) umma::mbar_init(&bars[g], 1);
@@ -183,7 +184,7 @@ decoder_fwd4_kernel(const float* __restrict__ feats, const float* __restrict__ m
         ray_vectors4<false>(rb, w3sh, rays_d, ray0, last - ray0 + 1, c.gtid);
         const int my_ray = (live ? n / S : ray0) - ray0;
         float head[10], zh[7];
-        forward_layers4<SPLIT>(c, smem, P, Q, x, rb + my_ray * 64, head, zh);
+        forward_layers4<SPLIT, FOLD>(c, smem, P, Q, x, rb + my_ray * 64, head, zh);
         float z[16];
         umma::tmem_ld16(c.tmem + c4Dh + c.lane_addr, z);
         umma::tc_wait_ld();
@@ -715,17 +716,6 @@ constexpr int smem_bytes = off_tiles + kTiles * kTile + 1024;
 // TMEM columns: two working accumulators + d[SH], then the persistent gradient accumulators
 constexpr int cDa = 0, cDb = 64, cSH = 128, gW1 = 144, gG = 192, gW3b = 256, gW4 = 272, gGhT = 336, gW5T = 352;   // ends at 368
 }  // namespace fold
-
-// element (r, c) of a Linear weight [out, in] in either parameter layout
-__device__ __forceinline__ float w_at(const float* __restrict__ W, int r, int c, int out, int in, int flat)
-{
-    return flat ? W[c * out + r] : W[r * in + c];
-}
-// row h of the stacked heads matrix Wh [7 x 32] = (sigma, diffuse3, tint3)
-__device__ __forceinline__ float wh_at(const DecoderParams& p, int h, int k)
-{
-    return h == 0 ? w_at(p.Ws, 0, k, 1, 32, p.flat) : (h < 4 ? w_at(p.Wd, h - 1, k, 3, 32, p.flat) : w_at(p.Wt, h - 4, k, 3, 32, p.flat));
-}
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(kThreadsDec, 1)
@@ -1280,6 +1270,7 @@ __device__ unsigned g_gmax_slots[64];      // a ring: concurrent backward launch
 int g_gmax_next = 0;
 
 int g_fwd_inflight = 4; // forward tiles in flight per CTA: 4 (in-place operands, per-ray SH term; S >= kMinS4) or 2
+int g_fwd_fold = 1;     // four-tile forward: layer 2 folded into its consumers (four dependent stages per tile instead of five)
 int g_bwd_merged = 2;   // backward with heads_fwd: 2 = layer 2 folded away (decoder_bwd_fold_kernel), 1 = layer 4 merged with the first backward stage, 0 = everything recomputed
 int g_split = 1;       // 1 = error-compensated bf16x3 operands in the forward GEMMs (default), 0 = plain bf16
 
@@ -1299,6 +1290,8 @@ SNRF_API void snrf_decoder_set_precision(int split) { g_split = split ? 1 : 0; }
 // tuning hook: 1 (default) = the backward uses heads_fwd when given (no heads GEMM / layer 5 in the recompute, layer 4 merged
 // with the first backward stage); 0 = ignore heads_fwd and recompute everything (the round-1 stage sequence)
 SNRF_API void snrf_decoder_set_bwd_merged(int on) { g_bwd_merged = on < 0 ? 0 : (on > 2 ? 2 : on); }
+// tuning hook: 1 (default) = the four-tile forward folds layer 2 into its consumers (decoder_core.cuh: forward_layers4<., FOLD>)
+SNRF_API void snrf_decoder_set_fwd_fold(int on) { g_fwd_fold = on ? 1 : 0; }
 // tuning hook: forward tiles in flight per CTA (4 = default, 2 = the round-1 kernel)
 SNRF_API void snrf_decoder_set_inflight(int n) { g_fwd_inflight = n == 2 ? 2 : 4; }
 
@@ -1315,8 +1308,10 @@ SNRF_API int snrf_decoder_fwd(const float* feats, const float* mask32, const flo
     if (!configured) {
         int rc = set_smem(decoder_fwd_kernel<true>, fwd_smem<true>(), "snrf_decoder_fwd");
         if (rc == 0) rc = set_smem(decoder_fwd_kernel<false>, fwd_smem<false>(), "snrf_decoder_fwd");
-        if (rc == 0) rc = set_smem(decoder_fwd4_kernel<true>, fwd4_smem<true>(), "snrf_decoder_fwd");
-        if (rc == 0) rc = set_smem(decoder_fwd4_kernel<false>, fwd4_smem<false>(), "snrf_decoder_fwd");
+        if (rc == 0) rc = set_smem(decoder_fwd4_kernel<true, true>, fwd4_smem<true>(), "snrf_decoder_fwd");
+        if (rc == 0) rc = set_smem(decoder_fwd4_kernel<true, false>, fwd4_smem<true>(), "snrf_decoder_fwd");
+        if (rc == 0) rc = set_smem(decoder_fwd4_kernel<false, true>, fwd4_smem<false>(), "snrf_decoder_fwd");
+        if (rc == 0) rc = set_smem(decoder_fwd4_kernel<false, false>, fwd4_smem<false>(), "snrf_decoder_fwd");
         if (rc) return rc;
         configured = true;
     }
@@ -1325,10 +1320,10 @@ SNRF_API int snrf_decoder_fwd(const float* feats, const float* mask32, const flo
     int grid = snrf_sm_count();                     // one 16-warp CTA per SM
     if (g_fwd_inflight == 4 && S >= kMinS4) {       // four tiles in flight each
         if (grid > (num_tiles + 3) / 4) grid = (num_tiles + 3) / 4;
-        if (g_split)
-            decoder_fwd4_kernel<true><<<grid, kThreadsDec, fwd4_smem<true>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
-        else
-            decoder_fwd4_kernel<false><<<grid, kThreadsDec, fwd4_smem<false>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid);
+#define SNRF_DEC_FWD4(SPLIT, FOLD) decoder_fwd4_kernel<SPLIT, FOLD><<<grid, kThreadsDec, fwd4_smem<SPLIT>(), s>>>(feats, mask32, rays_d, p, heads_out, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid)
+        if (g_split) { if (g_fwd_fold) SNRF_DEC_FWD4(true, true); else SNRF_DEC_FWD4(true, false); }
+        else         { if (g_fwd_fold) SNRF_DEC_FWD4(false, true); else SNRF_DEC_FWD4(false, false); }
+#undef SNRF_DEC_FWD4
         SNRF_RETURN_LAUNCH("snrf_decoder_fwd");
     }
     if (grid > (num_tiles + 1) / 2) grid = (num_tiles + 1) / 2;   // two tiles in flight each

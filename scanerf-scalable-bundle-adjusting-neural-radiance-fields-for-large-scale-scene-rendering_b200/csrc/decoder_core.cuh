@@ -557,10 +557,67 @@ __device__ inline void stage_w3sh(float* dst, const DecoderParams& p, int tid, i
     }
 }
 
+// element (r, c) of a Linear weight [out, in] in either parameter layout
+__device__ __forceinline__ float w_at(const float* __restrict__ W, int r, int c, int out, int in, int flat)
+{
+    return flat ? W[c * out + r] : W[r * in + c];
+}
+// row h of the stacked heads matrix Wh [7 x 32] = (sigma, diffuse3, tint3)
+__device__ __forceinline__ float wh_at(const DecoderParams& p, int h, int k)
+{
+    return h == 0 ? w_at(p.Ws, 0, k, 1, 32, p.flat) : (h < 4 ? w_at(p.Wd, h - 1, k, 3, 32, p.flat) : w_at(p.Wt, h - 4, k, 3, 32, p.flat));
+}
+
+// Composed weights of the FOLD forward, written over what stage_all_weights left (call after it; ends with the data in place
+// but NOT synchronised: the caller's fence + __syncthreads() follows).  `scratch`: >= 18 KB of shared memory not in use yet
+// (the operand-tile area).  W32 = W3[:, 0:32] W2[32:64, :] -> the W2 tiles; Wh2 = Wh W2[0:32, :] -> the Wh tile (hi) and
+// rows 0..15 of the W3-lo tile (lo); b32 = W3[:, 0:32] b2[32:64] + b3 -> the b3 slot; bh2 = Wh b2[0:32] + bh -> the head slot.
+template <bool SPLIT>
+__device__ void stage_fold_weights4(unsigned char* smem, const DecoderParams& p, float* scratch, int tid, int nthreads)
+{
+    float* s32 = scratch;                 // [64][64]
+    float* sh2 = scratch + 64 * 64;       // [7][64]
+    for (int i = tid; i < 64 * 64; i += nthreads) {
+        const int o = i >> 6, j = i & 63;
+        float acc = 0.0f;
+        for (int k = 0; k < 32; ++k) acc += w_at(p.W3, o, k, 64, 48, p.flat) * w_at(p.W2, 32 + k, j, 64, 64, p.flat);
+        s32[i] = acc;
+    }
+    for (int i = tid; i < 7 * 64; i += nthreads) {
+        const int h = i >> 6, j = i & 63;
+        float acc = 0.0f;
+        for (int k = 0; k < 32; ++k) acc += wh_at(p, h, k) * w_at(p.W2, k, j, 64, 64, p.flat);
+        sh2[i] = acc;
+    }
+    __syncthreads();                      // (also: stage_all_weights' stores to the tiles overwritten below are complete)
+    float* b = reinterpret_cast<float*>(smem + off_bias<SPLIT>());
+    for (int i = tid; i < 64 + 7; i += nthreads) {
+        if (i < 64) {
+            float v = p.b3[i];
+            for (int k = 0; k < 32; ++k) v += w_at(p.W3, i, k, 64, 48, p.flat) * p.b2[32 + k];
+            b[oB3 + i] = v;
+        } else {
+            const int h = i - 64;
+            float v = h == 0 ? p.bs[0] : (h < 4 ? p.bd[h - 1] : p.bt[h - 4]);
+            for (int k = 0; k < 32; ++k) v += wh_at(p, h, k) * p.b2[k];
+            b[oBh + h] = v;
+        }
+    }
+    zero_tile_rows(smem + oWh, 16, tid, nthreads);
+    if (SPLIT) zero_tile_rows(smem + oW3l, 16, tid, nthreads);
+    __syncthreads();
+    stage_weight<SPLIT>(smem + oW2, smem + oW2l, 0, s32, 64, 64, 0, tid, nthreads);
+    stage_weight<SPLIT>(smem + oWh, smem + oW3l, 0, sh2, 7, 64, 0, tid, nthreads);
+}
+
 // The layers of one tile, operands in place in (P, Q) = (hi, lo).  x (already masked) is this thread's whole input row;
 // rb = this row's ray vector W3_sh SH(d) (64 floats in shared memory).  Returns sigma / diffuse / tint activated in
 // head[0..6] and leaves the specular pre-activations in TMEM columns c4Dh .. c4Dh + 2 (after the last wait).
-template <bool SPLIT>
+// FOLD: layer 2 (linear, no activation) is composed into its consumers when the weights are staged (stage_fold_weights4):
+// the W2 tiles hold W32 = W3[:, 0:32] W2[32:64, :], the Wh tile / the first rows of the W3-lo tile hold Wh2 = Wh W2[0:32, :]
+// (hi / lo), the b3 / head bias slots the composed biases -- z3 and the heads come straight from a1 in ONE stage, H is never
+// formed: four dependent stages per tile instead of five, 12 MMAs and one 64-column epilogue less.
+template <bool SPLIT, bool FOLD = false>
 __device__ __forceinline__ void forward_layers4(Ctx4& c, unsigned char* smem, unsigned char* P, unsigned char* Q, const float* x,
                                                 const float* rb, float* head, float* zh)
 {
@@ -604,17 +661,25 @@ __device__ __forceinline__ void forward_layers4(Ctx4& c, unsigned char* smem, un
     };
     epilogue(oB1, nullptr, true);                                         // a1
     c.sync_operands();
-    if (c.leader()) {          // L2: D = a1 W2^T (K = 64)
-        fwd_gemm<SPLIT>(tmem + c4D, aP, 0, aQ, 0, aW2, 0, aW2l, 0, 4, id64, false);
-        umma::mma_commit(c.bar);
-    }
-    c.wait_mma();
-    epilogue(oB2, nullptr, false);                                        // H
-    c.sync_operands();
-    if (c.leader()) {          // heads: Dh = H[0:32] Wh^T (K = 32, N = 16);  L3: D = H[32:64] W3[:, 0:32]^T (K = 32)
-        fwd_gemm<SPLIT>(tmem + c4Dh, aP, 0, aQ, 0, aWh, 0, aWh, 2, 2, id16, false);
-        fwd_gemm<SPLIT>(tmem + c4D, aP, 2, aQ, 2, aW3, 0, aW3l, 0, 2, id64, false);
-        umma::mma_commit(c.bar);
+    if (FOLD) {
+        if (c.leader()) {      // heads: Dh = a1 Wh2^T (K = 64, N = 16);  z3: D = a1 W32^T (K = 64)
+            fwd_gemm<SPLIT>(tmem + c4Dh, aP, 0, aQ, 0, aWh, 0, aW3l, 0, 4, id16, false);
+            fwd_gemm<SPLIT>(tmem + c4D, aP, 0, aQ, 0, aW2, 0, aW2l, 0, 4, id64, false);
+            umma::mma_commit(c.bar);
+        }
+    } else {
+        if (c.leader()) {          // L2: D = a1 W2^T (K = 64)
+            fwd_gemm<SPLIT>(tmem + c4D, aP, 0, aQ, 0, aW2, 0, aW2l, 0, 4, id64, false);
+            umma::mma_commit(c.bar);
+        }
+        c.wait_mma();
+        epilogue(oB2, nullptr, false);                                        // H
+        c.sync_operands();
+        if (c.leader()) {          // heads: Dh = H[0:32] Wh^T (K = 32, N = 16);  L3: D = H[32:64] W3[:, 0:32]^T (K = 32)
+            fwd_gemm<SPLIT>(tmem + c4Dh, aP, 0, aQ, 0, aWh, 0, aWh, 2, 2, id16, false);
+            fwd_gemm<SPLIT>(tmem + c4D, aP, 2, aQ, 2, aW3, 0, aW3l, 0, 2, id64, false);
+            umma::mma_commit(c.bar);
+        }
     }
     c.wait_mma();
     {

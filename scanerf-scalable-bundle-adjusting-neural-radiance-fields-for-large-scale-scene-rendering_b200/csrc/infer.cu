@@ -456,7 +456,7 @@ infer_decode_kernel(InferArgs a, long long n0, int Nc, const float2* __restrict_
 
 // The same decode pass with FOUR tiles in flight per CTA (decoder_core.cuh: forward_layers4 -- operand tiles in place, the
 // SH term of the first directional layer added per ray in fp32): one thread per sample row.  Needs a.S >= kMinS4.
-template <bool SPLIT, int MODE>
+template <bool SPLIT, int MODE, bool FOLD>
 __global__ void __launch_bounds__(kThreadsDec, 1)
 infer_decode4_kernel(InferArgs a, long long n0, int Nc, const float2* __restrict__ feats_lm, const float2* __restrict__ aux,
                      const unsigned char* __restrict__ state, int num_tiles)
@@ -470,6 +470,7 @@ infer_decode4_kernel(InferArgs a, long long n0, int Nc, const float2* __restrict
     stage_all_weights<SPLIT>(smem, prm, nullptr, tid, kThreadsDec);
     float* w3sh = reinterpret_cast<float*>(smem + off_w3sh<SPLIT>());
     stage_w3sh(w3sh, prm, tid, kThreadsDec);
+    if (FOLD) stage_fold_weights4<SPLIT>(smem, prm, reinterpret_cast<float*>(smem + off_tiles4<SPLIT>()), tid, kThreadsDec);
     if (warp == 0) umma::tmem_alloc<512>(&tmem_slot);
     if (tid == 0) {
         for (int g = 0; g < kGroups4; ++g) umma::mbar_init(&bars[g], 1);
@@ -518,7 +519,7 @@ infer_decode4_kernel(InferArgs a, long long n0, int Nc, const float2* __restrict
             ray_vectors4<true>(rb, w3sh, a.rays_d, ray0, nrays, c.gtid);
             const int my_ray = active ? (int)(n / a.S) - ray0 : 0;
             float head[10], zh[7];
-            forward_layers4<SPLIT>(c, smem, P, Q, x, rb + my_ray * 64, head, zh);
+            forward_layers4<SPLIT, FOLD>(c, smem, P, Q, x, rb + my_ray * 64, head, zh);
             float zs[16];
             umma::tmem_ld16(c.tmem + c4Dh + c.lane_addr, zs);
             umma::tc_wait_ld();
@@ -780,6 +781,7 @@ work_combine_kernel(InferArgs a, long long n0, int Nc, Work w)
     }
 }
 
+int g_infer_fold = 1;        // the four-tile decode pass folds layer 2 into its consumers (decoder_core.cuh: forward_layers4<., FOLD>)
 int g_decode_inflight = 4;   // tiles in flight per CTA of the single-tile decode pass (4: infer_decode4_kernel, 2: infer_decode_kernel)
 int g_infer_split = 1;
 int g_infer_two_pass = 1;     // single-tile scenes: level-major encode pass + decoder pass (tuning hook)
@@ -826,8 +828,10 @@ int launch_two_pass(const InferArgs& a, void* stream, const char* name)
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(infer_decode_kernel<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<true>());
         if (e == cudaSuccess) e = cudaFuncSetAttribute(infer_decode_kernel<false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem<false>());
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(infer_decode4_kernel<true, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd4_smem<true>());
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(infer_decode4_kernel<false, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd4_smem<false>());
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(infer_decode4_kernel<true, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd4_smem<true>());
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(infer_decode4_kernel<false, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd4_smem<false>());
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(infer_decode4_kernel<true, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd4_smem<true>());
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(infer_decode4_kernel<false, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd4_smem<false>());
         if (e != cudaSuccess) { snrf_set_error("%s: %s", name, cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
@@ -854,8 +858,13 @@ int launch_two_pass(const InferArgs& a, void* stream, const char* name)
         int grid = sms;
         if (g_decode_inflight == 4 && a.S >= kMinS4) {           // four tiles in flight per CTA
             if (grid > (num_tiles + 3) / 4) grid = (num_tiles + 3) / 4;
-            if (g_infer_split) infer_decode4_kernel<true, MODE><<<grid, kThreadsDec, fwd4_smem<true>(), s>>>(a, n0, Nc, feats, aux, state, num_tiles);
-            else infer_decode4_kernel<false, MODE><<<grid, kThreadsDec, fwd4_smem<false>(), s>>>(a, n0, Nc, feats, aux, state, num_tiles);
+            if (g_infer_fold) {
+                if (g_infer_split) infer_decode4_kernel<true, MODE, true><<<grid, kThreadsDec, fwd4_smem<true>(), s>>>(a, n0, Nc, feats, aux, state, num_tiles);
+                else infer_decode4_kernel<false, MODE, true><<<grid, kThreadsDec, fwd4_smem<false>(), s>>>(a, n0, Nc, feats, aux, state, num_tiles);
+            } else {
+                if (g_infer_split) infer_decode4_kernel<true, MODE, false><<<grid, kThreadsDec, fwd4_smem<true>(), s>>>(a, n0, Nc, feats, aux, state, num_tiles);
+                else infer_decode4_kernel<false, MODE, false><<<grid, kThreadsDec, fwd4_smem<false>(), s>>>(a, n0, Nc, feats, aux, state, num_tiles);
+            }
             continue;
         }
         if (grid > (num_tiles + 1) / 2) grid = (num_tiles + 1) / 2;
@@ -939,6 +948,8 @@ int launch(const InferArgs& a, int nb, void* stream, const char* name)
 // ------------------------------- C ABI --------------------------------------
 // tiles in flight per CTA of the single-tile decode pass: 4 (default) or 2 (round-1 kernel)
 SNRF_API void snrf_infer_set_decode_inflight(int n) { g_decode_inflight = n == 2 ? 2 : 4; }
+// tuning hook: 1 (default) = the four-tile decode pass composes layer 2 into its consumers (four dependent stages per tile)
+SNRF_API void snrf_infer_set_fold(int on) { g_infer_fold = on ? 1 : 0; }
 SNRF_API void snrf_infer_set_precision(int split) { g_infer_split = split ? 1 : 0; }
 SNRF_API void snrf_infer_set_inflight(int tiles) { g_infer_inflight = tiles == 2 ? 2 : 1; }
 SNRF_API void snrf_infer_set_two_pass(int on) { g_infer_two_pass = on == 2 ? 2 : (on ? 1 : 0); }

@@ -51,8 +51,8 @@ def _decoder_and_inputs(N, S, seed):
 @pytest.mark.parametrize("N,S,masked", [(128, 128, False), (128 * 37 + 5, 64, True), (4096 * 5 + 77, 16, True), (128 * 9, 100, False),
                                         (128 * 700 + 3, 128, False)])
 def test_four_tiles_in_flight_forward_equals_two_tile_forward(N, S, masked):
-    """The forward with four tiles in flight (in-place operand tiles, the SH term of layer 3 added per ray in fp32) against
-    the round-1 two-tile kernel: same heads (the SH term is exact instead of split-compensated, everything else is the same
+    """The forward with four tiles in flight (in-place operand tiles, the SH term of layer 3 added per ray in fp32; with and
+    without layer 2 folded into its consumers) against the round-1 two-tile kernel: same heads (the SH term is exact instead of split-compensated, everything else is the same
     arithmetic), level-major and row-major inputs, ragged last tile, rays masked out, tiles that straddle many rays."""
     load_pkg()
     import scanerf_b200_capi as capi
@@ -66,17 +66,22 @@ def test_four_tiles_in_flight_forward_equals_two_tile_forward(N, S, masked):
         if lm:
             f = f.reshape(N, 16, 2).permute(1, 0, 2).contiguous()
         outs = []
-        for inflight in (2, 4):
+        for inflight, fold in ((2, 0), (4, 0), (4, 1)):
             capi.lib().snrf_decoder_set_inflight(capi.c_int(inflight))
+            capi.lib().snrf_decoder_set_fwd_fold(capi.c_int(fold))
             outs.append(_field.decoder_forward(f, mask.to(dev), rays_d.to(dev), S, pd, valid))
         capi.lib().snrf_decoder_set_inflight(capi.c_int(4))
+        capi.lib().snrf_decoder_set_fwd_fold(capi.c_int(1))
         torch.cuda.synchronize()
-        a, b = outs
-        if valid is not None:
-            keep = valid.repeat_interleave(S)[:N]
-            a, b = a[keep], b[keep]
-        assert bool(torch.isfinite(b).all())
-        assert float((a - b).abs().max()) < 2e-5, (lm, float((a - b).abs().max()))
+        a = outs[0]
+        for b in outs[1:]:
+            if valid is not None:
+                keep = valid.repeat_interleave(S)[:N]
+                aa, b = a[keep], b[keep]
+            else:
+                aa = a
+            assert bool(torch.isfinite(b).all())
+            assert float((aa - b).abs().max()) < 2e-5, (lm, float((aa - b).abs().max()))
 
 
 @pytest.mark.parametrize("split", [True, False])

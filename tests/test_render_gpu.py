@@ -60,15 +60,19 @@ def both(fn_name, ours, ref, make_args):
     return a, (b if ref is not None else None)
 
 
-@pytest.fixture(params=[1, 0], ids=["grouped", "fused"])
+@pytest.fixture(params=[(1, 1), (1, 0), (0, 1)], ids=["grouped", "grouped-unfolded", "fused"])
 def infer_path(request):
-    """Both implementations of the field evaluation behind pts_inference / bg_pts_inference*: the grouped
-    multi-pass path (default) and the single fused kernel (snrf_infer_set_two_pass(0))."""
+    """The implementations of the field evaluation behind pts_inference / bg_pts_inference*: the grouped
+    multi-pass path (default; its four-tile decode pass with decoder layer 2 folded into its consumers, or not:
+    snrf_infer_set_fold) and the single fused kernel (snrf_infer_set_two_pass(0))."""
     load_pkg()
     import scanerf_b200_capi as capi
-    capi.lib().snrf_infer_set_two_pass(capi.c_int(request.param))
-    yield request.param
+    two_pass, fold = request.param
+    capi.lib().snrf_infer_set_two_pass(capi.c_int(two_pass))
+    capi.lib().snrf_infer_set_fold(capi.c_int(fold))
+    yield two_pass
     capi.lib().snrf_infer_set_two_pass(capi.c_int(1))
+    capi.lib().snrf_infer_set_fold(capi.c_int(1))
 
 
 def _ops():
