@@ -761,7 +761,7 @@ int g_aggregate_override = -1;
 // leaves 32 / R times more same-address reductions on the coarse levels than the cross-lane sums do, and that costs
 // more than the shuffles it saves.  Kept selectable (and parity-tested) for tables / sample densities where runs are longer.
 int g_fwd_pairing = 0;         // snrf_field_encode_fwd: CTA rows walk level pairs (y, L-1-y) (experiment)
-int g_fwd_l2_mode = 1;         // snrf_field_set_fwd_l2_policy (1: measured 1.725 -> 1.653 ms at C2, profiles/r3a_fwd_sweep.json)
+int g_fwd_l2_mode = 0;         // snrf_field_set_fwd_l2_policy (no policy beats the default: profiles/r3a_fwd_per_level.md, r3e_fwd_sweep.json)
 int g_fwd_pin_mib = 0;
 int g_fwd_split_levels = 0;    // one forward launch per level (measurement hook)
 int g_fwd_pair_mode = 0;       // snrf_field_set_fwd_pair_loads

@@ -99,7 +99,7 @@ def test_forward_load_variants_are_bit_identical(R, S, log2T, mode, pair, first_
         got = run()
     finally:
         lib.snrf_field_set_fwd_pair_loads(ctypes.c_int(0), ctypes.c_int(0))
-        lib.snrf_field_set_fwd_l2_policy(ctypes.c_int(1), ctypes.c_int(0))        # the library's default
+        lib.snrf_field_set_fwd_l2_policy(ctypes.c_int(0), ctypes.c_int(0))        # the library's default
     assert torch.equal(got[0], want[0]), "features"
     # (the ray gradients are sums of atomics: same values, run-to-run order)
     assert _rel(got[1], want[1]) < 1e-5 and _rel(got[2], want[2]) < 1e-5

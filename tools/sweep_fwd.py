@@ -48,7 +48,7 @@ def main():
         rows.append(row)
         print(json.dumps(row), flush=True)
     lib.snrf_field_set_fwd_pair_loads(ctypes.c_int(0), ctypes.c_int(0))
-    lib.snrf_field_set_fwd_l2_policy(ctypes.c_int(1), ctypes.c_int(0))
+    lib.snrf_field_set_fwd_l2_policy(ctypes.c_int(0), ctypes.c_int(0))
     with open(args.out, "w") as fh:
         fh.write(json.dumps(rows) + "\n")
 

@@ -53,7 +53,7 @@ def main():
         rows.append(row)
         print(json.dumps(row), flush=True)
     lib.snrf_l2_fetch_granularity(ctypes.c_int(default))
-    lib.snrf_field_set_fwd_l2_policy(ctypes.c_int(1), ctypes.c_int(0))
+    lib.snrf_field_set_fwd_l2_policy(ctypes.c_int(0), ctypes.c_int(0))
     with open(args.out, "w") as fh:
         fh.write(json.dumps(rows) + "\n")
 
