@@ -186,6 +186,43 @@ int snrf_composite_bwd(const float* sigma, const float* tint, const float* diffu
                        int gs_sigma, int gs_tint, int gs_diffuse, int gs_specular,
                        float* grad_rays_d, void* stream);
 
+/* Early ray termination in TRAINING (opt-in; the north star's compositing subsystem.  The reference evaluates and
+ * back-propagates every sample, hashgrid/__init__.py:512-596, so this is an approximation the caller chooses: ert_eps = 0
+ * reproduces snrf_composite_fwd exactly).  A sample whose transmittance in front of it is below ert_eps is composited with
+ * weight 0 and flagged dead in sample_live [R*S] (1 = live; 0 also for the samples of masked-out rays; may be NULL).  In the
+ * joint batch (infinity != 0, R == 2 * inf_start: ray r + R/2 = the background chain of foreground ray r) the background
+ * samples are tested against T_left(foreground) * T.  The *_ert backward entry points below take the flags and skip the dead
+ * samples: zero head gradients (snrf_composite_bwd_ert), decoder tiles without a live sample skipped and grad_feats rows of
+ * dead samples left unwritten (snrf_decoder_bwd_ert), no table / ray gradient from them (snrf_field_encode_bwd{,_adam}_ert). */
+int snrf_composite_fwd_ert(const float* sigma, const float* tint, const float* diffuse, const float* specular,
+                           int s_sigma, int s_tint, int s_diffuse, int s_specular,
+                           const float* z_vals, const float* dists, const float* rays_d, const unsigned char* ray_valid,
+                           int R, int S, int infinity, int inf_start, float* weights, float* trans, float* out,
+                           float ert_eps, unsigned char* sample_live, void* stream);
+int snrf_composite_bwd_ert(const float* sigma, const float* tint, const float* diffuse, const float* specular,
+                           int s_sigma, int s_tint, int s_diffuse, int s_specular,
+                           const float* z_vals, const float* dists, const float* rays_d, const float* trans,
+                           const float* g_out, const float* g_weights, const unsigned char* ray_valid, int R, int S, int infinity,
+                           int inf_start, float* g_sigma, float* g_tint, float* g_diffuse, float* g_specular,
+                           int gs_sigma, int gs_tint, int gs_diffuse, int gs_specular,
+                           float* grad_rays_d, const unsigned char* sample_live, void* stream);
+int snrf_decoder_bwd_ert(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
+                         const float* grad_heads, float* grad_feats, float* grad_rays_d, float* const* grad_params,
+                         int N, int S, int level_major, const unsigned char* ray_valid, const float* heads_fwd,
+                         const unsigned char* sample_live, void* stream);
+int snrf_field_encode_bwd_ert(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
+                              const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
+                              const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points, float* grad_table,
+                              const unsigned char* ray_valid, int split, int N, int S, int L, int T,
+                              const unsigned char* sample_live, void* stream);
+int snrf_field_encode_bwd_adam_ert(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
+                                   const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
+                                   const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points,
+                                   float* table, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                                   int step, float* grad_scratch, long long scratch_entries, int small_levels, float* cpts_scratch,
+                                   const unsigned char* ray_valid, int split, int N, int S, int L, int T,
+                                   const unsigned char* sample_live, void* stream);
+
 /* ---- decoder MLP on the tensor cores (tcgen05 / TMEM) ------------------------- */
 /* Self-test of the tensor-core conventions (no reference counterpart): X[128,64], W[64,64],
  * G[128,64] f32, rounded to bf16 inside -> Y = X W^T [128,64], DX = G W [128,64],

@@ -62,17 +62,23 @@ __device__ __forceinline__ float warp_incl_suffix_sum(float v, int lane)
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_fwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __restrict__ dists,
                      const float* __restrict__ rays_d, const unsigned char* __restrict__ ray_valid, int R, int S, int infinity,
-                     int inf_start, float* __restrict__ weights, float* __restrict__ trans, float* __restrict__ out)
+                     int inf_start, float* __restrict__ weights, float* __restrict__ trans, float* __restrict__ out,
+                     float ert_eps, unsigned char* __restrict__ sample_live)
 {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int chunks = (S + 31) >> 5;
-    for (int r = warp; r < R; r += nwarps) {
+    // composites ray r; `front` = transmittance in front of the ray's first sample for the termination test only (1, or the
+    // T_left of the foreground chain when r is the background chain of the same pixel); returns the ray's T_left
+    auto composite_ray = [&](int r, float front) -> float {
         if (ray_valid && !ray_valid[r]) {   // masked-out ray: nothing composited, full transmittance (HashGrid._scatter_back defaults)
-            for (int k = lane; k < S; k += 32) weights[(size_t)r * S + k] = 0.0f;
+            for (int k = lane; k < S; k += 32) {
+                weights[(size_t)r * S + k] = 0.0f;
+                if (sample_live) sample_live[(size_t)r * S + k] = 0;
+            }
             if (lane < kOutStride) out[(size_t)r * kOutStride + lane] = lane == 13 ? 1.0f : 0.0f;
-            continue;
+            return 1.0f;
         }
         const f3 d = ld3(rays_d + 3 * (size_t)r);
         const float dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
@@ -98,7 +104,11 @@ composite_fwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
             if (lane == 0) excl = 1.0f;
             const float T = carry * excl;
             if (live) {
-                const float w = alpha * T;
+                // early ray termination (opt-in, ert_eps > 0): a sample behind transmittance < ert_eps is composited with
+                // weight 0 and flagged dead -- the backward kernels (composite, decoder, encode scatter) skip it
+                const bool dead = front * T < ert_eps;
+                const float w = dead ? 0.0f : alpha * T;
+                if (sample_live) sample_live[n] = dead ? 0 : 1;
                 weights[n] = w;
                 if (trans) trans[n] = T;
                 const float z = z_vals[n];
@@ -126,6 +136,17 @@ composite_fwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
         } else if (lane == 13) {
             o[13] = t_left;
         }
+        return t_left;
+    };
+    if (ert_eps > 0.0f && infinity != 0 && inf_start > 0 && R == 2 * inf_start) {
+        // joint batch with termination: rays [0, R/2) are the foreground chains, ray r + R/2 the background chain of the same
+        // pixel, whose colour is later weighted by the foreground's T_left -- one warp takes both, the second with that factor
+        for (int r = warp; r < inf_start; r += nwarps) {
+            const float t_fore = composite_ray(r, 1.0f);
+            composite_ray(r + inf_start, t_fore);
+        }
+    } else {
+        for (int r = warp; r < R; r += nwarps) composite_ray(r, 1.0f);
     }
 }
 
@@ -136,7 +157,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_bwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __restrict__ dists,
                      const float* __restrict__ rays_d, const float* __restrict__ trans,
                      const float* __restrict__ g_out, const float* __restrict__ g_weights, const unsigned char* __restrict__ ray_valid,
-                     int R, int S, int infinity, int inf_start, HeadGrads g, float* __restrict__ grad_rays_d)
+                     int R, int S, int infinity, int inf_start, HeadGrads g, float* __restrict__ grad_rays_d,
+                     const unsigned char* __restrict__ sample_live)
 {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -163,13 +185,14 @@ composite_bwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
             const bool live = k < S;
             const size_t n = (size_t)r * S + k;
             float Gw = 0.0f, w = 0.0f, e = 1.0f, delta = 0.0f, sig = 0.0f, G = 0.0f, T = 0.0f;
+            const bool dead = live && sample_live != nullptr && sample_live[n] == 0;    // terminated in the forward: weight 0, no gradient
             if (live) {
                 T = trans[n];
                 sig = in.sigma[n * in.s_sigma];
                 delta = dists[n] * dn;
                 if (inf && k == S - 1) delta = 1e10f;
                 e = expf(-sig * delta);                     // 1 - alpha
-                w = (1.0f - e) * T;
+                w = dead ? 0.0f : (1.0f - e) * T;
                 const f3 ti = ld3(in.tint + n * in.s_tint);
                 const f3 di = ld3(in.diffuse + n * in.s_diffuse);
                 const f3 sp = ld3(in.specular + n * in.s_specular);
@@ -191,7 +214,7 @@ composite_bwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
             const float after = suffix + (incl - tail);      // sum over samples strictly after k
             if (live) {
                 const float beta = e + 1e-6f;
-                const float g_alpha = G * T - after / beta;
+                const float g_alpha = dead ? 0.0f : G * T - after / beta;
                 g.sigma[n * g.s_sigma] = g_alpha * delta * e;
                 if (!(inf && k == S - 1)) g_dn += g_alpha * sig * e * dists[n];
             }
@@ -215,18 +238,37 @@ inline int grid_rays(int R)
 }  // namespace
 
 // ------------------------------- C ABI --------------------------------------
+// ert_eps > 0: early ray termination -- samples behind transmittance < ert_eps get weight 0; sample_live [R*S] (may be NULL)
+// receives 1 / 0 per sample (0 also for the samples of masked-out rays) for the backward kernels.
+SNRF_API int snrf_composite_fwd_ert(const float* sigma, const float* tint, const float* diffuse, const float* specular,
+                                    int s_sigma, int s_tint, int s_diffuse, int s_specular,
+                                    const float* z_vals, const float* dists, const float* rays_d, const unsigned char* ray_valid,
+                                    int R, int S, int infinity, int inf_start, float* weights, float* trans, float* out,
+                                    float ert_eps, unsigned char* sample_live, void* stream)
+{
+    SNRF_CHECK_ARG(S > 0, "snrf_composite_fwd: S must be positive");
+    SNRF_CHECK_ARG(ert_eps >= 0.0f && ert_eps < 1.0f, "snrf_composite_fwd_ert: ert_eps must lie in [0, 1) (got %g)", (double)ert_eps);
+    if (R <= 0) return 0;
+    Heads in{sigma, tint, diffuse, specular, s_sigma, s_tint, s_diffuse, s_specular};
+    composite_fwd_kernel<<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, ray_valid, R, S, infinity, inf_start, weights, trans, out, ert_eps, sample_live);
+    SNRF_RETURN_LAUNCH("snrf_composite_fwd");
+}
 SNRF_API int snrf_composite_fwd(const float* sigma, const float* tint, const float* diffuse, const float* specular,
                                 int s_sigma, int s_tint, int s_diffuse, int s_specular,
                                 const float* z_vals, const float* dists, const float* rays_d, const unsigned char* ray_valid,
                                 int R, int S, int infinity, int inf_start, float* weights, float* trans, float* out, void* stream)
 {
-    SNRF_CHECK_ARG(S > 0, "snrf_composite_fwd: S must be positive");
-    if (R <= 0) return 0;
-    Heads in{sigma, tint, diffuse, specular, s_sigma, s_tint, s_diffuse, s_specular};
-    composite_fwd_kernel<<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, ray_valid, R, S, infinity, inf_start, weights, trans, out);
-    SNRF_RETURN_LAUNCH("snrf_composite_fwd");
+    return snrf_composite_fwd_ert(sigma, tint, diffuse, specular, s_sigma, s_tint, s_diffuse, s_specular, z_vals, dists, rays_d, ray_valid,
+                                  R, S, infinity, inf_start, weights, trans, out, 0.0f, nullptr, stream);
 }
 
+SNRF_API int snrf_composite_bwd_ert(const float* sigma, const float* tint, const float* diffuse, const float* specular,
+                                    int s_sigma, int s_tint, int s_diffuse, int s_specular,
+                                    const float* z_vals, const float* dists, const float* rays_d, const float* trans,
+                                    const float* g_out, const float* g_weights, const unsigned char* ray_valid, int R, int S, int infinity,
+                                    int inf_start, float* g_sigma, float* g_tint, float* g_diffuse, float* g_specular,
+                                    int gs_sigma, int gs_tint, int gs_diffuse, int gs_specular,
+                                    float* grad_rays_d, const unsigned char* sample_live, void* stream);
 SNRF_API int snrf_composite_bwd(const float* sigma, const float* tint, const float* diffuse, const float* specular,
                                 int s_sigma, int s_tint, int s_diffuse, int s_specular,
                                 const float* z_vals, const float* dists, const float* rays_d, const float* trans,
@@ -235,10 +277,23 @@ SNRF_API int snrf_composite_bwd(const float* sigma, const float* tint, const flo
                                 int gs_sigma, int gs_tint, int gs_diffuse, int gs_specular,
                                 float* grad_rays_d, void* stream)
 {
+    return snrf_composite_bwd_ert(sigma, tint, diffuse, specular, s_sigma, s_tint, s_diffuse, s_specular, z_vals, dists, rays_d, trans,
+                                  g_out, g_weights, ray_valid, R, S, infinity, inf_start, g_sigma, g_tint, g_diffuse, g_specular,
+                                  gs_sigma, gs_tint, gs_diffuse, gs_specular, grad_rays_d, nullptr, stream);
+}
+// sample_live (may be NULL): the flags snrf_composite_fwd_ert wrote -- dead samples get zero gradients
+SNRF_API int snrf_composite_bwd_ert(const float* sigma, const float* tint, const float* diffuse, const float* specular,
+                                    int s_sigma, int s_tint, int s_diffuse, int s_specular,
+                                    const float* z_vals, const float* dists, const float* rays_d, const float* trans,
+                                    const float* g_out, const float* g_weights, const unsigned char* ray_valid, int R, int S, int infinity,
+                                    int inf_start, float* g_sigma, float* g_tint, float* g_diffuse, float* g_specular,
+                                    int gs_sigma, int gs_tint, int gs_diffuse, int gs_specular,
+                                    float* grad_rays_d, const unsigned char* sample_live, void* stream)
+{
     SNRF_CHECK_ARG(S > 0, "snrf_composite_bwd: S must be positive");
     if (R <= 0) return 0;
     Heads in{sigma, tint, diffuse, specular, s_sigma, s_tint, s_diffuse, s_specular};
     HeadGrads g{g_sigma, g_tint, g_diffuse, g_specular, gs_sigma, gs_tint, gs_diffuse, gs_specular};
-    composite_bwd_kernel<<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, trans, g_out, g_weights, ray_valid, R, S, infinity, inf_start, g, grad_rays_d);
+    composite_bwd_kernel<<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, trans, g_out, g_weights, ray_valid, R, S, infinity, inf_start, g, grad_rays_d, sample_live);
     SNRF_RETURN_LAUNCH("snrf_composite_bwd");
 }

@@ -222,7 +222,7 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
                    DecoderParams p, const float* __restrict__ grad_heads, float* __restrict__ grad_feats,
                    float* __restrict__ grad_rays_d, DecoderGrads gp, int N, int S, int num_tiles, long long level_stride,
                    const unsigned char* __restrict__ ray_valid, const unsigned* __restrict__ gmax_bits,
-                   const float* __restrict__ heads_fwd)
+                   const float* __restrict__ heads_fwd, const unsigned char* __restrict__ sample_live)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -367,8 +367,9 @@ decoder_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ ma
     bool first = true;      // no tile processed yet: the first one initialises the TMEM gradient accumulators
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n = tile * kRows + row;
-        const bool live = n < N && (ray_valid == nullptr || ray_valid[n / S] != 0);
-        if (ray_valid != nullptr && !c.any(live)) continue;              // tile of masked-out rays only
+        // (sample_live: the early-ray-termination flags of snrf_composite_fwd_ert -- a dead sample has a zero gradient row)
+        const bool live = n < N && (ray_valid == nullptr || ray_valid[n / S] != 0) && (sample_live == nullptr || sample_live[n] != 0);
+        if ((ray_valid != nullptr || sample_live != nullptr) && !c.any(live)) continue;     // tile of masked-out / terminated samples only
         float head[10], zh[7];
         f3 d = mk3(0.f, 0.f, 1.f);
         float dn = 1.0f;
@@ -723,7 +724,7 @@ decoder_bwd_fold_kernel(const float* __restrict__ feats, const float* __restrict
                         DecoderParams p, const float* __restrict__ grad_heads, float* __restrict__ grad_feats,
                         float* __restrict__ grad_rays_d, DecoderGrads gp, int N, int S, int num_tiles, long long level_stride,
                         const unsigned char* __restrict__ ray_valid, const unsigned* __restrict__ gmax_bits,
-                        const float* __restrict__ heads_fwd)
+                        const float* __restrict__ heads_fwd, const unsigned char* __restrict__ sample_live)
 {
     using namespace fold;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -894,8 +895,8 @@ decoder_bwd_fold_kernel(const float* __restrict__ feats, const float* __restrict
     bool first = true;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n = tile * kRows + row;
-        const bool live = n < N && (ray_valid == nullptr || ray_valid[n / S] != 0);
-        if (ray_valid != nullptr && !__syncthreads_or(live)) continue;
+        const bool live = n < N && (ray_valid == nullptr || ray_valid[n / S] != 0) && (sample_live == nullptr || sample_live[n] != 0);
+        if ((ray_valid != nullptr || sample_live != nullptr) && !__syncthreads_or(live)) continue;     // masked-out / terminated samples only
         if (cg == 0 && live) {
             prefetch_l2(grad_heads + (size_t)n * 10);
             prefetch_l2(grad_heads + (size_t)n * 10 + 8);
@@ -1270,6 +1271,7 @@ __device__ unsigned g_gmax_slots[64];      // a ring: concurrent backward launch
 int g_gmax_next = 0;
 
 int g_fwd_inflight = 4; // forward tiles in flight per CTA: 4 (in-place operands, per-ray SH term; S >= kMinS4) or 2
+thread_local const unsigned char* t_sample_live = nullptr;     // set by snrf_decoder_bwd_ert around its call of snrf_decoder_bwd
 int g_fwd_fold = 1;     // four-tile forward: layer 2 folded into its consumers (four dependent stages per tile instead of five)
 int g_bwd_merged = 2;   // backward with heads_fwd: 2 = layer 2 folded away (decoder_bwd_fold_kernel), 1 = layer 4 merged with the first backward stage, 0 = everything recomputed
 int g_split = 1;       // 1 = error-compensated bf16x3 operands in the forward GEMMs (default), 0 = plain bf16
@@ -1379,15 +1381,30 @@ SNRF_API int snrf_decoder_bwd(const float* feats, const float* mask32, const flo
     }
     if (heads_fwd != nullptr && g_bwd_merged == 2) {
         if (g_split)
-            decoder_bwd_fold_kernel<true><<<grid, kThreadsDec, fold::smem_bytes, s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot, heads_fwd);
+            decoder_bwd_fold_kernel<true><<<grid, kThreadsDec, fold::smem_bytes, s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot, heads_fwd, t_sample_live);
         else
-            decoder_bwd_fold_kernel<false><<<grid, kThreadsDec, fold::smem_bytes, s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot, heads_fwd);
+            decoder_bwd_fold_kernel<false><<<grid, kThreadsDec, fold::smem_bytes, s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot, heads_fwd, t_sample_live);
         SNRF_RETURN_LAUNCH("snrf_decoder_bwd");
     }
     const bool merged = heads_fwd != nullptr && g_bwd_merged;
-#define SNRF_DEC_BWD(SPLIT, HEADS) decoder_bwd_kernel<SPLIT, HEADS><<<grid, kThreadsDec, bwd_smem<SPLIT>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot, merged ? heads_fwd : nullptr)
+#define SNRF_DEC_BWD(SPLIT, HEADS) decoder_bwd_kernel<SPLIT, HEADS><<<grid, kThreadsDec, bwd_smem<SPLIT>(), s>>>(feats, mask32, rays_d, p, grad_heads, grad_feats, grad_rays_d, g, N, S, num_tiles, level_major ? (long long)N : 0ll, ray_valid, slot, merged ? heads_fwd : nullptr, t_sample_live)
     if (g_split) { if (merged) SNRF_DEC_BWD(true, true); else SNRF_DEC_BWD(true, false); }
     else         { if (merged) SNRF_DEC_BWD(false, true); else SNRF_DEC_BWD(false, false); }
 #undef SNRF_DEC_BWD
     SNRF_RETURN_LAUNCH("snrf_decoder_bwd");
+}
+
+// snrf_decoder_bwd with the per-sample early-ray-termination flags of snrf_composite_fwd_ert (sample_live [N], may be NULL):
+// dead samples are treated like the samples of masked-out rays -- tiles without a live sample are skipped, grad_feats rows of
+// dead samples are left unwritten.
+SNRF_API int snrf_decoder_bwd_ert(const float* feats, const float* mask32, const float* rays_d, const float* const* params,
+                                  const float* grad_heads, float* grad_feats, float* grad_rays_d, float* const* grad_params,
+                                  int N, int S, int level_major, const unsigned char* ray_valid, const float* heads_fwd,
+                                  const unsigned char* sample_live, void* stream)
+{
+    t_sample_live = sample_live;
+    const int rc = snrf_decoder_bwd(feats, mask32, rays_d, params, grad_heads, grad_feats, grad_rays_d, grad_params, N, S, level_major,
+                                    ray_valid, heads_fwd, stream);
+    t_sample_live = nullptr;
+    return rc;
 }

@@ -537,7 +537,8 @@ field_geom_raygrad_kernel(const float* __restrict__ rays_o, const float* __restr
                           const float* __restrict__ points, const float* __restrict__ bmin_p, const float* __restrict__ bsize_p,
                           const float2* __restrict__ grad, const float2* __restrict__ jac,
                           float* __restrict__ grad_o, float* __restrict__ grad_d, float* __restrict__ grad_points,
-                          float* __restrict__ cpts, const unsigned char* __restrict__ ray_valid, int ray_split, int N, int S, int L)
+                          float* __restrict__ cpts, const unsigned char* __restrict__ ray_valid, int ray_split, int N, int S, int L,
+                          const unsigned char* __restrict__ sample_live)
 {
     const int lane = threadIdx.x & 31;
     f3 bmin = mk3(0, 0, 0), bsize = mk3(1, 1, 1);
@@ -547,7 +548,8 @@ field_geom_raygrad_kernel(const float* __restrict__ rays_o, const float* __restr
     const int warp_base0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31;
     for (int wb = warp_base0; wb < N; wb += gridDim.x * blockDim.x) {
         const int n = wb + lane;
-        const bool live = n < N && (MODE == kNone || ray_valid == nullptr || ray_valid[n / S] != 0);
+        // (sample_live: early-ray-termination flags -- a dead sample has no gradient row and is marked like a masked-out one)
+        const bool live = n < N && (MODE == kNone || ray_valid == nullptr || ray_valid[n / S] != 0) && (sample_live == nullptr || sample_live[n] != 0);
         Pt p;
         float z = 0.0f;
         int r = -1;
@@ -754,6 +756,7 @@ inline int grid_x(int N)
     return wave * (waves > 4 ? 4 : waves);
 }
 
+thread_local const unsigned char* t_sample_live = nullptr;     // set by the *_ert entry points around their call of the plain ones
 int g_pass_bits_override = -1;
 int g_aggregate_override = -1;
 // Samples per thread of field_bwd_runs_kernel; 0 = the cross-lane kernel (default).  Measured on B200 at C2 (4.19 M samples,
@@ -915,9 +918,9 @@ SNRF_API int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, con
         cudaError_t e = snrf_scratch_alloc((void**)&cpts, (size_t)N * 3 * sizeof(float), s);
         if (e != cudaSuccess) { snrf_set_error("snrf_field_encode_bwd: scratch allocation: %s", cudaGetErrorString(e)); return (int)e; }
         if (mode == 0)
-            field_geom_raygrad_kernel<kNone><<<grid_x(N), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, g, j, grad_rays_o, grad_rays_d, grad_points, cpts, ray_valid, ray_split, N, S, L);
+            field_geom_raygrad_kernel<kNone><<<grid_x(N), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, g, j, grad_rays_o, grad_rays_d, grad_points, cpts, ray_valid, ray_split, N, S, L, t_sample_live);
         else
-            field_geom_raygrad_kernel<kRays><<<grid_x(N), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, g, j, grad_rays_o, grad_rays_d, grad_points, cpts, ray_valid, ray_split, N, S, L);
+            field_geom_raygrad_kernel<kRays><<<grid_x(N), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, g, j, grad_rays_o, grad_rays_d, grad_points, cpts, ray_valid, ray_split, N, S, L, t_sample_live);
         const long long slice = 1ll << range_shift;
         if (pass_bits == 0) {                              // whole levels: all of them in one launch
             field_scatter_slice_kernel<false><<<dim3(grid_x(N), L), kThreads, 0, s>>>(cpts, res, g, gt, N, 0, (uint32_t)T, 0u, range_shift, agg);
@@ -931,6 +934,7 @@ SNRF_API int snrf_field_encode_bwd(const float* rays_o, const float* rays_d, con
         if (e != cudaSuccess) { snrf_set_error("snrf_field_encode_bwd: %s", cudaGetErrorString(e)); return (int)e; }
         return 0;
     }
+    SNRF_CHECK_ARG(t_sample_live == nullptr, "snrf_field_encode_bwd_ert: the sample flags need the geometry + scatter kernel pair (snrf_field_set_bwd_impl(1), run length 0)");
     if (g_run_length == 2) { if (mode == 0) SNRF_RUNS(kNone, 2); else SNRF_RUNS(kRays, 2); }
     else if (g_run_length == 4) { if (mode == 0) SNRF_RUNS(kNone, 4); else SNRF_RUNS(kRays, 4); }
     else if (g_run_length == 8) { if (mode == 0) SNRF_RUNS(kNone, 8); else SNRF_RUNS(kRays, 8); }
@@ -1051,9 +1055,9 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
 
     mark(-1);
     if (mode == 0)
-        field_geom_raygrad_kernel<kNone><<<grid_x(N), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, g, j, grad_rays_o, grad_rays_d, grad_points, cpts_scratch, ray_valid, ray_split, N, S, L);
+        field_geom_raygrad_kernel<kNone><<<grid_x(N), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, g, j, grad_rays_o, grad_rays_d, grad_points, cpts_scratch, ray_valid, ray_split, N, S, L, t_sample_live);
     else
-        field_geom_raygrad_kernel<kRays><<<grid_x(N), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, g, j, grad_rays_o, grad_rays_d, grad_points, cpts_scratch, ray_valid, ray_split, N, S, L);
+        field_geom_raygrad_kernel<kRays><<<grid_x(N), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, g, j, grad_rays_o, grad_rays_d, grad_points, cpts_scratch, ray_valid, ray_split, N, S, L, t_sample_live);
     mark(0);
     int launches = 1;
 
@@ -1117,4 +1121,34 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
         if (!concurrent) g_profile_ms[3] = g_profile_ms[1] + g_profile_ms[2];
     }
     SNRF_RETURN_LAUNCH("snrf_field_encode_bwd_adam");
+}
+
+// The two backward entry points with the per-sample early-ray-termination flags of snrf_composite_fwd_ert (sample_live [N], may
+// be NULL): a dead sample contributes no table gradient and no ray gradient (its gradient row is never read).
+SNRF_API int snrf_field_encode_bwd_ert(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
+                                       const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
+                                       const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points, float* grad_table,
+                                       const unsigned char* ray_valid, int split, int N, int S, int L, int T,
+                                       const unsigned char* sample_live, void* stream)
+{
+    t_sample_live = sample_live;
+    const int rc = snrf_field_encode_bwd(rays_o, rays_d, z_vals, points, box_min, box_size, mode, res, grad_lm, jac_lm, grad_rays_o, grad_rays_d,
+                                         grad_points, grad_table, ray_valid, split, N, S, L, T, stream);
+    t_sample_live = nullptr;
+    return rc;
+}
+SNRF_API int snrf_field_encode_bwd_adam_ert(const float* rays_o, const float* rays_d, const float* z_vals, const float* points,
+                                            const float* box_min, const float* box_size, int mode, const int* res, const float* grad_lm,
+                                            const float* jac_lm, float* grad_rays_o, float* grad_rays_d, float* grad_points,
+                                            float* table, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                                            int step, float* grad_scratch, long long scratch_entries, int small_levels, float* cpts_scratch,
+                                            const unsigned char* ray_valid, int split, int N, int S, int L, int T,
+                                            const unsigned char* sample_live, void* stream)
+{
+    t_sample_live = sample_live;
+    const int rc = snrf_field_encode_bwd_adam(rays_o, rays_d, z_vals, points, box_min, box_size, mode, res, grad_lm, jac_lm, grad_rays_o,
+                                              grad_rays_d, grad_points, table, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scratch,
+                                              scratch_entries, small_levels, cpts_scratch, ray_valid, split, N, S, L, T, stream);
+    t_sample_live = nullptr;
+    return rc;
 }

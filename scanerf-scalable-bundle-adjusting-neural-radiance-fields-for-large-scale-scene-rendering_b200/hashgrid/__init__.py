@@ -42,6 +42,10 @@ class HashGrid(nn.Module):
     # with fused_decoder: also fuse sample position + contraction + hash encode (csrc/field_encode.cu);
     # False keeps torch contraction + the reference-shaped encode operator
     fused_encode = True
+    # early ray termination in TRAINING (opt-in; 0 = off = the reference's semantics: every sample evaluated and
+    # back-propagated, hashgrid/__init__.py:512-596).  > 0: samples behind transmittance < ert_eps are composited with weight 0
+    # and skipped by the backward of the compositing, the decoder and the encode scatter (fused path only).
+    ert_eps = 0.0
 
     def __init__(self, device, bbox_corner, bbox_size, log2_hashmap_size=24, grid_resolution=[32, 2048],
                  sampler_log2dim=4, init_outside=False, model_path="", near=None, far=None):
@@ -328,10 +332,11 @@ class HashGrid(nn.Module):
         no device->host synchronisation anywhere."""
         R, S = z_vals.shape
         mask32 = self.level_mask32(global_step)
+        ert = _render.ErtState(self.ert_eps) if (self.ert_eps > 0 and mode is TRAIN) else None
         feats = _field.field_encode(rays_o, rays_d, z_vals, self.HE.features, self.HE.resolution, self.min_bbox,
-                                    self.bbox_size, contract_mode, valid)
-        heads = _field.decoder_apply(feats, rays_d, mask32, S, params, valid)
-        return _render.composite_packed(heads, z_vals, dists, rays_d, infinity, train=(mode is TRAIN), valid=valid)
+                                    self.bbox_size, contract_mode, valid, 0, ert)
+        heads = _field.decoder_apply(feats, rays_d, mask32, S, params, valid, ert)
+        return _render.composite_packed(heads, z_vals, dists, rays_d, infinity, train=(mode is TRAIN), valid=valid, ert=ert)
 
     def render_fore_bg_rays(self, rays_o, rays_d, num_sample, decoder, mode, occlusion_mask=None, global_step=0,
                             invalid_underground=True):
@@ -356,9 +361,10 @@ class HashGrid(nn.Module):
         o2, d2 = torch.cat([rays_o, rays_o], 0), torch.cat([rays_d, rays_d], 0)
         valid2 = torch.cat([v_f, v_b], 0)
         mask32 = self.level_mask32(global_step)
-        feats = _field.field_encode(o2, d2, z2, self.HE.features, self.HE.resolution, self.min_bbox, self.bbox_size, 3, valid2, R)
-        heads = _field.decoder_apply(feats, d2, mask32, num_sample, params, valid2)
-        row, weights = _render.CompositePackedFn.apply(heads, z2, dist2, d2, R, valid2)      # rays >= R end at infinity
+        ert = _render.ErtState(self.ert_eps) if (self.ert_eps > 0 and mode is TRAIN) else None
+        feats = _field.field_encode(o2, d2, z2, self.HE.features, self.HE.resolution, self.min_bbox, self.bbox_size, 3, valid2, R, ert)
+        heads = _field.decoder_apply(feats, d2, mask32, num_sample, params, valid2, ert)
+        row, weights = _render.CompositePackedFn.apply(heads, z2, dist2, d2, R, valid2, ert)      # rays >= R end at infinity
         train = mode is TRAIN
         fg = _render._finish(row[:R], weights[:R], train, v_f)
         bg = _render._finish(row[R:], weights[R:], train, v_b)

@@ -59,11 +59,12 @@ class DecoderFn(torch.autograd.Function):
     inputs) and returns d/d feats, d/d rays_d (through the SH view encoding) and d/d params."""
 
     @staticmethod
-    def forward(ctx, feats, rays_d, mask32, S, valid, *params):
+    def forward(ctx, feats, rays_d, mask32, S, valid, ert, *params):
         feats = feats.contiguous()
         rays_d = rays_d.contiguous()
         heads = decoder_forward(feats, mask32, rays_d, S, params, valid)
         ctx.S = int(S)
+        ctx.ert = ert           # _render.ErtState | None: its sample flags exist by the time the backward runs
         ctx.has_mask, ctx.has_valid = mask32 is not None, valid is not None
         ctx.save_for_backward(feats, rays_d, mask32 if mask32 is not None else feats.new_empty(0),
                               valid if valid is not None else feats.new_empty(0), heads, *params)
@@ -86,15 +87,20 @@ class DecoderFn(torch.autograd.Function):
         arr, keep = _param_array(params)
         garr = (ctypes.c_void_p * 16)(*[g.data_ptr() for g in g_params])
         m = mask32.contiguous() if ctx.has_mask else None
-        rc = capi.lib().snrf_decoder_bwd(ptr(feats), ptr(m), ptr(rays_d), arr, ptr(g_heads), ptr(g_feats), ptr(g_d), garr,
-                                         c_int(N), c_int(ctx.S), c_int(lm), ptr(valid) if ctx.has_valid else c_void_p(0), ptr(heads), capi.stream())
+        args = (ptr(feats), ptr(m), ptr(rays_d), arr, ptr(g_heads), ptr(g_feats), ptr(g_d), garr,
+                c_int(N), c_int(ctx.S), c_int(lm), ptr(valid) if ctx.has_valid else c_void_p(0), ptr(heads))
+        if ctx.ert is not None and ctx.ert.sample_live is not None:
+            rc = capi.lib().snrf_decoder_bwd_ert(*args, ptr(ctx.ert.sample_live), capi.stream())
+        else:
+            rc = capi.lib().snrf_decoder_bwd(*args, capi.stream())
         capi.check(rc, "snrf_decoder_bwd")
-        return (g_feats, g_d, None, None, None) + tuple(g_params)
+        return (g_feats, g_d, None, None, None, None) + tuple(g_params)
 
 
-def decoder_apply(feats, rays_d, mask32, S, params, valid=None):
-    """valid (bool [R] or None): samples of rays flagged False are skipped (rows left unwritten)."""
-    return DecoderFn.apply(feats, rays_d, mask32, S, valid, *params)
+def decoder_apply(feats, rays_d, mask32, S, params, valid=None, ert=None):
+    """valid (bool [R] or None): samples of rays flagged False are skipped (rows left unwritten).
+    ert (_render.ErtState | None): early ray termination -- the backward skips the samples the compositing flagged dead."""
+    return DecoderFn.apply(feats, rays_d, mask32, S, valid, ert, *params)
 
 
 _small_levels_cache = {}
@@ -126,8 +132,9 @@ class FieldEncodeFn(torch.autograd.Function):
     consumed on the spot by the sparse Adam update ("fused": snrf_field_encode_bwd_adam)."""
 
     @staticmethod
-    def forward(ctx, rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid, split=0):
+    def forward(ctx, rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid, split=0, ert=None):
         R, S = z_vals.shape
+        ctx.ert = ert
         N, L, T = R * S, int(features.shape[0]), int(features.shape[1])
         rays_o, rays_d, z_vals = rays_o.contiguous(), rays_d.contiguous(), z_vals.contiguous()
         for t in (rays_o, rays_d, z_vals, features):
@@ -161,18 +168,22 @@ class FieldEncodeFn(torch.autograd.Function):
         mode = _gradmode.mode() if (features.is_leaf and features.requires_grad) else None
         common = (ptr(rays_o), ptr(rays_d), ptr(z_vals), c_void_p(0), ptr(box_min), ptr(box_size), c_int(ctx.mode), ptr(resolution),
                   ptr(g_out), ptr(jac) if ctx.has_jac else c_void_p(0), ptr(g_o), ptr(g_d), c_void_p(0))
-        tail = (ptr(valid) if ctx.has_valid else c_void_p(0), c_int(ctx.split), c_int(N), c_int(S), c_int(L), c_int(T), capi.stream())
+        live = ctx.ert.sample_live if (ctx.ert is not None and ctx.ert.sample_live is not None) else None
+        sfx = "_ert" if live is not None else ""
+        tail = (ptr(valid) if ctx.has_valid else c_void_p(0), c_int(ctx.split), c_int(N), c_int(S), c_int(L), c_int(T)) + \
+               ((ptr(live),) if live is not None else ()) + (capi.stream(),)
         if mode == "fused" and _gradmode.optimizer().owns(features):
             # scatter + sparse Adam in one pass: the table gradient never exists in HBM
             opt = _gradmode.optimizer()
             m, v, hyper, step, scratch = opt.begin_fused(features, ctx.small_levels)
             cpts = torch.empty(3, N, dtype=f32, device=g_out.device)
-            rc = capi.lib().snrf_field_encode_bwd_adam(*common, ptr(features.data), ptr(m), ptr(v), c_float(hyper["lr"]), c_float(hyper["beta1"]),
-                                                       c_float(hyper["beta2"]), c_float(hyper["eps"]), c_int(step), ptr(scratch),
-                                                       ctypes.c_longlong(scratch.shape[0]), c_int(ctx.small_levels), ptr(cpts), *tail)
+            fn = getattr(capi.lib(), "snrf_field_encode_bwd_adam" + sfx)
+            rc = fn(*common, ptr(features.data), ptr(m), ptr(v), c_float(hyper["lr"]), c_float(hyper["beta1"]),
+                    c_float(hyper["beta2"]), c_float(hyper["eps"]), c_int(step), ptr(scratch),
+                    ctypes.c_longlong(scratch.shape[0]), c_int(ctx.small_levels), ptr(cpts), *tail)
             capi.check(rc, "snrf_field_encode_bwd_adam")
             capi.launch_count += int(capi.lib().snrf_field_last_launch_count()) - 1     # one C call, many kernels
-            return g_o, g_d, None, None, None, None, None, None, None, None
+            return g_o, g_d, None, None, None, None, None, None, None, None, None
         direct = mode is not None
         if direct:
             # the training step's explicit opt-in (_gradmode.table_backward): accumulate in place, no dense temporary
@@ -181,12 +192,13 @@ class FieldEncodeFn(torch.autograd.Function):
             g_table = features.grad
         else:
             g_table = torch.zeros_like(features)
-        rc = capi.lib().snrf_field_encode_bwd(*common, ptr(g_table), *tail)
+        rc = getattr(capi.lib(), "snrf_field_encode_bwd" + sfx)(*common, ptr(g_table), *tail)
         capi.check(rc, "snrf_field_encode_bwd")
-        return g_o, g_d, None, (None if direct else g_table), None, None, None, None, None, None
+        return g_o, g_d, None, (None if direct else g_table), None, None, None, None, None, None, None
 
 
-def field_encode(rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid=None, split=0):
+def field_encode(rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid=None, split=0, ert=None):
     """valid (bool [R] or None): rays flagged False are skipped (their feature rows are left unwritten).
-    mode 3: rays [0, split) are contracted with the fore map, rays [split, R) with the background map."""
-    return FieldEncodeFn.apply(rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid, split)
+    mode 3: rays [0, split) are contracted with the fore map, rays [split, R) with the background map.
+    ert (_render.ErtState | None): early ray termination -- the backward skips the samples the compositing flagged dead."""
+    return FieldEncodeFn.apply(rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid, split, ert)

@@ -12,6 +12,16 @@ from scanerf_b200_capi import c_int, c_void_p, ptr
 _ROW = 16   # per-ray output row of snrf_composite_fwd
 
 
+class ErtState:
+    """Early ray termination of one render call in training (opt-in, HashGrid.ert_eps > 0): the compositing forward fills
+    `sample_live` (uint8 [R*S]: 0 = behind transmittance < eps, or a masked-out ray), the backward of the compositing, the
+    decoder and the encode read it and skip the dead samples (snrf_*_ert entry points)."""
+
+    def __init__(self, eps):
+        self.eps = float(eps)
+        self.sample_live = None
+
+
 def _strides(sigma, tint, diffuse, specular):
     return [c_int(1), c_int(3), c_int(3), c_int(3)]
 
@@ -71,7 +81,7 @@ class CompositePackedFn(torch.autograd.Function):
     rays flagged False are not composited (zero outputs, T_left = 1) and get no gradient."""
 
     @staticmethod
-    def forward(ctx, heads, z_vals, dists, rays_d, infinity, valid):
+    def forward(ctx, heads, z_vals, dists, rays_d, infinity, valid, ert=None):
         # infinity: False / True (all rays) or an int r0: the rays r >= r0 end at infinity (joint fore + background batch)
         R, S = z_vals.shape
         inf_flag, inf_start = (int(infinity), 0) if isinstance(infinity, bool) else (1, int(infinity))
@@ -81,13 +91,18 @@ class CompositePackedFn(torch.autograd.Function):
         trans = torch.empty(R, S, dtype=f32, device=z_vals.device)
         row = torch.empty(R, _ROW, dtype=f32, device=z_vals.device)
         hp = heads.data_ptr()
-        rc = capi.lib().snrf_composite_fwd(c_void_p(hp), c_void_p(hp + 4), c_void_p(hp + 16), c_void_p(hp + 28),
-                                           c_int(10), c_int(10), c_int(10), c_int(10),
-                                           ptr(z_vals), ptr(dists), ptr(rays_d), ptr(valid), c_int(R), c_int(S),
-                                           c_int(inf_flag), c_int(inf_start), ptr(weights), ptr(trans), ptr(row), capi.stream())
+        head_args = (c_void_p(hp), c_void_p(hp + 4), c_void_p(hp + 16), c_void_p(hp + 28), c_int(10), c_int(10), c_int(10), c_int(10),
+                     ptr(z_vals), ptr(dists), ptr(rays_d), ptr(valid), c_int(R), c_int(S),
+                     c_int(inf_flag), c_int(inf_start), ptr(weights), ptr(trans), ptr(row))
+        if ert is not None and ert.eps > 0.0:
+            ert.sample_live = torch.empty(R * S, dtype=torch.uint8, device=z_vals.device)
+            rc = capi.lib().snrf_composite_fwd_ert(*head_args, capi.c_float(ert.eps), ptr(ert.sample_live), capi.stream())
+        else:
+            ert = None
+            rc = capi.lib().snrf_composite_fwd(*head_args, capi.stream())
         capi.check(rc, "snrf_composite_fwd")
         ctx.save_for_backward(heads, z_vals, dists, rays_d, trans, valid if valid is not None else heads.new_empty(0))
-        ctx.infinity, ctx.inf_start, ctx.has_valid = inf_flag, inf_start, valid is not None
+        ctx.infinity, ctx.inf_start, ctx.has_valid, ctx.ert = inf_flag, inf_start, valid is not None, ert
         ctx.set_materialize_grads(False)        # an unused `weights` output costs no zero-filled gradient
         return row, weights
 
@@ -103,16 +118,18 @@ class CompositePackedFn(torch.autograd.Function):
         g_heads = torch.empty_like(heads)
         g_d = torch.empty_like(rays_d) if ctx.needs_input_grad[3] else None
         hp, gp = heads.data_ptr(), g_heads.data_ptr()
-        rc = capi.lib().snrf_composite_bwd(c_void_p(hp), c_void_p(hp + 4), c_void_p(hp + 16), c_void_p(hp + 28),
-                                           c_int(10), c_int(10), c_int(10), c_int(10),
-                                           ptr(z_vals), ptr(dists), ptr(rays_d), ptr(trans), ptr(g_row),
-                                           ptr(gw), ptr(valid) if ctx.has_valid else c_void_p(0),
-                                           c_int(R), c_int(S), c_int(ctx.infinity), c_int(ctx.inf_start),
-                                           c_void_p(gp), c_void_p(gp + 4), c_void_p(gp + 16), c_void_p(gp + 28),
-                                           c_int(10), c_int(10), c_int(10), c_int(10),
-                                           ptr(g_d) if g_d is not None else c_void_p(0), capi.stream())
+        args = (c_void_p(hp), c_void_p(hp + 4), c_void_p(hp + 16), c_void_p(hp + 28), c_int(10), c_int(10), c_int(10), c_int(10),
+                ptr(z_vals), ptr(dists), ptr(rays_d), ptr(trans), ptr(g_row),
+                ptr(gw), ptr(valid) if ctx.has_valid else c_void_p(0),
+                c_int(R), c_int(S), c_int(ctx.infinity), c_int(ctx.inf_start),
+                c_void_p(gp), c_void_p(gp + 4), c_void_p(gp + 16), c_void_p(gp + 28),
+                c_int(10), c_int(10), c_int(10), c_int(10), ptr(g_d) if g_d is not None else c_void_p(0))
+        if ctx.ert is not None:
+            rc = capi.lib().snrf_composite_bwd_ert(*args, ptr(ctx.ert.sample_live), capi.stream())
+        else:
+            rc = capi.lib().snrf_composite_bwd(*args, capi.stream())
         capi.check(rc, "snrf_composite_bwd")
-        return g_heads, None, None, g_d, None, None
+        return g_heads, None, None, g_d, None, None, None
 
 
 def _finish(row, weights, train, valid=None):
@@ -129,8 +146,8 @@ def _finish(row, weights, train, valid=None):
     return out
 
 
-def composite_packed(heads, z_vals, dists, rays_d, infinity, train, valid=None):
-    row, weights = CompositePackedFn.apply(heads, z_vals, dists, rays_d, infinity, valid)
+def composite_packed(heads, z_vals, dists, rays_d, infinity, train, valid=None, ert=None):
+    row, weights = CompositePackedFn.apply(heads, z_vals, dists, rays_d, infinity, valid, ert)
     return _finish(row, weights, train, valid)
 
 

@@ -141,11 +141,13 @@ class TileStep:
     def __init__(self, device, tile_corner, tile_size, Ks, c2ws, log2_hashmap_size=24, grid_resolution=(32, 8192),
                  num_sample=128, num_bg_sample=128, mesh_path="", sampler_log2dim=4, pose_noise=None,
                  lr_table=1e-3, lr_decoder=1e-3, lr_cam=1e-4, global_step=10000, invalid_underground=False,
-                 dense_table_adam=False):
+                 dense_table_adam=False, ert_eps=0.0):
         self.device = device
         f = lambda v: torch.as_tensor(v, dtype=torch.float32, device=device)
         self.featureGrid = HashGrid(device, f(tile_corner), f(tile_size), log2_hashmap_size, list(grid_resolution),
                                     sampler_log2dim, False, mesh_path)
+        # early ray termination in training (opt-in, 0 = the reference's semantics; see HashGrid.ert_eps)
+        self.featureGrid.ert_eps = float(ert_eps)
         self.decoder = ShallowMLP(32).to(device)
         self.poses = Poses(Ks, c2ws, device, pose_noise)
         self.num_sample, self.num_bg_sample = num_sample, num_bg_sample
