@@ -328,6 +328,18 @@ def bench_variants(step, cfg, dev, gen, devb, plain_ms):
     out["c1"] = {"workload": "c1-small: 16 x 2^19 x 2 table, %d rays x %d samples" % (B1, c1["S"] + c1["S_bg"]),
                  "ms_per_step": ms, "value": B1 / (ms * 1e-3), "unit": "rays/s", "steps": 20}
     del s1, b1
+    # (a) the warp loss on the headline tile
+    N, H, W = cfg["n_cam"], cfg["H"], cfg["W"]
+    images = torch.randint(0, 256, (N, H, W, 3), generator=gen, dtype=torch.uint8)
+    occl = torch.ones(N, H, W, 1, dtype=torch.bool)
+    step.enable_warp_loss(images, alpha=0.5, gamma=2.0, weight=1.0, occlusions=occl)
+    ms, loss = _time_steps(step, devb[:14], 4)
+    step.warp = None
+    B = devb[0][0].shape[0]
+    out["warp_loss"] = {"workload": "default.yaml single tile + warp loss (10 neighbour views per ray re-rendered)",
+                        "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "rays/s", "steps": 10, "loss_finite": loss == loss,
+                        "ms_per_step_without": plain_ms,
+                        "table_update": "gradient table + sparse Adam (two encodes of the table per step)"}
     # (c) early ray termination in training (opt-in, TileStep(ert_eps)): the random-initialised field of the headline is
     # nearly transparent, nothing terminates there; an OPAQUE field (density head bias + 5: rays saturate within a few samples,
     # as in a converged tile) shows what the backward kernels skip.  Same tile, same batches, with and without.
@@ -341,23 +353,10 @@ def bench_variants(step, cfg, dev, gen, devb, plain_ms):
     step.featureGrid.ert_eps = 0.0
     with torch.no_grad():
         step.decoder.sigma_layer.mlp[0].bias -= 5.0
-    B = devb[0][0].shape[0]
     m0, m1 = sum(ert[0.0]) / len(ert[0.0]), sum(ert[1e-4]) / len(ert[1e-4])
     out["ert_opaque_field"] = {"workload": "default.yaml single tile, density bias + 5 (opaque field), ert_eps 1e-4 vs 0",
                                "ms_per_step": m1, "ms_per_step_without": m0, "value": B / (m1 * 1e-3), "unit": "rays/s",
                                "steps": 20, "note": "opt-in approximation (the reference back-propagates every sample); off in the headline"}
-    # (a) the warp loss on the headline tile (kept last: it changes the step's configuration)
-    N, H, W = cfg["n_cam"], cfg["H"], cfg["W"]
-    images = torch.randint(0, 256, (N, H, W, 3), generator=gen, dtype=torch.uint8)
-    occl = torch.ones(N, H, W, 1, dtype=torch.bool)
-    step.enable_warp_loss(images, alpha=0.5, gamma=2.0, weight=1.0, occlusions=occl)
-    ms, loss = _time_steps(step, devb[:14], 4)
-    step.warp = None
-    B = devb[0][0].shape[0]
-    out["warp_loss"] = {"workload": "default.yaml single tile + warp loss (10 neighbour views per ray re-rendered)",
-                        "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "rays/s", "steps": 10, "loss_finite": loss == loss,
-                        "ms_per_step_without": plain_ms,
-                        "table_update": "gradient table + sparse Adam (two encodes of the table per step)"}
     return out
 
 
