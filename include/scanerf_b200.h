@@ -223,6 +223,18 @@ int snrf_field_encode_bwd_adam_ert(const float* rays_o, const float* rays_d, con
                                    const unsigned char* ray_valid, int split, int N, int S, int L, int T,
                                    const unsigned char* sample_live, void* stream);
 
+/* Colour loss of the joint foreground + background batch, value and gradient in one pass: replaces the torch chain between the
+ * compositing rows and loss.backward() in TILE.train_one_step -- the merge of the two chains (tile.py:661-681), the clamp of
+ * HashGrid.render_batch_rays (hashgrid/__init__.py:589), the masked MSE (criterions.py:126-147), the specular L2 regulariser
+ * (tile.py:999).  row [2R,16] = rows of snrf_composite_fwd (rays [0,R) foreground, [R,2R) the background chains of the same
+ * pixels); valid_f / valid_b [R] bytes; gt [R,3].
+ *   pred = clamp(dif_f + spec_f, 0, 1) + T_left_f * clamp(dif_b + spec_b, 0, 1)
+ *   loss = sum_{valid_f | valid_b} |pred - gt|^2 / (3 n_valid) + l2_weight * (sum row_f[10:13] / (3 n_f) + sum row_b[10:13] / (3 n_b))
+ * loss: one float, ACCUMULATED (zero it first); g_row [2R,16] = d loss / d row, WRITTEN; pred_color [R,3] optional;
+ * counts_scratch: 3 ints of device scratch. */
+int snrf_joint_loss(const float* row, const unsigned char* valid_f, const unsigned char* valid_b, const float* gt,
+                    float l2_weight, int R, float* loss, float* g_row, float* pred_color, int* counts_scratch, void* stream);
+
 /* ---- decoder MLP on the tensor cores (tcgen05 / TMEM) ------------------------- */
 /* Self-test of the tensor-core conventions (no reference counterpart): X[128,64], W[64,64],
  * G[128,64] f32, rounded to bf16 inside -> Y = X W^T [128,64], DX = G W [128,64],

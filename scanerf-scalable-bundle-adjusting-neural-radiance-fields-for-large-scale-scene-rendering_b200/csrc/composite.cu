@@ -297,3 +297,103 @@ SNRF_API int snrf_composite_bwd_ert(const float* sigma, const float* tint, const
     composite_bwd_kernel<<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, trans, g_out, g_weights, ray_valid, R, S, infinity, inf_start, g, grad_rays_d, sample_live);
     SNRF_RETURN_LAUNCH("snrf_composite_bwd");
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Colour loss of the joint foreground + background batch, forward and gradient in one pass.
+//
+// Replaces (behaviour, not code) the torch chain between the compositing rows and loss.backward() in the training step:
+// TILE.render_rays' merge of the two chains (tile.py:661-681), the clamp of HashGrid.render_batch_rays (hashgrid/__init__.py:
+// 589), the masked MSE (criterions.py:126-147) and the specular L2 regulariser (tile.py:999) -- ~30 small launches forward and
+// ~30 backward per step.  row [2R,16] = the rows of snrf_composite_fwd, rays [0,R) the foreground chains, [R,2R) the background
+// chains of the same pixels:
+//   rgb_f = clamp(dif_f + spec_f, 0, 1), rgb_b likewise;  pred = rgb_f + T_left_f * rgb_b
+//   loss  = sum_{valid} |pred - gt|^2 / (3 n_valid) + l2_weight * (sum row_f[10:13] / (3 n_f) + sum row_b[10:13] / (3 n_b))
+// with valid = valid_f | valid_b, n_* = max(count, 1).  g_row [2R,16] = d loss / d row (WRITTEN, every entry).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256)
+joint_loss_count_kernel(const unsigned char* __restrict__ vf, const unsigned char* __restrict__ vb, int R, int* __restrict__ counts)
+{
+    int cf = 0, cb = 0, cv = 0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
+        const int f = vf[r] != 0, b = vb[r] != 0;
+        cf += f; cb += b; cv += f | b;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        cf += __shfl_xor_sync(0xffffffffu, cf, off); cb += __shfl_xor_sync(0xffffffffu, cb, off); cv += __shfl_xor_sync(0xffffffffu, cv, off);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(counts, cf); atomicAdd(counts + 1, cb); atomicAdd(counts + 2, cv); }
+}
+
+__global__ void __launch_bounds__(256)
+joint_loss_kernel(const float* __restrict__ row, const unsigned char* __restrict__ vf, const unsigned char* __restrict__ vb,
+                  const float* __restrict__ gt, float l2_weight, int R, const int* __restrict__ counts, float* __restrict__ loss,
+                  float* __restrict__ g_row, float* __restrict__ pred_out)
+{
+    const float nf = (float)max(counts[0], 1), nb = (float)max(counts[1], 1), nv = (float)max(counts[2], 1);
+    const float inv_mse = 1.0f / (3.0f * nv), l2f = l2_weight / (3.0f * nf), l2b = l2_weight / (3.0f * nb);
+    float acc = 0.0f;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
+        const float4* pf = reinterpret_cast<const float4*>(row + (size_t)r * kOutStride);
+        const float4* pb = reinterpret_cast<const float4*>(row + (size_t)(R + r) * kOutStride);
+        const float4 f1 = pf[1], f2 = pf[2], f3v = pf[3], b1 = pb[1], b2 = pb[2], b3v = pb[3];
+        // row: [0] depth, [1..3] tint, [4..6] diffuse, [7..9] specular, [10..12] l2, [13] T_left
+        const float xf[3] = {f1.x + f1.w, f1.y + f2.x, f1.z + f2.y};
+        const float xb[3] = {b1.x + b1.w, b1.y + b2.x, b1.z + b2.y};
+        const float T = f3v.y;
+        const bool valid = (vf[r] | vb[r]) != 0;
+        float gp[3], gT = 0.0f, pf_pass[3], pb_pass[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float rf = fminf(fmaxf(xf[c], 0.0f), 1.0f), rb = fminf(fmaxf(xb[c], 0.0f), 1.0f);
+            const float pred = rf + T * rb;
+            const float diff = pred - gt[3 * (size_t)r + c];
+            if (pred_out) pred_out[3 * (size_t)r + c] = pred;
+            if (valid) acc += diff * diff * inv_mse;
+            gp[c] = valid ? 2.0f * diff * inv_mse : 0.0f;
+            pf_pass[c] = (xf[c] >= 0.0f && xf[c] <= 1.0f) ? gp[c] : 0.0f;           // torch.clamp: the gradient passes on [min, max]
+            pb_pass[c] = (xb[c] >= 0.0f && xb[c] <= 1.0f) ? gp[c] * T : 0.0f;
+            gT += gp[c] * rb;
+        }
+        acc += l2f * (f2.z + f2.w + f3v.x) + l2b * (b2.z + b2.w + b3v.x);
+        float4* gf = reinterpret_cast<float4*>(g_row + (size_t)r * kOutStride);
+        float4* gb = reinterpret_cast<float4*>(g_row + (size_t)(R + r) * kOutStride);
+        gf[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gf[1] = make_float4(pf_pass[0], pf_pass[1], pf_pass[2], pf_pass[0]);
+        gf[2] = make_float4(pf_pass[1], pf_pass[2], l2f, l2f);
+        gf[3] = make_float4(l2f, gT, 0.f, 0.f);
+        gb[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gb[1] = make_float4(pb_pass[0], pb_pass[1], pb_pass[2], pb_pass[0]);
+        gb[2] = make_float4(pb_pass[1], pb_pass[2], l2b, l2b);
+        gb[3] = make_float4(l2b, 0.f, 0.f, 0.f);
+    }
+    acc = warp_sum(acc);
+    __shared__ float part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += part[i];
+        atomicAdd(loss, t);
+    }
+}
+
+}  // namespace
+
+// loss: one float, ACCUMULATED (zero it first); counts_scratch: 3 ints of device scratch (cleared here); pred_color [R,3] optional
+SNRF_API int snrf_joint_loss(const float* row, const unsigned char* valid_f, const unsigned char* valid_b, const float* gt,
+                             float l2_weight, int R, float* loss, float* g_row, float* pred_color, int* counts_scratch, void* stream)
+{
+    SNRF_CHECK_ARG(row && valid_f && valid_b && gt && loss && g_row && counts_scratch, "snrf_joint_loss: NULL argument");
+    if (R <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(counts_scratch, 0, 3 * sizeof(int), s);
+    int gx = snrf_div_up(R, 256);
+    const int cap = snrf_sm_count() * 4;
+    if (gx > cap) gx = cap;
+    joint_loss_count_kernel<<<gx, 256, 0, s>>>(valid_f, valid_b, R, counts_scratch);
+    joint_loss_kernel<<<gx, 256, 0, s>>>(row, valid_f, valid_b, gt, l2_weight, R, counts_scratch, loss, g_row, pred_color);
+    SNRF_RETURN_LAUNCH("snrf_joint_loss");
+}

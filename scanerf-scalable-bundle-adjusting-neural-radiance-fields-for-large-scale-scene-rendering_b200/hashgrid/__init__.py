@@ -338,14 +338,10 @@ class HashGrid(nn.Module):
         heads = _field.decoder_apply(feats, rays_d, mask32, S, params, valid, ert)
         return _render.composite_packed(heads, z_vals, dists, rays_d, infinity, train=(mode is TRAIN), valid=valid, ert=ert)
 
-    def render_fore_bg_rays(self, rays_o, rays_d, num_sample, decoder, mode, occlusion_mask=None, global_step=0,
-                            invalid_underground=True):
-        """render_fore_rays + render_bg_rays ("IZ" background, same sample count) as ONE batch of 2R rays through
-        every kernel: rays [0, R) are the foreground chain, rays [R, 2R) the background chain (the encode kernel
-        switches the contraction, the compositing kernel the infinite last step, at ray R).  Halves the launches
-        and -- the point -- streams the hash table through L2 once per step instead of once per chain.
-        Returns (fore dict, background dict) with the keys of the two separate calls, or None when the fused path
-        is not available (non-stock decoder)."""
+    def _fore_bg_rows(self, rays_o, rays_d, num_sample, decoder, mode, occlusion_mask=None, global_step=0,
+                      invalid_underground=True):
+        """The joint 2R-ray batch up to the compositing rows: (row [2R,16], weights [2R,S], v_f, v_b) or None when the
+        fused path is not available (non-stock decoder)."""
         params = self._fused_ready(decoder)
         if params is None:
             return None
@@ -365,12 +361,39 @@ class HashGrid(nn.Module):
         feats = _field.field_encode(o2, d2, z2, self.HE.features, self.HE.resolution, self.min_bbox, self.bbox_size, 3, valid2, R, ert)
         heads = _field.decoder_apply(feats, d2, mask32, num_sample, params, valid2, ert)
         row, weights = _render.CompositePackedFn.apply(heads, z2, dist2, d2, R, valid2, ert)      # rays >= R end at infinity
+        return row, weights, v_f, v_b
+
+    def render_fore_bg_rays(self, rays_o, rays_d, num_sample, decoder, mode, occlusion_mask=None, global_step=0,
+                            invalid_underground=True):
+        """render_fore_rays + render_bg_rays ("IZ" background, same sample count) as ONE batch of 2R rays through
+        every kernel: rays [0, R) are the foreground chain, rays [R, 2R) the background chain (the encode kernel
+        switches the contraction, the compositing kernel the infinite last step, at ray R).  Halves the launches
+        and -- the point -- streams the hash table through L2 once per step instead of once per chain.
+        Returns (fore dict, background dict) with the keys of the two separate calls, or None when the fused path
+        is not available (non-stock decoder)."""
+        rows = self._fore_bg_rows(rays_o, rays_d, num_sample, decoder, mode, occlusion_mask, global_step, invalid_underground)
+        if rows is None:
+            return None
+        row, weights, v_f, v_b = rows
+        R = rays_o.shape[0]
         train = mode is TRAIN
         fg = _render._finish(row[:R], weights[:R], train, v_f)
         bg = _render._finish(row[R:], weights[R:], train, v_b)
         fg.update({"pred_color": fg["rgb"], "pred_depth": fg["depth"], "T_left": fg["T_left"][:, None], "fore_valid": v_f})
         bg.update({"T_left": bg["T_left"][:, None], "valid": v_b})
         return fg, bg
+
+    def fore_bg_colour_loss(self, rays_o, rays_d, num_sample, decoder, gt_color, l2_weight=0.01, global_step=0,
+                            invalid_underground=True):
+        """The training step's colour loss straight from the joint batch's compositing rows: the merge of the two chains
+        (tile.py:661-681), the clamp, the masked MSE (criterions.py:126-147) and `l2_weight` x the specular L2 regulariser
+        (tile.py:999) with their gradient as ONE kernel (_render.JointLossFn) instead of ~60 small torch launches.  Same value and
+        gradients as TileStep.loss computes from render_fore_bg_rays.  None when the fused path is not available."""
+        rows = self._fore_bg_rows(rays_o, rays_d, num_sample, decoder, TRAIN, None, global_step, invalid_underground)
+        if rows is None:
+            return None
+        row, _, v_f, v_b = rows
+        return _render.JointLossFn.apply(row, v_f, v_b, gt_color, l2_weight)
 
     def render_fore_rays(self, rays_o, rays_d, num_sample, decoder, mode, occlusion_mask=None, infinity=False, **kwargs):
         z_vals, dists = self.samplePoints(rays_o, rays_d, num_sample)

@@ -170,6 +170,7 @@ class TileStep:
         self.two_streams = False
         self.fused_table_update = True  # encode backward applies the sparse Adam slice by slice (see _table_backward)
         self.joint_chains = True        # foreground + background as one 2R-ray batch per kernel (render_fore_bg_rays)
+        self.fused_loss = True          # step_device: merge + clamp + masked MSE + L2 regulariser and their gradient as one kernel
         self._side = None
         self.consensus = None           # ADMM state, see enable_consensus()
         self.camera_ids = None
@@ -358,9 +359,23 @@ class TileStep:
             return opt.table_backward(fused=self.fused_table_update and self.warp is None)
         return _gradmode.table_backward("direct")
 
+    def loss_fused(self, locs, gt_color):
+        """The loss of `loss()` without its dictionary of intermediate images: the colour terms come from one kernel
+        (HashGrid.fore_bg_colour_loss).  None when that path does not apply (warp loss, separate chains, non-stock decoder)."""
+        if not (self.fused_loss and self.joint_chains and self.warp is None and self.num_sample == self.num_bg_sample):
+            return None
+        rays_o, rays_d = self.poses.rays(locs)
+        loss = self.featureGrid.fore_bg_colour_loss(rays_o, rays_d, self.num_sample, self.decoder, gt_color, 0.01,
+                                                    self.global_step, self.invalid_underground)
+        if loss is not None and self.consensus is not None and self.consensus.has_overlap:
+            loss = loss + self.consensus.camera_loss()                     # "Admm Loss", weight 1 (criterions.py:107-108)
+        return loss
+
     def step_device(self, locs, gt_color):
         """Inputs already on the device.  Returns the loss as a device scalar (no host sync)."""
-        loss, _ = self.loss(locs, gt_color)
+        loss = self.loss_fused(locs, gt_color)
+        if loss is None:
+            loss, _ = self.loss(locs, gt_color)
         if loss is None:
             self.global_step += 1
             return torch.zeros((), device=self.device)

@@ -115,3 +115,34 @@ def test_fused_table_update_equals_unfused_step():
     assert abs(la[0] - lb[0]) < 1e-6 and abs(la[-1] - lb[-1]) < 1e-3 * abs(lb[-1])
     assert float((va - vb).abs().max()) <= 1e-3 * float(vb.abs().max())
     assert float(((pa - pb).abs() > 1e-4).float().mean()) < 1e-3
+
+
+def test_fused_colour_loss_equals_the_torch_chain():
+    """TileStep.loss_fused (one kernel: merge of the two chains, clamp, masked MSE, specular L2 regulariser, and their gradient)
+    against TileStep.loss (the torch chain of tile.py:661-681 / criterions.py:126-147 / tile.py:999): same value, same gradients
+    for the table, the decoder and the poses -- also with part of the colours clamped and rays masked out."""
+    load_pkg()
+    dev = torch.device("cuda:0")
+    res = []
+    for fused in (False, True):
+        step, locs, gt = _tile(dev)
+        with torch.no_grad():           # push part of the colours beyond 1 so that the clamp is active
+            step.decoder.diffuse_layer.mlp[0].bias += 1.5
+        if fused:
+            loss = step.loss_fused(locs.to(dev), gt.to(dev))
+            assert loss is not None
+        else:
+            loss, _ = step.loss(locs.to(dev), gt.to(dev))
+        loss.backward()
+        torch.cuda.synchronize()
+        res.append((float(loss), step.featureGrid.HE.features.grad.clone(), [p.grad.clone() for p in step.decoder.parameters()],
+                    step.poses.se3_refine.grad.clone()))
+    (l0, t0, d0, p0), (l1, t1, d1, p1) = res
+    assert abs(l0 - l1) < 1e-6 * max(abs(l0), 1.0), (l0, l1)
+
+    def rel(a, b):
+        return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-20)
+    assert rel(t1, t0) < 1e-4, rel(t1, t0)
+    assert rel(p1, p0) < 1e-4, rel(p1, p0)
+    for a, b in zip(d1, d0):
+        assert rel(a, b) < 2e-4, (tuple(a.shape), rel(a, b))
