@@ -362,7 +362,7 @@ class TileStep:
     def loss_fused(self, locs, gt_color):
         """The loss of `loss()` without its dictionary of intermediate images: the colour terms come from one kernel
         (HashGrid.fore_bg_colour_loss).  None when that path does not apply (warp loss, separate chains, non-stock decoder)."""
-        if not (self.fused_loss and self.joint_chains and self.warp is None and self.num_sample == self.num_bg_sample):
+        if not (getattr(self, "fused_loss", False) and self.joint_chains and self.warp is None and self.num_sample == self.num_bg_sample):
             return None
         rays_o, rays_d = self.poses.rays(locs)
         loss = self.featureGrid.fore_bg_colour_loss(rays_o, rays_d, self.num_sample, self.decoder, gt_color, 0.01,

@@ -129,6 +129,7 @@ def build_reference_step(dev, tile_corner, tile_size, Ks, c2w, log2T, grid_resol
     step.camera_ids = None
     step.two_streams = False
     step.joint_chains = False
+    step.fused_loss = False
     step.featureGrid_optimizer = torch.optim.Adam([{"params": step.featureGrid.parameters(), "lr": lr_table, "betas": (0.9, 0.99), "eps": 1e-15}])
     step.optimizer = torch.optim.Adam([{"params": step.decoder.parameters(), "lr": lr_decoder, "weight_decay": 1e-6},
                                        {"params": step.poses.se3_refine, "lr": lr_cam}])
