@@ -136,6 +136,7 @@ def build_drivers():
     import zipfile
     out = os.path.join(OUT, "ref_drivers.zip")
     files = sorted(glob.glob(os.path.join(REF, "*.py")) + glob.glob(os.path.join(REF, "tools", "*.py")) +
+                   [os.path.join(REF, "preprocess", "build_tiles.py")] +
                    glob.glob(os.path.join(REF, "config", "*.yaml")) +
                    [os.path.join(REF, "hashgrid", n) for n in ("__init__.py", "PyHashGrid.py", "PyHashGridBG.py")] +
                    [os.path.join(REF, "cuda", "__init__.py"), os.path.join(REF, "fastMesh", "__init__.py")])

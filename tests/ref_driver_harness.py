@@ -59,6 +59,14 @@ def setup_imports(arm):
 
 
 SCENE_YAML = """DATADIR: "{datadir}"
+ALLOCATION:
+  TILE_SIZE: [8, 13, 12]
+  OVERLAP_RATIO: 0.2
+  OFFSET: [0, 0, 0]
+  EXPECT_NUM: 3
+  MIN_NUM_IMAGE: 2
+  MAX_DIM_TILE: [100, 1, 100]
+  SCENE_TYPE: "outdoor"
 DESCRIPTION: ""
 PREFIX: ""
 INVALID_UNDERGROUND: False
@@ -142,6 +150,47 @@ def write_scene(root, n_cam, H, W, log2T, bs_log2, S, warp):
     return data, yml
 
 
+def allocate_tiles(args, yml, data):
+    """The reference's tile allocation, preprocess/build_tiles.py (a script: executed as __main__ from the zip with its own
+    argv) on the synthetic scene -> tiles/training_views.txt + tiles/tile_info.txt.  In the drop-in arm this repo's
+    tile_allocation.py then runs on the same scene and its files are recorded next to the script's."""
+    import zipfile
+    import torch
+    tiles = os.path.join(data, "tiles")
+    with zipfile.ZipFile(ZIP) as z:
+        src = z.read("preprocess/build_tiles.py").decode()
+    argv, sys.argv = sys.argv, ["build_tiles.py", yml, "0"]
+    try:
+        exec(compile(src, "preprocess/build_tiles.py", "exec"), {"__name__": "__main__", "__file__": "preprocess/build_tiles.py"})
+    finally:
+        sys.argv = argv
+    torch.cuda.synchronize()
+    out = {"arm": args.arm, "training_views": open(os.path.join(tiles, "training_views.txt")).read(),
+           "tile_info": open(os.path.join(tiles, "tile_info.txt")).read()}
+    if args.arm == "dropin":
+        import tile_allocation as ta
+        from fastMesh import FastMesh
+        from load_data import read_campara
+        from tools import utils
+        cfg = utils.parse_yaml(yml).ALLOCATION
+        ks, c2ws, H, W = read_campara(os.path.join(data, "camera.log"), True)
+        dev = torch.device("cuda:0")
+        fm = FastMesh(os.path.join(data, "mesh/mesh.ply"))
+        corners = ta.tile_grid(fm.get_sceneinfo().cpu(), cfg.TILE_SIZE, cfg.OVERLAP_RATIO, cfg.OFFSET, cfg.MAX_DIM_TILE)
+        related = ta.camera_tile_visibility(fm, torch.from_numpy(ks).to(dev), torch.from_numpy(c2ws).to(dev), H, W, corners,
+                                            cfg.TILE_SIZE, scale=4).cpu()
+        kept, views = ta.select_tiles_and_views(related, torch.from_numpy(c2ws)[:, :, 3], corners, cfg.TILE_SIZE, cfg.EXPECT_NUM,
+                                                cfg.MIN_NUM_IMAGE, cfg.SCENE_TYPE)
+        own = os.path.join(data, "tiles_own")
+        os.makedirs(own, exist_ok=True)
+        ta.write_tile_files(own, corners, cfg.TILE_SIZE, kept, views, cfg.SCENE_TYPE)
+        out["own_training_views"] = open(os.path.join(own, "training_views.txt")).read()
+        out["own_tile_info"] = open(os.path.join(own, "tile_info.txt")).read()
+    with open(args.out, "w") as fh:
+        json.dump(out, fh)
+    print(json.dumps({k: v[:200] for k, v in out.items()}), flush=True)
+
+
 def render_frame(args, cfg, data):
     """One frame of an exported tile through the reference's own renderer (rendering.py:28-44 sets it up from
     DATADIR/demo/<name>/tile-*/, refined_camera.log and val_new.txt; RenderingHashGrid.render_rays_base renders)."""
@@ -192,6 +241,7 @@ def main():
     ap.add_argument("--render-tile", default="", help="do not train: render one frame of this exported tile directory through the "
                                                       "reference's rendering.py (RenderingHashGrid.render_rays_base, rendering.py:286-544)")
     ap.add_argument("--render-out", default="", help="npz of the rendered frame (with --render-tile)")
+    ap.add_argument("--alloc", action="store_true", help="do not train: run the reference's preprocess/build_tiles.py on the scene")
     args = ap.parse_args()
     args.out = os.path.abspath(args.out)
     args.init_in, args.init_out = (os.path.abspath(v) if v else "" for v in (args.init_in, args.init_out))
@@ -205,6 +255,8 @@ def main():
     data, yml = write_scene(root, args.cams, 96, 128, args.log2T, args.bs_log2, args.samples, args.warp)
 
     from tools import utils
+    if args.alloc:
+        return allocate_tiles(args, yml, data)
     if args.render_tile:
         return render_frame(args, utils.parse_yaml(yml), data)
     # ---- what admm_trainer.py does before it creates a TILE (admm_trainer.py:19-24, 96-121, 187-218, 322-327)

@@ -110,3 +110,19 @@ def test_occupancy_pruning_through_the_reference_tile_matches(tmp_path):
         print(f"{k}: {int(a[k].sum())} / {a[k].size} cells kept by the reference, {differ} differ")
         assert differ <= max(2, a[k].size // 500), (k, differ)        # cells whose largest alpha sits on the threshold
     assert min(kept) < max(kept), "the threshold sweep must cut through the alpha range"
+
+
+def test_tile_allocation_script_of_the_reference_runs_on_the_dropin_and_pins_the_host_mirror(tmp_path):
+    """SURVEY 8f-4.  The reference's own preprocess/build_tiles.py (byte for byte, executed as a script from the zip) on the
+    synthetic scene, once on the reference's extensions (fastMesh first-hit depth, ray_aabb_intersection_v2) and once on the
+    drop-in: the files it writes (tiles/training_views.txt, tiles/tile_info.txt) must be identical.  And this repo's host mirror
+    (tile_allocation.py: the chunked, sync-free formulation of the same selection) must write the same two files."""
+    _need("ref_drivers.zip", "CUDA_EXT.so", "fastMesh.so")
+    ref = _run("reference", str(tmp_path / "ref.json"), 0, ["--alloc", "--cams", "24"], tmp_path)
+    ours = _run("dropin", str(tmp_path / "ours.json"), 0, ["--alloc", "--cams", "24"], tmp_path)
+    assert ref["tile_info"].count("\n") >= 3, "the scene must allocate at least two tiles:\n" + ref["tile_info"]
+    assert len(ref["training_views"].split()) > 8
+    assert ours["tile_info"] == ref["tile_info"], (ours["tile_info"], ref["tile_info"])
+    assert ours["training_views"] == ref["training_views"], (ours["training_views"], ref["training_views"])
+    assert ours["own_tile_info"] == ref["tile_info"], (ours["own_tile_info"], ref["tile_info"])
+    assert ours["own_training_views"] == ref["training_views"], (ours["own_training_views"], ref["training_views"])
