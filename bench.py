@@ -10,7 +10,8 @@ One step = one pass of the hot path over one batch of 2^14 synthetic rays:
   -> contraction -> 16-level hash encode -> decoder MLP -> compositing -> MSE
   -> backward through all of it (incl. the analytic pose gradient) -> sparse Adam + Adam.
 `value`   : rays/s with the batches already resident in HBM (CUDA-event timed).
-`e2e`     : rays/s through TileStep.step(): pinned host batch in, python float loss out.
+`e2e`     : rays/s through TileStep.step(): pinned host batch in, python float loss out (the loss of that step, copied to
+            pinned memory right after the forward and read back inside the call; the backward is queued behind it).
 `roofline`: the dominant kernel (hash-encode backward) timed live with CUDA events on its stream.
 `cpu_baseline` / --impl reference: the reference's math restated on the CPU (oracle/), timed on
             this box's host cores on a bounded sample of the same workload.

@@ -170,6 +170,7 @@ class TileStep:
         self.two_streams = False
         self.fused_table_update = True  # encode backward applies the sparse Adam slice by slice (see _table_backward)
         self.joint_chains = True        # foreground + background as one 2R-ray batch per kernel (render_fore_bg_rays)
+        self._loss_host, self._loss_event, self._loss_wanted = None, None, False      # step(): early loss readback
         self.fused_loss = True          # step_device: merge + clamp + masked MSE + L2 regulariser and their gradient as one kernel
         self._side = None
         self.consensus = None           # ADMM state, see enable_consensus()
@@ -378,7 +379,10 @@ class TileStep:
             loss, _ = self.loss(locs, gt_color)
         if loss is None:
             self.global_step += 1
-            return torch.zeros((), device=self.device)
+            loss = torch.zeros((), device=self.device)
+            self._post_loss(loss)
+            return loss
+        self._post_loss(loss.detach())
         self.featureGrid_optimizer.zero_grad()
         self.optimizer.zero_grad()
         with self._table_backward():
@@ -436,8 +440,26 @@ class TileStep:
             with torch.no_grad():
                 self.poses.se3_refine.copy_(ck["poses"].to(self.device))
 
+    def _post_loss(self, loss):
+        """step(): the loss starts its way to the host as soon as the forward has produced it -- a copy into pinned memory and
+        an event BEFORE the backward is issued -- so that reading it does not wait for the backward / the optimisers."""
+        if getattr(self, "_loss_host", None) is not None and self._loss_wanted:
+            self._loss_host.copy_(loss.reshape(1), non_blocking=True)
+            self._loss_event.record()
+
     def step(self, locs_host, gt_host):
-        """The end-to-end call: pinned host batch in, python float loss out."""
-        locs = locs_host.to(self.device, non_blocking=True)
-        gt = gt_host.to(self.device, non_blocking=True)
-        return float(self.step_device(locs, gt).item())
+        """The end-to-end call: pinned host batch in, python float loss out.  The float is this step's loss, read back inside the
+        call; the call returns once the FORWARD has run on the device (the backward and the updates are queued behind it), so
+        a training loop that logs the loss every step keeps the device busy instead of draining it once per step."""
+        if getattr(self, "_loss_host", None) is None:
+            self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+            self._loss_event = torch.cuda.Event()
+        self._loss_wanted = True
+        try:
+            locs = locs_host.to(self.device, non_blocking=True)
+            gt = gt_host.to(self.device, non_blocking=True)
+            self.step_device(locs, gt)
+        finally:
+            self._loss_wanted = False
+        self._loss_event.synchronize()
+        return float(self._loss_host[0])
