@@ -18,7 +18,9 @@ pkg = importlib.import_module(bench.PKG)
 pkg.install()
 import scanerf_b200_capi as capi  # noqa: E402
 
-cfg = bench.WORKLOADS[os.environ.get("SNRF_PROFILE_WORKLOAD", "default.yaml-single-tile")]
+cfg = dict(bench.WORKLOADS[os.environ.get("SNRF_PROFILE_WORKLOAD", "default.yaml-single-tile")])
+if os.environ.get("SNRF_PROFILE_LOG2T"):          # the same workload on a smaller / larger table (L2-residency experiments)
+    cfg["log2T"] = int(os.environ["SNRF_PROFILE_LOG2T"])
 dev = torch.device("cuda:0")
 step, gen = bench.build_tile(cfg, dev, 0)
 capi.lib().snrf_field_set_overlap(ctypes.c_int(int(os.environ.get("SNRF_PROFILE_OVERLAP", "0"))))
