@@ -340,7 +340,7 @@ def bench_variants(step, cfg, dev, gen, devb, plain_ms):
     out["warp_loss"] = {"workload": "default.yaml single tile + warp loss (10 neighbour views per ray re-rendered)",
                         "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "rays/s", "steps": 10, "loss_finite": loss == loss,
                         "ms_per_step_without": plain_ms,
-                        "table_update": "gradient table + sparse Adam (two encodes of the table per step)"}
+                        "table_update": "scatter + sparse Adam fused per slice (the neighbour re-render carries no graph: one encode in the backward)"}
     # (c) early ray termination in training (opt-in, TileStep(ert_eps)): the random-initialised field of the headline is
     # nearly transparent, nothing terminates there; an OPAQUE field (density head bias + 5: rays saturate within a few samples,
     # as in a converged tile) shows what the backward kernels skip.  Same tile, same batches, with and without.

@@ -351,13 +351,15 @@ class TileStep:
         return loss, out
 
     def _table_backward(self):
-        """The explicit opt-in for where the table gradient goes (hashgrid/_gradmode.py).  vdbAdam + one encode per
-        step (no warp loss, which re-renders neighbour rays through the same table): scatter + update fusion, the
-        gradient table never exists.  Otherwise: accumulate into `.grad` in place."""
+        """The explicit opt-in for where the table gradient goes (hashgrid/_gradmode.py).  vdbAdam: scatter + update fusion, the
+        gradient table never exists -- it needs exactly one encode of the table in the BACKWARD, which also holds with the warp
+        loss: its re-render of the neighbour rays (warp_loss.py:355-377, compute_visibility) runs without a graph, only the
+        main chain is differentiated (vdbAdam raises if a second encode ever reaches the backward).  Otherwise: accumulate
+        into `.grad` in place."""
         from hashgrid import _gradmode
         opt = self.featureGrid_optimizer
         if isinstance(opt, vdbAdam):
-            return opt.table_backward(fused=self.fused_table_update and self.warp is None)
+            return opt.table_backward(fused=self.fused_table_update)
         return _gradmode.table_backward("direct")
 
     def loss_fused(self, locs, gt_color):

@@ -140,3 +140,31 @@ def test_warp_loss_without_valid_rays_is_zero():
     loss = wl(0, rays_o, rays_d, torch.ones(B, 1, device=DEV), z3, torch.zeros(B, 3, device=DEV), None,
               torch.zeros(B, dtype=torch.bool, device=DEV), None)
     assert float(loss) == 0.0
+
+
+def test_warp_loss_step_with_fused_table_update_equals_unfused():
+    """The training step WITH the warp loss on the scatter + Adam fusion: the neighbour re-render carries no graph
+    (warp_loss.py:355-377 runs under no_grad), so exactly one encode of the table reaches the backward and the in-backward
+    update applies (vdbAdam would raise on a second one).  Same table / decoder / poses after two steps as with the gradient
+    table + separate sparse Adam."""
+    load_pkg()
+    states = []
+    for fused in (True, False):
+        torch.manual_seed(0)
+        step, locs, images, occl, H, W = _tile()
+        with torch.no_grad():
+            step.featureGrid.HE.features.mul_(20.0)
+        step.enable_warp_loss(images, alpha=0.01, gamma=2.0, weight=1.0, occlusions=occl, topK=8)
+        step.fused_table_update = fused
+        gt = torch.rand(locs.shape[0], 3, generator=torch.Generator().manual_seed(3)).to(DEV)
+        l0 = float(step.step_device(locs, gt))
+        l1 = float(step.step_device(locs, gt))
+        torch.cuda.synchronize()
+        states.append((l0, l1, step.featureGrid.HE.features.detach().clone(),
+                       [p.detach().clone() for p in step.decoder.parameters()], step.poses.se3_refine.detach().clone()))
+    (a0, a1, ta, da, pa), (b0, b1, tb, db, pb) = states
+    assert abs(a0 - b0) < 1e-6 * max(abs(b0), 1.0) and abs(a1 - b1) < 2e-4 * max(abs(b1), 1e-3), (a0, b0, a1, b1)
+    assert float((ta - tb).abs().max()) < 5e-5, float((ta - tb).abs().max())        # (two Adam steps of lr 1e-3; see test_ert_gpu)
+    for x, y in zip(da, db):
+        assert float((x - y).abs().max()) < 5e-5
+    assert float((pa - pb).abs().max()) < 5e-6
