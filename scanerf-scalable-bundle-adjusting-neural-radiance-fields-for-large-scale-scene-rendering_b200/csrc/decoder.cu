@@ -1049,14 +1049,23 @@ decoder_bwd_fold_kernel(const float* __restrict__ feats, const float* __restrict
         if (lead_warp && umma::elect_one()) {
             dgrad(cDb, ag3, 0, aLOa, 0, aW32, aW32l, 4, idg64, false);
             dgrad(cDb, adz, 0, adz, 2, aWh2, aWh2l, 1, idg64, true);
-            dgrad(cSH, ag3, 0, aLOa, 0, aW3b, aW3b + 64, 4, idg16, false);
+            dgrad(cSH, ag3, 0, aLOa, 0, aW3b, aW3b + 64, 4, idg16, false);    // (N = 16: cheap; reads the dz3 lo tile this epilogue overwrites)
             umma::mma_commit(&bar);
             wgrad(gG, ag3, aa1, idw64, first);
             wgrad(gW3b, ag3, aA0 + 64, idw16, first);
         }
         wait_mma();
         mul_inplace(cDb, tg1, tLOa);                                 // dz1
-        if (grad_rays_d != nullptr && cg == 3) {                     // d/d(ray direction) through the SH encoding (one thread per row)
+        sync_operands();
+        // ---- B5: dx = dz1 W1 (32 columns) ; dW1 += dz1^T [x | SH] (column 32 -> db1)
+        if (lead_warp && umma::elect_one()) {
+            dgrad(cDa, ag1, 0, aLOa, 0, aW1, aW1 + 64, 4, idg32, false);
+            umma::mma_commit(&bar);
+            wgrad(gW1, ag1, aA0, idw48, first);
+            umma::mma_commit(&bar_tail);                            // everything this tile issued
+        }
+        // (under the B5 MMAs) d/d(ray direction) through the SH encoding, one thread per row of column group 3
+        if (grad_rays_d != nullptr && cg == 3) {
             float dsh[16];
             umma::tmem_ld16(tmem + cSH + lane_addr, dsh);
             umma::tc_wait_ld();
@@ -1105,14 +1114,6 @@ decoder_bwd_fold_kernel(const float* __restrict__ feats, const float* __restrict
                 atomicAdd(grad_rays_d + 3 * (size_t)ray + 1, gy);
                 atomicAdd(grad_rays_d + 3 * (size_t)ray + 2, gz);
             }
-        }
-        sync_operands();
-        // ---- B5: dx = dz1 W1 (32 columns) ; dW1 += dz1^T [x | SH] (column 32 -> db1)
-        if (lead_warp && umma::elect_one()) {
-            dgrad(cDa, ag1, 0, aLOa, 0, aW1, aW1 + 64, 4, idg32, false);
-            umma::mma_commit(&bar);
-            wgrad(gW1, ag1, aA0, idw48, first);
-            umma::mma_commit(&bar_tail);                            // everything this tile issued
         }
         wait_mma();
         umma::tmem_ld8(tmem + cDa + lane_addr + 8 * cg, v);         // d/d x, columns 8 cg .. 8 cg + 7 = levels 4 cg .. 4 cg + 3
