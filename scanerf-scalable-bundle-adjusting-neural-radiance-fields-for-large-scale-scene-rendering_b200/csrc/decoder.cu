@@ -888,9 +888,6 @@ decoder_bwd_fold_kernel(const float* __restrict__ feats, const float* __restrict
             store8_act<SPLIT>(Tg, 2 * cg + q, Tlo, 2 * cg + q, row, o);
         }
     };
-    Tiles Tin{};
-    Tin.A0 = tA0; Tin.LOb = tLOb;
-
     const bool lead_warp = umma::warp_uniform() == 4;
     bool first = true;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -913,15 +910,13 @@ decoder_bwd_fold_kernel(const float* __restrict__ feats, const float* __restrict
                 }
             }
         }
-        // ---- input rows: 8 features per thread times the level mask; SH of d / (|d| + 1e-8) (column groups 2, 3)
+        // ---- input rows: 8 features per thread times the level mask (the SH columns follow under the L1 MMAs)
         f3 d = mk3(0.f, 0.f, 1.f);
         float dn = 1.0f;
         {
-            float x[8], sh[16];
+            float x[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) sh[j] = 0.0f;
             if (live) {
                 if (level_stride == 0) {
 #pragma unroll
@@ -937,14 +932,9 @@ decoder_bwd_fold_kernel(const float* __restrict__ feats, const float* __restrict
                         x[2 * l] = a.x; x[2 * l + 1] = a.y;
                     }
                 }
+                if (cg >= 2) d = ld3(rays_d + 3 * (size_t)(n / S));      // (issued now, consumed under the L1 MMAs)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) x[j] *= maskv[8 * cg + j];
-                if (cg >= 2) {
-                    d = ld3(rays_d + 3 * (size_t)(n / S));
-                    dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
-                    const float inv = 1.0f / (dn + 1e-8f);
-                    sh16(d.x * inv, d.y * inv, d.z * inv, sh);
-                }
             }
             // the previous tile's trailing weight-gradient MMAs still read the operand tiles: waited for here, after this
             // tile's global loads have been issued
@@ -954,13 +944,27 @@ decoder_bwd_fold_kernel(const float* __restrict__ feats, const float* __restrict
                 tail_phase ^= 1u;
                 tail_pending = false;
             }
-            store_input_row<SPLIT, 4>(Tin, row, cg, x, sh + 8 * ((cg - 2) & 1));
+            store8_act<SPLIT>(tA0, cg, tLOb, cg, row, x);               // x_hi -> A0 columns 8 cg .., x_lo -> LOb
         }
         sync_operands();
         // ---- L1: Da = x W1^T (K = 32)
         if (lead_warp && umma::elect_one()) {
             fwd_gemm<SPLIT>(tmem + cDa, aA0, 0, aLOb, 0, aW1, 0, aW1, 2, 2, idf64, false);
             umma::mma_commit(&bar);
+        }
+        // (under the L1 MMAs, which read columns 0..31 of A0 only) SH of d / (|d| + 1e-8) -> A0 columns 32..47 (hi) / 48..63 (lo):
+        // column group 2 stores SH 0..7, column group 3 SH 8..15; the z3 stage's sync_operands orders the stores
+        if (cg >= 2) {
+            float sh[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sh[j] = 0.0f;
+            if (live) {
+                dn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+                const float inv = 1.0f / (dn + 1e-8f);
+                sh16(d.x * inv, d.y * inv, d.z * inv, sh);
+            }
+            store8_act<SPLIT>(tA0, 4 + (cg - 2), tA0, 6 + (cg - 2), row, sh + 8 * (cg - 2));
+            if (!SPLIT) umma::tile_zero8(tA0, row, 6 + (cg - 2));
         }
         wait_mma();
         gauss_epilogue(cDa, oB1, ta1, tLOa, tg1);
