@@ -180,11 +180,12 @@ decoder_fwd4_kernel(const float* __restrict__ feats, const float* __restrict__ m
         // and the first sync_operands of forward_layers4 orders these writes before any read)
         const int ray0 = n0 / S;
         const int last = (n0 + kRows - 1 < N ? n0 + kRows - 1 : N - 1) / S;
-        c.sync();
-        ray_vectors4<false>(rb, w3sh, rays_d, ray0, last - ray0 + 1, c.gtid);
         const int my_ray = (live ? n / S : ray0) - ray0;
         float head[10], zh[7];
-        forward_layers4<SPLIT, FOLD>(c, smem, P, Q, x, rb + my_ray * 64, head, zh);
+        // the ray vectors are formed under the L1 MMAs: the first barrier of forward_layers4 has every thread of the group past
+        // its last read of rb (the previous tile's z3 epilogue), two more barriers follow before the next read
+        forward_layers4<SPLIT, FOLD>(c, smem, P, Q, x, rb + my_ray * 64, head, zh,
+                                     [&]() { ray_vectors4<false>(rb, w3sh, rays_d, ray0, last - ray0 + 1, c.gtid); });
         float z[16];
         umma::tmem_ld16(c.tmem + c4Dh + c.lane_addr, z);
         umma::tc_wait_ld();

@@ -617,9 +617,12 @@ __device__ void stage_fold_weights4(unsigned char* smem, const DecoderParams& p,
 // the W2 tiles hold W32 = W3[:, 0:32] W2[32:64, :], the Wh tile / the first rows of the W3-lo tile hold Wh2 = Wh W2[0:32, :]
 // (hi / lo), the b3 / head bias slots the composed biases -- z3 and the heads come straight from a1 in ONE stage, H is never
 // formed: four dependent stages per tile instead of five, 12 MMAs and one 64-column epilogue less.
-template <bool SPLIT, bool FOLD = false>
+struct NoHook4 { __device__ __forceinline__ void operator()() const {} };
+// under_l1(): called by every thread of the group right after the L1 MMAs have been issued -- work that is not needed before
+// the z3 epilogue (the per-ray SH vectors rb) runs there instead of in front of the tile's first barrier.
+template <bool SPLIT, bool FOLD = false, class Hook = NoHook4>
 __device__ __forceinline__ void forward_layers4(Ctx4& c, unsigned char* smem, unsigned char* P, unsigned char* Q, const float* x,
-                                                const float* rb, float* head, float* zh)
+                                                const float* rb, float* head, float* zh, Hook under_l1 = Hook())
 {
     const int row = c.row;
     const uint32_t tmem = c.tmem, lane_addr = c.lane_addr;
@@ -641,6 +644,7 @@ __device__ __forceinline__ void forward_layers4(Ctx4& c, unsigned char* smem, un
         fwd_gemm<SPLIT>(tmem + c4D, aP, 0, aP, 2, aW1, 0, aW1, 2, 2, id64, false);
         umma::mma_commit(c.bar);
     }
+    under_l1();
     c.wait_mma();
     float v[32];
     // epilogue of a 64-wide layer on this thread's row, 32 columns at a time: v = D + bias (+ extra) -> f(v) -> (P, Q)

@@ -515,11 +515,10 @@ infer_decode4_kernel(InferArgs a, long long n0, int Nc, const float2* __restrict
             const int ray0 = (int)((n0 + i0) / a.S);
             const long long last_n = n0 + (i0 + kRows - 1 < Nc ? i0 + kRows - 1 : Nc - 1);
             const int nrays = (int)(last_n / a.S) - ray0 + 1;
-            c.sync();
-            ray_vectors4<true>(rb, w3sh, a.rays_d, ray0, nrays, c.gtid);
             const int my_ray = active ? (int)(n / a.S) - ray0 : 0;
             float head[10], zh[7];
-            forward_layers4<SPLIT, FOLD>(c, smem, P, Q, x, rb + my_ray * 64, head, zh);
+            forward_layers4<SPLIT, FOLD>(c, smem, P, Q, x, rb + my_ray * 64, head, zh,
+                                         [&]() { ray_vectors4<true>(rb, w3sh, a.rays_d, ray0, nrays, c.gtid); });   // under the L1 MMAs
             float zs[16];
             umma::tmem_ld16(c.tmem + c4Dh + c.lane_addr, zs);
             umma::tc_wait_ld();
