@@ -59,6 +59,10 @@ __device__ __forceinline__ float warp_incl_suffix_sum(float v, int lane)
     return v;
 }
 
+// PACKED: the four heads are the columns (sigma | tint3 | diffuse3 | specular3) of ONE [R*S, 10] array (the tensor-core decoder's
+// output): a warp's 32 rows are 1280 contiguous bytes, fetched with coalesced 8-byte loads into shared memory and read from
+// there -- the per-column loads at a 40-byte stride cost ten L1 wavefronts each and bound these kernels, not HBM.
+template <bool PACKED>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_fwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __restrict__ dists,
                      const float* __restrict__ rays_d, const unsigned char* __restrict__ ray_valid, int R, int S, int infinity,
@@ -69,6 +73,8 @@ composite_fwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int chunks = (S + 31) >> 5;
+    __shared__ __align__(16) float stage_all[PACKED ? kWarpsPerBlock * 320 : 1];
+    float* sw = stage_all + (PACKED ? (threadIdx.x >> 5) * 320 : 0);
     // composites ray r; `front` = transmittance in front of the ray's first sample for the termination test only (1, or the
     // T_left of the foreground chain when r is the background chain of the same pixel); returns the ray's T_left
     auto composite_ray = [&](int r, float front) -> float {
@@ -93,10 +99,17 @@ composite_fwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
             const bool live = k < S;
             const size_t n = (size_t)r * S + k;
             float beta = 1.0f, alpha = 0.0f;
+            if (PACKED) {
+                const int rows = min(32, S - c * 32);
+                const float2* src = reinterpret_cast<const float2*>(in.sigma + ((size_t)r * S + (size_t)c * 32) * 10);
+                __syncwarp();
+                for (int i = lane; i < rows * 5; i += 32) reinterpret_cast<float2*>(sw)[i] = __ldg(src + i);
+                __syncwarp();
+            }
             if (live) {
                 float delta = dists[n] * dn;
                 if (inf && k == S - 1) delta = 1e10f;
-                alpha = 1.0f - expf(-in.sigma[n * in.s_sigma] * delta);
+                alpha = 1.0f - expf(-(PACKED ? sw[lane * 10] : in.sigma[n * in.s_sigma]) * delta);
                 beta = 1.0f - alpha + 1e-6f;
             }
             const float incl = warp_incl_scan_mul(beta, lane);
@@ -112,9 +125,9 @@ composite_fwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
                 weights[n] = w;
                 if (trans) trans[n] = T;
                 const float z = z_vals[n];
-                const f3 ti = ld3(in.tint + n * in.s_tint);
-                const f3 di = ld3(in.diffuse + n * in.s_diffuse);
-                const f3 sp = ld3(in.specular + n * in.s_specular);
+                const f3 ti = PACKED ? ld3(sw + lane * 10 + 1) : ld3(in.tint + n * in.s_tint);
+                const f3 di = PACKED ? ld3(sw + lane * 10 + 4) : ld3(in.diffuse + n * in.s_diffuse);
+                const f3 sp = PACKED ? ld3(sw + lane * 10 + 7) : ld3(in.specular + n * in.s_specular);
                 acc[0] += w * z;
                 acc[1] += w * ti.x; acc[2] += w * ti.y; acc[3] += w * ti.z;
                 acc[4] += w * di.x; acc[5] += w * di.y; acc[6] += w * di.z;
@@ -153,6 +166,7 @@ composite_fwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
 // Backward.  g_out[R,16] uses the forward's row layout (depth, tint3, diffuse3, specular3,
 // l2_3, T_left); g_weights[R,S] optional.  Writes (overwrites) per-sample gradients and
 // accumulates nothing: grad_rays_d[R,3] is written (via |d| in delta).
+template <bool PACKED>      // (see composite_fwd_kernel; here the ten gradient columns of a row go back the same way)
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_bwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __restrict__ dists,
                      const float* __restrict__ rays_d, const float* __restrict__ trans,
@@ -164,6 +178,8 @@ composite_bwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const int chunks = (S + 31) >> 5;
+    __shared__ __align__(16) float stage_all[PACKED ? kWarpsPerBlock * 320 : 1];
+    float* sw = stage_all + (PACKED ? (threadIdx.x >> 5) * 320 : 0);
     for (int r = warp; r < R; r += nwarps) {
         if (ray_valid && !ray_valid[r]) {   // masked-out ray: its head gradients are never read downstream
             if (lane == 0 && grad_rays_d) st3(grad_rays_d + 3 * (size_t)r, mk3(0.f, 0.f, 0.f));
@@ -186,26 +202,38 @@ composite_bwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
             const size_t n = (size_t)r * S + k;
             float Gw = 0.0f, w = 0.0f, e = 1.0f, delta = 0.0f, sig = 0.0f, G = 0.0f, T = 0.0f;
             const bool dead = live && sample_live != nullptr && sample_live[n] == 0;    // terminated in the forward: weight 0, no gradient
+            const int rows = min(32, S - c * 32);
+            if (PACKED) {
+                const float2* src = reinterpret_cast<const float2*>(in.sigma + ((size_t)r * S + (size_t)c * 32) * 10);
+                __syncwarp();
+                for (int i = lane; i < rows * 5; i += 32) reinterpret_cast<float2*>(sw)[i] = __ldg(src + i);
+                __syncwarp();
+            }
+            f3 o_ti = mk3(0.f, 0.f, 0.f), o_di = o_ti, o_sp = o_ti;
             if (live) {
                 T = trans[n];
-                sig = in.sigma[n * in.s_sigma];
+                sig = PACKED ? sw[lane * 10] : in.sigma[n * in.s_sigma];
                 delta = dists[n] * dn;
                 if (inf && k == S - 1) delta = 1e10f;
                 e = expf(-sig * delta);                     // 1 - alpha
                 w = dead ? 0.0f : (1.0f - e) * T;
-                const f3 ti = ld3(in.tint + n * in.s_tint);
-                const f3 di = ld3(in.diffuse + n * in.s_diffuse);
-                const f3 sp = ld3(in.specular + n * in.s_specular);
+                const f3 ti = PACKED ? ld3(sw + lane * 10 + 1) : ld3(in.tint + n * in.s_tint);
+                const f3 di = PACKED ? ld3(sw + lane * 10 + 4) : ld3(in.diffuse + n * in.s_diffuse);
+                const f3 sp = PACKED ? ld3(sw + lane * 10 + 7) : ld3(in.specular + n * in.s_specular);
                 G = g_depth * z_vals[n] + dot3(g_ti, ti) + dot3(g_di, di) +
                     (g_sp.x * ti.x * sp.x + g_sp.y * ti.y * sp.y + g_sp.z * ti.z * sp.z);
                 if (g_weights) G += g_weights[n];
                 Gw = G * w;
                 // per-sample attribute gradients
-                st3(g.tint + n * g.s_tint, mk3(w * (g_ti.x + g_sp.x * sp.x), w * (g_ti.y + g_sp.y * sp.y), w * (g_ti.z + g_sp.z * sp.z)));
-                st3(g.diffuse + n * g.s_diffuse, w * g_di);
-                st3(g.specular + n * g.s_specular,
-                    mk3(w * (g_sp.x * ti.x + 2.0f * g_l2.x * sp.x), w * (g_sp.y * ti.y + 2.0f * g_l2.y * sp.y),
-                        w * (g_sp.z * ti.z + 2.0f * g_l2.z * sp.z)));
+                o_ti = mk3(w * (g_ti.x + g_sp.x * sp.x), w * (g_ti.y + g_sp.y * sp.y), w * (g_ti.z + g_sp.z * sp.z));
+                o_di = w * g_di;
+                o_sp = mk3(w * (g_sp.x * ti.x + 2.0f * g_l2.x * sp.x), w * (g_sp.y * ti.y + 2.0f * g_l2.y * sp.y),
+                           w * (g_sp.z * ti.z + 2.0f * g_l2.z * sp.z));
+                if (!PACKED) {
+                    st3(g.tint + n * g.s_tint, o_ti);
+                    st3(g.diffuse + n * g.s_diffuse, o_di);
+                    st3(g.specular + n * g.s_specular, o_sp);
+                }
             }
             // T_left = T_{S-1}: contributes to d/d alpha_k for k < S-1, i.e. it rides with sample S-1
             float tail = Gw;
@@ -215,8 +243,19 @@ composite_bwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
             if (live) {
                 const float beta = e + 1e-6f;
                 const float g_alpha = dead ? 0.0f : G * T - after / beta;
-                g.sigma[n * g.s_sigma] = g_alpha * delta * e;
+                const float o_sig = g_alpha * delta * e;
+                if (PACKED) {                                // (every lane has read its row: the shuffles above synchronised the warp)
+                    sw[lane * 10] = o_sig;
+                    st3(sw + lane * 10 + 1, o_ti); st3(sw + lane * 10 + 4, o_di); st3(sw + lane * 10 + 7, o_sp);
+                } else {
+                    g.sigma[n * g.s_sigma] = o_sig;
+                }
                 if (!(inf && k == S - 1)) g_dn += g_alpha * sig * e * dists[n];
+            }
+            if (PACKED) {
+                float2* dst = reinterpret_cast<float2*>(g.sigma + ((size_t)r * S + (size_t)c * 32) * 10);
+                __syncwarp();
+                for (int i = lane; i < rows * 5; i += 32) dst[i] = reinterpret_cast<const float2*>(sw)[i];
             }
             suffix += __shfl_sync(0xffffffffu, incl, 0);
         }
@@ -250,7 +289,11 @@ SNRF_API int snrf_composite_fwd_ert(const float* sigma, const float* tint, const
     SNRF_CHECK_ARG(ert_eps >= 0.0f && ert_eps < 1.0f, "snrf_composite_fwd_ert: ert_eps must lie in [0, 1) (got %g)", (double)ert_eps);
     if (R <= 0) return 0;
     Heads in{sigma, tint, diffuse, specular, s_sigma, s_tint, s_diffuse, s_specular};
-    composite_fwd_kernel<<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, ray_valid, R, S, infinity, inf_start, weights, trans, out, ert_eps, sample_live);
+    // one [R*S, 10] array behind the four pointers (the decoder's packed head rows)?
+    const bool packed = s_sigma == 10 && s_tint == 10 && s_diffuse == 10 && s_specular == 10 && tint == sigma + 1 && diffuse == sigma + 4 &&
+                        specular == sigma + 7 && ((uintptr_t)sigma & 7) == 0;
+    if (packed) composite_fwd_kernel<true><<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, ray_valid, R, S, infinity, inf_start, weights, trans, out, ert_eps, sample_live);
+    else composite_fwd_kernel<false><<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, ray_valid, R, S, infinity, inf_start, weights, trans, out, ert_eps, sample_live);
     SNRF_RETURN_LAUNCH("snrf_composite_fwd");
 }
 SNRF_API int snrf_composite_fwd(const float* sigma, const float* tint, const float* diffuse, const float* specular,
@@ -294,7 +337,12 @@ SNRF_API int snrf_composite_bwd_ert(const float* sigma, const float* tint, const
     if (R <= 0) return 0;
     Heads in{sigma, tint, diffuse, specular, s_sigma, s_tint, s_diffuse, s_specular};
     HeadGrads g{g_sigma, g_tint, g_diffuse, g_specular, gs_sigma, gs_tint, gs_diffuse, gs_specular};
-    composite_bwd_kernel<<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, trans, g_out, g_weights, ray_valid, R, S, infinity, inf_start, g, grad_rays_d, sample_live);
+    const bool packed = s_sigma == 10 && s_tint == 10 && s_diffuse == 10 && s_specular == 10 && tint == sigma + 1 && diffuse == sigma + 4 &&
+                        specular == sigma + 7 && ((uintptr_t)sigma & 7) == 0 &&
+                        gs_sigma == 10 && gs_tint == 10 && gs_diffuse == 10 && gs_specular == 10 && g_tint == g_sigma + 1 &&
+                        g_diffuse == g_sigma + 4 && g_specular == g_sigma + 7 && ((uintptr_t)g_sigma & 7) == 0;
+    if (packed) composite_bwd_kernel<true><<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, trans, g_out, g_weights, ray_valid, R, S, infinity, inf_start, g, grad_rays_d, sample_live);
+    else composite_bwd_kernel<false><<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, trans, g_out, g_weights, ray_valid, R, S, infinity, inf_start, g, grad_rays_d, sample_live);
     SNRF_RETURN_LAUNCH("snrf_composite_bwd");
 }
 
