@@ -186,6 +186,9 @@ int snrf_composite_bwd(const float* sigma, const float* tint, const float* diffu
                        int gs_sigma, int gs_tint, int gs_diffuse, int gs_specular,
                        float* grad_rays_d, void* stream);
 
+/* measurement hook: 1 = snrf_composite_fwd stages packed [R*S,10] head rows through shared memory as snrf_composite_bwd always
+ * does (default 0: measured slower in the forward) */
+void snrf_composite_set_fwd_packed(int on);
 /* Early ray termination in TRAINING (opt-in; the north star's compositing subsystem.  The reference evaluates and
  * back-propagates every sample, hashgrid/__init__.py:512-596, so this is an approximation the caller chooses: ert_eps = 0
  * reproduces snrf_composite_fwd exactly).  A sample whose transmittance in front of it is below ert_eps is composited with

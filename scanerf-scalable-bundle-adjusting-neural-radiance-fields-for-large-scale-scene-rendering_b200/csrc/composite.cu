@@ -267,6 +267,8 @@ composite_bwd_kernel(Heads in, const float* __restrict__ z_vals, const float* __
     }
 }
 
+int g_fwd_packed = 0;      // snrf_composite_set_fwd_packed
+
 inline int grid_rays(int R)
 {
     const int want = snrf_div_up(R, kWarpsPerBlock);
@@ -277,6 +279,8 @@ inline int grid_rays(int R)
 }  // namespace
 
 // ------------------------------- C ABI --------------------------------------
+// measurement hook: 1 = the forward stages packed head rows through shared memory like the backward does (default 0: slower)
+SNRF_API void snrf_composite_set_fwd_packed(int on) { g_fwd_packed = on ? 1 : 0; }
 // ert_eps > 0: early ray termination -- samples behind transmittance < ert_eps get weight 0; sample_live [R*S] (may be NULL)
 // receives 1 / 0 per sample (0 also for the samples of masked-out rays) for the backward kernels.
 SNRF_API int snrf_composite_fwd_ert(const float* sigma, const float* tint, const float* diffuse, const float* specular,
@@ -289,9 +293,11 @@ SNRF_API int snrf_composite_fwd_ert(const float* sigma, const float* tint, const
     SNRF_CHECK_ARG(ert_eps >= 0.0f && ert_eps < 1.0f, "snrf_composite_fwd_ert: ert_eps must lie in [0, 1) (got %g)", (double)ert_eps);
     if (R <= 0) return 0;
     Heads in{sigma, tint, diffuse, specular, s_sigma, s_tint, s_diffuse, s_specular};
-    // one [R*S, 10] array behind the four pointers (the decoder's packed head rows)?
-    const bool packed = s_sigma == 10 && s_tint == 10 && s_diffuse == 10 && s_specular == 10 && tint == sigma + 1 && diffuse == sigma + 4 &&
-                        specular == sigma + 7 && ((uintptr_t)sigma & 7) == 0;
+    // one [R*S, 10] array behind the four pointers (the decoder's packed head rows)?  Staging pays in the backward (ten strided
+    // stores per row on top of the loads: 0.152 -> 0.099 ms at C2) but not in the forward (0.063 -> 0.088 ms: its strided loads hit
+    // L1 after the first column): off here, kept selectable for measurements.
+    const bool packed = g_fwd_packed && s_sigma == 10 && s_tint == 10 && s_diffuse == 10 && s_specular == 10 && tint == sigma + 1 &&
+                        diffuse == sigma + 4 && specular == sigma + 7 && ((uintptr_t)sigma & 7) == 0;
     if (packed) composite_fwd_kernel<true><<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, ray_valid, R, S, infinity, inf_start, weights, trans, out, ert_eps, sample_live);
     else composite_fwd_kernel<false><<<grid_rays(R), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(in, z_vals, dists, rays_d, ray_valid, R, S, infinity, inf_start, weights, trans, out, ert_eps, sample_live);
     SNRF_RETURN_LAUNCH("snrf_composite_fwd");

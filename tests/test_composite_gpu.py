@@ -67,3 +67,31 @@ def test_composite_saturating_density_is_finite():
     assert torch.allclose(out["rgb"].cpu(), ref["rgb"], atol=1e-4)
     for k in heads:
         assert torch.isfinite(hg[k].grad).all()
+
+
+@pytest.mark.parametrize("R,S", [(64, 128), (33, 200), (7, 31)])
+def test_packed_rows_staged_through_shared_memory_equal_strided_access(R, S):
+    """Packed [R*S,10] head rows: the backward always stages a warp's 32 rows through shared memory (coalesced 8-byte copies),
+    the forward can (snrf_composite_set_fwd_packed); same values as the four separate tensors through the strided kernels."""
+    import ctypes
+    load_pkg()
+    import scanerf_b200_capi as capi
+    from hashgrid import _render
+    heads, z, dists, d = _inputs(R, S, 7 * R + S, big_sigma=True)
+    dev = "cuda:0"
+    packed = torch.cat([heads["sigma"], heads["tint"], heads["diffuse"], heads["specular"]], -1).reshape(R * S, 10)
+    hs = {k: v.to(dev).requires_grad_(True) for k, v in heads.items()}
+    ref = _render.composite(hs, z.to(dev), dists.to(dev), d.to(dev), True, train=True)
+    (ref["rgb"].sum() + 0.3 * ref["depth"].sum() + ref["T_left"].sum() + ref["l2_reg_specular"]).backward()
+    want_g = torch.cat([hs["sigma"].grad, hs["tint"].grad, hs["diffuse"].grad, hs["specular"].grad], -1).reshape(R * S, 10)
+    for fwd_packed in (0, 1):
+        capi.lib().snrf_composite_set_fwd_packed(ctypes.c_int(fwd_packed))
+        try:
+            hp = packed.to(dev).requires_grad_(True)
+            out = _render.composite_packed(hp, z.to(dev), dists.to(dev), d.to(dev), True, train=True)
+            (out["rgb"].sum() + 0.3 * out["depth"].sum() + out["T_left"].sum() + out["l2_reg_specular"]).backward()
+        finally:
+            capi.lib().snrf_composite_set_fwd_packed(ctypes.c_int(0))
+        for k in ("rgb", "depth", "T_left", "diffuse", "specular", "tint", "weights"):
+            assert torch.equal(out[k], ref[k]), (fwd_packed, k)
+        assert torch.equal(hp.grad, want_g), fwd_packed
