@@ -23,14 +23,16 @@ def main():
     pkg = importlib.import_module(bench.PKG)
     pkg.install()
     import scanerf_b200_capi as capi
-    cfg = bench.WORKLOADS["default.yaml-single-tile"]
+    cfg = dict(bench.WORKLOADS["default.yaml-single-tile"])
+    if os.environ.get("SNRF_SWEEP_LOG2T"):            # the same workload on a smaller table (e.g. 22: the city tiles)
+        cfg["log2T"] = int(os.environ["SNRF_SWEEP_LOG2T"])
     dev = torch.device("cuda:0")
     step, gen = bench.build_tile(cfg, dev, 0)
     batches = [(l.to(dev), g.to(dev)) for l, g in bench.make_batches(cfg, 14, gen)]
     rows = []
     lib = capi.lib()
     # (L2 policy mode, pin MiB, x-pair load mode, first level of the pair loads), interleaved with the default
-    variants = [(-1, 0, 0, 0), (0, 0, 0, 0), (1, 0, 0, 0), (0, 0, 0, 0), (1, 0, 0, 0), (1, 0, 2, 9), (1, 0, 1, 9)]
+    variants = [(-1, 0, 0, 0), (0, 0, 0, 0), (1, 0, 0, 0), (0, 0, 2, 0), (0, 0, 2, 6), (0, 0, 2, 9), (0, 0, 1, 6), (0, 0, 0, 0), (0, 0, 2, 6)]
     for mode, pin, pair, first in variants:
         if mode >= 0:          # (-1: the library's defaults, untouched)
             lib.snrf_field_set_fwd_l2_policy(ctypes.c_int(mode), ctypes.c_int(pin))
