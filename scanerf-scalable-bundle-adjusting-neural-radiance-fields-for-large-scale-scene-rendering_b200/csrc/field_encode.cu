@@ -502,6 +502,17 @@ field_bwd_runs_kernel(const float* __restrict__ rays_o, const float* __restrict_
 // it carry an evict_last cache policy, the streams that pass by once (gradients, p / m / v) an evict-first one, so that the
 // 64 MiB slice being reduced into is what the L2 keeps (without hints a fine-level slice wrote 95 MB to and re-read 68 MB
 // from DRAM per scatter, and the Adam pass fetched its 67 MB again: profiles/r2d_fused_bwd_full.md).
+// Programmatic dependent launch (snrf_field_set_pdl): the scatter / Adam slices of the fused backward are 56 short dependent
+// launches; launched with the programmatic-stream-serialization attribute a kernel's CTAs are scheduled while the previous
+// kernel drains its last wave and wait here until it has completed and flushed.  A no-op for a plain launch.
+// (launch_dependents right behind the wait: once every CTA of this grid has STARTED, the next grid's CTAs may take the slots
+// its last wave frees -- they then sit in their own wait until this grid has completed.)
+__device__ __forceinline__ void grid_dependency_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ uint64_t l2_policy_evict_last()
 {
     uint64_t p;
@@ -621,6 +632,7 @@ field_scatter_slice_kernel(const float* __restrict__ cpts, const int* __restrict
     constexpr bool hint = HINT;
     const uint64_t pol = l2_policy_evict_last();
     const uint32_t slice_mask = (1u << range_shift) - 1u;
+    grid_dependency_wait();             // (programmatic dependent launch: everything above overlapped the previous kernel's tail)
     const int lane = threadIdx.x & 31;
     const int l = l0 + blockIdx.y;
     float2* gl = scratch + ((size_t)blockIdx.y << range_shift);
@@ -711,6 +723,7 @@ adam_slice_kernel(float4* __restrict__ p4, float4* __restrict__ m4, float4* __re
         s_bc[0] = 1.0f - powf(h.b1, (float)h.step);
         s_bc[1] = 1.0f - powf(h.b2, (float)h.step);
     }
+    grid_dependency_wait();             // (programmatic dependent launch: the scatter of this slice has to be complete from here on)
     __syncthreads();
     const float bc1 = s_bc[0], bc2 = s_bc[1];
     constexpr int kUnroll = 2;
@@ -744,6 +757,23 @@ adam_slice_kernel(float4* __restrict__ p4, float4* __restrict__ m4, float4* __re
             st4_hint(g4 + i, make_float4(0.f, 0.f, 0.f, 0.f), pol, hint);
         }
     }
+}
+
+int g_pdl = 1;                 // snrf_field_set_pdl: scatter / Adam slices of the fused backward as programmatic dependent launches
+template <typename... KArgs, typename... Args>
+inline void launch_dep(void (*kernel)(KArgs...), dim3 grid, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 inline int grid_x(int N)
@@ -817,6 +847,8 @@ SNRF_API void snrf_field_set_profile(int on) { g_profile = on ? 1 : 0; }
 SNRF_API void snrf_field_last_profile(float* out4) { for (int i = 0; i < 4; ++i) out4[i] = g_profile_ms[i]; }
 SNRF_API void snrf_field_set_overlap(int on) { g_overlap = on ? 1 : 0; }
 SNRF_API void snrf_field_set_l2_hints(int on) { g_l2_hints = on ? 1 : 0; }
+// tuning hook: 1 (default) = the scatter / Adam slices of snrf_field_encode_bwd_adam are programmatic dependent launches
+SNRF_API void snrf_field_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 SNRF_API void snrf_field_set_coarse_concurrent(int on) { g_coarse_concurrent = on ? 1 : 0; }
 SNRF_API void snrf_field_set_slice_log2(int bits) { g_slice_cap = 1ll << (bits < 2 ? 2 : (bits > 30 ? 30 : bits)); }
 SNRF_API void snrf_field_set_levels_per_group(int n) { g_levels_per_group = n > 0 ? n : 0; }
@@ -1049,8 +1081,8 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
         const long long n4 = (long long)nl * entries / 2;                                // float4 groups (two entries each)
         long long gx = (n4 + kThreads * 2 - 1) / (kThreads * 2);
         if (gx > (long long)sms * 16) gx = (long long)sms * 16;
-        if (g_l2_hints) adam_slice_kernel<true><<<(int)gx, kThreads, 0, st>>>((float4*)(table + base), (float4*)(exp_avg + base), (float4*)(exp_avg_sq + base), (float4*)buf, n4, h);
-        else adam_slice_kernel<false><<<(int)gx, kThreads, 0, st>>>((float4*)(table + base), (float4*)(exp_avg + base), (float4*)(exp_avg_sq + base), (float4*)buf, n4, h);
+        if (g_l2_hints) launch_dep(adam_slice_kernel<true>, dim3((unsigned)gx), st, (float4*)(table + base), (float4*)(exp_avg + base), (float4*)(exp_avg_sq + base), (float4*)buf, n4, h);
+        else launch_dep(adam_slice_kernel<false>, dim3((unsigned)gx), st, (float4*)(table + base), (float4*)(exp_avg + base), (float4*)(exp_avg_sq + base), (float4*)buf, n4, h);
     };
 
     mark(-1);
@@ -1070,8 +1102,8 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
             sc = side->stream;
         }
         for (int l = 0; l < small_levels; ++l) {
-            if (g_l2_hints) field_scatter_slice_kernel<true><<<dim3(grid_x(N), 1), kThreads, 0, sc>>>(cpts_scratch, res, g, (float2*)coarse_buf, N, l, (uint32_t)T, 0u, log2T, agg);
-            else field_scatter_slice_kernel<false><<<dim3(grid_x(N), 1), kThreads, 0, sc>>>(cpts_scratch, res, g, (float2*)coarse_buf, N, l, (uint32_t)T, 0u, log2T, agg);
+            if (g_l2_hints) launch_dep(field_scatter_slice_kernel<true>, dim3(grid_x(N), 1), sc, (const float*)cpts_scratch, res, g, (float2*)coarse_buf, N, l, (uint32_t)T, 0u, log2T, agg);
+            else launch_dep(field_scatter_slice_kernel<false>, dim3(grid_x(N), 1), sc, (const float*)cpts_scratch, res, g, (float2*)coarse_buf, N, l, (uint32_t)T, 0u, log2T, agg);
             if (!coarse_on_side) mark(1);
             adam_launch(sc, coarse_buf, l, 1, 0, T);
             if (!coarse_on_side) mark(2);
@@ -1088,8 +1120,8 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
             const int b = overlap ? (k & 1) : 0;
             float* buf = fine_buf + (size_t)b * capacity * 2;
             if (overlap && k >= 2) cudaStreamWaitEvent(s, side->adam[b], 0);         // the half is free again
-            if (g_l2_hints) field_scatter_slice_kernel<true><<<dim3(grid_x(N), nl), kThreads, 0, s>>>(cpts_scratch, res, g, (float2*)buf, N, l0, (uint32_t)T, (uint32_t)pass, range_shift, agg);
-            else field_scatter_slice_kernel<false><<<dim3(grid_x(N), nl), kThreads, 0, s>>>(cpts_scratch, res, g, (float2*)buf, N, l0, (uint32_t)T, (uint32_t)pass, range_shift, agg);
+            if (g_l2_hints) launch_dep(field_scatter_slice_kernel<true>, dim3(grid_x(N), nl), s, (const float*)cpts_scratch, res, g, (float2*)buf, N, l0, (uint32_t)T, (uint32_t)pass, range_shift, agg);
+            else launch_dep(field_scatter_slice_kernel<false>, dim3(grid_x(N), nl), s, (const float*)cpts_scratch, res, g, (float2*)buf, N, l0, (uint32_t)T, (uint32_t)pass, range_shift, agg);
             mark(1);
             cudaStream_t sa = s;
             if (overlap) {

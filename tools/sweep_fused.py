@@ -29,17 +29,18 @@ def main():
     step, gen = bench.build_tile(cfg, dev, 0)
     batches = [(l.to(dev), g.to(dev)) for l, g in bench.make_batches(cfg, 14, gen)]
     rows = []
-    # (fused, scatter/Adam overlap, log2 of the slice, coarse levels on the side stream, L2 evict_last hints on the scratch)
-    for fused, overlap, log2, coarse, hints in ((0, 0, 23, 0, 0), (1, 0, 23, 0, 0), (1, 0, 23, 0, 1), (1, 0, 23, 1, 0), (1, 0, 23, 1, 1),
-                                               (1, 0, 22, 1, 1), (1, 1, 24, 0, 1)):
+    # (fused, scatter/Adam overlap, log2 of the slice, coarse levels on the side stream, L2 evict_last hints on the scratch, PDL)
+    for fused, overlap, log2, coarse, hints, pdl in ((1, 0, 23, 1, 1, 1), (1, 0, 23, 1, 1, 0), (1, 0, 23, 0, 1, 1), (1, 0, 23, 0, 1, 0),
+                                                    (1, 0, 23, 1, 1, 1), (1, 0, 23, 1, 1, 0), (0, 0, 23, 0, 0, 0)):
         step.fused_table_update = bool(fused)
+        capi.lib().snrf_field_set_pdl(ctypes.c_int(pdl))
         step.featureGrid_optimizer.scratch_log2 = log2
         capi.lib().snrf_field_set_slice_log2(ctypes.c_int(log2 - overlap))
         capi.lib().snrf_field_set_overlap(ctypes.c_int(overlap))
         capi.lib().snrf_field_set_coarse_concurrent(ctypes.c_int(coarse))
         capi.lib().snrf_field_set_l2_hints(ctypes.c_int(hints))
         ms, _ = bench._time_steps(step, batches, 4)
-        row = {"fused": fused, "overlap": overlap, "slice_log2": log2 - overlap, "coarse_side_stream": coarse, "l2_hints": hints, "ms_per_step": ms}
+        row = {"fused": fused, "overlap": overlap, "slice_log2": log2 - overlap, "coarse_side_stream": coarse, "l2_hints": hints, "pdl": pdl, "ms_per_step": ms}
         if fused:
             capi.lib().snrf_field_set_profile(ctypes.c_int(1))
             acc = [0.0] * 4
@@ -56,6 +57,7 @@ def main():
     capi.lib().snrf_field_set_slice_log2(ctypes.c_int(23))
     capi.lib().snrf_field_set_coarse_concurrent(ctypes.c_int(1))
     capi.lib().snrf_field_set_l2_hints(ctypes.c_int(1))
+    capi.lib().snrf_field_set_pdl(ctypes.c_int(1))
     with open(args.out, "w") as fh:
         fh.write(json.dumps(rows) + "\n")
 
