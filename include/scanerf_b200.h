@@ -373,6 +373,9 @@ void snrf_infer_set_precision(int split);
 void snrf_infer_set_inflight(int tiles);
 /* tuning hook: tiles in flight per CTA of the single-tile decode pass (4 = default, 2 = the round-1 kernel) */
 void snrf_infer_set_decode_inflight(int n);
+/* tuning hook: log2 of the samples per chunk of the single-tile two-pass evaluation behind pts_inference / bg_pts_inference*
+ * (20 .. 26): a chunk streams the table from HBM once, its scratch is 153 B per sample */
+void snrf_infer_set_chunk_log2(int bits);
 /* tuning hook: 1 (default) = the four-tile decode pass composes decoder layer 2 into its consumers (as snrf_decoder_set_fwd_fold) */
 void snrf_infer_set_fold(int on);
 /* tuning hook: 1 (default) = multi-pass paths (single-tile two-pass, multi-tile grouped), 0 = the fused kernel,

@@ -780,6 +780,7 @@ work_combine_kernel(InferArgs a, long long n0, int Nc, Work w)
     }
 }
 
+int g_chunk_log2 = 24;       // single-tile two-pass path: log2 of the samples per chunk (snrf_infer_set_chunk_log2; 22: 221 ms, 24: 218 ms per 1080p frame)
 int g_infer_fold = 1;        // the four-tile decode pass folds layer 2 into its consumers (decoder_core.cuh: forward_layers4<., FOLD>)
 int g_decode_inflight = 4;   // tiles in flight per CTA of the single-tile decode pass (4: infer_decode4_kernel, 2: infer_decode_kernel)
 int g_infer_split = 1;
@@ -836,7 +837,10 @@ int launch_two_pass(const InferArgs& a, void* stream, const char* name)
     }
     cudaStream_t s = (cudaStream_t)stream;
     const long long total = (long long)a.B * a.S;
-    const long long chunk = 4ll << 20;                          // 4 Mi samples: 512 MiB of features
+    // samples per chunk: every chunk streams the whole table from HBM once (level slice by level slice through L2), so the table
+    // traffic of a frame is (samples / chunk) GiB -- 128 GiB per 1080p frame at 4 Mi samples, ~10 % of its time; the scratch is
+    // 153 B per sample of a chunk (snrf_infer_set_chunk_log2)
+    const long long chunk = 1ll << g_chunk_log2;
     const long long cap = total < chunk ? total : chunk;
     void* scratch = nullptr;
     const size_t bytes = (size_t)cap * (16 * 8 + 16 + 8 + 1) + 256;
@@ -947,6 +951,8 @@ int launch(const InferArgs& a, int nb, void* stream, const char* name)
 // ------------------------------- C ABI --------------------------------------
 // tiles in flight per CTA of the single-tile decode pass: 4 (default) or 2 (round-1 kernel)
 SNRF_API void snrf_infer_set_decode_inflight(int n) { g_decode_inflight = n == 2 ? 2 : 4; }
+// tuning hook: log2 of the samples per chunk of the single-tile two-pass path (20 .. 26; scratch = 153 B per sample of a chunk)
+SNRF_API void snrf_infer_set_chunk_log2(int bits) { g_chunk_log2 = bits < 20 ? 20 : (bits > 26 ? 26 : bits); }
 // tuning hook: 1 (default) = the four-tile decode pass composes layer 2 into its consumers (four dependent stages per tile)
 SNRF_API void snrf_infer_set_fold(int on) { g_infer_fold = on ? 1 : 0; }
 SNRF_API void snrf_infer_set_precision(int split) { g_infer_split = split ? 1 : 0; }
