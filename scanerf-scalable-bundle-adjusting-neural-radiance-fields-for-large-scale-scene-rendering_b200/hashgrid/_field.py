@@ -104,6 +104,7 @@ def decoder_apply(feats, rays_d, mask32, S, params, valid=None, ert=None):
 
 
 _small_levels_cache = {}
+SMALL_LEVEL_LOG2 = 22          # levels with at most this many grid vertices are reduced in one pass (tools/sweep_small_levels.py)
 
 
 def small_levels(resolution):
@@ -116,7 +117,7 @@ def small_levels(resolution):
         r = resolution.detach().cpu().long() + 1
         verts = r[:, 0] * r[:, 1] * r[:, 2]
         n = 0
-        while n < verts.shape[0] and int(verts[n]) <= (1 << 22):
+        while n < verts.shape[0] and int(verts[n]) <= (1 << SMALL_LEVEL_LOG2):
             n += 1
         _small_levels_cache[key] = n
     return n
