@@ -135,7 +135,7 @@ __device__ __forceinline__ float4 ld_pair16(const float2* a, uint64_t pol, bool 
 }
 
 template <int MODE, bool JAC, bool POLICY, int PAIR>
-__global__ void __launch_bounds__(kThreads, (PAIR == 0 ? 5 : 4))
+__global__ void __launch_bounds__(kThreads, (PAIR == 0 ? 5 : 4))      // 5 CTAs per SM: 4 (58 registers) 1.74 ms, 5 (46) 1.68 ms, 6 (40) 1.78 ms at C2
 field_fwd_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_vals,
                  const float* __restrict__ points, const float* __restrict__ bmin_p, const float* __restrict__ bsize_p,
                  const float2* __restrict__ table, const int* __restrict__ res, float2* __restrict__ out, float2* __restrict__ jac,
