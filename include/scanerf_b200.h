@@ -117,6 +117,8 @@ void snrf_field_set_fwd_l2_policy(int mode, int pin_mib);
  * 16-byte load for an x-pair in an aligned 16-byte slot; 2 = one 32-byte sector load per x-pair, the second corner fetched by
  * itself when it lies in another sector.  Results are bit-identical in every mode */
 void snrf_field_set_fwd_pair_loads(int mode, int first_level);
+/* measurement hook: unused dynamic shared memory (<= 48 KB) per CTA of the scatter / Adam slices = a cap on their resident CTAs */
+void snrf_field_set_occupancy_smem(int bytes);
 /* tuning hook: 1 (default) = the scatter / Adam slices of snrf_field_encode_bwd_adam are launched with the programmatic-stream-
  * serialization attribute (a slice's CTAs are scheduled while the previous slice drains and wait in `griddepcontrol.wait`) */
 void snrf_field_set_pdl(int on);

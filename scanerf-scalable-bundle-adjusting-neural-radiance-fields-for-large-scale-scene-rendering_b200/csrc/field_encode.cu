@@ -759,6 +759,7 @@ adam_slice_kernel(float4* __restrict__ p4, float4* __restrict__ m4, float4* __re
     }
 }
 
+int g_occ_smem = 0;            // snrf_field_set_occupancy_smem: dynamic shared memory (unused) per CTA of the scatter / Adam slices
 int g_pdl = 1;                 // snrf_field_set_pdl: scatter / Adam slices of the fused backward as programmatic dependent launches
 template <typename... KArgs, typename... Args>
 inline void launch_dep(void (*kernel)(KArgs...), dim3 grid, cudaStream_t s, Args... args)
@@ -766,7 +767,7 @@ inline void launch_dep(void (*kernel)(KArgs...), dim3 grid, cudaStream_t s, Args
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = (size_t)g_occ_smem;      // (> 0 only in occupancy experiments: caps the resident CTAs per SM)
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -847,6 +848,8 @@ SNRF_API void snrf_field_set_profile(int on) { g_profile = on ? 1 : 0; }
 SNRF_API void snrf_field_last_profile(float* out4) { for (int i = 0; i < 4; ++i) out4[i] = g_profile_ms[i]; }
 SNRF_API void snrf_field_set_overlap(int on) { g_overlap = on ? 1 : 0; }
 SNRF_API void snrf_field_set_l2_hints(int on) { g_l2_hints = on ? 1 : 0; }
+// measurement hook: unused dynamic shared memory per CTA of the scatter / Adam slices, i.e. a cap on their resident CTAs per SM
+SNRF_API void snrf_field_set_occupancy_smem(int bytes) { g_occ_smem = bytes > 0 ? (bytes > 48 * 1024 ? 48 * 1024 : bytes) : 0; }
 // tuning hook: 1 (default) = the scatter / Adam slices of snrf_field_encode_bwd_adam are programmatic dependent launches
 SNRF_API void snrf_field_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 SNRF_API void snrf_field_set_coarse_concurrent(int on) { g_coarse_concurrent = on ? 1 : 0; }

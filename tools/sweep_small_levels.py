@@ -29,19 +29,22 @@ def main():
     step, gen = bench.build_tile(cfg, dev, 0)
     batches = [(l.to(dev), g.to(dev)) for l, g in bench.make_batches(cfg, 14, gen)]
     rows = []
-    for k in (22, 23, 25, 20, 22, 23, 25):
+    import ctypes
+    for k, occ in ((22, 0), (22, 38 * 1024), (22, 46 * 1024), (22, 0), (22, 30 * 1024), (22, 46 * 1024), (22, 38 * 1024)):
         _field.SMALL_LEVEL_LOG2 = k
         _field._small_levels_cache.clear()
+        capi.lib().snrf_field_set_occupancy_smem(ctypes.c_int(occ))
         ms, _ = bench._time_steps(step, batches, 4)
         capi.time_calls(("snrf_field_encode_bwd_adam",))
         for b in batches[:8]:
             step.step_device(*b)
         t = capi.timed_by_name().get("snrf_field_encode_bwd_adam", [])
         capi.time_calls(None)
-        row = {"small_level_log2": k, "small_levels": _field.small_levels(step.featureGrid.HE.resolution), "ms_per_step": ms,
+        row = {"occupancy_smem": occ, "small_level_log2": k, "small_levels": _field.small_levels(step.featureGrid.HE.resolution), "ms_per_step": ms,
                "bwd_adam_ms": sum(t) / max(len(t), 1)}
         rows.append(row)
         print(json.dumps(row), flush=True)
+    capi.lib().snrf_field_set_occupancy_smem(ctypes.c_int(0))
     with open(args.out, "w") as fh:
         fh.write(json.dumps(rows) + "\n")
 
