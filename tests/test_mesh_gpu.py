@@ -92,6 +92,18 @@ def test_first_hit_against_brute_force_properties():
         assert bool(hit[any_hit].all()), "a ray that intersects the mesh must report a hit"
         tmin = torch.where(ok, t, torch.full_like(t, 1e30)).min(-1)[0]
         assert bool((z[any_hit].double() >= tmin[any_hit] - 1e-3).all()), "no hit in front of the nearest intersection"
+        # The reference's answer is the nearest hit of the FIRST CELL THAT HAS ANY HIT (fastMesh_kernel.cu:230-329): a face is listed
+        # in every cell its bounding box overlaps, so that cell may hold a face the ray meets further out than a face listed only
+        # in later cells.  How often that differs from the globally nearest intersection (what a BVH traversal would return) is
+        # the measured reason why the reference's cell walk, not a BVH, defines the bit-exact answers.
+        farther = (z[any_hit].double() > tmin[any_hit] + 1e-3)
+        frac = float(farther.float().mean())
+        print(f"first-cell answer differs from the globally nearest intersection on {int(farther.sum())} of {int(any_hit.sum())} rays ({100 * frac:.2f} %)")
+        out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        if os.path.isdir(out_dir):
+            import json
+            with open(os.path.join(out_dir, "mesh_first_cell_vs_nearest.json"), "w") as fh:
+                json.dump({"rays_with_an_intersection": int(any_hit.sum()), "first_cell_answer_not_the_nearest": int(farther.sum()), "fraction": frac}, fh)
 
 
 @pytest.mark.parametrize("B", [1, 1000, 50000])
