@@ -755,18 +755,35 @@ decoder_bwd_fold_kernel(const float* __restrict__ feats, const float* __restrict
     for (int i = tid; i < weights_end / 16; i += kThreadsDec) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     float* s32 = reinterpret_cast<float*>(base);                       // W32 [64][64]
     float* sh2 = s32 + 64 * 64;                                        // Wh2 [7][64]
+    // fp32 copies of the factors, row pitch 65 / 33 (conflict-free whichever index the lanes run over): W2 [64][64], W3a =
+    // W3[:, 0:32] [64][32], Wh [7][32], b2 [64] -- the composition below and the flush at the end read them from shared memory
+    // (from global memory the 64-term sums cost ~75 us per launch in dependent, strided L1 / L2 loads)
+    float* sW2 = sh2 + 8 * 64;
+    float* sW3a = sW2 + 64 * 65;
+    float* sWh = sW3a + 64 * 33;
+    float* sb2 = sWh + 8 * 33;
+    auto load_factors = [&]() {
+        for (int i = tid; i < 64 * 64; i += kThreadsDec) sW2[(i >> 6) * 65 + (i & 63)] = w_at(p.W2, i >> 6, i & 63, 64, 64, p.flat);
+        for (int i = tid; i < 64 * 32; i += kThreadsDec) sW3a[(i >> 5) * 33 + (i & 31)] = w_at(p.W3, i >> 5, i & 31, 64, 48, p.flat);
+        for (int i = tid; i < 7 * 32; i += kThreadsDec) sWh[(i >> 5) * 33 + (i & 31)] = wh_at(p, i >> 5, i & 31);
+        for (int i = tid; i < 64; i += kThreadsDec) sb2[i] = p.b2[i];
+    };
     float* bias = reinterpret_cast<float*>(smem + off_bias);
     float* maskv = reinterpret_cast<float*>(smem + off_mask);
+    load_factors();
+    __syncthreads();
     for (int i = tid; i < 64 * 64; i += kThreadsDec) {
         const int o = i >> 6, j = i & 63;
         float acc = 0.0f;
-        for (int k = 0; k < 32; ++k) acc += w_at(p.W3, o, k, 64, 48, p.flat) * w_at(p.W2, 32 + k, j, 64, 64, p.flat);
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) acc += sW3a[o * 33 + k] * sW2[(32 + k) * 65 + j];
         s32[i] = acc;
     }
     for (int i = tid; i < 7 * 64; i += kThreadsDec) {
         const int h = i >> 6, j = i & 63;
         float acc = 0.0f;
-        for (int k = 0; k < 32; ++k) acc += wh_at(p, h, k) * w_at(p.W2, k, j, 64, 64, p.flat);
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) acc += sWh[h * 33 + k] * sW2[k * 65 + j];
         sh2[i] = acc;
     }
     for (int i = tid; i < nB; i += kThreadsDec) {
@@ -775,7 +792,7 @@ decoder_bwd_fold_kernel(const float* __restrict__ feats, const float* __restrict
         else if (i < 128) {
             const int o = i - 64;
             v = p.b3[o];
-            for (int k = 0; k < 32; ++k) v += w_at(p.W3, o, k, 64, 48, p.flat) * p.b2[32 + k];
+            for (int k = 0; k < 32; ++k) v += sW3a[o * 33 + k] * sb2[32 + k];
         } else v = p.b4[i - 128];
         bias[i] = v;
     }
@@ -1150,6 +1167,12 @@ decoder_bwd_fold_kernel(const float* __restrict__ feats, const float* __restrict
     float* sGh = sG + 64 * 64;                             // Gh [8][64] (7 used)
     float* sdb3 = sGh + 8 * 64;                            // [64]
     float* sdbh = sdb3 + 64;                               // [8]  (7 used)
+    // the factors again (their copies of the prologue were overwritten by the operand tiles), behind the four arrays above
+    sW2 = sdbh + 8;
+    sW3a = sW2 + 64 * 65;
+    sWh = sW3a + 64 * 33;
+    sb2 = sWh + 8 * 33;
+    load_factors();
     if (tid < 8) sdbh[tid] = 0.0f;
     __syncthreads();
     if (!first) {
@@ -1216,32 +1239,36 @@ decoder_bwd_fold_kernel(const float* __restrict__ feats, const float* __restrict
         // dW3a [o][k] = sum_j G[o][j] W2[32 + k][j] + db3[o] b2[32 + k]
         for (int i = tid; i < 64 * 32; i += kThreadsDec) {
             const int o = i >> 5, k = i & 31;
-            float acc = sdb3[o] * p.b2[32 + k];
-            for (int j = 0; j < 64; ++j) acc += sG[o * 64 + j] * w_at(p.W2, 32 + k, j, 64, 64, p.flat);
+            float acc = sdb3[o] * sb2[32 + k];
+#pragma unroll 8
+            for (int j = 0; j < 64; ++j) acc += sG[o * 64 + j] * sW2[(32 + k) * 65 + j];
             atomicAdd(gp.W3 + o * 48 + k, acc);
         }
         // dW2 [32 + k][j] = sum_o W3[o][k] G[o][j] ;  dW2 [k][j] = sum_h Wh[h][k] Gh[h][j]
         for (int i = tid; i < 32 * 64; i += kThreadsDec) {
             const int k = i >> 6, j = i & 63;
             float acc = 0.0f, acch = 0.0f;
-            for (int o = 0; o < 64; ++o) acc += w_at(p.W3, o, k, 64, 48, p.flat) * sG[o * 64 + j];
-            for (int h = 0; h < 7; ++h) acch += wh_at(p, h, k) * sGh[h * 64 + j];
+#pragma unroll 8
+            for (int o = 0; o < 64; ++o) acc += sW3a[o * 33 + k] * sG[o * 64 + j];
+#pragma unroll
+            for (int h = 0; h < 7; ++h) acch += sWh[h * 33 + k] * sGh[h * 64 + j];
             atomicAdd(gp.W2 + (32 + k) * 64 + j, acc);
             atomicAdd(gp.W2 + k * 64 + j, acch);
         }
         // dWh [h][k] = sum_j Gh[h][j] W2[k][j] + dbh[h] b2[k]
         for (int i = tid; i < 7 * 32; i += kThreadsDec) {
             const int h = i >> 5, k = i & 31;
-            float acc = sdbh[h] * p.b2[k];
-            for (int j = 0; j < 64; ++j) acc += sGh[h * 64 + j] * w_at(p.W2, k, j, 64, 64, p.flat);
+            float acc = sdbh[h] * sb2[k];
+#pragma unroll 8
+            for (int j = 0; j < 64; ++j) acc += sGh[h * 64 + j] * sW2[k * 65 + j];
             float* dst = h == 0 ? gp.Ws + k : (h < 4 ? gp.Wd + (h - 1) * 32 + k : gp.Wt + (h - 4) * 32 + k);
             atomicAdd(dst, acc);
         }
         // db2 [32 + k] = sum_o W3[o][k] db3[o] ;  db2 [k] = sum_h Wh[h][k] dbh[h]
         for (int k = tid; k < 32; k += kThreadsDec) {
             float acc = 0.0f, acch = 0.0f;
-            for (int o = 0; o < 64; ++o) acc += w_at(p.W3, o, k, 64, 48, p.flat) * sdb3[o];
-            for (int h = 0; h < 7; ++h) acch += wh_at(p, h, k) * sdbh[h];
+            for (int o = 0; o < 64; ++o) acc += sW3a[o * 33 + k] * sdb3[o];
+            for (int h = 0; h < 7; ++h) acch += sWh[h * 33 + k] * sdbh[h];
             atomicAdd(gp.b2 + 32 + k, acc);
             atomicAdd(gp.b2 + k, acch);
         }

@@ -569,7 +569,7 @@ __device__ __forceinline__ float wh_at(const DecoderParams& p, int h, int k)
 }
 
 // Composed weights of the FOLD forward, written over what stage_all_weights left (call after it; ends with the data in place
-// but NOT synchronised: the caller's fence + __syncthreads() follows).  `scratch`: >= 18 KB of shared memory not in use yet
+// but NOT synchronised: the caller's fence + __syncthreads() follows).  `scratch`: >= 48 KB of shared memory not in use yet
 // (the operand-tile area).  W32 = W3[:, 0:32] W2[32:64, :] -> the W2 tiles; Wh2 = Wh W2[0:32, :] -> the Wh tile (hi) and
 // rows 0..15 of the W3-lo tile (lo); b32 = W3[:, 0:32] b2[32:64] + b3 -> the b3 slot; bh2 = Wh b2[0:32] + bh -> the head slot.
 template <bool SPLIT>
@@ -577,29 +577,40 @@ __device__ void stage_fold_weights4(unsigned char* smem, const DecoderParams& p,
 {
     float* s32 = scratch;                 // [64][64]
     float* sh2 = scratch + 64 * 64;       // [7][64]
+    // fp32 copies of the factors (row pitch 65 / 33: conflict-free): the 32-term sums below read shared memory, not L1 / L2
+    float* sW2 = sh2 + 8 * 64;            // W2 [64][64]
+    float* sW3a = sW2 + 64 * 65;          // W3[:, 0:32] [64][32]
+    float* sWh = sW3a + 64 * 33;          // Wh [7][32]
+    float* sb2 = sWh + 8 * 33;            // b2 [64]
+    for (int i = tid; i < 64 * 64; i += nthreads) sW2[(i >> 6) * 65 + (i & 63)] = w_at(p.W2, i >> 6, i & 63, 64, 64, p.flat);
+    for (int i = tid; i < 64 * 32; i += nthreads) sW3a[(i >> 5) * 33 + (i & 31)] = w_at(p.W3, i >> 5, i & 31, 64, 48, p.flat);
+    for (int i = tid; i < 7 * 32; i += nthreads) sWh[(i >> 5) * 33 + (i & 31)] = wh_at(p, i >> 5, i & 31);
+    for (int i = tid; i < 64; i += nthreads) sb2[i] = p.b2[i];
+    __syncthreads();                      // (also: stage_all_weights' stores to the tiles overwritten below are complete)
     for (int i = tid; i < 64 * 64; i += nthreads) {
         const int o = i >> 6, j = i & 63;
         float acc = 0.0f;
-        for (int k = 0; k < 32; ++k) acc += w_at(p.W3, o, k, 64, 48, p.flat) * w_at(p.W2, 32 + k, j, 64, 64, p.flat);
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) acc += sW3a[o * 33 + k] * sW2[(32 + k) * 65 + j];
         s32[i] = acc;
     }
     for (int i = tid; i < 7 * 64; i += nthreads) {
         const int h = i >> 6, j = i & 63;
         float acc = 0.0f;
-        for (int k = 0; k < 32; ++k) acc += wh_at(p, h, k) * w_at(p.W2, k, j, 64, 64, p.flat);
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) acc += sWh[h * 33 + k] * sW2[k * 65 + j];
         sh2[i] = acc;
     }
-    __syncthreads();                      // (also: stage_all_weights' stores to the tiles overwritten below are complete)
     float* b = reinterpret_cast<float*>(smem + off_bias<SPLIT>());
     for (int i = tid; i < 64 + 7; i += nthreads) {
         if (i < 64) {
             float v = p.b3[i];
-            for (int k = 0; k < 32; ++k) v += w_at(p.W3, i, k, 64, 48, p.flat) * p.b2[32 + k];
+            for (int k = 0; k < 32; ++k) v += sW3a[i * 33 + k] * sb2[32 + k];
             b[oB3 + i] = v;
         } else {
             const int h = i - 64;
             float v = h == 0 ? p.bs[0] : (h < 4 ? p.bd[h - 1] : p.bt[h - 4]);
-            for (int k = 0; k < 32; ++k) v += wh_at(p, h, k) * p.b2[k];
+            for (int k = 0; k < 32; ++k) v += sWh[h * 33 + k] * sb2[k];
             b[oBh + h] = v;
         }
     }
