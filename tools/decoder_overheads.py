@@ -40,6 +40,9 @@ def main():
         cot = torch.randn(N, 10, device=dev)
 
         def run():
+            for q in params:                       # (as the training step: gradients start from None, autograd steals the kernel's buffers)
+                q.grad = None
+            feats.grad = None
             heads = _field.decoder_apply(feats, rays_d, mask, S, params)
             e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             torch.cuda._sleep(30_000_000)          # the device idles ~15 ms while the host queues the launches: GPU time, not launch latency
