@@ -148,8 +148,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
+    def wait_first(self, timeout=8.0):
+        """nvidia-smi needs a moment before its first line: the timed region (a fraction of a second) starts after it."""
+        t_end = time.time() + timeout
+        while self.proc is not None and not self.rows and time.time() < t_end:
+            time.sleep(0.05)
+
     def summary(self, t0, t1):
         if self.proc is not None:
+            time.sleep(0.15)                       # one more sampling interval, so that the end of the region is covered
             self.proc.terminate()
         sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -499,6 +506,8 @@ def main():
             st.step_device(l.to(dev), t.to(dev))
     torch.cuda.synchronize()
     clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.wait_first()
     # (1) device-resident inputs
     capi.launch_count = 0
     ms_dev, t0, t1, sync_ms, n_sync = timed(run_device, devb_all)
