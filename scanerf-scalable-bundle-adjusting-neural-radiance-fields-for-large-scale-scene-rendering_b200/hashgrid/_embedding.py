@@ -47,9 +47,10 @@ class _EncodeFn(torch.autograd.Function):
                 features.grad = torch.zeros_like(features)
             _ops._encode_bwd(points, grad_out.contiguous(), grad_points, features.grad, features, corner, size, resolution)
             return grad_points, None, None, None, None, None
-        grad_features = torch.zeros_like(features)
+        # dense grad_features as the reference returns it; the encodes of one backward pass share it (_gradmode)
+        grad_features, first = _gradmode.shared_table_grad(features)
         _ops._encode_bwd(points, grad_out.contiguous(), grad_points, grad_features, features, corner, size, resolution)
-        return grad_points, grad_features, None, None, None, None
+        return grad_points, (grad_features if first else None), None, None, None, None
 
 
 def resolution_ladder(base_resolution, finest_resolution, n_levels):

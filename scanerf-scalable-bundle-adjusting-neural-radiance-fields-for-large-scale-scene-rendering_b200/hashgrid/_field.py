@@ -190,12 +190,13 @@ class FieldEncodeFn(torch.autograd.Function):
             # the training step's explicit opt-in (_gradmode.table_backward): accumulate in place, no dense temporary
             if features.grad is None:
                 features.grad = torch.zeros_like(features)
-            g_table = features.grad
+            g_table, first = features.grad, False
         else:
-            g_table = torch.zeros_like(features)
+            # autograd-conformant default: a dense grad_features, shared by the encodes of one backward pass (_gradmode)
+            g_table, first = _gradmode.shared_table_grad(features)
         rc = getattr(capi.lib(), "snrf_field_encode_bwd" + sfx)(*common, ptr(g_table), *tail)
         capi.check(rc, "snrf_field_encode_bwd")
-        return g_o, g_d, None, (None if direct else g_table), None, None, None, None, None, None, None
+        return g_o, g_d, None, (g_table if first else None), None, None, None, None, None, None, None
 
 
 def field_encode(rays_o, rays_d, z_vals, features, resolution, box_min, box_size, mode, valid=None, split=0, ert=None):

@@ -241,9 +241,11 @@ def main():
     ap.add_argument("--render-tile", default="", help="do not train: render one frame of this exported tile directory through the "
                                                       "reference's rendering.py (RenderingHashGrid.render_rays_base, rendering.py:286-544)")
     ap.add_argument("--render-out", default="", help="npz of the rendered frame (with --render-tile)")
+    ap.add_argument("--profile", default="", help="after the timed steps: 3 more steps under torch.profiler, device time per kernel -> this json")
     ap.add_argument("--alloc", action="store_true", help="do not train: run the reference's preprocess/build_tiles.py on the scene")
     args = ap.parse_args()
     args.out = os.path.abspath(args.out)
+    args.profile = os.path.abspath(args.profile) if args.profile else ""
     args.init_in, args.init_out = (os.path.abspath(v) if v else "" for v in (args.init_in, args.init_out))
     args.export_tile, args.render_tile, args.render_out, args.prune_out = (os.path.abspath(v) if v else "" for v in (args.export_tile, args.render_tile, args.render_out, args.prune_out))
     setup_imports(args.arm)
@@ -323,6 +325,20 @@ def main():
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) / max(args.steps - 1, 1) * 1e3
     losses = [float(v) for v in t.crit.record_list]
+    prof_rows = None
+    if args.profile:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                t.train_one_step()
+            torch.cuda.synchronize()
+        rows = {}
+        for ev in prof.events():
+            if ev.device_type.name == "CUDA":
+                r = rows.setdefault(ev.name, [0, 0.0])
+                r[0] += 1
+                r[1] += ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
+        prof_rows = sorted(([k[:160], n / 3.0, us / 3.0e3] for k, (n, us) in rows.items()), key=lambda r: -r[2])
     out = {"arm": args.arm, "warp": bool(args.warp), "steps": args.steps, "losses": losses, "ms_per_step": ms,
            "global_step": int(t.global_step), "modules": where,
            "table_changed": bool((t.featureGrid.HE.features.detach().cpu() != (torch.load(args.init_in)["table"] if args.init_in else 0)).any()),
@@ -335,6 +351,10 @@ def main():
         out["exported"] = sorted(os.listdir(args.export_tile))
     with open(args.out, "w") as fh:
         json.dump(out, fh)
+    if prof_rows is not None:
+        with open(args.profile, "w") as fh:
+            json.dump({"arm": args.arm, "ms_per_step": ms, "device_ms_per_step": sum(r[2] for r in prof_rows),
+                       "kernels": [{"name": r[0], "launches_per_step": r[1], "ms_per_step": r[2]} for r in prof_rows]}, fh, indent=1)
     print(json.dumps({k: out[k] for k in ("arm", "ms_per_step", "modules")}), flush=True)
     print("losses:", " ".join(f"{v:.6f}" for v in losses), flush=True)
 

@@ -244,6 +244,36 @@ def test_encode_backward_has_no_side_effect_outside_the_training_context():
     assert float(t.grad.abs().max()) == 0.0, "zero_grad must not trust the clean flag after a foreign backward"
 
 
+def test_encodes_of_one_backward_pass_share_the_dense_gradient_table():
+    """The reference's drivers encode the table twice per step (foreground + background chain, tile.py:661-681).  Outside any
+    training context the encode Functions return a dense grad_features like the reference's (PyHashGridBG.py:20-30), but the
+    encodes of ONE backward pass scatter into one shared tensor (_gradmode.shared_table_grad): same `.grad` as two
+    independent tensors summed by autograd, for the fused Functions and for the reference-shaped PyHashGridBG Function."""
+    load_pkg()
+    from hashgrid import _embedding, _field, _gradmode
+    table, res, bmin, bsize, o, d, z_fg, z_bg, g = _case(16, 10, 19, 8)
+    t = torch.nn.Parameter(table.to(DEV).clone())
+    common = (res.to(DEV), bmin.to(DEV), bsize.to(DEV))
+    w = torch.randn(16, z_fg.numel(), 2, generator=torch.Generator().manual_seed(3)).to(DEV)
+    pts = (torch.rand(512, 3, generator=torch.Generator().manual_seed(4)) * 4 - 2).to(DEV)
+    w2 = torch.randn(512, 16, 2, generator=torch.Generator().manual_seed(5)).to(DEV)
+    got = {}
+    for share in (True, False):
+        _gradmode.share_enabled = share
+        try:
+            t.grad = None
+            for _ in range(2):           # second pass: accumulates onto .grad like any autograd gradient
+                loss = (_field.field_encode(o.to(DEV), d.to(DEV), z_fg.to(DEV), t, *common, 1) * w).sum() \
+                    + (_field.field_encode(o.to(DEV), d.to(DEV), z_bg.to(DEV), t, *common, 2) * w).sum() \
+                    + (_embedding._EncodeFn.apply(pts, t, None, None, res.to(DEV), False) * w2).sum()
+                loss.backward()
+            got[share] = t.grad.detach().clone()
+        finally:
+            _gradmode.share_enabled = True
+    assert float(got[False].abs().max()) > 0
+    assert torch.allclose(got[True], got[False], rtol=1e-5, atol=1e-6)
+
+
 def test_hashgrid_fused_and_unfused_render_agree():
     """HashGrid.render_batch_rays with and without the fused encode gives the same composited colours and gradients."""
     load_pkg()
