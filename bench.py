@@ -396,6 +396,32 @@ def bench_reference_cuda(cfg, dev, steps=10, warm=3):
                     "reference's torch graph (torch MLP / compositing / pose chain, dense torch Adam over the table), same workload",
             "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": "rays/s", "steps": steps, "warmup": warm, "loss": loss}
 
+def bench_reference_drivers(cfg, steps=12):
+    """What a user of the reference gets without touching their code: the reference's UNCHANGED tile.py (TILE.train_one_step,
+    tile.py:880-1015, from oracle/_ref/ref_drivers.zip) at the headline's size, once on this repo's drop-in packages and once on
+    the reference's own extensions (oracle/_ref/*.so), each in its own process (tests/ref_driver_harness.py).  Its step keeps
+    the driver's own torch code -- dense torch.optim.Adam over the whole table (tile.py:301), the torch pose chain and loss --
+    so it is slower than TileStep on either arm.  None when oracle/_ref is not there."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_drivers.zip")):
+        return None
+    out = {"what": "reference tile.py unchanged, TILE.train_one_step, 2^%d table, 2^14 rays x %d + %d samples, %d cameras; wall clock "
+                   "per step over %d steps after one warm-up step" % (cfg["log2T"], cfg["S"], cfg["S_bg"], cfg["n_cam"], steps - 1)}
+    tmp = tempfile.mkdtemp(prefix="snrf_drv_bench_")
+    for arm in ("dropin", "reference"):
+        res = os.path.join(tmp, arm + ".json")
+        cmd = [sys.executable, os.path.join(ROOT, "tests", "ref_driver_harness.py"), "--arm", arm, "--steps", str(steps),
+               "--log2T", str(cfg["log2T"]), "--bs-log2", "14", "--samples", str(cfg["S"]), "--cams", str(cfg["n_cam"]), "--out", res]
+        try:
+            subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=240, check=True)
+            r = json.load(open(res))
+            out[arm] = {"ms_per_step": r["ms_per_step"], "value": 2 ** 14 / (r["ms_per_step"] * 1e-3), "unit": "rays/s",
+                        "last_loss": r["losses"][-1], "hashgrid_module": r["modules"]["hashgrid"].replace(ROOT, ".")}
+        except Exception as e:                                  # evidence leg: never takes the headline down with it
+            out[arm] = {"error": repr(e)[:200]}
+    if "ms_per_step" in out.get("dropin", {}) and "ms_per_step" in out.get("reference", {}):
+        out["ratio"] = out["reference"]["ms_per_step"] / out["dropin"]["ms_per_step"]
+    return out
+
 # ----------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
@@ -667,6 +693,7 @@ def main():
             ref["ratio_value"] = line["value"] / ref["value"]
             ref["ratio_e2e"] = line["e2e"]["value"] / ref["value"]
         line["reference_cuda"] = ref
+        line["reference_drivers"] = bench_reference_drivers(cfg)
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         from oracle import native as on
