@@ -114,6 +114,11 @@ def _require_cuda(t, name):
         raise TypeError(f"{name} must be a torch.Tensor, got {type(t)}")
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor (scanerf_b200 has no CPU fallback)")
+    if t.device.index != torch.cuda.current_device():
+        # kernels are launched on the CURRENT device's current stream (one process per GPU, as the reference: cuda:0 of
+        # its CUDA_VISIBLE_DEVICES, admm_trainer.py:202); a tensor of another device would be dereferenced there
+        raise RuntimeError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                           "call torch.cuda.set_device(...) first")
 
 
 def inp(t, dtype, name):
