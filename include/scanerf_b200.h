@@ -122,6 +122,9 @@ void snrf_field_set_occupancy_smem(int bytes);
 /* tuning hook: 1 (default) = the scatter / Adam slices of snrf_field_encode_bwd_adam are launched with the programmatic-stream-
  * serialization attribute (a slice's CTAs are scheduled while the previous slice drains and wait in `griddepcontrol.wait`) */
 void snrf_field_set_pdl(int on);
+/* tuning hook (experiment, default 0 = off): MiB of hardware L2 set-aside for which the gradient scratch of
+ * snrf_field_encode_bwd_adam is a persisting access-policy window of its slice launches */
+void snrf_field_set_persist_mib(int mib);
 /* measurement hook: one forward launch per level, so that ncu reports L2 hit rate / DRAM bytes per level (default 0) */
 void snrf_field_set_fwd_split_levels(int on);
 /* tuning hook: samples per thread of the run-merging scatter kernel (2, 4 or 8; 0 selects the cross-lane kernel) */

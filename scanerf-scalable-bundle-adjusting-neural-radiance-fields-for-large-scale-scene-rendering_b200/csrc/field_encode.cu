@@ -761,6 +761,17 @@ adam_slice_kernel(float4* __restrict__ p4, float4* __restrict__ m4, float4* __re
 
 int g_occ_smem = 0;            // snrf_field_set_occupancy_smem: dynamic shared memory (unused) per CTA of the scatter / Adam slices
 int g_pdl = 1;                 // snrf_field_set_pdl: scatter / Adam slices of the fused backward as programmatic dependent launches
+// snrf_field_set_persist_mib (experiment, default 0 = off): the gradient scratch of the scatter + update fusion as a PERSISTING
+// access-policy window of the slice launches (hardware L2 set-aside, cudaLimitPersistingL2CacheSize) on top of / instead of
+// the per-instruction evict_last hints.
+// Measured on B200 at C2 and REJECTED (profiles/r5g_persist_sweep.json): the set-aside shrinks the L2 everything else lives in --
+// 48 / 64 / 72 MiB: step 8.87 -> 9.32 / 9.92 / 11.07 ms (encode forward 1.68 -> 1.80 / 2.08 / 2.55 ms, fused backward 4.15 -> 4.51 /
+// 4.76 / 5.42 ms) -- and the window itself buys nothing over the hints (same times with the limit set and the window off).
+int g_persist_mib = 0;
+int g_persist_reserved_mib[64] = {};
+size_t g_persist_max_window[64] = {}, g_persist_set_aside[64] = {};
+thread_local cudaAccessPolicyWindow t_window = {};
+thread_local bool t_window_on = false;
 template <typename... KArgs, typename... Args>
 inline void launch_dep(void (*kernel)(KArgs...), dim3 grid, cudaStream_t s, Args... args)
 {
@@ -769,13 +780,53 @@ inline void launch_dep(void (*kernel)(KArgs...), dim3 grid, cudaStream_t s, Args
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = (size_t)g_occ_smem;      // (> 0 only in occupancy experiments: caps the resident CTAs per SM)
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (g_pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (t_window_on) {
+        attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[n].val.accessPolicyWindow = t_window;
+        ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = g_pdl ? 1 : 0;
+    cfg.numAttrs = n;
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
+
+// Reserves the L2 set-aside once per device and describes `bytes` at `base` as the persisting window of the following launches.
+inline void persist_window_begin(void* base, size_t bytes)
+{
+    t_window_on = false;
+    if (g_persist_mib <= 0) return;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    int* reserved_mib = g_persist_reserved_mib;
+    size_t *max_window = g_persist_max_window, *set_aside = g_persist_set_aside;
+    if (reserved_mib[dev] != g_persist_mib) {
+        int max_persist = 0, max_win = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        size_t want = (size_t)g_persist_mib << 20;
+        if (want > (size_t)max_persist) want = (size_t)max_persist;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); return; }
+        reserved_mib[dev] = g_persist_mib;
+        set_aside[dev] = want;
+        max_window[dev] = (size_t)max_win;
+    }
+    if (set_aside[dev] == 0 || max_window[dev] == 0) return;
+    if (bytes > max_window[dev]) bytes = max_window[dev];
+    t_window.base_ptr = base;
+    t_window.num_bytes = bytes;
+    t_window.hitRatio = bytes <= set_aside[dev] ? 1.0f : (float)((double)set_aside[dev] / (double)bytes);
+    t_window.hitProp = cudaAccessPropertyPersisting;
+    t_window.missProp = cudaAccessPropertyStreaming;
+    t_window_on = true;
+}
+inline void persist_window_end() { t_window_on = false; }
 
 inline int grid_x(int N)
 {
@@ -852,6 +903,21 @@ SNRF_API void snrf_field_set_l2_hints(int on) { g_l2_hints = on ? 1 : 0; }
 SNRF_API void snrf_field_set_occupancy_smem(int bytes) { g_occ_smem = bytes > 0 ? (bytes > 48 * 1024 ? 48 * 1024 : bytes) : 0; }
 // tuning hook: 1 (default) = the scatter / Adam slices of snrf_field_encode_bwd_adam are programmatic dependent launches
 SNRF_API void snrf_field_set_pdl(int on) { g_pdl = on ? 1 : 0; }
+// tuning hook (experiment): > 0 = MiB of hardware L2 set-aside; the gradient scratch of snrf_field_encode_bwd_adam becomes a
+// persisting access-policy window of its slice launches.  0 (default) = off.
+SNRF_API void snrf_field_set_persist_mib(int mib)
+{
+    g_persist_mib = mib > 0 ? mib : 0;
+    int dev = 0;
+    if (g_persist_mib == 0 && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && g_persist_reserved_mib[dev] != 0) {
+        // give the set-aside back: it costs L2 capacity even while no window is active
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+        cudaCtxResetPersistingL2Cache();
+        cudaGetLastError();
+        g_persist_reserved_mib[dev] = 0;
+        g_persist_set_aside[dev] = 0;
+    }
+}
 SNRF_API void snrf_field_set_coarse_concurrent(int on) { g_coarse_concurrent = on ? 1 : 0; }
 SNRF_API void snrf_field_set_slice_log2(int bits) { g_slice_cap = 1ll << (bits < 2 ? 2 : (bits > 30 ? 30 : bits)); }
 SNRF_API void snrf_field_set_levels_per_group(int n) { g_levels_per_group = n > 0 ? n : 0; }
@@ -1088,6 +1154,7 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
         else launch_dep(adam_slice_kernel<false>, dim3((unsigned)gx), st, (float4*)(table + base), (float4*)(exp_avg + base), (float4*)(exp_avg_sq + base), (float4*)buf, n4, h);
     };
 
+    persist_window_begin(fine_buf, (size_t)fine_cap * 2 * sizeof(float));
     mark(-1);
     if (mode == 0)
         field_geom_raygrad_kernel<kNone><<<grid_x(N), kThreads, 0, s>>>(rays_o, rays_d, z_vals, points, box_min, box_size, g, j, grad_rays_o, grad_rays_d, grad_points, cpts_scratch, ray_valid, ray_split, N, S, L, t_sample_live);
@@ -1143,6 +1210,7 @@ SNRF_API int snrf_field_encode_bwd_adam(const float* rays_o, const float* rays_d
         if (k >= 2) cudaStreamWaitEvent(s, side->adam[1], 0);
     }
     if (coarse_on_side) cudaStreamWaitEvent(s, side->join, 0);
+    persist_window_end();
     g_last_launches = launches;
     if (prof) {
         if (concurrent) mark(3, true);                     // closing event on the caller's stream (after the joins)
